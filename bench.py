@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- candidate-circuit evals/sec (energy + adjoint gradient) of the QAS hot path.
+
+One "step" = one pass of the hot path over one batch of synthetic candidate circuits that
+share a parameter super-set: per circuit the energy E and dE/dtheta of its trainable angles,
+plus the batch-mean dense gradient (the reduction search() applies, qas/mcts/mcts.py:340-347).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lih_10q] [--batch B]
+    python bench.py --impl reference ...      # the CPU port of the reference path, all host cores
+
+Default workload: LiH sto-6g near_cx search (n=10, c=38, p=20; search-scripts-legacy/
+search_LiH_near_cx.py:64-116) -- the configuration BASELINE.json's metric and north_star target
+are quoted on ("energy + adjoint gradient at 1/2/4/8 GPUs", ">=1000x on the H2O/LiH searches").
+Multi-GPU: one process per GPU (torchrun), the batch is sharded by circuit (weak scaling: B per
+GPU fixed), rewards are all-gathered and the dense gradient all-reduced over NCCL.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+# ------------------------------------------------------------------------------- workloads
+def _line(n):
+    e = []
+    for i in range(n - 1):
+        e += [[i, i + 1], [i + 1, i]]
+    return e
+
+
+def _ring(n):
+    e = []
+    for i in range(n):
+        e += [[i, (i + 1) % n], [(i + 1) % n, i]]
+    return e
+
+
+# name -> (model class, n, p, coupling, CNOT limit, param scale, script batch sizes, source)
+WORKLOADS = {
+    "lih_10q": ("LiH", 10, 20, _line(10), 10, 1.0, (25, 500), "search_LiH_near_cx.py:64-116"),
+    "h2o_8q": ("H2O", 8, 50, _line(8), 25, 1.0, (50, 500), "search_H2O_near_cx.py:66-118"),
+    "h2_4q": ("FourQubitH2", 4, 40, _line(4), 40, 1.0, (100, 5000), "four_qubit_h2_only_near_cnot.py:43-97"),
+    "qaoa_7q": ("QAOAVQCDemo", 7, 15, _ring(7), 7, (2.0 / 2 ** 7) ** 0.5, (100, 100), "qaoa_search_demo.py:41-81"),
+    "h2_2q": ("TwoQubitH2", 2, 3, [[0, 1], [1, 0]], 2, 1.0, (50, 10), "two_qubit_h2.py:40-94"),
+}
+
+
+def make_workload(name, B, seed):
+    from qas_b200.qml_models import qml_models_legacy as L
+    from qas_b200.qml_models.qml_gate_ops import QMLPool
+    from qas_b200.sampling import sample_structure_lists
+    mname, n, p, coupling, cx_lim, scale, script_b, src = WORKLOADS[name]
+    model = getattr(L, mname)
+    pool = QMLPool(n, ["Rot", "PlaceHolder"], ["CNOT"], False, coupling)
+    c = len(pool)
+    params = np.random.default_rng(seed).standard_normal((p, c, 3)) * scale
+    ks = sample_structure_lists(pool, p, {"CNOT": cx_lim}, B, seed=seed)
+    return model, pool, params, ks
+
+
+def circuit_flops(ks, pool, n, S, T):
+    """Algorithmic flop of a batch.  N1 = non-PlaceHolder one-qubit gates per circuit.
+    executed-minimum model: 2^n (58 N1 + 4 S + 4)
+    SURVEY.md 8(d) formula:            2^n (122 N1 + 2 (8 G + 2 T))"""
+    is_1q = np.array([1 if ("Rot" in pool[k]) else 0 for k in range(len(pool))])
+    n1 = is_1q[ks].sum(axis=1).astype(np.float64)
+    dim = float(2 ** n)
+    return float(np.sum(dim * (58.0 * n1 + 4.0 * S + 4.0))), float(np.sum(dim * (122.0 * n1 + 2.0 * (8.0 * S + 2.0 * T))))
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- CPU arms
+def _cpu_worker(args):
+    name, lo, hi, seed, B = args
+    from oracle.refpattern import REF_METHOD, RefPatternEvaluator
+    model, pool, params, ks = make_workload(name, B, seed)
+    method, sparse = REF_METHOD[model.__name__]
+    ev = RefPatternEvaluator(WORKLOADS[name][1], pool.pool, model.terms(), model.init_state, method, sparse)
+    t0 = time.perf_counter()
+    acc = 0.0
+    for b in range(lo, hi):
+        e, g = ev.evaluate_one(ks[b], params)
+        acc += e + float(g.sum())
+    return time.perf_counter() - t0, acc
+
+
+def cpu_port_throughput(name, nsample, cores, seed):
+    """evals/s of the reference-pattern oracle on `cores` host processes over nsample circuits."""
+    import multiprocessing as mp
+    per = max(1, nsample // cores)
+    jobs = [(name, i * per, (i + 1) * per, seed, per * cores) for i in range(cores)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        _cpu_worker(jobs[0])
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_worker, jobs)
+    dt = time.perf_counter() - t0
+    return per * cores / dt, per * cores, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port, reference call pattern) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    name = args.workload
+    mname, n, p = WORKLOADS[name][:3]
+    # bounded sample per step, sized from a 1-circuit probe so the whole run stays within minutes
+    t_probe, _ = _cpu_worker((name, 0, 1, args.seed, 8))
+    per_step = max(cores, int(min(4096, max(1, 6.0 / max(t_probe, 1e-4)) * cores)) // cores * cores)
+    for _ in range(args.warmup):
+        cpu_port_throughput(name, cores, cores, args.seed)
+    tot_n, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        v, nn, dt = cpu_port_throughput(name, per_step, cores, args.seed)
+        tot_n += nn
+        tot_t += dt
+    value = tot_n / tot_t
+    from oracle.refpattern import REF_METHOD
+    line = {
+        "impl": "reference", "metric": "candidate-circuit evals/sec (energy+adjoint grad)", "value": value,
+        "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "model": mname, "n_qubits": n, "depth_p": p,
+                   "circuits_per_step": per_step, "gradient_method": REF_METHOD[mname][0]},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": "%d circuits/step x %d steps of the %s batch, oracle in the reference call pattern "
+                                   "(new model per eval, per-gate tensordot, %s gradient)" % (per_step, args.steps, name, REF_METHOD[mname][0])},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        dist.barrier()
+    if rank != 0:
+        ge.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    from qas_b200.evaluator import fp64_peak_tflops
+
+    name = args.workload
+    mname, n, p = WORKLOADS[name][:3]
+    B = args.batch
+    model, pool, params, ks = make_workload(name, B, args.seed + 1000 * rank)   # each rank its own shard
+    c = len(pool)
+    ev = model.evaluator(pool, 3, local)
+    T = len(model.terms())
+
+    d_k = torch.from_numpy(ks).to(dev)
+    d_params = torch.from_numpy(params).to(dev)
+    d_energy = torch.empty(B, dtype=torch.float64, device=dev)
+    d_gc = torch.empty(B, p, 3, dtype=torch.float64, device=dev)
+    d_gd = torch.empty(p, c, 3, dtype=torch.float64, device=dev)
+    d_all_e = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step():
+        ev.evaluate_device(d_k, d_params, d_energy, d_gc, d_gd, avg=(world == 1), stream=stream)
+        if world > 1:   # the exchange step: rewards gathered, gradient summed then / (B*world)
+            dist.all_gather_into_tensor(d_all_e, d_energy)
+            dist.all_reduce(d_gd)
+            d_gd.mul_(1.0 / (B * world))
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    launches0 = ev.stats()["launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    eval_ms = []
+    for i in range(args.steps):
+        flush.zero_()                     # L2 flush between timed iterations (outside the event pair)
+        e0[i].record(stream)
+        step()
+        e1[i].record(stream)
+        e1[i].synchronize()
+        eval_ms.append(ev.stats()["last_eval_kernel_ms"])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    step_ms = [a.elapsed_time(b) for a, b in zip(e0, e1)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ev.stats()["launches"] - launches0        # this library's kernels only
+    total_s = float(total_ms.item()) * 1e-3
+    value = world * B * args.steps / total_s
+
+    # ---- end to end through the public host API: pinned host buffers in, host results out
+    h_k = torch.from_numpy(ks).pin_memory()
+    h_params = torch.from_numpy(params).pin_memory()
+    hk_np, hp_np = h_k.numpy(), h_params.numpy()
+    for _ in range(2):
+        model.evaluate_batch(hk_np, hp_np, pool, want_grad=True)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = model.evaluate_batch(hk_np, hp_np, pool, want_grad=True)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(e2e_s.item())
+    h2d = ks.nbytes + params.nbytes
+    d2h = out["energy"].nbytes + out["grad_dense"].nbytes
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the evaluation kernel), FP64 pipe
+    S = None
+    try:
+        import ctypes  # noqa: F401
+        S = len({(w.replace("Y", "X").replace("Z", "I")) for _, w in model.terms()})
+    except Exception:
+        pass
+    f_exec, f_survey = circuit_flops(ks, pool, n, S, T)
+    k_ms = statistics.mean(eval_ms)
+    peak = fp64_peak_tflops(local, 5)
+    achieved = f_exec / (k_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "eval_kernel<%d>" % n, "kernel_ms": k_ms,
+                "kernel_share_of_step": k_ms * args.steps / sum(step_ms),
+                "achieved_survey_8d_formula": f_survey / (k_ms * 1e-3) / 1e12,
+                "peak_source": "measured live: qas_fp64_peak_tflops DFMA micro-benchmark (MEASURED_PEAKS.json has no FP64 entry)",
+                "flop_model": "2^n(58 N1 + 4 S + 4) executed-minimum; survey formula 2^n(122 N1 + 2(8G+2T)) alongside"}
+
+    # ---- CPU baseline: reference-pattern oracle on a bounded sample, 1 core (how the reference runs)
+    t_probe, _ = _cpu_worker((name, 0, 1, args.seed, 8))
+    ns = int(max(2, min(64, 12.0 / max(t_probe, 1e-3))))
+    cpu_v, cpu_n, cpu_t = cpu_port_throughput(name, ns, 1, args.seed)
+    from oracle.refpattern import REF_METHOD
+    cpu_baseline = {"value": cpu_v, "unit": "evals/s", "cores": 1, "kind": "port",
+                    "sample": "%d circuits of the %s batch (%.1f s), oracle in the reference call pattern, %s gradient"
+                              % (cpu_n, name, cpu_t, REF_METHOD[mname][0])}
+
+    line = {
+        "metric": "candidate-circuit evals/sec (energy+adjoint grad)", "value": value, "unit": "evals/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "model": mname, "n_qubits": n, "depth_p": p, "pool_c": c,
+                   "circuits_per_gpu_per_step": B, "pauli_terms": T, "xmask_groups": S,
+                   "source": "search-scripts-legacy/" + WORKLOADS[name][7], "l2_flush_between_steps": True,
+                   "parallelism": "circuits sharded over %d GPU(s); all_gather rewards + all_reduce gradient" % world},
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="lih_10q", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=65536, help="circuits per GPU per step")
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,151 @@
+/* qas_b200.h -- C ABI of libqas_b200.so: B200-native batched evaluator for the QAS hot path.
+ *
+ * The reference (peiyong-addwater/QAS) has no native code and no FFI: its hot path is the
+ * Python call chain  MCTSController.simulationWithSuperCircuitParamsAndK (qas/mcts/mcts.py:100-105)
+ * -> model(p,c,l,k,pool).getReward / getGradient / getLoss (qas/models.py:3-21,
+ * qas/qml_models/hamiltonian_model.py:55-91) -> PennyLane QNode.  Each entry point below
+ * names the reference interface it replaces.  All functions return an int status
+ * (QAS_OK == 0); no exception crosses this boundary; pointers are caller-owned and never
+ * retained past the call.
+ *
+ * Bit convention: wire w of an n-qubit register is bit (n-1-w) of a basis index / mask
+ * (wire 0 = most significant bit, as in PennyLane).
+ */
+#ifndef QAS_B200_H
+#define QAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QAS_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define QAS_OK 0
+#define QAS_ERR_INVALID 1     /* bad argument (the reference's bare asserts: utils.py:12-15,    */
+                              /* hamiltonian_model.py:56-58)                                     */
+#define QAS_ERR_CUDA 2        /* CUDA runtime error; see qas_last_error                          */
+#define QAS_ERR_UNSUPPORTED 3 /* configuration outside what the kernels cover                    */
+#define QAS_ERR_NOMEM 4
+
+/* ---- gate ids: the gate-name set of qas/qml_models/qml_gate_ops.py:66-105 -------------- */
+enum qas_gate_id {
+  QAS_G_PLACEHOLDER = 0,
+  QAS_G_HADAMARD, QAS_G_PAULIX, QAS_G_PAULIY, QAS_G_PAULIZ, QAS_G_S, QAS_G_SDG, QAS_G_T,
+  QAS_G_TDG, QAS_G_SX,
+  QAS_G_ROT, QAS_G_RX, QAS_G_RY, QAS_G_RZ, QAS_G_PHASESHIFT, QAS_G_U1, QAS_G_U2, QAS_G_U3,
+  QAS_G_CNOT, QAS_G_CZ, QAS_G_CY, QAS_G_SWAP, QAS_G_ISWAP, QAS_G_SISWAP,
+  QAS_G_CRX, QAS_G_CRY, QAS_G_CRZ, QAS_G_CROT, QAS_G_CPHASE,
+  QAS_G_ISINGXX, QAS_G_ISINGYY, QAS_G_ISINGZZ,
+  QAS_G_COUNT
+};
+
+/* One operator-pool entry: key -> {gate: wires}  (QMLPool, qml_gate_ops.py:136-185).
+ * wire1 = -1 for one-wire gates; for controlled gates wire0 = control, wire1 = target.    */
+typedef struct {
+  int32_t gate_id;
+  int32_t wire0;
+  int32_t wire1;
+} qas_pool_entry;
+
+/* One Pauli term  coeff * P,  P = tensor product with X where xmask&~zmask, Z where
+ * zmask&~xmask, Y where xmask&zmask  (replaces the qml.Hamiltonian objects at
+ * qml_models_legacy.py:1237-1256, kagome_heisenberg_model.py:41-52, the per-edge
+ * Hermitian(ZZ) of :2377-2393).                                                            */
+typedef struct {
+  uint64_t xmask;
+  uint64_t zmask;
+  double coeff;
+} qas_pauli_term;
+
+/* initial state of the register (qml.BasisState(hf) at qml_models_legacy.py:1298, the
+ * Hadamard layer at :2380-2381, or nothing = |0..0>)                                       */
+#define QAS_INIT_ZERO 0
+#define QAS_INIT_BASIS 1
+#define QAS_INIT_PLUS 2
+
+/* flags of qas_eval_batch */
+#define QAS_F_DEVICE_PTRS 0x1u /* k, params, energy, grad_* are device pointers; the call is    */
+                               /* asynchronous on `stream`. Otherwise host pointers: the call    */
+                               /* stages them through pinned memory and returns synchronously.   */
+#define QAS_F_GRAD_SUM 0x2u    /* grad_dense = sum over the batch instead of mean                */
+                               /* (search(..., avg_gradients=False), mcts.py:347)                */
+
+typedef struct qas_ctx qas_ctx;
+
+/* Library / build info. */
+int qas_abi_version(void);
+const char *qas_build_info(void);
+
+/* Create an evaluator for one model family: n qubits, an initial state, a Pauli-sum
+ * Hamiltonian and an operator pool.  Replaces the per-evaluation construction of
+ * model + qml.device + QNode (mcts.py:103, qml_models_legacy.py:1269,1295-1301).
+ * l = number of parameter slots per (depth, key) (3 everywhere in the reference).          */
+int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_kind, uint64_t init_basis,
+                   const qas_pauli_term *terms, int num_terms,
+                   const qas_pool_entry *pool, int c, int l);
+int qas_ctx_destroy(qas_ctx *ctx);
+
+/* Human-readable description of the last error on this context (or of a failed create
+ * when ctx == NULL).  The string stays valid until the next call on the same context.      */
+const char *qas_last_error(const qas_ctx *ctx);
+
+/* Evaluate a batch of B candidate circuits that share one parameter super-set.
+ *   k        int32  [B][p]     structure lists (pool keys), row-major
+ *   params   double [p][c][l]  shared parameter super-set (read-only)
+ *   energy   double [B]        out: E_b = <psi_b|H|psi_b>  (getLoss; getReward = -E)
+ *   grad_compact double [B][p][l] or NULL
+ *                              out: dE_b/dparams[i][k_b[i]][j]; zero where gate k_b[i] has
+ *                              fewer than j+1 parameters (getGradient's non-zero entries,
+ *                              hamiltonian_model.py:75-91)
+ *   grad_dense   double [p][c][l] or NULL
+ *                              out: mean (or sum) over the batch of the dense gradients after
+ *                              nan_to_num -- the reduction at mcts.py:345-347
+ * Replaces the serial loops mcts.py:298-305 (rewards) and :340-347 (gradients).            */
+int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, const double *params,
+                   double *energy, double *grad_compact, double *grad_dense, uint32_t flags,
+                   void *stream);
+
+/* Host-side run of the tape compiler on ONE structure list (no GPU needed): lowers k to the
+ * generalised-gate tape the kernels execute (CNOT/SWAP folded into the index frame).
+ * out_ops receives up to max_ops records of 5 uint32 {xor_mask, target_parity_mask,
+ * control_parity_mask, table_index, meta}; *num_ops the count; *init_index the physical
+ * basis index of the initial state when init_kind == QAS_INIT_BASIS.
+ * Restates backboneCirc (hamiltonian_model.py:22-41).                                      */
+int qas_compile_tape(const qas_ctx *ctx, int p, const int32_t *k, uint32_t *out_ops, int max_ops,
+                     int *num_ops, uint32_t *init_index);
+
+/* Same, but usable without a context/GPU (pool passed directly).                            */
+int qas_compile_tape_host(int n_qubits, const qas_pool_entry *pool, int c, int p,
+                          const int32_t *k, uint64_t init_basis, uint32_t *out_ops, int max_ops,
+                          int *num_ops, uint32_t *init_index);
+
+/* Counters since context creation: evaluations and kernel launches; device time of the
+ * last call's kernels (ms, CUDA events on the launch stream; host-pointer calls only) and of
+ * the last evaluation kernel alone (any call; qas_get_stats waits for that kernel).         */
+typedef struct {
+  uint64_t evals;
+  uint64_t launches;
+  double last_kernel_ms;
+  double last_eval_kernel_ms;
+  int teams_per_cta;
+  int threads_per_team;
+  int ctas_per_sm;
+  int smem_bytes_per_cta;
+  int path;                 /* 0 = shared-memory resident, 1 = global-memory resident */
+} qas_stats;
+int qas_get_stats(const qas_ctx *ctx, qas_stats *out);
+
+/* Measured FP64 roofline denominator: runs a dependent-chain-free DFMA micro-benchmark on
+ * `device` and returns the best of `reps` timings in TFLOP/s (2 flop per DFMA).            */
+int qas_fp64_peak_tflops(int device, int reps, double *tflops);
+
+/* ---- large-state mode (one statevector resident in HBM, optionally sharded) ---------- */
+/* see DESIGN.md section "Large-state mode"; declared in qas_b200_sv.h                       */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QAS_B200_H */

@@ -1,0 +1,468 @@
+// api.cu -- host side of libqas_b200.so: context, launch logic and the extern "C" ABI declared
+// in include/qas_b200.h.  No torch types, no exceptions across the boundary.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+static thread_local std::string g_create_error;
+
+struct qas_ctx {
+  int device = 0, n = 0, init_kind = 0, c = 0, l = 0, num_sms = 0;
+  uint64_t init_basis = 0;
+  std::vector<qas_pool_entry> pool;
+  int max_expansion = 1;
+  int S = 0;                       // number of sign-table slices
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ek0 = nullptr, ek1 = nullptr;
+  bool ek_pending = false;
+  // device buffers owned by the context
+  qas_pool_entry *d_pool = nullptr;
+  double *d_vtab = nullptr;
+  uint32_t *d_sx = nullptr, *d_simag = nullptr;
+  GateTab *d_U = nullptr;
+  GateDTab *d_dU = nullptr;
+  int tab_p = 0;
+  int32_t *d_k = nullptr;  size_t cap_k = 0;
+  double *d_params = nullptr; size_t cap_params = 0;
+  double *d_energy = nullptr; size_t cap_energy = 0;
+  double *d_grad = nullptr; size_t cap_grad = 0;
+  double *d_partial = nullptr; size_t cap_partial = 0;
+  double *d_dense = nullptr; size_t cap_dense = 0;
+  double2 *d_gstate = nullptr; size_t cap_gstate = 0;
+  qas_stats stats{};
+  mutable std::string err;
+};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      char buf_[512];                                                                         \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),     \
+               __FILE__, __LINE__);                                                           \
+      if (ctx) ctx->err = buf_; else g_create_error = buf_;                                   \
+      return QAS_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+static int fail(const qas_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return code;
+}
+
+template <typename Tp>
+static cudaError_t ensure(Tp **ptr, size_t *cap, size_t need_elems) {
+  if (*cap >= need_elems && *ptr) return cudaSuccess;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *cap = 0;
+  size_t want = std::max<size_t>(need_elems, 16);
+  cudaError_t e = cudaMalloc((void **)ptr, want * sizeof(Tp));
+  if (e == cudaSuccess) *cap = want;
+  return e;
+}
+
+// ---------------------------------------------------------------------------------- info
+extern "C" int qas_abi_version(void) { return QAS_ABI_VERSION; }
+extern "C" const char *qas_build_info(void) {
+  return "qas_b200 sm_100a; smem-resident complex128 statevector, CNOT-folded tapes, "
+         "X-mask sign tables, 2x2 cross-matrix adjoint; built " __DATE__;
+}
+extern "C" const char *qas_last_error(const qas_ctx *ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+// ---------------------------------------------------------------------------------- pool checks
+static int validate_pool(const qas_pool_entry *pool, int c, int n, int l, std::string &why,
+                         int *max_exp) {
+  *max_exp = 1;
+  for (int i = 0; i < c; ++i) {
+    const int g = pool[i].gate_id;
+    if (g < 0 || g >= QAS_G_COUNT) { why = "pool entry " + std::to_string(i) + ": unknown gate id"; return 1; }
+    const int nw = qas_gate_nwires(g);
+    if (pool[i].wire0 < 0 || pool[i].wire0 >= n) { why = "pool entry " + std::to_string(i) + ": wire0 out of range"; return 1; }
+    if (nw == 2 && (pool[i].wire1 < 0 || pool[i].wire1 >= n || pool[i].wire1 == pool[i].wire0)) {
+      why = "pool entry " + std::to_string(i) + ": wire1 invalid"; return 1;
+    }
+    if (qas_gate_nparams(g) > l) { why = "pool entry " + std::to_string(i) + ": gate needs more parameter slots than l"; return 1; }
+    *max_exp = std::max(*max_exp, qas_gate_expansion(g));
+  }
+  return 0;
+}
+
+static void fill_const_table(std::vector<GateTab> &t) {
+  auto set = [&](int id, double2 a, double2 b, double2 c_, double2 d) {
+    t[id].u[0] = a; t[id].u[1] = b; t[id].u[2] = c_; t[id].u[3] = d;
+  };
+  const double r = 0.70710678118654752440;
+  const double2 Z0 = make_double2(0, 0), ONE = make_double2(1, 0), I = make_double2(0, 1),
+                MI = make_double2(0, -1), MONE = make_double2(-1, 0);
+  set(QAS_C_H, make_double2(r, 0), make_double2(r, 0), make_double2(r, 0), make_double2(-r, 0));
+  set(QAS_C_X, Z0, ONE, ONE, Z0);
+  set(QAS_C_Y, Z0, MI, I, Z0);
+  set(QAS_C_Z, ONE, Z0, Z0, MONE);
+  set(QAS_C_S, ONE, Z0, Z0, I);
+  set(QAS_C_SDG, ONE, Z0, Z0, MI);
+  set(QAS_C_T, ONE, Z0, Z0, make_double2(r, r));
+  set(QAS_C_TDG, ONE, Z0, Z0, make_double2(r, -r));
+  set(QAS_C_SX, make_double2(0.5, 0.5), make_double2(0.5, -0.5), make_double2(0.5, -0.5), make_double2(0.5, 0.5));
+  // S*H = [[r, r], [i r, -i r]] ;  H*S^dagger = [[r, -i r], [r, i r]]
+  set(QAS_C_SH, make_double2(r, 0), make_double2(r, 0), make_double2(0, r), make_double2(0, -r));
+  set(QAS_C_HSDG, make_double2(r, 0), make_double2(0, -r), make_double2(r, 0), make_double2(0, r));
+  // parity-diagonal core of exp(+i pi/8 PP) = Ising(-pi/4): diag(e^{+i pi/8}, e^{-i pi/8})
+  const double cs = std::cos(M_PI / 8), sn = std::sin(M_PI / 8);
+  set(QAS_C_ZZ_MPI4, make_double2(cs, sn), Z0, Z0, make_double2(cs, -sn));
+}
+
+// ---------------------------------------------------------------------------------- create
+extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_kind,
+                              uint64_t init_basis, const qas_pauli_term *terms, int num_terms,
+                              const qas_pool_entry *pool, int c, int l) {
+  qas_ctx *ctx = nullptr;
+  if (!out) return fail(nullptr, QAS_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (n_qubits < 2 || n_qubits > 20)
+    return fail(nullptr, QAS_ERR_UNSUPPORTED, "batched evaluator supports 2..20 qubits (use the large-state API above that)");
+  if (init_kind < 0 || init_kind > 2) return fail(nullptr, QAS_ERR_INVALID, "bad init_kind");
+  if (init_kind == QAS_INIT_BASIS && (init_basis >> n_qubits)) return fail(nullptr, QAS_ERR_INVALID, "init_basis out of range");
+  if (!terms || num_terms <= 0 || !pool || c <= 0 || l <= 0) return fail(nullptr, QAS_ERR_INVALID, "empty Hamiltonian or pool");
+  std::string why;
+  int max_exp = 1;
+  if (validate_pool(pool, c, n_qubits, l, why, &max_exp)) return fail(nullptr, QAS_ERR_INVALID, why);
+  const uint64_t full = (1ull << n_qubits) - 1;
+  for (int t = 0; t < num_terms; ++t)
+    if ((terms[t].xmask | terms[t].zmask) & ~full) return fail(nullptr, QAS_ERR_INVALID, "Pauli term acts outside the register");
+
+  cudaError_t e0 = cudaSetDevice(device);
+  if (e0 != cudaSuccess) return fail(nullptr, QAS_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e0));
+
+  qas_ctx *cx = new qas_ctx();
+  ctx = cx;
+  cx->device = device; cx->n = n_qubits; cx->init_kind = init_kind; cx->init_basis = init_basis;
+  cx->c = c; cx->l = l; cx->max_expansion = max_exp;
+  cx->pool.assign(pool, pool + c);
+
+  // group the Hamiltonian by X mask: slice key = (xmask, is_imag); term sign from i^{nY}
+  std::map<std::pair<uint64_t, int>, std::vector<std::pair<uint32_t, double>>> slices;
+  for (int t = 0; t < num_terms; ++t) {
+    const int ny = __builtin_popcountll(terms[t].xmask & terms[t].zmask);
+    const double sgn = (ny & 2) ? -1.0 : 1.0;
+    slices[{terms[t].xmask, ny & 1}].push_back({(uint32_t)terms[t].zmask, sgn * terms[t].coeff});
+  }
+  std::vector<uint32_t> sx, simag, tz;
+  std::vector<int> sbegin;
+  std::vector<double> tc;
+  for (auto &kv : slices) {
+    sx.push_back((uint32_t)kv.first.first);
+    simag.push_back((uint32_t)kv.first.second);
+    sbegin.push_back((int)tz.size());
+    for (auto &zc : kv.second) { tz.push_back(zc.first); tc.push_back(zc.second); }
+  }
+  sbegin.push_back((int)tz.size());
+  cx->S = (int)sx.size();
+  const size_t dim = (size_t)1 << n_qubits;
+  if ((double)cx->S * (double)dim * 8.0 > 4.0e9) {
+    delete cx;
+    return fail(nullptr, QAS_ERR_UNSUPPORTED, "sign tables would exceed 4 GB; use the large-state API");
+  }
+
+  int rc = QAS_OK;
+  auto guard = [&](cudaError_t e, const char *what) {
+    if (e != cudaSuccess && rc == QAS_OK) {
+      g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+      rc = QAS_ERR_CUDA;
+    }
+  };
+  cudaDeviceProp prop;
+  guard(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+  cx->num_sms = prop.multiProcessorCount;
+  guard(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  guard(cudaEventCreate(&cx->ev0), "cudaEventCreate");
+  guard(cudaEventCreate(&cx->ev1), "cudaEventCreate");
+  guard(cudaEventCreate(&cx->ek0), "cudaEventCreate");
+  guard(cudaEventCreate(&cx->ek1), "cudaEventCreate");
+  guard(cudaMalloc(&cx->d_pool, sizeof(qas_pool_entry) * c), "cudaMalloc pool");
+  guard(cudaMalloc(&cx->d_vtab, sizeof(double) * dim * cx->S), "cudaMalloc sign tables");
+  guard(cudaMalloc(&cx->d_sx, 4 * cx->S), "cudaMalloc sx");
+  guard(cudaMalloc(&cx->d_simag, 4 * cx->S), "cudaMalloc simag");
+  uint32_t *d_tz = nullptr; double *d_tc = nullptr; int *d_sbegin = nullptr;
+  guard(cudaMalloc(&d_tz, 4 * tz.size()), "cudaMalloc tz");
+  guard(cudaMalloc(&d_tc, 8 * tc.size()), "cudaMalloc tc");
+  guard(cudaMalloc(&d_sbegin, 4 * sbegin.size()), "cudaMalloc sbegin");
+  if (rc == QAS_OK) {
+    guard(cudaMemcpy(cx->d_pool, pool, sizeof(qas_pool_entry) * c, cudaMemcpyHostToDevice), "copy pool");
+    guard(cudaMemcpy(cx->d_sx, sx.data(), 4 * sx.size(), cudaMemcpyHostToDevice), "copy sx");
+    guard(cudaMemcpy(cx->d_simag, simag.data(), 4 * simag.size(), cudaMemcpyHostToDevice), "copy simag");
+    guard(cudaMemcpy(d_tz, tz.data(), 4 * tz.size(), cudaMemcpyHostToDevice), "copy tz");
+    guard(cudaMemcpy(d_tc, tc.data(), 8 * tc.size(), cudaMemcpyHostToDevice), "copy tc");
+    guard(cudaMemcpy(d_sbegin, sbegin.data(), 4 * sbegin.size(), cudaMemcpyHostToDevice), "copy sbegin");
+    const size_t total = dim * cx->S;
+    build_sign_tables_kernel<<<(unsigned)((total + 255) / 256), 256, 0, cx->stream>>>(
+        n_qubits, cx->S, cx->d_sx, d_sbegin, d_tz, d_tc, cx->d_vtab);
+    guard(cudaGetLastError(), "build_sign_tables launch");
+    guard(cudaStreamSynchronize(cx->stream), "build_sign_tables");
+  }
+  cudaFree(d_tz); cudaFree(d_tc); cudaFree(d_sbegin);
+  if (rc != QAS_OK) { qas_ctx_destroy(cx); return rc; }
+  *out = cx;
+  return QAS_OK;
+}
+
+extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
+  if (!ctx) return QAS_OK;
+  cudaSetDevice(ctx->device);
+  cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sx); cudaFree(ctx->d_simag);
+  cudaFree(ctx->d_U); cudaFree(ctx->d_dU); cudaFree(ctx->d_k); cudaFree(ctx->d_params);
+  cudaFree(ctx->d_energy); cudaFree(ctx->d_grad); cudaFree(ctx->d_partial); cudaFree(ctx->d_dense);
+  cudaFree(ctx->d_gstate);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ek0) cudaEventDestroy(ctx->ek0);
+  if (ctx->ek1) cudaEventDestroy(ctx->ek1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return QAS_OK;
+}
+
+extern "C" int qas_get_stats(const qas_ctx *cctx, qas_stats *out) {
+  if (!cctx || !out) return QAS_ERR_INVALID;
+  qas_ctx *ctx = const_cast<qas_ctx *>(cctx);
+  if (ctx->ek_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->ek1) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, ctx->ek0, ctx->ek1) == cudaSuccess)
+      ctx->stats.last_eval_kernel_ms = ms;
+    ctx->ek_pending = false;
+  }
+  *out = ctx->stats;
+  return QAS_OK;
+}
+
+// ---------------------------------------------------------------------------------- launch
+constexpr int team_threads(int n) {
+  return n <= 4 ? 8 : n == 5 ? 16 : n <= 8 ? 32 : n == 9 ? 64 : n == 10 ? 128 : 256;
+}
+
+template <int N, bool GRAD>
+static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t st) {
+  constexpr int T = team_threads(N);
+  constexpr int TEAMS = 256 / T;
+  const size_t smem = eval_team_smem_bytes(N, T, GRAD, P.ops_cap, true) * TEAMS;
+  auto kern = eval_kernel<N, T, GRAD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
+  const int grid = (P.B + TEAMS - 1) / TEAMS;
+  ctx->stats.teams_per_cta = TEAMS;
+  ctx->stats.threads_per_team = T;
+  ctx->stats.ctas_per_sm = occ;
+  ctx->stats.smem_bytes_per_cta = (int)smem;
+  ctx->stats.path = 0;
+  kern<<<grid, 256, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+template <bool GRAD>
+static cudaError_t launch_gmem(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
+  const size_t smem = eval_team_smem_bytes(P.n, 256, GRAD, P.ops_cap, false);
+  auto kern = eval_kernel<0, 256, GRAD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
+  occ = std::max(1, std::min(occ, 4));
+  const size_t per_cta = ((size_t)1 << P.n) * (GRAD ? 2 : 1);
+  int grid = std::min(P.B, ctx->num_sms * occ);
+  while (grid > 1 && per_cta * grid * 16 > ((size_t)8 << 30)) grid /= 2;
+  e = ensure(&ctx->d_gstate, &ctx->cap_gstate, per_cta * grid);
+  if (e != cudaSuccess) return e;
+  P.gstate = ctx->d_gstate;
+  ctx->stats.teams_per_cta = 1;
+  ctx->stats.threads_per_team = 256;
+  ctx->stats.ctas_per_sm = occ;
+  ctx->stats.smem_bytes_per_cta = (int)smem;
+  ctx->stats.path = 1;
+  kern<<<grid, 256, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+template <bool GRAD>
+static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
+  const int nmax_smem = GRAD ? 12 : 13;
+  if (P.n <= nmax_smem) {
+    // the tape must also fit next to the state; fall back to the global-memory path if not
+    const int T = team_threads(P.n);
+    const size_t smem = eval_team_smem_bytes(P.n, T, GRAD, P.ops_cap, true) * (256 / T);
+    if (smem <= 227 * 1024) {
+      switch (P.n) {
+#define QAS_CASE(N_) case N_: return launch_smem<N_, GRAD>(ctx, P, st);
+        QAS_CASE(2) QAS_CASE(3) QAS_CASE(4) QAS_CASE(5) QAS_CASE(6) QAS_CASE(7) QAS_CASE(8)
+        QAS_CASE(9) QAS_CASE(10) QAS_CASE(11) QAS_CASE(12)
+#undef QAS_CASE
+        case 13: if constexpr (!GRAD) return launch_smem<13, false>(ctx, P, st); break;
+        default: break;
+      }
+    }
+  }
+  return launch_gmem<GRAD>(ctx, P, st);
+}
+
+extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, const double *params,
+                              double *energy, double *grad_compact, double *grad_dense,
+                              uint32_t flags, void *stream) {
+  if (!ctx) return QAS_ERR_INVALID;
+  if (B <= 0 || p <= 0 || p > 65535 || !k || !params || !energy) return fail(ctx, QAS_ERR_INVALID, "bad arguments to qas_eval_batch");
+  const bool dev = flags & QAS_F_DEVICE_PTRS;
+  const bool want_grad = grad_compact || grad_dense;
+  const int c = ctx->c, l = ctx->l;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const size_t nk = (size_t)B * p, npar = (size_t)p * c * l, ng = (size_t)B * p * l;
+
+  if (!dev) {   // the reference's asserts on k (utils.py:12-15)
+    for (size_t i = 0; i < nk; ++i)
+      if (k[i] < 0 || k[i] >= c) return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
+  }
+
+  // gate tables sized for this depth
+  if (ctx->tab_p < p) {
+    cudaFree(ctx->d_U); cudaFree(ctx->d_dU);
+    ctx->d_U = nullptr; ctx->d_dU = nullptr; ctx->tab_p = 0;
+    const size_t ne = (size_t)QAS_NCONST + (size_t)p * c;
+    CK(cudaMalloc(&ctx->d_U, ne * sizeof(GateTab)));
+    CK(cudaMalloc(&ctx->d_dU, ne * sizeof(GateDTab)));
+    CK(cudaMemsetAsync(ctx->d_dU, 0, ne * sizeof(GateDTab), st));
+    std::vector<GateTab> ct(QAS_NCONST);
+    fill_const_table(ct);
+    CK(cudaMemcpyAsync(ctx->d_U, ct.data(), sizeof(GateTab) * QAS_NCONST, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->tab_p = p;
+  }
+
+  const int32_t *dk = k;
+  const double *dparams = params;
+  double *denergy = energy, *dgrad = grad_compact, *ddense = grad_dense;
+  if (!dev) {
+    CK(ensure(&ctx->d_k, &ctx->cap_k, nk));
+    CK(ensure(&ctx->d_params, &ctx->cap_params, npar));
+    CK(ensure(&ctx->d_energy, &ctx->cap_energy, (size_t)B));
+    CK(cudaMemcpyAsync(ctx->d_k, k, nk * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_params, params, npar * 8, cudaMemcpyHostToDevice, st));
+    dk = ctx->d_k; dparams = ctx->d_params; denergy = ctx->d_energy;
+    dgrad = nullptr;
+    if (grad_dense) { CK(ensure(&ctx->d_dense, &ctx->cap_dense, npar)); ddense = ctx->d_dense; }
+  }
+  if (want_grad && (!dev || !grad_compact)) {
+    CK(ensure(&ctx->d_grad, &ctx->cap_grad, ng));
+    dgrad = ctx->d_grad;
+  }
+
+  EvalParams P{};
+  P.k = dk; P.pool = ctx->d_pool; P.U = ctx->d_U; P.dU = ctx->d_dU;
+  P.vtab = ctx->d_vtab; P.sx = ctx->d_sx; P.simag = ctx->d_simag;
+  P.energy = denergy; P.grad = dgrad; P.gstate = nullptr;
+  P.init_basis = ctx->init_basis;
+  P.B = B; P.p = p; P.c = c; P.l = l; P.n = ctx->n; P.S = ctx->S;
+  P.ops_cap = std::max(1, p * ctx->max_expansion);
+  P.init_kind = ctx->init_kind;
+
+  if (!dev) CK(cudaEventRecord(ctx->ev0, st));
+  build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ek0, st));
+  if (want_grad) CK(launch_eval<true>(ctx, P, st)); else CK(launch_eval<false>(ctx, P, st));
+  CK(cudaEventRecord(ctx->ek1, st));
+  ctx->ek_pending = true;
+  ctx->stats.launches += 2;
+
+  if (grad_dense) {
+    const int chunk = 128;
+    const int nchunks = (B + chunk - 1) / chunk;
+    int depth_tile = p;
+    while ((size_t)depth_tile * c * l * 8 > 96 * 1024 && depth_tile > 1) depth_tile = (depth_tile + 1) / 2;
+    const size_t sm = (size_t)depth_tile * c * l * 8;
+    CK(ensure(&ctx->d_partial, &ctx->cap_partial, (size_t)nchunks * npar));
+    CK(cudaFuncSetAttribute(grad_chunk_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dim3 grid(nchunks, (p + depth_tile - 1) / depth_tile);
+    grad_chunk_reduce_kernel<<<grid, 128, sm, st>>>(dk, dgrad, B, p, c, l, chunk, depth_tile, ctx->d_partial);
+    CK(cudaGetLastError());
+    const double scale = (flags & QAS_F_GRAD_SUM) ? 1.0 : 1.0 / (double)B;
+    grad_final_reduce_kernel<<<(unsigned)((npar + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, scale, ddense);
+    CK(cudaGetLastError());
+    ctx->stats.launches += 2;
+  }
+  ctx->stats.evals += (uint64_t)B;
+
+  if (!dev) {
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(energy, denergy, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if (grad_compact) CK(cudaMemcpyAsync(grad_compact, dgrad, ng * 8, cudaMemcpyDeviceToHost, st));
+    if (grad_dense) CK(cudaMemcpyAsync(grad_dense, ddense, npar * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
+  }
+  return QAS_OK;
+}
+
+// ---------------------------------------------------------------------------------- tape export
+extern "C" int qas_compile_tape_host(int n_qubits, const qas_pool_entry *pool, int c, int p,
+                                     const int32_t *k, uint64_t init_basis, uint32_t *out_ops,
+                                     int max_ops, int *num_ops, uint32_t *init_index) {
+  if (n_qubits < 1 || n_qubits > QAS_MAX_QUBITS || !pool || c <= 0 || p <= 0 || !k || !out_ops || !num_ops)
+    return QAS_ERR_INVALID;
+  std::string why;
+  int me = 1;
+  if (validate_pool(pool, c, n_qubits, 3, why, &me)) { g_create_error = why; return QAS_ERR_INVALID; }
+  uint32_t col[32], row[32];
+  QasTapeSink sink{out_ops, max_ops, 0, 0};
+  const int st = qas_compile_circuit(k, p, pool, c, n_qubits, col, row, sink);
+  if (st == 1) { g_create_error = "structure list entry out of range"; return QAS_ERR_INVALID; }
+  if (st == 2) { g_create_error = "tape buffer too small"; return QAS_ERR_NOMEM; }
+  *num_ops = sink.n;
+  if (init_index) *init_index = qas_frame_map_basis(col, n_qubits, init_basis);
+  return QAS_OK;
+}
+
+extern "C" int qas_compile_tape(const qas_ctx *ctx, int p, const int32_t *k, uint32_t *out_ops,
+                                int max_ops, int *num_ops, uint32_t *init_index) {
+  if (!ctx) return QAS_ERR_INVALID;
+  return qas_compile_tape_host(ctx->n, ctx->pool.data(), ctx->c, p, k, ctx->init_basis, out_ops,
+                               max_ops, num_ops, init_index);
+}
+
+// ---------------------------------------------------------------------------------- FP64 peak
+extern "C" int qas_fp64_peak_tflops(int device, int reps, double *tflops) {
+  qas_ctx *ctx = nullptr;
+  if (!tflops) return QAS_ERR_INVALID;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  double *d = nullptr;
+  CK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  double best = 0.0;
+  for (int r = 0; r < std::max(reps, 1) + 1; ++r) {
+    CK(cudaEventRecord(a));
+    dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+    if (r > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+  *tflops = best;
+  return QAS_OK;
+}

@@ -1,0 +1,183 @@
+// tape.h -- the tape compiler: lowers one structure list k (pool keys) to the generalised-gate
+// tape the statevector kernels execute.  Compiled for host AND device: the evaluation kernel
+// runs it in its prologue (one compile per circuit, no tape round-trip through HBM) and
+// qas_compile_tape() exposes the identical code on the host for tests.
+//
+// Restates backboneCirc (reference qas/qml_models/hamiltonian_model.py:22-41): walk k, skip
+// PlaceHolder, emit one operator per pool key.  What is new here:
+//
+//  * CNOT / SWAP folding.  A CNOT is the basis permutation |i> -> |C i> with C linear over
+//    GF(2).  Instead of moving amplitudes, the compiler keeps the frame S_j = C_N ... C_{j+1}
+//    (product of all CNOT maps AFTER position j) and stores the vector in the END-of-circuit
+//    frame: phi_j[S_j i] = psi_j[i].  CNOTs then cost nothing; a 1-qubit gate on logical
+//    qubit q becomes a "generalised" gate that pairs physical indices (P, P ^ m) with
+//    m = S e_q (column q of S) and reads the logical bit as parity(P & r), r = row q of S^-1.
+//    The frame at the end is the identity, so the Hamiltonian is applied in plain logical
+//    coordinates, and basis / uniform initial states stay basis / uniform.
+//  * every gate of the pool vocabulary lowers to two primitive kinds:
+//      K_U1    2x2 unitary on the pair (P, P^m), optionally controlled by parity(P & rc)
+//      K_PDIAG diagonal phase d[parity(P & r)]   (IsingZZ; IsingXX/YY after basis change)
+//
+// The walk is backwards in time, so ops are emitted last-gate-first; the kernels run the
+// forward pass from the end of the tape and the adjoint sweep from its start.
+#pragma once
+#include <stdint.h>
+#include "../../include/qas_b200.h"
+
+#if defined(__CUDACC__)
+#define QAS_HD __host__ __device__ __forceinline__
+#else
+#define QAS_HD inline
+#endif
+
+#define QAS_MAX_QUBITS 30
+#define QAS_OP_WORDS 5      // {m, r, rc, tab, meta}
+#define QAS_K_U1 0u
+#define QAS_K_PDIAG 1u
+
+// constant 2x2 table entries (device table rows [0, QAS_NCONST))
+enum {
+  QAS_C_H = 0, QAS_C_X, QAS_C_Y, QAS_C_Z, QAS_C_S, QAS_C_SDG, QAS_C_T, QAS_C_TDG, QAS_C_SX,
+  QAS_C_SH, QAS_C_HSDG, QAS_C_ZZ_MPI4, QAS_NCONST
+};
+
+// meta word: depth (bits 0-15) | kind (16-19) | nparams (20-21)
+QAS_HD uint32_t qas_meta(int depth, uint32_t kind, int npar) {
+  return (uint32_t)depth | (kind << 16) | ((uint32_t)npar << 20);
+}
+QAS_HD int qas_meta_depth(uint32_t m) { return (int)(m & 0xffffu); }
+QAS_HD uint32_t qas_meta_kind(uint32_t m) { return (m >> 16) & 0xfu; }
+QAS_HD int qas_meta_npar(uint32_t m) { return (int)((m >> 20) & 0x3u); }
+
+// number of parameters of a gate id (SUPPORTED_OPS_DICT[name].num_params upstream)
+QAS_HD int qas_gate_nparams(int g) {
+  switch (g) {
+    case QAS_G_ROT: case QAS_G_U3: case QAS_G_CROT: return 3;
+    case QAS_G_U2: return 2;
+    case QAS_G_RX: case QAS_G_RY: case QAS_G_RZ: case QAS_G_PHASESHIFT: case QAS_G_U1:
+    case QAS_G_CRX: case QAS_G_CRY: case QAS_G_CRZ: case QAS_G_CPHASE:
+    case QAS_G_ISINGXX: case QAS_G_ISINGYY: case QAS_G_ISINGZZ: return 1;
+    default: return 0;
+  }
+}
+QAS_HD int qas_gate_nwires(int g) { return g >= QAS_G_CNOT ? 2 : 1; }
+// worst-case number of tape ops one pool key can expand to
+QAS_HD int qas_gate_expansion(int g) {
+  switch (g) {
+    case QAS_G_PLACEHOLDER: case QAS_G_CNOT: case QAS_G_SWAP: return 0;
+    case QAS_G_ISINGXX: case QAS_G_ISINGYY: return 5;
+    case QAS_G_ISWAP: return 3;
+    case QAS_G_SISWAP: return 10;
+    default: return 1;
+  }
+}
+
+struct QasTapeSink {
+  uint32_t *ops;   // [cap][QAS_OP_WORDS]
+  int cap;
+  int n;           // emitted so far
+  int overflow;
+};
+
+QAS_HD void qas_emit(QasTapeSink &s, uint32_t m, uint32_t r, uint32_t rc, uint32_t tab,
+                     uint32_t meta) {
+  if (s.n >= s.cap) { s.overflow = 1; return; }
+  uint32_t *o = s.ops + (size_t)s.n * QAS_OP_WORDS;
+  o[0] = m; o[1] = r; o[2] = rc; o[3] = tab; o[4] = meta;
+  s.n++;
+}
+
+// Compile one circuit.  col/row: scratch arrays of n words each (frame S and S^-1).
+// Returns 0, or 1 if some key is out of range (the reference asserts min(k)>=0, max(k)<c at
+// utils.py:12-15), or 2 on tape overflow.
+QAS_HD int qas_compile_circuit(const int32_t *k, int p, const qas_pool_entry *pool, int c, int n,
+                               uint32_t *col, uint32_t *row, QasTapeSink &s) {
+  for (int q = 0; q < n; ++q) col[q] = row[q] = 1u << (n - 1 - q);
+  s.n = 0;
+  s.overflow = 0;
+  for (int i = p - 1; i >= 0; --i) {
+    const int key = k[i];
+    if (key < 0 || key >= c) return 1;
+    const int g = pool[key].gate_id;
+    const int a = pool[key].wire0, b = pool[key].wire1;
+    const uint32_t ptab = (uint32_t)QAS_NCONST + (uint32_t)i * (uint32_t)c + (uint32_t)key;
+    const int np = qas_gate_nparams(g);
+    switch (g) {
+      case QAS_G_PLACEHOLDER: break;
+      case QAS_G_HADAMARD: case QAS_G_PAULIX: case QAS_G_PAULIY: case QAS_G_PAULIZ:
+      case QAS_G_S: case QAS_G_SDG: case QAS_G_T: case QAS_G_TDG: case QAS_G_SX:
+        // constant table rows are laid out in the same order as the gate ids 1..9
+        qas_emit(s, col[a], row[a], 0u, (uint32_t)(g - QAS_G_HADAMARD), qas_meta(i, QAS_K_U1, 0));
+        break;
+      case QAS_G_ROT: case QAS_G_RX: case QAS_G_RY: case QAS_G_RZ: case QAS_G_PHASESHIFT:
+      case QAS_G_U1: case QAS_G_U2: case QAS_G_U3:
+        qas_emit(s, col[a], row[a], 0u, ptab, qas_meta(i, QAS_K_U1, np));
+        break;
+      case QAS_G_CNOT:      // fold: S <- S o C,  S^-1 <- C S^-1   (control a, target b)
+        col[a] ^= col[b];
+        row[b] ^= row[a];
+        break;
+      case QAS_G_SWAP: {
+        uint32_t t = col[a]; col[a] = col[b]; col[b] = t;
+        t = row[a]; row[a] = row[b]; row[b] = t;
+        break;
+      }
+      case QAS_G_CZ:
+        qas_emit(s, col[b], row[b], row[a], QAS_C_Z, qas_meta(i, QAS_K_U1, 0));
+        break;
+      case QAS_G_CY:
+        qas_emit(s, col[b], row[b], row[a], QAS_C_Y, qas_meta(i, QAS_K_U1, 0));
+        break;
+      case QAS_G_CRX: case QAS_G_CRY: case QAS_G_CRZ: case QAS_G_CROT: case QAS_G_CPHASE:
+        qas_emit(s, col[b], row[b], row[a], ptab, qas_meta(i, QAS_K_U1, np));
+        break;
+      case QAS_G_ISINGZZ:
+        qas_emit(s, 0u, row[a] ^ row[b], 0u, ptab, qas_meta(i, QAS_K_PDIAG, 1));
+        break;
+      case QAS_G_ISINGXX:   // (H x H) ZZ(theta) (H x H); emitted last-first
+        qas_emit(s, col[a], row[a], 0u, QAS_C_H, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, col[b], row[b], 0u, QAS_C_H, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, 0u, row[a] ^ row[b], 0u, ptab, qas_meta(i, QAS_K_PDIAG, 1));
+        qas_emit(s, col[a], row[a], 0u, QAS_C_H, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, col[b], row[b], 0u, QAS_C_H, qas_meta(i, QAS_K_U1, 0));
+        break;
+      case QAS_G_ISINGYY:   // (SH x SH) ZZ(theta) (HS^ x HS^)
+        qas_emit(s, col[a], row[a], 0u, QAS_C_SH, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, col[b], row[b], 0u, QAS_C_SH, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, 0u, row[a] ^ row[b], 0u, ptab, qas_meta(i, QAS_K_PDIAG, 1));
+        qas_emit(s, col[a], row[a], 0u, QAS_C_HSDG, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, col[b], row[b], 0u, QAS_C_HSDG, qas_meta(i, QAS_K_U1, 0));
+        break;
+      case QAS_G_ISWAP: {   // (S x S) CZ SWAP  (SWAP acts first, so it is folded last)
+        qas_emit(s, col[a], row[a], 0u, QAS_C_S, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, col[b], row[b], 0u, QAS_C_S, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, col[b], row[b], row[a], QAS_C_Z, qas_meta(i, QAS_K_U1, 0));
+        uint32_t t = col[a]; col[a] = col[b]; col[b] = t;
+        t = row[a]; row[a] = row[b]; row[b] = t;
+        break;
+      }
+      case QAS_G_SISWAP:    // exp(i pi/8 (XX+YY)) = IsingXX(-pi/4) IsingYY(-pi/4)
+        qas_emit(s, col[a], row[a], 0u, QAS_C_H, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, col[b], row[b], 0u, QAS_C_H, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, 0u, row[a] ^ row[b], 0u, QAS_C_ZZ_MPI4, qas_meta(i, QAS_K_PDIAG, 0));
+        qas_emit(s, col[a], row[a], 0u, QAS_C_H, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, col[b], row[b], 0u, QAS_C_H, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, col[a], row[a], 0u, QAS_C_SH, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, col[b], row[b], 0u, QAS_C_SH, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, 0u, row[a] ^ row[b], 0u, QAS_C_ZZ_MPI4, qas_meta(i, QAS_K_PDIAG, 0));
+        qas_emit(s, col[a], row[a], 0u, QAS_C_HSDG, qas_meta(i, QAS_K_U1, 0));
+        qas_emit(s, col[b], row[b], 0u, QAS_C_HSDG, qas_meta(i, QAS_K_U1, 0));
+        break;
+      default: return 1;
+    }
+  }
+  return s.overflow ? 2 : 0;
+}
+
+// physical index of a logical basis state in the end-of-circuit frame: S_0 * basis
+QAS_HD uint32_t qas_frame_map_basis(const uint32_t *col, int n, uint64_t basis) {
+  uint32_t out = 0;
+  for (int q = 0; q < n; ++q)
+    if ((basis >> (n - 1 - q)) & 1ull) out ^= col[q];
+  return out;
+}

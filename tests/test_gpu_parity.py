@@ -1,0 +1,276 @@
+"""GPU tier: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances are the north_star's: |dE| <= 1e-9 Ha, gradient components <= 1e-8 (floating point,
+complex128 arithmetic on both sides).  Small cases compare against the oracle on the same seeded
+inputs and against the committed golden fixtures; BASELINE-size batches are checked through
+size-independent properties (spectral bounds, linearity in the Hamiltonian, the parameter-shift
+identity between the energy path and the adjoint path, permutation invariance, determinism).
+"""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import sim
+from qas_b200.evaluator import BatchEvaluator
+from qas_b200.qml_models.qml_gate_ops import QMLPool
+from qas_b200.sampling import sample_structure_lists
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-9
+G_TOL = 1e-8
+
+
+def _oracle_batch(n, ks, pool, params, terms, init, grad=True):
+    es, gs = [], []
+    for k in ks:
+        k = [int(x) for x in k]
+        es.append(sim.energy(n, k, pool, params, terms, init))
+        if grad:
+            gs.append(sim.grad_adjoint(n, k, pool, params, terms, init))
+    return np.array(es), gs
+
+
+@pytest.mark.parametrize("cfg", list(helpers.CONFIGS))
+def test_config_batch_matches_oracle(cfg):
+    mname, n, p, mk, lim = helpers.CONFIGS[cfg]
+    model = helpers.get_model(mname)
+    pool = mk()
+    c = len(pool)
+    B = 24 if n <= 8 else 6
+    scale = np.sqrt(2.0 / 2 ** n) if "qaoa" in cfg else 1.0      # qaoa_search_demo.py:55
+    params = np.random.default_rng(1).standard_normal((p, c, 3)) * scale
+    ks = sample_structure_lists(pool, p, lim, B, seed=2)
+    out = model.evaluate_batch(ks, params, pool, want_grad=True, compact=True)
+    e_ref, g_ref = _oracle_batch(n, ks, pool.pool, params, model.terms(), model.init_state)
+    assert np.max(np.abs(out["energy"] - e_ref)) <= E_TOL
+    dense = helpers.dense_from_compact(ks, out["grad_compact"], c)
+    for b in range(B):
+        assert np.max(np.abs(dense[b] - g_ref[b])) <= G_TOL
+    assert np.max(np.abs(out["grad_dense"] - sim.batch_mean_gradient(g_ref))) <= G_TOL
+    # energy-only launch (the reward path) gives the same energies
+    out2 = model.evaluate_batch(ks, params, pool, want_grad=False)
+    assert np.max(np.abs(out2["energy"] - e_ref)) <= E_TOL
+    assert out2["grad_dense"] is None
+
+
+@pytest.mark.parametrize("g", helpers.goldens(), ids=lambda g: g["fixture"])
+def test_golden_through_model_interface(g):
+    """getLoss / getReward / getGradient / toList of the drop-in classes on the reference's saved
+    circuits: energy = oracle = the reference's recorded loss (to the one-step lag)."""
+    ev = BatchEvaluator(g["n_qubits"], g["terms"], g["pool"], g["init"])
+    out = ev.evaluate([g["k"]], g["params"], want_grad=True, compact=True)
+    e = out["energy"][0]
+    assert abs(e - sim.energy(g["n_qubits"], g["k"], g["pool"], g["params"], g["terms"], g["init"])) <= E_TOL
+    if g["tolerance_vs_last_loss"] is not None:
+        assert abs(e - g["fine_tune_loss_tail"][-1]) <= g["tolerance_vs_last_loss"]
+    ga = sim.grad_adjoint(g["n_qubits"], g["k"], g["pool"], g["params"], g["terms"], g["init"])
+    dense = helpers.dense_from_compact([g["k"]], out["grad_compact"], len(g["pool"]))[0]
+    assert np.max(np.abs(dense - ga)) <= G_TOL
+    ev.close()
+
+
+def test_model_methods_mirror_reference_interface():
+    from qas_b200.qml_models.qml_models_legacy import FourQubitH2, QAOAVQCDemo
+    g = [x for x in helpers.goldens() if x["fixture"] == "h2_hf_a"][0]
+    pool = helpers.near_cx_pool(4)
+    assert pool.pool == g["pool"]
+    p, c, l = g["params"].shape
+    m = FourQubitH2(p, c, l, g["k"], pool)
+    loss = m.getLoss(g["params"])
+    assert isinstance(loss, float) and abs(loss - g["fine_tune_loss_tail"][-1]) < 5e-5
+    assert m.getReward(g["params"]) == -loss
+    grad = m.getGradient(g["params"])
+    assert grad.shape == g["params"].shape and grad is not g["params"]
+    ga = sim.grad_adjoint(4, g["k"], g["pool"], g["params"], m.terms(), m.init_state)
+    assert np.max(np.abs(grad - ga)) <= G_TOL
+    ops = m.toList(g["params"])
+    assert [(a, list(b)) for a, b, _ in ops] == [(a, list(b)) for a, b, _ in g["op_list"]]
+    with pytest.raises(AssertionError):
+        m.getLoss(g["params"][:-1])
+    # QAOA: reward = -loss = expected cut value
+    q = [x for x in helpers.goldens() if x["fixture"] == "qaoa7q_a"][0]
+    qpool = helpers.near_cx_pool(7, helpers.ring(7))
+    assert qpool.pool == q["pool"]
+    qm = QAOAVQCDemo(15, len(qpool), 3, q["k"], qpool)
+    assert abs(qm.getReward(q["params"]) - 7.0) < 1e-8
+    # a circuit with no trainable gate: zero gradient (hamiltonian_model.py:84-85)
+    m0 = FourQubitH2(3, c, l, [0, 8, 1], pool)
+    assert m0.getGradient(g["params"][:3]).shape == (3, c, l)
+
+
+def test_full_vocabulary_random_circuits():
+    rng = np.random.default_rng(3)
+    for n in (3, 5, 6):
+        pool = helpers.full_vocab_pool(n)
+        c = len(pool)
+        terms = [(float(rng.standard_normal()), "".join(rng.choice(list("IXYZ"), size=n))) for _ in range(12)]
+        for init in (("zero", 0), ("basis", int(rng.integers(0, 2 ** n))), ("plus", 0)):
+            ev = BatchEvaluator(n, terms, pool, init)
+            p, B = 9, 10
+            ks = rng.integers(0, c, size=(B, p)).astype(np.int32)
+            params = rng.standard_normal((p, c, 3))
+            out = ev.evaluate(ks, params, want_grad=True, compact=True)
+            e_ref, g_ref = _oracle_batch(n, ks, pool.pool, params, terms, init)
+            assert np.max(np.abs(out["energy"] - e_ref)) <= E_TOL
+            dense = helpers.dense_from_compact(ks, out["grad_compact"], c)
+            assert max(np.max(np.abs(dense[b] - g_ref[b])) for b in range(B)) <= G_TOL
+            ev.close()
+
+
+@pytest.mark.parametrize("n,grad", [(9, True), (11, True), (12, True), (13, False), (13, True), (14, True)])
+def test_qubit_count_sweep_including_global_memory_path(n, grad):
+    """11-12 qubits: 256-thread teams; 13 energy-only still shared-memory resident; 13 with
+    gradients and 14 fall to the global-memory path."""
+    rng = np.random.default_rng(n)
+    pool = helpers.near_cx_pool(n)
+    c = len(pool)
+    terms = [(float(rng.standard_normal()), "".join(rng.choice(list("IXYZ"), size=n, p=[.55, .15, .15, .15])))
+             for _ in range(10)]
+    p, B = 8, 3
+    ev = BatchEvaluator(n, terms, pool, ("zero", 0))
+    ks = sample_structure_lists(pool, p, {"CNOT": 4}, B, seed=n)
+    params = rng.standard_normal((p, c, 3))
+    out = ev.evaluate(ks, params, want_grad=grad, compact=grad)
+    st = ev.stats()
+    assert st["path"] == (0 if n <= (12 if grad else 13) else 1)
+    e_ref, g_ref = _oracle_batch(n, ks, pool.pool, params, terms, ("zero", 0), grad)
+    assert np.max(np.abs(out["energy"] - e_ref)) <= E_TOL
+    if grad:
+        dense = helpers.dense_from_compact(ks, out["grad_compact"], c)
+        assert max(np.max(np.abs(dense[b] - g_ref[b])) for b in range(B)) <= G_TOL
+    ev.close()
+
+
+def test_edge_cases():
+    from qas_b200.qml_models.qml_models_legacy import FourQubitH2
+    pool = helpers.near_cx_pool(4)
+    c = len(pool)
+    params = np.random.default_rng(0).standard_normal((4, c, 3))
+    terms = FourQubitH2.terms()
+    # all-PlaceHolder-like circuit is impossible under legality, but the evaluator accepts any keys:
+    # only PlaceHolders -> the initial state's energy, zero gradient
+    out = FourQubitH2.evaluate_batch([[1, 3, 5, 7]], params, pool, compact=True)
+    e0 = sim.energy(4, [1, 3, 5, 7], pool.pool, params, terms, FourQubitH2.init_state)
+    assert abs(out["energy"][0] - e0) <= E_TOL and not out["grad_compact"].any()
+    # only CNOTs: tape is empty after folding, state is a permuted basis state
+    out = FourQubitH2.evaluate_batch([[8, 10, 12, 9]], params, pool, compact=True)
+    e1 = sim.energy(4, [8, 10, 12, 9], pool.pool, params, terms, FourQubitH2.init_state)
+    assert abs(out["energy"][0] - e1) <= E_TOL
+    # out-of-range key -> AssertionError, like the reference's asserts (utils.py:12-15)
+    with pytest.raises(AssertionError):
+        FourQubitH2.evaluate_batch([[0, 14, 1, 2]], params, pool)
+    # ragged batch sizes around the team/CTA granularity
+    for B in (1, 7, 31, 33, 257):
+        ks = sample_structure_lists(pool, 4, None, B, seed=B)
+        out = FourQubitH2.evaluate_batch(ks, params, pool, want_grad=False)
+        ref = np.array([sim.energy(4, [int(x) for x in k], pool.pool, params, terms, FourQubitH2.init_state)
+                        for k in ks[:5]])
+        assert np.max(np.abs(out["energy"][:5] - ref)) <= E_TOL
+        assert np.all(np.isfinite(out["energy"]))
+    # sum instead of mean (avg_gradients=False, mcts.py:347)
+    ks = sample_structure_lists(pool, 4, None, 8, seed=4)
+    a = FourQubitH2.evaluate_batch(ks, params, pool, avg=True)["grad_dense"]
+    s = FourQubitH2.evaluate_batch(ks, params, pool, avg=False)["grad_dense"]
+    assert np.max(np.abs(8 * a - s)) <= 1e-12
+
+
+def test_device_pointer_entry_is_equivalent():
+    import torch
+    from qas_b200.qml_models.qml_models_legacy import LiH
+    pool = helpers.near_cx_pool(10)
+    c, p, B = len(pool), 20, 64
+    params = np.random.default_rng(0).standard_normal((p, c, 3))
+    ks = sample_structure_lists(pool, p, {"CNOT": 10}, B, seed=0)
+    host = LiH.evaluate_batch(ks, params, pool, compact=True)
+    ev = LiH.evaluator(pool)
+    dk = torch.from_numpy(ks).cuda()
+    dp = torch.from_numpy(params).cuda()
+    de = torch.empty(B, dtype=torch.float64, device="cuda")
+    dgc = torch.empty(B, p, 3, dtype=torch.float64, device="cuda")
+    dgd = torch.empty(p, c, 3, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream()
+    ev.evaluate_device(dk, dp, de, dgc, dgd, stream=stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(de.cpu().numpy(), host["energy"])
+    assert np.array_equal(dgc.cpu().numpy(), host["grad_compact"])
+    assert np.array_equal(dgd.cpu().numpy(), host["grad_dense"])
+
+
+# --------------------------------------------------------------------------- BASELINE-size properties
+def test_baseline_size_properties_lih():
+    """LiH near_cx at the script's depth (p=20) and a saturating batch: properties that do not
+    need the oracle at full size."""
+    from qas_b200.qml_models.qml_models_legacy import LiH
+    n, p, B = 10, 20, 8192
+    pool = helpers.near_cx_pool(n)
+    c = len(pool)
+    params = np.random.default_rng(10).standard_normal((p, c, 3))
+    ks = sample_structure_lists(pool, p, {"CNOT": p // 2}, B, seed=10)
+    out = LiH.evaluate_batch(ks, params, pool, compact=True)
+    e = out["energy"]
+    # (1) spectral bounds of the 10-qubit operator
+    ev = np.linalg.eigvalsh(sim.hamiltonian_matrix(n, LiH.terms()).real)
+    assert e.min() >= ev[0] - 1e-9 and e.max() <= ev[-1] + 1e-9
+    # (2) determinism + permutation invariance
+    perm = np.random.default_rng(0).permutation(B)
+    out2 = LiH.evaluate_batch(ks[perm], params, pool, compact=True)
+    assert np.array_equal(out2["energy"], e[perm])
+    assert np.array_equal(out2["grad_compact"], out["grad_compact"][perm])
+    # (3) dense mean = mean over the batch of the scattered compact gradients (zeros included)
+    dense = np.zeros((p, c, 3))
+    for i in range(p):
+        np.add.at(dense[i], ks[:, i], out["grad_compact"][:, i, :])
+    assert np.max(np.abs(dense / B - out["grad_dense"])) <= 1e-12
+    # (4) parameter-shift identity ties the adjoint kernel to the energy kernel at full size:
+    #     dE/dtheta = (E(theta + pi/2) - E(theta - pi/2)) / 2 for every Rot angle
+    rng = np.random.default_rng(1)
+    for _ in range(6):
+        i, j = int(rng.integers(0, p)), int(rng.integers(0, 3))
+        key = 2 * int(rng.integers(0, n))             # a Rot key
+        sel = np.nonzero(ks[:, i] == key)[0]
+        if len(sel) == 0:
+            continue
+        pp, pm = params.copy(), params.copy()
+        pp[i, key, j] += np.pi / 2
+        pm[i, key, j] -= np.pi / 2
+        ep = LiH.evaluate_batch(ks[sel], pp, pool, want_grad=False)["energy"]
+        em = LiH.evaluate_batch(ks[sel], pm, pool, want_grad=False)["energy"]
+        assert np.max(np.abs(0.5 * (ep - em) - out["grad_compact"][sel, i, j])) <= G_TOL
+    # (5) oracle spot check on a few members of the big batch
+    for b in (0, B // 2, B - 1):
+        k = [int(x) for x in ks[b]]
+        assert abs(e[b] - sim.energy(n, k, pool.pool, params, LiH.terms(), LiH.init_state)) <= E_TOL
+
+
+def test_linearity_in_hamiltonian():
+    """E_{H1+H2} = E_{H1} + E_{H2} for the same circuits (X-mask grouping must not mix terms)."""
+    from qas_b200.qml_models.qml_models_legacy import H2O
+    n, p, B = 8, 50, 512
+    pool = helpers.near_cx_pool(n)
+    terms = H2O.terms()
+    half = len(terms) // 2
+    params = np.random.default_rng(3).standard_normal((p, len(pool), 3))
+    ks = sample_structure_lists(pool, p, {"CNOT": 25}, B, seed=3)
+    outs = []
+    for tt in (terms, terms[:half], terms[half:]):
+        ev = BatchEvaluator(n, tt, pool, ("zero", 0))
+        outs.append(ev.evaluate(ks, params))
+        ev.close()
+    assert np.max(np.abs(outs[0]["energy"] - outs[1]["energy"] - outs[2]["energy"])) <= 1e-10
+    assert np.max(np.abs(outs[0]["grad_dense"] - outs[1]["grad_dense"] - outs[2]["grad_dense"])) <= 1e-10
+
+
+def test_kagome_16q_global_memory_path_small_depth():
+    from qas_b200.qml_models.kagome_heisenberg_model import KagomeHeisenberg as K
+    n, p, B = 16, 6, 2
+    pool = QMLPool(n, ["Rot", "PlaceHolder"], ["CNOT"], False, helpers.line(n))
+    params = np.random.default_rng(16).standard_normal((p, len(pool), 3))
+    ks = sample_structure_lists(pool, p, {"CNOT": 3}, B, seed=16)
+    out = K.evaluate_batch(ks, params, pool, compact=True)
+    for b in range(B):
+        k = [int(x) for x in ks[b]]
+        assert abs(out["energy"][b] - sim.energy(n, k, pool.pool, params, K.terms(), K.init_state)) <= E_TOL
+        ga = sim.grad_adjoint(n, k, pool.pool, params, K.terms(), K.init_state)
+        dense = helpers.dense_from_compact([k], out["grad_compact"][b:b + 1], len(pool))[0]
+        assert np.max(np.abs(dense - ga)) <= G_TOL

@@ -1,0 +1,155 @@
+"""CPU tier: the C-ABI library loads and exports its symbols, the host-side tape compiler and
+the kernel algorithm (NumPy tape interpreter) agree with the oracle, and the host mirror of the
+reference plugin surface (pool, indices, legality) behaves like the reference's."""
+import ctypes
+import re
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import tape_interp as TI
+from oracle import sim
+from qas_b200 import _lib
+from qas_b200.evaluator import compile_tape_host
+from qas_b200.mcts.qml_mcts_state import QMLStateBasicGates
+from qas_b200.qml_models.qml_gate_ops import QMLGate, QMLPool, SUPPORTED_OPS_DICT
+from qas_b200.qml_models.utils import extractParamIndicesQML
+from qas_b200.sampling import legal_mask, sample_structure_lists
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    assert lib.qas_abi_version() == 1
+    header = open(os.path.join(os.path.dirname(_lib.LIB_PATH), "..", "..", "include", "qas_b200.h")).read()
+    declared = set(re.findall(r"\b(qas_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert declared == set(_lib.EXPORTS)
+
+
+def test_gate_id_table_matches_header():
+    header = open(os.path.join(os.path.dirname(_lib.LIB_PATH), "..", "..", "include", "qas_b200.h")).read()
+    body = header.split("enum qas_gate_id {")[1].split("}")[0]
+    names = [x.strip().split("=")[0].strip() for x in body.replace("\n", " ").split(",") if x.strip()]
+    names = [x for x in names if x != "QAS_G_COUNT"]
+    ours = sorted(set(_lib.GATE_IDS.values()))
+    assert ours == list(range(len(names)))
+    assert names[_lib.GATE_IDS["Rot"]] == "QAS_G_ROT"
+    assert names[_lib.GATE_IDS["CNOT"]] == "QAS_G_CNOT"
+    assert names[_lib.GATE_IDS["IsingZZ"]] == "QAS_G_ISINGZZ"
+
+
+def test_pool_key_layout():
+    # qml_gate_ops.py:167-176: key 2i = Rot on i, 2i+1 = PlaceHolder on i, 2n+j = CNOT on coupling[j]
+    pool = helpers.near_cx_pool(4)
+    assert len(pool) == 14
+    assert pool[0] == {"Rot": [0]} and pool[1] == {"PlaceHolder": [0]} and pool[6] == {"Rot": [3]}
+    assert pool[8] == {"CNOT": [0, 1]} and pool[13] == {"CNOT": [3, 2]}
+    full = QMLPool(3, ["Rot"], ["CNOT"])
+    assert full.coupling == [(0, 1), (0, 2), (1, 0), (1, 2), (2, 0), (2, 1)]
+    with pytest.raises(AssertionError):
+        QMLPool(3, ["CNOT"], [])
+    with pytest.raises(AssertionError):
+        QMLPool(3, ["MultiRZ"], [])
+    with pytest.raises(AssertionError):
+        QMLPool(3, ["Rot"], ["CNOT"], True, [[0, 1]])
+
+
+def test_extract_param_indices_and_gate_record():
+    pool = helpers.near_cx_pool(4)
+    assert extractParamIndicesQML([0, 8, 1, 2], pool) == [(0, 0, 0), (0, 0, 1), (0, 0, 2), (3, 2, 0), (3, 2, 1), (3, 2, 2)]
+    with pytest.raises(AssertionError):
+        extractParamIndicesQML([0, 14], pool)
+    g = QMLGate("Rot", [2], [0.1, 0.2, 0.3])
+    assert g.getOp().name == "Rot" and g.getQregPos() == [2] and g.num_params == 3
+    with pytest.raises(AssertionError):
+        QMLGate("Rot", [2], [0.1])
+    assert SUPPORTED_OPS_DICT["PlaceHolder"].num_params == 0
+
+
+@pytest.mark.parametrize("g", helpers.goldens(), ids=lambda g: g["fixture"])
+def test_tape_compiler_and_kernel_algorithm_on_goldens(g):
+    ib = g["init"][1] if g["init"][0] == "basis" else 0
+    ops, idx = compile_tape_host(g["n_qubits"], g["pool"], g["k"], ib)
+    # CNOTs and PlaceHolders are folded away: one op per remaining gate
+    assert len(ops) == sum(1 for name, _, _ in g["op_list"] if name != "CNOT")
+    e, gr = TI.run_tape(g["n_qubits"], ops, g["init"], idx, g["pool"], len(g["pool"]), g["params"], g["terms"])
+    assert abs(e - sim.energy(g["n_qubits"], g["k"], g["pool"], g["params"], g["terms"], g["init"])) < 1e-11
+    ga = sim.grad_adjoint(g["n_qubits"], g["k"], g["pool"], g["params"], g["terms"], g["init"])
+    for (d, j), v in gr.items():
+        assert abs(v - ga[d, g["k"][d], j]) < 1e-10
+
+
+def test_tape_compiler_full_vocabulary_random():
+    rng = np.random.default_rng(0)
+    n = 4
+    pool = helpers.full_vocab_pool(n)
+    c = len(pool)
+    terms = [(0.3, "XYZI"), (0.2, "IYII"), (-0.15, "XZYY"), (0.5, "ZZII"), (0.1, "IIII")]
+    for trial in range(12):
+        p = 10
+        k = [int(x) for x in rng.integers(0, c, size=p)]
+        params = rng.standard_normal((p, c, 3))
+        init = [("zero", 0), ("basis", int(rng.integers(0, 16))), ("plus", 0)][trial % 3]
+        ops, idx = compile_tape_host(n, pool, k, init[1] if init[0] == "basis" else 0)
+        e, gr = TI.run_tape(n, ops, init, idx, pool.pool, c, params, terms)
+        assert abs(e - sim.energy(n, k, pool.pool, params, terms, init)) < 1e-11
+        ga = sim.grad_adjoint(n, k, pool.pool, params, terms, init)
+        got = np.zeros_like(ga)
+        for (d, j), v in gr.items():
+            got[d, k[d], j] = v
+        assert np.max(np.abs(got - ga)) < 1e-10
+
+
+def test_tape_compiler_rejects_out_of_range_keys():
+    pool = helpers.near_cx_pool(4)
+    with pytest.raises(AssertionError):
+        compile_tape_host(4, pool, [0, 14, 2])
+    with pytest.raises(AssertionError):
+        compile_tape_host(4, pool, [0, -1, 2])
+
+
+def test_all_placeholder_circuit_has_empty_tape():
+    pool = helpers.near_cx_pool(3)
+    ops, _ = compile_tape_host(3, pool, [1, 3, 5, 1])
+    assert len(ops) == 0
+
+
+def test_sampler_only_draws_legal_actions_and_matches_state_class():
+    pool = helpers.near_cx_pool(5, helpers.ring(5))
+    p = 12
+    lim = {"CNOT": 4}
+    ks = sample_structure_lists(pool, p, lim, 64, seed=1)
+    assert ks.shape == (64, p) and ks.dtype == np.int32
+    for k in ks:
+        st = QMLStateBasicGates([], pool, p, set(), lim)
+        for a in k:
+            assert int(a) in st.getLegalActions()
+            st = st.takeAction(int(a))
+        assert st.isTerminal() and st.getCurrK() == [int(a) for a in k]
+        assert sum(1 for a in k if "CNOT" in pool[int(a)]) <= 4
+    # first action is necessarily a parameterised 1-q gate
+    assert all("Rot" in pool[int(k[0])] for k in ks)
+
+
+def test_legality_rules_clifford_t():
+    pool = QMLPool(2, ["T", "Tdg", "S", "Sdg", "PauliZ", "Hadamard", "PlaceHolder"], ["CNOT", "CZ"])
+    names = {k: list(v.keys())[0] for k, v in pool.pool.items()}
+    key = lambda nm, w: [k for k, v in pool.pool.items() if list(v) == [nm] and list(v[nm]) == w][0]  # noqa: E731
+    st = QMLStateBasicGates([], pool, 6, set(), None).takeAction(key("T", [0]))
+    legal = st.getLegalActions()
+    assert key("Tdg", [0]) not in legal            # T then Tdg cancels
+    assert key("T", [0]) not in legal              # two T = S and S is in the pool
+    assert key("S", [0]) in legal
+    assert key("CNOT", [1, 0]) not in legal        # control qubit 1 untouched
+    assert key("CNOT", [0, 1]) in legal
+    assert key("PlaceHolder", [1]) not in legal and key("PlaceHolder", [0]) in legal
+    st2 = st.takeAction(key("CNOT", [0, 1]))
+    assert key("CNOT", [0, 1]) not in st2.getLegalActions()
+    assert names[key("CZ", [0, 1])] == "CZ" and key("CZ", [0, 1]) in st2.getLegalActions()
+    st3 = st2.takeAction(key("Hadamard", [1]))
+    assert key("Hadamard", [1]) not in st3.getLegalActions()
+    assert key("CNOT", [0, 1]) in st3.getLegalActions()   # last op on qubit 1 is no longer the CNOT
