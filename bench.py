@@ -308,7 +308,7 @@ def run_b200(args):
 
     # ---- CPU baseline: reference-pattern oracle on a bounded sample, 1 core (how the reference runs)
     t_probe, _ = _cpu_worker((name, 0, 1, args.seed, 8))
-    ns = int(max(2, min(64, 12.0 / max(t_probe, 1e-3))))
+    ns = int(max(2, min(4096, 15.0 / max(t_probe, 1e-3))))
     cpu_v, cpu_n, cpu_t = cpu_port_throughput(name, ns, 1, args.seed)
     from oracle.refpattern import REF_METHOD
     cpu_baseline = {"value": cpu_v, "unit": "evals/s", "cores": 1, "kind": "port",

@@ -103,6 +103,8 @@ const char *qas_last_error(const qas_ctx *ctx);
  *   grad_dense   double [p][c][l] or NULL
  *                              out: mean (or sum) over the batch of the dense gradients after
  *                              nan_to_num -- the reduction at mcts.py:345-347
+ * stream: a cudaStream_t.  With QAS_F_DEVICE_PTRS the work is enqueued on exactly that stream
+ * (NULL = the CUDA default stream); with host pointers NULL selects the context's own stream.
  * Replaces the serial loops mcts.py:298-305 (rewards) and :340-347 (gradients).            */
 int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, const double *params,
                    double *energy, double *grad_compact, double *grad_dense, uint32_t flags,

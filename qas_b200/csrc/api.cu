@@ -323,7 +323,10 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   const bool want_grad = grad_compact || grad_dense;
   const int c = ctx->c, l = ctx->l;
   CK(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  // device-pointer calls run on exactly the stream given (NULL = the CUDA default stream, which is
+  // what torch.cuda.current_stream() is unless the caller changed it); host-pointer calls default to
+  // the context's own stream
+  cudaStream_t st = (dev || stream) ? (cudaStream_t)stream : ctx->stream;
   const size_t nk = (size_t)B * p, npar = (size_t)p * c * l, ng = (size_t)B * p * l;
 
   if (!dev) {   // the reference's asserts on k (utils.py:12-15)
