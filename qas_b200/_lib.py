@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libqas_b200.so")
+LIB_PATH = os.environ.get("QAS_B200_LIB", os.path.join(_HERE, "lib", "libqas_b200.so"))
 
 QAS_OK = 0
 QAS_ERR_INVALID = 1

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -24,7 +25,10 @@ struct qas_ctx {
   // device buffers owned by the context
   qas_pool_entry *d_pool = nullptr;
   double *d_vtab = nullptr;
-  uint32_t *d_sx = nullptr, *d_simag = nullptr;
+  uint32_t *d_sdesc = nullptr;
+  int team_scale = 1;              // QAS_B200_TEAM_SCALE: threads per team = scale * default
+  int T = 0, RB = 0, rb[3] = {0, 0, 0};
+  int num_classes = 0;
   GateTab *d_U = nullptr;
   GateDTab *d_dU = nullptr;
   int tab_p = 0;
@@ -35,6 +39,7 @@ struct qas_ctx {
   double *d_partial = nullptr; size_t cap_partial = 0;
   double *d_dense = nullptr; size_t cap_dense = 0;
   double2 *d_gstate = nullptr; size_t cap_gstate = 0;
+  uint32_t *d_tape = nullptr; size_t cap_tape = 0;
   qas_stats stats{};
   mutable std::string err;
 };
@@ -120,6 +125,17 @@ static void fill_const_table(std::vector<GateTab> &t) {
   set(QAS_C_ZZ_MPI4, make_double2(cs, sn), Z0, Z0, make_double2(cs, -sn));
 }
 
+constexpr int team_threads(int n) {
+  return n <= 4 ? 8 : n == 5 ? 16 : n <= 8 ? 32 : n == 9 ? 64 : n == 10 ? 128 : 256;
+}
+static int team_threads_for(int n, int scale) {
+  const int t = team_threads(n);
+  if (n >= 14) return 256;
+  // doubled variants exist for n = 4..10 (see launch_eval)
+  if (scale >= 2 && n >= 4 && n <= 10 && t * 2 <= 256) return t * 2;
+  return t;
+}
+
 // ---------------------------------------------------------------------------------- create
 extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_kind,
                               uint64_t init_basis, const qas_pauli_term *terms, int num_terms,
@@ -148,6 +164,11 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   cx->c = c; cx->l = l; cx->max_expansion = max_exp;
   cx->pool.assign(pool, pool + c);
 
+  // threads per team and the register bits of the H-apply blocking
+  if (const char *ts = getenv("QAS_B200_TEAM_SCALE")) cx->team_scale = std::max(1, atoi(ts));
+  cx->T = team_threads_for(n_qubits, cx->team_scale);
+  cx->RB = qas_register_bits(n_qubits <= 13 ? n_qubits : 20, cx->T);
+
   // group the Hamiltonian by X mask: slice key = (xmask, is_imag); term sign from i^{nY}
   std::map<std::pair<uint64_t, int>, std::vector<std::pair<uint32_t, double>>> slices;
   for (int t = 0; t < num_terms; ++t) {
@@ -155,14 +176,59 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
     const double sgn = (ny & 2) ? -1.0 : 1.0;
     slices[{terms[t].xmask, ny & 1}].push_back({(uint32_t)terms[t].zmask, sgn * terms[t].coeff});
   }
-  std::vector<uint32_t> sx, simag, tz;
+  // choose the register-bit positions that minimise the number of X-mask classes
+  {
+    std::vector<uint32_t> xs;
+    for (auto &kv : slices) xs.push_back((uint32_t)kv.first.first);
+    size_t best = (size_t)-1;
+    int pos[3] = {0, 1, 2};
+    const int RBc = cx->RB, nq = n_qubits;
+    // positions below bit 3 would break up the 8-amplitude (128-byte) rows consecutive lanes read
+    const int lo = (nq - RBc >= 3 && nq - 3 >= RBc) ? 3 : 0;
+    for (int a = lo; a < nq; ++a)
+      for (int b = (RBc >= 2 ? a + 1 : nq - 1); b < nq; ++b)
+        for (int c3 = (RBc >= 3 ? b + 1 : nq - 1); c3 < nq; ++c3) {
+          uint32_t mask = 0;
+          if (RBc >= 1) mask |= 1u << a;
+          if (RBc >= 2) mask |= 1u << b;
+          if (RBc >= 3) mask |= 1u << c3;
+          std::vector<uint32_t> cls;
+          for (uint32_t x : xs) cls.push_back(x & ~mask);
+          std::sort(cls.begin(), cls.end());
+          const size_t ncls = std::unique(cls.begin(), cls.end()) - cls.begin();
+          if (ncls < best) { best = ncls; pos[0] = a; pos[1] = b; pos[2] = c3; }
+          if (RBc < 3) break;
+        }
+    cx->rb[0] = pos[0]; cx->rb[1] = RBc >= 2 ? pos[1] : 0; cx->rb[2] = RBc >= 3 ? pos[2] : 0;
+    cx->num_classes = (int)best;
+  }
+  uint32_t regmask = 0;
+  for (int q = 0; q < cx->RB; ++q) regmask |= 1u << cx->rb[q];
+  auto compress = [&](uint32_t x) {   // register bits of x -> xh
+    uint32_t h = 0;
+    for (int q = 0; q < cx->RB; ++q) h |= ((x >> cx->rb[q]) & 1u) << q;
+    return h;
+  };
+  // order slices by class (x outside the register bits), then by xh
+  struct SliceRef { uint32_t x; int imag; const std::vector<std::pair<uint32_t, double>> *terms; };
+  std::vector<SliceRef> order;
+  for (auto &kv : slices) order.push_back({(uint32_t)kv.first.first, kv.first.second, &kv.second});
+  std::stable_sort(order.begin(), order.end(), [&](const SliceRef &a, const SliceRef &b) {
+    const uint32_t ca = a.x & ~regmask, cb = b.x & ~regmask;
+    if (ca != cb) return ca < cb;
+    return compress(a.x) < compress(b.x);
+  });
+  std::vector<uint32_t> sx, sdesc, tz;
   std::vector<int> sbegin;
   std::vector<double> tc;
-  for (auto &kv : slices) {
-    sx.push_back((uint32_t)kv.first.first);
-    simag.push_back((uint32_t)kv.first.second);
+  for (size_t si = 0; si < order.size(); ++si) {
+    const SliceRef &sr = order[si];
+    const uint32_t xrest = sr.x & ~regmask;
+    const bool newclass = si == 0 || (order[si - 1].x & ~regmask) != xrest;
+    sx.push_back(sr.x);
+    sdesc.push_back(xrest | (compress(sr.x) << 20) | (sr.imag ? QAS_SD_IMAG : 0u) | (newclass ? QAS_SD_NEWCLASS : 0u));
     sbegin.push_back((int)tz.size());
-    for (auto &zc : kv.second) { tz.push_back(zc.first); tc.push_back(zc.second); }
+    for (auto &zc : *sr.terms) { tz.push_back(zc.first); tc.push_back(zc.second); }
   }
   sbegin.push_back((int)tz.size());
   cx->S = (int)sx.size();
@@ -189,26 +255,26 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   guard(cudaEventCreate(&cx->ek1), "cudaEventCreate");
   guard(cudaMalloc(&cx->d_pool, sizeof(qas_pool_entry) * c), "cudaMalloc pool");
   guard(cudaMalloc(&cx->d_vtab, sizeof(double) * dim * cx->S), "cudaMalloc sign tables");
-  guard(cudaMalloc(&cx->d_sx, 4 * cx->S), "cudaMalloc sx");
-  guard(cudaMalloc(&cx->d_simag, 4 * cx->S), "cudaMalloc simag");
-  uint32_t *d_tz = nullptr; double *d_tc = nullptr; int *d_sbegin = nullptr;
+  guard(cudaMalloc(&cx->d_sdesc, 4 * cx->S), "cudaMalloc sdesc");
+  uint32_t *d_tz = nullptr, *d_sx = nullptr; double *d_tc = nullptr; int *d_sbegin = nullptr;
+  guard(cudaMalloc(&d_sx, 4 * cx->S), "cudaMalloc sx");
   guard(cudaMalloc(&d_tz, 4 * tz.size()), "cudaMalloc tz");
   guard(cudaMalloc(&d_tc, 8 * tc.size()), "cudaMalloc tc");
   guard(cudaMalloc(&d_sbegin, 4 * sbegin.size()), "cudaMalloc sbegin");
   if (rc == QAS_OK) {
     guard(cudaMemcpy(cx->d_pool, pool, sizeof(qas_pool_entry) * c, cudaMemcpyHostToDevice), "copy pool");
-    guard(cudaMemcpy(cx->d_sx, sx.data(), 4 * sx.size(), cudaMemcpyHostToDevice), "copy sx");
-    guard(cudaMemcpy(cx->d_simag, simag.data(), 4 * simag.size(), cudaMemcpyHostToDevice), "copy simag");
+    guard(cudaMemcpy(d_sx, sx.data(), 4 * sx.size(), cudaMemcpyHostToDevice), "copy sx");
+    guard(cudaMemcpy(cx->d_sdesc, sdesc.data(), 4 * sdesc.size(), cudaMemcpyHostToDevice), "copy sdesc");
     guard(cudaMemcpy(d_tz, tz.data(), 4 * tz.size(), cudaMemcpyHostToDevice), "copy tz");
     guard(cudaMemcpy(d_tc, tc.data(), 8 * tc.size(), cudaMemcpyHostToDevice), "copy tc");
     guard(cudaMemcpy(d_sbegin, sbegin.data(), 4 * sbegin.size(), cudaMemcpyHostToDevice), "copy sbegin");
     const size_t total = dim * cx->S;
     build_sign_tables_kernel<<<(unsigned)((total + 255) / 256), 256, 0, cx->stream>>>(
-        n_qubits, cx->S, cx->d_sx, d_sbegin, d_tz, d_tc, cx->d_vtab);
+        n_qubits, cx->S, cx->RB, cx->rb[0], cx->rb[1], cx->rb[2], d_sx, d_sbegin, d_tz, d_tc, cx->d_vtab);
     guard(cudaGetLastError(), "build_sign_tables launch");
     guard(cudaStreamSynchronize(cx->stream), "build_sign_tables");
   }
-  cudaFree(d_tz); cudaFree(d_tc); cudaFree(d_sbegin);
+  cudaFree(d_tz); cudaFree(d_tc); cudaFree(d_sbegin); cudaFree(d_sx);
   if (rc != QAS_OK) { qas_ctx_destroy(cx); return rc; }
   *out = cx;
   return QAS_OK;
@@ -217,10 +283,10 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
 extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   if (!ctx) return QAS_OK;
   cudaSetDevice(ctx->device);
-  cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sx); cudaFree(ctx->d_simag);
+  cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc);
   cudaFree(ctx->d_U); cudaFree(ctx->d_dU); cudaFree(ctx->d_k); cudaFree(ctx->d_params);
   cudaFree(ctx->d_energy); cudaFree(ctx->d_grad); cudaFree(ctx->d_partial); cudaFree(ctx->d_dense);
-  cudaFree(ctx->d_gstate);
+  cudaFree(ctx->d_gstate); cudaFree(ctx->d_tape);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ek0) cudaEventDestroy(ctx->ek0);
@@ -245,15 +311,12 @@ extern "C" int qas_get_stats(const qas_ctx *cctx, qas_stats *out) {
 }
 
 // ---------------------------------------------------------------------------------- launch
-constexpr int team_threads(int n) {
-  return n <= 4 ? 8 : n == 5 ? 16 : n <= 8 ? 32 : n == 9 ? 64 : n == 10 ? 128 : 256;
-}
+static size_t sdesc_bytes(int S) { return (((size_t)S * 4) + 15) & ~(size_t)15; }
 
-template <int N, bool GRAD>
+template <int N, int T, bool GRAD>
 static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t st) {
-  constexpr int T = team_threads(N);
   constexpr int TEAMS = 256 / T;
-  const size_t smem = eval_team_smem_bytes(N, T, GRAD, P.ops_cap, true) * TEAMS;
+  const size_t smem = eval_team_smem_bytes(N, T, GRAD, P.ops_cap, true, qas_stage_u(N)) * TEAMS + sdesc_bytes(P.S);
   auto kern = eval_kernel<N, T, GRAD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -271,7 +334,7 @@ static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t s
 
 template <bool GRAD>
 static cudaError_t launch_gmem(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
-  const size_t smem = eval_team_smem_bytes(P.n, 256, GRAD, P.ops_cap, false);
+  const size_t smem = eval_team_smem_bytes(P.n, 256, GRAD, P.ops_cap, false, true) + sdesc_bytes(P.S);
   auto kern = eval_kernel<0, 256, GRAD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -293,24 +356,25 @@ static cudaError_t launch_gmem(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// (N, T) instantiations: the default team size of each qubit count and its double
 template <bool GRAD>
 static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
   const int nmax_smem = GRAD ? 12 : 13;
+  const int T = ctx->T;
   if (P.n <= nmax_smem) {
-    // the tape must also fit next to the state; fall back to the global-memory path if not
-    const int T = team_threads(P.n);
-    const size_t smem = eval_team_smem_bytes(P.n, T, GRAD, P.ops_cap, true) * (256 / T);
+    const size_t smem = eval_team_smem_bytes(P.n, T, GRAD, P.ops_cap, true, qas_stage_u(P.n)) * (256 / T) + sdesc_bytes(P.S);
     if (smem <= 227 * 1024) {
-      switch (P.n) {
-#define QAS_CASE(N_) case N_: return launch_smem<N_, GRAD>(ctx, P, st);
-        QAS_CASE(2) QAS_CASE(3) QAS_CASE(4) QAS_CASE(5) QAS_CASE(6) QAS_CASE(7) QAS_CASE(8)
-        QAS_CASE(9) QAS_CASE(10) QAS_CASE(11) QAS_CASE(12)
+#define QAS_CASE(N_, T_) if (P.n == N_ && T == T_) return launch_smem<N_, T_, GRAD>(ctx, P, st);
+      QAS_CASE(2, 8) QAS_CASE(3, 8) QAS_CASE(4, 8) QAS_CASE(4, 16) QAS_CASE(5, 16) QAS_CASE(5, 32)
+      QAS_CASE(6, 32) QAS_CASE(6, 64) QAS_CASE(7, 32) QAS_CASE(7, 64) QAS_CASE(8, 32) QAS_CASE(8, 64)
+      QAS_CASE(9, 64) QAS_CASE(9, 128) QAS_CASE(10, 128) QAS_CASE(10, 256) QAS_CASE(11, 256)
+      QAS_CASE(12, 256)
 #undef QAS_CASE
-        case 13: if constexpr (!GRAD) return launch_smem<13, false>(ctx, P, st); break;
-        default: break;
-      }
+      if constexpr (!GRAD) { if (P.n == 13) return launch_smem<13, 256, false>(ctx, P, st); }
     }
   }
+  // the global-memory instantiation is compiled for 256-thread teams and 3 register bits
+  if (ctx->T != 256 || ctx->RB != qas_register_bits(20, 256)) return cudaErrorInvalidConfiguration;
   return launch_gmem<GRAD>(ctx, P, st);
 }
 
@@ -369,21 +433,28 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
 
   EvalParams P{};
   P.k = dk; P.pool = ctx->d_pool; P.U = ctx->d_U; P.dU = ctx->d_dU;
-  P.vtab = ctx->d_vtab; P.sx = ctx->d_sx; P.simag = ctx->d_simag;
+  P.vtab = ctx->d_vtab; P.sdesc = ctx->d_sdesc; P.rb0 = ctx->rb[0]; P.rb1 = ctx->rb[1]; P.rb2 = ctx->rb[2];
   P.energy = denergy; P.grad = dgrad; P.gstate = nullptr;
   P.init_basis = ctx->init_basis;
   P.B = B; P.p = p; P.c = c; P.l = l; P.n = ctx->n; P.S = ctx->S;
   P.ops_cap = std::max(1, p * ctx->max_expansion);
   P.init_kind = ctx->init_kind;
 
+  const size_t rec_words = QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS;
+  CK(ensure(&ctx->d_tape, &ctx->cap_tape, rec_words * (size_t)B));
+  P.tape = ctx->d_tape;
+
   if (!dev) CK(cudaEventRecord(ctx->ev0, st));
+  compile_tapes_kernel<<<(B + 127) / 128, 128, 0, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap,
+                                                         ctx->init_kind, ctx->init_basis, ctx->d_tape);
+  CK(cudaGetLastError());
   build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ek0, st));
   if (want_grad) CK(launch_eval<true>(ctx, P, st)); else CK(launch_eval<false>(ctx, P, st));
   CK(cudaEventRecord(ctx->ek1, st));
   ctx->ek_pending = true;
-  ctx->stats.launches += 2;
+  ctx->stats.launches += 3;
 
   if (grad_dense) {
     const int chunk = 128;

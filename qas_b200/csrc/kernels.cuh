@@ -26,12 +26,13 @@ struct EvalParams {
   const qas_pool_entry *pool;  // [c]
   const GateTab *U;            // [NCONST + p*c]
   const GateDTab *dU;          // [NCONST + p*c]
-  const double *vtab;          // [S][2^n] sign tables (one per slice)
-  const uint32_t *sx;          // [S] x mask of each slice
-  const uint32_t *simag;       // [S] 1 if the slice is the imaginary part (multiply by i)
+  const double *vtab;          // [S][2^RB][2^(n-RB)] sign tables, register-bit-major (see 3.3)
+  const uint32_t *sdesc;       // [S] slice descriptors: x_rest | xh<<20 | imag<<23 | newclass<<24
+  int rb0, rb1, rb2;           // ascending positions of the register bits of the H-apply blocking
   double *energy;              // [B]
   double *grad;                // [B][p][l] compact, may be null when !GRAD
   double2 *gstate;             // global-memory statevector scratch (path 1)
+  const uint32_t *tape;        // [B][4 + ops_cap*5] compiled tape records (compile_tapes_kernel)
   uint64_t init_basis;
   int B, p, c, l, n, S, ops_cap, init_kind;
 };
@@ -51,6 +52,14 @@ __device__ __forceinline__ double2 cmul_conj(double2 a, double2 b) {            
 }
 __device__ __forceinline__ uint32_t insert_zero(uint32_t t, int b) {
   return ((t >> b) << (b + 1)) | (t & ((1u << b) - 1u));
+}
+#ifndef QAS_RB_MAX
+#define QAS_RB_MAX 2     // at most 2^2 amplitudes per thread in the register-blocked H application
+#endif
+__host__ __device__ constexpr int qas_register_bits(int n, int T) {
+  int lt = 0;
+  while ((1 << lt) < T) ++lt;
+  return n - lt >= QAS_RB_MAX ? QAS_RB_MAX : (n - lt > 0 ? n - lt : 0);
 }
 __device__ __forceinline__ double shfl_xor_d(double v, int off) {
   return __shfl_xor_sync(0xffffffffu, v, off);
@@ -176,53 +185,140 @@ __global__ void build_gate_table_kernel(const qas_pool_entry *pool, int c, int p
 }
 
 // ------------------------------------------------------------------------------ sign tables
-// V_s[i] = sum_{t in slice s} c_t * (+-1 from i^{nY}) * (-1)^{popc((i ^ x) & z_t)}  so that
-// (H psi)[i] = sum_s (i if imag) V_s[i] psi[i ^ x_s].      terms sorted by slice on the host.
-__global__ void build_sign_tables_kernel(int n, int S, const uint32_t *sx, const int *sbegin,
-                                         const uint32_t *tz, const double *tc, double *vtab) {
+// H is grouped by X mask ("slice"):  (H psi)[i] = sum_s (i if imag) V_s[i] psi[i ^ x_s],
+// V_s[i] = sum_{t in slice s} c_t * (+-1 from i^{nY}) * (-1)^{popc((i ^ x_s) & z_t)}.
+// Blocking of the H application: every thread owns 2^RB amplitudes that differ only in RB
+// "register bits" (positions rb0<rb1<rb2, chosen per Hamiltonian on the host so that as many X
+// masks as possible differ only inside them).  Slices whose X masks agree outside the register
+// bits form a class: the thread loads the 2^RB partner amplitudes ONCE per class and serves
+// every slice of the class from registers (partner j ^ xh).  The tables are stored
+// register-bit-major, vtab[s][j][u] with i = deposit(u) | spread(j), so that for fixed (s, j)
+// consecutive threads read consecutive doubles.
+#define QAS_SD_XREST 0xfffffu
+#define QAS_SD_XH(d) (((d) >> 20) & 7u)
+#define QAS_SD_IMAG (1u << 23)
+#define QAS_SD_NEWCLASS (1u << 24)
+
+__host__ __device__ __forceinline__ uint32_t qas_insert_zero(uint32_t t, int b) {
+  return ((t >> b) << (b + 1)) | (t & ((1u << b) - 1u));
+}
+__host__ __device__ __forceinline__ uint32_t qas_deposit_rest(uint32_t u, int RB, int rb0, int rb1, int rb2) {
+  if (RB >= 1) u = qas_insert_zero(u, rb0);
+  if (RB >= 2) u = qas_insert_zero(u, rb1);
+  if (RB >= 3) u = qas_insert_zero(u, rb2);
+  return u;
+}
+__host__ __device__ __forceinline__ uint32_t qas_spread_reg(uint32_t j, int rb0, int rb1, int rb2) {
+  return ((j & 1u) << rb0) | (((j >> 1) & 1u) << rb1) | (((j >> 2) & 1u) << rb2);
+}
+
+__global__ void build_sign_tables_kernel(int n, int S, int RB, int rb0, int rb1, int rb2,
+                                         const uint32_t *sx, const int *sbegin, const uint32_t *tz,
+                                         const double *tc, double *vtab) {
   const size_t dim = (size_t)1 << n;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= dim * (size_t)S) return;
   const int s = (int)(idx >> n);
-  const uint32_t i = (uint32_t)(idx & (dim - 1));
+  const uint32_t e = (uint32_t)(idx & (dim - 1));
+  const uint32_t u = e & ((1u << (n - RB)) - 1u), jj = e >> (n - RB);
+  const uint32_t i = qas_deposit_rest(u, RB, rb0, rb1, rb2) | qas_spread_reg(jj, rb0, rb1, rb2);
   const uint32_t j = i ^ sx[s];
   double v = 0.0;
   for (int t = sbegin[s]; t < sbegin[s + 1]; ++t) v += (__popc(j & tz[t]) & 1) ? -tc[t] : tc[t];
   vtab[idx] = v;
 }
 
+// acc[j] += (i if imag) V[j] * a[j ^ XH]   for the 2^RB amplitudes a thread owns
+template <int NB, int XH>
+__device__ __forceinline__ void hacc(double2 (&acc)[NB], const double2 (&a)[NB], const double (&v)[NB],
+                                     bool imag) {
+  if (!imag) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      acc[j].x = fma(v[j], a[(j ^ XH) & (NB - 1)].x, acc[j].x);
+      acc[j].y = fma(v[j], a[(j ^ XH) & (NB - 1)].y, acc[j].y);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      acc[j].x = fma(-v[j], a[(j ^ XH) & (NB - 1)].y, acc[j].x);
+      acc[j].y = fma(v[j], a[(j ^ XH) & (NB - 1)].x, acc[j].y);
+    }
+  }
+}
+template <int NB>
+__device__ __forceinline__ void hacc_dispatch(double2 (&acc)[NB], const double2 (&a)[NB],
+                                              const double (&v)[NB], uint32_t xh, bool imag) {
+  switch (xh) {
+    case 0: hacc<NB, 0>(acc, a, v, imag); break;
+    case 1: if constexpr (NB > 1) hacc<NB, 1>(acc, a, v, imag); break;
+    case 2: if constexpr (NB > 2) hacc<NB, 2>(acc, a, v, imag); break;
+    case 3: if constexpr (NB > 2) hacc<NB, 3>(acc, a, v, imag); break;
+    case 4: if constexpr (NB > 4) hacc<NB, 4>(acc, a, v, imag); break;
+    case 5: if constexpr (NB > 4) hacc<NB, 5>(acc, a, v, imag); break;
+    case 6: if constexpr (NB > 4) hacc<NB, 6>(acc, a, v, imag); break;
+    default: if constexpr (NB > 4) hacc<NB, 7>(acc, a, v, imag); break;
+  }
+}
+
+// ------------------------------------------------------------------------------ tape compile
+// One thread per circuit: runs the tape compiler (tape.h) and writes a record
+//   [nops, status, init_index, n1q | ops[ops_cap][5]]   (uint32)
+// to global memory.  Doing this in its own launch (B-way parallel) keeps the serial GF(2)
+// frame walk out of the evaluation teams' critical path; the records stay L2-resident.
+#define QAS_REC_HDR 4
+__global__ void compile_tapes_kernel(const int32_t *k, const qas_pool_entry *pool, int B, int p, int c,
+                                     int n, int ops_cap, int init_kind, uint64_t init_basis,
+                                     uint32_t *tape) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  uint32_t col[32], row[32];
+  uint32_t *rec = tape + (size_t)b * (QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS);
+  QasTapeSink sink{rec + QAS_REC_HDR, ops_cap, 0, 0};
+  const int st = qas_compile_circuit(k + (size_t)b * p, p, pool, c, n, col, row, sink);
+  rec[0] = st ? 0u : (uint32_t)sink.n;
+  rec[1] = (uint32_t)st;
+  rec[2] = (init_kind == QAS_INIT_BASIS && !st) ? qas_frame_map_basis(col, n, init_basis) : 0u;
+  rec[3] = 0u;
+}
+
 // ------------------------------------------------------------------------------ evaluation
 // shared-memory layout per team (bytes, all 16-aligned):
-//   psi  [DIM] double2 | lam [DIM] double2 (GRAD) | ops [ops_cap][5] u32 | red [2][WPT][8] f64
-//   | ered [WPT] f64 | col [32] u32 | row [32] u32 | meta [4] i32
+//   psi [DIM] double2 | lam [DIM] double2 (GRAD) | rec [4 + ops_cap*5] u32
+//   | Us [ops_cap][4] double2 (STAGE_U) | red [2][WPT][8] f64 | ered [WPT] f64
+__host__ __device__ constexpr bool qas_stage_u(int N) { return N == 0 || N >= 9; }
 __host__ __device__ inline size_t eval_team_smem_bytes(int n, int T, bool grad, int ops_cap,
-                                                       bool state_in_smem) {
+                                                       bool state_in_smem, bool stage_u) {
   const size_t dim = (size_t)1 << n;
   const int wpt = T >= 32 ? T / 32 : 1;
   size_t b = 0;
   if (state_in_smem) b += dim * 16 * (grad ? 2 : 1);
-  b += (((size_t)ops_cap * QAS_OP_WORDS * 4) + 15) & ~(size_t)15;
+  b += (((size_t)(QAS_REC_HDR + ops_cap * QAS_OP_WORDS) * 4) + 15) & ~(size_t)15;
+  if (stage_u) b += (size_t)ops_cap * 64;
   b += (size_t)2 * wpt * 8 * 8;
   b += (((size_t)wpt * 8) + 15) & ~(size_t)15;
-  b += 32 * 4 * 2;
-  b += 16;
   return b;
 }
 
 // N > 0: compile-time qubit count, state in shared memory.  N == 0: run-time qubit count,
 // state in global memory (one team per CTA, L2/HBM resident) -- same code path otherwise.
+#ifndef QAS_MIN_CTAS
+#define QAS_MIN_CTAS 3
+#endif
 template <int N, int T, bool GRAD>
-__global__ void __launch_bounds__(256) eval_kernel(const EvalParams P) {
+__global__ void __launch_bounds__(256, QAS_MIN_CTAS) eval_kernel(const EvalParams P) {
   constexpr int TEAMS = 256 / T;
   constexpr int WPT = T >= 32 ? T / 32 : 1;      // warps per team
   constexpr int TW = T >= 32 ? 32 : T;           // lanes of one warp that belong to the team
+  constexpr int RB = qas_register_bits(N == 0 ? 20 : N, T);   // register bits of the H blocking
+  constexpr bool STAGE_U = qas_stage_u(N);
   const int n = N ? N : P.n;
   const uint32_t DIM = 1u << n, HALF = DIM >> 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
   const int team = threadIdx.x / T, tid = threadIdx.x % T;
   const int lane = threadIdx.x & 31, warp_in_team = tid >> 5;
-  const size_t team_bytes = eval_team_smem_bytes(n, T, GRAD, P.ops_cap, N != 0);
+  const size_t team_bytes = eval_team_smem_bytes(n, T, GRAD, P.ops_cap, N != 0, STAGE_U);
   unsigned char *base = smem_raw + (size_t)team * team_bytes;
   double2 *psi, *lam = nullptr;
   if constexpr (N != 0) {
@@ -233,43 +329,41 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams P) {
     psi = P.gstate + (size_t)blockIdx.x * DIM * (GRAD ? 2 : 1);
     if constexpr (GRAD) lam = psi + DIM;
   }
-  uint32_t *ops = reinterpret_cast<uint32_t *>(base);
-  base += (((size_t)P.ops_cap * QAS_OP_WORDS * 4) + 15) & ~(size_t)15;
+  const int rec_words = QAS_REC_HDR + P.ops_cap * QAS_OP_WORDS;
+  uint32_t *rec = reinterpret_cast<uint32_t *>(base);
+  uint32_t *ops = rec + QAS_REC_HDR;
+  base += (((size_t)rec_words * 4) + 15) & ~(size_t)15;
+  double2 *Us = reinterpret_cast<double2 *>(base);
+  if constexpr (STAGE_U) base += (size_t)P.ops_cap * 64;
   double *red = reinterpret_cast<double *>(base);
   base += (size_t)2 * WPT * 8 * 8;
   double *ered = reinterpret_cast<double *>(base);
-  base += (((size_t)WPT * 8) + 15) & ~(size_t)15;
-  uint32_t *col = reinterpret_cast<uint32_t *>(base);
-  uint32_t *row = col + 32;
-  int *meta = reinterpret_cast<int *>(row + 32);   // [0]=nops [1]=status [2]=init index
+  // slice descriptors, shared by the CTA's teams
+  uint32_t *sdesc = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TEAMS * team_bytes);
+  for (int s = threadIdx.x; s < P.S; s += 256) sdesc[s] = P.sdesc[s];
+  __syncthreads();
 
   for (int b0 = blockIdx.x * TEAMS; b0 < P.B; b0 += gridDim.x * TEAMS) {
     const int b = b0 + team;
     const bool active = b < P.B;
     if constexpr (T > 32) { if (!active) continue; }   // whole warps: nobody else waits on them
 
-    // ---- 1. tape compile (one lane per team) + zero the state / the gradient row
-    if (tid == 0) {
-      int st = 0, no = 0;
-      uint32_t init_idx = 0;
-      if (active) {
-        QasTapeSink sink{ops, P.ops_cap, 0, 0};
-        st = qas_compile_circuit(P.k + (size_t)b * P.p, P.p, P.pool, P.c, n, col, row, sink);
-        no = st ? 0 : sink.n;
-        if (P.init_kind == QAS_INIT_BASIS) init_idx = qas_frame_map_basis(col, n, P.init_basis);
-      }
-      meta[0] = no; meta[1] = st; meta[2] = (int)init_idx;
-    }
+    // ---- 1. fetch the compiled tape record, zero the state / the gradient row
     {
+      const uint32_t *grec = P.tape + (size_t)(active ? b : 0) * rec_words;
+      for (int w = tid; w < rec_words; w += T) rec[w] = active ? grec[w] : 0u;
       const double amp0 = (P.init_kind == QAS_INIT_PLUS) ? exp2(-0.5 * (double)n) : 0.0;
       for (uint32_t i = tid; i < DIM; i += T) psi[i] = make_double2(amp0, 0.0);
       if (GRAD && active)
         for (int i = tid; i < P.p * P.l; i += T) P.grad[(size_t)b * P.p * P.l + i] = 0.0;
     }
     team_sync<T>(team);
-    const int nops = meta[0];
-    const int status = meta[1];
-    if (tid == 0 && P.init_kind != QAS_INIT_PLUS) psi[(uint32_t)meta[2]] = make_double2(1.0, 0.0);
+    const int nops = (int)rec[0];
+    const int status = (int)rec[1];
+    if (tid == 0 && P.init_kind != QAS_INIT_PLUS) psi[rec[2]] = make_double2(1.0, 0.0);
+    if constexpr (STAGE_U) {   // gate matrices of this circuit -> shared memory (one round trip)
+      for (int w = tid; w < nops * 4; w += T) Us[w] = P.U[ops[(w >> 2) * QAS_OP_WORDS + 3]].u[w & 3];
+    }
     int nloop = nops;
     if constexpr (T < 32) nloop = __reduce_max_sync(0xffffffffu, nops);
     team_sync<T>(team);
@@ -280,9 +374,9 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams P) {
       if (j >= 0) {
         const uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
         const uint32_t m = o[0], r = o[1], rc = o[2];
-        const GateTab *g = P.U + o[3];
+        const double2 *g = STAGE_U ? (Us + 4 * j) : P.U[o[3]].u;
         if (qas_meta_kind(o[4]) == QAS_K_U1) {
-          const double2 u00 = g->u[0], u01 = g->u[1], u10 = g->u[2], u11 = g->u[3];
+          const double2 u00 = g[0], u01 = g[1], u10 = g[2], u11 = g[3];
           const int pb = 31 - __clz(r);
 #pragma unroll 4
           for (uint32_t t = tid; t < HALF; t += T) {
@@ -295,7 +389,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams P) {
             psi[p1] = cfma(u11, a1, cmul(u10, a0));
           }
         } else {
-          const double2 d0 = g->u[0], d1 = g->u[3];
+          const double2 d0 = g[0], d1 = g[3];
 #pragma unroll 4
           for (uint32_t i = tid; i < DIM; i += T)
             psi[i] = cmul((__popc(i & r) & 1) ? d1 : d0, psi[i]);
@@ -304,20 +398,49 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams P) {
       team_sync<T>(team);
     }
 
-    // ---- 3. lambda = H psi, E = Re <psi|lambda>
+    // ---- 3. lambda = H psi, E = Re <psi|lambda>   (register-blocked over X-mask classes)
     double e_part = 0.0;
-    for (uint32_t i = tid; i < DIM; i += T) {
-      double2 acc = make_double2(0.0, 0.0);
-      const double *vt = P.vtab + i;
-      for (int s = 0; s < P.S; ++s) {
-        const double v = __ldg(vt + ((size_t)s << n));
-        const double2 a = psi[i ^ P.sx[s]];
-        if (P.simag[s]) { acc.x = fma(-v, a.y, acc.x); acc.y = fma(v, a.x, acc.y); }
-        else            { acc.x = fma(v, a.x, acc.x);  acc.y = fma(v, a.y, acc.y); }
+    {
+      constexpr int NB = 1 << RB;
+      const uint32_t nrest = DIM >> RB;
+      uint32_t roff[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) roff[j] = qas_spread_reg((uint32_t)j, P.rb0, P.rb1, P.rb2);
+      for (uint32_t u = tid; u < nrest; u += T) {
+        const uint32_t base_i = qas_deposit_rest(u, RB, P.rb0, P.rb1, P.rb2);
+        double2 acc[NB], a[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) { acc[j] = make_double2(0.0, 0.0); a[j] = acc[j]; }
+        // sign-table values are prefetched one slice ahead (L2 latency ~300 cycles)
+        const double *vp = P.vtab + u;
+        double vn[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) vn[j] = __ldg(vp + (size_t)j * nrest);
+        for (int s = 0; s < P.S; ++s) {
+          const uint32_t d = sdesc[s];
+          double v[NB];
+#pragma unroll
+          for (int j = 0; j < NB; ++j) v[j] = vn[j];
+          if (s + 1 < P.S) {
+            const double *vq = vp + ((size_t)(s + 1) << n);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) vn[j] = __ldg(vq + (size_t)j * nrest);
+          }
+          if (d & QAS_SD_NEWCLASS) {
+            const uint32_t pb = base_i ^ (d & QAS_SD_XREST);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) a[j] = psi[pb | roff[j]];
+          }
+          hacc_dispatch<NB>(acc, a, v, QAS_SD_XH(d), (d & QAS_SD_IMAG) != 0);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const uint32_t i = base_i | roff[j];
+          const double2 ai = psi[i];
+          e_part = fma(ai.x, acc[j].x, fma(ai.y, acc[j].y, e_part));
+          if constexpr (GRAD) lam[i] = acc[j];
+        }
       }
-      const double2 a = psi[i];
-      e_part = fma(a.x, acc.x, fma(a.y, acc.y, e_part));
-      if constexpr (GRAD) lam[i] = acc;
     }
 #pragma unroll
     for (int off = TW / 2; off > 0; off >>= 1) e_part += shfl_xor_d(e_part, off);
@@ -342,13 +465,23 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams P) {
         const uint32_t *o = ops + (size_t)(live ? it : 0) * QAS_OP_WORDS;
         const uint32_t m = o[0], r = o[1], rc = o[2], tab = o[3], mt = o[4];
         const int npar = live ? qas_meta_npar(mt) : 0;
+        // lanes of the team's first warp prefetch dU/dtheta entries: lane l holds (dU_j)_{l%4} with
+        // j = l/4 (teams of >= 16 lanes) or j = round (8-lane teams); the load overlaps the pair loop
+        constexpr int ROUNDS = T >= 16 ? 1 : 3;
+        double2 dpre[ROUNDS];
+#pragma unroll
+        for (int rr = 0; rr < ROUNDS; ++rr) {
+          const int jj = T >= 16 ? (tid >> 2) : rr;
+          const bool valid = T >= 16 ? (tid < 4 * npar) : (tid < 4 && rr < npar);
+          dpre[rr] = valid ? P.dU[tab].d[jj][tid & 3] : make_double2(0.0, 0.0);
+        }
         double acc[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] = 0.0;
         if (live) {
-          const GateTab *g = P.U + tab;
+          const double2 *g = STAGE_U ? (Us + 4 * it) : P.U[tab].u;
           if (qas_meta_kind(mt) == QAS_K_U1) {
-            const double2 u00 = g->u[0], u01 = g->u[1], u10 = g->u[2], u11 = g->u[3];
+            const double2 u00 = g[0], u01 = g[1], u10 = g[2], u11 = g[3];
             const int pb = 31 - __clz(r);
 #pragma unroll 2
             for (uint32_t t = tid; t < HALF; t += T) {
@@ -372,7 +505,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams P) {
               lam[p1] = cfma_conj(u11, l1, cmul_conj(u01, l0));
             }
           } else {
-            const double2 d0 = g->u[0], d1 = g->u[3];
+            const double2 d0 = g[0], d1 = g[3];
 #pragma unroll 2
             for (uint32_t i = tid; i < DIM; i += T) {
               const bool hi = __popc(i & r) & 1;
@@ -415,23 +548,31 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvalParams P) {
           }
         }
         team_sync<T>(team);
-        if (tid < npar && active && !status) {
-          double mm[8];
+        // gradient of this gate: lane l = 4j+q contributes Re[(dU_j)_q * M_q]; 4-lane shuffle sum.
+        // (for T < 32 every lane of the warp takes part in the shuffles; only lanes tid < 12 count)
+        bool fin = npar > 0;
+        if constexpr (T < 32) fin = __any_sync(0xffffffffu, fin); else fin = fin && (tid < 32);
+        if (fin) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            double sacc = 0.0;
+          for (int rr = 0; rr < ROUNDS; ++rr) {
+            const int jj = T >= 16 ? (tid >> 2) : rr;
+            const bool valid = T >= 16 ? (tid < 4 * npar) : (tid < 4 && rr < npar);
+            double part = 0.0;
+            if (valid) {
+              const int q = tid & 3;
+              double mre = 0.0, mim = 0.0;
 #pragma unroll
-            for (int w = 0; w < WPT; ++w) sacc += red[((it & 1) * WPT + w) * 8 + q];
-            mm[q] = sacc;
+              for (int w = 0; w < WPT; ++w) {
+                mre += red[((it & 1) * WPT + w) * 8 + 2 * q];
+                mim += red[((it & 1) * WPT + w) * 8 + 2 * q + 1];
+              }
+              part = dpre[rr].x * mre - dpre[rr].y * mim;
+            }
+            part += shfl_xor_d(part, 1);
+            part += shfl_xor_d(part, 2);
+            if (valid && (tid & 3) == 0 && active && !status)
+              P.grad[((size_t)b * P.p + qas_meta_depth(mt)) * P.l + jj] = 2.0 * part;
           }
-          const GateDTab *dg = P.dU + tab;
-          double gsum = 0.0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double2 dv = dg->d[tid][q];
-            gsum += dv.x * mm[2 * q] - dv.y * mm[2 * q + 1];
-          }
-          P.grad[((size_t)b * P.p + qas_meta_depth(mt)) * P.l + tid] = 2.0 * gsum;
         }
       }
     }
