@@ -62,6 +62,22 @@ class HamiltonianModel(ModelFromK):
         return cls.evaluator(op_pool, l).evaluate(ks, super_circ_params, want_grad=want_grad,
                                                   dense=True, compact=compact, avg=avg)
 
+    @classmethod
+    def evaluate_batch_sharded(cls, ks, super_circ_params, op_pool, want_grad=True, avg=True, group=None):
+        """Multi-GPU form of evaluate_batch: every rank passes the same global batch, evaluates its
+        own shard on its own GPU and the rewards / gradient are combined over NCCL
+        (qas_b200/distributed.py).  Needs an initialised torch.distributed process group."""
+        import torch
+        from qas_b200.distributed import evaluate_sharded
+        dev = default_device()
+
+        def local(ks_local, params, avg=False):
+            return cls.evaluator(op_pool, np.shape(params)[2], dev).evaluate(
+                ks_local, params, want_grad=want_grad, dense=True, avg=avg)
+
+        return evaluate_sharded(local, ks, super_circ_params, op_pool, want_grad=want_grad, avg=avg,
+                                group=group, device=torch.device("cuda", dev))
+
     def _check(self, super_circ_params):
         assert super_circ_params.shape[0] == self.p
         assert super_circ_params.shape[1] == self.c
