@@ -263,3 +263,50 @@ def hamiltonian_matrix(n, terms):
             m = np.kron(m, _PAULI[ch])
         h += coeff * m
     return h
+
+
+# ----------------------------------------------------------------------------- large registers
+def run_flat(n, gate_list, init=("zero", 0)):
+    """Same evolution as `run`, on a flat 2^n vector with strided views (no tensordot copies);
+    used to check the large-state mode at 20-24 qubits in reasonable time."""
+    kind, arg = init
+    if kind == "plus":
+        st = np.full(2 ** n, 2.0 ** (-0.5 * n), dtype=np.complex128)
+    else:
+        st = np.zeros(2 ** n, dtype=np.complex128)
+        st[arg if kind == "basis" else 0] = 1.0
+    for name, wires, theta in gate_list:
+        m = G.matrix(name, theta or ())
+        if len(wires) == 1:
+            b = n - 1 - wires[0]
+            v = st.reshape(-1, 2, 1 << b)
+            a0, a1 = v[:, 0, :].copy(), v[:, 1, :]
+            v[:, 0, :] = m[0, 0] * a0 + m[0, 1] * a1
+            v[:, 1, :] = m[1, 0] * a0 + m[1, 1] * a1
+        elif name in ("CNOT", "CZ", "CY", "CRX", "CRY", "CRZ", "CRot", "CPhase", "ControlledPhaseShift"):
+            u = m[2:, 2:]
+            bc, bt = n - 1 - wires[0], n - 1 - wires[1]
+            hi, lo = max(bc, bt), min(bc, bt)
+            v = st.reshape(-1, 2, 1 << (hi - lo - 1), 2, 1 << lo)
+            if bc == hi:
+                sub0, sub1 = v[:, 1, :, 0, :], v[:, 1, :, 1, :]
+            else:
+                sub0, sub1 = v[:, 0, :, 1, :], v[:, 1, :, 1, :]
+            a0, a1 = sub0.copy(), sub1.copy()
+            sub0[...] = u[0, 0] * a0 + u[0, 1] * a1
+            sub1[...] = u[1, 0] * a0 + u[1, 1] * a1
+        else:
+            st = apply_matrix(st.reshape([2] * n), m, wires).reshape(-1)
+    return st
+
+
+def expval_diag_zz_chain(st, n):
+    """<sum_i Z_i Z_{i+1}> on a flat vector (wire 0 = MSB)."""
+    p = np.abs(st) ** 2
+    idx = np.arange(st.size, dtype=np.int64)
+    e = 0.0
+    for i in range(n - 1):
+        b0, b1 = n - 1 - i, n - 2 - i
+        sign = 1.0 - 2.0 * (((idx >> b0) ^ (idx >> b1)) & 1)
+        e += float(np.dot(p, sign))
+    return e

@@ -52,6 +52,19 @@ class Stats(ctypes.Structure):
                 ("smem_bytes_per_cta", ctypes.c_int), ("path", ctypes.c_int)]
 
 
+class SvGate(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("target", ctypes.c_int32), ("control", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("mask", ctypes.c_uint64), ("m", ctypes.c_double * 8)]
+
+
+class SvInfo(ctypes.Structure):
+    _fields_ = [("passes", ctypes.c_int), ("tile_bits", ctypes.c_int), ("bytes_per_pass", ctypes.c_double),
+                ("last_ms", ctypes.c_double)]
+
+
+QAS_SV_U1 = 0
+QAS_SV_PDIAG = 1
+
 _lib = None
 
 # every symbol include/qas_b200.h declares (tests check the export list against this)
@@ -60,6 +73,8 @@ EXPORTS = [
     "qas_eval_batch", "qas_compile_tape", "qas_compile_tape_host", "qas_get_stats",
     "qas_fp64_peak_tflops",
 ]
+# include/qas_b200_sv.h
+SV_EXPORTS = ["qas_sv_init", "qas_sv_apply", "qas_sv_plan", "qas_sv_expval", "qas_sv_norm2", "qas_sv_last_error"]
 
 
 def load():
@@ -98,5 +113,20 @@ def load():
     lib.qas_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.qas_fp64_peak_tflops.restype = ctypes.c_int
     lib.qas_fp64_peak_tflops.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    lib.qas_sv_last_error.restype = ctypes.c_char_p
+    lib.qas_sv_init.restype = ctypes.c_int
+    lib.qas_sv_init.argtypes = [vp, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_double, vp]
+    lib.qas_sv_apply.restype = ctypes.c_int
+    lib.qas_sv_apply.argtypes = [vp, ctypes.c_int, ctypes.POINTER(SvGate), ctypes.c_int, ctypes.c_int, vp,
+                                 ctypes.c_int, ctypes.POINTER(SvInfo)]
+    lib.qas_sv_plan.restype = ctypes.c_int
+    lib.qas_sv_plan.argtypes = [ctypes.c_int, ctypes.POINTER(SvGate), ctypes.c_int, ctypes.c_int,
+                                ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
+    lib.qas_sv_expval.restype = ctypes.c_int
+    lib.qas_sv_expval.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(PauliTerm),
+                                  ctypes.c_int, ctypes.POINTER(ctypes.c_double), vp]
+    lib.qas_sv_norm2.restype = ctypes.c_int
+    lib.qas_sv_norm2.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), vp]
     _lib = lib
     return lib

@@ -28,6 +28,11 @@ def test_library_loads_and_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     assert declared == set(_lib.EXPORTS)
+    header_sv = open(os.path.join(os.path.dirname(_lib.LIB_PATH), "..", "..", "include", "qas_b200_sv.h")).read()
+    declared_sv = set(re.findall(r"\b(qas_sv_[a-z0-9_]+)\s*\(", header_sv))
+    for sym in declared_sv:
+        assert hasattr(lib, sym), sym
+    assert declared_sv == set(_lib.SV_EXPORTS)
 
 
 def test_gate_id_table_matches_header():
