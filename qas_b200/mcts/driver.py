@@ -1,0 +1,201 @@
+"""Epoch loop of the circuit search and the fine-tuning loop, on the batched evaluator.
+
+``search`` and ``circuitModelTuning`` accept exactly the keyword arguments of the reference
+functions (qas/mcts/mcts.py:216-250 and :381-392; every experiment script calls them by keyword)
+and return the same tuples.  Epoch structure (reference :284-376):
+
+  warm-up epoch   sample ``warmup_arc_batchsize`` uniformly random legal arcs, reward each, discard
+                  the tree if ``warm_up_reset``;
+  search epoch    reset / decay alpha / ramp the prune ratio, then ``search_arc_batchsize`` times:
+                  grow the tree by ``sampling_execute_rounds`` rollouts, descend greedily, reward;
+  both            gradient of every sampled arc w.r.t. the shared parameters -> nan_to_num ->
+                  mean (or sum) -> + Gaussian noise -> one optimiser step -> exploit the tree for
+                  the current best arc -> early stopping on the mean of the last penalised rewards.
+
+Differences, all result-preserving: the gradient batch is one
+``evaluate_batch`` launch instead of a Python loop over models (:340-347); warm-up rewards are
+computed in one launch after all arcs are drawn (``randomSample`` never looks at rewards, :107-114);
+rewards are cached per structure list while the parameters are unchanged.
+"""
+import time
+from dataclasses import dataclass, fields
+from typing import Any, Callable, Optional, Set
+
+import numpy as np
+
+from qas_b200.mcts.tree import MCTSController
+from qas_b200.optim import AdamOptimizer
+
+
+@dataclass
+class SearchConfig:
+    """Keyword arguments of ``search`` with the reference's defaults."""
+    model: Any = None
+    op_pool: Any = None
+    target_circuit_depth: int = None
+    init_qubit_with_controls: Optional[Set] = None
+    init_params: Any = None
+    state_class: Any = None
+    num_iterations: int = 500
+    num_warmup_iterations: int = 20
+    warm_up_reset: bool = True
+    super_circ_train_optimizer: Any = AdamOptimizer
+    early_stop_threshold: float = 0.95
+    early_stop_lookback_count: int = 5
+    super_circ_train_gradient_noise_factor: float = 0.
+    super_circ_train_lr: float = 0.01
+    penalty_function: Optional[Callable] = None
+    gate_limit_dict: Optional[dict] = None
+    warmup_arc_batchsize: int = 200
+    search_arc_batchsize: int = 20
+    alpha_max: float = 2
+    alpha_decay_rate: float = 0.95
+    prune_constant_max: float = 0.9
+    prune_constant_min: float = 0.2
+    max_visits_prune_threshold: int = 100
+    min_num_children: int = 5
+    sampling_execute_rounds: int = 200
+    exploit_execute_rounds: int = 200
+    cmab_sample_policy: str = 'local_optimal'
+    cmab_exploit_policy: str = 'local_optimal'
+    uct_sample_policy: str = 'local_optimal'
+    verbose: int = 1
+    search_reset: bool = True
+    prune: bool = True
+    avg_gradients: bool = True
+
+    @classmethod
+    def from_call(cls, args, kwargs):
+        names = [f.name for f in fields(cls)]
+        if len(args) > len(names):
+            raise TypeError("search() takes at most %d positional arguments" % len(names))
+        merged = dict(zip(names, args))
+        for key, value in kwargs.items():
+            if key not in names:
+                raise TypeError("search() got an unexpected keyword argument %r" % key)
+            if key in merged:
+                raise TypeError("search() got multiple values for argument %r" % key)
+            merged[key] = value
+        return cls(**merged)
+
+
+def batchGradient(model, arcs, params, op_pool, avg_gradients=True):
+    """nan_to_num'ed mean (or sum) of the arcs' gradients: one launch for evaluator-backed models,
+    the reference's per-model loop otherwise."""
+    if hasattr(model, "evaluate_batch"):
+        ks = np.asarray(arcs, dtype=np.int32)
+        return model.evaluate_batch(ks, params, op_pool, want_grad=True, avg=avg_gradients)["grad_dense"]
+    p, c, l = params.shape
+    stack = np.nan_to_num(np.stack([model(p, c, l, k, op_pool).getGradient(params) for k in arcs]))
+    return stack.mean(axis=0) if avg_gradients else stack.sum(axis=0)
+
+
+def _penalised(cfg, reward, node):
+    return reward if cfg.penalty_function is None else cfg.penalty_function(reward, node)
+
+
+def _warmup_epoch(cfg, controller, params):
+    drawn = [controller.randomSample() for _ in range(cfg.warmup_arc_batchsize)]
+    arcs = [k for k, _ in drawn]
+    for (k, node), reward in zip(drawn, controller.batchRewards(arcs, params)):
+        controller.backPropagate(node, _penalised(cfg, reward, node))
+    if cfg.warm_up_reset:
+        controller._reset()
+    return arcs
+
+
+def _search_epoch(cfg, controller, params, epoch):
+    if cfg.search_reset:
+        controller._reset()
+    controller.alpha *= cfg.alpha_decay_rate
+    span = cfg.num_iterations - cfg.num_warmup_iterations
+    done = epoch + 1 - cfg.num_warmup_iterations
+    controller.prune_reward_ratio = cfg.prune_constant_min + (cfg.prune_constant_max - cfg.prune_constant_min) / span * done
+    arcs = []
+    for _ in range(cfg.search_arc_batchsize):
+        k, node = controller.sampleArcWithSuperCircParams(params)
+        arcs.append(k)
+        reward = controller.simulationWithSuperCircuitParamsAndK(k, params)
+        controller.backPropagate(node, _penalised(cfg, reward, node))
+    return arcs
+
+
+def search(*args, **kwargs):
+    cfg = SearchConfig.from_call(args, kwargs)
+    model, pool = cfg.model, cfg.op_pool
+    p, c, l = cfg.target_circuit_depth, len(pool), cfg.init_params.shape[2]
+    assert p == cfg.init_params.shape[0]
+    assert c == cfg.init_params.shape[1]
+    assert cfg.prune_constant_min <= cfg.prune_constant_max
+    controller = MCTSController(
+        model=model, op_pool=pool, target_circuit_depth=p, state_class=cfg.state_class,
+        reward_penalty_function=cfg.penalty_function,
+        initial_legal_control_qubit_choice=cfg.init_qubit_with_controls, alpha=cfg.alpha_max,
+        prune_reward_ratio=cfg.prune_constant_min, max_visits_prune_threshold=cfg.max_visits_prune_threshold,
+        min_num_children=cfg.min_num_children, sampling_execute_rounds=cfg.sampling_execute_rounds,
+        exploit_execute_rounds=cfg.exploit_execute_rounds, sample_policy=cfg.cmab_sample_policy,
+        exploit_policy=cfg.cmab_exploit_policy, gate_limit_dict=cfg.gate_limit_dict, prune=cfg.prune)
+    controller.setRoot()
+    params = np.array(cfg.init_params, dtype=np.float64)
+    optimizer = cfg.super_circ_train_optimizer(cfg.super_circ_train_lr)
+    log = print if cfg.verbose >= 1 else (lambda *a, **k: None)
+    history, recent = [], []
+    best_arc = best_node = best_reward = None
+    for epoch in range(cfg.num_iterations):
+        t0 = time.time()
+        controller.clearRewardCache()
+        warm = epoch < cfg.num_warmup_iterations
+        log("[%s] epoch %d/%d (%s): pool %d, batch %d" % (
+            model.name, epoch + 1, cfg.num_iterations, "warm-up" if warm else "search", c,
+            cfg.warmup_arc_batchsize if warm else cfg.search_arc_batchsize))
+        arcs = _warmup_epoch(cfg, controller, params) if warm else _search_epoch(cfg, controller, params, epoch)
+        grad = batchGradient(model, arcs, params, pool, cfg.avg_gradients)
+        grad = grad + np.random.randn(p, c, l) * cfg.super_circ_train_gradient_noise_factor
+        params = np.array(optimizer.apply_grad(grad=grad, args=params))
+        controller.clearRewardCache()                      # rewards of the old parameters are stale
+        best_arc, best_node = controller.exploitArcWithSuperCircParams(params)
+        best_model = model(p, c, l, best_arc, pool)
+        best_loss = best_model.getLoss(params)
+        best_reward = best_model.getReward(params)
+        penalised = _penalised(cfg, best_reward, best_node)
+        log("  pruned %d | best reward %r (penalised %r) | best loss %r | %.2f s" % (
+            controller.prune_counter, best_reward, penalised, best_loss, time.time() - t0))
+        log("  best k: %s" % (best_arc,))
+        if cfg.verbose > 1:
+            log(best_node.state)
+        history.append((epoch, best_arc, best_reward, penalised))
+        recent.append(penalised)
+        enough = epoch + 1 >= cfg.early_stop_lookback_count + cfg.num_warmup_iterations
+        if enough and np.average(recent[-cfg.early_stop_lookback_count:]) >= cfg.early_stop_threshold:
+            log("  early stop at epoch %d" % (epoch + 1))
+            break
+    return params, best_arc, best_node, best_reward, controller, history
+
+
+def circuitModelTuning(initial_params=None, model=None, num_epochs: int = None, k=None, op_pool=None,
+                       opt_callable=AdamOptimizer, lr=0.01, grad_noise_factor=1 / 100, verbose=1,
+                       early_stop_threshold=1e-15):
+    """Fixed structure list: loss -> gradient -> nan_to_num -> + noise -> optimiser step, until
+    ``num_epochs`` or ``loss <= early_stop_threshold`` (reference :381-412).  Evaluator-backed
+    models deliver the loss and the gradient of an epoch from a single launch."""
+    p, c, l = initial_params.shape
+    circuit = model(p, c, l, k, op_pool)
+    optimizer = opt_callable(stepsize=lr)
+    theta = np.array(initial_params, dtype=np.float64)
+    losses = []
+    fused = hasattr(model, "evaluate_batch")
+    for epoch in range(num_epochs):
+        if fused:
+            out = model.evaluate_batch([k], theta, op_pool, want_grad=True, avg=True)
+            loss, grad = float(out["energy"][0]), out["grad_dense"]
+        else:
+            loss, grad = circuit.getLoss(theta), np.nan_to_num(circuit.getGradient(theta))
+        losses.append(loss)
+        if verbose >= 1:
+            print("tuning epoch %d/%d: loss %r" % (epoch + 1, num_epochs, loss))
+        grad = grad + np.random.randn(p, c, l) * grad_noise_factor
+        theta = np.array(optimizer.apply_grad(grad=grad, args=theta))
+        if loss <= early_stop_threshold:
+            print("early stop at epoch %d" % (epoch + 1))
+            break
+    return theta, losses

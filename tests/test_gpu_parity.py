@@ -320,3 +320,36 @@ def test_two_gpu_sharded_batch_matches_single_gpu():
         assert pr.exitcode == 0
     assert np.max(np.abs(energy - ref["energy"])) <= 1e-12
     assert np.max(np.abs(grad - ref["grad_dense"])) <= 1e-12
+
+
+def test_search_and_tuning_drop_in_on_gpu():
+    """The reference's driver calls, through the CUDA-backed model: a short nested-MCTS search on the
+    4-qubit H2 model followed by fine-tuning must reach chemical accuracy territory, and the golden
+    circuit's tuning loop must reproduce the energy the reference recorded."""
+    import random
+    from qas_b200.mcts import QMLStateBasicGates, circuitModelTuning, search
+    from qas_b200.qml_models.qml_models_legacy import FourQubitH2
+    random.seed(0)
+    np.random.seed(0)
+    pool = helpers.near_cx_pool(4)
+    p, c = 10, len(pool)
+    init = np.random.default_rng(0).standard_normal((p, c, 3))
+    params, arc, node, reward, ctl, hist = search(
+        model=FourQubitH2, op_pool=pool, target_circuit_depth=p, init_qubit_with_controls=set(),
+        init_params=init, num_iterations=6, num_warmup_iterations=2, super_circ_train_lr=0.2,
+        early_stop_threshold=5.0, gate_limit_dict={"CNOT": p}, warmup_arc_batchsize=200, search_arc_batchsize=10,
+        alpha_max=2, alpha_decay_rate=0.99, prune_constant_max=0.99, prune_constant_min=0.8,
+        max_visits_prune_threshold=20, min_num_children=c // 2 + 1, sampling_execute_rounds=10,
+        exploit_execute_rounds=10, verbose=0, state_class=QMLStateBasicGates)
+    assert len(arc) == p and len(hist) == 6
+    m = FourQubitH2(p, c, 3, arc, pool)
+    assert abs(m.getReward(params) - reward) < 1e-12
+    assert abs(reward + sim.energy(4, arc, pool.pool, params, FourQubitH2.terms(), FourQubitH2.init_state)) < 1e-9
+    theta, losses = circuitModelTuning(initial_params=params, model=FourQubitH2, num_epochs=120, k=arc, op_pool=pool,
+                                       lr=0.1, grad_noise_factor=0, verbose=0, early_stop_threshold=-2.0)
+    assert losses[-1] <= losses[0] + 1e-12 and losses[-1] >= -1.136189454088 - 1e-9
+    # golden circuit: continuing the reference's own fine-tuning does not move the energy it recorded
+    g = [x for x in helpers.goldens() if x["fixture"] == "h2_hf_a"][0]
+    theta, losses = circuitModelTuning(initial_params=g["params"], model=FourQubitH2, num_epochs=3, k=g["k"],
+                                       op_pool=pool, lr=1e-4, grad_noise_factor=0, verbose=0, early_stop_threshold=-2.0)
+    assert abs(losses[0] - g["fine_tune_loss_tail"][-1]) < 5e-5

@@ -1,0 +1,159 @@
+"""CPU tier: the search driver (tree policy, epoch loop, batched gradient / warm-up rewards, reward
+cache, Adam rule) with an oracle-backed model standing in for the CUDA evaluator."""
+import random
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import sim
+from qas_b200.mcts import QMLStateBasicGates, TreeNode, circuitModelTuning, search
+from qas_b200.mcts.driver import SearchConfig
+from qas_b200.mcts.tree import MCTSController
+from qas_b200.models import ModelFromK
+from qas_b200.optim import AdamOptimizer
+from qas_b200.qml_models.utils import extractParamIndicesQML
+
+TERMS = [(-0.3324042513238793, "II"), (0.39793742484318045, "IZ"), (-0.39793742484318045, "ZI"),
+         (-0.01128010425623538, "ZZ"), (0.18093119978423156, "XX")]
+
+
+class OracleModel(ModelFromK):
+    """2-qubit H2 stand-in evaluated by the oracle, one circuit per call (the reference's shape)."""
+    name = "OracleTwoQubitH2"
+    calls = 0
+
+    def __init__(self, p, c, l, structure_list, op_pool):
+        self.p, self.c, self.l, self.k, self.pool = p, c, l, structure_list, op_pool
+        self.param_indices = extractParamIndicesQML(self.k, self.pool)
+
+    def getLoss(self, params):
+        type(self).calls += 1
+        return sim.energy(2, self.k, self.pool.pool, params, TERMS)
+
+    def getReward(self, params):
+        return -self.getLoss(params)
+
+    def getGradient(self, params):
+        return sim.grad_adjoint(2, self.k, self.pool.pool, params, TERMS)
+
+    def toList(self, params):
+        return sim.to_list(self.k, self.pool.pool, params)
+
+
+class OracleBatchModel(OracleModel):
+    """Same arithmetic behind the batched entry the CUDA-backed classes expose."""
+    name = "OracleTwoQubitH2Batched"
+    reward_sign = -1.0
+    batch_calls = 0
+
+    @classmethod
+    def evaluate_batch(cls, ks, params, op_pool, want_grad=True, avg=True, compact=False):
+        cls.batch_calls += 1
+        ks = [[int(x) for x in k] for k in np.asarray(ks)]
+        e = np.array([sim.energy(2, k, op_pool.pool, params, TERMS) for k in ks])
+        g = None
+        if want_grad:
+            g = sim.batch_mean_gradient([sim.grad_adjoint(2, k, op_pool.pool, params, TERMS) for k in ks], avg)
+        return {"energy": e, "grad_dense": g, "grad_compact": None}
+
+
+def _run(model, seed, **over):
+    random.seed(seed)
+    np.random.seed(seed)
+    pool = helpers.near_cx_pool(2, [[0, 1], [1, 0]])
+    p = 3
+    kw = dict(model=model, op_pool=pool, target_circuit_depth=p, init_qubit_with_controls=set(),
+              init_params=np.random.default_rng(seed).standard_normal((p, len(pool), 3)),
+              num_iterations=6, num_warmup_iterations=2, super_circ_train_lr=0.1, early_stop_threshold=10.0,
+              gate_limit_dict={"CNOT": 2}, warmup_arc_batchsize=6, search_arc_batchsize=4, alpha_max=2,
+              prune_constant_max=0.99, prune_constant_min=0.8, max_visits_prune_threshold=3, min_num_children=2,
+              sampling_execute_rounds=5, exploit_execute_rounds=5, verbose=0, state_class=QMLStateBasicGates)
+    kw.update(over)
+    return search(**kw)
+
+
+def test_batched_driver_equals_per_circuit_driver():
+    """Same seeds -> identical parameters, arcs and rewards whether the gradient batch / warm-up
+    rewards go through evaluate_batch or through one model per circuit (the reference's loop)."""
+    a = _run(OracleModel, 3)
+    b = _run(OracleBatchModel, 3)
+    assert np.max(np.abs(a[0] - b[0])) < 1e-13
+    assert a[1] == b[1] and abs(a[3] - b[3]) < 1e-13
+    assert [x[1] for x in a[5]] == [x[1] for x in b[5]]
+    assert OracleBatchModel.batch_calls >= 6 + 2          # one gradient launch per epoch + warm-up rewards
+
+
+def test_search_return_shape_and_reward_cache():
+    params, arc, node, reward, controller, history = _run(OracleBatchModel, 1)
+    assert params.shape == (3, 6, 3) and len(arc) == 3 and isinstance(node, TreeNode)
+    assert len(history) == 6 and history[-1][1] == arc
+    assert node.state.getCurrK() == arc
+    # depth-3 trees over a 6-key pool revisit terminals constantly: the cache must absorb most requests
+    assert controller.num_reward_evaluations < controller.num_reward_requests
+
+
+def test_search_argument_handling():
+    with pytest.raises(TypeError):
+        search(model=OracleModel, not_an_argument=1)
+    cfg = SearchConfig.from_call((), dict(model=OracleModel))
+    assert cfg.num_iterations == 500 and cfg.warmup_arc_batchsize == 200 and cfg.alpha_decay_rate == 0.95
+    assert cfg.super_circ_train_optimizer is AdamOptimizer
+
+
+def test_penalty_function_is_applied_by_the_driver():
+    seen = []
+
+    def penalty(r, node):
+        seen.append(node.state.getCurrK())
+        return r - 1.0
+    out = _run(OracleBatchModel, 2, penalty_function=penalty, num_iterations=3)
+    assert seen and all(h[3] == h[2] - 1.0 for h in out[5])
+
+
+def test_uct_and_prune_rules():
+    pool = helpers.near_cx_pool(2, [[0, 1], [1, 0]])
+    ctl = MCTSController(OracleModel, pool, 3, state_class=QMLStateBasicGates, alpha=0.0,
+                         prune_reward_ratio=0.9, max_visits_prune_threshold=1, min_num_children=1)
+    ctl.setRoot()
+    root = ctl.root
+    while not root.isFullyExpanded:
+        ctl.expand(root)
+    kids = list(root.children.values())
+    assert len(kids) == 2                      # first move: Rot on qubit 0 or 1
+    for i, ch in enumerate(kids):
+        ch.numVisits, ch.totalReward = 4, 4.0 * (i + 1)
+    root.numVisits, root.totalReward = 8, 12.0
+    assert ctl.getBestChild(root, 0.0) is kids[1]
+    assert ctl.getBestChild(root, 0.0, policy="local_sub_optimal") is kids[0]
+    with pytest.raises(ValueError):
+        ctl.getBestChild(root, 0.0, policy="nope")
+    # mean(kid0) = 1 < 0.9 * 1.5 and visited > threshold -> pruned (min_num_children=1 keeps the rest)
+    assert ctl.selectNode(root) is kids[1]
+    assert len(root.children) == 1 and ctl.prune_counter == 1
+
+
+def test_adam_rule():
+    opt = AdamOptimizer(0.1)
+    x = np.array([1.0, -2.0])
+    g = np.array([0.5, -0.25])
+    x1 = opt.apply_grad(g, x)
+    # first step: m = 0.1 g, v = 0.01 g^2, bias-corrected step = lr * g / (|g| + eps*sqrt(..)) ~ lr * sign(g)
+    assert np.allclose(x1, x - 0.1 * np.sign(g), atol=1e-6)
+    x2 = opt.apply_grad(g, x1)
+    m = 0.9 * 0.1 * g + 0.1 * g
+    v = 0.99 * 0.01 * g * g + 0.01 * g * g
+    step = 0.1 * np.sqrt(1 - 0.99 ** 2) / (1 - 0.9 ** 2)
+    assert np.allclose(x2, x1 - step * m / (np.sqrt(v) + 1e-8), atol=1e-15)
+
+
+def test_circuit_model_tuning_converges_on_the_oracle_model():
+    pool = helpers.near_cx_pool(2, [[0, 1], [1, 0]])
+    k = [0, 4, 2]                                   # Rot(0), CNOT(0,1), Rot(1)
+    params = np.random.default_rng(0).standard_normal((3, len(pool), 3))
+    for model in (OracleModel, OracleBatchModel):
+        np.random.seed(0)
+        theta, losses = circuitModelTuning(initial_params=params, model=model, num_epochs=150, k=k, op_pool=pool,
+                                           lr=0.1, grad_noise_factor=0, verbose=0, early_stop_threshold=-2.0)
+        assert len(losses) == 150 and losses[-1] < losses[0]
+        assert losses[-1] < -1.11          # ground energy of the stand-in operator is -1.1373
