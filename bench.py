@@ -307,13 +307,16 @@ def run_b200(args):
                 "flop_model": "2^n(58 N1 + 4 S + 4) executed-minimum; survey formula 2^n(122 N1 + 2(8G+2T)) alongside"}
 
     # ---- CPU baseline: reference-pattern oracle on a bounded sample, 1 core (how the reference runs)
-    t_probe, _ = _cpu_worker((name, 0, 1, args.seed, 8))
-    ns = int(max(2, min(4096, 15.0 / max(t_probe, 1e-3))))
-    cpu_v, cpu_n, cpu_t = cpu_port_throughput(name, ns, 1, args.seed)
-    from oracle.refpattern import REF_METHOD
-    cpu_baseline = {"value": cpu_v, "unit": "evals/s", "cores": 1, "kind": "port",
-                    "sample": "%d circuits of the %s batch (%.1f s), oracle in the reference call pattern, %s gradient"
-                              % (cpu_n, name, cpu_t, REF_METHOD[mname][0])}
+    if args.tune:      # kernel-tuning runs skip the CPU leg; such a line is not a bench result
+        cpu_baseline = None
+    else:
+        t_probe, _ = _cpu_worker((name, 0, 1, args.seed, 8))
+        ns = int(max(2, min(4096, 15.0 / max(t_probe, 1e-3))))
+        cpu_v, cpu_n, cpu_t = cpu_port_throughput(name, ns, 1, args.seed)
+        from oracle.refpattern import REF_METHOD
+        cpu_baseline = {"value": cpu_v, "unit": "evals/s", "cores": 1, "kind": "port",
+                        "sample": "%d circuits of the %s batch (%.1f s), oracle in the reference call pattern, %s gradient"
+                                  % (cpu_n, name, cpu_t, REF_METHOD[mname][0])}
 
     line = {
         "metric": "candidate-circuit evals/sec (energy+adjoint grad)", "value": value, "unit": "evals/s",
@@ -343,6 +346,7 @@ def main():
     ap.add_argument("--workload", default="lih_10q", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=65536, help="circuits per GPU per step")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--tune", action="store_true", help="kernel tuning: skip the CPU-baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

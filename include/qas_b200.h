@@ -124,6 +124,13 @@ int qas_compile_tape_host(int n_qubits, const qas_pool_entry *pool, int c, int p
                           const int32_t *k, uint64_t init_basis, uint32_t *out_ops, int max_ops,
                           int *num_ops, uint32_t *init_index);
 
+/* Pass planner (host run of the code the tape-compile kernel executes): groups consecutive
+ * uncontrolled 2x2 ops of a compiled tape into register-fused passes of up to gmax <= 3 gates.
+ * Rewrites, in place, the target parity masks of grouped ops to their reduced row-echelon form
+ * and records the group sizes in meta bits 24-25 (first op of a group) and 26-27 (last op).
+ * No reference counterpart (PennyLane applies one gate per tensordot).                       */
+int qas_plan_passes_host(uint32_t *ops, int num_ops, int gmax, int *num_groups);
+
 /* Counters since context creation: evaluations and kernel launches; device time of the
  * last call's kernels (ms, CUDA events on the launch stream; host-pointer calls only) and of
  * the last evaluation kernel alone (any call; qas_get_stats waits for that kernel).         */

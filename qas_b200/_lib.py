@@ -70,7 +70,8 @@ _lib = None
 # every symbol include/qas_b200.h declares (tests check the export list against this)
 EXPORTS = [
     "qas_abi_version", "qas_build_info", "qas_ctx_create", "qas_ctx_destroy", "qas_last_error",
-    "qas_eval_batch", "qas_compile_tape", "qas_compile_tape_host", "qas_get_stats",
+    "qas_eval_batch", "qas_compile_tape", "qas_compile_tape_host", "qas_plan_passes_host",
+    "qas_get_stats",
     "qas_fp64_peak_tflops",
 ]
 # include/qas_b200_sv.h
@@ -109,6 +110,8 @@ def load():
                                           ctypes.c_int, vp, ctypes.c_uint64, vp, ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_int),
                                           ctypes.POINTER(ctypes.c_uint32)]
+    lib.qas_plan_passes_host.restype = ctypes.c_int
+    lib.qas_plan_passes_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     lib.qas_get_stats.restype = ctypes.c_int
     lib.qas_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.qas_fp64_peak_tflops.restype = ctypes.c_int

@@ -26,9 +26,13 @@ struct qas_ctx {
   qas_pool_entry *d_pool = nullptr;
   double *d_vtab = nullptr;
   uint32_t *d_sdesc = nullptr;
-  int team_scale = 1;              // QAS_B200_TEAM_SCALE: threads per team = scale * default
-  int T = 0, RB = 0, rb[3] = {0, 0, 0};
-  int num_classes = 0;
+  int team_shift = 0;              // QAS_B200_TEAM_SHIFT: threads per team = default << shift (tuning)
+  int T = 0, RB = 0, GMAX = 1, rb[3] = {0, 0, 0};
+  WComb wc{};                      // register subspace W of the H-apply blocking (kernels.cuh)
+  int num_classes = 0, C_real = 0, C_imag = 0;
+  uint32_t *d_cdesc_plain = nullptr;
+  double *d_mout = nullptr; size_t cap_mout = 0;
+  int RBH = 0, PD = 1;             // H-apply blocking / prefetch depth (QAS_B200_HCFG=rb,pd overrides)
   GateTab *d_U = nullptr;
   GateDTab *d_dU = nullptr;
   int tab_p = 0;
@@ -128,12 +132,98 @@ static void fill_const_table(std::vector<GateTab> &t) {
 constexpr int team_threads(int n) {
   return n <= 4 ? 8 : n == 5 ? 16 : n <= 8 ? 32 : n == 9 ? 64 : n == 10 ? 128 : 256;
 }
-static int team_threads_for(int n, int scale) {
+constexpr int qas_gmax(int n, int T) { return qas_block_bits(n, T) > 1 ? qas_block_bits(n, T) : 1; }
+// H application: 4 amplitudes per thread and a 2-deep prefetch ring where the team has the
+// amplitudes for it (measured best on LiH-10q / H2O-8q among (3,1) (3,2) (2,2) (2,4))
+constexpr int qas_hrb(int n, int T) { return qas_block_bits(n, T) >= 2 ? 2 : qas_block_bits(n, T); }
+constexpr int qas_hpd(int n, int T) { return qas_hrb(n, T) >= 1 ? 2 : 1; }   // PD must divide 2^RB
+static int team_threads_for(int n, int shift) {
   const int t = team_threads(n);
-  if (n >= 14) return 256;
-  // doubled variants exist for n = 4..10 (see launch_eval)
-  if (scale >= 2 && n >= 4 && n <= 10 && t * 2 <= 256) return t * 2;
+  if (n >= 13) return 256;
+  // alternative team sizes exist for n = 8..10 (see launch_eval)
+  if (shift > 0 && n >= 8 && n <= 10 && t * 2 <= 256) return t * 2;
+  if (shift < 0 && n >= 9 && n <= 10) return t / 2;
   return t;
+}
+
+// ---- register subspace W of the H application -------------------------------------------------
+// Reduced row-echelon basis (pivot = highest set bit) of a set of vectors over GF(2).
+struct Gf2Basis {
+  uint32_t v[3];
+  int pv[3];
+  int rank = 0;
+  bool add(uint32_t x) {
+    for (int i = 0; i < rank; ++i) if ((x >> pv[i]) & 1u) x ^= v[i];
+    if (!x || rank == 3) return false;
+    const int p = 31 - __builtin_clz(x);
+    for (int i = 0; i < rank; ++i) if ((v[i] >> p) & 1u) v[i] ^= x;
+    v[rank] = x; pv[rank] = p; ++rank;
+    return true;
+  }
+  uint32_t reduce(uint32_t x) const {
+    for (int i = 0; i < rank; ++i) if ((x >> pv[i]) & 1u) x ^= v[i];
+    return x;
+  }
+};
+// cost of a candidate W: number of X-mask classes (cosets of W hit by the masks), ties broken
+// towards pivots >= 3 (keeps the 8 low index values of consecutive lanes distinct)
+static size_t w_cost(const Gf2Basis &b, const std::vector<uint32_t> &xs, std::vector<uint32_t> &tmp) {
+  tmp.clear();
+  for (uint32_t x : xs) tmp.push_back(b.reduce(x));
+  std::sort(tmp.begin(), tmp.end());
+  size_t ncls = std::unique(tmp.begin(), tmp.end()) - tmp.begin();
+  int low = 0;
+  for (int i = 0; i < b.rank; ++i) low += b.pv[i] < 3;
+  return ncls * 8 + (size_t)low;
+}
+static Gf2Basis choose_register_subspace(const std::vector<uint32_t> &xs, int n, int RB) {
+  Gf2Basis best;
+  if (RB == 0) return best;
+  std::vector<uint32_t> cand;
+  for (uint32_t x : xs) if (x) cand.push_back(x);
+  for (int b = 0; b < n; ++b) cand.push_back(1u << b);
+  std::sort(cand.begin(), cand.end());
+  cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+  const size_t nc = cand.size();
+  std::vector<uint32_t> tmp;
+  size_t best_cost = (size_t)-1;
+  double combos = 1.0;
+  for (int i = 0; i < RB; ++i) combos *= (double)(nc - i) / (i + 1);
+  if (combos <= 2.0e5) {      // exhaustive
+    std::vector<int> idx(RB);
+    for (int i = 0; i < RB; ++i) idx[i] = i;
+    while (true) {
+      Gf2Basis b;
+      bool ok = true;
+      for (int i = 0; i < RB && ok; ++i) ok = b.add(cand[idx[i]]);
+      if (ok) {
+        const size_t cst = w_cost(b, xs, tmp);
+        if (cst < best_cost) { best_cost = cst; best = b; }
+      }
+      int i = RB - 1;
+      while (i >= 0 && idx[i] == (int)nc - RB + i) --i;
+      if (i < 0) break;
+      ++idx[i];
+      for (int q = i + 1; q < RB; ++q) idx[q] = idx[q - 1] + 1;
+    }
+  } else {                    // greedy, one basis vector at a time
+    Gf2Basis cur;
+    for (int step = 0; step < RB; ++step) {
+      Gf2Basis step_best = cur;
+      size_t step_cost = (size_t)-1;
+      for (uint32_t w : cand) {
+        Gf2Basis b = cur;
+        if (!b.add(w)) continue;
+        const size_t cst = w_cost(b, xs, tmp);
+        if (cst < step_cost) { step_cost = cst; step_best = b; }
+      }
+      cur = step_best;
+    }
+    best = cur;
+  }
+  // fallback (cannot happen for n >= RB): unit vectors
+  for (int b = n - 1; best.rank < RB && b >= 0; --b) best.add(1u << b);
+  return best;
 }
 
 // ---------------------------------------------------------------------------------- create
@@ -164,10 +254,17 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   cx->c = c; cx->l = l; cx->max_expansion = max_exp;
   cx->pool.assign(pool, pool + c);
 
-  // threads per team and the register bits of the H-apply blocking
-  if (const char *ts = getenv("QAS_B200_TEAM_SCALE")) cx->team_scale = std::max(1, atoi(ts));
-  cx->T = team_threads_for(n_qubits, cx->team_scale);
-  cx->RB = qas_register_bits(n_qubits <= 13 ? n_qubits : 20, cx->T);
+  // threads per team, amplitudes per thread of the fused gate passes and of the H application
+  if (const char *ts = getenv("QAS_B200_TEAM_SHIFT")) cx->team_shift = atoi(ts);
+  cx->T = team_threads_for(n_qubits, cx->team_shift);
+  cx->GMAX = qas_gmax(n_qubits <= 13 ? n_qubits : 20, cx->T);
+  cx->RB = qas_hrb(n_qubits <= 13 ? n_qubits : 20, cx->T);
+  cx->PD = qas_hpd(n_qubits <= 13 ? n_qubits : 20, cx->T);
+  if (const char *hc = getenv("QAS_B200_HCFG")) {   // tuning: "rb,pd" among the compiled variants
+    int rbv = 0, pdv = 0;
+    if (sscanf(hc, "%d,%d", &rbv, &pdv) == 2 && (n_qubits == 8 || n_qubits == 10) && cx->team_shift == 0 &&
+        ((rbv == 3 && pdv == 2) || (rbv == 2 && (pdv == 1 || pdv == 2 || pdv == 4)) || (rbv == 1 && pdv == 2))) { cx->RB = rbv; cx->PD = pdv; }
+  }
 
   // group the Hamiltonian by X mask: slice key = (xmask, is_imag); term sign from i^{nY}
   std::map<std::pair<uint64_t, int>, std::vector<std::pair<uint32_t, double>>> slices;
@@ -176,61 +273,57 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
     const double sgn = (ny & 2) ? -1.0 : 1.0;
     slices[{terms[t].xmask, ny & 1}].push_back({(uint32_t)terms[t].zmask, sgn * terms[t].coeff});
   }
-  // choose the register-bit positions that minimise the number of X-mask classes
+  // register subspace W (RB-dimensional) minimising the number of X-mask classes
+  Gf2Basis W;
   {
     std::vector<uint32_t> xs;
     for (auto &kv : slices) xs.push_back((uint32_t)kv.first.first);
-    size_t best = (size_t)-1;
-    int pos[3] = {0, 1, 2};
-    const int RBc = cx->RB, nq = n_qubits;
-    // positions below bit 3 would break up the 8-amplitude (128-byte) rows consecutive lanes read
-    const int lo = (nq - RBc >= 3 && nq - 3 >= RBc) ? 3 : 0;
-    for (int a = lo; a < nq; ++a)
-      for (int b = (RBc >= 2 ? a + 1 : nq - 1); b < nq; ++b)
-        for (int c3 = (RBc >= 3 ? b + 1 : nq - 1); c3 < nq; ++c3) {
-          uint32_t mask = 0;
-          if (RBc >= 1) mask |= 1u << a;
-          if (RBc >= 2) mask |= 1u << b;
-          if (RBc >= 3) mask |= 1u << c3;
-          std::vector<uint32_t> cls;
-          for (uint32_t x : xs) cls.push_back(x & ~mask);
-          std::sort(cls.begin(), cls.end());
-          const size_t ncls = std::unique(cls.begin(), cls.end()) - cls.begin();
-          if (ncls < best) { best = ncls; pos[0] = a; pos[1] = b; pos[2] = c3; }
-          if (RBc < 3) break;
-        }
-    cx->rb[0] = pos[0]; cx->rb[1] = RBc >= 2 ? pos[1] : 0; cx->rb[2] = RBc >= 3 ? pos[2] : 0;
-    cx->num_classes = (int)best;
+    std::sort(xs.begin(), xs.end());
+    xs.erase(std::unique(xs.begin(), xs.end()), xs.end());
+    W = choose_register_subspace(xs, n_qubits, cx->RB);
+    // basis sorted by ascending pivot: rb0 < rb1 < rb2
+    for (int i = 0; i < W.rank; ++i)
+      for (int q = i + 1; q < W.rank; ++q)
+        if (W.pv[q] < W.pv[i]) { std::swap(W.pv[q], W.pv[i]); std::swap(W.v[q], W.v[i]); }
+    for (int q = 0; q < 3; ++q) cx->rb[q] = q < W.rank ? W.pv[q] : 0;
+    for (int j = 0; j < 8; ++j) {
+      uint32_t w = 0;
+      for (int q = 0; q < W.rank; ++q) if ((j >> q) & 1) w ^= W.v[q];
+      cx->wc.w[j] = w;
+    }
+    std::vector<uint32_t> tmp;
+    cx->num_classes = (int)(w_cost(W, xs, tmp) / 8);
   }
-  uint32_t regmask = 0;
-  for (int q = 0; q < cx->RB; ++q) regmask |= 1u << cx->rb[q];
-  auto compress = [&](uint32_t x) {   // register bits of x -> xh
-    uint32_t h = 0;
-    for (int q = 0; q < cx->RB; ++q) h |= ((x >> cx->rb[q]) & 1u) << q;
-    return h;
-  };
-  // order slices by class (x outside the register bits), then by xh
-  struct SliceRef { uint32_t x; int imag; const std::vector<std::pair<uint32_t, double>> *terms; };
-  std::vector<SliceRef> order;
-  for (auto &kv : slices) order.push_back({(uint32_t)kv.first.first, kv.first.second, &kv.second});
-  std::stable_sort(order.begin(), order.end(), [&](const SliceRef &a, const SliceRef &b) {
-    const uint32_t ca = a.x & ~regmask, cb = b.x & ~regmask;
-    if (ca != cb) return ca < cb;
-    return compress(a.x) < compress(b.x);
-  });
-  std::vector<uint32_t> sx, sdesc, tz;
+  // Classes = cosets of W hit by the X masks; real (even nY) classes first, then imaginary ones.
+  // Every class owns 2^RB table rows, one per jw (x = rho ^ wcomb[jw]); rows without a slice are
+  // zero rows, so the kernel's class loop is fully static (no per-slice descriptor decoding).
+  const int NBh = 1 << cx->RB;
+  std::vector<uint32_t> sx, cdesc_swz, cdesc_plain, tz;
   std::vector<int> sbegin;
   std::vector<double> tc;
-  for (size_t si = 0; si < order.size(); ++si) {
-    const SliceRef &sr = order[si];
-    const uint32_t xrest = sr.x & ~regmask;
-    const bool newclass = si == 0 || (order[si - 1].x & ~regmask) != xrest;
-    sx.push_back(sr.x);
-    sdesc.push_back(xrest | (compress(sr.x) << 20) | (sr.imag ? QAS_SD_IMAG : 0u) | (newclass ? QAS_SD_NEWCLASS : 0u));
-    sbegin.push_back((int)tz.size());
-    for (auto &zc : *sr.terms) { tz.push_back(zc.first); tc.push_back(zc.second); }
+  auto swz = [](uint32_t i) { return i ^ (((i >> 3) & 1u) * 7u); };
+  for (int imag = 0; imag < 2; ++imag) {
+    std::vector<uint32_t> reps;
+    for (auto &kv : slices) if (kv.first.second == imag) reps.push_back(W.reduce((uint32_t)kv.first.first));
+    std::sort(reps.begin(), reps.end());
+    reps.erase(std::unique(reps.begin(), reps.end()), reps.end());
+    for (uint32_t rho : reps) {
+      cdesc_swz.push_back(swz(rho) << 4);
+      cdesc_plain.push_back(rho << 4);
+      for (int jw = 0; jw < NBh; ++jw) {
+        const uint32_t x = rho ^ cx->wc.w[jw];
+        sx.push_back(x);
+        sbegin.push_back((int)tz.size());
+        auto it = slices.find({(uint64_t)x, imag});
+        if (it != slices.end())
+          for (auto &zc : it->second) { tz.push_back(zc.first); tc.push_back(zc.second); }
+      }
+    }
+    (imag ? cx->C_imag : cx->C_real) = (int)reps.size();
   }
+  for (int padrow = 0; padrow < 8; ++padrow) { sx.push_back(0u); sbegin.push_back((int)tz.size()); }   // prefetch overrun
   sbegin.push_back((int)tz.size());
+  if (tz.empty()) { tz.push_back(0u); tc.push_back(0.0); }
   cx->S = (int)sx.size();
   const size_t dim = (size_t)1 << n_qubits;
   if ((double)cx->S * (double)dim * 8.0 > 4.0e9) {
@@ -255,7 +348,8 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   guard(cudaEventCreate(&cx->ek1), "cudaEventCreate");
   guard(cudaMalloc(&cx->d_pool, sizeof(qas_pool_entry) * c), "cudaMalloc pool");
   guard(cudaMalloc(&cx->d_vtab, sizeof(double) * dim * cx->S), "cudaMalloc sign tables");
-  guard(cudaMalloc(&cx->d_sdesc, 4 * cx->S), "cudaMalloc sdesc");
+  guard(cudaMalloc(&cx->d_sdesc, 4 * std::max<size_t>(cdesc_swz.size(), 1)), "cudaMalloc cdesc");
+  guard(cudaMalloc(&cx->d_cdesc_plain, 4 * std::max<size_t>(cdesc_plain.size(), 1)), "cudaMalloc cdesc");
   uint32_t *d_tz = nullptr, *d_sx = nullptr; double *d_tc = nullptr; int *d_sbegin = nullptr;
   guard(cudaMalloc(&d_sx, 4 * cx->S), "cudaMalloc sx");
   guard(cudaMalloc(&d_tz, 4 * tz.size()), "cudaMalloc tz");
@@ -264,13 +358,14 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   if (rc == QAS_OK) {
     guard(cudaMemcpy(cx->d_pool, pool, sizeof(qas_pool_entry) * c, cudaMemcpyHostToDevice), "copy pool");
     guard(cudaMemcpy(d_sx, sx.data(), 4 * sx.size(), cudaMemcpyHostToDevice), "copy sx");
-    guard(cudaMemcpy(cx->d_sdesc, sdesc.data(), 4 * sdesc.size(), cudaMemcpyHostToDevice), "copy sdesc");
+    guard(cudaMemcpy(cx->d_sdesc, cdesc_swz.data(), 4 * cdesc_swz.size(), cudaMemcpyHostToDevice), "copy cdesc");
+    guard(cudaMemcpy(cx->d_cdesc_plain, cdesc_plain.data(), 4 * cdesc_plain.size(), cudaMemcpyHostToDevice), "copy cdesc");
     guard(cudaMemcpy(d_tz, tz.data(), 4 * tz.size(), cudaMemcpyHostToDevice), "copy tz");
     guard(cudaMemcpy(d_tc, tc.data(), 8 * tc.size(), cudaMemcpyHostToDevice), "copy tc");
     guard(cudaMemcpy(d_sbegin, sbegin.data(), 4 * sbegin.size(), cudaMemcpyHostToDevice), "copy sbegin");
     const size_t total = dim * cx->S;
     build_sign_tables_kernel<<<(unsigned)((total + 255) / 256), 256, 0, cx->stream>>>(
-        n_qubits, cx->S, cx->RB, cx->rb[0], cx->rb[1], cx->rb[2], d_sx, d_sbegin, d_tz, d_tc, cx->d_vtab);
+        n_qubits, cx->S, cx->RB, cx->rb[0], cx->rb[1], cx->rb[2], cx->wc, d_sx, d_sbegin, d_tz, d_tc, cx->d_vtab);
     guard(cudaGetLastError(), "build_sign_tables launch");
     guard(cudaStreamSynchronize(cx->stream), "build_sign_tables");
   }
@@ -283,10 +378,10 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
 extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   if (!ctx) return QAS_OK;
   cudaSetDevice(ctx->device);
-  cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc);
+  cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_cdesc_plain);
   cudaFree(ctx->d_U); cudaFree(ctx->d_dU); cudaFree(ctx->d_k); cudaFree(ctx->d_params);
   cudaFree(ctx->d_energy); cudaFree(ctx->d_grad); cudaFree(ctx->d_partial); cudaFree(ctx->d_dense);
-  cudaFree(ctx->d_gstate); cudaFree(ctx->d_tape);
+  cudaFree(ctx->d_gstate); cudaFree(ctx->d_mout); cudaFree(ctx->d_tape);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ek0) cudaEventDestroy(ctx->ek0);
@@ -313,11 +408,15 @@ extern "C" int qas_get_stats(const qas_ctx *cctx, qas_stats *out) {
 // ---------------------------------------------------------------------------------- launch
 static size_t sdesc_bytes(int S) { return (((size_t)S * 4) + 15) & ~(size_t)15; }
 
-template <int N, int T, bool GRAD>
+// CTAs per SM the register allocation is bounded for: the 3-gate adjoint pass holds 8 + 8
+// amplitudes and a 2x2 cross matrix in registers (128-register budget)
+constexpr int qas_minb(int n, int T) { return qas_block_bits(n, T) >= 2 ? 2 : 3; }
+
+template <int N, int T, bool GRAD, int RBH, int PD>
 static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t st) {
   constexpr int TEAMS = 256 / T;
-  const size_t smem = eval_team_smem_bytes(N, T, GRAD, P.ops_cap, true, qas_stage_u(N)) * TEAMS + sdesc_bytes(P.S);
-  auto kern = eval_kernel<N, T, GRAD>;
+  const size_t smem = eval_team_smem_bytes(N, T, GRAD, P.ops_cap, true, qas_stage_u(N)) * TEAMS + sdesc_bytes(P.C_real + P.C_imag);
+  auto kern = eval_kernel<N, T, GRAD, qas_gmax(N, T), RBH, PD, qas_minb(N, T)>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -334,8 +433,8 @@ static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t s
 
 template <bool GRAD>
 static cudaError_t launch_gmem(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
-  const size_t smem = eval_team_smem_bytes(P.n, 256, GRAD, P.ops_cap, false, true) + sdesc_bytes(P.S);
-  auto kern = eval_kernel<0, 256, GRAD>;
+  const size_t smem = eval_team_smem_bytes(P.n, 256, GRAD, P.ops_cap, false, true) + sdesc_bytes(P.C_real + P.C_imag);
+  auto kern = eval_kernel<0, 256, GRAD, 3, 2, 2, 2>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -356,25 +455,31 @@ static cudaError_t launch_gmem(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// (N, T) instantiations: the default team size of each qubit count and its double
+// (N, T) instantiations: the default team size of each qubit count plus tuning alternatives
 template <bool GRAD>
 static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
   const int nmax_smem = GRAD ? 12 : 13;
   const int T = ctx->T;
   if (P.n <= nmax_smem) {
-    const size_t smem = eval_team_smem_bytes(P.n, T, GRAD, P.ops_cap, true, qas_stage_u(P.n)) * (256 / T) + sdesc_bytes(P.S);
+    const size_t smem = eval_team_smem_bytes(P.n, T, GRAD, P.ops_cap, true, qas_stage_u(P.n)) * (256 / T) + sdesc_bytes(P.C_real + P.C_imag);
     if (smem <= 227 * 1024) {
-#define QAS_CASE(N_, T_) if (P.n == N_ && T == T_) return launch_smem<N_, T_, GRAD>(ctx, P, st);
-      QAS_CASE(2, 8) QAS_CASE(3, 8) QAS_CASE(4, 8) QAS_CASE(4, 16) QAS_CASE(5, 16) QAS_CASE(5, 32)
-      QAS_CASE(6, 32) QAS_CASE(6, 64) QAS_CASE(7, 32) QAS_CASE(7, 64) QAS_CASE(8, 32) QAS_CASE(8, 64)
-      QAS_CASE(9, 64) QAS_CASE(9, 128) QAS_CASE(10, 128) QAS_CASE(10, 256) QAS_CASE(11, 256)
-      QAS_CASE(12, 256)
+#define QAS_CASE(N_, T_)                                                              \
+  if (P.n == N_ && T == T_ && ctx->RB == qas_hrb(N_, T_) && ctx->PD == qas_hpd(N_, T_)) \
+    return launch_smem<N_, T_, GRAD, qas_hrb(N_, T_), qas_hpd(N_, T_)>(ctx, P, st);
+#define QAS_HCASE(N_, T_, RB_, PD_) \
+  if (P.n == N_ && T == T_ && ctx->RB == RB_ && ctx->PD == PD_) return launch_smem<N_, T_, GRAD, RB_, PD_>(ctx, P, st);
+      QAS_CASE(2, 8) QAS_CASE(3, 8) QAS_CASE(4, 8) QAS_CASE(5, 16) QAS_CASE(6, 32) QAS_CASE(7, 32)
+      QAS_CASE(8, 32) QAS_CASE(8, 64) QAS_CASE(9, 64) QAS_CASE(9, 32) QAS_CASE(9, 128)
+      QAS_CASE(10, 128) QAS_CASE(10, 64) QAS_CASE(10, 256) QAS_CASE(11, 256) QAS_CASE(12, 256)
+      QAS_HCASE(8, 32, 3, 2) QAS_HCASE(8, 32, 2, 4) QAS_HCASE(8, 32, 2, 1) QAS_HCASE(8, 32, 1, 2)
+      QAS_HCASE(10, 128, 3, 2) QAS_HCASE(10, 128, 2, 4) QAS_HCASE(10, 128, 2, 1) QAS_HCASE(10, 128, 1, 2)
 #undef QAS_CASE
-      if constexpr (!GRAD) { if (P.n == 13) return launch_smem<13, 256, false>(ctx, P, st); }
+#undef QAS_HCASE
+      if constexpr (!GRAD) { if (P.n == 13) return launch_smem<13, 256, false, qas_hrb(13, 256), qas_hpd(13, 256)>(ctx, P, st); }
     }
   }
-  // the global-memory instantiation is compiled for 256-thread teams and 3 register bits
-  if (ctx->T != 256 || ctx->RB != qas_register_bits(20, 256)) return cudaErrorInvalidConfiguration;
+  // the global-memory instantiation is compiled for 256-thread teams, 3-gate passes, 4-amplitude H rows
+  if (ctx->T != 256 || ctx->RB != 2 || ctx->PD != 2 || ctx->GMAX != 3) return cudaErrorInvalidConfiguration;
   return launch_gmem<GRAD>(ctx, P, st);
 }
 
@@ -432,11 +537,20 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   }
 
   EvalParams P{};
-  P.k = dk; P.pool = ctx->d_pool; P.U = ctx->d_U; P.dU = ctx->d_dU;
-  P.vtab = ctx->d_vtab; P.sdesc = ctx->d_sdesc; P.rb0 = ctx->rb[0]; P.rb1 = ctx->rb[1]; P.rb2 = ctx->rb[2];
-  P.energy = denergy; P.grad = dgrad; P.gstate = nullptr;
+  P.k = dk; P.pool = ctx->d_pool; P.U = ctx->d_U;
+  P.vtab = ctx->d_vtab; P.rb0 = ctx->rb[0]; P.rb1 = ctx->rb[1]; P.rb2 = ctx->rb[2];
+  P.C_real = ctx->C_real; P.C_imag = ctx->C_imag;
+  {   // class descriptors and W combinations as byte offsets, swizzled for the shared-memory path
+    const bool smem_path = ctx->n <= (want_grad ? 12 : 13);
+    P.cdesc = smem_path ? ctx->d_sdesc : ctx->d_cdesc_plain;
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t w = ctx->wc.w[j];
+      P.wc16.w[j] = (smem_path ? (w ^ (((w >> 3) & 1u) * 7u)) : w) << 4;
+    }
+  }
+  P.energy = denergy; P.gstate = nullptr; P.mout = nullptr;
   P.init_basis = ctx->init_basis;
-  P.B = B; P.p = p; P.c = c; P.l = l; P.n = ctx->n; P.S = ctx->S;
+  P.B = B; P.p = p; P.c = c; P.l = l; P.n = ctx->n;
   P.ops_cap = std::max(1, p * ctx->max_expansion);
   P.init_kind = ctx->init_kind;
 
@@ -444,9 +558,15 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   CK(ensure(&ctx->d_tape, &ctx->cap_tape, rec_words * (size_t)B));
   P.tape = ctx->d_tape;
 
+  if (want_grad) {
+    CK(ensure(&ctx->d_mout, &ctx->cap_mout, (size_t)B * P.ops_cap * 8));
+    P.mout = ctx->d_mout;
+  }
+
   if (!dev) CK(cudaEventRecord(ctx->ev0, st));
+  if (want_grad) CK(cudaMemsetAsync(dgrad, 0, ng * 8, st));
   compile_tapes_kernel<<<(B + 127) / 128, 128, 0, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap,
-                                                         ctx->init_kind, ctx->init_basis, ctx->d_tape);
+                                                         ctx->init_kind, ctx->init_basis, ctx->GMAX, ctx->d_tape);
   CK(cudaGetLastError());
   build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
   CK(cudaGetLastError());
@@ -455,6 +575,13 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   CK(cudaEventRecord(ctx->ek1, st));
   ctx->ek_pending = true;
   ctx->stats.launches += 3;
+  if (want_grad) {
+    const size_t nthr = (size_t)B * P.ops_cap * 3;
+    grad_finalize_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ctx->d_tape, ctx->d_mout, ctx->d_dU, B, p, l,
+                                                                        P.ops_cap, dgrad);
+    CK(cudaGetLastError());
+    ctx->stats.launches += 1;
+  }
 
   if (grad_dense) {
     const int chunk = 128;
@@ -502,6 +629,12 @@ extern "C" int qas_compile_tape_host(int n_qubits, const qas_pool_entry *pool, i
   if (st == 2) { g_create_error = "tape buffer too small"; return QAS_ERR_NOMEM; }
   *num_ops = sink.n;
   if (init_index) *init_index = qas_frame_map_basis(col, n_qubits, init_basis);
+  return QAS_OK;
+}
+
+extern "C" int qas_plan_passes_host(uint32_t *ops, int num_ops, int gmax, int *num_groups) {
+  if (!ops || num_ops < 0 || gmax < 1 || gmax > 3 || !num_groups) return QAS_ERR_INVALID;
+  *num_groups = qas_plan_groups(ops, num_ops, gmax);
   return QAS_OK;
 }
 

@@ -21,20 +21,23 @@
 struct __align__(16) GateTab { double2 u[4]; };        // U00 U01 U10 U11
 struct __align__(16) GateDTab { double2 d[3][4]; };    // dU/dtheta_j, same layout
 
+struct WComb { uint32_t w[8]; };
+
 struct EvalParams {
   const int32_t *k;            // [B][p]
   const qas_pool_entry *pool;  // [c]
   const GateTab *U;            // [NCONST + p*c]
-  const GateDTab *dU;          // [NCONST + p*c]
-  const double *vtab;          // [S][2^RB][2^(n-RB)] sign tables, register-bit-major (see 3.3)
-  const uint32_t *sdesc;       // [S] slice descriptors: x_rest | xh<<20 | imag<<23 | newclass<<24
-  int rb0, rb1, rb2;           // ascending positions of the register bits of the H-apply blocking
+  const double *vtab;          // [S][2^(n-RB)][2^RB] sign tables, coset-major (see "sign tables")
+  const uint32_t *cdesc;       // [C_real + C_imag] class representatives rho as (swizzled) byte offsets
+  int C_real, C_imag;          // X-mask classes with real / imaginary sign tables (real first)
+  int rb0, rb1, rb2;           // ascending pivots of the register subspace W of the H-apply blocking
+  WComb wc16;                  // byte offset of wcomb[j] = xor of the basis vectors of W selected by j
   double *energy;              // [B]
-  double *grad;                // [B][p][l] compact, may be null when !GRAD
   double2 *gstate;             // global-memory statevector scratch (path 1)
+  double *mout;                // [B][ops_cap][8] cross matrices M of the parametrised ops (GRAD)
   const uint32_t *tape;        // [B][4 + ops_cap*5] compiled tape records (compile_tapes_kernel)
   uint64_t init_basis;
-  int B, p, c, l, n, S, ops_cap, init_kind;
+  int B, p, c, l, n, ops_cap, init_kind;
 };
 
 // ------------------------------------------------------------------------------ helpers
@@ -53,22 +56,21 @@ __device__ __forceinline__ double2 cmul_conj(double2 a, double2 b) {            
 __device__ __forceinline__ uint32_t insert_zero(uint32_t t, int b) {
   return ((t >> b) << (b + 1)) | (t & ((1u << b) - 1u));
 }
-#ifndef QAS_RB_MAX
-#define QAS_RB_MAX 2     // at most 2^2 amplitudes per thread in the register-blocked H application
-#endif
-__host__ __device__ constexpr int qas_register_bits(int n, int T) {
+// amplitudes per thread = 2^bits in the fused gate passes and in the H application: as many as
+// leave every thread of the team one coset, at most 3 bits
+__host__ __device__ constexpr int qas_block_bits(int n, int T) {
   int lt = 0;
   while ((1 << lt) < T) ++lt;
-  return n - lt >= QAS_RB_MAX ? QAS_RB_MAX : (n - lt > 0 ? n - lt : 0);
+  return n - lt >= 3 ? 3 : (n - lt > 0 ? n - lt : 0);
 }
-__device__ __forceinline__ double shfl_xor_d(double v, int off) {
-  return __shfl_xor_sync(0xffffffffu, v, off);
+__device__ __forceinline__ double shfl_xor_d(double v, int off, uint32_t mask = 0xffffffffu) {
+  return __shfl_xor_sync(mask, v, off);
 }
 
 template <int T>
-__device__ __forceinline__ void team_sync(int team) {
+__device__ __forceinline__ void team_sync(int team, uint32_t tmask) {
   if constexpr (T <= 32) {
-    __syncwarp();
+    __syncwarp(tmask);
   } else if constexpr (T == 256) {
     __syncthreads();
   } else {
@@ -187,18 +189,18 @@ __global__ void build_gate_table_kernel(const qas_pool_entry *pool, int c, int p
 // ------------------------------------------------------------------------------ sign tables
 // H is grouped by X mask ("slice"):  (H psi)[i] = sum_s (i if imag) V_s[i] psi[i ^ x_s],
 // V_s[i] = sum_{t in slice s} c_t * (+-1 from i^{nY}) * (-1)^{popc((i ^ x_s) & z_t)}.
-// Blocking of the H application: every thread owns 2^RB amplitudes that differ only in RB
-// "register bits" (positions rb0<rb1<rb2, chosen per Hamiltonian on the host so that as many X
-// masks as possible differ only inside them).  Slices whose X masks agree outside the register
-// bits form a class: the thread loads the 2^RB partner amplitudes ONCE per class and serves
-// every slice of the class from registers (partner j ^ xh).  The tables are stored
-// register-bit-major, vtab[s][j][u] with i = deposit(u) | spread(j), so that for fixed (s, j)
-// consecutive threads read consecutive doubles.
-#define QAS_SD_XREST 0xfffffu
-#define QAS_SD_XH(d) (((d) >> 20) & 7u)
-#define QAS_SD_IMAG (1u << 23)
-#define QAS_SD_NEWCLASS (1u << 24)
-
+// Blocking of the H application: every thread owns the 2^RB amplitudes of one coset
+// P ^ span(w_0..w_{RB-1}) of a "register subspace" W chosen per Hamiltonian on the host (basis in
+// reduced row-echelon form, pivots rb0<rb1<rb2; wcomb[j] = xor of the basis vectors selected by
+// the bits of j).  Slices whose X masks agree modulo W form a class: the thread loads the 2^RB
+// partner amplitudes psi[P ^ rho ^ wcomb[j]] ONCE per class (rho = class representative, zero at
+// the pivots) and serves every slice x = rho ^ wcomb[jw] of the class from registers (partner of
+// own slot j is slot j ^ jw).  For chemistry Hamiltonians W is spanned by excitation masks, which
+// collapses e.g. the 35 X masks of LiH-10q into 11 classes of 4.  Every class owns exactly 2^RB
+// table rows (jw = 0..2^RB-1; a zero row where the Hamiltonian has no such mask), so the class
+// loop is fully static: no per-slice descriptor decoding, partner slots are compile-time register
+// names.  Rows are stored coset-major, vtab[row][u][j] = V_row[P(u) ^ wcomb[j]]: as double2 pairs,
+// vtab[row][jp][u][2], so that every 128-bit load of a warp covers 512 contiguous bytes.
 __host__ __device__ __forceinline__ uint32_t qas_insert_zero(uint32_t t, int b) {
   return ((t >> b) << (b + 1)) | (t & ((1u << b) - 1u));
 }
@@ -208,11 +210,8 @@ __host__ __device__ __forceinline__ uint32_t qas_deposit_rest(uint32_t u, int RB
   if (RB >= 3) u = qas_insert_zero(u, rb2);
   return u;
 }
-__host__ __device__ __forceinline__ uint32_t qas_spread_reg(uint32_t j, int rb0, int rb1, int rb2) {
-  return ((j & 1u) << rb0) | (((j >> 1) & 1u) << rb1) | (((j >> 2) & 1u) << rb2);
-}
 
-__global__ void build_sign_tables_kernel(int n, int S, int RB, int rb0, int rb1, int rb2,
+__global__ void build_sign_tables_kernel(int n, int S, int RB, int rb0, int rb1, int rb2, WComb wc,
                                          const uint32_t *sx, const int *sbegin, const uint32_t *tz,
                                          const double *tc, double *vtab) {
   const size_t dim = (size_t)1 << n;
@@ -220,8 +219,11 @@ __global__ void build_sign_tables_kernel(int n, int S, int RB, int rb0, int rb1,
   if (idx >= dim * (size_t)S) return;
   const int s = (int)(idx >> n);
   const uint32_t e = (uint32_t)(idx & (dim - 1));
-  const uint32_t u = e & ((1u << (n - RB)) - 1u), jj = e >> (n - RB);
-  const uint32_t i = qas_deposit_rest(u, RB, rb0, rb1, rb2) | qas_spread_reg(jj, rb0, rb1, rb2);
+  // element e of a row: [jp][u][2] with j = 2 jp + (e & 1)  (RB = 0: [u])
+  const uint32_t nrest = (uint32_t)(dim >> RB);
+  const uint32_t u = RB ? ((e >> 1) % nrest) : e;
+  const uint32_t jj = RB ? ((((e >> 1) / nrest) << 1) | (e & 1u)) : 0u;
+  const uint32_t i = qas_deposit_rest(u, RB, rb0, rb1, rb2) ^ wc.w[jj];
   const uint32_t j = i ^ sx[s];
   double v = 0.0;
   for (int t = sbegin[s]; t < sbegin[s + 1]; ++t) v += (__popc(j & tz[t]) & 1) ? -tc[t] : tc[t];
@@ -246,47 +248,153 @@ __device__ __forceinline__ void hacc(double2 (&acc)[NB], const double2 (&a)[NB],
     }
   }
 }
+// row jw of a class: partner of own slot j is slot j ^ jw (jw is a compile-time value after unrolling)
 template <int NB>
-__device__ __forceinline__ void hacc_dispatch(double2 (&acc)[NB], const double2 (&a)[NB],
-                                              const double (&v)[NB], uint32_t xh, bool imag) {
-  switch (xh) {
-    case 0: hacc<NB, 0>(acc, a, v, imag); break;
-    case 1: if constexpr (NB > 1) hacc<NB, 1>(acc, a, v, imag); break;
-    case 2: if constexpr (NB > 2) hacc<NB, 2>(acc, a, v, imag); break;
-    case 3: if constexpr (NB > 2) hacc<NB, 3>(acc, a, v, imag); break;
-    case 4: if constexpr (NB > 4) hacc<NB, 4>(acc, a, v, imag); break;
-    case 5: if constexpr (NB > 4) hacc<NB, 5>(acc, a, v, imag); break;
-    case 6: if constexpr (NB > 4) hacc<NB, 6>(acc, a, v, imag); break;
-    default: if constexpr (NB > 4) hacc<NB, 7>(acc, a, v, imag); break;
+__device__ __forceinline__ void hacc_row(double2 (&acc)[NB], const double2 (&a)[NB], const double (&v)[NB],
+                                         int jw, bool imag) {
+  if constexpr (NB == 1) { hacc<1, 0>(acc, a, v, imag); }
+  else if constexpr (NB == 2) { if (jw == 0) hacc<2, 0>(acc, a, v, imag); else hacc<2, 1>(acc, a, v, imag); }
+  else if constexpr (NB == 4) {
+    switch (jw) { case 0: hacc<4, 0>(acc, a, v, imag); break; case 1: hacc<4, 1>(acc, a, v, imag); break;
+                  case 2: hacc<4, 2>(acc, a, v, imag); break; default: hacc<4, 3>(acc, a, v, imag); break; }
+  } else {
+    switch (jw) { case 0: hacc<8, 0>(acc, a, v, imag); break; case 1: hacc<8, 1>(acc, a, v, imag); break;
+                  case 2: hacc<8, 2>(acc, a, v, imag); break; case 3: hacc<8, 3>(acc, a, v, imag); break;
+                  case 4: hacc<8, 4>(acc, a, v, imag); break; case 5: hacc<8, 5>(acc, a, v, imag); break;
+                  case 6: hacc<8, 6>(acc, a, v, imag); break; default: hacc<8, 7>(acc, a, v, imag); break; }
+  }
+}
+// p -> this thread's first element of the row; pair jp of the row sits nrest double2 further on
+template <int NB>
+__device__ __forceinline__ void load_vrow(double (&v)[NB], const double *p, uint32_t nrest) {
+  if constexpr (NB >= 2) {
+#pragma unroll
+    for (int j = 0; j < NB; j += 2) {
+      const double2 t = __ldg(reinterpret_cast<const double2 *>(p) + (size_t)(j >> 1) * nrest);
+      v[j] = t.x;
+      v[j + 1] = t.y;
+    }
+  } else {
+    v[0] = __ldg(p);
   }
 }
 
 // ------------------------------------------------------------------------------ tape compile
-// One thread per circuit: runs the tape compiler (tape.h) and writes a record
-//   [nops, status, init_index, n1q | ops[ops_cap][5]]   (uint32)
+// One thread per circuit: runs the tape compiler and the pass planner (tape.h) and writes a record
+//   [nops, status, init_index, ngroups | ops[ops_cap][5]]   (uint32)
 // to global memory.  Doing this in its own launch (B-way parallel) keeps the serial GF(2)
 // frame walk out of the evaluation teams' critical path; the records stay L2-resident.
 #define QAS_REC_HDR 4
 __global__ void compile_tapes_kernel(const int32_t *k, const qas_pool_entry *pool, int B, int p, int c,
                                      int n, int ops_cap, int init_kind, uint64_t init_basis,
-                                     uint32_t *tape) {
+                                     int gmax, uint32_t *tape) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   uint32_t col[32], row[32];
   uint32_t *rec = tape + (size_t)b * (QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS);
   QasTapeSink sink{rec + QAS_REC_HDR, ops_cap, 0, 0};
   const int st = qas_compile_circuit(k + (size_t)b * p, p, pool, c, n, col, row, sink);
-  rec[0] = st ? 0u : (uint32_t)sink.n;
+  const int nops = st ? 0 : sink.n;
+  rec[0] = (uint32_t)nops;
   rec[1] = (uint32_t)st;
   rec[2] = (init_kind == QAS_INIT_BASIS && !st) ? qas_frame_map_basis(col, n, init_basis) : 0u;
-  rec[3] = 0u;
+  rec[3] = (uint32_t)qas_plan_groups(rec + QAS_REC_HDR, nops, gmax);   // passes per sweep
 }
 
 // ------------------------------------------------------------------------------ evaluation
+// Shared-memory statevectors are stored swizzled, slot(i) = i ^ (bit 3 of i ? 7 : 0): a pass
+// whose coset enumeration has a pivot below bit 3 would otherwise put two lanes of every
+// quarter-warp on the same 16-byte bank group (2-way conflicts on ~30 % of the gates).
+template <bool SWZ>
+__device__ __forceinline__ uint32_t sw(uint32_t i) {
+  if constexpr (SWZ) return i ^ (((i >> 3) & 1u) * 7u);
+  return i;
+}
+__device__ __forceinline__ void apply_u(double2 &a0, double2 &a1, const double2 (&u)[4]) {
+  const double2 b0 = cfma(u[1], a1, cmul(u[0], a0));
+  const double2 b1 = cfma(u[3], a1, cmul(u[2], a0));
+  a0 = b0;
+  a1 = b1;
+}
+__device__ __forceinline__ void apply_udag(double2 &a0, double2 &a1, const double2 (&u)[4]) {
+  const double2 b0 = cfma_conj(u[2], a1, cmul_conj(u[0], a0));
+  const double2 b1 = cfma_conj(u[3], a1, cmul_conj(u[1], a0));
+  a0 = b0;
+  a1 = b1;
+}
+// M_ab += conj(l_a) q_b  (acc = M00 M01 M10 M11 as re,im pairs)
+__device__ __forceinline__ void macc(double (&acc)[8], double2 l0, double2 l1, double2 q0, double2 q1) {
+  acc[0] = fma(l0.x, q0.x, fma(l0.y, q0.y, acc[0])); acc[1] = fma(l0.x, q0.y, fma(-l0.y, q0.x, acc[1]));
+  acc[2] = fma(l0.x, q1.x, fma(l0.y, q1.y, acc[2])); acc[3] = fma(l0.x, q1.y, fma(-l0.y, q1.x, acc[3]));
+  acc[4] = fma(l1.x, q0.x, fma(l1.y, q0.y, acc[4])); acc[5] = fma(l1.x, q0.y, fma(-l1.y, q0.x, acc[5]));
+  acc[6] = fma(l1.x, q1.x, fma(l1.y, q1.y, acc[6])); acc[7] = fma(l1.x, q1.y, fma(-l1.y, q1.x, acc[7]));
+}
+
+// coset enumeration of one pass group (see qas_plan_groups): R = reduced parity functionals with
+// strictly descending pivots, xm[c] = xor of the gate masks selected by the bits of slot c
+template <int G>
+struct GroupGeom {
+  uint32_t R[G];
+  int pv[G];
+  uint32_t xm[1 << G];
+  __device__ __forceinline__ void load(const uint32_t *o) {
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      R[q] = o[q * QAS_OP_WORDS + 1];
+      pv[q] = 31 - __clz(R[q]);
+    }
+    xm[0] = 0u;
+#pragma unroll
+    for (int c = 1; c < (1 << G); ++c) {
+      const int q = c >= 4 ? 2 : (c >= 2 ? 1 : 0);
+      xm[c] = xm[c & ~(1 << q)] ^ o[q * QAS_OP_WORDS];
+    }
+  }
+  __device__ __forceinline__ uint32_t base(uint32_t t) const {
+    uint32_t ins = t;
+#pragma unroll
+    for (int q = G - 1; q >= 0; --q) ins = insert_zero(ins, pv[q]);
+    uint32_t P = ins;
+#pragma unroll
+    for (int q = 0; q < G; ++q) P |= (uint32_t)(__popc(ins & R[q]) & 1) << pv[q];
+    return P;
+  }
+};
+
+// warp-level reduce-scatter of a 2x2 cross matrix (8 doubles) over the TW lanes of a team's warp;
+// afterwards lanes with (lane & (TW/8-1)) == 0 hold component v = 4*h1 + 2*h2 + h3.
+// ACC: add to the value already at dst when `add` is set (later cosets of a multi-iteration pass;
+// only used with the shared-memory ring, where every slot has a single writer lane)
+template <int TW, bool ACC>
+__device__ __forceinline__ void reduce_store_m(double (&acc)[8], int lane, uint32_t tmask, double *dst, bool add) {
+  const bool h1 = lane & (TW / 2), h2 = lane & (TW / 4), h3 = lane & (TW / 8);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double send = h1 ? acc[q] : acc[q + 4], keep = h1 ? acc[q + 4] : acc[q];
+    acc[q] = keep + shfl_xor_d(send, TW / 2, tmask);
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const double send = h2 ? acc[q] : acc[q + 2], keep = h2 ? acc[q + 2] : acc[q];
+    acc[q] = keep + shfl_xor_d(send, TW / 4, tmask);
+  }
+  {
+    const double send = h3 ? acc[0] : acc[1], keep = h3 ? acc[1] : acc[0];
+    acc[0] = keep + shfl_xor_d(send, TW / 8, tmask);
+  }
+#pragma unroll
+  for (int off = TW / 16; off > 0; off >>= 1) acc[0] += shfl_xor_d(acc[0], off, tmask);
+  if ((lane & (TW / 8 - 1)) == 0) {
+    double *d = dst + (h1 ? 4 : 0) + (h2 ? 2 : 0) + (h3 ? 1 : 0);
+    if constexpr (ACC) *d = add ? *d + acc[0] : acc[0];
+    else *d = acc[0];
+  }
+}
+
 // shared-memory layout per team (bytes, all 16-aligned):
 //   psi [DIM] double2 | lam [DIM] double2 (GRAD) | rec [4 + ops_cap*5] u32
-//   | Us [ops_cap][4] double2 (STAGE_U) | red [2][WPT][8] f64 | ered [WPT] f64
-__host__ __device__ constexpr bool qas_stage_u(int N) { return N == 0 || N >= 9; }
+//   | Us [ops_cap][4] double2 (STAGE_U) | red [2][3][WPT][8] f64 (GRAD, multi-warp teams) | ered [WPT] f64
+__host__ __device__ constexpr bool qas_stage_u(int N) { return N == 0 || N >= 7; }
 __host__ __device__ inline size_t eval_team_smem_bytes(int n, int T, bool grad, int ops_cap,
                                                        bool state_in_smem, bool stage_u) {
   const size_t dim = (size_t)1 << n;
@@ -295,29 +403,145 @@ __host__ __device__ inline size_t eval_team_smem_bytes(int n, int T, bool grad, 
   if (state_in_smem) b += dim * 16 * (grad ? 2 : 1);
   b += (((size_t)(QAS_REC_HDR + ops_cap * QAS_OP_WORDS) * 4) + 15) & ~(size_t)15;
   if (stage_u) b += (size_t)ops_cap * 64;
-  b += (size_t)2 * wpt * 8 * 8;
+  if (grad && wpt > 1) b += (size_t)2 * 3 * wpt * 64;
   b += (((size_t)wpt * 8) + 15) & ~(size_t)15;
   return b;
 }
 
+// ---- one forward pass: G gates on the 2^G amplitudes of every coset, in registers
+template <int G, int T, bool SWZ, bool STAGE_U>
+__device__ __forceinline__ void fwd_group(double2 *psi, const uint32_t *o, int j, const double2 *Us,
+                                          const GateTab *Utab, uint32_t DIM, int tid) {
+  GroupGeom<G> gg;
+  gg.load(o);
+  double2 u[G][4];
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
+    const double2 *g = STAGE_U ? (Us + 4 * (j + q)) : Utab[o[q * QAS_OP_WORDS + 3]].u;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) u[q][e] = g[e];
+  }
+  const uint32_t rc = (G == 1) ? o[2] : 0u;
+  const uint32_t nper = DIM >> G;
+  constexpr int UNR = (8 >> G) > 0 ? (8 >> G) : 1;
+#pragma unroll UNR
+  for (uint32_t t = tid; t < nper; t += T) {
+    const uint32_t P = gg.base(t);
+    if (G == 1 && rc && !(__popc(P & rc) & 1)) continue;
+    double2 a[1 << G];
+#pragma unroll
+    for (int c = 0; c < (1 << G); ++c) a[c] = psi[sw<SWZ>(P ^ gg.xm[c])];
+#pragma unroll
+    for (int q = G - 1; q >= 0; --q) {       // time order = descending tape index
+#pragma unroll
+      for (int c = 0; c < (1 << G); ++c)
+        if (!((c >> q) & 1)) apply_u(a[c], a[c | (1 << q)], u[q]);
+    }
+#pragma unroll
+    for (int c = 0; c < (1 << G); ++c) psi[sw<SWZ>(P ^ gg.xm[c])] = a[c];
+  }
+}
+
+// ---- one adjoint pass: per gate (tape order)  psi <- U^ psi ; M += conj(lam) psi ; lam <- U^ lam
+// The 2x2 cross matrix M of a parametrised gate is reduced over the team's warp lanes and
+// published: single-warp teams write it straight to global memory (mout_op), multi-warp teams leave
+// per-warp partials in the shared-memory ring (summed in fixed warp order after the team barrier).
+// 3-gate passes reduce M right after each gate (one live accumulator instead of three: the 8 + 8
+// amplitudes already take 64 registers); 1- and 2-gate passes accumulate over the thread's cosets
+// first and reduce once.
+template <int G, int T, int TW, int WPT, bool SWZ, bool STAGE_U>
+__device__ __forceinline__ void adj_group(double2 *psi, double2 *lam, const uint32_t *o, int j,
+                                          const double2 *Us, const GateTab *Utab, uint32_t DIM, int tid,
+                                          int lane, int warp_in_team, uint32_t tmask, double *ring,
+                                          double *mout_op) {
+  constexpr bool EACH = (G == 3);
+  GroupGeom<G> gg;
+  gg.load(o);
+  int npar[G];
+#pragma unroll
+  for (int q = 0; q < G; ++q) npar[q] = qas_meta_npar(o[q * QAS_OP_WORDS + 4]);
+  double M[EACH ? 1 : G][8];
+  if constexpr (!EACH) {
+#pragma unroll
+    for (int q = 0; q < G; ++q)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) M[q][e] = 0.0;
+  }
+  const uint32_t rc = (G == 1) ? o[2] : 0u;
+  const uint32_t nper = DIM >> G;
+  constexpr int UNR = EACH ? 1 : ((4 >> G) > 0 ? (4 >> G) : 1);
+#pragma unroll UNR
+  for (uint32_t t = tid; t < nper; t += T) {
+    const uint32_t P = gg.base(t);
+    if (G == 1 && rc && !(__popc(P & rc) & 1)) continue;
+    double2 a[1 << G], l[1 << G];
+#pragma unroll
+    for (int c = 0; c < (1 << G); ++c) {
+      const uint32_t x = sw<SWZ>(P ^ gg.xm[c]);
+      a[c] = psi[x];
+      l[c] = lam[x];
+    }
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      double2 u[4];
+      const double2 *g = STAGE_U ? (Us + 4 * (j + q)) : Utab[o[q * QAS_OP_WORDS + 3]].u;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) u[e] = g[e];
+      double (&Mq)[8] = M[EACH ? 0 : q];
+      if constexpr (EACH) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) Mq[e] = 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < (1 << G); ++c) {
+        if ((c >> q) & 1) continue;
+        const int c1 = c | (1 << q);
+        apply_udag(a[c], a[c1], u);
+        if (npar[q]) macc(Mq, l[c], l[c1], a[c], a[c1]);
+        apply_udag(l[c], l[c1], u);
+      }
+      if constexpr (EACH) {
+        if (npar[q]) {
+          if constexpr (WPT == 1) reduce_store_m<TW, false>(Mq, lane, tmask, mout_op + (size_t)q * 8, false);
+          else reduce_store_m<TW, true>(Mq, lane, tmask, ring + ((size_t)q * WPT + warp_in_team) * 8, t != (uint32_t)tid);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < (1 << G); ++c) {
+      const uint32_t x = sw<SWZ>(P ^ gg.xm[c]);
+      psi[x] = a[c];
+      lam[x] = l[c];
+    }
+  }
+  if constexpr (!EACH) {
+#pragma unroll
+    for (int q = 0; q < G; ++q)
+      if (npar[q]) reduce_store_m<TW, false>(M[q], lane, tmask, WPT == 1 ? mout_op + (size_t)q * 8
+                                                                            : ring + ((size_t)q * WPT + warp_in_team) * 8, false);
+  }
+}
+
 // N > 0: compile-time qubit count, state in shared memory.  N == 0: run-time qubit count,
 // state in global memory (one team per CTA, L2/HBM resident) -- same code path otherwise.
-#ifndef QAS_MIN_CTAS
-#define QAS_MIN_CTAS 3
-#endif
-template <int N, int T, bool GRAD>
-__global__ void __launch_bounds__(256, QAS_MIN_CTAS) eval_kernel(const EvalParams P) {
+// GMAX = gates per fused pass, RB = log2(amplitudes per thread) in the H application, PD = depth of
+// the register ring that prefetches sign-table rows (L2 latency is the exposed cost there)
+template <int N, int T, bool GRAD, int GMAX, int RB, int PD, int MINB>
+__global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
   constexpr int TEAMS = 256 / T;
   constexpr int WPT = T >= 32 ? T / 32 : 1;      // warps per team
   constexpr int TW = T >= 32 ? 32 : T;           // lanes of one warp that belong to the team
-  constexpr int RB = qas_register_bits(N == 0 ? 20 : N, T);   // register bits of the H blocking
   constexpr bool STAGE_U = qas_stage_u(N);
+  constexpr bool SWZ = N != 0;
   const int n = N ? N : P.n;
-  const uint32_t DIM = 1u << n, HALF = DIM >> 1;
+  const uint32_t DIM = 1u << n;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
   const int team = threadIdx.x / T, tid = threadIdx.x % T;
   const int lane = threadIdx.x & 31, warp_in_team = tid >> 5;
+  // sub-warp teams synchronise and shuffle with their own lane mask, so the teams that share a
+  // warp run independent tapes without waiting on each other
+  const uint32_t tmask = T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << ((lane / TW) * TW));
   const size_t team_bytes = eval_team_smem_bytes(n, T, GRAD, P.ops_cap, N != 0, STAGE_U);
   unsigned char *base = smem_raw + (size_t)team * team_bytes;
   double2 *psi, *lam = nullptr;
@@ -335,67 +559,64 @@ __global__ void __launch_bounds__(256, QAS_MIN_CTAS) eval_kernel(const EvalParam
   base += (((size_t)rec_words * 4) + 15) & ~(size_t)15;
   double2 *Us = reinterpret_cast<double2 *>(base);
   if constexpr (STAGE_U) base += (size_t)P.ops_cap * 64;
-  double *red = reinterpret_cast<double *>(base);
-  base += (size_t)2 * WPT * 8 * 8;
+  double *red = nullptr;
+  if constexpr (GRAD && WPT > 1) { red = reinterpret_cast<double *>(base); base += (size_t)2 * 3 * WPT * 64; }
   double *ered = reinterpret_cast<double *>(base);
   // slice descriptors, shared by the CTA's teams
   uint32_t *sdesc = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TEAMS * team_bytes);
-  for (int s = threadIdx.x; s < P.S; s += 256) sdesc[s] = P.sdesc[s];
+  for (int s = threadIdx.x; s < P.C_real + P.C_imag; s += 256) sdesc[s] = P.cdesc[s];
   __syncthreads();
 
   for (int b0 = blockIdx.x * TEAMS; b0 < P.B; b0 += gridDim.x * TEAMS) {
     const int b = b0 + team;
-    const bool active = b < P.B;
-    if constexpr (T > 32) { if (!active) continue; }   // whole warps: nobody else waits on them
+    if (b >= P.B) continue;      // teams are independent: nobody waits on an idle one
+    constexpr bool active = true;
 
     // ---- 1. fetch the compiled tape record, zero the state / the gradient row
     {
       const uint32_t *grec = P.tape + (size_t)(active ? b : 0) * rec_words;
-      for (int w = tid; w < rec_words; w += T) rec[w] = active ? grec[w] : 0u;
+      const int used = active ? (int)(QAS_REC_HDR + grec[0] * QAS_OP_WORDS) : 0;
+      for (int w = tid; w < QAS_REC_HDR || w < used; w += T) rec[w] = active ? grec[w] : 0u;
       const double amp0 = (P.init_kind == QAS_INIT_PLUS) ? exp2(-0.5 * (double)n) : 0.0;
       for (uint32_t i = tid; i < DIM; i += T) psi[i] = make_double2(amp0, 0.0);
-      if (GRAD && active)
-        for (int i = tid; i < P.p * P.l; i += T) P.grad[(size_t)b * P.p * P.l + i] = 0.0;
     }
-    team_sync<T>(team);
+    team_sync<T>(team, tmask);
     const int nops = (int)rec[0];
     const int status = (int)rec[1];
-    if (tid == 0 && P.init_kind != QAS_INIT_PLUS) psi[rec[2]] = make_double2(1.0, 0.0);
+    const int ngroups = (int)rec[3];
+    if (tid == 0 && P.init_kind != QAS_INIT_PLUS) psi[sw<SWZ>(rec[2])] = make_double2(1.0, 0.0);
     if constexpr (STAGE_U) {   // gate matrices of this circuit -> shared memory (one round trip)
       for (int w = tid; w < nops * 4; w += T) Us[w] = P.U[ops[(w >> 2) * QAS_OP_WORDS + 3]].u[w & 3];
     }
-    int nloop = nops;
-    if constexpr (T < 32) nloop = __reduce_max_sync(0xffffffffu, nops);
-    team_sync<T>(team);
+    const int nloop = ngroups;
+    team_sync<T>(team, tmask);
 
-    // ---- 2. forward sweep (tape is stored last-gate-first)
-    for (int it = 0; it < nloop; ++it) {
-      const int j = nops - 1 - it;
-      if (j >= 0) {
-        const uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
-        const uint32_t m = o[0], r = o[1], rc = o[2];
-        const double2 *g = STAGE_U ? (Us + 4 * j) : P.U[o[3]].u;
-        if (qas_meta_kind(o[4]) == QAS_K_U1) {
-          const double2 u00 = g[0], u01 = g[1], u10 = g[2], u11 = g[3];
-          const int pb = 31 - __clz(r);
+    // ---- 2. forward sweep (tape is stored last-gate-first: walk the groups from the end)
+    {
+      int e = nops - 1;
+      for (int it = 0; it < nloop; ++it) {
+        if (e >= 0) {
+          const int g = (int)QAS_META_GLAST(ops[(size_t)e * QAS_OP_WORDS + 4]);
+          const int j = e - g + 1;
+          const uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
+          if (qas_meta_kind(o[4]) == QAS_K_U1) {
+            if (GMAX >= 3 && g == 3) { if constexpr (GMAX >= 3) fwd_group<3, T, SWZ, STAGE_U>(psi, o, j, Us, P.U, DIM, tid); }
+            else if (GMAX >= 2 && g == 2) { if constexpr (GMAX >= 2) fwd_group<2, T, SWZ, STAGE_U>(psi, o, j, Us, P.U, DIM, tid); }
+            else fwd_group<1, T, SWZ, STAGE_U>(psi, o, j, Us, P.U, DIM, tid);
+          } else {
+            const double2 *gm = STAGE_U ? (Us + 4 * j) : P.U[o[3]].u;
+            const double2 d0 = gm[0], d1 = gm[3];
+            const uint32_t r = o[1];
 #pragma unroll 4
-          for (uint32_t t = tid; t < HALF; t += T) {
-            uint32_t p0 = insert_zero(t, pb);
-            p0 |= (uint32_t)(__popc(p0 & r) & 1) << pb;
-            if (rc && !(__popc(p0 & rc) & 1)) continue;
-            const uint32_t p1 = p0 ^ m;
-            const double2 a0 = psi[p0], a1 = psi[p1];
-            psi[p0] = cfma(u01, a1, cmul(u00, a0));
-            psi[p1] = cfma(u11, a1, cmul(u10, a0));
+            for (uint32_t i = tid; i < DIM; i += T) {
+              const uint32_t x = sw<SWZ>(i);
+              psi[x] = cmul((__popc(i & r) & 1) ? d1 : d0, psi[x]);
+            }
           }
-        } else {
-          const double2 d0 = g[0], d1 = g[3];
-#pragma unroll 4
-          for (uint32_t i = tid; i < DIM; i += T)
-            psi[i] = cmul((__popc(i & r) & 1) ? d1 : d0, psi[i]);
+          e = j - 1;
         }
+        team_sync<T>(team, tmask);
       }
-      team_sync<T>(team);
     }
 
     // ---- 3. lambda = H psi, E = Re <psi|lambda>   (register-blocked over X-mask classes)
@@ -403,50 +624,49 @@ __global__ void __launch_bounds__(256, QAS_MIN_CTAS) eval_kernel(const EvalParam
     {
       constexpr int NB = 1 << RB;
       const uint32_t nrest = DIM >> RB;
-      uint32_t roff[NB];
-#pragma unroll
-      for (int j = 0; j < NB; ++j) roff[j] = qas_spread_reg((uint32_t)j, P.rb0, P.rb1, P.rb2);
+      const char *psib = reinterpret_cast<const char *>(psi);
       for (uint32_t u = tid; u < nrest; u += T) {
-        const uint32_t base_i = qas_deposit_rest(u, RB, P.rb0, P.rb1, P.rb2);
-        double2 acc[NB], a[NB];
+        const uint32_t sb16 = sw<SWZ>(qas_deposit_rest(u, RB, P.rb0, P.rb1, P.rb2)) << 4;
+        double2 acc[NB];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) { acc[j] = make_double2(0.0, 0.0); a[j] = acc[j]; }
-        // sign-table values are prefetched one slice ahead (L2 latency ~300 cycles)
-        const double *vp = P.vtab + u;
-        double vn[NB];
+        for (int j = 0; j < NB; ++j) acc[j] = make_double2(0.0, 0.0);
+        // sign-table rows are prefetched PD rows ahead through a register ring (L2 latency); the
+        // table ends with zero rows, so the prefetch never needs a bounds test
+        const double *vp = P.vtab + (size_t)u * (NB >= 2 ? 2 : 1);
+        double ring[PD][NB];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) vn[j] = __ldg(vp + (size_t)j * nrest);
-        for (int s = 0; s < P.S; ++s) {
-          const uint32_t d = sdesc[s];
-          double v[NB];
+        for (int d = 0; d < PD; ++d) load_vrow<NB>(ring[d], vp + ((size_t)d << n), nrest);
+        const int C = P.C_real + P.C_imag;
+        for (int cls = 0; cls < C; ++cls) {
+          const uint32_t r16 = sb16 ^ sdesc[cls];
+          double2 a[NB];
 #pragma unroll
-          for (int j = 0; j < NB; ++j) v[j] = vn[j];
-          if (s + 1 < P.S) {
-            const double *vq = vp + ((size_t)(s + 1) << n);
+          for (int j = 0; j < NB; ++j) a[j] = *reinterpret_cast<const double2 *>(psib + (r16 ^ P.wc16.w[j]));
+          const bool imag = cls >= P.C_real;
 #pragma unroll
-            for (int j = 0; j < NB; ++j) vn[j] = __ldg(vq + (size_t)j * nrest);
+          for (int jw = 0; jw < NB; ++jw) {
+            double v[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) v[j] = ring[jw % PD][j];
+            load_vrow<NB>(ring[jw % PD], vp + ((size_t)(jw + PD) << n), nrest);
+            hacc_row<NB>(acc, a, v, jw, imag);
           }
-          if (d & QAS_SD_NEWCLASS) {
-            const uint32_t pb = base_i ^ (d & QAS_SD_XREST);
-#pragma unroll
-            for (int j = 0; j < NB; ++j) a[j] = psi[pb | roff[j]];
-          }
-          hacc_dispatch<NB>(acc, a, v, QAS_SD_XH(d), (d & QAS_SD_IMAG) != 0);
+          vp += (size_t)NB << n;
         }
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-          const uint32_t i = base_i | roff[j];
-          const double2 ai = psi[i];
+          const uint32_t off = sb16 ^ P.wc16.w[j];
+          const double2 ai = *reinterpret_cast<const double2 *>(psib + off);
           e_part = fma(ai.x, acc[j].x, fma(ai.y, acc[j].y, e_part));
-          if constexpr (GRAD) lam[i] = acc[j];
+          if constexpr (GRAD) *reinterpret_cast<double2 *>(reinterpret_cast<char *>(lam) + off) = acc[j];
         }
       }
     }
 #pragma unroll
-    for (int off = TW / 2; off > 0; off >>= 1) e_part += shfl_xor_d(e_part, off);
+    for (int off = TW / 2; off > 0; off >>= 1) e_part += shfl_xor_d(e_part, off, tmask);
     if constexpr (WPT > 1) {
       if (lane == 0) ered[warp_in_team] = e_part;
-      team_sync<T>(team);
+      team_sync<T>(team, tmask);
       if (tid == 0) {
         double e = 0.0;
 #pragma unroll
@@ -454,130 +674,90 @@ __global__ void __launch_bounds__(256, QAS_MIN_CTAS) eval_kernel(const EvalParam
         e_part = e;
       }
     } else if constexpr (GRAD) {
-      team_sync<T>(team);      // lambda visible to the whole team
+      team_sync<T>(team, tmask);      // lambda visible to the whole team
     }
     if (tid == 0 && active) P.energy[b] = status ? __longlong_as_double(0x7ff8000000000000ll) : e_part;
 
-    // ---- 4. adjoint sweep (tape order = reverse time order)
+    // ---- 4. adjoint sweep (tape order = reverse time order), then the gradient finalize
     if constexpr (GRAD) {
+      int j = 0;
       for (int it = 0; it < nloop; ++it) {
-        const bool live = it < nops;
-        const uint32_t *o = ops + (size_t)(live ? it : 0) * QAS_OP_WORDS;
-        const uint32_t m = o[0], r = o[1], rc = o[2], tab = o[3], mt = o[4];
-        const int npar = live ? qas_meta_npar(mt) : 0;
-        // lanes of the team's first warp prefetch dU/dtheta entries: lane l holds (dU_j)_{l%4} with
-        // j = l/4 (teams of >= 16 lanes) or j = round (8-lane teams); the load overlaps the pair loop
-        constexpr int ROUNDS = T >= 16 ? 1 : 3;
-        double2 dpre[ROUNDS];
-#pragma unroll
-        for (int rr = 0; rr < ROUNDS; ++rr) {
-          const int jj = T >= 16 ? (tid >> 2) : rr;
-          const bool valid = T >= 16 ? (tid < 4 * npar) : (tid < 4 && rr < npar);
-          dpre[rr] = valid ? P.dU[tab].d[jj][tid & 3] : make_double2(0.0, 0.0);
-        }
-        double acc[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-        if (live) {
-          const double2 *g = STAGE_U ? (Us + 4 * it) : P.U[tab].u;
-          if (qas_meta_kind(mt) == QAS_K_U1) {
-            const double2 u00 = g[0], u01 = g[1], u10 = g[2], u11 = g[3];
-            const int pb = 31 - __clz(r);
-#pragma unroll 2
-            for (uint32_t t = tid; t < HALF; t += T) {
-              uint32_t p0 = insert_zero(t, pb);
-              p0 |= (uint32_t)(__popc(p0 & r) & 1) << pb;
-              if (rc && !(__popc(p0 & rc) & 1)) continue;
-              const uint32_t p1 = p0 ^ m;
-              const double2 a0 = psi[p0], a1 = psi[p1];
-              const double2 q0 = cfma_conj(u10, a1, cmul_conj(u00, a0));   // U^dagger psi
-              const double2 q1 = cfma_conj(u11, a1, cmul_conj(u01, a0));
-              psi[p0] = q0;
-              psi[p1] = q1;
-              const double2 l0 = lam[p0], l1 = lam[p1];
-              if (npar) {   // M_ab += conj(l_a) q_b
-                acc[0] = fma(l0.x, q0.x, fma(l0.y, q0.y, acc[0])); acc[1] = fma(l0.x, q0.y, fma(-l0.y, q0.x, acc[1]));
-                acc[2] = fma(l0.x, q1.x, fma(l0.y, q1.y, acc[2])); acc[3] = fma(l0.x, q1.y, fma(-l0.y, q1.x, acc[3]));
-                acc[4] = fma(l1.x, q0.x, fma(l1.y, q0.y, acc[4])); acc[5] = fma(l1.x, q0.y, fma(-l1.y, q0.x, acc[5]));
-                acc[6] = fma(l1.x, q1.x, fma(l1.y, q1.y, acc[6])); acc[7] = fma(l1.x, q1.y, fma(-l1.y, q1.x, acc[7]));
-              }
-              lam[p0] = cfma_conj(u10, l1, cmul_conj(u00, l0));
-              lam[p1] = cfma_conj(u11, l1, cmul_conj(u01, l0));
-            }
+        if (j < nops) {
+          const uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
+          const int g = (int)QAS_META_GFIRST(o[4]);
+          double *ring = WPT > 1 ? red + (size_t)(it & 1) * 3 * WPT * 8 : nullptr;
+          double *mop = P.mout + ((size_t)b * P.ops_cap + j) * 8;
+          if (qas_meta_kind(o[4]) == QAS_K_U1) {
+            if (GMAX >= 3 && g == 3) { if constexpr (GMAX >= 3) adj_group<3, T, TW, WPT, SWZ, STAGE_U>(psi, lam, o, j, Us, P.U, DIM, tid, lane, warp_in_team, tmask, ring, mop); }
+            else if (GMAX >= 2 && g == 2) { if constexpr (GMAX >= 2) adj_group<2, T, TW, WPT, SWZ, STAGE_U>(psi, lam, o, j, Us, P.U, DIM, tid, lane, warp_in_team, tmask, ring, mop); }
+            else adj_group<1, T, TW, WPT, SWZ, STAGE_U>(psi, lam, o, j, Us, P.U, DIM, tid, lane, warp_in_team, tmask, ring, mop);
           } else {
-            const double2 d0 = g[0], d1 = g[3];
+            const double2 *gm = STAGE_U ? (Us + 4 * j) : P.U[o[3]].u;
+            const double2 d0 = gm[0], d1 = gm[3];
+            const uint32_t r = o[1];
+            const int npar = qas_meta_npar(o[4]);
+            double acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.0;
 #pragma unroll 2
             for (uint32_t i = tid; i < DIM; i += T) {
               const bool hi = __popc(i & r) & 1;
+              const uint32_t x = sw<SWZ>(i);
               const double2 d = hi ? d1 : d0;
-              const double2 q = cmul_conj(d, psi[i]);
-              const double2 lv = lam[i];
-              psi[i] = q;
+              const double2 q = cmul_conj(d, psi[x]);
+              const double2 lv = lam[x];
+              psi[x] = q;
               if (npar) {
                 const double re = fma(lv.x, q.x, lv.y * q.y), im = fma(lv.x, q.y, -lv.y * q.x);
                 if (hi) { acc[6] += re; acc[7] += im; } else { acc[0] += re; acc[1] += im; }
               }
-              lam[i] = cmul_conj(d, lv);
+              lam[x] = cmul_conj(d, lv);
             }
+            if (npar) reduce_store_m<TW, false>(acc, lane, tmask, WPT == 1 ? mop : ring + (size_t)warp_in_team * 8, false);
           }
-        }
-        // team reduction of the 2x2 cross matrix M (8 doubles): reduce-scatter butterfly
-        bool any_par = npar > 0;
-        if constexpr (T < 32) any_par = __any_sync(0xffffffffu, any_par);
-        if (any_par) {
-          const bool h1 = lane & (TW / 2), h2 = lane & (TW / 4), h3 = lane & (TW / 8);
+          if constexpr (WPT > 1) {
+            team_sync<T>(team, tmask);
+            // fixed-order sum of the warps' partials -> M of each parametrised op of the group
+            if (tid < 8 * g) {
+              const int q = tid >> 3, v = tid & 7;
+              if (qas_meta_npar(o[q * QAS_OP_WORDS + 4])) {
+                double m = 0.0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double send = h1 ? acc[q] : acc[q + 4], keep = h1 ? acc[q + 4] : acc[q];
-            acc[q] = keep + shfl_xor_d(send, TW / 2);
-          }
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const double send = h2 ? acc[q] : acc[q + 2], keep = h2 ? acc[q + 2] : acc[q];
-            acc[q] = keep + shfl_xor_d(send, TW / 4);
-          }
-          {
-            const double send = h3 ? acc[0] : acc[1], keep = h3 ? acc[1] : acc[0];
-            acc[0] = keep + shfl_xor_d(send, TW / 8);
-          }
-#pragma unroll
-          for (int off = TW / 16; off > 0; off >>= 1) acc[0] += shfl_xor_d(acc[0], off);
-          if ((lane & (TW / 8 - 1)) == 0 && npar) {
-            const int v = (h1 ? 4 : 0) + (h2 ? 2 : 0) + (h3 ? 1 : 0);
-            red[((it & 1) * WPT + warp_in_team) * 8 + v] = acc[0];
-          }
-        }
-        team_sync<T>(team);
-        // gradient of this gate: lane l = 4j+q contributes Re[(dU_j)_q * M_q]; 4-lane shuffle sum.
-        // (for T < 32 every lane of the warp takes part in the shuffles; only lanes tid < 12 count)
-        bool fin = npar > 0;
-        if constexpr (T < 32) fin = __any_sync(0xffffffffu, fin); else fin = fin && (tid < 32);
-        if (fin) {
-#pragma unroll
-          for (int rr = 0; rr < ROUNDS; ++rr) {
-            const int jj = T >= 16 ? (tid >> 2) : rr;
-            const bool valid = T >= 16 ? (tid < 4 * npar) : (tid < 4 && rr < npar);
-            double part = 0.0;
-            if (valid) {
-              const int q = tid & 3;
-              double mre = 0.0, mim = 0.0;
-#pragma unroll
-              for (int w = 0; w < WPT; ++w) {
-                mre += red[((it & 1) * WPT + w) * 8 + 2 * q];
-                mim += red[((it & 1) * WPT + w) * 8 + 2 * q + 1];
+                for (int wp = 0; wp < WPT; ++wp) m += ring[((size_t)q * WPT + wp) * 8 + v];
+                mop[(size_t)q * 8 + v] = m;
               }
-              part = dpre[rr].x * mre - dpre[rr].y * mim;
             }
-            part += shfl_xor_d(part, 1);
-            part += shfl_xor_d(part, 2);
-            if (valid && (tid & 3) == 0 && active && !status)
-              P.grad[((size_t)b * P.p + qas_meta_depth(mt)) * P.l + jj] = 2.0 * part;
           }
+          j += g;
         }
+        if constexpr (WPT == 1) team_sync<T>(team, tmask);
       }
     }
-    team_sync<T>(team);   // state buffers are reused by the next circuit of this team
+    team_sync<T>(team, tmask);   // state buffers are reused by the next circuit of this team
   }
+}
+
+// ------------------------------------------------------------------------------ gradient finalize
+// dE/dtheta_j = 2 Re sum_ab (dU_j)_ab M_ab for every parametrised op of every circuit: one thread
+// per (circuit, tape op, parameter slot).  Kept out of the evaluation kernel so that no team
+// waits on the dU table (L2 latency) between passes.  grad must be zero-filled beforehand.
+__global__ void grad_finalize_kernel(const uint32_t *tape, const double *mout, const GateDTab *dU, int B,
+                                     int p, int l, int ops_cap, double *grad) {
+  const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t)ops_cap * 3;
+  if (x >= (size_t)B * per) return;
+  const int b = (int)(x / per), rem = (int)(x % per), oi = rem / 3, jj = rem - oi * 3;
+  const uint32_t *rec = tape + (size_t)b * (QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS);
+  if (oi >= (int)rec[0] || rec[1]) return;
+  const uint32_t *o = rec + QAS_REC_HDR + (size_t)oi * QAS_OP_WORDS;
+  const uint32_t mt = o[4];
+  if (jj >= qas_meta_npar(mt) || jj >= l) return;
+  const double *m = mout + ((size_t)b * ops_cap + oi) * 8;
+  const double2 *d = dU[o[3]].d[jj];
+  double part = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) part += d[q].x * m[2 * q] - d[q].y * m[2 * q + 1];
+  grad[((size_t)b * p + qas_meta_depth(mt)) * l + jj] = 2.0 * part;
 }
 
 // ------------------------------------------------------------------------------ batch reduce

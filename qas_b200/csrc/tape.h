@@ -174,6 +174,74 @@ QAS_HD int qas_compile_circuit(const int32_t *k, int p, const qas_pool_entry *po
   return s.overflow ? 2 : 0;
 }
 
+// ---- pass planner ----------------------------------------------------------------------------
+// Consecutive uncontrolled K_U1 ops (tape indices j .. j+g-1, g <= gmax <= 3) share ONE pass over
+// the state when every thread can own the 2^g amplitudes {P ^ span(m_0..m_{g-1})} and apply all
+// g gates in registers.  Condition: no cross terms, parity(m_a & r_b) = 0 for a != b (with
+// parity(m_a & r_a) = 1, which always holds, this makes the m's and the r's linearly independent
+// and makes the register index bit c_a of slot P ^ (c_0 m_0 ^ c_1 m_1 ^ c_2 m_2) equal to the
+// logical bit of gate a whenever r_a.P = 0 for all a).  The coset representatives P are the
+// common kernel of the r's; to enumerate it the planner replaces the r's of a group by their
+// reduced row-echelon form R_0..R_{g-1} (pivot = highest set bit, strictly descending, every
+// pivot column has a single 1): P = t with zeros inserted at the pivots, then pivot bit q set to
+// parity(P & R_q).  The grouping is greedy in tape order.  It is recorded in the meta words:
+// bits 24-25 = g on the FIRST op of a group (adjoint sweep walks up), bits 26-27 = g on the LAST
+// op (forward sweep walks down).  Returns the number of groups (= passes per sweep).
+#define QAS_META_GFIRST(m) (((m) >> 24) & 3u)
+#define QAS_META_GLAST(m) (((m) >> 26) & 3u)
+
+QAS_HD int qas_parity32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __popc(v) & 1;
+#else
+  return __builtin_popcount(v) & 1;
+#endif
+}
+QAS_HD int qas_msb32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz(v);
+#else
+  return 31 - __builtin_clz(v);
+#endif
+}
+QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax) {
+  int ngroups = 0;
+  for (int j = 0; j < nops;) {
+    uint32_t *a = ops + (size_t)j * QAS_OP_WORDS;
+    int g = 1;
+    if (qas_meta_kind(a[4]) == QAS_K_U1 && a[2] == 0u) {
+      while (g < gmax && j + g < nops) {
+        const uint32_t *b = ops + (size_t)(j + g) * QAS_OP_WORDS;
+        if (qas_meta_kind(b[4]) != QAS_K_U1 || b[2] != 0u) break;
+        bool ok = true;
+        for (int q = 0; q < g; ++q) {
+          const uint32_t *e = ops + (size_t)(j + q) * QAS_OP_WORDS;
+          if (qas_parity32(e[0] & b[1]) || qas_parity32(b[0] & e[1])) ok = false;
+        }
+        if (!ok) break;
+        ++g;
+      }
+    }
+    if (g > 1) {   // Gauss-Jordan on the parity functionals of the group
+      uint32_t R[3] = {0u, 0u, 0u};
+      for (int q = 0; q < g; ++q) R[q] = ops[(size_t)(j + q) * QAS_OP_WORDS + 1];
+      for (int i = 0; i < g; ++i) {
+        int best = i;
+        for (int q = i + 1; q < g; ++q) if (R[q] > R[best]) best = q;
+        const uint32_t t = R[i]; R[i] = R[best]; R[best] = t;
+        const int pv = qas_msb32(R[i]);
+        for (int q = 0; q < g; ++q) if (q != i && ((R[q] >> pv) & 1u)) R[q] ^= R[i];
+      }
+      for (int q = 0; q < g; ++q) ops[(size_t)(j + q) * QAS_OP_WORDS + 1] = R[q];
+    }
+    a[4] |= (uint32_t)g << 24;
+    ops[(size_t)(j + g - 1) * QAS_OP_WORDS + 4] |= (uint32_t)g << 26;
+    j += g;
+    ++ngroups;
+  }
+  return ngroups;
+}
+
 // physical index of a logical basis state in the end-of-circuit frame: S_0 * basis
 QAS_HD uint32_t qas_frame_map_basis(const uint32_t *col, int n, uint64_t basis) {
   uint32_t out = 0;

@@ -109,6 +109,43 @@ def test_tape_compiler_full_vocabulary_random():
         assert np.max(np.abs(got - ga)) < 1e-10
 
 
+@pytest.mark.parametrize("gmax", [2, 3])
+def test_pass_planner_fused_groups_match_oracle(gmax):
+    """Register-fused passes (qas_plan_groups + the kernel's coset enumeration, restated in
+    tape_interp.run_tape_planned) give the oracle's energies and gradients; every group tiles the
+    index space exactly once."""
+    rng = np.random.default_rng(5)
+    fused_any = 0
+    for trial, (n, pool, p) in enumerate([(5, helpers.near_cx_pool(5, helpers.ring(5)), 14),
+                                          (6, helpers.near_cx_pool(6), 16),
+                                          (4, helpers.full_vocab_pool(4), 10),
+                                          (4, helpers.full_vocab_pool(4), 10)]):
+        c = len(pool)
+        if trial < 2:
+            k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": p // 2}, 1, seed=trial)[0]]
+        else:
+            k = [int(x) for x in rng.integers(0, c, size=p)]
+        params = rng.standard_normal((p, c, 3))
+        words = ["".join(rng.choice(list("IXYZ"), size=n)) for _ in range(6)]
+        terms = [(float(rng.standard_normal()), w) for w in words]
+        init = [("zero", 0), ("basis", int(rng.integers(0, 1 << n))), ("plus", 0), ("zero", 0)][trial]
+        ops, idx = compile_tape_host(n, pool, k, init[1] if init[0] == "basis" else 0)
+        planned, ng = TI.plan_passes(ops, gmax)
+        assert ng <= len(ops)
+        fused_any += len(ops) - ng
+        # planning never touches masks, tables or depths
+        assert np.array_equal(planned[:, [0, 2, 3]], ops[:, [0, 2, 3]])
+        assert np.array_equal(planned[:, 4] & 0xFFFFFF, ops[:, 4])
+        e, gr = TI.run_tape_planned(n, planned, init, idx, pool.pool, c, params, terms)
+        assert abs(e - sim.energy(n, k, pool.pool, params, terms, init)) < 1e-11
+        ga = sim.grad_adjoint(n, k, pool.pool, params, terms, init)
+        got = np.zeros_like(ga)
+        for (d, j), v in gr.items():
+            got[d, k[d], j] = v
+        assert np.max(np.abs(got - ga)) < 1e-10
+    assert fused_any > 0
+
+
 def test_tape_compiler_rejects_out_of_range_keys():
     pool = helpers.near_cx_pool(4)
     with pytest.raises(AssertionError):
