@@ -3,6 +3,7 @@
 // C ABI: include/qas_b200_sv.h.  HBM-bandwidth bound: 32 * 2^n_local bytes per pass.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -29,21 +30,37 @@ extern "C" const char *qas_sv_last_error(void) { return g_sv_error.c_str(); }
 #define SV_MAX_TILE_BITS 13
 #define SV_THREADS 256
 
-struct SvTileGate {
-  int kind;            // QAS_SV_U1 / QAS_SV_PDIAG
-  int tbit;            // tile bit index of the target (U1)
-  int cbit_tile;       // tile bit index of the control, -1 if none / outside
-  int cpos_out;        // slab bit position of a control outside the tile, -1 if none
+#define SV_K_U1 0       // dense 2x2 on the target (optionally controlled)
+#define SV_K_PDIAG 1    // parity-diagonal phase
+#define SV_K_SWAPX 2    // (controlled) Pauli-X: a pure exchange of the pair, no arithmetic
+
+struct __align__(16) SvTileGate {
+  int kind;            // SV_K_*
+  int tslot;           // U1: register slot bit (0..2) of the target inside its group
+  int cslot;           // U1: register slot bit of the control, -1 if the control is not a slot bit
+  int cbit_tile;       // U1: tile bit index of a control that is a tile bit but not a slot bit, else -1
+  int cpos_out;        // U1: slab bit position of a control outside the tile, -1 if none
   uint32_t tmask;      // PDIAG: parity mask over tile bits
-  uint32_t pad;
   unsigned long long omask;   // PDIAG: parity mask over slab bits outside the tile
   double2 u[4];
+};
+
+// A group = consecutive gates of a pass whose targets fall on at most three tile bits tb[0..2]:
+// every thread holds the 8 amplitudes that differ in those bits and applies ALL gates of the
+// group in registers, so the tile goes through shared memory once per group instead of once per
+// gate (the un-grouped version was shared-memory-bandwidth bound at ~18 gates per pass).
+struct SvGroup {
+  int first, ngates;
+  int tb[3];           // ascending tile bit indices held in registers
+  int ls[3];           // coset-counter bit that trades places with counter bit 0 / 1 / 2 (see sv_swz)
 };
 
 struct SvBlockParams {
   double2 *state;
   const SvTileGate *gates;
-  int n_local, kb, c, ngates;
+  const SvGroup *groups;
+  const unsigned short *ctab;  // [ngroups][2^(kb-3)] swizzled tile index of every coset representative
+  int n_local, kb, c, ngates, ngroups;
   unsigned char bits[16];      // ascending slab positions of the tile bits; bits[0..c-1] = 0..c-1
 };
 
@@ -53,19 +70,71 @@ __device__ __forceinline__ double2 sv_cmul(double2 a, double2 b) {
 __device__ __forceinline__ double2 sv_cfma(double2 a, double2 b, double2 c) {
   return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
 }
+__device__ __forceinline__ uint32_t sv_ins0(uint32_t t, int b) {
+  return ((t >> b) << (b + 1)) | (t & ((1u << b) - 1u));
+}
+// Shared-memory tiles are stored swizzled: the low three index bits are xor-ed with every higher
+// 3-bit group of the index, so index bit p lands on bank-group bit p mod 3.  A group's eight lanes
+// of a quarter-warp walk the coset counter bits 0..2; the host picks (SvGroup::ls) three non-register
+// tile bits with distinct p mod 3 for them, which makes every register-slot access conflict-free
+// whatever the target bits are (un-swizzled, gates on tile bits 0..2 were 8-way conflicted).
+__device__ __forceinline__ uint32_t sv_swz(uint32_t j) {
+  uint32_t f = j >> 3;
+  f ^= f >> 3;
+  f ^= f >> 6;
+  return j ^ (f & 7u);
+}
+__device__ __forceinline__ uint32_t sv_swapbits(uint32_t t, int a, int b) {
+  const uint32_t x = ((t >> a) ^ (t >> b)) & 1u;
+  return t ^ ((x << a) | (x << b));
+}
+// target on register slot bit Q; cm = mask of the register slot bit that controls the gate (0: none)
+template <int Q>
+__device__ __forceinline__ void sv_apply_slot(double2 (&a)[8], const double2 (&u)[4], uint32_t cm) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if ((c >> Q) & 1) continue;
+    if ((c & cm) != cm) continue;
+    const int c1 = c | (1 << Q);
+    const double2 a0 = a[c], a1 = a[c1];
+    a[c] = sv_cfma(u[1], a1, sv_cmul(u[0], a0));
+    a[c1] = sv_cfma(u[3], a1, sv_cmul(u[2], a0));
+  }
+}
+// (controlled) Pauli-X: exchange the pair, no arithmetic
+template <int Q>
+__device__ __forceinline__ void sv_swap_slot(double2 (&a)[8], uint32_t cm) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if ((c >> Q) & 1) continue;
+    const bool sw = (c & cm) == cm;
+    const int c1 = c | (1 << Q);
+    const double2 a0 = a[c], a1 = a[c1];
+    a[c] = sw ? a1 : a0;
+    a[c1] = sw ? a0 : a1;
+  }
+}
 
 // One CTA per tile.  Tile element j (kb bits) lives at slab index base | spread(j): the low c
 // bits are contiguous (coalesced 16*2^c-byte runs), the others are scattered by offs[].
-__global__ void __launch_bounds__(SV_THREADS) sv_block_kernel(const SvBlockParams P) {
+// dynamic shared memory: tile [2^kb] double2 | gates [ngates] SvTileGate
+template <int MINB>
+__global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBlockParams P) {
   extern __shared__ __align__(16) double2 tile[];
   __shared__ unsigned long long offs[1 << (SV_MAX_TILE_BITS - 5)];
   __shared__ unsigned long long s_base;
   const int kb = P.kb, c = P.c;
   const uint32_t tsize = 1u << kb, nhi = 1u << (kb - c), lowmask = (1u << c) - 1u;
+  SvTileGate *sg = reinterpret_cast<SvTileGate *>(tile + tsize);
   for (uint32_t h = threadIdx.x; h < nhi; h += SV_THREADS) {
     unsigned long long o = 0;
     for (int q = c; q < kb; ++q) o |= (unsigned long long)((h >> (q - c)) & 1u) << P.bits[q];
     offs[h] = o;
+  }
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(P.gates);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(sg);
+    for (uint32_t w = threadIdx.x; w < (uint32_t)(P.ngates * (sizeof(SvTileGate) / 4)); w += SV_THREADS) dst[w] = src[w];
   }
   const unsigned long long ntiles = 1ull << (P.n_local - kb);
   for (unsigned long long tid_ = blockIdx.x; tid_ < ntiles; tid_ += gridDim.x) {
@@ -82,37 +151,87 @@ __global__ void __launch_bounds__(SV_THREADS) sv_block_kernel(const SvBlockParam
     __syncthreads();
     const unsigned long long base = s_base;
     double2 *g = P.state + base;
-    for (uint32_t j = threadIdx.x; j < tsize; j += SV_THREADS) tile[j] = g[(j & lowmask) | offs[j >> c]];
-    __syncthreads();
-    for (int gi = 0; gi < P.ngates; ++gi) {
-      const SvTileGate *gt = P.gates + gi;
-      if (gt->kind == QAS_SV_U1) {
-        const bool on = gt->cpos_out < 0 || ((base >> gt->cpos_out) & 1ull);
-        if (on) {
-          const double2 u00 = gt->u[0], u01 = gt->u[1], u10 = gt->u[2], u11 = gt->u[3];
-          const int tb = gt->tbit, cb = gt->cbit_tile;
-          const uint32_t tbm = 1u << tb;
+    // HBM -> shared memory with cp.async: every thread has all of its 16-byte copies in flight at
+    // once (the register-staged loop kept 4, which left the kernel latency-bound at ~1.5 TB/s)
+    {
+      const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+      const uint32_t sw0 = sv_swz(threadIdx.x) * 16u;
 #pragma unroll 4
-          for (uint32_t t = threadIdx.x; t < (tsize >> 1); t += SV_THREADS) {
-            const uint32_t j0 = ((t >> tb) << (tb + 1)) | (t & (tbm - 1u));
-            if (cb >= 0 && !((j0 >> cb) & 1u)) continue;
-            const uint32_t j1 = j0 | tbm;
-            const double2 a0 = tile[j0], a1 = tile[j1];
-            tile[j0] = sv_cfma(u01, a1, sv_cmul(u00, a0));
-            tile[j1] = sv_cfma(u11, a1, sv_cmul(u10, a0));
+      for (uint32_t k = 0; k < tsize; k += SV_THREADS) {   // swz(tid | k) = swz(tid) ^ swz(k): disjoint bits
+        const uint32_t j = threadIdx.x | k;
+        if (j >= tsize) break;               // tiles smaller than the CTA (test sizes)
+        const double2 *src = g + ((j & lowmask) | offs[j >> c]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_s + (sw0 ^ (sv_swz(k) * 16u))), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    for (int gr = 0; gr < P.ngroups; ++gr) {
+      const SvGroup grp = P.groups[gr];
+      const int b0 = grp.tb[0], b1 = grp.tb[1], b2 = grp.tb[2];
+      const uint32_t s1 = 1u << b0, s2 = 1u << b1, s4 = 1u << b2;
+      const uint32_t w1 = sv_swz(s1), w2 = sv_swz(s2), w4 = sv_swz(s4);     // the swizzle is xor-linear
+      const unsigned short *ctab = P.ctab + ((size_t)gr << (kb - 3));
+      for (uint32_t t = threadIdx.x; t < (tsize >> 3); t += SV_THREADS) {
+        // coset representative from the host-built table (the index arithmetic -- bit swaps, zero
+        // insertion, swizzle -- was a third of the kernel's instructions)
+        const uint32_t Ps = __ldg(ctab + t);
+        const uint32_t Pj = sv_swz(Ps);       // the swizzle is an involution
+        uint32_t sm[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sm[q] = Ps ^ ((q & 1) ? w1 : 0u) ^ ((q & 2) ? w2 : 0u) ^ ((q & 4) ? w4 : 0u);
+        double2 a[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = tile[sm[q]];
+        for (int gi = grp.first; gi < grp.first + grp.ngates; ++gi) {
+          const SvTileGate *gt = sg + gi;
+          const int kind = gt->kind;
+          if (kind != SV_K_PDIAG) {
+            const int cpo = gt->cpos_out, cbt = gt->cbit_tile;
+            const bool on = (cpo < 0 || ((base >> cpo) & 1ull)) && (cbt < 0 || ((Pj >> cbt) & 1u));
+            if (on) {
+              const uint32_t cm = gt->cslot >= 0 ? (1u << gt->cslot) : 0u;
+              const int ts = gt->tslot;
+              if (kind == SV_K_U1) {
+                double2 u[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) u[e] = gt->u[e];
+                if (ts == 0) sv_apply_slot<0>(a, u, cm);
+                else if (ts == 1) sv_apply_slot<1>(a, u, cm);
+                else sv_apply_slot<2>(a, u, cm);
+              } else {
+                if (ts == 0) sv_swap_slot<0>(a, cm);
+                else if (ts == 1) sv_swap_slot<1>(a, cm);
+                else sv_swap_slot<2>(a, cm);
+              }
+            }
+          } else {
+            const bool flip = (__popcll(base & gt->omask) ^ __popc(Pj & gt->tmask)) & 1;
+            const double2 d0 = flip ? gt->u[3] : gt->u[0], d1 = flip ? gt->u[0] : gt->u[3];
+            const uint32_t tm = gt->tmask;
+            const uint32_t p1 = __popc(s1 & tm) & 1, p2 = __popc(s2 & tm) & 1, p4 = __popc(s4 & tm) & 1;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t par = ((q & 1) ? p1 : 0u) ^ ((q & 2) ? p2 : 0u) ^ ((q & 4) ? p4 : 0u);
+              a[q] = sv_cmul(par ? d1 : d0, a[q]);
+            }
           }
         }
-      } else {
-        const bool flip = __popcll(base & gt->omask) & 1;
-        const double2 d0 = flip ? gt->u[3] : gt->u[0], d1 = flip ? gt->u[0] : gt->u[3];
-        const uint32_t tm = gt->tmask;
-#pragma unroll 4
-        for (uint32_t j = threadIdx.x; j < tsize; j += SV_THREADS)
-          tile[j] = sv_cmul((__popc(j & tm) & 1) ? d1 : d0, tile[j]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tile[sm[q]] = a[q];
       }
       __syncthreads();
     }
-    for (uint32_t j = threadIdx.x; j < tsize; j += SV_THREADS) g[(j & lowmask) | offs[j >> c]] = tile[j];
+    {
+      const uint32_t sw0 = sv_swz(threadIdx.x);
+#pragma unroll 4
+      for (uint32_t k = 0; k < tsize; k += SV_THREADS) {
+        const uint32_t j = threadIdx.x | k;
+        if (j >= tsize) break;
+        g[(j & lowmask) | offs[j >> c]] = tile[sw0 ^ sv_swz(k)];
+      }
+    }
     __syncthreads();
   }
 }
@@ -278,60 +397,146 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
   }
   cudaStream_t st = (cudaStream_t)stream;
   int kb = tile_bits > 0 ? tile_bits : 12;
-  kb = std::min(std::min(kb, SV_MAX_TILE_BITS), n_local);
+  kb = std::max(3, std::min(std::min(kb, SV_MAX_TILE_BITS), n_local));
+  if (n_local < 3) { g_sv_error = "large-state mode needs at least 3 local qubits"; return QAS_ERR_UNSUPPORTED; }
   // c = contiguous low bits every tile contains (coalescing); leave at least one free tile bit
-  const int c = std::max(0, std::min(5, kb - 1));
+  int cwant = 5;
+  if (const char *ce = getenv("QAS_B200_SV_C")) cwant = std::max(0, atoi(ce));   // tuning knob
+  const int c = std::max(0, std::min(cwant, kb - 1));
   if (info) { info->passes = 0; info->tile_bits = kb; info->bytes_per_pass = 32.0 * (double)(1ull << n_local); info->last_ms = 0.0; }
   if (ngates == 0) return QAS_OK;
   std::vector<Block> blocks = plan_blocks(gates, ngates, n_local, kb, c);
   if (blocks.empty()) { g_sv_error = "gate blocking made no progress (tile_bits too small)"; return QAS_ERR_UNSUPPORTED; }
 
-  // translate every block's gates into tile coordinates, upload once
+  // translate every block's gates into tile coordinates and register groups, upload once
   std::vector<SvTileGate> tg;
-  std::vector<int> first(blocks.size() + 1, 0);
+  std::vector<SvGroup> groups;
+  std::vector<unsigned short> ctab;      // per group: swizzled tile index of every coset representative
+  auto h_ins0 = [](uint32_t t, int b) { return ((t >> b) << (b + 1)) | (t & ((1u << b) - 1u)); };
+  auto h_swap = [](uint32_t t, int a, int b) { const uint32_t x = ((t >> a) ^ (t >> b)) & 1u; return t ^ ((x << a) | (x << b)); };
+  auto h_swz = [](uint32_t j) { uint32_t f = j >> 3; f ^= f >> 3; f ^= f >> 6; return j ^ (f & 7u); };
+  std::vector<int> first(blocks.size() + 1, 0), gfirst(blocks.size() + 1, 0);
   for (size_t bi = 0; bi < blocks.size(); ++bi) {
     const Block &blk = blocks[bi];
     std::vector<int> tix(n_local, -1);
     for (size_t q = 0; q < blk.bits.size(); ++q) tix[blk.bits[q]] = (int)q;
+    const int gate0 = (int)tg.size();
+    std::vector<int> cur_bits;      // tile bits (targets) of the open group
+    int cur_first = 0;              // first gate (index relative to the block) of the open group
+    auto close_group = [&](int end_rel) {
+      if (end_rel == cur_first) return;
+      // pad the register bits with the highest free tile bits (low bits stay with the lanes)
+      for (int b = kb - 1; b >= 0 && (int)cur_bits.size() < 3; --b)
+        if (std::find(cur_bits.begin(), cur_bits.end(), b) == cur_bits.end()) cur_bits.push_back(b);
+      std::sort(cur_bits.begin(), cur_bits.end());
+      SvGroup gr{};
+      gr.first = cur_first; gr.ngates = end_rel - cur_first;
+      for (int q = 0; q < 3; ++q) gr.tb[q] = cur_bits[q];
+      {   // coset-counter bit i sits on the i-th non-register tile bit (ascending).  Counter bits 0..2
+          // are the lanes of a quarter-warp: move each of them (by a swap with a counter bit >= 3, or
+          // not at all) so that the three positions they land on are distinct modulo 3 (see sv_swz).
+        std::vector<int> npos;
+        for (int b = 0; b < kb; ++b) if (std::find(cur_bits.begin(), cur_bits.end(), b) == cur_bits.end()) npos.push_back(b);
+        const int m = (int)npos.size();
+        for (int q = 0; q < 3; ++q) gr.ls[q] = q;
+        bool done = m < 3;
+        for (int k0 = 0; k0 < m && !done; k0 = (k0 == 0 ? 3 : k0 + 1))
+          for (int k1 = 1; k1 < m && !done; k1 = (k1 == 1 ? 3 : k1 + 1))
+            for (int k2 = 2; k2 < m && !done; k2 = (k2 == 2 ? 3 : k2 + 1)) {
+              if (k0 == k1 || k0 == k2 || k1 == k2) continue;
+              const int r0 = npos[k0] % 3, r1 = npos[k1] % 3, r2 = npos[k2] % 3;
+              if (r0 != r1 && r0 != r2 && r1 != r2) { gr.ls[0] = k0; gr.ls[1] = k1; gr.ls[2] = k2; done = true; }
+            }
+      }
+      // slot indices of the group's gates
+      for (int r = cur_first; r < end_rel; ++r) {
+        SvTileGate &t = tg[gate0 + r];
+        if (t.kind == SV_K_PDIAG) continue;
+        const int tb_ = t.tslot;    // holds the tile bit until the group closes
+        t.tslot = (int)(std::find(cur_bits.begin(), cur_bits.end(), tb_) - cur_bits.begin());
+        if (t.cbit_tile >= 0) {
+          auto it = std::find(cur_bits.begin(), cur_bits.end(), t.cbit_tile);
+          if (it != cur_bits.end()) { t.cslot = (int)(it - cur_bits.begin()); t.cbit_tile = -1; }
+        }
+      }
+      for (uint32_t t = 0; t < (1u << (kb - 3)); ++t) {
+        const uint32_t tp = h_swap(h_swap(h_swap(t, 0, gr.ls[0]), 1, gr.ls[1]), 2, gr.ls[2]);
+        ctab.push_back((unsigned short)h_swz(h_ins0(h_ins0(h_ins0(tp, gr.tb[0]), gr.tb[1]), gr.tb[2])));
+      }
+      groups.push_back(gr);
+      cur_bits.clear();
+      cur_first = end_rel;
+    };
+    int rel = 0;
     for (int gi : blk.gates) {
       const qas_sv_gate &g = gates[gi];
       SvTileGate t{};
       t.kind = g.kind;
-      t.tbit = -1; t.cbit_tile = -1; t.cpos_out = -1;
+      t.tslot = -1; t.cslot = -1; t.cbit_tile = -1; t.cpos_out = -1;
       if (g.kind == QAS_SV_U1) {
-        t.tbit = tix[g.target];
+        const int tb_ = tix[g.target];
+        if (std::find(cur_bits.begin(), cur_bits.end(), tb_) == cur_bits.end()) {
+          if ((int)cur_bits.size() == 3) close_group(rel);
+          cur_bits.push_back(tb_);
+        }
+        t.tslot = tb_;
         if (g.control >= 0) { if (tix[g.control] >= 0) t.cbit_tile = tix[g.control]; else t.cpos_out = g.control; }
       } else {
         for (int b = 0; b < n_local; ++b)
           if ((g.mask >> b) & 1ull) { if (tix[b] >= 0) t.tmask |= 1u << tix[b]; else t.omask |= 1ull << b; }
       }
       for (int q = 0; q < 4; ++q) t.u[q] = make_double2(g.m[2 * q], g.m[2 * q + 1]);
+      if (g.kind == QAS_SV_U1 && g.m[0] == 0.0 && g.m[1] == 0.0 && g.m[6] == 0.0 && g.m[7] == 0.0 &&
+          g.m[2] == 1.0 && g.m[3] == 0.0 && g.m[4] == 1.0 && g.m[5] == 0.0)
+        t.kind = SV_K_SWAPX;        // PauliX / CNOT: exchange the pair, no flops
       tg.push_back(t);
+      ++rel;
     }
+    close_group(rel);
     first[bi + 1] = (int)tg.size();
+    gfirst[bi + 1] = (int)groups.size();
   }
+  unsigned short *d_ctab = nullptr;
+  SVCK(cudaMallocAsync((void **)&d_ctab, ctab.size() * sizeof(unsigned short), st));
+  SVCK(cudaMemcpyAsync(d_ctab, ctab.data(), ctab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, st));
+  SvGroup *d_groups = nullptr;
+  SVCK(cudaMallocAsync((void **)&d_groups, groups.size() * sizeof(SvGroup), st));
+  SVCK(cudaMemcpyAsync(d_groups, groups.data(), groups.size() * sizeof(SvGroup), cudaMemcpyHostToDevice, st));
   SvTileGate *d_gates = nullptr;
   SVCK(cudaMallocAsync((void **)&d_gates, tg.size() * sizeof(SvTileGate), st));
   SVCK(cudaMemcpyAsync(d_gates, tg.data(), tg.size() * sizeof(SvTileGate), cudaMemcpyHostToDevice, st));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (info && sync) { SVCK(cudaEventCreate(&e0)); SVCK(cudaEventCreate(&e1)); SVCK(cudaEventRecord(e0, st)); }
-  const size_t smem = (size_t)16 << kb;
-  SVCK(cudaFuncSetAttribute(sv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  size_t max_gates = 0;
+  for (size_t bi = 0; bi < blocks.size(); ++bi) max_gates = std::max<size_t>(max_gates, first[bi + 1] - first[bi]);
+  const size_t smem_max = ((size_t)16 << kb) + max_gates * sizeof(SvTileGate);
+  if (smem_max > 227 * 1024) { g_sv_error = "too many gates in one pass for the shared-memory gate table"; return QAS_ERR_UNSUPPORTED; }
+  int minb = 3;
+  if (const char *mb = getenv("QAS_B200_SV_MINB")) minb = atoi(mb) == 2 ? 2 : 3;   // tuning knob
+  SVCK(cudaFuncSetAttribute(sv_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  SVCK(cudaFuncSetAttribute(sv_block_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   const unsigned long long ntiles = 1ull << (n_local - kb);
   const int grid = (int)std::min<unsigned long long>(ntiles, 1u << 20);
   for (size_t bi = 0; bi < blocks.size(); ++bi) {
     SvBlockParams P{};
     P.state = (double2 *)state;
     P.gates = d_gates + first[bi];
+    P.groups = d_groups + gfirst[bi];
+    P.ctab = d_ctab + ((size_t)gfirst[bi] << (kb - 3));
     P.n_local = n_local; P.kb = kb; P.c = c; P.ngates = first[bi + 1] - first[bi];
+    P.ngroups = gfirst[bi + 1] - gfirst[bi];
     for (int q = 0; q < kb; ++q) P.bits[q] = (unsigned char)blocks[bi].bits[q];
-    sv_block_kernel<<<grid, SV_THREADS, smem, st>>>(P);
+    const size_t smem = ((size_t)16 << kb) + (size_t)P.ngates * sizeof(SvTileGate);
+    if (minb == 2) sv_block_kernel<2><<<grid, SV_THREADS, smem, st>>>(P);
+    else sv_block_kernel<3><<<grid, SV_THREADS, smem, st>>>(P);
     SVCK(cudaGetLastError());
   }
   // the upload buffer must outlive the kernels: tg is host memory copied asynchronously from a
   // pageable vector, so wait for the copy before it goes out of scope
   if (info && sync) SVCK(cudaEventRecord(e1, st));
   SVCK(cudaFreeAsync(d_gates, st));
+  SVCK(cudaFreeAsync(d_groups, st));
+  SVCK(cudaFreeAsync(d_ctab, st));
   SVCK(cudaStreamSynchronize(st));
   if (info) {
     info->passes = (int)blocks.size();
