@@ -124,12 +124,19 @@ int qas_compile_tape_host(int n_qubits, const qas_pool_entry *pool, int c, int p
                           const int32_t *k, uint64_t init_basis, uint32_t *out_ops, int max_ops,
                           int *num_ops, uint32_t *init_index);
 
-/* Pass planner (host run of the code the tape-compile kernel executes): groups consecutive
- * uncontrolled 2x2 ops of a compiled tape into register-fused passes of up to gmax <= 3 gates.
- * Rewrites, in place, the target parity masks of grouped ops to their reduced row-echelon form
- * and records the group sizes in meta bits 24-25 (first op of a group) and 26-27 (last op).
- * No reference counterpart (PennyLane applies one gate per tensordot).                       */
-int qas_plan_passes_host(uint32_t *ops, int num_ops, int gmax, int *num_groups);
+/* Pass planner (host run of the code the tape-compile kernel executes on a compiled tape).
+ * (1) groups consecutive uncontrolled 2x2 ops into register-fused passes of up to gmax <= 3 gates
+ *     (group sizes go into meta bits 24-25 of the first and 26-27 of the last op of a group);
+ * (2) tracks the affine support  init_index ^ span(xor masks applied so far)  of the state and
+ *     writes one descriptor {P0, dc, X_0 .. X_{n-1-g}} of 2 + n_qubits words per group to gdesc
+ *     (tape order of the groups): coset representative t of a group is P0 ^ xor of the X_i selected
+ *     by the bits of t, and only the cosets t < 2^dc can hold non-zero amplitudes after the group.
+ * init_kind / init_index as in qas_compile_tape; swizzled = order the X_i for the shared-memory
+ * slot layout.  gdesc may be NULL (grouping only).  No reference counterpart (PennyLane applies
+ * one gate per tensordot to the dense state).                                                 */
+int qas_plan_passes_host(int n_qubits, uint32_t *ops, int num_ops, int gmax, int init_kind,
+                         uint32_t init_index, int swizzled, uint32_t *gdesc, int gdesc_words,
+                         int *num_groups);
 
 /* Counters since context creation: evaluations and kernel launches; device time of the
  * last call's kernels (ms, CUDA events on the launch stream; host-pointer calls only) and of
@@ -146,6 +153,12 @@ typedef struct {
   int path;                 /* 0 = shared-memory resident, 1 = global-memory resident */
 } qas_stats;
 int qas_get_stats(const qas_ctx *ctx, qas_stats *out);
+
+/* Diagnostic (contexts created with the environment variable QAS_B200_PHASE_CLOCKS=1 only): sums,
+ * over all circuits evaluated so far, of the SM clock cycles a team spent in the four phases of the
+ * evaluation kernel -- out4 = {prologue, forward sweep, H application + energy, adjoint sweep}.
+ * Synchronises the device.  Used by tools/phase_clocks.py to see where a circuit's latency goes.   */
+int qas_debug_phase_clocks(qas_ctx *ctx, uint64_t *out4, int reset);
 
 /* Measured FP64 roofline denominator: runs a dependent-chain-free DFMA micro-benchmark on
  * `device` and returns the best of `reps` timings in TFLOP/s (2 flop per DFMA).            */

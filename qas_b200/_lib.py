@@ -71,7 +71,7 @@ _lib = None
 EXPORTS = [
     "qas_abi_version", "qas_build_info", "qas_ctx_create", "qas_ctx_destroy", "qas_last_error",
     "qas_eval_batch", "qas_compile_tape", "qas_compile_tape_host", "qas_plan_passes_host",
-    "qas_get_stats",
+    "qas_get_stats", "qas_debug_phase_clocks",
     "qas_fp64_peak_tflops",
 ]
 # include/qas_b200_sv.h
@@ -111,7 +111,10 @@ def load():
                                           ctypes.POINTER(ctypes.c_int),
                                           ctypes.POINTER(ctypes.c_uint32)]
     lib.qas_plan_passes_host.restype = ctypes.c_int
-    lib.qas_plan_passes_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.qas_plan_passes_host.argtypes = [ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
+                                         ctypes.c_int, vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.qas_debug_phase_clocks.restype = ctypes.c_int
+    lib.qas_debug_phase_clocks.argtypes = [vp, vp, ctypes.c_int]
     lib.qas_get_stats.restype = ctypes.c_int
     lib.qas_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.qas_fp64_peak_tflops.restype = ctypes.c_int

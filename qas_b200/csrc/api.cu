@@ -32,7 +32,9 @@ struct qas_ctx {
   int num_classes = 0, C_real = 0, C_imag = 0;
   uint32_t *d_cdesc_plain = nullptr;
   double *d_mout = nullptr; size_t cap_mout = 0;
+  unsigned long long *d_phase = nullptr;   // QAS_B200_PHASE_CLOCKS=1: per-phase clock sums (diagnostic)
   int RBH = 0, PD = 1;             // H-apply blocking / prefetch depth (QAS_B200_HCFG=rb,pd overrides)
+  int gcfg_g = 0, gcfg_m = 0;      // QAS_B200_GCFG=gmax,minb tuning override (n = 8, 10 default teams)
   GateTab *d_U = nullptr;
   GateDTab *d_dU = nullptr;
   int tab_p = 0;
@@ -132,7 +134,10 @@ static void fill_const_table(std::vector<GateTab> &t) {
 constexpr int team_threads(int n) {
   return n <= 4 ? 8 : n == 5 ? 16 : n <= 8 ? 32 : n == 9 ? 64 : n == 10 ? 128 : 256;
 }
-constexpr int qas_gmax(int n, int T) { return qas_block_bits(n, T) > 1 ? qas_block_bits(n, T) : 1; }
+// gates per fused pass: 2 where the team has the amplitudes for it.  3-gate passes (8 + 8 amplitudes
+// in registers) measured slower once the passes became support-restricted: the kernel is bound by
+// per-pass latency at 4 teams per SM, and the 2-gate code needs no spills inside 128 registers.
+constexpr int qas_gmax(int n, int T) { return qas_block_bits(n, T) >= 2 ? 2 : 1; }
 // H application: 4 amplitudes per thread and a 2-deep prefetch ring where the team has the
 // amplitudes for it (measured best on LiH-10q / H2O-8q among (3,1) (3,2) (2,2) (2,4))
 constexpr int qas_hrb(int n, int T) { return qas_block_bits(n, T) >= 2 ? 2 : qas_block_bits(n, T); }
@@ -256,10 +261,16 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
 
   // threads per team, amplitudes per thread of the fused gate passes and of the H application
   if (const char *ts = getenv("QAS_B200_TEAM_SHIFT")) cx->team_shift = atoi(ts);
+  const bool want_phase = getenv("QAS_B200_PHASE_CLOCKS") && atoi(getenv("QAS_B200_PHASE_CLOCKS")) != 0;
   cx->T = team_threads_for(n_qubits, cx->team_shift);
   cx->GMAX = qas_gmax(n_qubits <= 13 ? n_qubits : 20, cx->T);
   cx->RB = qas_hrb(n_qubits <= 13 ? n_qubits : 20, cx->T);
   cx->PD = qas_hpd(n_qubits <= 13 ? n_qubits : 20, cx->T);
+  if (const char *gc = getenv("QAS_B200_GCFG")) {   // tuning: "gmax,min CTAs per SM" among the compiled variants
+    int gv = 0, mv = 0;
+    if (sscanf(gc, "%d,%d", &gv, &mv) == 2 && cx->team_shift == 0 &&
+        (n_qubits == 10 || n_qubits == 8) && mv == 2 && (gv == 1 || gv == 3)) { cx->gcfg_g = gv; cx->gcfg_m = mv; cx->GMAX = gv; }
+  }
   if (const char *hc = getenv("QAS_B200_HCFG")) {   // tuning: "rb,pd" among the compiled variants
     int rbv = 0, pdv = 0;
     if (sscanf(hc, "%d,%d", &rbv, &pdv) == 2 && (n_qubits == 8 || n_qubits == 10) && cx->team_shift == 0 &&
@@ -301,7 +312,7 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   std::vector<uint32_t> sx, cdesc_swz, cdesc_plain, tz;
   std::vector<int> sbegin;
   std::vector<double> tc;
-  auto swz = [](uint32_t i) { return i ^ (((i >> 3) & 1u) * 7u); };
+  auto swz = [](uint32_t i) { return qas_swz(i); };
   for (int imag = 0; imag < 2; ++imag) {
     std::vector<uint32_t> reps;
     for (auto &kv : slices) if (kv.first.second == imag) reps.push_back(W.reduce((uint32_t)kv.first.first));
@@ -347,6 +358,10 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   guard(cudaEventCreate(&cx->ek0), "cudaEventCreate");
   guard(cudaEventCreate(&cx->ek1), "cudaEventCreate");
   guard(cudaMalloc(&cx->d_pool, sizeof(qas_pool_entry) * c), "cudaMalloc pool");
+  if (want_phase) {
+    guard(cudaMalloc(&cx->d_phase, 8 * sizeof(unsigned long long)), "cudaMalloc phase clocks");
+    guard(cudaMemset(cx->d_phase, 0, 8 * sizeof(unsigned long long)), "cudaMemset phase clocks");
+  }
   guard(cudaMalloc(&cx->d_vtab, sizeof(double) * dim * cx->S), "cudaMalloc sign tables");
   guard(cudaMalloc(&cx->d_sdesc, 4 * std::max<size_t>(cdesc_swz.size(), 1)), "cudaMalloc cdesc");
   guard(cudaMalloc(&cx->d_cdesc_plain, 4 * std::max<size_t>(cdesc_plain.size(), 1)), "cudaMalloc cdesc");
@@ -381,13 +396,25 @@ extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_cdesc_plain);
   cudaFree(ctx->d_U); cudaFree(ctx->d_dU); cudaFree(ctx->d_k); cudaFree(ctx->d_params);
   cudaFree(ctx->d_energy); cudaFree(ctx->d_grad); cudaFree(ctx->d_partial); cudaFree(ctx->d_dense);
-  cudaFree(ctx->d_gstate); cudaFree(ctx->d_mout); cudaFree(ctx->d_tape);
+  cudaFree(ctx->d_gstate); cudaFree(ctx->d_mout); cudaFree(ctx->d_tape); cudaFree(ctx->d_phase);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ek0) cudaEventDestroy(ctx->ek0);
   if (ctx->ek1) cudaEventDestroy(ctx->ek1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+  return QAS_OK;
+}
+
+extern "C" int qas_debug_phase_clocks(qas_ctx *ctx, uint64_t *out4, int reset) {
+  if (!ctx || !out4) return QAS_ERR_INVALID;
+  if (!ctx->d_phase) return fail(ctx, QAS_ERR_UNSUPPORTED, "create the context with QAS_B200_PHASE_CLOCKS=1");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  unsigned long long h[8];
+  CK(cudaMemcpy(h, ctx->d_phase, sizeof h, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; ++i) out4[i] = h[i];
+  if (reset) CK(cudaMemset(ctx->d_phase, 0, sizeof h));
   return QAS_OK;
 }
 
@@ -412,11 +439,11 @@ static size_t sdesc_bytes(int S) { return (((size_t)S * 4) + 15) & ~(size_t)15; 
 // amplitudes and a 2x2 cross matrix in registers (128-register budget)
 constexpr int qas_minb(int n, int T) { return qas_block_bits(n, T) >= 2 ? 2 : 3; }
 
-template <int N, int T, bool GRAD, int RBH, int PD>
+template <int N, int T, bool GRAD, int RBH, int PD, int GMAX_ = 0, int MINB_ = 0>
 static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t st) {
   constexpr int TEAMS = 256 / T;
   const size_t smem = eval_team_smem_bytes(N, T, GRAD, P.ops_cap, true, qas_stage_u(N)) * TEAMS + sdesc_bytes(P.C_real + P.C_imag);
-  auto kern = eval_kernel<N, T, GRAD, qas_gmax(N, T), RBH, PD, qas_minb(N, T)>;
+  auto kern = eval_kernel<N, T, GRAD, (GMAX_ ? GMAX_ : qas_gmax(N, T)), RBH, PD, (MINB_ ? MINB_ : qas_minb(N, T))>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -434,7 +461,7 @@ static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t s
 template <bool GRAD>
 static cudaError_t launch_gmem(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
   const size_t smem = eval_team_smem_bytes(P.n, 256, GRAD, P.ops_cap, false, true) + sdesc_bytes(P.C_real + P.C_imag);
-  auto kern = eval_kernel<0, 256, GRAD, 3, 2, 2, 2>;
+  auto kern = eval_kernel<0, 256, GRAD, 2, 2, 2, 2>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -463,6 +490,10 @@ static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
   if (P.n <= nmax_smem) {
     const size_t smem = eval_team_smem_bytes(P.n, T, GRAD, P.ops_cap, true, qas_stage_u(P.n)) * (256 / T) + sdesc_bytes(P.C_real + P.C_imag);
     if (smem <= 227 * 1024) {
+#define QAS_GCASE(N_, T_, G_, M_) \
+  if (P.n == N_ && T == T_ && ctx->gcfg_g == G_ && ctx->gcfg_m == M_) return launch_smem<N_, T_, GRAD, 2, 2, G_, M_>(ctx, P, st);
+      QAS_GCASE(10, 128, 3, 2) QAS_GCASE(10, 128, 1, 2) QAS_GCASE(8, 32, 3, 2) QAS_GCASE(8, 32, 1, 2)
+#undef QAS_GCASE
 #define QAS_CASE(N_, T_)                                                              \
   if (P.n == N_ && T == T_ && ctx->RB == qas_hrb(N_, T_) && ctx->PD == qas_hpd(N_, T_)) \
     return launch_smem<N_, T_, GRAD, qas_hrb(N_, T_), qas_hpd(N_, T_)>(ctx, P, st);
@@ -479,7 +510,7 @@ static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
     }
   }
   // the global-memory instantiation is compiled for 256-thread teams, 3-gate passes, 4-amplitude H rows
-  if (ctx->T != 256 || ctx->RB != 2 || ctx->PD != 2 || ctx->GMAX != 3) return cudaErrorInvalidConfiguration;
+  if (ctx->T != 256 || ctx->RB != 2 || ctx->PD != 2 || ctx->GMAX != 2) return cudaErrorInvalidConfiguration;
   return launch_gmem<GRAD>(ctx, P, st);
 }
 
@@ -545,16 +576,16 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     P.cdesc = smem_path ? ctx->d_sdesc : ctx->d_cdesc_plain;
     for (int j = 0; j < 8; ++j) {
       const uint32_t w = ctx->wc.w[j];
-      P.wc16.w[j] = (smem_path ? (w ^ (((w >> 3) & 1u) * 7u)) : w) << 4;
+      P.wc16.w[j] = (smem_path ? qas_swz(w) : w) << 4;
     }
   }
-  P.energy = denergy; P.gstate = nullptr; P.mout = nullptr;
+  P.energy = denergy; P.gstate = nullptr; P.mout = nullptr; P.phase_clk = ctx->d_phase;
   P.init_basis = ctx->init_basis;
   P.B = B; P.p = p; P.c = c; P.l = l; P.n = ctx->n;
   P.ops_cap = std::max(1, p * ctx->max_expansion);
   P.init_kind = ctx->init_kind;
 
-  const size_t rec_words = QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS;
+  const size_t rec_words = qas_rec_words(P.ops_cap, ctx->n);
   CK(ensure(&ctx->d_tape, &ctx->cap_tape, rec_words * (size_t)B));
   P.tape = ctx->d_tape;
 
@@ -565,8 +596,9 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
 
   if (!dev) CK(cudaEventRecord(ctx->ev0, st));
   if (want_grad) CK(cudaMemsetAsync(dgrad, 0, ng * 8, st));
-  compile_tapes_kernel<<<(B + 127) / 128, 128, 0, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap,
-                                                         ctx->init_kind, ctx->init_basis, ctx->GMAX, ctx->d_tape);
+  compile_tapes_kernel<<<(B + 63) / 64, 64, (size_t)64 * (2 * ctx->n + 1) * 4, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap,
+                                                         ctx->init_kind, ctx->init_basis, ctx->GMAX,
+                                                         ctx->n <= (want_grad ? 12 : 13) ? 1 : 0, ctx->d_tape);
   CK(cudaGetLastError());
   build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
   CK(cudaGetLastError());
@@ -578,13 +610,13 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   if (want_grad) {
     const size_t nthr = (size_t)B * P.ops_cap * 3;
     grad_finalize_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ctx->d_tape, ctx->d_mout, ctx->d_dU, B, p, l,
-                                                                        P.ops_cap, dgrad);
+                                                                        P.ops_cap, ctx->n, dgrad);
     CK(cudaGetLastError());
     ctx->stats.launches += 1;
   }
 
   if (grad_dense) {
-    const int chunk = 128;
+    const int chunk = 32;      // circuits per CTA of the first stage (2048 CTAs at B = 65536)
     const int nchunks = (B + chunk - 1) / chunk;
     int depth_tile = p;
     while ((size_t)depth_tile * c * l * 8 > 96 * 1024 && depth_tile > 1) depth_tile = (depth_tile + 1) / 2;
@@ -592,10 +624,11 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     CK(ensure(&ctx->d_partial, &ctx->cap_partial, (size_t)nchunks * npar));
     CK(cudaFuncSetAttribute(grad_chunk_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid(nchunks, (p + depth_tile - 1) / depth_tile);
-    grad_chunk_reduce_kernel<<<grid, 128, sm, st>>>(dk, dgrad, B, p, c, l, chunk, depth_tile, ctx->d_partial);
+    const int cthreads = std::min(256, std::max(64, ((std::min(depth_tile, p) * l + 31) / 32) * 32));
+    grad_chunk_reduce_kernel<<<grid, cthreads, sm, st>>>(dk, dgrad, B, p, c, l, chunk, depth_tile, ctx->d_partial);
     CK(cudaGetLastError());
     const double scale = (flags & QAS_F_GRAD_SUM) ? 1.0 : 1.0 / (double)B;
-    grad_final_reduce_kernel<<<(unsigned)((npar + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, scale, ddense);
+    grad_final_reduce_kernel<<<(unsigned)((npar * 32 + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, scale, ddense);
     CK(cudaGetLastError());
     ctx->stats.launches += 2;
   }
@@ -632,9 +665,13 @@ extern "C" int qas_compile_tape_host(int n_qubits, const qas_pool_entry *pool, i
   return QAS_OK;
 }
 
-extern "C" int qas_plan_passes_host(uint32_t *ops, int num_ops, int gmax, int *num_groups) {
-  if (!ops || num_ops < 0 || gmax < 1 || gmax > 3 || !num_groups) return QAS_ERR_INVALID;
-  *num_groups = qas_plan_groups(ops, num_ops, gmax);
+extern "C" int qas_plan_passes_host(int n_qubits, uint32_t *ops, int num_ops, int gmax, int init_kind,
+                                    uint32_t init_index, int swizzled, uint32_t *gdesc, int gdesc_words,
+                                    int *num_groups) {
+  if (!ops || num_ops < 0 || gmax < 1 || gmax > 3 || !num_groups || n_qubits < 1 || n_qubits > QAS_MAX_QUBITS)
+    return QAS_ERR_INVALID;
+  if (gdesc && gdesc_words < num_ops * QAS_GD_STRIDE(n_qubits)) return QAS_ERR_NOMEM;
+  *num_groups = qas_plan_groups(ops, num_ops, gmax, n_qubits, init_kind, init_index, gdesc, swizzled);
   return QAS_OK;
 }
 

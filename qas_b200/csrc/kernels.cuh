@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "tape.h"
 
 struct __align__(16) GateTab { double2 u[4]; };        // U00 U01 U10 U11
@@ -35,6 +36,7 @@ struct EvalParams {
   double *energy;              // [B]
   double2 *gstate;             // global-memory statevector scratch (path 1)
   double *mout;                // [B][ops_cap][8] cross matrices M of the parametrised ops (GRAD)
+  unsigned long long *phase_clk;   // diagnostic: summed per-team clock64 deltas [prologue, forward, H, adjoint] or null
   const uint32_t *tape;        // [B][4 + ops_cap*5] compiled tape records (compile_tapes_kernel)
   uint64_t init_basis;
   int B, p, c, l, n, ops_cap, init_kind;
@@ -281,33 +283,40 @@ __device__ __forceinline__ void load_vrow(double (&v)[NB], const double *p, uint
 
 // ------------------------------------------------------------------------------ tape compile
 // One thread per circuit: runs the tape compiler and the pass planner (tape.h) and writes a record
-//   [nops, status, init_index, ngroups | ops[ops_cap][5]]   (uint32)
-// to global memory.  Doing this in its own launch (B-way parallel) keeps the serial GF(2)
-// frame walk out of the evaluation teams' critical path; the records stay L2-resident.
+//   [nops, status, init_index, ngroups | ops[ops_cap][5] | gd[ops_cap][2 + n]]   (uint32)
+// to global memory.  Doing this in its own launch (B-way parallel) keeps the serial GF(2) work
+// out of the evaluation teams' critical path; the records stay L2-resident.
 #define QAS_REC_HDR 4
+__host__ __device__ __forceinline__ size_t qas_rec_words(int ops_cap, int n) {
+  return (size_t)QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS + (size_t)ops_cap * QAS_GD_STRIDE(n);
+}
 __global__ void compile_tapes_kernel(const int32_t *k, const qas_pool_entry *pool, int B, int p, int c,
                                      int n, int ops_cap, int init_kind, uint64_t init_basis,
-                                     int gmax, uint32_t *tape) {
+                                     int gmax, int swizzled, uint32_t *tape) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  uint32_t col[32], row[32];
-  uint32_t *rec = tape + (size_t)b * (QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS);
+  // GF(2) frame (col / row, indexed by wire at run time): shared memory, odd stride per thread
+  extern __shared__ uint32_t frame_smem[];
+  uint32_t *col = frame_smem + (size_t)threadIdx.x * (2 * n + 1), *row = col + n;
+  uint32_t *rec = tape + (size_t)b * qas_rec_words(ops_cap, n);
   QasTapeSink sink{rec + QAS_REC_HDR, ops_cap, 0, 0};
   const int st = qas_compile_circuit(k + (size_t)b * p, p, pool, c, n, col, row, sink);
   const int nops = st ? 0 : sink.n;
+  const uint32_t init_index = (init_kind == QAS_INIT_BASIS && !st) ? qas_frame_map_basis(col, n, init_basis) : 0u;
   rec[0] = (uint32_t)nops;
   rec[1] = (uint32_t)st;
-  rec[2] = (init_kind == QAS_INIT_BASIS && !st) ? qas_frame_map_basis(col, n, init_basis) : 0u;
-  rec[3] = (uint32_t)qas_plan_groups(rec + QAS_REC_HDR, nops, gmax);   // passes per sweep
+  rec[2] = init_index;
+  rec[3] = (uint32_t)qas_plan_groups(rec + QAS_REC_HDR, nops, gmax, n, init_kind, init_index,
+                                     rec + QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS, swizzled);   // passes per sweep
 }
 
 // ------------------------------------------------------------------------------ evaluation
-// Shared-memory statevectors are stored swizzled, slot(i) = i ^ (bit 3 of i ? 7 : 0): a pass
-// whose coset enumeration has a pivot below bit 3 would otherwise put two lanes of every
-// quarter-warp on the same 16-byte bank group (2-way conflicts on ~30 % of the gates).
+// Shared-memory statevectors are stored swizzled (qas_swz, tape.h): a pass whose cosets differ
+// only in high index bits would otherwise put the lanes of a quarter-warp on the same 16-byte bank
+// group.  The planner hands the gate passes slot coordinates, so only the dense loops evaluate it.
 template <bool SWZ>
 __device__ __forceinline__ uint32_t sw(uint32_t i) {
-  if constexpr (SWZ) return i ^ (((i >> 3) & 1u) * 7u);
+  if constexpr (SWZ) return qas_swz(i);
   return i;
 }
 __device__ __forceinline__ void apply_u(double2 &a0, double2 &a1, const double2 (&u)[4]) {
@@ -330,18 +339,26 @@ __device__ __forceinline__ void macc(double (&acc)[8], double2 l0, double2 l1, d
   acc[6] = fma(l1.x, q1.x, fma(l1.y, q1.y, acc[6])); acc[7] = fma(l1.x, q1.y, fma(-l1.y, q1.x, acc[7]));
 }
 
-// coset enumeration of one pass group (see qas_plan_groups): R = reduced parity functionals with
-// strictly descending pivots, xm[c] = xor of the gate masks selected by the bits of slot c
-template <int G>
+// coset enumeration of one pass group from its planner descriptor gd = {P0, dc, X_0 ..}: P(t) = P0 ^
+// xor of the X_i selected by the bits of t; the cosets t < 2^dc are the ones that can be non-zero
+// (see qas_plan_groups).  xm[c] = xor of the gate masks selected by the bits of slot c.
+// NXS = number of X vectors when known at compile time (they then live in registers), -1 otherwise
+// (run-time qubit count: read from the descriptor on every use).  GT = descriptor word type.
+template <int G, int NXS, typename GT>
 struct GroupGeom {
-  uint32_t R[G];
-  int pv[G];
   uint32_t xm[1 << G];
-  __device__ __forceinline__ void load(const uint32_t *o) {
+  uint32_t P0, nsup;
+  uint32_t X[NXS > 0 ? NXS : 1];
+  const GT *gd;
+  int nx;
+  __device__ __forceinline__ void load(const uint32_t *o, const GT *gd_, int n) {
+    gd = gd_;
+    nx = n - G;
+    P0 = gd[0];
+    nsup = 1u << gd[1];
+    if constexpr (NXS > 0) {
 #pragma unroll
-    for (int q = 0; q < G; ++q) {
-      R[q] = o[q * QAS_OP_WORDS + 1];
-      pv[q] = 31 - __clz(R[q]);
+      for (int i = 0; i < NXS; ++i) X[i] = gd[QAS_GD_HDR + i];
     }
     xm[0] = 0u;
 #pragma unroll
@@ -351,12 +368,13 @@ struct GroupGeom {
     }
   }
   __device__ __forceinline__ uint32_t base(uint32_t t) const {
-    uint32_t ins = t;
+    uint32_t P = P0;
+    if constexpr (NXS > 0) {
 #pragma unroll
-    for (int q = G - 1; q >= 0; --q) ins = insert_zero(ins, pv[q]);
-    uint32_t P = ins;
-#pragma unroll
-    for (int q = 0; q < G; ++q) P |= (uint32_t)(__popc(ins & R[q]) & 1) << pv[q];
+      for (int i = 0; i < NXS; ++i) P ^= ((t >> i) & 1u) ? X[i] : 0u;
+    } else if constexpr (NXS < 0) {
+      for (int i = 0; i < nx; ++i) P ^= ((t >> i) & 1u) ? (uint32_t)gd[QAS_GD_HDR + i] : 0u;
+    }
     return P;
   }
 };
@@ -393,6 +411,7 @@ __device__ __forceinline__ void reduce_store_m(double (&acc)[8], int lane, uint3
 
 // shared-memory layout per team (bytes, all 16-aligned):
 //   psi [DIM] double2 | lam [DIM] double2 (GRAD) | rec [4 + ops_cap*5] u32
+//   | gd [ops_cap][2 + n] u16 (shared-memory path; the global-memory path reads the u32 record)
 //   | Us [ops_cap][4] double2 (STAGE_U) | red [2][3][WPT][8] f64 (GRAD, multi-warp teams) | ered [WPT] f64
 __host__ __device__ constexpr bool qas_stage_u(int N) { return N == 0 || N >= 7; }
 __host__ __device__ inline size_t eval_team_smem_bytes(int n, int T, bool grad, int ops_cap,
@@ -402,18 +421,19 @@ __host__ __device__ inline size_t eval_team_smem_bytes(int n, int T, bool grad, 
   size_t b = 0;
   if (state_in_smem) b += dim * 16 * (grad ? 2 : 1);
   b += (((size_t)(QAS_REC_HDR + ops_cap * QAS_OP_WORDS) * 4) + 15) & ~(size_t)15;
+  if (state_in_smem) b += (((size_t)ops_cap * QAS_GD_STRIDE(n) * 2) + 15) & ~(size_t)15;
   if (stage_u) b += (size_t)ops_cap * 64;
   if (grad && wpt > 1) b += (size_t)2 * 3 * wpt * 64;
   b += (((size_t)wpt * 8) + 15) & ~(size_t)15;
   return b;
 }
 
-// ---- one forward pass: G gates on the 2^G amplitudes of every coset, in registers
-template <int G, int T, bool SWZ, bool STAGE_U>
-__device__ __forceinline__ void fwd_group(double2 *psi, const uint32_t *o, int j, const double2 *Us,
-                                          const GateTab *Utab, uint32_t DIM, int tid) {
-  GroupGeom<G> gg;
-  gg.load(o);
+// ---- one forward pass: G gates on the 2^G amplitudes of every coset that can be non-zero
+template <int G, int NXS, typename GT, int T, bool SWZ, bool STAGE_U>
+__device__ __forceinline__ void fwd_group(double2 *psi, const uint32_t *o, const GT *gd, int n, int j,
+                                          const double2 *Us, const GateTab *Utab, int tid) {
+  GroupGeom<G, NXS, GT> gg;
+  gg.load(o, gd, n);
   double2 u[G][4];
 #pragma unroll
   for (int q = 0; q < G; ++q) {
@@ -422,15 +442,14 @@ __device__ __forceinline__ void fwd_group(double2 *psi, const uint32_t *o, int j
     for (int e = 0; e < 4; ++e) u[q][e] = g[e];
   }
   const uint32_t rc = (G == 1) ? o[2] : 0u;
-  const uint32_t nper = DIM >> G;
   constexpr int UNR = (8 >> G) > 0 ? (8 >> G) : 1;
 #pragma unroll UNR
-  for (uint32_t t = tid; t < nper; t += T) {
+  for (uint32_t t = tid; t < gg.nsup; t += T) {
     const uint32_t P = gg.base(t);
-    if (G == 1 && rc && !(__popc(P & rc) & 1)) continue;
+    if (G == 1 && rc && !(__popc(sw<SWZ>(P) & rc) & 1)) continue;   // rc is a mask over index bits
     double2 a[1 << G];
 #pragma unroll
-    for (int c = 0; c < (1 << G); ++c) a[c] = psi[sw<SWZ>(P ^ gg.xm[c])];
+    for (int c = 0; c < (1 << G); ++c) a[c] = psi[P ^ gg.xm[c]];
 #pragma unroll
     for (int q = G - 1; q >= 0; --q) {       // time order = descending tape index
 #pragma unroll
@@ -438,7 +457,7 @@ __device__ __forceinline__ void fwd_group(double2 *psi, const uint32_t *o, int j
         if (!((c >> q) & 1)) apply_u(a[c], a[c | (1 << q)], u[q]);
     }
 #pragma unroll
-    for (int c = 0; c < (1 << G); ++c) psi[sw<SWZ>(P ^ gg.xm[c])] = a[c];
+    for (int c = 0; c < (1 << G); ++c) psi[P ^ gg.xm[c]] = a[c];
   }
 }
 
@@ -449,14 +468,14 @@ __device__ __forceinline__ void fwd_group(double2 *psi, const uint32_t *o, int j
 // 3-gate passes reduce M right after each gate (one live accumulator instead of three: the 8 + 8
 // amplitudes already take 64 registers); 1- and 2-gate passes accumulate over the thread's cosets
 // first and reduce once.
-template <int G, int T, int TW, int WPT, bool SWZ, bool STAGE_U>
-__device__ __forceinline__ void adj_group(double2 *psi, double2 *lam, const uint32_t *o, int j,
-                                          const double2 *Us, const GateTab *Utab, uint32_t DIM, int tid,
+template <int G, int NXS, typename GT, int T, int TW, int WPT, bool SWZ, bool STAGE_U>
+__device__ __forceinline__ void adj_group(double2 *psi, double2 *lam, const uint32_t *o, const GT *gd, int n,
+                                          int j, const double2 *Us, const GateTab *Utab, uint32_t DIM, int tid,
                                           int lane, int warp_in_team, uint32_t tmask, double *ring,
                                           double *mout_op) {
   constexpr bool EACH = (G == 3);
-  GroupGeom<G> gg;
-  gg.load(o);
+  GroupGeom<G, NXS, GT> gg;
+  gg.load(o, gd, n);
   int npar[G];
 #pragma unroll
   for (int q = 0; q < G; ++q) npar[q] = qas_meta_npar(o[q * QAS_OP_WORDS + 4]);
@@ -473,12 +492,16 @@ __device__ __forceinline__ void adj_group(double2 *psi, double2 *lam, const uint
 #pragma unroll UNR
   for (uint32_t t = tid; t < nper; t += T) {
     const uint32_t P = gg.base(t);
-    if (G == 1 && rc && !(__popc(P & rc) & 1)) continue;
+    if (G == 1 && rc && !(__popc(sw<SWZ>(P) & rc) & 1)) continue;   // rc is a mask over index bits
+    // psi is zero outside the first 2^dc cosets: only lambda is propagated there.  wins: some lane
+    // of this warp is inside (warp-uniform for whole-warp teams; sub-warp teams always reduce)
+    const bool ins = t < gg.nsup;
+    const bool wins = T < 32 || (t & ~31u) < gg.nsup;
     double2 a[1 << G], l[1 << G];
 #pragma unroll
     for (int c = 0; c < (1 << G); ++c) {
-      const uint32_t x = sw<SWZ>(P ^ gg.xm[c]);
-      a[c] = psi[x];
+      const uint32_t x = P ^ gg.xm[c];
+      a[c] = ins ? psi[x] : make_double2(0.0, 0.0);
       l[c] = lam[x];
     }
 #pragma unroll
@@ -496,12 +519,14 @@ __device__ __forceinline__ void adj_group(double2 *psi, double2 *lam, const uint
       for (int c = 0; c < (1 << G); ++c) {
         if ((c >> q) & 1) continue;
         const int c1 = c | (1 << q);
-        apply_udag(a[c], a[c1], u);
-        if (npar[q]) macc(Mq, l[c], l[c1], a[c], a[c1]);
+        if (ins) {
+          apply_udag(a[c], a[c1], u);
+          if (npar[q]) macc(Mq, l[c], l[c1], a[c], a[c1]);
+        }
         apply_udag(l[c], l[c1], u);
       }
       if constexpr (EACH) {
-        if (npar[q]) {
+        if (npar[q] && wins) {
           if constexpr (WPT == 1) reduce_store_m<TW, false>(Mq, lane, tmask, mout_op + (size_t)q * 8, false);
           else reduce_store_m<TW, true>(Mq, lane, tmask, ring + ((size_t)q * WPT + warp_in_team) * 8, t != (uint32_t)tid);
         }
@@ -509,16 +534,19 @@ __device__ __forceinline__ void adj_group(double2 *psi, double2 *lam, const uint
     }
 #pragma unroll
     for (int c = 0; c < (1 << G); ++c) {
-      const uint32_t x = sw<SWZ>(P ^ gg.xm[c]);
-      psi[x] = a[c];
+      const uint32_t x = P ^ gg.xm[c];
+      if (ins) psi[x] = a[c];
       lam[x] = l[c];
     }
   }
   if constexpr (!EACH) {
+    const bool wins0 = T < 32 || ((uint32_t)tid & ~31u) < gg.nsup;
+    if (wins0) {
 #pragma unroll
-    for (int q = 0; q < G; ++q)
-      if (npar[q]) reduce_store_m<TW, false>(M[q], lane, tmask, WPT == 1 ? mout_op + (size_t)q * 8
-                                                                            : ring + ((size_t)q * WPT + warp_in_team) * 8, false);
+      for (int q = 0; q < G; ++q)
+        if (npar[q]) reduce_store_m<TW, false>(M[q], lane, tmask, WPT == 1 ? mout_op + (size_t)q * 8
+                                                                              : ring + ((size_t)q * WPT + warp_in_team) * 8, false);
+    }
   }
 }
 
@@ -553,10 +581,17 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
     psi = P.gstate + (size_t)blockIdx.x * DIM * (GRAD ? 2 : 1);
     if constexpr (GRAD) lam = psi + DIM;
   }
-  const int rec_words = QAS_REC_HDR + P.ops_cap * QAS_OP_WORDS;
+  const int rec_words = QAS_REC_HDR + P.ops_cap * QAS_OP_WORDS;       // staged part of a tape record
+  const size_t grec_words = qas_rec_words(P.ops_cap, n);              // its full length in global memory
+  const int gstride = QAS_GD_STRIDE(n);
   uint32_t *rec = reinterpret_cast<uint32_t *>(base);
   uint32_t *ops = rec + QAS_REC_HDR;
   base += (((size_t)rec_words * 4) + 15) & ~(size_t)15;
+  // group descriptors: 16-bit copies in shared memory (N != 0) or the 32-bit record in global memory
+  using GT = typename std::conditional<N != 0, uint16_t, uint32_t>::type;
+  constexpr int NXS3 = N != 0 ? N - 3 : -1, NXS2 = N != 0 ? N - 2 : -1, NXS1 = N != 0 ? N - 1 : -1;
+  uint16_t *gd16 = reinterpret_cast<uint16_t *>(base);
+  if constexpr (N != 0) base += (((size_t)P.ops_cap * gstride * 2) + 15) & ~(size_t)15;
   double2 *Us = reinterpret_cast<double2 *>(base);
   if constexpr (STAGE_U) base += (size_t)P.ops_cap * 64;
   double *red = nullptr;
@@ -572,11 +607,18 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
     if (b >= P.B) continue;      // teams are independent: nobody waits on an idle one
     constexpr bool active = true;
 
+    long long clk_prev = 0;
+    if (P.phase_clk && tid == 0) clk_prev = clock64();
     // ---- 1. fetch the compiled tape record, zero the state / the gradient row
     {
-      const uint32_t *grec = P.tape + (size_t)(active ? b : 0) * rec_words;
-      const int used = active ? (int)(QAS_REC_HDR + grec[0] * QAS_OP_WORDS) : 0;
-      for (int w = tid; w < QAS_REC_HDR || w < used; w += T) rec[w] = active ? grec[w] : 0u;
+      const uint32_t *grec = P.tape + (size_t)b * grec_words;
+      const int used = (int)(QAS_REC_HDR + grec[0] * QAS_OP_WORDS);
+      for (int w = tid; w < QAS_REC_HDR || w < used; w += T) rec[w] = grec[w];
+      if constexpr (N != 0) {
+        const uint32_t *ggd = grec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS;
+        const int gused = (int)grec[3] * gstride;
+        for (int w = tid; w < gused; w += T) gd16[w] = (uint16_t)ggd[w];
+      }
       const double amp0 = (P.init_kind == QAS_INIT_PLUS) ? exp2(-0.5 * (double)n) : 0.0;
       for (uint32_t i = tid; i < DIM; i += T) psi[i] = make_double2(amp0, 0.0);
     }
@@ -589,8 +631,12 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
       for (int w = tid; w < nops * 4; w += T) Us[w] = P.U[ops[(w >> 2) * QAS_OP_WORDS + 3]].u[w & 3];
     }
     const int nloop = ngroups;
+    const GT *gdb;
+    if constexpr (N != 0) gdb = gd16;
+    else gdb = P.tape + (size_t)b * grec_words + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS;
     team_sync<T>(team, tmask);
 
+    if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 0, (unsigned long long)(c_ - clk_prev)); clk_prev = c_; }
     // ---- 2. forward sweep (tape is stored last-gate-first: walk the groups from the end)
     {
       int e = nops - 1;
@@ -599,10 +645,11 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
           const int g = (int)QAS_META_GLAST(ops[(size_t)e * QAS_OP_WORDS + 4]);
           const int j = e - g + 1;
           const uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
+          const GT *gd = gdb + (size_t)(nloop - 1 - it) * gstride;
           if (qas_meta_kind(o[4]) == QAS_K_U1) {
-            if (GMAX >= 3 && g == 3) { if constexpr (GMAX >= 3) fwd_group<3, T, SWZ, STAGE_U>(psi, o, j, Us, P.U, DIM, tid); }
-            else if (GMAX >= 2 && g == 2) { if constexpr (GMAX >= 2) fwd_group<2, T, SWZ, STAGE_U>(psi, o, j, Us, P.U, DIM, tid); }
-            else fwd_group<1, T, SWZ, STAGE_U>(psi, o, j, Us, P.U, DIM, tid);
+            if (GMAX >= 3 && g == 3) { if constexpr (GMAX >= 3) fwd_group<3, NXS3, GT, T, SWZ, STAGE_U>(psi, o, gd, n, j, Us, P.U, tid); }
+            else if (GMAX >= 2 && g == 2) { if constexpr (GMAX >= 2) fwd_group<2, NXS2, GT, T, SWZ, STAGE_U>(psi, o, gd, n, j, Us, P.U, tid); }
+            else fwd_group<1, NXS1, GT, T, SWZ, STAGE_U>(psi, o, gd, n, j, Us, P.U, tid);
           } else {
             const double2 *gm = STAGE_U ? (Us + 4 * j) : P.U[o[3]].u;
             const double2 d0 = gm[0], d1 = gm[3];
@@ -619,6 +666,7 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
       }
     }
 
+    if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 1, (unsigned long long)(c_ - clk_prev)); clk_prev = c_; }
     // ---- 3. lambda = H psi, E = Re <psi|lambda>   (register-blocked over X-mask classes)
     double e_part = 0.0;
     {
@@ -678,7 +726,8 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
     }
     if (tid == 0 && active) P.energy[b] = status ? __longlong_as_double(0x7ff8000000000000ll) : e_part;
 
-    // ---- 4. adjoint sweep (tape order = reverse time order), then the gradient finalize
+    if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 2, (unsigned long long)(c_ - clk_prev)); clk_prev = c_; }
+    // ---- 4. adjoint sweep (tape order = reverse time order)
     if constexpr (GRAD) {
       int j = 0;
       for (int it = 0; it < nloop; ++it) {
@@ -687,10 +736,14 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
           const int g = (int)QAS_META_GFIRST(o[4]);
           double *ring = WPT > 1 ? red + (size_t)(it & 1) * 3 * WPT * 8 : nullptr;
           double *mop = P.mout + ((size_t)b * P.ops_cap + j) * 8;
+          const GT *gd = gdb + (size_t)it * gstride;
+          // warps of the team that own cosets inside the support (they publish partial M's)
+          int nact = WPT;
           if (qas_meta_kind(o[4]) == QAS_K_U1) {
-            if (GMAX >= 3 && g == 3) { if constexpr (GMAX >= 3) adj_group<3, T, TW, WPT, SWZ, STAGE_U>(psi, lam, o, j, Us, P.U, DIM, tid, lane, warp_in_team, tmask, ring, mop); }
-            else if (GMAX >= 2 && g == 2) { if constexpr (GMAX >= 2) adj_group<2, T, TW, WPT, SWZ, STAGE_U>(psi, lam, o, j, Us, P.U, DIM, tid, lane, warp_in_team, tmask, ring, mop); }
-            else adj_group<1, T, TW, WPT, SWZ, STAGE_U>(psi, lam, o, j, Us, P.U, DIM, tid, lane, warp_in_team, tmask, ring, mop);
+            nact = (int)min((uint32_t)WPT, ((1u << gd[1]) + 31u) >> 5);
+            if (GMAX >= 3 && g == 3) { if constexpr (GMAX >= 3) adj_group<3, NXS3, GT, T, TW, WPT, SWZ, STAGE_U>(psi, lam, o, gd, n, j, Us, P.U, DIM, tid, lane, warp_in_team, tmask, ring, mop); }
+            else if (GMAX >= 2 && g == 2) { if constexpr (GMAX >= 2) adj_group<2, NXS2, GT, T, TW, WPT, SWZ, STAGE_U>(psi, lam, o, gd, n, j, Us, P.U, DIM, tid, lane, warp_in_team, tmask, ring, mop); }
+            else adj_group<1, NXS1, GT, T, TW, WPT, SWZ, STAGE_U>(psi, lam, o, gd, n, j, Us, P.U, DIM, tid, lane, warp_in_team, tmask, ring, mop);
           } else {
             const double2 *gm = STAGE_U ? (Us + 4 * j) : P.U[o[3]].u;
             const double2 d0 = gm[0], d1 = gm[3];
@@ -722,8 +775,7 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
               const int q = tid >> 3, v = tid & 7;
               if (qas_meta_npar(o[q * QAS_OP_WORDS + 4])) {
                 double m = 0.0;
-#pragma unroll
-                for (int wp = 0; wp < WPT; ++wp) m += ring[((size_t)q * WPT + wp) * 8 + v];
+                for (int wp = 0; wp < nact; ++wp) m += ring[((size_t)q * WPT + wp) * 8 + v];
                 mop[(size_t)q * 8 + v] = m;
               }
             }
@@ -733,6 +785,7 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
         if constexpr (WPT == 1) team_sync<T>(team, tmask);
       }
     }
+    if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 3, (unsigned long long)(c_ - clk_prev)); }
     team_sync<T>(team, tmask);   // state buffers are reused by the next circuit of this team
   }
 }
@@ -742,12 +795,12 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
 // per (circuit, tape op, parameter slot).  Kept out of the evaluation kernel so that no team
 // waits on the dU table (L2 latency) between passes.  grad must be zero-filled beforehand.
 __global__ void grad_finalize_kernel(const uint32_t *tape, const double *mout, const GateDTab *dU, int B,
-                                     int p, int l, int ops_cap, double *grad) {
+                                     int p, int l, int ops_cap, int n, double *grad) {
   const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t per = (size_t)ops_cap * 3;
   if (x >= (size_t)B * per) return;
   const int b = (int)(x / per), rem = (int)(x % per), oi = rem / 3, jj = rem - oi * 3;
-  const uint32_t *rec = tape + (size_t)b * (QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS);
+  const uint32_t *rec = tape + (size_t)b * qas_rec_words(ops_cap, n);
   if (oi >= (int)rec[0] || rec[1]) return;
   const uint32_t *o = rec + QAS_REC_HDR + (size_t)oi * QAS_OP_WORDS;
   const uint32_t mt = o[4];
@@ -793,13 +846,18 @@ __global__ void grad_chunk_reduce_kernel(const int32_t *k, const double *grad, i
   for (int x = threadIdx.x; x < nd * c * l; x += blockDim.x) out[x] = acc[x];
 }
 
+// one warp per output element: lane q sums chunks q, q+32, ... in order, then a fixed shuffle tree
+// combines the 32 lanes -- the summation order depends only on (nchunks), never on scheduling
 __global__ void grad_final_reduce_kernel(const double *partial, int nchunks, size_t total,
                                          double scale, double *out) {
-  const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (x >= total) return;
   double s = 0.0;
-  for (int ch = 0; ch < nchunks; ++ch) s += partial[(size_t)ch * total + x];
-  out[x] = s * scale;
+  for (int ch = lane; ch < nchunks; ch += 32) s += partial[(size_t)ch * total + x];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) out[x] = s * scale;
 }
 
 // ------------------------------------------------------------------------------ FP64 peak

@@ -30,7 +30,7 @@
 #define QAS_HD inline
 #endif
 
-#define QAS_MAX_QUBITS 30
+#define QAS_MAX_QUBITS 20
 #define QAS_OP_WORDS 5      // {m, r, rc, tab, meta}
 #define QAS_K_U1 0u
 #define QAS_K_PDIAG 1u
@@ -175,20 +175,33 @@ QAS_HD int qas_compile_circuit(const int32_t *k, int p, const qas_pool_entry *po
 }
 
 // ---- pass planner ----------------------------------------------------------------------------
-// Consecutive uncontrolled K_U1 ops (tape indices j .. j+g-1, g <= gmax <= 3) share ONE pass over
-// the state when every thread can own the 2^g amplitudes {P ^ span(m_0..m_{g-1})} and apply all
-// g gates in registers.  Condition: no cross terms, parity(m_a & r_b) = 0 for a != b (with
-// parity(m_a & r_a) = 1, which always holds, this makes the m's and the r's linearly independent
-// and makes the register index bit c_a of slot P ^ (c_0 m_0 ^ c_1 m_1 ^ c_2 m_2) equal to the
-// logical bit of gate a whenever r_a.P = 0 for all a).  The coset representatives P are the
-// common kernel of the r's; to enumerate it the planner replaces the r's of a group by their
-// reduced row-echelon form R_0..R_{g-1} (pivot = highest set bit, strictly descending, every
-// pivot column has a single 1): P = t with zeros inserted at the pivots, then pivot bit q set to
-// parity(P & R_q).  The grouping is greedy in tape order.  It is recorded in the meta words:
+// (1) Grouping.  Consecutive uncontrolled K_U1 ops (tape indices j .. j+g-1, g <= gmax <= 3) share
+// ONE pass over the state when every thread can own the 2^g amplitudes {P ^ span(m_0..m_{g-1})}
+// and apply all g gates in registers.  Condition: no cross terms, parity(m_a & r_b) = 0 for a != b
+// (with parity(m_a & r_a) = 1, which always holds, the m's and the r's are linearly independent and
+// the register index bit c_a of slot P ^ (c_0 m_0 ^ c_1 m_1 ^ c_2 m_2) equals the logical bit of
+// gate a whenever r_a.P = 0 for all a).  Greedy in tape order; recorded in the meta words:
 // bits 24-25 = g on the FIRST op of a group (adjoint sweep walks up), bits 26-27 = g on the LAST
-// op (forward sweep walks down).  Returns the number of groups (= passes per sweep).
+// op (forward sweep walks down).
+//
+// (2) Support tracking.  Starting from a basis state |b0>, the state after some gates is non-zero
+// only on the affine subspace b0 ^ D, D = span of the xor masks of the gates applied so far.  The
+// planner walks the groups in TIME order, keeps D, and gives every group a descriptor
+//     gd = { P0, dc, X_0 .. X_{n-g-1} }
+// (in slot coordinates when `swizzled`, like the ops' xor masks after planning)
+// such that the coset representatives of the group are  P(t) = P0 ^ xor_{i: bit i of t} X_i,
+// t = 0 .. 2^(n-g)-1, every P(t) lies in the common kernel of the group's r's (so slot index bits
+// are logical bits), and the cosets that can hold non-zero amplitudes AFTER the group are exactly
+// t < 2^dc.  The forward sweep visits only those; the adjoint sweep visits all cosets for lambda
+// but touches psi and the cross matrices only for t < 2^dc.  For shallow circuits from a basis
+// state (the QAS search regime) this removes most of the forward work and ~2/3 of the adjoint's.
+// The X_i are put in lowest-set-bit echelon form of their (swizzled) shared-memory slot index and
+// sorted by pivot, so that the three lane bits of a quarter-warp get independent low address bits
+// whenever the subspace allows it (bank conflicts).  Uniform initial state: D is everything.
 #define QAS_META_GFIRST(m) (((m) >> 24) & 3u)
 #define QAS_META_GLAST(m) (((m) >> 26) & 3u)
+#define QAS_GD_HDR 2        // P0, dc
+#define QAS_GD_STRIDE(n) (QAS_GD_HDR + (n))
 
 QAS_HD int qas_parity32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
@@ -204,7 +217,127 @@ QAS_HD int qas_msb32(uint32_t v) {
   return 31 - __builtin_clz(v);
 #endif
 }
-QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax) {
+QAS_HD int qas_lsb32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __ffs(v) - 1;
+#else
+  return __builtin_ctz(v);
+#endif
+}
+// slot index of amplitude i in the swizzled shared-memory statevector: every 3-bit group of the
+// index above bit 2 is xor-folded onto bits 0..2, so index bit p also moves bank-group bit p mod 3
+// (xor-linear and an involution: the fold only reads bits >= 3, which it leaves unchanged)
+QAS_HD uint32_t qas_swz(uint32_t i) {
+  uint32_t f = i >> 3;
+  f ^= f >> 3;
+  f ^= f >> 6;
+  f ^= f >> 12;
+  return i ^ (f & 7u);
+}
+
+// Subspaces of GF(2)^n are kept as pivot-indexed tables, tab[p] = the basis vector whose pivot is
+// bit p (0 = none), and every loop over them has a compile-time trip count NQ: on the device the
+// tables then live in registers (one thread plans one circuit).
+template <int NQ>
+struct QasPivTab {
+  uint32_t v[NQ];
+  QAS_HD void clear() {
+#pragma unroll
+    for (int p = 0; p < NQ; ++p) v[p] = 0u;
+  }
+};
+// highest-set-bit pivots (rank / membership)
+template <int NQ>
+QAS_HD bool qas_tab_add_msb(QasPivTab<NQ> &t, uint32_t x) {
+  bool placed = false;
+#pragma unroll
+  for (int p = NQ - 1; p >= 0; --p) {
+    if (!placed && ((x >> p) & 1u)) {
+      if (t.v[p]) x ^= t.v[p];
+      else { t.v[p] = x; placed = true; }
+    }
+  }
+  return placed;
+}
+// lowest-set-bit pivots: x is reduced against `a` and `b` (either may hold pivot p) and, if something
+// is left, stored in `dst` (which is `a` or `b`).  Reducing at pivot p only changes bits above p.
+template <int NQ>
+QAS_HD bool qas_tab_add_lsb(const QasPivTab<NQ> &a, QasPivTab<NQ> &b, bool into_b, QasPivTab<NQ> &a_mut, uint32_t x) {
+  bool placed = false;
+#pragma unroll
+  for (int p = 0; p < NQ; ++p) {
+    if (!placed && ((x >> p) & 1u)) {
+      const uint32_t v = a.v[p] ? a.v[p] : b.v[p];
+      if (v) x ^= v;
+      else { if (into_b) b.v[p] = x; else a_mut.v[p] = x; placed = true; }
+    }
+  }
+  return placed;
+}
+
+template <int NQ>
+QAS_HD void qas_plan_supports(const uint32_t *ops, int nops, int ngroups, int n, int init_kind,
+                              uint32_t init_index, uint32_t *gd, int swizzled) {
+  QasPivTab<NQ> D;
+  D.clear();
+  if (init_kind == QAS_INIT_PLUS) {
+#pragma unroll
+    for (int p = 0; p < NQ; ++p) if (p < n) D.v[p] = 1u << p;
+  }
+  const uint32_t b0 = (init_kind == QAS_INIT_BASIS) ? init_index : 0u;
+  const int stride = QAS_GD_STRIDE(n);
+  int e = nops - 1;
+  for (int gi = ngroups - 1; gi >= 0; --gi) {          // groups in time order
+    const int g = (int)QAS_META_GLAST(ops[(size_t)e * QAS_OP_WORDS + 4]);
+    const int j = e - g + 1;
+    const uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
+    uint32_t *d = gd + (size_t)gi * stride;
+    e = j - 1;
+    if (qas_meta_kind(o[4]) != QAS_K_U1) {       // parity-diagonal: dense, support unchanged
+      d[0] = 0u; d[1] = (uint32_t)n;
+      for (int i = 0; i < n; ++i) d[QAS_GD_HDR + i] = 1u << i;
+      continue;
+    }
+    uint32_t m0 = o[0], r0 = o[1], m1 = 0u, r1 = 0u, m2 = 0u, r2 = 0u;
+    if (g > 1) { m1 = o[QAS_OP_WORDS]; r1 = o[QAS_OP_WORDS + 1]; }
+    if (g > 2) { m2 = o[2 * QAS_OP_WORDS]; r2 = o[2 * QAS_OP_WORDS + 1]; }
+    // projection onto the common kernel of the r's along span(m's), then to slot coordinates
+    auto proj = [&](uint32_t x) {
+      uint32_t y = x;
+      if (qas_parity32(r0 & x)) y ^= m0;
+      if (qas_parity32(r1 & x)) y ^= m1;
+      if (qas_parity32(r2 & x)) y ^= m2;
+      return swizzled ? qas_swz(y) : y;
+    };
+    QasPivTab<NQ> Sin, Sout;
+    Sin.clear();
+    Sout.clear();
+    int dc = 0, tot = 0;
+#pragma unroll
+    for (int p = 0; p < NQ; ++p)
+      if (D.v[p]) dc += qas_tab_add_lsb<NQ>(Sin, Sout, false, Sin, proj(D.v[p])) ? 1 : 0;
+    tot = dc;
+#pragma unroll
+    for (int p = 0; p < NQ; ++p)
+      if (p < n && tot < n - g) tot += qas_tab_add_lsb<NQ>(Sin, Sout, true, Sin, proj(1u << p)) ? 1 : 0;
+    d[0] = proj(b0);
+    d[1] = (uint32_t)dc;
+    int cnt = 0;
+#pragma unroll
+    for (int p = 0; p < NQ; ++p) if (Sin.v[p]) d[QAS_GD_HDR + cnt++] = Sin.v[p];
+#pragma unroll
+    for (int p = 0; p < NQ; ++p) if (Sout.v[p]) d[QAS_GD_HDR + cnt++] = Sout.v[p];
+    qas_tab_add_msb<NQ>(D, m0);
+    if (g > 1) qas_tab_add_msb<NQ>(D, m1);
+    if (g > 2) qas_tab_add_msb<NQ>(D, m2);
+  }
+}
+
+// Returns the number of groups.  gd receives one descriptor of QAS_GD_STRIDE(n) words per group,
+// in TAPE order of the groups (may be null: grouping only).  swizzled: the statevector lives in
+// shared memory; descriptors and the ops' xor masks are then written in slot coordinates.
+QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax, int n, int init_kind, uint32_t init_index,
+                           uint32_t *gd, int swizzled) {
   int ngroups = 0;
   for (int j = 0; j < nops;) {
     uint32_t *a = ops + (size_t)j * QAS_OP_WORDS;
@@ -222,23 +355,19 @@ QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax) {
         ++g;
       }
     }
-    if (g > 1) {   // Gauss-Jordan on the parity functionals of the group
-      uint32_t R[3] = {0u, 0u, 0u};
-      for (int q = 0; q < g; ++q) R[q] = ops[(size_t)(j + q) * QAS_OP_WORDS + 1];
-      for (int i = 0; i < g; ++i) {
-        int best = i;
-        for (int q = i + 1; q < g; ++q) if (R[q] > R[best]) best = q;
-        const uint32_t t = R[i]; R[i] = R[best]; R[best] = t;
-        const int pv = qas_msb32(R[i]);
-        for (int q = 0; q < g; ++q) if (q != i && ((R[q] >> pv) & 1u)) R[q] ^= R[i];
-      }
-      for (int q = 0; q < g; ++q) ops[(size_t)(j + q) * QAS_OP_WORDS + 1] = R[q];
-    }
     a[4] |= (uint32_t)g << 24;
     ops[(size_t)(j + g - 1) * QAS_OP_WORDS + 4] |= (uint32_t)g << 26;
     j += g;
     ++ngroups;
   }
+  if (!gd) return ngroups;
+  if (n <= 12) qas_plan_supports<12>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled);
+  else qas_plan_supports<QAS_MAX_QUBITS>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled);
+  if (swizzled)
+    for (int j = 0; j < nops; ++j) {
+      uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
+      if (qas_meta_kind(o[4]) == QAS_K_U1) o[0] = qas_swz(o[0]);
+    }
   return ngroups;
 }
 

@@ -105,51 +105,77 @@ def run_tape(n, ops, init, init_index, pool, c, params, terms, want_grad=True):
 
 
 # ---------------------------------------------------------------------------------------------
-# Planned (register-fused) passes: restates GroupGeom / fwd_group / adj_group of kernels.cuh.
-def plan_passes(ops, gmax):
-    """Run the C pass planner (qas_plan_passes_host) on a copy of a compiled tape."""
+# Planned (register-fused, support-restricted) passes: restates GroupGeom / fwd_group / adj_group
+# of kernels.cuh on the descriptors the C pass planner emits.
+GD_HDR = 2
+
+
+def plan_passes(n, ops, gmax, init=("zero", 0), init_index=0, swizzled=True):
+    """Run the C pass planner (qas_plan_passes_host) on a copy of a compiled tape ->
+    (ops with group marks, number of groups, descriptors uint32[ngroups, 2 + n])."""
     import ctypes
     from qas_b200 import _lib
     lib = _lib.load()
     out = np.ascontiguousarray(ops, dtype=np.uint32).copy()
+    stride = GD_HDR + n
+    gd = np.zeros(max(1, len(out)) * stride, dtype=np.uint32)
     ng = ctypes.c_int(0)
-    rc = lib.qas_plan_passes_host(out.ctypes.data, len(out), int(gmax), ctypes.byref(ng))
+    kind = {"zero": 0, "basis": 1, "plus": 2}[init[0]]
+    rc = lib.qas_plan_passes_host(n, out.ctypes.data, len(out), int(gmax), kind, int(init_index), int(bool(swizzled)),
+                                  gd.ctypes.data, len(gd), ctypes.byref(ng))
     assert rc == 0
-    return out, ng.value
+    return out, ng.value, gd[:ng.value * stride].reshape(ng.value, stride).copy()
 
 
-def _insert_zero(t, b):
-    return ((t >> b) << (b + 1)) | (t & ((1 << b) - 1))
+def _swz(i):
+    f = i >> 3
+    f ^= f >> 3
+    f ^= f >> 6
+    f ^= f >> 12
+    return i ^ (f & 7)
 
 
-def group_cosets(n, grp):
-    """coset representatives P and slot masks xm of one group, exactly as the kernel enumerates them"""
+def group_cosets(n, grp, gd, swizzled=True):
+    """coset representatives (in planner order) and slot masks of one group, as the kernel enumerates
+    them: P(t) = P0 ^ xor of X_i over the bits of t; returns (Ps, xm, nsup) in INDEX coordinates
+    (a swizzled plan stores slot coordinates; the swizzle is a linear involution)"""
     g = len(grp)
-    R = [int(o[1]) for o in grp]
-    pv = [r.bit_length() - 1 for r in R]
-    assert all(pv[q] > pv[q + 1] for q in range(g - 1)), "pivots must be strictly descending"
-    for q in range(g):
-        for q2 in range(g):
-            if q != q2:
-                assert not (R[q2] >> pv[q]) & 1, "pivot column must have a single 1"
+    cv = _swz if swizzled else (lambda x: x)
+    P0, dc = cv(int(gd[0])), int(gd[1])
+    X = [cv(int(x)) for x in gd[GD_HDR:GD_HDR + n - g]]
     xm = [0] * (1 << g)
     for c in range(1, 1 << g):
         q = c.bit_length() - 1
-        xm[c] = xm[c & ~(1 << q)] ^ int(grp[q][0])
+        xm[c] = xm[c & ~(1 << q)] ^ cv(int(grp[q][0]))
+    # every representative lies in the common kernel of the r's: slot bits are logical bits
+    for x in X + [P0]:
+        for o in grp:
+            assert _parity(x & int(o[1])) == 0
     Ps = []
     for t in range(1 << (n - g)):
-        ins = t
-        for q in range(g - 1, -1, -1):
-            ins = _insert_zero(ins, pv[q])
-        P = ins
-        for q in range(g):
-            P |= _parity(ins & R[q]) << pv[q]
+        P = P0
+        for i in range(n - g):
+            if (t >> i) & 1:
+                P ^= X[i]
         Ps.append(P)
-    return Ps, xm
+    return Ps, xm, 1 << dc
 
 
-def run_tape_planned(n, ops, init, init_index, pool, c, params, terms, want_grad=True):
-    """Same contract as run_tape, on a tape that went through the pass planner."""
+def quarter_warp_conflicts(n, grp, gd, swizzled=True):
+    """worst bank-group multiplicity over the first quarter-warp (coset counter 0..7) and all slots"""
+    Ps, xm, _ = group_cosets(n, grp, gd, swizzled)
+    worst = 1
+    for x in xm:
+        seen = {}
+        for P in Ps[:8]:
+            a = (_swz(P ^ x) if swizzled else (P ^ x)) & 7
+            seen[a] = seen.get(a, 0) + 1
+        worst = max(worst, max(seen.values()))
+    return worst
+
+
+def run_tape_planned(n, ops, gds, init, init_index, pool, c, params, terms, want_grad=True, swizzled=True):
+    """Same contract as run_tape, on a tape that went through the pass planner; gds = descriptors."""
     dim = 1 << n
     kind = init[0]
     if kind == "plus":
@@ -167,22 +193,37 @@ def run_tape_planned(n, ops, init, init_index, pool, c, params, terms, want_grad
         assert (int(ops[j + g - 1][4]) >> 26) & 3 == g
         groups.append((j, g))
         j += g
+    assert len(groups) == len(gds)
+    state = {"psi": psi}
 
-    def apply_group(j, g, adjoint, lam=None, grads=None):
+    def apply_group(gi, adjoint, lam=None, grads=None):
+        j, g = groups[gi]
+        psi = state["psi"]
         grp = [ops[j + q] for q in range(g)]
-        k0 = (int(grp[0][4]) >> 16) & 0xF
-        if k0 != 0 or int(grp[0][2]) != 0:
-            assert g == 1
+        if (int(grp[0][4]) >> 16) & 0xF != 0:
             return False
-        Ps, xm = group_cosets(n, grp)
+        rc = int(grp[0][2])
+        assert rc == 0 or g == 1
+        Ps, xm, nsup = group_cosets(n, grp, gds[gi], swizzled)
         seen = np.zeros(dim, dtype=np.int64)
         order = range(g) if adjoint else range(g - 1, -1, -1)
         Ms = [np.zeros((2, 2), dtype=np.complex128) for _ in range(g)]
         mats = [table_entry(int(o[3]), pool, c, params) for o in grp]
-        for P in Ps:
+        for t, P in enumerate(Ps):
             slots = [P ^ x for x in xm]
             for s_ in slots:
                 seen[s_] += 1
+            ins = t < nsup
+            if not ins:
+                # the planner's claim: nothing lives outside the first 2^dc cosets.  Forward sweep:
+                # exactly zero (never written).  Adjoint sweep: un-applying a gate leaves rounding
+                # residue where the support shrank; it is never read again.
+                tol = 1e-13 if adjoint else 0.0
+                assert all(abs(psi[s_]) <= tol for s_ in slots), "amplitude outside the tracked support"
+                if not adjoint:
+                    continue
+            if rc and not _parity(P & rc):
+                continue
             a = [psi[s_] for s_ in slots]
             l = [lam[s_] for s_ in slots] if adjoint else None
             for q in order:
@@ -195,14 +236,16 @@ def run_tape_planned(n, ops, init, init_index, pool, c, params, terms, want_grad
                     if not adjoint:
                         a[cc], a[c1] = u[0, 0] * a[cc] + u[0, 1] * a[c1], u[1, 0] * a[cc] + u[1, 1] * a[c1]
                     else:
-                        a[cc], a[c1] = ud[0, 0] * a[cc] + ud[0, 1] * a[c1], ud[1, 0] * a[cc] + ud[1, 1] * a[c1]
-                        Ms[q][0, 0] += np.conj(l[cc]) * a[cc]
-                        Ms[q][0, 1] += np.conj(l[cc]) * a[c1]
-                        Ms[q][1, 0] += np.conj(l[c1]) * a[cc]
-                        Ms[q][1, 1] += np.conj(l[c1]) * a[c1]
+                        if ins:
+                            a[cc], a[c1] = ud[0, 0] * a[cc] + ud[0, 1] * a[c1], ud[1, 0] * a[cc] + ud[1, 1] * a[c1]
+                            Ms[q][0, 0] += np.conj(l[cc]) * a[cc]
+                            Ms[q][0, 1] += np.conj(l[cc]) * a[c1]
+                            Ms[q][1, 0] += np.conj(l[c1]) * a[cc]
+                            Ms[q][1, 1] += np.conj(l[c1]) * a[c1]
                         l[cc], l[c1] = ud[0, 0] * l[cc] + ud[0, 1] * l[c1], ud[1, 0] * l[cc] + ud[1, 1] * l[c1]
-            for s_, v in zip(slots, a):
-                psi[s_] = v
+            if ins:
+                for s_, v in zip(slots, a):
+                    psi[s_] = v
             if adjoint:
                 for s_, v in zip(slots, l):
                     lam[s_] = v
@@ -215,20 +258,13 @@ def run_tape_planned(n, ops, init, init_index, pool, c, params, terms, want_grad
                     grads[(meta & 0xFFFF, jj)] = 2.0 * float(np.sum(du[jj] * Ms[q]).real)
         return True
 
-    for j, g in groups[::-1]:
-        if not apply_group(j, g, False):
+    for gi in range(len(groups) - 1, -1, -1):
+        if not apply_group(gi, False):
+            j, g = groups[gi]
             m, r, rc, tab, meta = (int(x) for x in ops[j])
             u, _ = table_entry(tab, pool, c, params)
-            if (meta >> 16) & 0xF == 0:
-                p0 = idx[par(idx & r) == 0]
-                if rc:
-                    p0 = p0[par(p0 & rc) == 1]
-                p1 = p0 ^ m
-                a0, a1 = psi[p0].copy(), psi[p1].copy()
-                psi[p0] = u[0, 0] * a0 + u[0, 1] * a1
-                psi[p1] = u[1, 0] * a0 + u[1, 1] * a1
-            else:
-                psi = np.where(par(idx & r) == 1, u[1, 1], u[0, 0]) * psi
+            state["psi"] = np.where(par(idx & r) == 1, u[1, 1], u[0, 0]) * state["psi"]
+    psi = state["psi"]
     lam = np.zeros(dim, dtype=np.complex128)
     for coeff, word in terms:
         x, z = sim.word_to_masks(word)
@@ -238,33 +274,22 @@ def run_tape_planned(n, ops, init, init_index, pool, c, params, terms, want_grad
     energy = float(np.vdot(psi, lam).real)
     grads = {}
     if want_grad:
-        for j, g in groups:
-            if apply_group(j, g, True, lam, grads):
+        for gi in range(len(groups)):
+            if apply_group(gi, True, lam, grads):
                 continue
+            j, g = groups[gi]
+            psi = state["psi"]
             m, r, rc, tab, meta = (int(x) for x in ops[j])
             u, du = table_entry(tab, pool, c, params)
             depth, npar = meta & 0xFFFF, (meta >> 20) & 3
             M = np.zeros((2, 2), dtype=np.complex128)
-            if (meta >> 16) & 0xF == 0:
-                p0 = idx[par(idx & r) == 0]
-                if rc:
-                    p0 = p0[par(p0 & rc) == 1]
-                p1 = p0 ^ m
-                ud = u.conj().T
-                a0, a1 = psi[p0].copy(), psi[p1].copy()
-                q0, q1 = ud[0, 0] * a0 + ud[0, 1] * a1, ud[1, 0] * a0 + ud[1, 1] * a1
-                psi[p0], psi[p1] = q0, q1
-                l0, l1 = lam[p0].copy(), lam[p1].copy()
-                M[0, 0], M[0, 1] = np.vdot(l0, q0), np.vdot(l0, q1)
-                M[1, 0], M[1, 1] = np.vdot(l1, q0), np.vdot(l1, q1)
-                lam[p0], lam[p1] = ud[0, 0] * l0 + ud[0, 1] * l1, ud[1, 0] * l0 + ud[1, 1] * l1
-            else:
-                hi = par(idx & r) == 1
-                d = np.where(hi, u[1, 1], u[0, 0]).conj()
-                psi = d * psi
-                M[0, 0] = np.vdot(lam[~hi], psi[~hi])
-                M[1, 1] = np.vdot(lam[hi], psi[hi])
-                lam = d * lam
+            hi = par(idx & r) == 1
+            d = np.where(hi, u[1, 1], u[0, 0]).conj()
+            psi = d * psi
+            M[0, 0] = np.vdot(lam[~hi], psi[~hi])
+            M[1, 1] = np.vdot(lam[hi], psi[hi])
+            lam *= d
+            state["psi"] = psi
             for jj in range(npar):
                 grads[(depth, jj)] = 2.0 * float(np.sum(du[jj] * M).real)
     return energy, grads

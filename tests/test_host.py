@@ -109,41 +109,49 @@ def test_tape_compiler_full_vocabulary_random():
         assert np.max(np.abs(got - ga)) < 1e-10
 
 
-@pytest.mark.parametrize("gmax", [2, 3])
-def test_pass_planner_fused_groups_match_oracle(gmax):
-    """Register-fused passes (qas_plan_groups + the kernel's coset enumeration, restated in
-    tape_interp.run_tape_planned) give the oracle's energies and gradients; every group tiles the
-    index space exactly once."""
+@pytest.mark.parametrize("gmax", [1, 2, 3])
+def test_pass_planner_fused_support_restricted_passes_match_oracle(gmax):
+    """Register-fused, support-restricted passes (qas_plan_groups + the kernel's coset enumeration,
+    restated in tape_interp.run_tape_planned) give the oracle's energies and gradients; every group
+    tiles the index space exactly once and nothing ever lives outside the tracked support."""
     rng = np.random.default_rng(5)
-    fused_any = 0
-    for trial, (n, pool, p) in enumerate([(5, helpers.near_cx_pool(5, helpers.ring(5)), 14),
-                                          (6, helpers.near_cx_pool(6), 16),
-                                          (4, helpers.full_vocab_pool(4), 10),
-                                          (4, helpers.full_vocab_pool(4), 10)]):
+    fused_any, sparse_any = 0, 0
+    cases = [(5, helpers.near_cx_pool(5, helpers.ring(5)), 14, ("zero", 0)),
+             (6, helpers.near_cx_pool(6), 16, ("basis", 0b101100)),
+             (7, helpers.near_cx_pool(7), 12, ("zero", 0)),
+             (6, helpers.near_cx_pool(6), 10, ("plus", 0)),
+             (4, helpers.full_vocab_pool(4), 10, ("basis", 9)),
+             (4, helpers.full_vocab_pool(4), 10, ("zero", 0))]
+    for trial, (n, pool, p, init) in enumerate(cases):
         c = len(pool)
-        if trial < 2:
+        if trial < 4:
             k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": p // 2}, 1, seed=trial)[0]]
         else:
             k = [int(x) for x in rng.integers(0, c, size=p)]
         params = rng.standard_normal((p, c, 3))
         words = ["".join(rng.choice(list("IXYZ"), size=n)) for _ in range(6)]
         terms = [(float(rng.standard_normal()), w) for w in words]
-        init = [("zero", 0), ("basis", int(rng.integers(0, 1 << n))), ("plus", 0), ("zero", 0)][trial]
         ops, idx = compile_tape_host(n, pool, k, init[1] if init[0] == "basis" else 0)
-        planned, ng = TI.plan_passes(ops, gmax)
-        assert ng <= len(ops)
-        fused_any += len(ops) - ng
-        # planning never touches masks, tables or depths
-        assert np.array_equal(planned[:, [0, 2, 3]], ops[:, [0, 2, 3]])
-        assert np.array_equal(planned[:, 4] & 0xFFFFFF, ops[:, 4])
-        e, gr = TI.run_tape_planned(n, planned, init, idx, pool.pool, c, params, terms)
-        assert abs(e - sim.energy(n, k, pool.pool, params, terms, init)) < 1e-11
-        ga = sim.grad_adjoint(n, k, pool.pool, params, terms, init)
-        got = np.zeros_like(ga)
-        for (d, j), v in gr.items():
-            got[d, k[d], j] = v
-        assert np.max(np.abs(got - ga)) < 1e-10
-    assert fused_any > 0
+        for swizzled in (True, False):
+            planned, ng, gds = TI.plan_passes(n, ops, gmax, init, idx, swizzled)
+            assert ng <= len(ops)
+            fused_any += len(ops) - ng
+            sparse_any += sum(1 for d in gds if int(d[1]) < n - 3)
+            # planning never touches parity masks, tables or depths; xor masks of 2x2 ops move to
+            # slot coordinates in a swizzled plan
+            assert np.array_equal(planned[:, 1:4], ops[:, 1:4])
+            is_u1 = ((ops[:, 4] >> 16) & 0xF) == 0
+            want_m = np.array([TI._swz(int(m)) if (swizzled and u) else int(m) for m, u in zip(ops[:, 0], is_u1)], dtype=np.uint32)
+            assert np.array_equal(planned[:, 0], want_m)
+            assert np.array_equal(planned[:, 4] & 0xFFFFFF, ops[:, 4])
+            e, gr = TI.run_tape_planned(n, planned, gds, init, idx, pool.pool, c, params, terms, swizzled=swizzled)
+            assert abs(e - sim.energy(n, k, pool.pool, params, terms, init)) < 1e-11
+            ga = sim.grad_adjoint(n, k, pool.pool, params, terms, init)
+            got = np.zeros_like(ga)
+            for (d, j), v in gr.items():
+                got[d, k[d], j] = v
+            assert np.max(np.abs(got - ga)) < 1e-10
+    assert (fused_any > 0 or gmax == 1) and sparse_any > 0
 
 
 def test_tape_compiler_rejects_out_of_range_keys():
