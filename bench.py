@@ -265,6 +265,24 @@ def run_b200(args):
     total_s = float(total_ms.item()) * 1e-3
     value = world * B * args.steps / total_s
 
+    # ---- reward-only evaluations (energy without gradient): rewards outnumber gradients 10-170x in a
+    # real search, so their rate is reported next to the headline metric
+    for _ in range(2):
+        ev.evaluate_device(d_k, d_params, d_energy, stream=stream)
+    torch.cuda.synchronize()
+    r0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    r1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()
+        r0[i].record(stream)
+        ev.evaluate_device(d_k, d_params, d_energy, stream=stream)
+        r1[i].record(stream)
+    torch.cuda.synchronize()
+    reward_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(r0, r1))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(reward_ms, op=dist.ReduceOp.MAX)
+    reward_value = world * B * args.steps / (float(reward_ms.item()) * 1e-3)
+
     # ---- end to end through the public host API: pinned host buffers in, host results out
     h_k = torch.from_numpy(ks).pin_memory()
     h_params = torch.from_numpy(params).pin_memory()
@@ -299,12 +317,21 @@ def run_b200(args):
     k_ms = statistics.mean(eval_ms)
     peak = fp64_peak_tflops(local, 5)
     achieved = f_exec / (k_ms * 1e-3) / 1e12
+    traffic = None
+    try:      # DRAM bytes per launch of the same kernel/workload from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if name in tj and B == 65536:
+            traffic = tj[name]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "eval_kernel<%d>" % n, "kernel_ms": k_ms,
+                "traffic": traffic, "kernel": "eval_kernel<%d>" % n, "kernel_ms": k_ms,
                 "kernel_share_of_step": k_ms * args.steps / sum(step_ms),
                 "achieved_survey_8d_formula": f_survey / (k_ms * 1e-3) / 1e12,
                 "peak_source": "measured live: qas_fp64_peak_tflops DFMA micro-benchmark (MEASURED_PEAKS.json has no FP64 entry)",
-                "flop_model": "2^n(58 N1 + 4 S + 4) executed-minimum; survey formula 2^n(122 N1 + 2(8G+2T)) alongside"}
+                "flop_model": "2^n(58 N1 + 4 S + 4): minimum of the dense adjoint algorithm; survey formula 2^n(122 N1 + 2(8G+2T)) "
+                              "alongside. The kernel skips work outside the state's support, so its FP64-pipe utilisation "
+                              "(ncu, profiles/) is lower than this fraction"}
 
     # ---- CPU baseline: reference-pattern oracle on a bounded sample, 1 core (how the reference runs)
     if args.tune:      # kernel-tuning runs skip the CPU leg; such a line is not a bench result
@@ -327,6 +354,8 @@ def run_b200(args):
                    "source": "search-scripts-legacy/" + WORKLOADS[name][7], "l2_flush_between_steps": True,
                    "parallelism": "circuits sharded over %d GPU(s); all_gather rewards + all_reduce gradient" % world},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "reward_only": {"value": reward_value, "unit": "evals/s", "ms_per_step": float(reward_ms.item()) / args.steps,
+                        "note": "energy without gradient (getReward), same batch, device-resident inputs"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
