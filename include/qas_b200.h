@@ -154,6 +154,17 @@ typedef struct {
 } qas_stats;
 int qas_get_stats(const qas_ctx *ctx, qas_stats *out);
 
+/* One optimiser step on the device: the update rule of qml.AdamOptimizer, the optimiser the
+ * reference hands to search() and circuitModelTuning() (qas/mcts/mcts.py:226,351-352,387,407-408),
+ * preceded by the caller-side gradient conditioning of mcts.py:346,349-350 / :404-406:
+ *   g = nan_to_num(grad) + noise_factor * noise ;  m = b1 m + (1-b1) g ;  v = b2 v + (1-b2) g*g ;
+ *   params -= stepsize * sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)
+ * All pointers are device pointers to n doubles (noise may be NULL); t = 1 for the first step.
+ * Asynchronous on `stream`.  PennyLane's defaults: beta1 0.9, beta2 0.99, eps 1e-8.            */
+int qas_adam_step(void *params, const void *grad, void *m, void *v, const void *noise, uint64_t n,
+                  int t, double stepsize, double beta1, double beta2, double eps, double noise_factor,
+                  void *stream);
+
 /* Diagnostic (contexts created with the environment variable QAS_B200_PHASE_CLOCKS=1 only): sums,
  * over all circuits evaluated so far, of the SM clock cycles a team spent in the four phases of the
  * evaluation kernel -- out4 = {prologue, forward sweep, H application + energy, adjoint sweep}.

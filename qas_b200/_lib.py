@@ -71,7 +71,7 @@ _lib = None
 EXPORTS = [
     "qas_abi_version", "qas_build_info", "qas_ctx_create", "qas_ctx_destroy", "qas_last_error",
     "qas_eval_batch", "qas_compile_tape", "qas_compile_tape_host", "qas_plan_passes_host",
-    "qas_get_stats", "qas_debug_phase_clocks",
+    "qas_get_stats", "qas_debug_phase_clocks", "qas_adam_step",
     "qas_fp64_peak_tflops",
 ]
 # include/qas_b200_sv.h
@@ -113,6 +113,9 @@ def load():
     lib.qas_plan_passes_host.restype = ctypes.c_int
     lib.qas_plan_passes_host.argtypes = [ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
                                          ctypes.c_int, vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.qas_adam_step.restype = ctypes.c_int
+    lib.qas_adam_step.argtypes = [vp, vp, vp, vp, vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                  ctypes.c_double, ctypes.c_double, ctypes.c_double, vp]
     lib.qas_debug_phase_clocks.restype = ctypes.c_int
     lib.qas_debug_phase_clocks.argtypes = [vp, vp, ctypes.c_int]
     lib.qas_get_stats.restype = ctypes.c_int

@@ -596,9 +596,22 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
 
   if (!dev) CK(cudaEventRecord(ctx->ev0, st));
   if (want_grad) CK(cudaMemsetAsync(dgrad, 0, ng * 8, st));
-  compile_tapes_kernel<<<(B + 63) / 64, 64, (size_t)64 * (2 * ctx->n + 1) * 4, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap,
-                                                         ctx->init_kind, ctx->init_basis, ctx->GMAX,
-                                                         ctx->n <= (want_grad ? 12 : 13) ? 1 : 0, ctx->d_tape);
+  {
+    const int cthr = 64;
+    // ops in shared memory only while that keeps >= 8 CTAs per SM resident (short tapes)
+    const bool ops_smem = qas_compile_smem_words(ctx->n, P.ops_cap, p, true) * 4 * cthr <= 24 * 1024;
+    const size_t csm = qas_compile_smem_words(ctx->n, P.ops_cap, p, ops_smem) * 4 * cthr;
+    if (csm > 200 * 1024) return fail(ctx, QAS_ERR_UNSUPPORTED, "structure lists too long for the tape-compile kernel");
+    const int swz_plan = ctx->n <= (want_grad ? 12 : 13) ? 1 : 0;
+    if (ops_smem) {
+      CK(cudaFuncSetAttribute(compile_tapes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+      compile_tapes_kernel<true><<<(B + cthr - 1) / cthr, cthr, csm, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap, ctx->init_kind,
+                                                                         ctx->init_basis, ctx->GMAX, swz_plan, ctx->d_tape);
+    } else {
+      compile_tapes_kernel<false><<<(B + cthr - 1) / cthr, cthr, csm, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap, ctx->init_kind,
+                                                                          ctx->init_basis, ctx->GMAX, swz_plan, ctx->d_tape);
+    }
+  }
   CK(cudaGetLastError());
   build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
   CK(cudaGetLastError());
@@ -680,6 +693,20 @@ extern "C" int qas_compile_tape(const qas_ctx *ctx, int p, const int32_t *k, uin
   if (!ctx) return QAS_ERR_INVALID;
   return qas_compile_tape_host(ctx->n, ctx->pool.data(), ctx->c, p, k, ctx->init_basis, out_ops,
                                max_ops, num_ops, init_index);
+}
+
+// ---------------------------------------------------------------------------------- optimiser
+extern "C" int qas_adam_step(void *params, const void *grad, void *m, void *v, const void *noise, uint64_t n,
+                             int t, double stepsize, double beta1, double beta2, double eps,
+                             double noise_factor, void *stream) {
+  if (!params || !grad || !m || !v || n == 0 || t < 1) { g_create_error = "bad arguments to qas_adam_step"; return QAS_ERR_INVALID; }
+  const double step = stepsize * std::sqrt(1.0 - std::pow(beta2, (double)t)) / (1.0 - std::pow(beta1, (double)t));
+  adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (double *)params, (const double *)grad, (double *)m, (double *)v, (const double *)noise, (size_t)n, step, beta1,
+      beta2, eps, noise_factor);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_create_error = std::string("adam_step_kernel: ") + cudaGetErrorString(e); return QAS_ERR_CUDA; }
+  return QAS_OK;
 }
 
 // ---------------------------------------------------------------------------------- FP64 peak

@@ -290,24 +290,60 @@ __device__ __forceinline__ void load_vrow(double (&v)[NB], const double *p, uint
 __host__ __device__ __forceinline__ size_t qas_rec_words(int ops_cap, int n) {
   return (size_t)QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS + (size_t)ops_cap * QAS_GD_STRIDE(n);
 }
+// OPS_SMEM: the ops are built and planned in shared memory (the planner reads them back many
+// times; from global memory every read is a dependent L2 round trip) and copied out warp-
+// cooperatively, coalesced.  Per thread: frame (2n+1 words) | ops (ops_cap*5 words, odd stride).
+// plus the circuit's structure list (p words, odd stride), staged coalesced by the whole CTA.
+__host__ __device__ __forceinline__ size_t qas_compile_smem_words(int n, int ops_cap, int p, bool ops_smem) {
+  return (size_t)(2 * n + 1) + (size_t)(p | 1) + (ops_smem ? (size_t)((ops_cap * QAS_OP_WORDS) | 1) : 0);
+}
+template <bool OPS_SMEM>
 __global__ void compile_tapes_kernel(const int32_t *k, const qas_pool_entry *pool, int B, int p, int c,
                                      int n, int ops_cap, int init_kind, uint64_t init_basis,
                                      int gmax, int swizzled, uint32_t *tape) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  const bool live = b < B;
   // GF(2) frame (col / row, indexed by wire at run time): shared memory, odd stride per thread
   extern __shared__ uint32_t frame_smem[];
-  uint32_t *col = frame_smem + (size_t)threadIdx.x * (2 * n + 1), *row = col + n;
-  uint32_t *rec = tape + (size_t)b * qas_rec_words(ops_cap, n);
-  QasTapeSink sink{rec + QAS_REC_HDR, ops_cap, 0, 0};
-  const int st = qas_compile_circuit(k + (size_t)b * p, p, pool, c, n, col, row, sink);
-  const int nops = st ? 0 : sink.n;
-  const uint32_t init_index = (init_kind == QAS_INIT_BASIS && !st) ? qas_frame_map_basis(col, n, init_basis) : 0u;
-  rec[0] = (uint32_t)nops;
-  rec[1] = (uint32_t)st;
-  rec[2] = init_index;
-  rec[3] = (uint32_t)qas_plan_groups(rec + QAS_REC_HDR, nops, gmax, n, init_kind, init_index,
-                                     rec + QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS, swizzled);   // passes per sweep
+  const size_t stride = qas_compile_smem_words(n, ops_cap, p, OPS_SMEM);
+  uint32_t *mine = frame_smem + (size_t)threadIdx.x * stride;
+  uint32_t *col = mine, *row = col + n;
+  int32_t *ks = reinterpret_cast<int32_t *>(mine + (2 * n + 1));
+  uint32_t *rec = tape + (size_t)(live ? b : 0) * qas_rec_words(ops_cap, n);
+  uint32_t *ops = OPS_SMEM ? mine + (2 * n + 1) + (p | 1) : rec + QAS_REC_HDR;
+  {   // the CTA's structure lists are contiguous in global memory: coalesced copy, row t -> thread t
+    const size_t first = (size_t)blockIdx.x * blockDim.x * p;
+    const size_t count = (size_t)min((int)blockDim.x, B - (int)(blockIdx.x * blockDim.x)) * p;
+    for (size_t w = threadIdx.x; w < count; w += blockDim.x) {
+      const size_t t = w / p, i = w - t * p;
+      reinterpret_cast<int32_t *>(frame_smem + t * stride + (2 * n + 1))[i] = k[first + w];
+    }
+    __syncthreads();
+  }
+  int nops = 0;
+  if (live) {
+    QasTapeSink sink{ops, ops_cap, 0, 0};
+    const int st = qas_compile_circuit(ks, p, pool, c, n, col, row, sink);
+    nops = st ? 0 : sink.n;
+    const uint32_t init_index = (init_kind == QAS_INIT_BASIS && !st) ? qas_frame_map_basis(col, n, init_basis) : 0u;
+    rec[0] = (uint32_t)nops;
+    rec[1] = (uint32_t)st;
+    rec[2] = init_index;
+    rec[3] = (uint32_t)qas_plan_groups(ops, nops, gmax, n, init_kind, init_index,
+                                       rec + QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS, swizzled);   // passes per sweep
+  }
+  if constexpr (OPS_SMEM) {
+    __syncwarp();
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    for (int t = 0; t < 32; ++t) {
+      const int words = __shfl_sync(0xffffffffu, nops, t) * QAS_OP_WORDS;
+      const int bt = blockIdx.x * blockDim.x + wbase + t;
+      if (bt >= B) break;
+      const uint32_t *src = frame_smem + (size_t)(wbase + t) * stride + (2 * n + 1) + (p | 1);
+      uint32_t *dst = tape + (size_t)bt * qas_rec_words(ops_cap, n) + QAS_REC_HDR;
+      for (int w = lane; w < words; w += 32) dst[w] = src[w];
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------ evaluation
@@ -858,6 +894,26 @@ __global__ void grad_final_reduce_kernel(const double *partial, int nchunks, siz
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   if (lane == 0) out[x] = s * scale;
+}
+
+// ------------------------------------------------------------------------------ optimiser step
+// One Adam step with the rule of qml.AdamOptimizer (the optimiser the reference passes to search /
+// circuitModelTuning, qas/mcts/mcts.py:226,351-352,387,407-408), on the device so that a tuning
+// loop never moves the parameter tensor over PCIe:
+//   g <- nan_to_num(grad) + noise_factor * noise        (mcts.py:346,349-350 / :404-406)
+//   m <- b1 m + (1-b1) g ;  v <- b2 v + (1-b2) g g ;  x <- x - step * m / (sqrt(v) + eps)
+// step = stepsize * sqrt(1 - b2^t) / (1 - b1^t) is computed on the host in double precision.
+__global__ void adam_step_kernel(double *x, const double *grad, double *m, double *v, const double *noise,
+                                 size_t n, double step, double b1, double b2, double eps, double noise_factor) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double g = nan_to_num_d(grad[i]);
+  if (noise) g += noise_factor * noise[i];
+  const double mi = b1 * m[i] + (1.0 - b1) * g;
+  const double vi = b2 * v[i] + (1.0 - b2) * g * g;
+  m[i] = mi;
+  v[i] = vi;
+  x[i] = x[i] - step * mi / (sqrt(vi) + eps);
 }
 
 // ------------------------------------------------------------------------------ FP64 peak

@@ -199,3 +199,41 @@ def circuitModelTuning(initial_params=None, model=None, num_epochs: int = None, 
             print("early stop at epoch %d" % (epoch + 1))
             break
     return theta, losses
+
+
+def circuitModelTuningDevice(initial_params=None, model=None, num_epochs: int = None, k=None, op_pool=None, lr=0.01,
+                             grad_noise_factor=0.0, verbose=0, early_stop_threshold=1e-15, check_every=1, seed=None):
+    """circuitModelTuning (reference :381-412) with the whole loop on the GPU: the parameter tensor,
+    the Adam moments and the gradient never leave HBM; per epoch the host reads back one double (the
+    loss, every ``check_every`` epochs) for the early-stop test.  Noise, when requested, comes from
+    torch's CUDA generator (a different stream of random numbers than np.random.randn upstream).
+    Returns (theta as ndarray, losses)."""
+    import torch
+    from qas_b200.optim import DeviceAdam
+    p, c, l = initial_params.shape
+    ev = model.evaluator(op_pool, l)
+    dev = torch.device("cuda", ev.device)
+    stream = torch.cuda.current_stream(dev)
+    theta = torch.as_tensor(np.ascontiguousarray(initial_params, dtype=np.float64)).to(dev)
+    d_k = torch.as_tensor(np.ascontiguousarray(np.asarray(k, dtype=np.int32)[None, :])).to(dev)
+    d_e = torch.empty(1, dtype=torch.float64, device=dev)
+    d_g = torch.empty(p, c, l, dtype=torch.float64, device=dev)
+    d_losses = torch.empty(num_epochs, dtype=torch.float64, device=dev)
+    gen = None
+    if grad_noise_factor:
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(0 if seed is None else int(seed))
+    opt = DeviceAdam(theta, stepsize=lr)
+    done = 0
+    for epoch in range(num_epochs):
+        ev.evaluate_device(d_k, theta, d_e, None, d_g, avg=True, stream=stream)
+        d_losses[epoch:epoch + 1].copy_(d_e)
+        noise = torch.randn(p, c, l, dtype=torch.float64, device=dev, generator=gen) if gen is not None else None
+        opt.step(d_g, noise, grad_noise_factor, stream)
+        done = epoch + 1
+        if (epoch + 1) % check_every == 0 and float(d_e.item()) <= early_stop_threshold:
+            if verbose:
+                print("early stop at epoch %d" % (epoch + 1))
+            break
+    losses = [float(x) for x in d_losses[:done].cpu().numpy()]
+    return theta.cpu().numpy(), losses

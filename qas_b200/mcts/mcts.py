@@ -1,7 +1,8 @@
 """Import-compatible face of the search driver: the reference exposes everything from one module
 (``from qas.mcts.mcts import search, TreeNode, MCTSController, circuitModelTuning``); here the
 tree lives in ``tree.py`` and the epoch loops in ``driver.py``."""
-from qas_b200.mcts.driver import SearchConfig, batchGradient, circuitModelTuning, search  # noqa: F401
+from qas_b200.mcts.driver import (SearchConfig, batchGradient, circuitModelTuning,  # noqa: F401
+                                  circuitModelTuningDevice, search)
 from qas_b200.mcts.tree import MCTSController, TreeNode  # noqa: F401
 
 

@@ -32,3 +32,33 @@ class AdamOptimizer:
     def reset(self):
         self.fm = self.sm = None
         self.t = 0
+
+
+class DeviceAdam:
+    """The same rule on the GPU (libqas_b200: qas_adam_step): parameters, moments and the gradient
+    stay in HBM, so an optimisation loop over a fixed circuit never moves them over PCIe.
+    ``params`` is a CUDA float64 tensor updated in place by ``step``."""
+
+    def __init__(self, params, stepsize=0.01, beta1=0.9, beta2=0.99, eps=1e-8):
+        import torch
+        from qas_b200 import _lib
+        assert params.is_cuda and params.dtype == torch.float64 and params.is_contiguous()
+        self._lib = _lib.load()
+        self.params = params
+        self.stepsize, self.beta1, self.beta2, self.eps = stepsize, beta1, beta2, eps
+        self.fm = torch.zeros_like(params)
+        self.sm = torch.zeros_like(params)
+        self.t = 0
+
+    def step(self, grad, noise=None, noise_factor=0.0, stream=None):
+        """grad (and noise, if given): CUDA float64 tensors of params' shape."""
+        import ctypes
+        assert grad.is_cuda and grad.is_contiguous() and grad.numel() == self.params.numel()
+        self.t += 1
+        sp = ctypes.c_void_p(stream.cuda_stream) if stream is not None else None
+        rc = self._lib.qas_adam_step(self.params.data_ptr(), grad.data_ptr(), self.fm.data_ptr(), self.sm.data_ptr(),
+                                     noise.data_ptr() if noise is not None else None, self.params.numel(), self.t,
+                                     self.stepsize, self.beta1, self.beta2, self.eps, float(noise_factor), sp)
+        if rc != 0:
+            raise RuntimeError("qas_adam_step failed (%d): %s" % (rc, self._lib.qas_last_error(None).decode()))
+        return self.params

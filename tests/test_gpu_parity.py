@@ -353,3 +353,46 @@ def test_search_and_tuning_drop_in_on_gpu():
     theta, losses = circuitModelTuning(initial_params=g["params"], model=FourQubitH2, num_epochs=3, k=g["k"],
                                        op_pool=pool, lr=1e-4, grad_noise_factor=0, verbose=0, early_stop_threshold=-2.0)
     assert abs(losses[0] - g["fine_tune_loss_tail"][-1]) < 5e-5
+
+
+def test_device_adam_step_matches_numpy_rule():
+    """qas_adam_step = the qml.AdamOptimizer rule of qas_b200.optim.AdamOptimizer (mcts.py:351-352),
+    including the nan_to_num / noise conditioning of the gradient (mcts.py:346-350)."""
+    import torch
+    from qas_b200.optim import AdamOptimizer, DeviceAdam
+    rng = np.random.default_rng(3)
+    x0 = rng.standard_normal((7, 5, 3))
+    host = AdamOptimizer(stepsize=0.05)
+    xh = x0.copy()
+    xd = torch.from_numpy(x0.copy()).cuda()
+    dev = DeviceAdam(xd, stepsize=0.05)
+    for step in range(6):
+        g = rng.standard_normal(x0.shape)
+        noise = rng.standard_normal(x0.shape)
+        if step == 2:
+            g[0, 0, 0] = np.nan
+            g[1, 2, 1] = np.inf
+        xh = host.apply_grad(np.nan_to_num(g) + 0.01 * noise, xh)
+        dev.step(torch.from_numpy(g).cuda(), torch.from_numpy(noise).cuda(), 0.01)
+        torch.cuda.synchronize()
+        assert np.max(np.abs(xd.cpu().numpy() - xh)) <= 1e-13 * max(1.0, np.max(np.abs(xh)))
+
+
+def test_device_tuning_loop_matches_host_loop():
+    """circuitModelTuningDevice (loop resident on the GPU) follows the host loop of
+    circuitModelTuning (reference mcts.py:381-412) step for step when no noise is injected."""
+    from qas_b200.mcts.mcts import circuitModelTuning, circuitModelTuningDevice
+    from qas_b200.qml_models.qml_models_legacy import FourQubitH2
+    pool = helpers.near_cx_pool(4)
+    c = len(pool)
+    p = 8
+    k = [0, 2, 8, 4, 6, 10, 3, 12]
+    params = np.random.default_rng(11).standard_normal((p, c, 3))
+    th_h, loss_h = circuitModelTuning(params, FourQubitH2, 12, k, pool, lr=0.05, grad_noise_factor=0.0, verbose=0,
+                                      early_stop_threshold=-1e9)
+    th_d, loss_d = circuitModelTuningDevice(params, FourQubitH2, 12, k, pool, lr=0.05, grad_noise_factor=0.0,
+                                            early_stop_threshold=-1e9)
+    assert len(loss_h) == len(loss_d) == 12
+    assert np.max(np.abs(np.array(loss_h) - np.array(loss_d))) <= 1e-9
+    assert np.max(np.abs(th_h - th_d)) <= 1e-9
+    assert loss_d[-1] < loss_d[0]
