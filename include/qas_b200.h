@@ -73,6 +73,11 @@ typedef struct {
 #define QAS_F_GRAD_SUM 0x2u    /* grad_dense = sum over the batch instead of mean                */
                                /* (search(..., avg_gradients=False), mcts.py:347)                */
 
+#define QAS_F_PARAMS_RESIDENT 0x4u /* host-pointer calls only: ignore `params`, use the super-set (and   */
+                                  /* its gate table) that qas_set_params left on the device -- the   */
+                                  /* one-reward-at-a-time rollouts of mcts.py:100-105,181 then cost   */
+                                  /* one k upload, the kernels and an 8-byte read-back                */
+
 typedef struct qas_ctx qas_ctx;
 
 /* Library / build info. */
@@ -109,6 +114,12 @@ const char *qas_last_error(const qas_ctx *ctx);
 int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, const double *params,
                    double *energy, double *grad_compact, double *grad_dense, uint32_t flags,
                    void *stream);
+
+/* Upload the parameter super-set params[p][c][l] once and build its gate table; later
+ * qas_eval_batch calls with QAS_F_PARAMS_RESIDENT reuse both.  Any qas_eval_batch call without the
+ * flag invalidates the resident copy.  (The reference passes the same `params` to every
+ * getReward of an epoch, mcts.py:284-351.)                                                   */
+int qas_set_params(qas_ctx *ctx, int p, const double *params);
 
 /* Host-side run of the tape compiler on ONE structure list (no GPU needed): lowers k to the
  * generalised-gate tape the kernels execute (CNOT/SWAP folded into the index frame).

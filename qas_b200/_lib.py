@@ -21,6 +21,7 @@ QAS_INIT_PLUS = 2
 
 QAS_F_DEVICE_PTRS = 0x1
 QAS_F_GRAD_SUM = 0x2
+QAS_F_PARAMS_RESIDENT = 0x4
 
 QAS_OP_WORDS = 5
 
@@ -71,7 +72,7 @@ _lib = None
 EXPORTS = [
     "qas_abi_version", "qas_build_info", "qas_ctx_create", "qas_ctx_destroy", "qas_last_error",
     "qas_eval_batch", "qas_compile_tape", "qas_compile_tape_host", "qas_plan_passes_host",
-    "qas_get_stats", "qas_debug_phase_clocks", "qas_adam_step",
+    "qas_get_stats", "qas_debug_phase_clocks", "qas_adam_step", "qas_set_params",
     "qas_fp64_peak_tflops",
 ]
 # include/qas_b200_sv.h
@@ -113,6 +114,8 @@ def load():
     lib.qas_plan_passes_host.restype = ctypes.c_int
     lib.qas_plan_passes_host.argtypes = [ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
                                          ctypes.c_int, vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.qas_set_params.restype = ctypes.c_int
+    lib.qas_set_params.argtypes = [vp, ctypes.c_int, vp]
     lib.qas_adam_step.restype = ctypes.c_int
     lib.qas_adam_step.argtypes = [vp, vp, vp, vp, vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                   ctypes.c_double, ctypes.c_double, ctypes.c_double, vp]

@@ -33,11 +33,14 @@ struct qas_ctx {
   uint32_t *d_cdesc_plain = nullptr;
   double *d_mout = nullptr; size_t cap_mout = 0;
   unsigned long long *d_phase = nullptr;   // QAS_B200_PHASE_CLOCKS=1: per-phase clock sums (diagnostic)
+  bool stage_times = false;                // QAS_B200_STAGE_TIMES=1: print per-kernel stream times of every call
+  cudaEvent_t sev[8] = {nullptr};
   int RBH = 0, PD = 1;             // H-apply blocking / prefetch depth (QAS_B200_HCFG=rb,pd overrides)
   int gcfg_g = 0, gcfg_m = 0;      // QAS_B200_GCFG=gmax,minb tuning override (n = 8, 10 default teams)
   GateTab *d_U = nullptr;
   GateDTab *d_dU = nullptr;
   int tab_p = 0;
+  int resident_p = 0;              // depth of the parameter super-set left on the device by qas_set_params (0: none)
   int32_t *d_k = nullptr;  size_t cap_k = 0;
   double *d_params = nullptr; size_t cap_params = 0;
   double *d_energy = nullptr; size_t cap_energy = 0;
@@ -261,6 +264,7 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
 
   // threads per team, amplitudes per thread of the fused gate passes and of the H application
   if (const char *ts = getenv("QAS_B200_TEAM_SHIFT")) cx->team_shift = atoi(ts);
+  cx->stage_times = getenv("QAS_B200_STAGE_TIMES") && atoi(getenv("QAS_B200_STAGE_TIMES")) != 0;
   const bool want_phase = getenv("QAS_B200_PHASE_CLOCKS") && atoi(getenv("QAS_B200_PHASE_CLOCKS")) != 0;
   cx->T = team_threads_for(n_qubits, cx->team_shift);
   cx->GMAX = qas_gmax(n_qubits <= 13 ? n_qubits : 20, cx->T);
@@ -401,6 +405,7 @@ extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ek0) cudaEventDestroy(ctx->ek0);
   if (ctx->ek1) cudaEventDestroy(ctx->ek1);
+  for (int i = 0; i < 8; ++i) if (ctx->sev[i]) cudaEventDestroy(ctx->sev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return QAS_OK;
@@ -514,11 +519,45 @@ static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
   return launch_gmem<GRAD>(ctx, P, st);
 }
 
+// gate tables sized for depth p (constant rows filled once)
+static int ensure_gate_tables(qas_ctx *ctx, int p, cudaStream_t st) {
+  if (ctx->tab_p >= p) return QAS_OK;
+  const int c = ctx->c;
+  cudaFree(ctx->d_U); cudaFree(ctx->d_dU);
+  ctx->d_U = nullptr; ctx->d_dU = nullptr; ctx->tab_p = 0; ctx->resident_p = 0;
+  const size_t ne = (size_t)QAS_NCONST + (size_t)p * c;
+  CK(cudaMalloc(&ctx->d_U, ne * sizeof(GateTab)));
+  CK(cudaMalloc(&ctx->d_dU, ne * sizeof(GateDTab)));
+  CK(cudaMemsetAsync(ctx->d_dU, 0, ne * sizeof(GateDTab), st));
+  std::vector<GateTab> ct(QAS_NCONST);
+  fill_const_table(ct);
+  CK(cudaMemcpyAsync(ctx->d_U, ct.data(), sizeof(GateTab) * QAS_NCONST, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  ctx->tab_p = p;
+  return QAS_OK;
+}
+
+extern "C" int qas_set_params(qas_ctx *ctx, int p, const double *params) {
+  if (!ctx || p <= 0 || p > 65535 || !params) return fail(ctx, QAS_ERR_INVALID, "bad arguments to qas_set_params");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t npar = (size_t)p * ctx->c * ctx->l;
+  { const int rc = ensure_gate_tables(ctx, p, st); if (rc != QAS_OK) return rc; }
+  CK(ensure(&ctx->d_params, &ctx->cap_params, npar));
+  CK(cudaMemcpyAsync(ctx->d_params, params, npar * 8, cudaMemcpyHostToDevice, st));
+  build_gate_table_kernel<<<(p * ctx->c + 127) / 128, 128, 0, st>>>(ctx->d_pool, ctx->c, p, ctx->l, ctx->d_params, ctx->d_U, ctx->d_dU);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  ctx->resident_p = p;
+  return QAS_OK;
+}
+
 extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, const double *params,
                               double *energy, double *grad_compact, double *grad_dense,
                               uint32_t flags, void *stream) {
   if (!ctx) return QAS_ERR_INVALID;
-  if (B <= 0 || p <= 0 || p > 65535 || !k || !params || !energy) return fail(ctx, QAS_ERR_INVALID, "bad arguments to qas_eval_batch");
+  if (B <= 0 || p <= 0 || p > 65535 || !k || (!params && !(flags & QAS_F_PARAMS_RESIDENT)) || !energy)
+    return fail(ctx, QAS_ERR_INVALID, "bad arguments to qas_eval_batch");
   const bool dev = flags & QAS_F_DEVICE_PTRS;
   const bool want_grad = grad_compact || grad_dense;
   const int c = ctx->c, l = ctx->l;
@@ -534,20 +573,11 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
       if (k[i] < 0 || k[i] >= c) return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
   }
 
-  // gate tables sized for this depth
-  if (ctx->tab_p < p) {
-    cudaFree(ctx->d_U); cudaFree(ctx->d_dU);
-    ctx->d_U = nullptr; ctx->d_dU = nullptr; ctx->tab_p = 0;
-    const size_t ne = (size_t)QAS_NCONST + (size_t)p * c;
-    CK(cudaMalloc(&ctx->d_U, ne * sizeof(GateTab)));
-    CK(cudaMalloc(&ctx->d_dU, ne * sizeof(GateDTab)));
-    CK(cudaMemsetAsync(ctx->d_dU, 0, ne * sizeof(GateDTab), st));
-    std::vector<GateTab> ct(QAS_NCONST);
-    fill_const_table(ct);
-    CK(cudaMemcpyAsync(ctx->d_U, ct.data(), sizeof(GateTab) * QAS_NCONST, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-    ctx->tab_p = p;
-  }
+  const bool resident = (flags & QAS_F_PARAMS_RESIDENT) != 0;
+  if (resident && (dev || ctx->resident_p != p))
+    return fail(ctx, QAS_ERR_INVALID, "QAS_F_PARAMS_RESIDENT needs host pointers and a prior qas_set_params of the same depth");
+  { const int rc = ensure_gate_tables(ctx, p, st); if (rc != QAS_OK) return rc; }
+  if (!resident) ctx->resident_p = 0;      // the tables are about to be rebuilt from other parameters
 
   const int32_t *dk = k;
   const double *dparams = params;
@@ -557,7 +587,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     CK(ensure(&ctx->d_params, &ctx->cap_params, npar));
     CK(ensure(&ctx->d_energy, &ctx->cap_energy, (size_t)B));
     CK(cudaMemcpyAsync(ctx->d_k, k, nk * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_params, params, npar * 8, cudaMemcpyHostToDevice, st));
+    if (!resident) CK(cudaMemcpyAsync(ctx->d_params, params, npar * 8, cudaMemcpyHostToDevice, st));
     dk = ctx->d_k; dparams = ctx->d_params; denergy = ctx->d_energy;
     dgrad = nullptr;
     if (grad_dense) { CK(ensure(&ctx->d_dense, &ctx->cap_dense, npar)); ddense = ctx->d_dense; }
@@ -594,8 +624,15 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     P.mout = ctx->d_mout;
   }
 
+  auto stamp = [&](int i) {
+    if (!ctx->stage_times) return;
+    if (!ctx->sev[i]) cudaEventCreate(&ctx->sev[i]);
+    cudaEventRecord(ctx->sev[i], st);
+  };
   if (!dev) CK(cudaEventRecord(ctx->ev0, st));
+  stamp(0);
   if (want_grad) CK(cudaMemsetAsync(dgrad, 0, ng * 8, st));
+  stamp(1);
   {
     const int cthr = 64;
     // ops in shared memory only while that keeps >= 8 CTAs per SM resident (short tapes)
@@ -613,20 +650,26 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     }
   }
   CK(cudaGetLastError());
-  build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
-  CK(cudaGetLastError());
+  stamp(2);
+  if (!resident) {
+    build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
+    CK(cudaGetLastError());
+  }
   CK(cudaEventRecord(ctx->ek0, st));
+  stamp(3);
   if (want_grad) CK(launch_eval<true>(ctx, P, st)); else CK(launch_eval<false>(ctx, P, st));
   CK(cudaEventRecord(ctx->ek1, st));
+  stamp(4);
   ctx->ek_pending = true;
   ctx->stats.launches += 3;
   if (want_grad) {
-    const size_t nthr = (size_t)B * P.ops_cap * 3;
+    const size_t nthr = (size_t)B * P.ops_cap;
     grad_finalize_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ctx->d_tape, ctx->d_mout, ctx->d_dU, B, p, l,
                                                                         P.ops_cap, ctx->n, dgrad);
     CK(cudaGetLastError());
     ctx->stats.launches += 1;
   }
+  stamp(5);
 
   if (grad_dense) {
     const int chunk = 32;      // circuits per CTA of the first stage (2048 CTAs at B = 65536)
@@ -640,10 +683,23 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     const int cthreads = std::min(256, std::max(64, ((std::min(depth_tile, p) * l + 31) / 32) * 32));
     grad_chunk_reduce_kernel<<<grid, cthreads, sm, st>>>(dk, dgrad, B, p, c, l, chunk, depth_tile, ctx->d_partial);
     CK(cudaGetLastError());
+    stamp(6);
     const double scale = (flags & QAS_F_GRAD_SUM) ? 1.0 : 1.0 / (double)B;
     grad_final_reduce_kernel<<<(unsigned)((npar * 32 + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, scale, ddense);
     CK(cudaGetLastError());
     ctx->stats.launches += 2;
+    stamp(7);
+  }
+  if (ctx->stage_times) {
+    cudaStreamSynchronize(st);
+    const char *names[7] = {"memset", "compile_tapes", "gate_table", "eval", "finalize", "chunk_reduce", "final_reduce"};
+    fprintf(stderr, "[qas stage times] B=%d:", B);
+    for (int i = 0; i < (grad_dense ? 7 : 5); ++i) {
+      float ms = 0.f;
+      if (ctx->sev[i] && ctx->sev[i + 1] && cudaEventElapsedTime(&ms, ctx->sev[i], ctx->sev[i + 1]) == cudaSuccess)
+        fprintf(stderr, " %s %.1f us", names[i], ms * 1e3);
+    }
+    fprintf(stderr, "\n");
   }
   ctx->stats.evals += (uint64_t)B;
 

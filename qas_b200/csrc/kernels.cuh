@@ -828,25 +828,31 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
 
 // ------------------------------------------------------------------------------ gradient finalize
 // dE/dtheta_j = 2 Re sum_ab (dU_j)_ab M_ab for every parametrised op of every circuit: one thread
-// per (circuit, tape op, parameter slot).  Kept out of the evaluation kernel so that no team
+// per (circuit, tape op), all of its <= 3 parameter slots.  Kept out of the evaluation kernel so that no team
 // waits on the dU table (L2 latency) between passes.  grad must be zero-filled beforehand.
 __global__ void grad_finalize_kernel(const uint32_t *tape, const double *mout, const GateDTab *dU, int B,
                                      int p, int l, int ops_cap, int n, double *grad) {
   const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t per = (size_t)ops_cap * 3;
-  if (x >= (size_t)B * per) return;
-  const int b = (int)(x / per), rem = (int)(x % per), oi = rem / 3, jj = rem - oi * 3;
+  if (x >= (size_t)B * ops_cap) return;
+  const int b = (int)(x / ops_cap), oi = (int)(x % ops_cap);
   const uint32_t *rec = tape + (size_t)b * qas_rec_words(ops_cap, n);
   if (oi >= (int)rec[0] || rec[1]) return;
   const uint32_t *o = rec + QAS_REC_HDR + (size_t)oi * QAS_OP_WORDS;
   const uint32_t mt = o[4];
-  if (jj >= qas_meta_npar(mt) || jj >= l) return;
-  const double *m = mout + ((size_t)b * ops_cap + oi) * 8;
-  const double2 *d = dU[o[3]].d[jj];
-  double part = 0.0;
+  const int npar = min(qas_meta_npar(mt), l);
+  if (!npar) return;
+  const double2 *mp = reinterpret_cast<const double2 *>(mout + ((size_t)b * ops_cap + oi) * 8);
+  double2 m[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) part += d[q].x * m[2 * q] - d[q].y * m[2 * q + 1];
-  grad[((size_t)b * p + qas_meta_depth(mt)) * l + jj] = 2.0 * part;
+  for (int q = 0; q < 4; ++q) m[q] = mp[q];
+  double *g = grad + ((size_t)b * p + qas_meta_depth(mt)) * l;
+  for (int jj = 0; jj < npar; ++jj) {
+    const double2 *d = dU[o[3]].d[jj];
+    double part = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) part += d[q].x * m[q].x - d[q].y * m[q].y;
+    g[jj] = 2.0 * part;
+  }
 }
 
 // ------------------------------------------------------------------------------ batch reduce

@@ -312,14 +312,23 @@ QAS_HD void qas_plan_supports(const uint32_t *ops, int nops, int ngroups, int n,
     QasPivTab<NQ> Sin, Sout;
     Sin.clear();
     Sout.clear();
-    int dc = 0, tot = 0;
+    int dc = 0, tot = 0, drank = 0;
 #pragma unroll
-    for (int p = 0; p < NQ; ++p)
-      if (D.v[p]) dc += qas_tab_add_lsb<NQ>(Sin, Sout, false, Sin, proj(D.v[p])) ? 1 : 0;
-    tot = dc;
+    for (int p = 0; p < NQ; ++p) drank += D.v[p] ? 1 : 0;
+    if (drank == n) {     // the state is dense already: every coset is inside, one echelon pass
 #pragma unroll
-    for (int p = 0; p < NQ; ++p)
-      if (p < n && tot < n - g) tot += qas_tab_add_lsb<NQ>(Sin, Sout, true, Sin, proj(1u << p)) ? 1 : 0;
+      for (int p = 0; p < NQ; ++p)
+        if (p < n) dc += qas_tab_add_lsb<NQ>(Sin, Sout, false, Sin, proj(1u << p)) ? 1 : 0;
+      tot = dc;
+    } else {
+#pragma unroll
+      for (int p = 0; p < NQ; ++p)
+        if (D.v[p]) dc += qas_tab_add_lsb<NQ>(Sin, Sout, false, Sin, proj(D.v[p])) ? 1 : 0;
+      tot = dc;
+#pragma unroll
+      for (int p = 0; p < NQ; ++p)
+        if (p < n && tot < n - g) tot += qas_tab_add_lsb<NQ>(Sin, Sout, true, Sin, proj(1u << p)) ? 1 : 0;
+    }
     d[0] = proj(b0);
     d[1] = (uint32_t)dc;
     int cnt = 0;
@@ -361,7 +370,9 @@ QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax, int n, int init_ki
     ++ngroups;
   }
   if (!gd) return ngroups;
-  if (n <= 12) qas_plan_supports<12>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled);
+  if (n <= 5) qas_plan_supports<5>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled);
+  else if (n <= 8) qas_plan_supports<8>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled);
+  else if (n <= 12) qas_plan_supports<12>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled);
   else qas_plan_supports<QAS_MAX_QUBITS>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled);
   if (swizzled)
     for (int j = 0; j < nops; ++j) {

@@ -90,11 +90,28 @@ def batchGradient(model, arcs, params, op_pool, avg_gradients=True):
     return stack.mean(axis=0) if avg_gradients else stack.sum(axis=0)
 
 
+# "auto": use the native tree policy when the model is backed by the CUDA evaluator (that is when the
+# Python tree is the bottleneck) and the configuration can run natively (reference state classes,
+# penalty None or a PlaceholderPenalty); True: whenever it can run natively; False: never.
+USE_NATIVE_TREE = "auto"
+
+
+def _native_possible(cfg):
+    from qas_b200.mcts.native import native_penalty
+    name = getattr(cfg.state_class, "name", "")
+    return name in ("QMLStateBasicGates", "QMLStateBasicGatesNoRestrictions") and native_penalty(cfg.penalty_function) is not None
+
+
 def _penalised(cfg, reward, node):
     return reward if cfg.penalty_function is None else cfg.penalty_function(reward, node)
 
 
 def _warmup_epoch(cfg, controller, params):
+    if hasattr(controller, "warmupBatch"):                 # native tree: sampling, batch reward, back-propagation
+        arcs, _ = controller.warmupBatch(cfg.warmup_arc_batchsize)
+        if cfg.warm_up_reset:
+            controller._reset()
+        return arcs
     drawn = [controller.randomSample() for _ in range(cfg.warmup_arc_batchsize)]
     arcs = [k for k, _ in drawn]
     for (k, node), reward in zip(drawn, controller.batchRewards(arcs, params)):
@@ -112,6 +129,10 @@ def _search_epoch(cfg, controller, params, epoch):
     done = epoch + 1 - cfg.num_warmup_iterations
     controller.prune_reward_ratio = cfg.prune_constant_min + (cfg.prune_constant_max - cfg.prune_constant_min) / span * done
     arcs = []
+    if hasattr(controller, "sampleArcAndBackPropagate"):   # native tree
+        for _ in range(cfg.search_arc_batchsize):
+            arcs.append(controller.sampleArcAndBackPropagate()[0])
+        return arcs
     for _ in range(cfg.search_arc_batchsize):
         k, node = controller.sampleArcWithSuperCircParams(params)
         arcs.append(k)
@@ -127,7 +148,12 @@ def search(*args, **kwargs):
     assert p == cfg.init_params.shape[0]
     assert c == cfg.init_params.shape[1]
     assert cfg.prune_constant_min <= cfg.prune_constant_max
-    controller = MCTSController(
+    native = _native_possible(cfg) and (USE_NATIVE_TREE is True or (USE_NATIVE_TREE == "auto" and hasattr(model, "evaluator")))
+    if native:
+        from qas_b200.mcts.native import NativeMCTSController as Controller
+    else:
+        Controller = MCTSController
+    controller = Controller(
         model=model, op_pool=pool, target_circuit_depth=p, state_class=cfg.state_class,
         reward_penalty_function=cfg.penalty_function,
         initial_legal_control_qubit_choice=cfg.init_qubit_with_controls, alpha=cfg.alpha_max,
@@ -143,7 +169,10 @@ def search(*args, **kwargs):
     best_arc = best_node = best_reward = None
     for epoch in range(cfg.num_iterations):
         t0 = time.time()
-        controller.clearRewardCache()
+        if native:
+            controller.setParams(params)                   # upload once per epoch, drops cached rewards
+        else:
+            controller.clearRewardCache()
         warm = epoch < cfg.num_warmup_iterations
         log("[%s] epoch %d/%d (%s): pool %d, batch %d" % (
             model.name, epoch + 1, cfg.num_iterations, "warm-up" if warm else "search", c,
@@ -152,7 +181,10 @@ def search(*args, **kwargs):
         grad = batchGradient(model, arcs, params, pool, cfg.avg_gradients)
         grad = grad + np.random.randn(p, c, l) * cfg.super_circ_train_gradient_noise_factor
         params = np.array(optimizer.apply_grad(grad=grad, args=params))
-        controller.clearRewardCache()                      # rewards of the old parameters are stale
+        if native:
+            controller.setParams(params)                   # rewards of the old parameters are stale
+        else:
+            controller.clearRewardCache()
         best_arc, best_node = controller.exploitArcWithSuperCircParams(params)
         best_model = model(p, c, l, best_arc, pool)
         best_loss = best_model.getLoss(params)

@@ -396,3 +396,34 @@ def test_device_tuning_loop_matches_host_loop():
     assert np.max(np.abs(np.array(loss_h) - np.array(loss_d))) <= 1e-9
     assert np.max(np.abs(th_h - th_d)) <= 1e-9
     assert loss_d[-1] < loss_d[0]
+
+
+def test_native_tree_with_resident_parameters_on_gpu():
+    """Native tree policy bound to the CUDA evaluator: parameters uploaded once (qas_set_params),
+    every rollout reward = one qas_eval_batch(QAS_F_PARAMS_RESIDENT); rewards equal the oracle's."""
+    from qas_b200.mcts import QMLStateBasicGates
+    from qas_b200.mcts.native import NativeMCTSController, PlaceholderPenalty
+    from qas_b200.qml_models.qml_models_legacy import FourQubitH2
+    pool = helpers.near_cx_pool(4)
+    p, c = 10, len(pool)
+    params = np.random.default_rng(5).standard_normal((p, c, 3))
+    ctl = NativeMCTSController(FourQubitH2, pool, p, state_class=QMLStateBasicGates, gate_limit_dict={"CNOT": 5},
+                               reward_penalty_function=PlaceholderPenalty(pool, p, 1.0), sampling_execute_rounds=10,
+                               exploit_execute_rounds=20, seed=3)
+    ctl.setParams(params)
+    arcs, rewards = ctl.warmupBatch(64)
+    terms = FourQubitH2.terms()
+    for k, r in list(zip(arcs, rewards))[:16]:
+        assert abs(r + sim.energy(4, k, pool.pool, params, terms, FourQubitH2.init_state)) <= E_TOL
+    ctl._reset()
+    k, leaf, r = ctl.sampleArcAndBackPropagate()
+    assert abs(r + sim.energy(4, k, pool.pool, params, terms, FourQubitH2.init_state)) <= E_TOL
+    # a plain batch call in between invalidates the resident copy; setParams restores it
+    FourQubitH2.evaluate_batch(np.array(arcs[:4], dtype=np.int32), params * 0.5, pool, want_grad=False)
+    with pytest.raises(RuntimeError):
+        ctl.sampleArcAndBackPropagate()
+    ctl.setParams(params)
+    k2, leaf2 = ctl.exploitArcWithSuperCircParams()
+    assert abs(leaf2.reward + sim.energy(4, k2, pool.pool, params, terms, FourQubitH2.init_state)) <= E_TOL
+    assert ctl.stats()["reward_evaluations"] < ctl.stats()["reward_requests"]
+    ctl.close()

@@ -33,6 +33,12 @@ def test_library_loads_and_exports_every_declared_symbol():
     for sym in declared_sv:
         assert hasattr(lib, sym), sym
     assert declared_sv == set(_lib.SV_EXPORTS)
+    from qas_b200.mcts.native import MCTS_EXPORTS
+    header_m = open(os.path.join(os.path.dirname(_lib.LIB_PATH), "..", "..", "include", "qas_b200_mcts.h")).read()
+    declared_m = set(re.findall(r"\b(qas_mcts_[a-z0-9_]+)\s*\(", header_m))
+    for sym in declared_m:
+        assert hasattr(lib, sym), sym
+    assert declared_m == set(MCTS_EXPORTS)
 
 
 def test_gate_id_table_matches_header():

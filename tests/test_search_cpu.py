@@ -157,3 +157,126 @@ def test_circuit_model_tuning_converges_on_the_oracle_model():
                                            lr=0.1, grad_noise_factor=0, verbose=0, early_stop_threshold=-2.0)
         assert len(losses) == 150 and losses[-1] < losses[0]
         assert losses[-1] < -1.11          # ground energy of the stand-in operator is -1.1373
+
+
+# ---------------------------------------------------------------------------------------------
+# native tree policy (libqas_b200: qas_b200_mcts.h) against the Python controller it restates
+def _walk_pools():
+    from qas_b200.qml_models.qml_gate_ops import QMLPool
+    yield helpers.near_cx_pool(4), {"CNOT": 3}
+    yield helpers.near_cx_pool(3, helpers.ring(3)), {}
+    yield QMLPool(3, ["T", "Tdg", "S", "Sdg", "PauliZ", "Hadamard", "RX", "PlaceHolder"], ["CZ", "CRZ"], True), {"CZ": 2, "T": 3}
+    yield QMLPool(2, ["T", "S", "Rot"], ["CNOT", "IsingXX"], False, [[0, 1], [1, 0]]), {}
+
+
+def test_native_legality_rules_match_python_state_class():
+    """qas_mcts_legal_actions == QMLStateBasicGates.getLegalActions on random walks (the rules of
+    qas/mcts/qml_mcts_state.py:58-148), including gate limits, T/S cancellation and the
+    unrestricted root of QMLStateBasicGatesNoRestrictions."""
+    from qas_b200.mcts import QMLStateBasicGatesNoRestrictions
+    from qas_b200.mcts.native import NativeMCTSController
+    rng = random.Random(4)
+    for pool, limits in _walk_pools():
+        for state_class in (QMLStateBasicGates, QMLStateBasicGatesNoRestrictions):
+            depth = 9
+            ctl = NativeMCTSController(OracleModel, pool, depth, state_class=state_class, gate_limit_dict=limits,
+                                       initial_legal_control_qubit_choice=set(), use_gpu=False, seed=1)
+            for walk in range(30):
+                state = state_class(op_pool=pool, maxDepth=depth, qubit_with_actions=set(), gate_limit_dict=limits)
+                k = []
+                while True:
+                    want = sorted(state.getLegalActions())
+                    assert ctl.legalActions(k) == want, (pool.pool, k)
+                    if not want:
+                        break
+                    a = rng.choice(want)
+                    k.append(a)
+                    state = state.takeAction(a)
+            ctl.close()
+
+
+def test_native_tree_warmup_sampling_and_cache():
+    from qas_b200.mcts.native import NativeMCTSController, PlaceholderPenalty
+    pool = helpers.near_cx_pool(2, [[0, 1], [1, 0]])
+    p = 3
+    params = np.random.default_rng(0).standard_normal((p, len(pool), 3))
+    before = OracleBatchModel.batch_calls
+    ctl = NativeMCTSController(OracleBatchModel, pool, p, state_class=QMLStateBasicGates, gate_limit_dict={"CNOT": 2},
+                               reward_penalty_function=PlaceholderPenalty(pool, 2, 1.0), sampling_execute_rounds=5,
+                               exploit_execute_rounds=5, max_visits_prune_threshold=3, min_num_children=2,
+                               use_gpu=False, seed=5)
+    ctl.setParams(params)
+    arcs, rewards = ctl.warmupBatch(40)
+    assert OracleBatchModel.batch_calls == before + 1           # ONE batched evaluation
+    st = ctl.stats()
+    assert st["root_visits"] == 40 and st["reward_requests"] == 40
+    assert st["reward_evaluations"] == len({tuple(k) for k in arcs}) < 40
+    for k, r in zip(arcs, rewards):
+        assert abs(r + sim.energy(2, k, pool.pool, params, TERMS)) < 1e-12      # reward = -E
+        state = QMLStateBasicGates(op_pool=pool, maxDepth=p, qubit_with_actions=set(), gate_limit_dict={"CNOT": 2})
+        for a in k:                                               # every arc is a legal walk
+            assert a in state.getLegalActions()
+            state = state.takeAction(a)
+    # rollouts: arcs are legal, rewards come from the cache where possible, exploitation returns the
+    # best arc's raw and penalised reward
+    k, leaf, r = ctl.sampleArcAndBackPropagate()
+    assert leaf.state.getCurrK() == k and abs(r + sim.energy(2, k, pool.pool, params, TERMS)) < 1e-12
+    k2, leaf2 = ctl.exploitArcWithSuperCircParams()
+    ph = sum(1 for a in k2 if "PlaceHolder" in pool[a])
+    assert abs(leaf2.penalised_reward - (leaf2.reward - (ph - 2 if ph >= 2 else 0))) < 1e-12
+    evals = ctl.stats()["reward_evaluations"]
+    ctl.setParams(params)                                         # new parameters -> cache dropped
+    ctl._reset()
+    ctl.sampleArcAndBackPropagate()
+    assert ctl.stats()["reward_evaluations"] > evals
+    ctl.close()
+
+
+def test_native_uct_and_prune_follow_the_reference_rules():
+    """alpha = 0, local_optimal: after enough rounds the root's best child by mean reward is the one
+    the greedy descent takes; pruning removes under-performing, often-visited children only."""
+    from qas_b200.mcts.native import NativeMCTSController
+    pool = helpers.near_cx_pool(2, [[0, 1], [1, 0]])
+    p = 3
+    params = np.random.default_rng(2).standard_normal((p, len(pool), 3))
+    ctl = NativeMCTSController(OracleBatchModel, pool, p, state_class=QMLStateBasicGates, alpha=0.5,
+                               prune_reward_ratio=0.5, max_visits_prune_threshold=2, min_num_children=1,
+                               sampling_execute_rounds=200, exploit_execute_rounds=50, use_gpu=False, seed=9)
+    ctl.setParams(params)
+    k, leaf, r = ctl.sampleArcAndBackPropagate()
+    # brute force: the best depth-3 legal arc under these parameters
+    best = None
+    def rec(state, kk):
+        nonlocal best
+        if len(kk) == p:
+            rr = -sim.energy(2, kk, pool.pool, params, TERMS)
+            if best is None or rr > best[0]:
+                best = (rr, list(kk))
+            return
+        for a in state.getLegalActions():
+            rec(state.takeAction(a), kk + [a])
+    rec(QMLStateBasicGates(op_pool=pool, maxDepth=p, qubit_with_actions=set(), gate_limit_dict={}), [])
+    k2, leaf2 = ctl.exploitArcWithSuperCircParams()
+    assert leaf2.reward >= best[0] - 0.05                # 200 + 150 rounds over a tree of < 60 leaves find (near) the optimum
+    assert ctl.stats()["root_visits"] >= 200
+    ctl.close()
+
+
+def test_search_with_native_tree_matches_python_tree_statistically():
+    """The driver with the native tree (forced) reaches the same quality as with the Python tree on
+    the 2-qubit stand-in and returns the same shapes; trajectories differ (separate generators)."""
+    from qas_b200.mcts import driver
+    from qas_b200.mcts.native import NativeMCTSController
+    py = _run(OracleBatchModel, 7, num_iterations=8)
+    old = driver.USE_NATIVE_TREE
+    driver.USE_NATIVE_TREE = True
+    try:
+        nat = _run(OracleBatchModel, 7, num_iterations=8)
+    finally:
+        driver.USE_NATIVE_TREE = old
+    assert isinstance(nat[4], NativeMCTSController)
+    assert nat[0].shape == py[0].shape and len(nat[1]) == 3 and len(nat[5]) == 8
+    assert nat[2].state.getCurrK() == nat[1]
+    assert nat[4].num_reward_evaluations < nat[4].num_reward_requests
+    assert nat[3] > py[3] - 0.2                            # best reward in the same ballpark
+    nat[4].close()
