@@ -55,6 +55,15 @@ struct SvGroup {
   int ls[3];           // coset-counter bit that trades places with counter bit 0 / 1 / 2 (see sv_swz)
 };
 
+// The gate list and the groups of the pass being executed live in constant memory: every thread of
+// the grid walks the same list, so descriptor fields and matrix entries come through the constant
+// cache and the uniform datapath instead of per-thread shared-memory loads (the per-thread
+// interpretation of the list was the kernel's largest cost).
+#define SV_CONST_GATES 448
+#define SV_CONST_GROUPS 448
+__constant__ SvTileGate c_sv_gates[SV_CONST_GATES];
+__constant__ SvGroup c_sv_groups[SV_CONST_GROUPS];
+
 struct SvBlockParams {
   double2 *state;
   const SvTileGate *gates;
@@ -117,7 +126,7 @@ __device__ __forceinline__ void sv_swap_slot(double2 (&a)[8], uint32_t cm) {
 
 // One CTA per tile.  Tile element j (kb bits) lives at slab index base | spread(j): the low c
 // bits are contiguous (coalesced 16*2^c-byte runs), the others are scattered by offs[].
-// dynamic shared memory: tile [2^kb] double2 | gates [ngates] SvTileGate
+// dynamic shared memory: tile [2^kb] double2
 template <int MINB>
 __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBlockParams P) {
   extern __shared__ __align__(16) double2 tile[];
@@ -125,16 +134,10 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
   __shared__ unsigned long long s_base;
   const int kb = P.kb, c = P.c;
   const uint32_t tsize = 1u << kb, nhi = 1u << (kb - c), lowmask = (1u << c) - 1u;
-  SvTileGate *sg = reinterpret_cast<SvTileGate *>(tile + tsize);
   for (uint32_t h = threadIdx.x; h < nhi; h += SV_THREADS) {
     unsigned long long o = 0;
     for (int q = c; q < kb; ++q) o |= (unsigned long long)((h >> (q - c)) & 1u) << P.bits[q];
     offs[h] = o;
-  }
-  {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(P.gates);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(sg);
-    for (uint32_t w = threadIdx.x; w < (uint32_t)(P.ngates * (sizeof(SvTileGate) / 4)); w += SV_THREADS) dst[w] = src[w];
   }
   const unsigned long long ntiles = 1ull << (P.n_local - kb);
   for (unsigned long long tid_ = blockIdx.x; tid_ < ntiles; tid_ += gridDim.x) {
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
     }
     __syncthreads();
     for (int gr = 0; gr < P.ngroups; ++gr) {
-      const SvGroup grp = P.groups[gr];
+      const SvGroup &grp = c_sv_groups[gr];
       const int b0 = grp.tb[0], b1 = grp.tb[1], b2 = grp.tb[2];
       const uint32_t s1 = 1u << b0, s2 = 1u << b1, s4 = 1u << b2;
       const uint32_t w1 = sv_swz(s1), w2 = sv_swz(s2), w4 = sv_swz(s4);     // the swizzle is xor-linear
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
 #pragma unroll
         for (int q = 0; q < 8; ++q) a[q] = tile[sm[q]];
         for (int gi = grp.first; gi < grp.first + grp.ngates; ++gi) {
-          const SvTileGate *gt = sg + gi;
+          const SvTileGate *gt = c_sv_gates + gi;
           const int kind = gt->kind;
           if (kind != SV_K_PDIAG) {
             const int cpo = gt->cpos_out, cbt = gt->cbit_tile;
@@ -509,8 +512,10 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
   if (info && sync) { SVCK(cudaEventCreate(&e0)); SVCK(cudaEventCreate(&e1)); SVCK(cudaEventRecord(e0, st)); }
   size_t max_gates = 0;
   for (size_t bi = 0; bi < blocks.size(); ++bi) max_gates = std::max<size_t>(max_gates, first[bi + 1] - first[bi]);
-  const size_t smem_max = ((size_t)16 << kb) + max_gates * sizeof(SvTileGate);
-  if (smem_max > 227 * 1024) { g_sv_error = "too many gates in one pass for the shared-memory gate table"; return QAS_ERR_UNSUPPORTED; }
+  size_t max_groups = 0;
+  for (size_t bi = 0; bi < blocks.size(); ++bi) max_groups = std::max<size_t>(max_groups, gfirst[bi + 1] - gfirst[bi]);
+  const size_t smem_max = (size_t)16 << kb;
+  if (max_gates > SV_CONST_GATES || max_groups > SV_CONST_GROUPS) { g_sv_error = "too many gates in one pass for the constant-memory gate list"; return QAS_ERR_UNSUPPORTED; }
   int minb = 3;
   if (const char *mb = getenv("QAS_B200_SV_MINB")) minb = atoi(mb) == 2 ? 2 : 3;   // tuning knob
   SVCK(cudaFuncSetAttribute(sv_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
@@ -526,7 +531,10 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
     P.n_local = n_local; P.kb = kb; P.c = c; P.ngates = first[bi + 1] - first[bi];
     P.ngroups = gfirst[bi + 1] - gfirst[bi];
     for (int q = 0; q < kb; ++q) P.bits[q] = (unsigned char)blocks[bi].bits[q];
-    const size_t smem = ((size_t)16 << kb) + (size_t)P.ngates * sizeof(SvTileGate);
+    const size_t smem = (size_t)16 << kb;
+    // stream-ordered: the copy waits for the previous pass's kernel, which still reads the old list
+    SVCK(cudaMemcpyToSymbolAsync(c_sv_gates, tg.data() + first[bi], (size_t)P.ngates * sizeof(SvTileGate), 0, cudaMemcpyHostToDevice, st));
+    SVCK(cudaMemcpyToSymbolAsync(c_sv_groups, groups.data() + gfirst[bi], (size_t)P.ngroups * sizeof(SvGroup), 0, cudaMemcpyHostToDevice, st));
     if (minb == 2) sv_block_kernel<2><<<grid, SV_THREADS, smem, st>>>(P);
     else sv_block_kernel<3><<<grid, SV_THREADS, smem, st>>>(P);
     SVCK(cudaGetLastError());

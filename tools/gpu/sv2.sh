@@ -1,7 +1,7 @@
 tag=${1:-sv}
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_largestate.py -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; tail -3 gpurun_out/${tag}_pytest.log
-for cfg in "28 4 12 5 3" "28 4 12 5 2" "28 4 12 6 2" "28 4 13 5 2" "30 2 12 5 2"; do set -- $cfg
+for cfg in "28 4 12 5 3" "28 4 12 5 2" "30 2 12 5 3"; do set -- $cfg
   f=gpurun_out/${tag}_$1q_L$2_t$3_c$4_m$5.json
   QAS_B200_SV_C=$4 QAS_B200_SV_MINB=$5 python tools/bench_largestate.py --qubits $1 --layers $2 --tile-bits $3 --reps 2 2>&1 | tail -1 > $f
   python - $f <<'PY'
