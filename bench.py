@@ -367,29 +367,40 @@ def run_b200(args):
 
 
 # ------------------------------------------------------------------------------- search epoch
+# per workload: (search batch, sampling rounds, exploit rounds, warm-up batch, lr, placeholder-penalty scale)
+# from the reference scripts: four_qubit_h2_only_near_cnot.py:88-97, search_LiH_near_cx.py:107-116,
+# search_H2O_near_cx.py:109-118, qaoa_search_demo.py:72-81
+SEARCH_CONFIGS = {"h2_4q": (100, 10, 100, 5000, 1.0, 1.0), "lih_10q": (25, 10, 20, 500, 0.1, 1.0),
+                  "h2o_8q": (50, 10, 20, 500, 0.1, 10.0), "qaoa_7q": (100, 100, 500, 100, 0.1, 1.0)}
+
+
 def run_search_epoch(args):
-    """--search-epoch: wall time of whole search() epochs of the reference's
-    four_qubit_h2_only_near_cnot.py configuration (p 40, warm-up batch 5000, search batch 100,
-    10 sampling rounds, 100 exploit rounds) with the B200 evaluator behind the drop-in model class,
-    next to the same driver on the CPU oracle in the reference's one-model-per-evaluation pattern."""
+    """--search-epoch: wall time of whole search() epochs in a reference script's
+    configuration (default workload lih_10q = search_LiH_near_cx.py) with the B200 evaluator behind
+    the drop-in model class -- native tree policy and the reference's Python tree policy -- next to
+    the same driver on the CPU oracle in the reference's one-model-per-evaluation pattern."""
     import contextlib
     import io
+    import random
     import re
     import __graft_entry__ as ge
     ge.build()
     from oracle.refpattern import REF_METHOD, RefPatternEvaluator
-    from qas_b200.mcts import QMLStateBasicGates, search
+    from qas_b200.mcts import QMLStateBasicGates, driver, search
+    from qas_b200.mcts.native import PlaceholderPenalty
     from qas_b200.models import ModelFromK
     from qas_b200.optim import AdamOptimizer
-    from qas_b200.qml_models.qml_gate_ops import QMLPool
-    from qas_b200.qml_models.qml_models_legacy import FourQubitH2
-    pool = QMLPool(4, ["Rot", "PlaceHolder"], ["CNOT"], False, _line(4))
-    p, l, c = 40, 3, len(pool)
-    method, sparse = REF_METHOD["FourQubitH2"]
-    ref_ev = RefPatternEvaluator(4, pool.pool, FourQubitH2.terms(), FourQubitH2.init_state, method, sparse)
+    name = args.workload
+    mname, n, p, coupling, cx_lim, scale = WORKLOADS[name][:6]
+    bs, rs, re_, warm_bs, lr, pen_scale = SEARCH_CONFIGS[name]
+    model, pool, _, _ = make_workload(name, 1, 0)
+    l, c = 3, len(pool)
+    method, sparse = REF_METHOD[mname]
+    ref_ev = RefPatternEvaluator(n, pool.pool, model.terms(), model.init_state, method, sparse)
+    sign = float(getattr(model, "reward_sign", -1.0))
 
-    class RefPatternFourQubitH2(ModelFromK):          # one circuit per call, like the reference's class
-        name = "FourQubitH2_cpu_reference_pattern"
+    class RefPatternModel(ModelFromK):          # one circuit per call, like the reference's class
+        name = mname + "_cpu_reference_pattern"
 
         def __init__(self, p_, c_, l_, structure_list, op_pool):
             self.k = [int(x) for x in structure_list]
@@ -398,7 +409,7 @@ def run_search_epoch(args):
             return ref_ev._energy(self.k, params)
 
         def getReward(self, params):
-            return -ref_ev._energy(self.k, params)
+            return sign * ref_ev._energy(self.k, params)
 
         def getGradient(self, params):
             return ref_ev.gradient(self.k, params)
@@ -406,40 +417,40 @@ def run_search_epoch(args):
         def toList(self, params):
             return []
 
-    from qas_b200.mcts import driver
-
-    def epochs(model, n_warm, n_search, warm_bs, native="auto"):
+    def epochs(mdl, n_warm, n_search, wbs, native):
         driver.USE_NATIVE_TREE = native
         np.random.seed(args.seed)
-        import random
         random.seed(args.seed)
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):
-            search(model=model, op_pool=pool, target_circuit_depth=p, init_qubit_with_controls=set(),
-                   init_params=np.random.randn(p, c, l), num_iterations=n_warm + n_search, num_warmup_iterations=n_warm,
-                   super_circ_train_optimizer=AdamOptimizer, super_circ_train_gradient_noise_factor=0.0,
-                   early_stop_threshold=1e9, early_stop_lookback_count=5, super_circ_train_lr=1.0,
-                   penalty_function=None, gate_limit_dict={"CNOT": p}, warmup_arc_batchsize=warm_bs,
-                   search_arc_batchsize=100, alpha_max=2, alpha_decay_rate=0.99, prune_constant_max=0.99,
-                   prune_constant_min=0.80, max_visits_prune_threshold=20, min_num_children=c // 2 + 1,
-                   sampling_execute_rounds=10, exploit_execute_rounds=100, verbose=1,
-                   state_class=QMLStateBasicGates, search_reset=True)
+            search(model=mdl, op_pool=pool, target_circuit_depth=p, init_qubit_with_controls=set(),
+                   init_params=np.random.randn(p, c, l) * scale, num_iterations=n_warm + n_search,
+                   num_warmup_iterations=n_warm, super_circ_train_optimizer=AdamOptimizer,
+                   super_circ_train_gradient_noise_factor=0.0, early_stop_threshold=1e9, early_stop_lookback_count=5,
+                   super_circ_train_lr=lr, penalty_function=PlaceholderPenalty(pool, p, pen_scale),
+                   gate_limit_dict={"CNOT": cx_lim}, warmup_arc_batchsize=wbs, search_arc_batchsize=bs, alpha_max=2,
+                   alpha_decay_rate=0.99, prune_constant_max=0.99, prune_constant_min=0.80,
+                   max_visits_prune_threshold=20, min_num_children=c // 2 + 1, sampling_execute_rounds=rs,
+                   exploit_execute_rounds=re_, verbose=1, state_class=QMLStateBasicGates, search_reset=True)
         secs = [float(x) for x in re.findall(r"\| ([0-9.]+) s", buf.getvalue())]
         return secs[:n_warm], secs[n_warm:]
 
-    epochs(FourQubitH2, 1, 1, 5000)                          # first-call costs (context, tables)
-    gw, gs = epochs(FourQubitH2, 2, 3, 5000, native=True)    # native tree policy (C++), rewards resident on the GPU
-    pw, ps = epochs(FourQubitH2, 2, 3, 5000, native=False)   # the reference's tree policy in Python, GPU rewards
-    cw, cs = epochs(RefPatternFourQubitH2, 1, 1, 500, native=False)   # CPU: a tenth of the warm-up batch, scaled below
+    epochs(model, 1, 1, warm_bs, True)                       # first-call costs (context, tables)
+    gw, gs = epochs(model, 2, 3, warm_bs, True)              # native tree policy (C++), rewards resident on the GPU
+    pw, ps = epochs(model, 2, 3, warm_bs, False)             # the reference's tree policy in Python, GPU rewards
+    cpu_wbs = max(10, warm_bs // 10)
+    cw, cs = epochs(RefPatternModel, 1, 1, cpu_wbs, False)   # CPU: a tenth of the warm-up batch, scaled below
     driver.USE_NATIVE_TREE = "auto"
-    line = {"metric": "search() epoch wall time, four_qubit_h2_only_near_cnot configuration", "unit": "s",
+    line = {"metric": "search() epoch wall time", "unit": "s",
+            "config": {"workload": name, "model": mname, "depth_p": p, "search_arc_batchsize": bs, "sampling_rounds": rs,
+                       "exploit_rounds": re_, "warmup_arc_batchsize": warm_bs, "source": "search-scripts-legacy/" + WORKLOADS[name][7]},
             "b200": {"warmup_epoch_s": min(gw), "search_epoch_s": statistics.median(gs), "tree": "native (libqas_b200 qas_mcts_*)"},
             "b200_python_tree": {"warmup_epoch_s": min(pw), "search_epoch_s": statistics.median(ps)},
-            "cpu_reference_pattern": {"warmup_epoch_s_scaled_to_5000": cw[0] * 10.0, "search_epoch_s": cs[0],
-                                      "cores": 1, "note": "oracle in the reference call pattern; warm-up epoch run "
-                                                          "with 500 arcs and scaled x10"},
-            "note": "with the Python tree the epochs are bound by the tree policy (about 1e5 expansions per search epoch), "
-                    "not by the evaluator; the native tree removes that"}
+            "cpu_reference_pattern": {"warmup_epoch_s_scaled": cw[0] * warm_bs / cpu_wbs, "search_epoch_s": cs[0], "cores": 1,
+                                      "note": "oracle in the reference call pattern (%s gradient); warm-up epoch run with %d "
+                                              "arcs and scaled to %d" % (method, cpu_wbs, warm_bs)},
+            "note": "epoch times as printed by the driver (0.1 ms resolution); with the Python tree the epochs are bound by the "
+                    "tree policy, not by the evaluator; the native tree removes that"}
     print(json.dumps(line), flush=True)
 
 

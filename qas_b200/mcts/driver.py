@@ -190,7 +190,7 @@ def search(*args, **kwargs):
         best_loss = best_model.getLoss(params)
         best_reward = best_model.getReward(params)
         penalised = _penalised(cfg, best_reward, best_node)
-        log("  pruned %d | best reward %r (penalised %r) | best loss %r | %.2f s" % (
+        log("  pruned %d | best reward %r (penalised %r) | best loss %r | %.4f s" % (
             controller.prune_counter, best_reward, penalised, best_loss, time.time() - t0))
         log("  best k: %s" % (best_arc,))
         if cfg.verbose > 1:
