@@ -49,6 +49,7 @@ struct qas_ctx {
   double *d_dense = nullptr; size_t cap_dense = 0;
   double2 *d_gstate = nullptr; size_t cap_gstate = 0;
   uint32_t *d_tape = nullptr; size_t cap_tape = 0;
+  uint32_t *h_tape = nullptr; size_t cap_htape = 0;   // pinned staging for host-compiled tapes (tiny batches)
   qas_stats stats{};
   mutable std::string err;
 };
@@ -401,6 +402,7 @@ extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   cudaFree(ctx->d_U); cudaFree(ctx->d_dU); cudaFree(ctx->d_k); cudaFree(ctx->d_params);
   cudaFree(ctx->d_energy); cudaFree(ctx->d_grad); cudaFree(ctx->d_partial); cudaFree(ctx->d_dense);
   cudaFree(ctx->d_gstate); cudaFree(ctx->d_mout); cudaFree(ctx->d_tape); cudaFree(ctx->d_phase);
+  if (ctx->h_tape) cudaFreeHost(ctx->h_tape);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ek0) cudaEventDestroy(ctx->ek0);
@@ -633,13 +635,36 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   stamp(0);
   if (want_grad) CK(cudaMemsetAsync(dgrad, 0, ng * 8, st));
   stamp(1);
-  {
+  // Tiny host-pointer batches (the one-reward-at-a-time rollouts of the tree search): the tape
+  // compiler and pass planner are host-callable, and one CPU core runs them in a few microseconds,
+  // whereas a single GPU thread needs tens -- compile here and upload the records.
+  const int swz_plan = ctx->n <= (want_grad ? 12 : 13) ? 1 : 0;
+  if (!dev && B <= 16) {
+    const size_t words = rec_words * (size_t)B;
+    if (ctx->cap_htape < words) {
+      if (ctx->h_tape) cudaFreeHost(ctx->h_tape);
+      ctx->h_tape = nullptr; ctx->cap_htape = 0;
+      CK(cudaHostAlloc((void **)&ctx->h_tape, std::max<size_t>(words, 4096) * 4, cudaHostAllocDefault));
+      ctx->cap_htape = std::max<size_t>(words, 4096);
+    }
+    uint32_t col[32], row[32];
+    for (int b = 0; b < B; ++b) {
+      uint32_t *rec = ctx->h_tape + (size_t)b * rec_words;
+      QasTapeSink sink{rec + QAS_REC_HDR, P.ops_cap, 0, 0};
+      const int stc = qas_compile_circuit(k + (size_t)b * p, p, ctx->pool.data(), c, ctx->n, col, row, sink);
+      const int nops = stc ? 0 : sink.n;
+      const uint32_t init_index = (ctx->init_kind == QAS_INIT_BASIS && !stc) ? qas_frame_map_basis(col, ctx->n, ctx->init_basis) : 0u;
+      rec[0] = (uint32_t)nops; rec[1] = (uint32_t)stc; rec[2] = init_index;
+      rec[3] = (uint32_t)qas_plan_groups(rec + QAS_REC_HDR, nops, ctx->GMAX, ctx->n, ctx->init_kind, init_index,
+                                         rec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS, swz_plan);
+    }
+    CK(cudaMemcpyAsync(ctx->d_tape, ctx->h_tape, words * 4, cudaMemcpyHostToDevice, st));
+  } else {
     const int cthr = 64;
     // ops in shared memory only while that keeps >= 8 CTAs per SM resident (short tapes)
     const bool ops_smem = qas_compile_smem_words(ctx->n, P.ops_cap, p, true) * 4 * cthr <= 24 * 1024;
     const size_t csm = qas_compile_smem_words(ctx->n, P.ops_cap, p, ops_smem) * 4 * cthr;
     if (csm > 200 * 1024) return fail(ctx, QAS_ERR_UNSUPPORTED, "structure lists too long for the tape-compile kernel");
-    const int swz_plan = ctx->n <= (want_grad ? 12 : 13) ? 1 : 0;
     if (ops_smem) {
       CK(cudaFuncSetAttribute(compile_tapes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
       compile_tapes_kernel<true><<<(B + cthr - 1) / cthr, cthr, csm, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap, ctx->init_kind,
