@@ -53,15 +53,24 @@ WORKLOADS = {
     "h2_4q": ("FourQubitH2", 4, 40, _line(4), 40, 1.0, (100, 5000), "four_qubit_h2_only_near_cnot.py:43-97"),
     "qaoa_7q": ("QAOAVQCDemo", 7, 15, _ring(7), 7, (2.0 / 2 ** 7) ** 0.5, (100, 100), "qaoa_search_demo.py:41-81"),
     "h2_2q": ("TwoQubitH2", 2, 3, [[0, 1], [1, 0]], 2, 1.0, (50, 10), "two_qubit_h2.py:40-94"),
+    # new-API models (qas/qml_models/qchem_model.py, kagome_heisenberg_model.py): larger registers; the
+    # 14- and 16-qubit ones run the global-memory instantiation of the evaluation kernel (use --batch 2048)
+    "lih_12q": ("LiHSTO3G", 12, 20, _line(12), 10, 1.0, (25, 500), "../h2_sto-3g.py:43-53 (LiHSTO3G, qchem_model.py:36-47)"),
+    "h2o_14q": ("H2OSTO3G", 14, 20, _line(14), 10, 1.0, (25, 500), "../h2_sto-3g.py:43-53 (H2OSTO3G, qchem_model.py:49-60)"),
+    "kagome_16q": ("KagomeHeisenberg", 16, 500, [[0, 1], [1, 4], [1, 2], [1, 0], [2, 1], [2, 3], [3, 2], [3, 5], [4, 1], [4, 7],
+                                                  [5, 8], [5, 3], [6, 7], [7, 4], [7, 10], [7, 6], [8, 5], [8, 9], [8, 11], [9, 8],
+                                                  [10, 12], [10, 7], [11, 8], [11, 14], [12, 15], [12, 10], [12, 13], [13, 14],
+                                                  [13, 12], [14, 13], [14, 11], [15, 12]], 500, 1.0, (50, 100), "../kagome.py:43-53"),
 }
 
 
 def make_workload(name, B, seed):
+    from qas_b200.qml_models import kagome_heisenberg_model, qchem_model
     from qas_b200.qml_models import qml_models_legacy as L
     from qas_b200.qml_models.qml_gate_ops import QMLPool
     from qas_b200.sampling import sample_structure_lists
     mname, n, p, coupling, cx_lim, scale, script_b, src = WORKLOADS[name]
-    model = getattr(L, mname)
+    model = next(getattr(m, mname) for m in (L, qchem_model, kagome_heisenberg_model) if hasattr(m, mname))
     pool = QMLPool(n, ["Rot", "PlaceHolder"], ["CNOT"], False, coupling)
     c = len(pool)
     params = np.random.default_rng(seed).standard_normal((p, c, 3)) * scale

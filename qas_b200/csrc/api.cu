@@ -670,6 +670,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
       compile_tapes_kernel<true><<<(B + cthr - 1) / cthr, cthr, csm, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap, ctx->init_kind,
                                                                          ctx->init_basis, ctx->GMAX, swz_plan, ctx->d_tape);
     } else {
+      CK(cudaFuncSetAttribute(compile_tapes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
       compile_tapes_kernel<false><<<(B + cthr - 1) / cthr, cthr, csm, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap, ctx->init_kind,
                                                                           ctx->init_basis, ctx->GMAX, swz_plan, ctx->d_tape);
     }
