@@ -37,6 +37,8 @@ struct qas_ctx {
   cudaEvent_t sev[8] = {nullptr};
   int RBH = 0, PD = 1;             // H-apply blocking / prefetch depth (QAS_B200_HCFG=rb,pd overrides)
   int gcfg_g = 0, gcfg_m = 0;      // QAS_B200_GCFG=gmax,minb tuning override (n = 8, 10 default teams)
+  bool small_kernel = true;        // n <= 5: thread-per-circuit kernel (QAS_B200_SMALL=0 disables)
+  bool small_now = false;          // ... and chosen for the call in progress
   GateTab *d_U = nullptr;
   GateDTab *d_dU = nullptr;
   int tab_p = 0;
@@ -271,6 +273,8 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   cx->GMAX = qas_gmax(n_qubits <= 13 ? n_qubits : 20, cx->T);
   cx->RB = qas_hrb(n_qubits <= 13 ? n_qubits : 20, cx->T);
   cx->PD = qas_hpd(n_qubits <= 13 ? n_qubits : 20, cx->T);
+  if (const char *sk = getenv("QAS_B200_SMALL")) cx->small_kernel = atoi(sk) != 0;
+  if (n_qubits <= 5 && cx->small_kernel) { cx->GMAX = 1; cx->RB = n_qubits >= 4 ? 1 : 0; cx->PD = cx->RB >= 1 ? 2 : 1; }
   if (const char *gc = getenv("QAS_B200_GCFG")) {   // tuning: "gmax,min CTAs per SM" among the compiled variants
     int gv = 0, mv = 0;
     if (sscanf(gc, "%d,%d", &gv, &mv) == 2 && cx->team_shift == 0 &&
@@ -490,8 +494,41 @@ static cudaError_t launch_gmem(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
 }
 
 // (N, T) instantiations: the default team size of each qubit count plus tuning alternatives
+// n <= 5: thread-per-circuit kernel (eval_small_kernel); QAS_B200_SMALL=0 keeps the team kernel
+static bool use_small_kernel(const qas_ctx *ctx) { return ctx->n <= 5 && ctx->small_kernel; }
+// ... and the packed tape must fit next to the statevectors (very deep circuits fall back to the team kernel)
+static bool small_fits(const qas_ctx *ctx, int ops_cap) {
+  return eval_small_smem_bytes(ctx->n, ctx->n <= 4 ? 128 : 64, true, ops_cap, ctx->c) <= 200 * 1024;
+}
+
+template <int N, bool GRAD>
+static cudaError_t launch_small(qas_ctx *ctx, const EvalParams &P, cudaStream_t st) {
+  constexpr int BLK = N <= 4 ? 128 : 64;
+  const size_t smem = eval_small_smem_bytes(N, BLK, GRAD, P.ops_cap, P.c);
+  auto kern = eval_small_kernel<N, GRAD, BLK>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLK, smem);
+  ctx->stats.teams_per_cta = BLK;
+  ctx->stats.threads_per_team = 1;
+  ctx->stats.ctas_per_sm = occ;
+  ctx->stats.smem_bytes_per_cta = (int)smem;
+  ctx->stats.path = 2;
+  kern<<<(P.B + BLK - 1) / BLK, BLK, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
 template <bool GRAD>
 static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
+  if (ctx->small_now) {
+    switch (P.n) {
+      case 2: return launch_small<2, GRAD>(ctx, P, st);
+      case 3: return launch_small<3, GRAD>(ctx, P, st);
+      case 4: return launch_small<4, GRAD>(ctx, P, st);
+      default: return launch_small<5, GRAD>(ctx, P, st);
+    }
+  }
   const int nmax_smem = GRAD ? 12 : 13;
   const int T = ctx->T;
   if (P.n <= nmax_smem) {
@@ -599,12 +636,14 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     dgrad = ctx->d_grad;
   }
 
+  const bool small = use_small_kernel(ctx) && small_fits(ctx, std::max(1, p * ctx->max_expansion));
+  ctx->small_now = small;
   EvalParams P{};
-  P.k = dk; P.pool = ctx->d_pool; P.U = ctx->d_U;
+  P.k = dk; P.pool = ctx->d_pool; P.U = ctx->d_U; P.dU = ctx->d_dU; P.grad = dgrad;
   P.vtab = ctx->d_vtab; P.rb0 = ctx->rb[0]; P.rb1 = ctx->rb[1]; P.rb2 = ctx->rb[2];
   P.C_real = ctx->C_real; P.C_imag = ctx->C_imag;
   {   // class descriptors and W combinations as byte offsets, swizzled for the shared-memory path
-    const bool smem_path = ctx->n <= (want_grad ? 12 : 13);
+    const bool smem_path = ctx->n <= (want_grad ? 12 : 13) && !small;
     P.cdesc = smem_path ? ctx->d_sdesc : ctx->d_cdesc_plain;
     for (int j = 0; j < 8; ++j) {
       const uint32_t w = ctx->wc.w[j];
@@ -638,8 +677,10 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   // Tiny host-pointer batches (the one-reward-at-a-time rollouts of the tree search): the tape
   // compiler and pass planner are host-callable, and one CPU core runs them in a few microseconds,
   // whereas a single GPU thread needs tens -- compile here and upload the records.
-  const int swz_plan = ctx->n <= (want_grad ? 12 : 13) ? 1 : 0;
-  if (!dev && B <= 16) {
+  const int swz_plan = (ctx->n <= (want_grad ? 12 : 13) && !small) ? 1 : 0;
+  if (small) {
+    // the thread-per-circuit kernel compiles its own tapes
+  } else if (!dev && B <= 16) {
     const size_t words = rec_words * (size_t)B;
     if (ctx->cap_htape < words) {
       if (ctx->h_tape) cudaFreeHost(ctx->h_tape);
@@ -688,7 +729,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   stamp(4);
   ctx->ek_pending = true;
   ctx->stats.launches += 3;
-  if (want_grad) {
+  if (want_grad && !small) {
     const size_t nthr = (size_t)B * P.ops_cap;
     grad_finalize_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ctx->d_tape, ctx->d_mout, ctx->d_dU, B, p, l,
                                                                         P.ops_cap, ctx->n, dgrad);

@@ -36,6 +36,8 @@ struct EvalParams {
   double *energy;              // [B]
   double2 *gstate;             // global-memory statevector scratch (path 1)
   double *mout;                // [B][ops_cap][8] cross matrices M of the parametrised ops (GRAD)
+  const GateDTab *dU;          // [NCONST + p*c]          (thread-per-circuit kernel only)
+  double *grad;                // [B][p][l] compact gradients, zero-filled (thread-per-circuit kernel only)
   unsigned long long *phase_clk;   // diagnostic: summed per-team clock64 deltas [prologue, forward, H, adjoint] or null
   const uint32_t *tape;        // [B][4 + ops_cap*5] compiled tape records (compile_tapes_kernel)
   uint64_t init_basis;
@@ -823,6 +825,188 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
     }
     if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 3, (unsigned long long)(c_ - clk_prev)); }
     team_sync<T>(team, tmask);   // state buffers are reused by the next circuit of this team
+  }
+}
+
+// ------------------------------------------------------------------------------ small registers
+// n <= 5: ONE THREAD per circuit, and the whole evaluation in one kernel -- tape compile, forward
+// sweep, H application, adjoint sweep and the parameter derivatives.  The statevectors and the
+// packed tape are thread-private columns of shared memory (element i of thread t at [i * BLK + t]:
+// every lane of a warp touches the same row, so all accesses are conflict-free and nothing is ever
+// shared between threads -- no barriers, no shuffles, no tape round trip through L2/HBM).  Sign-table
+// values and class descriptors are the same for every lane (broadcast loads); the 2x2 cross matrix
+// of a gate is a thread-local sum, contracted with dU/dtheta on the spot.
+// The sub-warp-team path this replaces paid a 1.8 KB tape record per circuit (three more kernels:
+// compile, memset, finalize) and per-pass __syncwarp latency.
+struct QasPackedSink {            // op -> {m | r<<5 | rc<<10 | kind<<15 | npar<<16 | depth<<18, tab}
+  uint2 *ops;                     // thread-private column, stride BLK
+  int stride, cap, n, overflow;
+  __device__ __forceinline__ void emit(uint32_t m, uint32_t r, uint32_t rc, uint32_t tab, uint32_t meta) {
+    if (n >= cap) { overflow = 1; return; }
+    ops[(size_t)n * stride] = make_uint2(m | (r << 5) | (rc << 10) | (qas_meta_kind(meta) << 15) |
+                                         ((uint32_t)qas_meta_npar(meta) << 16) | ((uint32_t)qas_meta_depth(meta) << 18), tab);
+    n++;
+  }
+};
+// shared memory: psi | lam (GRAD) | packed ops [ops_cap][BLK] | frame [BLK][11] u32 | pool [c]
+__host__ __device__ inline size_t eval_small_smem_bytes(int n, int blk, bool grad, int ops_cap, int c) {
+  return ((size_t)16 << n) * blk * (grad ? 2 : 1) + (size_t)ops_cap * 8 * blk + (size_t)blk * 11 * 4 +
+         (((size_t)c * sizeof(qas_pool_entry)) + 15) / 16 * 16;
+}
+
+template <int N, bool GRAD, int BLK>
+__global__ void __launch_bounds__(BLK) eval_small_kernel(const EvalParams P) {
+  constexpr uint32_t DIM = 1u << N, HALF = DIM >> 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *psi = reinterpret_cast<double2 *>(smem_raw) + threadIdx.x;
+  double2 *lam = psi + (size_t)DIM * BLK;           // only present when GRAD
+  unsigned char *sp = smem_raw + ((size_t)16 << N) * BLK * (GRAD ? 2 : 1);
+  uint2 *ops = reinterpret_cast<uint2 *>(sp) + threadIdx.x;
+  sp += (size_t)P.ops_cap * 8 * BLK;
+  uint32_t *frame = reinterpret_cast<uint32_t *>(sp) + (size_t)threadIdx.x * 11;   // odd stride: conflict-free
+  sp += (size_t)BLK * 11 * 4;
+  qas_pool_entry *spool = reinterpret_cast<qas_pool_entry *>(sp);
+  for (int x = threadIdx.x; x < P.c; x += BLK) spool[x] = P.pool[x];
+  __syncthreads();
+  const int b = blockIdx.x * BLK + threadIdx.x;
+  if (b >= P.B) return;
+  // ---- tape compile (CNOT-folded frame, tape.h), ops packed into this thread's column
+  int nops, status;
+  uint32_t init_index;
+  {
+    uint32_t *col = frame, *row = frame + 5;
+    QasPackedSink sink{ops, BLK, P.ops_cap, 0, 0};
+    status = qas_compile_circuit(P.k + (size_t)b * P.p, P.p, spool, P.c, N, col, row, sink);
+    nops = status ? 0 : sink.n;
+    init_index = (P.init_kind == QAS_INIT_BASIS && !status) ? qas_frame_map_basis(col, N, P.init_basis) : 0u;
+  }
+  {
+    const double amp0 = (P.init_kind == QAS_INIT_PLUS) ? exp2(-0.5 * (double)N) : 0.0;
+#pragma unroll
+    for (uint32_t i = 0; i < DIM; ++i) psi[(size_t)i * BLK] = make_double2(amp0, 0.0);
+    if (P.init_kind != QAS_INIT_PLUS) psi[(size_t)init_index * BLK] = make_double2(1.0, 0.0);
+  }
+  // ---- forward sweep (ops are stored last-gate-first)
+  for (int j = nops - 1; j >= 0; --j) {
+    const uint2 o = ops[(size_t)j * BLK];
+    const uint32_t m = o.x & 31u, r = (o.x >> 5) & 31u, rc = (o.x >> 10) & 31u;
+    const GateTab &gt = P.U[o.y];
+    if (((o.x >> 15) & 1u) == QAS_K_U1) {
+      double2 u[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) u[e] = gt.u[e];
+      const int pb = 31 - __clz(r);
+#pragma unroll
+      for (uint32_t t = 0; t < HALF; ++t) {
+        uint32_t p0 = insert_zero(t, pb);
+        p0 |= (uint32_t)(__popc(p0 & r) & 1) << pb;
+        if (rc && !(__popc(p0 & rc) & 1)) continue;
+        const uint32_t p1 = p0 ^ m;
+        double2 a0 = psi[(size_t)p0 * BLK], a1 = psi[(size_t)p1 * BLK];
+        apply_u(a0, a1, u);
+        psi[(size_t)p0 * BLK] = a0;
+        psi[(size_t)p1 * BLK] = a1;
+      }
+    } else {
+      const double2 d0 = gt.u[0], d1 = gt.u[3];
+#pragma unroll
+      for (uint32_t i = 0; i < DIM; ++i)
+        psi[(size_t)i * BLK] = cmul((__popc(i & r) & 1) ? d1 : d0, psi[(size_t)i * BLK]);
+    }
+  }
+  // ---- lambda = H psi (class by class, same tables as the team kernel), E = Re <psi|lambda>
+  double e_acc = 0.0;
+  {
+    constexpr int RB = N >= 4 ? 1 : 0;              // = the host's choice for these qubit counts
+    constexpr int NB = 1 << RB;
+    constexpr uint32_t nrest = DIM >> RB;
+    const int C = P.C_real + P.C_imag;
+    for (uint32_t u = 0; u < nrest; ++u) {
+      const uint32_t base_i = qas_deposit_rest(u, RB, P.rb0, P.rb1, P.rb2);
+      double2 acc[NB];
+#pragma unroll
+      for (int q = 0; q < NB; ++q) acc[q] = make_double2(0.0, 0.0);
+      const double *vp = P.vtab + (size_t)u * (NB >= 2 ? 2 : 1);
+      for (int cls = 0; cls < C; ++cls) {
+        const uint32_t rho = P.cdesc[cls] >> 4;
+        const bool imag = cls >= P.C_real;
+        double2 a[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) a[q] = psi[(size_t)(base_i ^ rho ^ (P.wc16.w[q] >> 4)) * BLK];
+#pragma unroll
+        for (int jw = 0; jw < NB; ++jw) {
+          double v[NB];
+          load_vrow<NB>(v, vp + ((size_t)(cls * NB + jw) << N), nrest);
+          hacc_row<NB>(acc, a, v, jw, imag);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const uint32_t i = base_i ^ (P.wc16.w[q] >> 4);
+        const double2 ai = psi[(size_t)i * BLK];
+        e_acc = fma(ai.x, acc[q].x, fma(ai.y, acc[q].y, e_acc));
+        if constexpr (GRAD) lam[(size_t)i * BLK] = acc[q];
+      }
+    }
+  }
+  P.energy[b] = status ? __longlong_as_double(0x7ff8000000000000ll) : e_acc;
+  // ---- adjoint sweep; derivatives written straight into grad[b][depth][j] (zero-filled beforehand)
+  if constexpr (GRAD) {
+    for (int j = 0; j < nops; ++j) {
+      const uint2 o = ops[(size_t)j * BLK];
+      const uint32_t m = o.x & 31u, r = (o.x >> 5) & 31u, rc = (o.x >> 10) & 31u;
+      const int npar = (int)((o.x >> 16) & 3u);
+      const GateTab &gt = P.U[o.y];
+      double M[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) M[e] = 0.0;
+      if (((o.x >> 15) & 1u) == QAS_K_U1) {
+        double2 u[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) u[e] = gt.u[e];
+        const int pb = 31 - __clz(r);
+#pragma unroll
+        for (uint32_t t = 0; t < HALF; ++t) {
+          uint32_t p0 = insert_zero(t, pb);
+          p0 |= (uint32_t)(__popc(p0 & r) & 1) << pb;
+          if (rc && !(__popc(p0 & rc) & 1)) continue;
+          const uint32_t p1 = p0 ^ m;
+          double2 a0 = psi[(size_t)p0 * BLK], a1 = psi[(size_t)p1 * BLK];
+          double2 l0 = lam[(size_t)p0 * BLK], l1 = lam[(size_t)p1 * BLK];
+          apply_udag(a0, a1, u);
+          if (npar) macc(M, l0, l1, a0, a1);
+          apply_udag(l0, l1, u);
+          psi[(size_t)p0 * BLK] = a0; psi[(size_t)p1 * BLK] = a1;
+          lam[(size_t)p0 * BLK] = l0; lam[(size_t)p1 * BLK] = l1;
+        }
+      } else {
+        const double2 d0 = gt.u[0], d1 = gt.u[3];
+#pragma unroll
+        for (uint32_t i = 0; i < DIM; ++i) {
+          const bool hi = __popc(i & r) & 1;
+          const double2 d = hi ? d1 : d0;
+          const double2 q = cmul_conj(d, psi[(size_t)i * BLK]);
+          const double2 lv = lam[(size_t)i * BLK];
+          psi[(size_t)i * BLK] = q;
+          const double re = fma(lv.x, q.x, lv.y * q.y), im = fma(lv.x, q.y, -lv.y * q.x);
+          if (hi) { M[6] += re; M[7] += im; } else { M[0] += re; M[1] += im; }
+          lam[(size_t)i * BLK] = cmul_conj(d, lv);
+        }
+      }
+      if (npar) {
+        const GateDTab &dt = P.dU[o.y];
+        double *g = P.grad + ((size_t)b * P.p + (o.x >> 18)) * P.l;
+        for (int jj = 0; jj < npar; ++jj) {
+          double part = 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double2 dq = dt.d[jj][q];
+            part += dq.x * M[2 * q] - dq.y * M[2 * q + 1];
+          }
+          g[jj] = 2.0 * part;
+        }
+      }
+    }
   }
 }
 

@@ -72,26 +72,32 @@ QAS_HD int qas_gate_expansion(int g) {
   }
 }
 
+// Where compiled ops go.  Any type with fields n / overflow and emit(m, r, rc, tab, meta) works:
+// QasTapeSink writes 5-word records; the thread-per-circuit kernel packs ops into shared memory.
 struct QasTapeSink {
   uint32_t *ops;   // [cap][QAS_OP_WORDS]
   int cap;
   int n;           // emitted so far
   int overflow;
+  QAS_HD void emit(uint32_t m, uint32_t r, uint32_t rc, uint32_t tab, uint32_t meta) {
+    if (n >= cap) { overflow = 1; return; }
+    uint32_t *o = ops + (size_t)n * QAS_OP_WORDS;
+    o[0] = m; o[1] = r; o[2] = rc; o[3] = tab; o[4] = meta;
+    n++;
+  }
 };
 
-QAS_HD void qas_emit(QasTapeSink &s, uint32_t m, uint32_t r, uint32_t rc, uint32_t tab,
-                     uint32_t meta) {
-  if (s.n >= s.cap) { s.overflow = 1; return; }
-  uint32_t *o = s.ops + (size_t)s.n * QAS_OP_WORDS;
-  o[0] = m; o[1] = r; o[2] = rc; o[3] = tab; o[4] = meta;
-  s.n++;
+template <class Sink>
+QAS_HD void qas_emit(Sink &s, uint32_t m, uint32_t r, uint32_t rc, uint32_t tab, uint32_t meta) {
+  s.emit(m, r, rc, tab, meta);
 }
 
 // Compile one circuit.  col/row: scratch arrays of n words each (frame S and S^-1).
 // Returns 0, or 1 if some key is out of range (the reference asserts min(k)>=0, max(k)<c at
 // utils.py:12-15), or 2 on tape overflow.
+template <class Sink>
 QAS_HD int qas_compile_circuit(const int32_t *k, int p, const qas_pool_entry *pool, int c, int n,
-                               uint32_t *col, uint32_t *row, QasTapeSink &s) {
+                               uint32_t *col, uint32_t *row, Sink &s) {
   for (int q = 0; q < n; ++q) col[q] = row[q] = 1u << (n - 1 - q);
   s.n = 0;
   s.overflow = 0;
