@@ -39,6 +39,7 @@ struct qas_ctx {
   int gcfg_g = 0, gcfg_m = 0;      // QAS_B200_GCFG=gmax,minb tuning override (n = 8, 10 default teams)
   bool small_kernel = true;        // n <= 5: thread-per-circuit kernel (QAS_B200_SMALL=0 disables)
   bool small_now = false;          // ... and chosen for the call in progress
+  int *d_counter = nullptr;        // work-queue head of the team kernels
   GateTab *d_U = nullptr;
   GateDTab *d_dU = nullptr;
   int tab_p = 0;
@@ -367,6 +368,7 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   guard(cudaEventCreate(&cx->ek0), "cudaEventCreate");
   guard(cudaEventCreate(&cx->ek1), "cudaEventCreate");
   guard(cudaMalloc(&cx->d_pool, sizeof(qas_pool_entry) * c), "cudaMalloc pool");
+  guard(cudaMalloc(&cx->d_counter, sizeof(int)), "cudaMalloc work counter");
   if (want_phase) {
     guard(cudaMalloc(&cx->d_phase, 8 * sizeof(unsigned long long)), "cudaMalloc phase clocks");
     guard(cudaMemset(cx->d_phase, 0, 8 * sizeof(unsigned long long)), "cudaMemset phase clocks");
@@ -402,7 +404,7 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
 extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   if (!ctx) return QAS_OK;
   cudaSetDevice(ctx->device);
-  cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_cdesc_plain);
+  cudaFree(ctx->d_counter); cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_cdesc_plain);
   cudaFree(ctx->d_U); cudaFree(ctx->d_dU); cudaFree(ctx->d_k); cudaFree(ctx->d_params);
   cudaFree(ctx->d_energy); cudaFree(ctx->d_grad); cudaFree(ctx->d_partial); cudaFree(ctx->d_dense);
   cudaFree(ctx->d_gstate); cudaFree(ctx->d_mout); cudaFree(ctx->d_tape); cudaFree(ctx->d_phase);
@@ -459,7 +461,9 @@ static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t s
   if (e != cudaSuccess) return e;
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
-  const int grid = (P.B + TEAMS - 1) / TEAMS;
+  const int grid = std::min((P.B + TEAMS - 1) / TEAMS, std::max(1, occ) * ctx->num_sms);   // persistent CTAs, queue-fed
+  e = cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
   ctx->stats.teams_per_cta = TEAMS;
   ctx->stats.threads_per_team = T;
   ctx->stats.ctas_per_sm = occ;
@@ -484,6 +488,8 @@ static cudaError_t launch_gmem(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
   e = ensure(&ctx->d_gstate, &ctx->cap_gstate, per_cta * grid);
   if (e != cudaSuccess) return e;
   P.gstate = ctx->d_gstate;
+  e = cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
   ctx->stats.teams_per_cta = 1;
   ctx->stats.threads_per_team = 256;
   ctx->stats.ctas_per_sm = occ;
@@ -607,9 +613,11 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   cudaStream_t st = (dev || stream) ? (cudaStream_t)stream : ctx->stream;
   const size_t nk = (size_t)B * p, npar = (size_t)p * c * l, ng = (size_t)B * p * l;
 
-  if (!dev) {   // the reference's asserts on k (utils.py:12-15)
-    for (size_t i = 0; i < nk; ++i)
-      if (k[i] < 0 || k[i] >= c) return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
+  if (!dev) {   // the reference's asserts on k (utils.py:12-15); branch-free so that it vectorises
+    uint32_t bad = 0;
+    const uint32_t cu = (uint32_t)c;
+    for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k[i] >= cu);
+    if (bad) return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
   }
 
   const bool resident = (flags & QAS_F_PARAMS_RESIDENT) != 0;
@@ -650,7 +658,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
       P.wc16.w[j] = (smem_path ? qas_swz(w) : w) << 4;
     }
   }
-  P.energy = denergy; P.gstate = nullptr; P.mout = nullptr; P.phase_clk = ctx->d_phase;
+  P.energy = denergy; P.gstate = nullptr; P.mout = nullptr; P.phase_clk = ctx->d_phase; P.work_counter = ctx->d_counter;
   P.init_basis = ctx->init_basis;
   P.B = B; P.p = p; P.c = c; P.l = l; P.n = ctx->n;
   P.ops_cap = std::max(1, p * ctx->max_expansion);

@@ -39,6 +39,7 @@ struct EvalParams {
   const GateDTab *dU;          // [NCONST + p*c]          (thread-per-circuit kernel only)
   double *grad;                // [B][p][l] compact gradients, zero-filled (thread-per-circuit kernel only)
   unsigned long long *phase_clk;   // diagnostic: summed per-team clock64 deltas [prologue, forward, H, adjoint] or null
+  int *work_counter;           // global queue head of the team kernels (zeroed before every launch)
   const uint32_t *tape;        // [B][4 + ops_cap*5] compiled tape records (compile_tapes_kernel)
   uint64_t init_basis;
   int B, p, c, l, n, ops_cap, init_kind;
@@ -463,6 +464,7 @@ __host__ __device__ inline size_t eval_team_smem_bytes(int n, int T, bool grad, 
   if (stage_u) b += (size_t)ops_cap * 64;
   if (grad && wpt > 1) b += (size_t)2 * 3 * wpt * 64;
   b += (((size_t)wpt * 8) + 15) & ~(size_t)15;
+  b += 16;                                   // the team's work-queue slot
   return b;
 }
 
@@ -635,14 +637,21 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
   double *red = nullptr;
   if constexpr (GRAD && WPT > 1) { red = reinterpret_cast<double *>(base); base += (size_t)2 * 3 * WPT * 64; }
   double *ered = reinterpret_cast<double *>(base);
+  base += (((size_t)WPT * 8) + 15) & ~(size_t)15;
+  int *bslot = reinterpret_cast<int *>(base);
   // slice descriptors, shared by the CTA's teams
   uint32_t *sdesc = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TEAMS * team_bytes);
   for (int s = threadIdx.x; s < P.C_real + P.C_imag; s += 256) sdesc[s] = P.cdesc[s];
   __syncthreads();
 
-  for (int b0 = blockIdx.x * TEAMS; b0 < P.B; b0 += gridDim.x * TEAMS) {
-    const int b = b0 + team;
-    if (b >= P.B) continue;      // teams are independent: nobody waits on an idle one
+  // Every team pulls circuits from one global queue: circuit lengths differ (2-14 gates on the LiH
+  // batch), and with a fixed circuit -> CTA assignment the short circuit's team would idle until its
+  // CTA mates finish.  The grid is persistent (CTAs per SM x SMs).
+  for (;;) {
+    if (tid == 0) *bslot = atomicAdd(P.work_counter, 1);
+    team_sync<T>(team, tmask);
+    const int b = *bslot;
+    if (b >= P.B) break;
     constexpr bool active = true;
 
     long long clk_prev = 0;
