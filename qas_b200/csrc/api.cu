@@ -35,11 +35,11 @@ struct qas_ctx {
   unsigned long long *d_phase = nullptr;   // QAS_B200_PHASE_CLOCKS=1: per-phase clock sums (diagnostic)
   bool stage_times = false;                // QAS_B200_STAGE_TIMES=1: print per-kernel stream times of every call
   cudaEvent_t sev[8] = {nullptr};
-  int RBH = 0, PD = 1;             // H-apply blocking / prefetch depth (QAS_B200_HCFG=rb,pd overrides)
-  int gcfg_g = 0, gcfg_m = 0;      // QAS_B200_GCFG=gmax,minb tuning override (n = 8, 10 default teams)
+  int PD = 1;                      // H-apply prefetch depth (rows)
   bool small_kernel = true;        // n <= 5: thread-per-circuit kernel (QAS_B200_SMALL=0 disables)
   bool small_now = false;          // ... and chosen for the call in progress
   int *d_counter = nullptr;        // work-queue head of the team kernels
+  int blk = 256;                   // threads per CTA of the team kernel
   GateTab *d_U = nullptr;
   GateDTab *d_dU = nullptr;
   int tab_p = 0;
@@ -138,12 +138,14 @@ static void fill_const_table(std::vector<GateTab> &t) {
   set(QAS_C_ZZ_MPI4, make_double2(cs, sn), Z0, Z0, make_double2(cs, -sn));
 }
 
+// threads per team and threads per CTA by qubit count (n <= 5 normally run the thread-per-circuit
+// kernel).  n = 10, 11: two-warp / four-warp teams in 128-thread CTAs -- six / three circuits in flight
+// per SM instead of four / two, and less waiting inside a team for the warp that owns the in-support
+// cosets of the adjoint sweep (LiH-10q: 2.46 -> 2.23 ms against 128-thread teams in 256-thread CTAs).
 constexpr int team_threads(int n) {
-  return n <= 4 ? 8 : n == 5 ? 16 : n <= 8 ? 32 : n == 9 ? 64 : n == 10 ? 128 : 256;
+  return n <= 4 ? 8 : n == 5 ? 16 : n <= 8 ? 32 : n <= 10 ? 64 : n == 11 ? 128 : 256;
 }
-// gates per fused pass: 2 where the team has the amplitudes for it.  3-gate passes (8 + 8 amplitudes
-// in registers) measured slower once the passes became support-restricted: the kernel is bound by
-// per-pass latency at 4 teams per SM, and the 2-gate code needs no spills inside 128 registers.
+constexpr int team_blk(int n) { return (n == 10 || n == 11) ? 128 : 256; }
 constexpr int qas_gmax(int n, int T) { return qas_block_bits(n, T) >= 2 ? 2 : 1; }
 // H application: 4 amplitudes per thread and a 2-deep prefetch ring where the team has the
 // amplitudes for it (measured best on LiH-10q / H2O-8q among (3,1) (3,2) (2,2) (2,4))
@@ -151,10 +153,8 @@ constexpr int qas_hrb(int n, int T) { return qas_block_bits(n, T) >= 2 ? 2 : qas
 constexpr int qas_hpd(int n, int T) { return qas_hrb(n, T) >= 1 ? 2 : 1; }   // PD must divide 2^RB
 static int team_threads_for(int n, int shift) {
   const int t = team_threads(n);
-  if (n >= 13) return 256;
-  // alternative team sizes exist for n = 8..10 (see launch_eval)
-  if (shift > 0 && n >= 8 && n <= 10 && t * 2 <= 256) return t * 2;
-  if (shift < 0 && n >= 9 && n <= 10) return t / 2;
+  // QAS_B200_TEAM_SHIFT=1: the doubled team in a 256-thread CTA (compiled for n = 8..11, see launch_eval)
+  if (shift > 0 && n >= 8 && n <= 11) return t * 2;
   return t;
 }
 
@@ -271,21 +271,12 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   cx->stage_times = getenv("QAS_B200_STAGE_TIMES") && atoi(getenv("QAS_B200_STAGE_TIMES")) != 0;
   const bool want_phase = getenv("QAS_B200_PHASE_CLOCKS") && atoi(getenv("QAS_B200_PHASE_CLOCKS")) != 0;
   cx->T = team_threads_for(n_qubits, cx->team_shift);
+  cx->blk = cx->team_shift > 0 ? 256 : team_blk(n_qubits);
   cx->GMAX = qas_gmax(n_qubits <= 13 ? n_qubits : 20, cx->T);
   cx->RB = qas_hrb(n_qubits <= 13 ? n_qubits : 20, cx->T);
   cx->PD = qas_hpd(n_qubits <= 13 ? n_qubits : 20, cx->T);
   if (const char *sk = getenv("QAS_B200_SMALL")) cx->small_kernel = atoi(sk) != 0;
   if (n_qubits <= 5 && cx->small_kernel) { cx->GMAX = 1; cx->RB = n_qubits >= 4 ? 1 : 0; cx->PD = cx->RB >= 1 ? 2 : 1; }
-  if (const char *gc = getenv("QAS_B200_GCFG")) {   // tuning: "gmax,min CTAs per SM" among the compiled variants
-    int gv = 0, mv = 0;
-    if (sscanf(gc, "%d,%d", &gv, &mv) == 2 && cx->team_shift == 0 &&
-        (n_qubits == 10 || n_qubits == 8) && mv == 2 && (gv == 1 || gv == 3)) { cx->gcfg_g = gv; cx->gcfg_m = mv; cx->GMAX = gv; }
-  }
-  if (const char *hc = getenv("QAS_B200_HCFG")) {   // tuning: "rb,pd" among the compiled variants
-    int rbv = 0, pdv = 0;
-    if (sscanf(hc, "%d,%d", &rbv, &pdv) == 2 && (n_qubits == 8 || n_qubits == 10) && cx->team_shift == 0 &&
-        ((rbv == 3 && pdv == 2) || (rbv == 2 && (pdv == 1 || pdv == 2 || pdv == 4)) || (rbv == 1 && pdv == 2))) { cx->RB = rbv; cx->PD = pdv; }
-  }
 
   // group the Hamiltonian by X mask: slice key = (xmask, is_imag); term sign from i^{nY}
   std::map<std::pair<uint64_t, int>, std::vector<std::pair<uint32_t, double>>> slices;
@@ -450,17 +441,17 @@ static size_t sdesc_bytes(int S) { return (((size_t)S * 4) + 15) & ~(size_t)15; 
 
 // CTAs per SM the register allocation is bounded for: the 3-gate adjoint pass holds 8 + 8
 // amplitudes and a 2x2 cross matrix in registers (128-register budget)
-constexpr int qas_minb(int n, int T) { return qas_block_bits(n, T) >= 2 ? 2 : 3; }
+constexpr int qas_minb(int n, int T, int blk) { return blk == 128 ? 3 : (qas_block_bits(n, T) >= 2 ? 2 : 3); }
 
-template <int N, int T, bool GRAD, int RBH, int PD, int GMAX_ = 0, int MINB_ = 0>
+template <int N, int T, bool GRAD, int RBH, int PD, int GMAX_ = 0, int MINB_ = 0, int BLK = 256>
 static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t st) {
-  constexpr int TEAMS = 256 / T;
+  constexpr int TEAMS = BLK / T;
   const size_t smem = eval_team_smem_bytes(N, T, GRAD, P.ops_cap, true, qas_stage_u(N)) * TEAMS + sdesc_bytes(P.C_real + P.C_imag);
-  auto kern = eval_kernel<N, T, GRAD, (GMAX_ ? GMAX_ : qas_gmax(N, T)), RBH, PD, (MINB_ ? MINB_ : qas_minb(N, T))>;
+  auto kern = eval_kernel<N, T, GRAD, (GMAX_ ? GMAX_ : qas_gmax(N, T)), RBH, PD, (MINB_ ? MINB_ : qas_minb(N, T, BLK)), BLK>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLK, smem);
   const int grid = std::min((P.B + TEAMS - 1) / TEAMS, std::max(1, occ) * ctx->num_sms);   // persistent CTAs, queue-fed
   e = cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
@@ -469,7 +460,7 @@ static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t s
   ctx->stats.ctas_per_sm = occ;
   ctx->stats.smem_bytes_per_cta = (int)smem;
   ctx->stats.path = 0;
-  kern<<<grid, 256, smem, st>>>(P);
+  kern<<<grid, BLK, smem, st>>>(P);
   return cudaGetLastError();
 }
 
@@ -538,25 +529,16 @@ static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
   const int nmax_smem = GRAD ? 12 : 13;
   const int T = ctx->T;
   if (P.n <= nmax_smem) {
-    const size_t smem = eval_team_smem_bytes(P.n, T, GRAD, P.ops_cap, true, qas_stage_u(P.n)) * (256 / T) + sdesc_bytes(P.C_real + P.C_imag);
+    const size_t smem = eval_team_smem_bytes(P.n, T, GRAD, P.ops_cap, true, qas_stage_u(P.n)) * (ctx->blk / T) + sdesc_bytes(P.C_real + P.C_imag);
     if (smem <= 227 * 1024) {
-#define QAS_GCASE(N_, T_, G_, M_) \
-  if (P.n == N_ && T == T_ && ctx->gcfg_g == G_ && ctx->gcfg_m == M_) return launch_smem<N_, T_, GRAD, 2, 2, G_, M_>(ctx, P, st);
-      QAS_GCASE(10, 128, 3, 2) QAS_GCASE(10, 128, 1, 2) QAS_GCASE(8, 32, 3, 2) QAS_GCASE(8, 32, 1, 2)
-#undef QAS_GCASE
-#define QAS_CASE(N_, T_)                                                              \
-  if (P.n == N_ && T == T_ && ctx->RB == qas_hrb(N_, T_) && ctx->PD == qas_hpd(N_, T_)) \
-    return launch_smem<N_, T_, GRAD, qas_hrb(N_, T_), qas_hpd(N_, T_)>(ctx, P, st);
-#define QAS_HCASE(N_, T_, RB_, PD_) \
-  if (P.n == N_ && T == T_ && ctx->RB == RB_ && ctx->PD == PD_) return launch_smem<N_, T_, GRAD, RB_, PD_>(ctx, P, st);
-      QAS_CASE(2, 8) QAS_CASE(3, 8) QAS_CASE(4, 8) QAS_CASE(5, 16) QAS_CASE(6, 32) QAS_CASE(7, 32)
-      QAS_CASE(8, 32) QAS_CASE(8, 64) QAS_CASE(9, 64) QAS_CASE(9, 32) QAS_CASE(9, 128)
-      QAS_CASE(10, 128) QAS_CASE(10, 64) QAS_CASE(10, 256) QAS_CASE(11, 256) QAS_CASE(12, 256)
-      QAS_HCASE(8, 32, 3, 2) QAS_HCASE(8, 32, 2, 4) QAS_HCASE(8, 32, 2, 1) QAS_HCASE(8, 32, 1, 2)
-      QAS_HCASE(10, 128, 3, 2) QAS_HCASE(10, 128, 2, 4) QAS_HCASE(10, 128, 2, 1) QAS_HCASE(10, 128, 1, 2)
+#define QAS_CASE(N_, T_, BLK_) \
+  if (P.n == N_ && T == T_ && ctx->blk == BLK_) return launch_smem<N_, T_, GRAD, qas_hrb(N_, T_), qas_hpd(N_, T_), 0, 0, BLK_>(ctx, P, st);
+      QAS_CASE(2, 8, 256) QAS_CASE(3, 8, 256) QAS_CASE(4, 8, 256) QAS_CASE(5, 16, 256) QAS_CASE(6, 32, 256)
+      QAS_CASE(7, 32, 256) QAS_CASE(8, 32, 256) QAS_CASE(9, 64, 256) QAS_CASE(10, 64, 128) QAS_CASE(11, 128, 128)
+      QAS_CASE(12, 256, 256)
+      QAS_CASE(8, 64, 256) QAS_CASE(9, 128, 256) QAS_CASE(10, 128, 256) QAS_CASE(11, 256, 256)     // QAS_B200_TEAM_SHIFT=1
 #undef QAS_CASE
-#undef QAS_HCASE
-      if constexpr (!GRAD) { if (P.n == 13) return launch_smem<13, 256, false, qas_hrb(13, 256), qas_hpd(13, 256)>(ctx, P, st); }
+      if constexpr (!GRAD) { if (P.n == 13 && T == 256) return launch_smem<13, 256, false, qas_hrb(13, 256), qas_hpd(13, 256)>(ctx, P, st); }
     }
   }
   // the global-memory instantiation is compiled for 256-thread teams, 3-gate passes, 4-amplitude H rows

@@ -77,7 +77,7 @@ __device__ __forceinline__ void team_sync(int team, uint32_t tmask) {
   if constexpr (T <= 32) {
     __syncwarp(tmask);
   } else if constexpr (T == 256) {
-    __syncthreads();
+    __syncthreads();          // 256-thread teams are always alone in their CTA
   } else {
     asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(T) : "memory");
   }
@@ -594,9 +594,9 @@ __device__ __forceinline__ void adj_group(double2 *psi, double2 *lam, const uint
 // state in global memory (one team per CTA, L2/HBM resident) -- same code path otherwise.
 // GMAX = gates per fused pass, RB = log2(amplitudes per thread) in the H application, PD = depth of
 // the register ring that prefetches sign-table rows (L2 latency is the exposed cost there)
-template <int N, int T, bool GRAD, int GMAX, int RB, int PD, int MINB>
-__global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
-  constexpr int TEAMS = 256 / T;
+template <int N, int T, bool GRAD, int GMAX, int RB, int PD, int MINB, int BLK = 256>
+__global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
+  constexpr int TEAMS = BLK / T;
   constexpr int WPT = T >= 32 ? T / 32 : 1;      // warps per team
   constexpr int TW = T >= 32 ? 32 : T;           // lanes of one warp that belong to the team
   constexpr bool STAGE_U = qas_stage_u(N);
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(256, MINB) eval_kernel(const EvalParams P) {
   int *bslot = reinterpret_cast<int *>(base);
   // slice descriptors, shared by the CTA's teams
   uint32_t *sdesc = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TEAMS * team_bytes);
-  for (int s = threadIdx.x; s < P.C_real + P.C_imag; s += 256) sdesc[s] = P.cdesc[s];
+  for (int s = threadIdx.x; s < P.C_real + P.C_imag; s += BLK) sdesc[s] = P.cdesc[s];
   __syncthreads();
 
   // Every team pulls circuits from one global queue: circuit lengths differ (2-14 gates on the LiH
