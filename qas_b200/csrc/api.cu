@@ -595,13 +595,10 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   cudaStream_t st = (dev || stream) ? (cudaStream_t)stream : ctx->stream;
   const size_t nk = (size_t)B * p, npar = (size_t)p * c * l, ng = (size_t)B * p * l;
 
-  if (!dev) {   // the reference's asserts on k (utils.py:12-15); branch-free so that it vectorises
-    uint32_t bad = 0;
-    const uint32_t cu = (uint32_t)c;
-    for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k[i] >= cu);
-    if (bad) return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
-  }
-
+  // one-reward-at-a-time rollouts: no timing events, no structure-list upload (the tapes are compiled
+  // on the host and the reward path never reads k on the device)
+  const bool tiny = !dev && B <= 16;
+  const bool small = use_small_kernel(ctx) && small_fits(ctx, std::max(1, p * ctx->max_expansion));   // n <= 5 kernel compiles from k itself
   const bool resident = (flags & QAS_F_PARAMS_RESIDENT) != 0;
   if (resident && (dev || ctx->resident_p != p))
     return fail(ctx, QAS_ERR_INVALID, "QAS_F_PARAMS_RESIDENT needs host pointers and a prior qas_set_params of the same depth");
@@ -615,7 +612,17 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     CK(ensure(&ctx->d_k, &ctx->cap_k, nk));
     CK(ensure(&ctx->d_params, &ctx->cap_params, npar));
     CK(ensure(&ctx->d_energy, &ctx->cap_energy, (size_t)B));
-    CK(cudaMemcpyAsync(ctx->d_k, k, nk * 4, cudaMemcpyHostToDevice, st));
+    if (!(tiny && !want_grad && !small)) CK(cudaMemcpyAsync(ctx->d_k, k, nk * 4, cudaMemcpyHostToDevice, st));
+    {   // the reference's asserts on k (utils.py:12-15), checked while the copy is in flight;
+        // branch-free so that it vectorises
+      uint32_t bad = 0;
+      const uint32_t cu = (uint32_t)c;
+      for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k[i] >= cu);
+      if (bad) {
+        cudaStreamSynchronize(st);
+        return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
+      }
+    }
     if (!resident) CK(cudaMemcpyAsync(ctx->d_params, params, npar * 8, cudaMemcpyHostToDevice, st));
     dk = ctx->d_k; dparams = ctx->d_params; denergy = ctx->d_energy;
     dgrad = nullptr;
@@ -626,7 +633,6 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     dgrad = ctx->d_grad;
   }
 
-  const bool small = use_small_kernel(ctx) && small_fits(ctx, std::max(1, p * ctx->max_expansion));
   ctx->small_now = small;
   EvalParams P{};
   P.k = dk; P.pool = ctx->d_pool; P.U = ctx->d_U; P.dU = ctx->d_dU; P.grad = dgrad;
@@ -660,7 +666,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     if (!ctx->sev[i]) cudaEventCreate(&ctx->sev[i]);
     cudaEventRecord(ctx->sev[i], st);
   };
-  if (!dev) CK(cudaEventRecord(ctx->ev0, st));
+  if (!dev && !tiny) CK(cudaEventRecord(ctx->ev0, st));
   stamp(0);
   if (want_grad) CK(cudaMemsetAsync(dgrad, 0, ng * 8, st));
   stamp(1);
@@ -712,12 +718,11 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
     CK(cudaGetLastError());
   }
-  CK(cudaEventRecord(ctx->ek0, st));
+  if (!tiny) CK(cudaEventRecord(ctx->ek0, st));
   stamp(3);
   if (want_grad) CK(launch_eval<true>(ctx, P, st)); else CK(launch_eval<false>(ctx, P, st));
-  CK(cudaEventRecord(ctx->ek1, st));
+  if (!tiny) { CK(cudaEventRecord(ctx->ek1, st)); ctx->ek_pending = true; }
   stamp(4);
-  ctx->ek_pending = true;
   ctx->stats.launches += 3;
   if (want_grad && !small) {
     const size_t nthr = (size_t)B * P.ops_cap;
@@ -761,13 +766,13 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   ctx->stats.evals += (uint64_t)B;
 
   if (!dev) {
-    CK(cudaEventRecord(ctx->ev1, st));
+    if (!tiny) CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaMemcpyAsync(energy, denergy, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     if (grad_compact) CK(cudaMemcpyAsync(grad_compact, dgrad, ng * 8, cudaMemcpyDeviceToHost, st));
     if (grad_dense) CK(cudaMemcpyAsync(grad_dense, ddense, npar * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
+    if (!tiny && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
   }
   return QAS_OK;
 }
