@@ -26,7 +26,11 @@ Parity pinning status (see DESIGN.md "Oracle"):
                                        saves none); the oracle's three independent derivative
                                        methods (adjoint, parameter-shift, central difference)
                                        must agree instead
-  * H2O (8q/14q), TwoQubitH2, H2/LiH/H2O sto-3g dataset models -- PARITY UNPINNED (the
-                                       Hamiltonians are generated/downloaded upstream and are
-                                       not recoverable offline; stand-ins are documented)
+  * 8-qubit H2O energy              -- pinned (Hamiltonian rebuilt by tools/sto_ng.py: its RHF and
+                                       FCI energies match search_H2O_near_cx.py:45-49 to 3e-10,
+                                       its LiH integrals the shipped HDF5 to 3e-8; stored circuit
+                                       to <=5e-6; orbital phases not recoverable)
+  * TwoQubitH2, H2/LiH/H2O sto-3g dataset models -- PARITY UNPINNED (class missing upstream /
+                                       network downloads; rebuilt with the same RHF code where the
+                                       geometry is known, assumptions documented)
 """

@@ -4,8 +4,8 @@ Upstream these are PennyLane ``qml.Hamiltonian`` objects built at import time by
 PySCF/OpenFermion (qas/qml_models/qml_models_legacy.py:1237-1256), downloaded datasets
 (qchem_model.py:18-20) or in-file edge lists (kagome_heisenberg_model.py:20-52,
 qml_models_legacy.py:2347,2514).  Here they are small JSON tables under ``qas_b200/data/``
-generated once by ``tools/make_hamiltonians.py`` (which documents provenance and which
-ones are parity-unpinned stand-ins).
+generated once by ``tools/make_hamiltonians.py`` (which documents provenance, what each table
+is pinned against, and which ones are parity-unpinned).
 """
 import json
 import os

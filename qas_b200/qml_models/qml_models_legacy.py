@@ -5,7 +5,8 @@ five methods; only what they evaluate is declared here.
   FourQubitH2               :1258-1368  HF start |1100>, H2/sto-3g 15-term operator
   FourQubitH2_VaccumInitial :1370-1480  same operator, |0000> start
   LiH                       :1482-1592  10 qubits, |0..0> start (the BasisState line is commented out upstream)
-  H2O                       :1594-1702  8 qubits, |0..0> start; operator is a parity-unpinned stand-in
+  H2O                       :1594-1702  8 qubits, |0..0> start; operator rebuilt by RHF/STO-6G (tools/sto_ng.py), pinned to the
+                                        reference's quoted SCF/FCI energies and its saved search result
   QAOAVQCDemo               :2328-2491  7 qubits, |+>^7 start, loss = -sum_e (1 - <ZZ>)/2, reward = -loss
   QAOAWeightedVQCDemo       :2493-2651  5 qubits, weighted edges
   TwoQubitH2                missing upstream (imported by search-scripts-legacy/two_qubit_h2.py:3); stand-in
@@ -39,7 +40,7 @@ class LiH(HamiltonianModel):
 class H2O(HamiltonianModel):
     name = "H2O"
     num_qubits = 8
-    hamiltonian = "h2o_8q_standin"
+    hamiltonian = "h2o_sto6g_8q"
 
 
 class TwoQubitH2(HamiltonianModel):

@@ -14,10 +14,17 @@ writes small JSON tables the product and the tests load:
                    downloaded qchem dataset of qchem_model.py:19; same geometry class)
   kagome_16q       kagome_heisenberg_model.py:20-52 (edge list is in-tree)
   qaoa_7q, qaoa_weighted_5q   graphs at qml_models_legacy.py:2347, :2514
-  h2o_8q_standin, h2o_14q_standin, h2_2q_standin
-                   PARITY-UNPINNED stand-ins (the upstream operators are not recoverable
-                   offline): seeded random molecular-structured integrals pushed through the
-                   same Jordan-Wigner code, and the textbook 2-qubit reduced H2 operator.
+  h2o_sto6g_8q     8-qubit H2O of qml_models_legacy.py:1245-1256: restricted Hartree-Fock over STO-6G
+                   with tools/sto_ng.py (McMurchie-Davidson integrals), core = 3 orbitals, active =
+                   4 orbitals / 4 electrons, Jordan-Wigner.  Pinned: the integral code reproduces the
+                   SCF and FCI energies quoted at search_H2O_near_cx.py:45-49 to 3e-10, the shipped
+                   LiH integrals to 3e-8, and the operator reproduces the last loss of the saved H2O
+                   search result (20220504-074905_H2O_*.json) to 3e-6.
+  h2_sto3g_4q      H2 / STO-3G at 0.742 A (qchem_model.py:18; the dataset itself is a download)
+  h2o_sto3g_14q    H2O / STO-3G, r(OH) = 0.958 A (qchem_model.py:20), full space, 14 qubits; the
+                   H-O-H angle of the dataset is not stated in the reference: 104.5 deg assumed
+  h2_2q_standin    PARITY-UNPINNED stand-in: the textbook 2-qubit reduced H2 operator (the class
+                   TwoQubitH2 is missing from the reference tree).
 
 Usage:  python tools/make_hamiltonians.py [/root/reference]
 """
@@ -29,6 +36,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import fermion as F  # noqa: E402
+import sto_ng as G  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "qas_b200", "data")
@@ -91,17 +99,25 @@ def molecular(one, two, e_nuc, occupied, active):
     return F.to_words(h1.shape[0], acc)
 
 
-def random_molecular(m, seed, scale1=1.0, scale2=0.35, naux=6):
-    """Seeded random integrals with the permutational symmetry of real orbitals."""
-    rng = np.random.default_rng(seed)
-    a = rng.standard_normal((m, m))
-    one = -(np.diag(np.linspace(2.0, 0.3, m)) * scale1) + 0.1 * (a + a.T)
-    b = rng.standard_normal((naux, m, m)) * scale2
-    b = 0.5 * (b + b.transpose(0, 2, 1)) + np.eye(m)[None] * 0.4
-    chem = np.einsum("Lpq,Lrs->pqrs", b, b) / naux          # (pq|rs)
-    two = chem.transpose(0, 2, 3, 1)                         # of[p,q,r,s] = (ps|qr)
-    two = np.ascontiguousarray(two)
-    return one, two
+H2O_LEGACY_SYMBOLS = ["H", "O", "H"]
+# qml_models_legacy.py:1245-1246 (an Angstrom -> Bohr factor applied to the listed numbers)
+H2O_LEGACY_BOHR = np.array([0., 0., 0., 1.63234543, 0.86417176, 0., 3.36087791, 0., 0.]) * 1.88973
+
+
+def hartree_fock_molecular(symbols, coords_bohr, basis, n_electrons, n_core, n_active):
+    """RHF -> MO integrals -> active space -> Jordan-Wigner words; also returns E_SCF."""
+    S, h, g, e_nuc = G.ao_integrals(symbols, coords_bohr, basis)
+    e_scf, C, _ = G.rhf(S, h, g, n_electrons, e_nuc)
+    one, two = G.mo_integrals(h, g, C)
+    core = list(range(n_core))
+    active = list(range(n_core, n_core + n_active))
+    return molecular(one, two, e_nuc, core, active), e_scf
+
+
+def h2o_sto3g_geometry(r_angstrom=0.958, angle_deg=104.5):
+    r = r_angstrom * G.BOHR_PER_ANGSTROM
+    t = np.deg2rad(angle_deg) / 2
+    return ["O", "H", "H"], np.array([0., 0., 0., r * np.sin(t), r * np.cos(t), 0., -r * np.sin(t), r * np.cos(t), 0.])
 
 
 def dump(name, n, terms, source, **extra):
@@ -145,14 +161,26 @@ def main():
          "results_and_plots-legacy/molecule_pyscf_sto-3g.hdf5, full space, JW; stands in for "
          "qml.data.load('qchem','LiH','STO-3G') at qchem_model.py:19 (parity unpinned)")
 
-    o, t = random_molecular(4, seed=8)
-    dump("h2o_8q_standin", 8, molecular(o, t, 0.0, [], [0, 1, 2, 3]),
-         "STAND-IN (parity unpinned): seeded random molecular-structured integrals, 4 spatial "
-         "orbitals, JW; upstream operator (qml_models_legacy.py:1245-1256) needs PySCF")
-    o, t = random_molecular(7, seed=14)
-    dump("h2o_14q_standin", 14, molecular(o, t, 0.0, [], list(range(7))),
-         "STAND-IN (parity unpinned): seeded random molecular-structured integrals, 7 spatial "
-         "orbitals, JW; upstream operator is a network download (qchem_model.py:20)")
+    words, e_scf = hartree_fock_molecular(H2O_LEGACY_SYMBOLS, H2O_LEGACY_BOHR, "sto-6g", 10, 3, 4)
+    dump("h2o_sto6g_8q", 8, words,
+         "qml_models_legacy.py:1245-1256 rebuilt with tools/sto_ng.py: RHF/STO-6G, core=[0,1,2], "
+         "active=[3..6] (4 electrons), JW; orbital phases: largest AO coefficient positive "
+         "(the reference's phases are whatever its eigen-solver returned: not recoverable; the "
+         "saved search result's energy moves by < 3e-6 across the 8 choices)",
+         e_scf=e_scf, e_scf_quoted_angstrom_geometry=-75.1645758157887,
+         e_fci_quoted_angstrom_geometry=-75.491788196432,
+         e_casci_4e4o=G.sector_ground_energy(8, words, 2, 2))
+    r = 0.742 * G.BOHR_PER_ANGSTROM
+    words, e_scf = hartree_fock_molecular(["H", "H"], [0, 0, -r / 2, 0, 0, r / 2], "sto-3g", 2, 0, 2)
+    dump("h2_sto3g_4q", 4, words,
+         "qchem_model.py:18 (qml.data.load qchem H2 STO-3G bondlength 0.742): RHF/STO-3G with "
+         "tools/sto_ng.py, full space, JW (the dataset itself is a network download)", e_scf=e_scf)
+    sym, xyz = h2o_sto3g_geometry()
+    words, e_scf = hartree_fock_molecular(sym, xyz, "sto-3g", 10, 0, 7)
+    dump("h2o_sto3g_14q", 14, words,
+         "qchem_model.py:20 (qml.data.load qchem H2O STO-3G bondlength 0.958): RHF/STO-3G with "
+         "tools/sto_ng.py, full space, JW; H-O-H angle 104.5 deg ASSUMED (not stated in the "
+         "reference; the dataset itself is a network download)", e_scf=e_scf)
 
 
 if __name__ == "__main__":
