@@ -2,6 +2,8 @@
 // shared-memory-tiled passes (one HBM read + write per pass), Pauli-sum expectation.
 // C ABI: include/qas_b200_sv.h.  HBM-bandwidth bound: 32 * 2^n_local bytes per pass.
 #include <algorithm>
+#include <array>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -38,21 +40,29 @@ struct __align__(16) SvTileGate {
   int kind;            // SV_K_*
   int tslot;           // U1: register slot bit (0..2) of the target inside its group
   int cslot;           // U1: register slot bit of the control, -1 if the control is not a slot bit
-  int cbit_tile;       // U1: tile bit index of a control that is a tile bit but not a slot bit, else -1
+  uint32_t crmask;     // U1: control = parity(tile index & crmask) for a tile-bit control that is not a slot bit, else 0
   int cpos_out;        // U1: slab bit position of a control outside the tile, -1 if none
   uint32_t tmask;      // PDIAG: parity mask over tile bits
   unsigned long long omask;   // PDIAG: parity mask over slab bits outside the tile
   double2 u[4];
 };
 
-// A group = consecutive gates of a pass whose targets fall on at most three tile bits tb[0..2]:
-// every thread holds the 8 amplitudes that differ in those bits and applies ALL gates of the
-// group in registers, so the tile goes through shared memory once per group instead of once per
-// gate (the un-grouped version was shared-memory-bandwidth bound at ~18 gates per pass).
+// A group = consecutive gates of a pass whose targets fall on at most three logical tile bits:
+// every thread holds the 8 amplitudes P ^ span(m[0..2]) and applies ALL gates of the group in
+// registers, so the tile goes through shared memory once per group instead of once per gate (the
+// un-grouped version was shared-memory-bandwidth bound at ~18 gates per pass).
+//
+// CNOT folding inside a pass: a CNOT whose control and target are both tile bits is the index map
+// j -> C j, linear over GF(2).  It is never executed: the host keeps the frame A of the pass (tile
+// position p holds the amplitude of logical tile index A p), a gate on logical bit q then pairs the
+// positions (p, p ^ m), m = A^-1 e_q, and reads logical bits as parity(p & r), r = row q of A; the
+// coset representatives of a group lie in the common kernel of its r's (host-built table), so slot
+// index bits are logical bits.  The frame is undone once, by the pass's store to HBM
+// (position of logical index j = A^-1 j).
 struct SvGroup {
   int first, ngates;
-  int tb[3];           // ascending tile bit indices held in registers
-  int ls[3];           // coset-counter bit that trades places with counter bit 0 / 1 / 2 (see sv_swz)
+  uint32_t m[3];       // xor masks (tile positions) of the three logical bits held in registers
+  uint32_t w[3];       // sv_swz(m[q])
 };
 
 // The gate list and the groups of the pass being executed live in constant memory: every thread of
@@ -71,6 +81,8 @@ struct SvBlockParams {
   const unsigned short *ctab;  // [ngroups][2^(kb-3)] swizzled tile index of every coset representative
   int n_local, kb, c, ngates, ngroups;
   unsigned char bits[16];      // ascending slab positions of the tile bits; bits[0..c-1] = 0..c-1
+  unsigned short ainv[16];     // columns of A^-1 at the end of the pass (tile position of logical bit q)
+  int framed;                  // 0: the frame is the identity at the end of the pass
 };
 
 __device__ __forceinline__ double2 sv_cmul(double2 a, double2 b) {
@@ -172,9 +184,8 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
     __syncthreads();
     for (int gr = 0; gr < P.ngroups; ++gr) {
       const SvGroup &grp = c_sv_groups[gr];
-      const int b0 = grp.tb[0], b1 = grp.tb[1], b2 = grp.tb[2];
-      const uint32_t s1 = 1u << b0, s2 = 1u << b1, s4 = 1u << b2;
-      const uint32_t w1 = sv_swz(s1), w2 = sv_swz(s2), w4 = sv_swz(s4);     // the swizzle is xor-linear
+      const uint32_t s1 = grp.m[0], s2 = grp.m[1], s4 = grp.m[2];
+      const uint32_t w1 = grp.w[0], w2 = grp.w[1], w4 = grp.w[2];           // the swizzle is xor-linear
       const unsigned short *ctab = P.ctab + ((size_t)gr << (kb - 3));
       for (uint32_t t = threadIdx.x; t < (tsize >> 3); t += SV_THREADS) {
         // coset representative from the host-built table (the index arithmetic -- bit swaps, zero
@@ -191,8 +202,9 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
           const SvTileGate *gt = c_sv_gates + gi;
           const int kind = gt->kind;
           if (kind != SV_K_PDIAG) {
-            const int cpo = gt->cpos_out, cbt = gt->cbit_tile;
-            const bool on = (cpo < 0 || ((base >> cpo) & 1ull)) && (cbt < 0 || ((Pj >> cbt) & 1u));
+            const int cpo = gt->cpos_out;
+            const uint32_t crm = gt->crmask;
+            const bool on = (cpo < 0 || ((base >> cpo) & 1ull)) && (crm == 0u || (__popc(Pj & crm) & 1));
             if (on) {
               const uint32_t cm = gt->cslot >= 0 ? (1u << gt->cslot) : 0u;
               const int ts = gt->tslot;
@@ -226,13 +238,27 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
       }
       __syncthreads();
     }
-    {
+    if (!P.framed) {
       const uint32_t sw0 = sv_swz(threadIdx.x);
 #pragma unroll 4
       for (uint32_t k = 0; k < tsize; k += SV_THREADS) {
         const uint32_t j = threadIdx.x | k;
         if (j >= tsize) break;
         g[(j & lowmask) | offs[j >> c]] = tile[sw0 ^ sv_swz(k)];
+      }
+    } else {     // undo the frame: logical index j sits at tile position A^-1 j
+      uint32_t pt = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pt ^= ((threadIdx.x >> q) & 1u) ? (uint32_t)P.ainv[q] : 0u;
+      const uint32_t sw0 = sv_swz(pt);
+#pragma unroll 2
+      for (uint32_t k = 0; k < tsize; k += SV_THREADS) {
+        const uint32_t j = threadIdx.x | k;
+        if (j >= tsize) break;
+        uint32_t pk = 0;
+#pragma unroll
+        for (int q = 8; q < SV_MAX_TILE_BITS; ++q) pk ^= ((k >> q) & 1u) ? (uint32_t)P.ainv[q] : 0u;
+        g[(j & lowmask) | offs[j >> c]] = tile[sw0 ^ sv_swz(pk)];
       }
     }
     __syncthreads();
@@ -415,56 +441,78 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
   std::vector<SvTileGate> tg;
   std::vector<SvGroup> groups;
   std::vector<unsigned short> ctab;      // per group: swizzled tile index of every coset representative
-  auto h_ins0 = [](uint32_t t, int b) { return ((t >> b) << (b + 1)) | (t & ((1u << b) - 1u)); };
-  auto h_swap = [](uint32_t t, int a, int b) { const uint32_t x = ((t >> a) ^ (t >> b)) & 1u; return t ^ ((x << a) | (x << b)); };
   auto h_swz = [](uint32_t j) { uint32_t f = j >> 3; f ^= f >> 3; f ^= f >> 6; return j ^ (f & 7u); };
+  auto h_par = [](uint32_t v) { return (uint32_t)(__builtin_popcount(v) & 1); };
   std::vector<int> first(blocks.size() + 1, 0), gfirst(blocks.size() + 1, 0);
+  std::vector<std::array<unsigned short, 16>> ainv_of(blocks.size());
+  std::vector<int> framed_of(blocks.size(), 0);
+  int fold = 1;
+  if (const char *fe = getenv("QAS_B200_SV_FOLD")) fold = atoi(fe) != 0;   // tuning knob: 0 executes every CNOT
   for (size_t bi = 0; bi < blocks.size(); ++bi) {
     const Block &blk = blocks[bi];
     std::vector<int> tix(n_local, -1);
     for (size_t q = 0; q < blk.bits.size(); ++q) tix[blk.bits[q]] = (int)q;
+    // frame of the pass: tile position p holds logical tile index A p.  arow[q] = row q of A (reads
+    // logical bit q of a position), acol[q] = column q of A^-1 (xor mask that flips logical bit q).
+    std::vector<uint32_t> arow(kb), acol(kb);
+    for (int q = 0; q < kb; ++q) arow[q] = acol[q] = 1u << q;
     const int gate0 = (int)tg.size();
-    std::vector<int> cur_bits;      // tile bits (targets) of the open group
+    std::vector<int> cur_bits;      // logical tile bits (targets) of the open group
     int cur_first = 0;              // first gate (index relative to the block) of the open group
     auto close_group = [&](int end_rel) {
-      if (end_rel == cur_first) return;
-      // pad the register bits with the highest free tile bits (low bits stay with the lanes)
+      if (end_rel == cur_first) { cur_bits.clear(); return; }
+      // pad the register bits with the highest free logical bits (low bits stay with the lanes)
       for (int b = kb - 1; b >= 0 && (int)cur_bits.size() < 3; --b)
         if (std::find(cur_bits.begin(), cur_bits.end(), b) == cur_bits.end()) cur_bits.push_back(b);
       std::sort(cur_bits.begin(), cur_bits.end());
       SvGroup gr{};
       gr.first = cur_first; gr.ngates = end_rel - cur_first;
-      for (int q = 0; q < 3; ++q) gr.tb[q] = cur_bits[q];
-      {   // coset-counter bit i sits on the i-th non-register tile bit (ascending).  Counter bits 0..2
-          // are the lanes of a quarter-warp: move each of them (by a swap with a counter bit >= 3, or
-          // not at all) so that the three positions they land on are distinct modulo 3 (see sv_swz).
-        std::vector<int> npos;
-        for (int b = 0; b < kb; ++b) if (std::find(cur_bits.begin(), cur_bits.end(), b) == cur_bits.end()) npos.push_back(b);
-        const int m = (int)npos.size();
-        for (int q = 0; q < 3; ++q) gr.ls[q] = q;
-        bool done = m < 3;
-        for (int k0 = 0; k0 < m && !done; k0 = (k0 == 0 ? 3 : k0 + 1))
-          for (int k1 = 1; k1 < m && !done; k1 = (k1 == 1 ? 3 : k1 + 1))
-            for (int k2 = 2; k2 < m && !done; k2 = (k2 == 2 ? 3 : k2 + 1)) {
-              if (k0 == k1 || k0 == k2 || k1 == k2) continue;
-              const int r0 = npos[k0] % 3, r1 = npos[k1] % 3, r2 = npos[k2] % 3;
-              if (r0 != r1 && r0 != r2 && r1 != r2) { gr.ls[0] = k0; gr.ls[1] = k1; gr.ls[2] = k2; done = true; }
-            }
-      }
-      // slot indices of the group's gates
+      uint32_t rr[3];
+      for (int q = 0; q < 3; ++q) { gr.m[q] = acol[cur_bits[q]]; gr.w[q] = h_swz(gr.m[q]); rr[q] = arow[cur_bits[q]]; }
+      // slot indices of the group's gates; tile-bit controls outside the group become parity masks
       for (int r = cur_first; r < end_rel; ++r) {
         SvTileGate &t = tg[gate0 + r];
         if (t.kind == SV_K_PDIAG) continue;
-        const int tb_ = t.tslot;    // holds the tile bit until the group closes
+        const int tb_ = t.tslot;    // holds the logical tile bit until the group closes
         t.tslot = (int)(std::find(cur_bits.begin(), cur_bits.end(), tb_) - cur_bits.begin());
-        if (t.cbit_tile >= 0) {
-          auto it = std::find(cur_bits.begin(), cur_bits.end(), t.cbit_tile);
-          if (it != cur_bits.end()) { t.cslot = (int)(it - cur_bits.begin()); t.cbit_tile = -1; }
+        if (t.cslot >= 0) {         // holds the logical tile bit of the control
+          const int cb_ = t.cslot;
+          auto it = std::find(cur_bits.begin(), cur_bits.end(), cb_);
+          if (it != cur_bits.end()) { t.cslot = (int)(it - cur_bits.begin()); t.crmask = 0u; }
+          else { t.cslot = -1; t.crmask = arow[cb_]; }
         }
       }
+      // coset representatives: the common kernel of the three read masks, as xor-span of a basis whose
+      // first three vectors move the three bank-group bits of the swizzled index independently when
+      // the kernel allows it (they are the lanes of a quarter-warp, see sv_swz)
+      std::vector<uint32_t> kern;
+      {
+        // eliminate: x in kernel <=> rr[q].x = 0; rr's are independent with rr[a].m[b] = delta_ab, so
+        // projecting the unit vectors along span(m) onto the kernel spans it
+        std::vector<uint32_t> ech;      // echelon basis (highest-bit pivots) of the projections
+        for (int b = 0; b < kb; ++b) {
+          uint32_t x = 1u << b;
+          for (int q = 0; q < 3; ++q) if (h_par(x & rr[q])) x ^= gr.m[q];
+          for (uint32_t e : ech) if ((x ^ e) < x) x ^= e;
+          if (x) { ech.push_back(x); std::sort(ech.begin(), ech.end(), std::greater<uint32_t>()); }
+        }
+        // pick three with independent low swizzled bits first
+        std::vector<uint32_t> lead, rest, keys;
+        for (uint32_t v : ech) {
+          uint32_t key = h_swz(v) & 7u;
+          for (uint32_t kk : keys) if ((key ^ kk) < key) key ^= kk;
+          if (key && lead.size() < 3) { lead.push_back(v); keys.push_back(key); std::sort(keys.begin(), keys.end(), std::greater<uint32_t>()); }
+          else rest.push_back(v);
+        }
+        kern = lead;
+        std::sort(rest.begin(), rest.end());
+        kern.insert(kern.end(), rest.begin(), rest.end());
+      }
+      const int kd = (int)kern.size();       // = kb - 3
       for (uint32_t t = 0; t < (1u << (kb - 3)); ++t) {
-        const uint32_t tp = h_swap(h_swap(h_swap(t, 0, gr.ls[0]), 1, gr.ls[1]), 2, gr.ls[2]);
-        ctab.push_back((unsigned short)h_swz(h_ins0(h_ins0(h_ins0(tp, gr.tb[0]), gr.tb[1]), gr.tb[2])));
+        uint32_t P = 0;
+        for (int i = 0; i < kd; ++i) if ((t >> i) & 1u) P ^= kern[i];
+        ctab.push_back((unsigned short)h_swz(P));
       }
       groups.push_back(gr);
       cur_bits.clear();
@@ -475,7 +523,18 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
       const qas_sv_gate &g = gates[gi];
       SvTileGate t{};
       t.kind = g.kind;
-      t.tslot = -1; t.cslot = -1; t.cbit_tile = -1; t.cpos_out = -1;
+      t.tslot = -1; t.cslot = -1; t.crmask = 0u; t.cpos_out = -1;
+      const bool is_x = g.kind == QAS_SV_U1 && g.m[0] == 0.0 && g.m[1] == 0.0 && g.m[6] == 0.0 && g.m[7] == 0.0 &&
+                        g.m[2] == 1.0 && g.m[3] == 0.0 && g.m[4] == 1.0 && g.m[5] == 0.0;
+      if (fold && is_x && g.control >= 0 && tix[g.control] >= 0) {
+        // CNOT inside the tile: fold into the frame (A <- C A), nothing to execute
+        close_group(rel);
+        const int qt = tix[g.target], qc = tix[g.control];
+        arow[qt] ^= arow[qc];
+        acol[qc] ^= acol[qt];
+        framed_of[bi] = 1;
+        continue;
+      }
       if (g.kind == QAS_SV_U1) {
         const int tb_ = tix[g.target];
         if (std::find(cur_bits.begin(), cur_bits.end(), tb_) == cur_bits.end()) {
@@ -483,19 +542,20 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
           cur_bits.push_back(tb_);
         }
         t.tslot = tb_;
-        if (g.control >= 0) { if (tix[g.control] >= 0) t.cbit_tile = tix[g.control]; else t.cpos_out = g.control; }
+        if (g.control >= 0) { if (tix[g.control] >= 0) t.cslot = tix[g.control]; else t.cpos_out = g.control; }
       } else {
+        uint32_t lmask = 0;
         for (int b = 0; b < n_local; ++b)
-          if ((g.mask >> b) & 1ull) { if (tix[b] >= 0) t.tmask |= 1u << tix[b]; else t.omask |= 1ull << b; }
+          if ((g.mask >> b) & 1ull) { if (tix[b] >= 0) lmask |= 1u << tix[b]; else t.omask |= 1ull << b; }
+        for (int q = 0; q < kb; ++q) if ((lmask >> q) & 1u) t.tmask ^= arow[q];     // parity over positions
       }
       for (int q = 0; q < 4; ++q) t.u[q] = make_double2(g.m[2 * q], g.m[2 * q + 1]);
-      if (g.kind == QAS_SV_U1 && g.m[0] == 0.0 && g.m[1] == 0.0 && g.m[6] == 0.0 && g.m[7] == 0.0 &&
-          g.m[2] == 1.0 && g.m[3] == 0.0 && g.m[4] == 1.0 && g.m[5] == 0.0)
-        t.kind = SV_K_SWAPX;        // PauliX / CNOT: exchange the pair, no flops
+      if (is_x) t.kind = SV_K_SWAPX;        // PauliX / CNOT with an outside control: exchange the pair, no flops
       tg.push_back(t);
       ++rel;
     }
     close_group(rel);
+    for (int q = 0; q < 16; ++q) ainv_of[bi][q] = q < kb ? (unsigned short)acol[q] : (unsigned short)0;
     first[bi + 1] = (int)tg.size();
     gfirst[bi + 1] = (int)groups.size();
   }
@@ -531,6 +591,9 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
     P.n_local = n_local; P.kb = kb; P.c = c; P.ngates = first[bi + 1] - first[bi];
     P.ngroups = gfirst[bi + 1] - gfirst[bi];
     for (int q = 0; q < kb; ++q) P.bits[q] = (unsigned char)blocks[bi].bits[q];
+    for (int q = 0; q < 16; ++q) P.ainv[q] = ainv_of[bi][q];
+    P.framed = framed_of[bi];
+    if (P.ngroups == 0 && !P.framed) continue;      // (cannot happen: a pass without gates)
     const size_t smem = (size_t)16 << kb;
     // stream-ordered: the copy waits for the previous pass's kernel, which still reads the old list
     SVCK(cudaMemcpyToSymbolAsync(c_sv_gates, tg.data() + first[bi], (size_t)P.ngates * sizeof(SvTileGate), 0, cudaMemcpyHostToDevice, st));
