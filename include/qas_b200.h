@@ -149,6 +149,17 @@ int qas_plan_passes_host(int n_qubits, uint32_t *ops, int num_ops, int gmax, int
                          uint32_t init_index, int swizzled, uint32_t *gdesc, int gdesc_words,
                          int *num_groups);
 
+/* Final-support descriptor of the H application (host run of the planner code the tape-compile
+ * kernel executes).  W = register subspace of the H blocking: w_rank <= 3 basis vectors in reduced
+ * echelon form (highest-bit pivots w_pivots ascending).  hdesc (>= 32 words) receives
+ * { ubar(init_index), dbar, X_0 .. X_{nu-1}, chk_0 .. chk_{nu-dbar-1} },  nu = n_qubits - w_rank:
+ * quotient coordinates (index with W's pivot bits removed after reduction by W) of a basis adapted to
+ * Dbar = image of the support span of the final state; dbar = nu means dense / not restricted.
+ * No reference counterpart (PennyLane applies every Hamiltonian term to the full state).        */
+int qas_plan_hsupport_host(int n_qubits, const uint32_t *ops, int num_ops, int init_kind,
+                           uint32_t init_index, int w_rank, const int *w_pivots,
+                           const uint32_t *w_basis, uint32_t *hdesc, int hdesc_words);
+
 /* Counters since context creation: evaluations and kernel launches; device time of the
  * last call's kernels (ms, CUDA events on the launch stream; host-pointer calls only) and of
  * the last evaluation kernel alone (any call; qas_get_stats waits for that kernel).         */

@@ -31,6 +31,9 @@ struct qas_ctx {
   WComb wc{};                      // register subspace W of the H-apply blocking (kernels.cuh)
   int num_classes = 0, C_real = 0, C_imag = 0;
   uint32_t *d_cdesc_plain = nullptr;
+  uint32_t *d_cdesc_u = nullptr;   // class representatives in quotient coordinates (support-restricted H application)
+  QasHInfo hinfo{};                // register subspace W for the planner's final-support descriptor
+  int hs_min = 1;                  // QAS_B200_HSPARSE: minimum log2 saving for the support-restricted path (0 = off)
   double *d_mout = nullptr; size_t cap_mout = 0;
   unsigned long long *d_phase = nullptr;   // QAS_B200_PHASE_CLOCKS=1: per-phase clock sums (diagnostic)
   bool stage_times = false;                // QAS_B200_STAGE_TIMES=1: print per-kernel stream times of every call
@@ -305,12 +308,16 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
     }
     std::vector<uint32_t> tmp;
     cx->num_classes = (int)(w_cost(W, xs, tmp) / 8);
+    cx->hinfo.RB = W.rank;
+    for (int q = 0; q < 3; ++q) { cx->hinfo.rb[q] = q < W.rank ? W.pv[q] : 0; cx->hinfo.wv[q] = q < W.rank ? W.v[q] : 0u; }
+    if (const char *hs = getenv("QAS_B200_HSPARSE")) cx->hs_min = std::max(0, atoi(hs));
+    cx->hinfo.enable = cx->hs_min > 0 && init_kind != QAS_INIT_PLUS && n_qubits >= 8 && n_qubits <= 13;
   }
   // Classes = cosets of W hit by the X masks; real (even nY) classes first, then imaginary ones.
   // Every class owns 2^RB table rows, one per jw (x = rho ^ wcomb[jw]); rows without a slice are
   // zero rows, so the kernel's class loop is fully static (no per-slice descriptor decoding).
   const int NBh = 1 << cx->RB;
-  std::vector<uint32_t> sx, cdesc_swz, cdesc_plain, tz;
+  std::vector<uint32_t> sx, cdesc_swz, cdesc_plain, cdesc_u, tz;
   std::vector<int> sbegin;
   std::vector<double> tc;
   auto swz = [](uint32_t i) { return qas_swz(i); };
@@ -322,6 +329,7 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
     for (uint32_t rho : reps) {
       cdesc_swz.push_back(swz(rho) << 4);
       cdesc_plain.push_back(rho << 4);
+      cdesc_u.push_back(qas_ubar(cx->hinfo, rho));
       for (int jw = 0; jw < NBh; ++jw) {
         const uint32_t x = rho ^ cx->wc.w[jw];
         sx.push_back(x);
@@ -367,6 +375,7 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   guard(cudaMalloc(&cx->d_vtab, sizeof(double) * dim * cx->S), "cudaMalloc sign tables");
   guard(cudaMalloc(&cx->d_sdesc, 4 * std::max<size_t>(cdesc_swz.size(), 1)), "cudaMalloc cdesc");
   guard(cudaMalloc(&cx->d_cdesc_plain, 4 * std::max<size_t>(cdesc_plain.size(), 1)), "cudaMalloc cdesc");
+  guard(cudaMalloc(&cx->d_cdesc_u, 4 * std::max<size_t>(cdesc_u.size(), 1)), "cudaMalloc cdesc");
   uint32_t *d_tz = nullptr, *d_sx = nullptr; double *d_tc = nullptr; int *d_sbegin = nullptr;
   guard(cudaMalloc(&d_sx, 4 * cx->S), "cudaMalloc sx");
   guard(cudaMalloc(&d_tz, 4 * tz.size()), "cudaMalloc tz");
@@ -377,6 +386,7 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
     guard(cudaMemcpy(d_sx, sx.data(), 4 * sx.size(), cudaMemcpyHostToDevice), "copy sx");
     guard(cudaMemcpy(cx->d_sdesc, cdesc_swz.data(), 4 * cdesc_swz.size(), cudaMemcpyHostToDevice), "copy cdesc");
     guard(cudaMemcpy(cx->d_cdesc_plain, cdesc_plain.data(), 4 * cdesc_plain.size(), cudaMemcpyHostToDevice), "copy cdesc");
+    guard(cudaMemcpy(cx->d_cdesc_u, cdesc_u.data(), 4 * cdesc_u.size(), cudaMemcpyHostToDevice), "copy cdesc");
     guard(cudaMemcpy(d_tz, tz.data(), 4 * tz.size(), cudaMemcpyHostToDevice), "copy tz");
     guard(cudaMemcpy(d_tc, tc.data(), 8 * tc.size(), cudaMemcpyHostToDevice), "copy tc");
     guard(cudaMemcpy(d_sbegin, sbegin.data(), 4 * sbegin.size(), cudaMemcpyHostToDevice), "copy sbegin");
@@ -395,7 +405,7 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
 extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   if (!ctx) return QAS_OK;
   cudaSetDevice(ctx->device);
-  cudaFree(ctx->d_counter); cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_cdesc_plain);
+  cudaFree(ctx->d_counter); cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_cdesc_plain); cudaFree(ctx->d_cdesc_u);
   cudaFree(ctx->d_U); cudaFree(ctx->d_dU); cudaFree(ctx->d_k); cudaFree(ctx->d_params);
   cudaFree(ctx->d_energy); cudaFree(ctx->d_grad); cudaFree(ctx->d_partial); cudaFree(ctx->d_dense);
   cudaFree(ctx->d_gstate); cudaFree(ctx->d_mout); cudaFree(ctx->d_tape); cudaFree(ctx->d_phase);
@@ -641,6 +651,8 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   {   // class descriptors and W combinations as byte offsets, swizzled for the shared-memory path
     const bool smem_path = ctx->n <= (want_grad ? 12 : 13) && !small;
     P.cdesc = smem_path ? ctx->d_sdesc : ctx->d_cdesc_plain;
+    P.cdesc_u = ctx->d_cdesc_u;
+    P.hs_min = smem_path ? ctx->hs_min : 0;
     for (int j = 0; j < 8; ++j) {
       const uint32_t w = ctx->wc.w[j];
       P.wc16.w[j] = (smem_path ? qas_swz(w) : w) << 4;
@@ -693,7 +705,8 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
       const uint32_t init_index = (ctx->init_kind == QAS_INIT_BASIS && !stc) ? qas_frame_map_basis(col, ctx->n, ctx->init_basis) : 0u;
       rec[0] = (uint32_t)nops; rec[1] = (uint32_t)stc; rec[2] = init_index;
       rec[3] = (uint32_t)qas_plan_groups(rec + QAS_REC_HDR, nops, ctx->GMAX, ctx->n, ctx->init_kind, init_index,
-                                         rec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS, swz_plan);
+                                         rec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS, swz_plan,
+                                         &ctx->hinfo, rec + qas_rec_hd_offset(P.ops_cap, ctx->n));
     }
     CK(cudaMemcpyAsync(ctx->d_tape, ctx->h_tape, words * 4, cudaMemcpyHostToDevice, st));
   } else {
@@ -705,11 +718,11 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     if (ops_smem) {
       CK(cudaFuncSetAttribute(compile_tapes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
       compile_tapes_kernel<true><<<(B + cthr - 1) / cthr, cthr, csm, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap, ctx->init_kind,
-                                                                         ctx->init_basis, ctx->GMAX, swz_plan, ctx->d_tape);
+                                                                         ctx->init_basis, ctx->GMAX, swz_plan, ctx->hinfo, ctx->d_tape);
     } else {
       CK(cudaFuncSetAttribute(compile_tapes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
       compile_tapes_kernel<false><<<(B + cthr - 1) / cthr, cthr, csm, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap, ctx->init_kind,
-                                                                          ctx->init_basis, ctx->GMAX, swz_plan, ctx->d_tape);
+                                                                          ctx->init_basis, ctx->GMAX, swz_plan, ctx->hinfo, ctx->d_tape);
     }
   }
   CK(cudaGetLastError());
@@ -803,6 +816,23 @@ extern "C" int qas_plan_passes_host(int n_qubits, uint32_t *ops, int num_ops, in
     return QAS_ERR_INVALID;
   if (gdesc && gdesc_words < num_ops * QAS_GD_STRIDE(n_qubits)) return QAS_ERR_NOMEM;
   *num_groups = qas_plan_groups(ops, num_ops, gmax, n_qubits, init_kind, init_index, gdesc, swizzled);
+  return QAS_OK;
+}
+
+extern "C" int qas_plan_hsupport_host(int n_qubits, const uint32_t *ops, int num_ops, int init_kind,
+                                      uint32_t init_index, int w_rank, const int *w_pivots,
+                                      const uint32_t *w_basis, uint32_t *hdesc, int hdesc_words) {
+  if ((num_ops > 0 && !ops) || num_ops < 0 || n_qubits < 1 || n_qubits > QAS_MAX_QUBITS || w_rank < 0 || w_rank > 3 ||
+      (w_rank > 0 && (!w_pivots || !w_basis)) || !hdesc)
+    return QAS_ERR_INVALID;
+  if (hdesc_words < QAS_HD_WORDS) return QAS_ERR_NOMEM;
+  QasHInfo hi{};
+  hi.RB = w_rank; hi.enable = 1;
+  for (int q = 0; q < w_rank; ++q) { hi.rb[q] = w_pivots[q]; hi.wv[q] = w_basis[q]; }
+  std::vector<uint32_t> tmp(ops, ops + (size_t)num_ops * QAS_OP_WORDS);
+  std::vector<uint32_t> gd((size_t)std::max(1, num_ops) * QAS_GD_STRIDE(n_qubits));
+  for (int w = 0; w < QAS_HD_WORDS; ++w) hdesc[w] = 0u;
+  qas_plan_groups(tmp.data(), num_ops, 2, n_qubits, init_kind, init_index, gd.data(), 0, &hi, hdesc);
   return QAS_OK;
 }
 

@@ -30,6 +30,8 @@ struct EvalParams {
   const GateTab *U;            // [NCONST + p*c]
   const double *vtab;          // [S][2^(n-RB)][2^RB] sign tables, coset-major (see "sign tables")
   const uint32_t *cdesc;       // [C_real + C_imag] class representatives rho as (swizzled) byte offsets
+  const uint32_t *cdesc_u;     // the same representatives in quotient coordinates, qas_ubar(rho)
+  int hs_min;                  // support-restricted H application when dbar + hs_min <= n - RB (0: never)
   int C_real, C_imag;          // X-mask classes with real / imaginary sign tables (real first)
   int rb0, rb1, rb2;           // ascending pivots of the register subspace W of the H-apply blocking
   WComb wc16;                  // byte offset of wcomb[j] = xor of the basis vectors of W selected by j
@@ -286,11 +288,14 @@ __device__ __forceinline__ void load_vrow(double (&v)[NB], const double *p, uint
 
 // ------------------------------------------------------------------------------ tape compile
 // One thread per circuit: runs the tape compiler and the pass planner (tape.h) and writes a record
-//   [nops, status, init_index, ngroups | ops[ops_cap][5] | gd[ops_cap][2 + n]]   (uint32)
+//   [nops, status, init_index, ngroups | ops[ops_cap][5] | gd[ops_cap][2 + n] | hd[QAS_HD_WORDS]]   (uint32)
 // to global memory.  Doing this in its own launch (B-way parallel) keeps the serial GF(2) work
 // out of the evaluation teams' critical path; the records stay L2-resident.
 #define QAS_REC_HDR 4
 __host__ __device__ __forceinline__ size_t qas_rec_words(int ops_cap, int n) {
+  return (size_t)QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS + (size_t)ops_cap * QAS_GD_STRIDE(n) + QAS_HD_WORDS;
+}
+__host__ __device__ __forceinline__ size_t qas_rec_hd_offset(int ops_cap, int n) {
   return (size_t)QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS + (size_t)ops_cap * QAS_GD_STRIDE(n);
 }
 // OPS_SMEM: the ops are built and planned in shared memory (the planner reads them back many
@@ -303,7 +308,7 @@ __host__ __device__ __forceinline__ size_t qas_compile_smem_words(int n, int ops
 template <bool OPS_SMEM>
 __global__ void compile_tapes_kernel(const int32_t *k, const qas_pool_entry *pool, int B, int p, int c,
                                      int n, int ops_cap, int init_kind, uint64_t init_basis,
-                                     int gmax, int swizzled, uint32_t *tape) {
+                                     int gmax, int swizzled, QasHInfo hinfo, uint32_t *tape) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = b < B;
   // GF(2) frame (col / row, indexed by wire at run time): shared memory, odd stride per thread
@@ -333,7 +338,8 @@ __global__ void compile_tapes_kernel(const int32_t *k, const qas_pool_entry *poo
     rec[1] = (uint32_t)st;
     rec[2] = init_index;
     rec[3] = (uint32_t)qas_plan_groups(ops, nops, gmax, n, init_kind, init_index,
-                                       rec + QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS, swizzled);   // passes per sweep
+                                       rec + QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS, swizzled,   // passes per sweep
+                                       &hinfo, rec + qas_rec_hd_offset(ops_cap, n));
   }
   if constexpr (OPS_SMEM) {
     __syncwarp();
@@ -452,6 +458,7 @@ __device__ __forceinline__ void reduce_store_m(double (&acc)[8], int lane, uint3
 //   psi [DIM] double2 | lam [DIM] double2 (GRAD) | rec [4 + ops_cap*5] u32
 //   | gd [ops_cap][2 + n] u16 (shared-memory path; the global-memory path reads the u32 record)
 //   | Us [ops_cap][4] double2 (STAGE_U) | red [2][3][WPT][8] f64 (GRAD, multi-warp teams) | ered [WPT] f64
+//   | hx [QAS_HD_WORDS] u32 + tcls [32] u32 (shared-memory path: final-support descriptor, class coset ids)
 __host__ __device__ constexpr bool qas_stage_u(int N) { return N == 0 || N >= 7; }
 __host__ __device__ inline size_t eval_team_smem_bytes(int n, int T, bool grad, int ops_cap,
                                                        bool state_in_smem, bool stage_u) {
@@ -465,6 +472,7 @@ __host__ __device__ inline size_t eval_team_smem_bytes(int n, int T, bool grad, 
   if (grad && wpt > 1) b += (size_t)2 * 3 * wpt * 64;
   b += (((size_t)wpt * 8) + 15) & ~(size_t)15;
   b += 16;                                   // the team's work-queue slot
+  if (state_in_smem) b += (size_t)(QAS_HD_WORDS + 32) * 4;
   return b;
 }
 
@@ -639,6 +647,9 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
   double *ered = reinterpret_cast<double *>(base);
   base += (((size_t)WPT * 8) + 15) & ~(size_t)15;
   int *bslot = reinterpret_cast<int *>(base);
+  base += 16;
+  uint32_t *hx = reinterpret_cast<uint32_t *>(base);      // N != 0 only
+  uint32_t *tcls = hx + QAS_HD_WORDS;
   // slice descriptors, shared by the CTA's teams
   uint32_t *sdesc = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TEAMS * team_bytes);
   for (int s = threadIdx.x; s < P.C_real + P.C_imag; s += BLK) sdesc[s] = P.cdesc[s];
@@ -665,6 +676,8 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
         const uint32_t *ggd = grec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS;
         const int gused = (int)grec[3] * gstride;
         for (int w = tid; w < gused; w += T) gd16[w] = (uint16_t)ggd[w];
+        const uint32_t *ghd = grec + qas_rec_hd_offset(P.ops_cap, n);
+        for (int w = tid; w < QAS_HD_WORDS; w += T) hx[w] = ghd[w];
       }
       const double amp0 = (P.init_kind == QAS_INIT_PLUS) ? exp2(-0.5 * (double)n) : 0.0;
       for (uint32_t i = tid; i < DIM; i += T) psi[i] = make_double2(amp0, 0.0);
@@ -720,6 +733,62 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
       constexpr int NB = 1 << RB;
       const uint32_t nrest = DIM >> RB;
       const char *psib = reinterpret_cast<const char *>(psi);
+      const int C = P.C_real + P.C_imag;
+      // own amplitudes of coset sb16: energy contribution and lambda
+      auto finish = [&](uint32_t sb16, const double2 (&acc)[NB]) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const uint32_t off = sb16 ^ P.wc16.w[j];
+          const double2 ai = *reinterpret_cast<const double2 *>(psib + off);
+          e_part = fma(ai.x, acc[j].x, fma(ai.y, acc[j].y, e_part));
+          if constexpr (GRAD) *reinterpret_cast<double2 *>(reinterpret_cast<char *>(lam) + off) = acc[j];
+        }
+      };
+      bool sparse = false;
+      constexpr bool HSPARSE = N >= 8;      // below that the whole register fits a few warp iterations
+      if constexpr (HSPARSE) sparse = P.hs_min > 0 && C <= 32 && (int)hx[1] + P.hs_min <= N - RB;
+      if (sparse) {
+        // Support-restricted application (tape.h, "Support of the FINAL state"): the cosets are walked in
+        // the basis adapted to Dbar, so coset u(t) only hears from the classes whose Dbar-coset id equals
+        // t >> dbar -- every other partner coset holds zeros.  Whole warps share t >> dbar when
+        // dbar >= log2(lanes), so the skipped classes cost neither loads nor issue slots.
+        if constexpr (HSPARSE) {
+          constexpr int NU = N - RB;
+          const int dbar = (int)hx[1], nchk = NU - dbar;
+          for (int cls = tid; cls < C; cls += T) {
+            const uint32_t ru = P.cdesc_u[cls];
+            uint32_t tau = 0;
+            for (int i = 0; i < nchk; ++i) tau |= (uint32_t)(__popc(ru & hx[2 + NU + i]) & 1) << i;
+            tcls[cls] = tau;
+          }
+          team_sync<T>(team, tmask);
+          for (uint32_t t = tid; t < nrest; t += T) {
+            uint32_t u = hx[0];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) u ^= ((t >> i) & 1u) ? hx[2 + i] : 0u;
+            const uint32_t tau_u = t >> dbar;
+            const uint32_t sb16 = sw<SWZ>(qas_deposit_rest(u, RB, P.rb0, P.rb1, P.rb2)) << 4;
+            double2 acc[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) acc[j] = make_double2(0.0, 0.0);
+            const double *vp = P.vtab + (size_t)u * (NB >= 2 ? 2 : 1);
+            for (int cls = 0; cls < C; ++cls) {
+              if (tcls[cls] != tau_u) continue;
+              const uint32_t r16 = sb16 ^ sdesc[cls];
+              double v[NB][NB];
+#pragma unroll
+              for (int jw = 0; jw < NB; ++jw) load_vrow<NB>(v[jw], vp + ((size_t)(cls * NB + jw) << n), nrest);
+              double2 a[NB];
+#pragma unroll
+              for (int j = 0; j < NB; ++j) a[j] = *reinterpret_cast<const double2 *>(psib + (r16 ^ P.wc16.w[j]));
+              const bool imag = cls >= P.C_real;
+#pragma unroll
+              for (int jw = 0; jw < NB; ++jw) hacc_row<NB>(acc, a, v[jw], jw, imag);
+            }
+            finish(sb16, acc);
+          }
+        }
+      } else {
       for (uint32_t u = tid; u < nrest; u += T) {
         const uint32_t sb16 = sw<SWZ>(qas_deposit_rest(u, RB, P.rb0, P.rb1, P.rb2)) << 4;
         double2 acc[NB];
@@ -731,7 +800,6 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
         double ring[PD][NB];
 #pragma unroll
         for (int d = 0; d < PD; ++d) load_vrow<NB>(ring[d], vp + ((size_t)d << n), nrest);
-        const int C = P.C_real + P.C_imag;
         for (int cls = 0; cls < C; ++cls) {
           const uint32_t r16 = sb16 ^ sdesc[cls];
           double2 a[NB];
@@ -748,13 +816,8 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
           }
           vp += (size_t)NB << n;
         }
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const uint32_t off = sb16 ^ P.wc16.w[j];
-          const double2 ai = *reinterpret_cast<const double2 *>(psib + off);
-          e_part = fma(ai.x, acc[j].x, fma(ai.y, acc[j].y, e_part));
-          if constexpr (GRAD) *reinterpret_cast<double2 *>(reinterpret_cast<char *>(lam) + off) = acc[j];
-        }
+        finish(sb16, acc);
+      }
       }
     }
 #pragma unroll

@@ -281,9 +281,33 @@ QAS_HD bool qas_tab_add_lsb(const QasPivTab<NQ> &a, QasPivTab<NQ> &b, bool into_
   return placed;
 }
 
+// (3) Support of the FINAL state, for the H application.  The evaluation kernel blocks lambda = H psi
+// over cosets of a register subspace W (kernels.cuh, "sign tables"): coset u (n - RB bits, the index
+// with W's pivot bits removed) receives from X-mask class rho only if psi is non-zero somewhere on
+// coset u ^ rho, i.e. iff  u ^ rho ^ ubar(b0)  lies in Dbar = image of D in the quotient by W.  The
+// planner hands the kernel a basis of the quotient space adapted to Dbar,
+//     hd = { ubar(b0), dbar, X_0 .. X_{nu-1}, chk_0 .. chk_{nu-dbar-1} }          (nu = n - RB)
+// X_0..X_{dbar-1} = reduced echelon basis of Dbar (highest-bit pivots, ascending: X_i only touches
+// bits <= its pivot, so the low counter bits -- the lanes -- stay on neighbouring table entries),
+// X_dbar.. = the unit vectors of the non-pivot positions.  Enumerating u(t) = ubar(b0) ^ xor of the
+// X_i selected by t, the Dbar-coset of u is t >> dbar, and the Dbar-coset of a class representative
+// is read off its parities with the check masks chk_i.  dbar = nu means "dense: no restriction".
+#define QAS_HD_WORDS 32
+struct QasHInfo {
+  int RB, enable;
+  int rb[3];           // ascending pivots of W
+  uint32_t wv[3];      // basis of W in reduced echelon form (wv[q] has pivot rb[q])
+};
+QAS_HD uint32_t qas_ubar(const QasHInfo &hi, uint32_t x) {
+  for (int q = 0; q < hi.RB; ++q) if ((x >> hi.rb[q]) & 1u) x ^= hi.wv[q];
+  for (int q = hi.RB - 1; q >= 0; --q) x = ((x >> (hi.rb[q] + 1)) << hi.rb[q]) | (x & ((1u << hi.rb[q]) - 1u));
+  return x;
+}
+
 template <int NQ>
 QAS_HD void qas_plan_supports(const uint32_t *ops, int nops, int ngroups, int n, int init_kind,
-                              uint32_t init_index, uint32_t *gd, int swizzled) {
+                              uint32_t init_index, uint32_t *gd, int swizzled,
+                              const QasHInfo *hi = nullptr, uint32_t *hd = nullptr) {
   QasPivTab<NQ> D;
   D.clear();
   if (init_kind == QAS_INIT_PLUS) {
@@ -346,13 +370,54 @@ QAS_HD void qas_plan_supports(const uint32_t *ops, int nops, int ngroups, int n,
     if (g > 1) qas_tab_add_msb<NQ>(D, m1);
     if (g > 2) qas_tab_add_msb<NQ>(D, m2);
   }
+  if (!hd) return;
+  const int nu = n - (hi ? hi->RB : 0);
+  hd[0] = 0u;
+  hd[1] = (uint32_t)nu;                           // dense unless shown otherwise
+  if (!hi || !hi->enable || nu > NQ || 2 + 2 * nu > QAS_HD_WORDS) return;
+  int drank = 0;
+#pragma unroll
+  for (int p = 0; p < NQ; ++p) drank += D.v[p] ? 1 : 0;
+  if (drank >= n) return;                         // the final state is dense
+  QasPivTab<NQ> E;
+  E.clear();
+  int dbar = 0;
+#pragma unroll
+  for (int p = 0; p < NQ; ++p)
+    if (D.v[p]) dbar += qas_tab_add_msb<NQ>(E, qas_ubar(*hi, D.v[p])) ? 1 : 0;
+  if (dbar >= nu) return;
+  // reduced echelon form: clear every pivot bit from the other basis vectors (ascending pivots, so the
+  // vector xor-ed in is already free of lower pivot bits)
+#pragma unroll
+  for (int p = 0; p < NQ; ++p)
+    if (E.v[p]) {
+#pragma unroll
+      for (int p2 = 0; p2 < NQ; ++p2)
+        if (p2 > p && ((E.v[p2] >> p) & 1u)) E.v[p2] ^= E.v[p];
+    }
+  hd[0] = qas_ubar(*hi, b0);
+  hd[1] = (uint32_t)dbar;
+  int cnt = 0;
+#pragma unroll
+  for (int p = 0; p < NQ; ++p) if (p < nu && E.v[p]) hd[2 + cnt++] = E.v[p];
+#pragma unroll
+  for (int p = 0; p < NQ; ++p) if (p < nu && !E.v[p]) hd[2 + cnt++] = 1u << p;
+  int kc = 0;
+#pragma unroll
+  for (int f = 0; f < NQ; ++f)
+    if (f < nu && !E.v[f]) {
+      uint32_t chk = 1u << f;
+#pragma unroll
+      for (int p = 0; p < NQ; ++p) if (E.v[p] && ((E.v[p] >> f) & 1u)) chk |= 1u << p;
+      hd[2 + nu + kc++] = chk;
+    }
 }
 
 // Returns the number of groups.  gd receives one descriptor of QAS_GD_STRIDE(n) words per group,
 // in TAPE order of the groups (may be null: grouping only).  swizzled: the statevector lives in
 // shared memory; descriptors and the ops' xor masks are then written in slot coordinates.
 QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax, int n, int init_kind, uint32_t init_index,
-                           uint32_t *gd, int swizzled) {
+                           uint32_t *gd, int swizzled, const QasHInfo *hi = nullptr, uint32_t *hd = nullptr) {
   int ngroups = 0;
   for (int j = 0; j < nops;) {
     uint32_t *a = ops + (size_t)j * QAS_OP_WORDS;
@@ -376,10 +441,10 @@ QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax, int n, int init_ki
     ++ngroups;
   }
   if (!gd) return ngroups;
-  if (n <= 5) qas_plan_supports<5>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled);
-  else if (n <= 8) qas_plan_supports<8>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled);
-  else if (n <= 12) qas_plan_supports<12>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled);
-  else qas_plan_supports<QAS_MAX_QUBITS>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled);
+  if (n <= 5) qas_plan_supports<5>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
+  else if (n <= 8) qas_plan_supports<8>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
+  else if (n <= 12) qas_plan_supports<12>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
+  else qas_plan_supports<QAS_MAX_QUBITS>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
   if (swizzled)
     for (int j = 0; j < nops; ++j) {
       uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;

@@ -243,6 +243,37 @@ def test_baseline_size_properties_lih():
         assert abs(e[b] - sim.energy(n, k, pool.pool, params, LiH.terms(), LiH.init_state)) <= E_TOL
 
 
+@pytest.mark.parametrize("cfg", ["lih_10q", "h2o_8q"])
+def test_support_restricted_h_application_equals_dense(cfg, monkeypatch):
+    """The support-restricted H application (planner descriptor + per-coset class skipping) only
+    leaves out exact zeros: energies and gradients equal the dense application's on the same batch
+    (both against the oracle on a sample, and against each other on the whole batch)."""
+    from qas_b200.evaluator import BatchEvaluator
+    name, n, p, mkpool, lim = helpers.CONFIGS[cfg]
+    model = helpers.get_model(name)
+    pool = mkpool()
+    # shallow circuits too, so that many different support dimensions occur
+    outs = {}
+    for hs in ("0", "1"):
+        monkeypatch.setenv("QAS_B200_HSPARSE", hs)
+        ev = BatchEvaluator(n, model.terms(), pool, init=model.init_state)
+        res = []
+        for depth, seed in ((p, 5), (max(4, p // 3), 6), (3, 7)):
+            params = np.random.default_rng(seed).standard_normal((depth, len(pool), 3))
+            ks = sample_structure_lists(pool, depth, {"CNOT": depth // 2}, 2048, seed=seed)
+            res.append((ks, params, ev.evaluate(ks, params, want_grad=True, dense=True, compact=True)))
+        outs[hs] = res
+        ev.close()
+    for (ks, params, a), (_, _, b) in zip(outs["0"], outs["1"]):
+        assert np.max(np.abs(a["energy"] - b["energy"])) <= 1e-12
+        assert np.max(np.abs(a["grad_compact"] - b["grad_compact"])) <= 1e-12
+        assert np.max(np.abs(a["grad_dense"] - b["grad_dense"])) <= 1e-12
+        for bi in range(0, 2048, 512):
+            k = [int(x) for x in ks[bi]]
+            e = sim.energy(n, k, pool.pool, params, model.terms(), model.init_state)
+            assert abs(b["energy"][bi] - e) <= 1e-9
+
+
 def test_linearity_in_hamiltonian():
     """E_{H1+H2} = E_{H1} + E_{H2} for the same circuits (X-mask grouping must not mix terms)."""
     from qas_b200.qml_models.qml_models_legacy import H2O

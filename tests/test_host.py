@@ -209,3 +209,83 @@ def test_legality_rules_clifford_t():
     st3 = st2.takeAction(key("Hadamard", [1]))
     assert key("Hadamard", [1]) not in st3.getLegalActions()
     assert key("CNOT", [0, 1]) in st3.getLegalActions()   # last op on qubit 1 is no longer the CNOT
+
+
+def _par(x):
+    return bin(int(x)).count("1") & 1
+
+
+def test_final_support_descriptor_of_the_h_application():
+    """qas_plan_hsupport_host (the planner code behind the support-restricted H application): the
+    descriptor's vectors form a basis of the quotient space adapted to Dbar, the check masks read the
+    Dbar-coset id, and the oracle's final state has no amplitude outside ubar(b0) ^ Dbar."""
+    import ctypes
+    from qas_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    restricted = 0
+    for trial in range(40):
+        n = [8, 9, 10][trial % 3]
+        pool = helpers.near_cx_pool(n)
+        p = int(rng.integers(4, 14))
+        init = ("zero", 0) if trial % 4 else ("basis", int(rng.integers(0, 1 << n)))
+        k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": p // 2}, 1, seed=100 + trial)[0]]
+        ops, idx = compile_tape_host(n, pool, k, init[1] if init[0] == "basis" else 0)
+        # a register subspace W in reduced echelon form (highest-bit pivots ascending)
+        rb_count = int(rng.integers(0, 4))
+        W = []
+        while len(W) < rb_count:
+            x = int(rng.integers(1, 1 << n))
+            for pv, v in W:
+                if (x >> pv) & 1:
+                    x ^= v
+            if not x:
+                continue
+            pv = x.bit_length() - 1
+            W = [(q, v ^ x if (v >> pv) & 1 else v) for q, v in W] + [(pv, x)]
+        W.sort()
+        piv = np.array([pv for pv, _ in W] + [0] * (3 - len(W)), dtype=np.int32)
+        wv = np.array([v for _, v in W] + [0] * (3 - len(W)), dtype=np.uint32)
+        hd = np.zeros(32, dtype=np.uint32)
+        opsc = np.ascontiguousarray(ops, dtype=np.uint32)
+        rc = lib.qas_plan_hsupport_host(n, opsc.ctypes.data, len(opsc), 1 if init[0] == "basis" else 0, int(idx),
+                                        rb_count, piv.ctypes.data, wv.ctypes.data, hd.ctypes.data, 32)
+        assert rc == 0
+        nu = n - rb_count
+        dbar = int(hd[1])
+        assert 0 <= dbar <= nu
+
+        def ubar(x):
+            for pv, v in W:
+                if (x >> pv) & 1:
+                    x ^= v
+            for pv, _ in reversed(W):
+                x = ((x >> (pv + 1)) << pv) | (x & ((1 << pv) - 1))
+            return x
+
+        st = sim.run(n, sim.lower(k, pool.pool, rng.standard_normal((p, len(pool), 3))), init).reshape(-1)
+        support = [i for i in range(1 << n) if abs(st[i]) > 1e-14]
+        if dbar == nu:
+            continue          # dense: nothing claimed
+        restricted += 1
+        X = [int(x) for x in hd[2:2 + nu]]
+        chk = [int(x) for x in hd[2 + nu:2 + 2 * nu - dbar]]
+        # the X's are a basis: 2^nu distinct xor-combinations
+        span = {0}
+        for x in X:
+            span |= {s ^ x for s in span}
+        assert len(span) == 1 << nu
+        # Dbar part only touches bits <= its pivot, pivots ascending
+        pivs = [x.bit_length() - 1 for x in X[:dbar]]
+        assert pivs == sorted(pivs) and len(set(pivs)) == dbar
+        # check masks: zero on Dbar, delta on the completion vectors
+        for i, c_ in enumerate(chk):
+            assert all(_par(c_ & x) == 0 for x in X[:dbar])
+            assert [_par(c_ & x) for x in X[dbar:]] == [int(j == i) for j in range(nu - dbar)]
+        # every amplitude of the final state sits on a coset u with u ^ ubar(b0) in Dbar
+        dspan = {0}
+        for x in X[:dbar]:
+            dspan |= {s ^ x for s in dspan}
+        assert int(hd[0]) == ubar(int(idx))
+        assert all((ubar(i) ^ int(hd[0])) in dspan for i in support)
+    assert restricted >= 10
