@@ -535,14 +535,20 @@ __device__ __forceinline__ void adj_group(double2 *psi, double2 *lam, const uint
       for (int e = 0; e < 8; ++e) M[q][e] = 0.0;
   }
   const uint32_t rc = (G == 1) ? o[2] : 0u;
-  const uint32_t nper = DIM >> G;
+  // Only the first 2^dc cosets are visited.  psi is zero outside them, and lambda is not needed there
+  // either: the derivative of gate g pairs lambda_g with dU_g psi_{g-1}, which lives on the support
+  // of psi_g, and lambda_{g-1} = U_g^ lambda_g on the (smaller) support of psi_{g-1} only reads
+  // lambda_g inside the support of psi_g.  So lambda, like psi, is propagated inside the shrinking
+  // support and whatever it holds outside is never read again.  (The bound is rounded up to whole
+  // warps / teams so that the shuffles below see uniform trip counts.)
+  const uint32_t nper = min(DIM >> G, (gg.nsup + (uint32_t)(TW - 1)) & ~(uint32_t)(TW - 1));
   constexpr int UNR = EACH ? 1 : ((4 >> G) > 0 ? (4 >> G) : 1);
 #pragma unroll UNR
   for (uint32_t t = tid; t < nper; t += T) {
     const uint32_t P = gg.base(t);
     if (G == 1 && rc && !(__popc(sw<SWZ>(P) & rc) & 1)) continue;   // rc is a mask over index bits
-    // psi is zero outside the first 2^dc cosets: only lambda is propagated there.  wins: some lane
-    // of this warp is inside (warp-uniform for whole-warp teams; sub-warp teams always reduce)
+    // ins: this coset is inside the support (the rounding above admits a few that are not).  wins: some
+    // lane of this warp is inside (warp-uniform for whole-warp teams; sub-warp teams always reduce)
     const bool ins = t < gg.nsup;
     const bool wins = T < 32 || (t & ~31u) < gg.nsup;
     double2 a[1 << G], l[1 << G];
@@ -749,9 +755,10 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
       if constexpr (HSPARSE) sparse = P.hs_min > 0 && C <= 32 && (int)hx[1] + P.hs_min <= N - RB;
       if (sparse) {
         // Support-restricted application (tape.h, "Support of the FINAL state"): the cosets are walked in
-        // the basis adapted to Dbar, so coset u(t) only hears from the classes whose Dbar-coset id equals
-        // t >> dbar -- every other partner coset holds zeros.  Whole warps share t >> dbar when
-        // dbar >= log2(lanes), so the skipped classes cost neither loads nor issue slots.
+        // the basis adapted to Dbar.  Coset u(t) only hears from the classes whose Dbar-coset id equals
+        // t >> dbar (every other partner coset holds zeros), and lambda = H psi is only needed ON the
+        // support (energy = <psi|lambda>; the adjoint sweep never leaves it, see adj_group): the cosets
+        // t < 2^dbar, from the classes with id 0.
         if constexpr (HSPARSE) {
           constexpr int NU = N - RB;
           const int dbar = (int)hx[1], nchk = NU - dbar;
@@ -766,14 +773,21 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
             uint32_t u = hx[0];
 #pragma unroll
             for (int i = 0; i < NU; ++i) u ^= ((t >> i) & 1u) ? hx[2 + i] : 0u;
-            const uint32_t tau_u = t >> dbar;
             const uint32_t sb16 = sw<SWZ>(qas_deposit_rest(u, RB, P.rb0, P.rb1, P.rb2)) << 4;
             double2 acc[NB];
 #pragma unroll
             for (int j = 0; j < NB; ++j) acc[j] = make_double2(0.0, 0.0);
+            if (t >> dbar) {         // outside the support: lambda is never read there (adj_group); keep it defined
+              if constexpr (GRAD) {
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                  *reinterpret_cast<double2 *>(reinterpret_cast<char *>(lam) + (sb16 ^ P.wc16.w[j])) = acc[j];
+              }
+              continue;
+            }
             const double *vp = P.vtab + (size_t)u * (NB >= 2 ? 2 : 1);
             for (int cls = 0; cls < C; ++cls) {
-              if (tcls[cls] != tau_u) continue;
+              if (tcls[cls] != 0u) continue;
               const uint32_t r16 = sb16 ^ sdesc[cls];
               double v[NB][NB];
 #pragma unroll

@@ -218,10 +218,11 @@ def run_tape_planned(n, ops, gds, init, init_index, pool, c, params, terms, want
                 # the planner's claim: nothing lives outside the first 2^dc cosets.  Forward sweep:
                 # exactly zero (never written).  Adjoint sweep: un-applying a gate leaves rounding
                 # residue where the support shrank; it is never read again.
+                # lambda is not propagated outside either: every later (earlier-in-time) gate only
+                # reads it inside its own, smaller support (kernels.cuh adj_group).
                 tol = 1e-13 if adjoint else 0.0
                 assert all(abs(psi[s_]) <= tol for s_ in slots), "amplitude outside the tracked support"
-                if not adjoint:
-                    continue
+                continue
             if rc and not _parity(P & rc):
                 continue
             a = [psi[s_] for s_ in slots]
@@ -273,6 +274,16 @@ def run_tape_planned(n, ops, gds, init, init_index, pool, c, params, terms, want
         lam += coeff * (1j ** ny) * np.where(par(jx & z) == 1, -1.0, 1.0) * psi[jx]
     energy = float(np.vdot(psi, lam).real)
     grads = {}
+    if want_grad and groups and (int(ops[groups[0][0]][4]) >> 16) & 0xF == 0:
+        # the kernel computes lambda only on the support of the final state: poison the rest
+        j0, g0 = groups[0]
+        Ps, xm, nsup = group_cosets(n, [ops[j0 + q] for q in range(g0)], gds[0], swizzled)
+        inside = np.zeros(dim, dtype=bool)
+        for t, P in enumerate(Ps):
+            if t < nsup:
+                for x in xm:
+                    inside[P ^ x] = True
+        lam = np.where(inside, lam, 1.0e3 * (1.0 + 1.0j))
     if want_grad:
         for gi in range(len(groups)):
             if apply_group(gi, True, lam, grads):
