@@ -158,6 +158,7 @@ static int team_threads_for(int n, int shift) {
   const int t = team_threads(n);
   // QAS_B200_TEAM_SHIFT=1: the doubled team in a 256-thread CTA (compiled for n = 8..11, see launch_eval)
   if (shift > 0 && n >= 8 && n <= 11) return t * 2;
+  if (shift < 0 && (n == 10 || n == 9)) return 32;      // QAS_B200_TEAM_SHIFT=-1: one warp per circuit, no team barriers
   return t;
 }
 
@@ -275,6 +276,8 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   const bool want_phase = getenv("QAS_B200_PHASE_CLOCKS") && atoi(getenv("QAS_B200_PHASE_CLOCKS")) != 0;
   cx->T = team_threads_for(n_qubits, cx->team_shift);
   cx->blk = cx->team_shift > 0 ? 256 : team_blk(n_qubits);
+  if (cx->team_shift < 0 && n_qubits == 10) cx->blk = 64;
+  if (cx->team_shift < 0 && n_qubits == 9) cx->blk = 128;
   cx->GMAX = qas_gmax(n_qubits <= 13 ? n_qubits : 20, cx->T);
   cx->RB = qas_hrb(n_qubits <= 13 ? n_qubits : 20, cx->T);
   cx->PD = qas_hpd(n_qubits <= 13 ? n_qubits : 20, cx->T);
@@ -537,15 +540,20 @@ static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
     }
   }
   const int nmax_smem = GRAD ? 12 : 13;
-  const int T = ctx->T;
+  int T = ctx->T, blk = ctx->blk;
+  // energy-only launches at n = 10: one warp per circuit (no team barriers; same GMAX / RB / PD, so tapes
+  // and sign tables are shared with the gradient launches).  LiH reward-only 72 -> 84 M evals/s; the
+  // gradient kernel is slower that way (1.15 -> 1.44 ms: the dense tail of the batch runs on one warp).
+  if (!GRAD && P.n == 10 && ctx->team_shift == 0 && T == 64 && blk == 128) { T = 32; blk = 64; }
   if (P.n <= nmax_smem) {
-    const size_t smem = eval_team_smem_bytes(P.n, T, GRAD, P.ops_cap, true, qas_stage_u(P.n)) * (ctx->blk / T) + sdesc_bytes(P.C_real + P.C_imag);
+    const size_t smem = eval_team_smem_bytes(P.n, T, GRAD, P.ops_cap, true, qas_stage_u(P.n)) * (blk / T) + sdesc_bytes(P.C_real + P.C_imag);
     if (smem <= 227 * 1024) {
 #define QAS_CASE(N_, T_, BLK_) \
-  if (P.n == N_ && T == T_ && ctx->blk == BLK_) return launch_smem<N_, T_, GRAD, qas_hrb(N_, T_), qas_hpd(N_, T_), 0, 0, BLK_>(ctx, P, st);
+  if (P.n == N_ && T == T_ && blk == BLK_) return launch_smem<N_, T_, GRAD, qas_hrb(N_, T_), qas_hpd(N_, T_), 0, 0, BLK_>(ctx, P, st);
       QAS_CASE(2, 8, 256) QAS_CASE(3, 8, 256) QAS_CASE(4, 8, 256) QAS_CASE(5, 16, 256) QAS_CASE(6, 32, 256)
       QAS_CASE(7, 32, 256) QAS_CASE(8, 32, 256) QAS_CASE(9, 64, 256) QAS_CASE(10, 64, 128) QAS_CASE(11, 128, 128)
       QAS_CASE(12, 256, 256)
+      QAS_CASE(10, 32, 64) QAS_CASE(9, 32, 128)                                                    // QAS_B200_TEAM_SHIFT=-1
       QAS_CASE(8, 64, 256) QAS_CASE(9, 128, 256) QAS_CASE(10, 128, 256) QAS_CASE(11, 256, 256)     // QAS_B200_TEAM_SHIFT=1
 #undef QAS_CASE
       if constexpr (!GRAD) { if (P.n == 13 && T == 256) return launch_smem<13, 256, false, qas_hrb(13, 256), qas_hpd(13, 256)>(ctx, P, st); }

@@ -204,6 +204,15 @@ QAS_HD int qas_compile_circuit(const int32_t *k, int p, const qas_pool_entry *po
 // The X_i are put in lowest-set-bit echelon form of their (swizzled) shared-memory slot index and
 // sorted by pivot, so that the three lane bits of a quarter-warp get independent low address bits
 // whenever the subspace allows it (bank conflicts).  Uniform initial state: D is everything.
+// Loops over the pivot tables: unrolled, so that the tables live in registers.  Measured alternative
+// (-DQAS_PLAN_ROLLED: tables in local memory, 4k instead of 63k instructions in the tape-compile kernel):
+// compile time LiH-10q 0.21 -> 0.56 ms per 65536 circuits -- the local-memory round trips cost more than
+// the instruction-fetch stalls of the unrolled code.
+#if defined(QAS_PLAN_ROLLED)
+#define QAS_PUNROLL _Pragma("unroll 1")
+#else
+#define QAS_PUNROLL _Pragma("unroll")
+#endif
 #define QAS_META_GFIRST(m) (((m) >> 24) & 3u)
 #define QAS_META_GLAST(m) (((m) >> 26) & 3u)
 #define QAS_GD_HDR 2        // P0, dc
@@ -248,7 +257,7 @@ template <int NQ>
 struct QasPivTab {
   uint32_t v[NQ];
   QAS_HD void clear() {
-#pragma unroll
+QAS_PUNROLL
     for (int p = 0; p < NQ; ++p) v[p] = 0u;
   }
 };
@@ -256,7 +265,7 @@ struct QasPivTab {
 template <int NQ>
 QAS_HD bool qas_tab_add_msb(QasPivTab<NQ> &t, uint32_t x) {
   bool placed = false;
-#pragma unroll
+QAS_PUNROLL
   for (int p = NQ - 1; p >= 0; --p) {
     if (!placed && ((x >> p) & 1u)) {
       if (t.v[p]) x ^= t.v[p];
@@ -270,7 +279,7 @@ QAS_HD bool qas_tab_add_msb(QasPivTab<NQ> &t, uint32_t x) {
 template <int NQ>
 QAS_HD bool qas_tab_add_lsb(const QasPivTab<NQ> &a, QasPivTab<NQ> &b, bool into_b, QasPivTab<NQ> &a_mut, uint32_t x) {
   bool placed = false;
-#pragma unroll
+QAS_PUNROLL
   for (int p = 0; p < NQ; ++p) {
     if (!placed && ((x >> p) & 1u)) {
       const uint32_t v = a.v[p] ? a.v[p] : b.v[p];
@@ -311,7 +320,7 @@ QAS_HD void qas_plan_supports(const uint32_t *ops, int nops, int ngroups, int n,
   QasPivTab<NQ> D;
   D.clear();
   if (init_kind == QAS_INIT_PLUS) {
-#pragma unroll
+QAS_PUNROLL
     for (int p = 0; p < NQ; ++p) if (p < n) D.v[p] = 1u << p;
   }
   const uint32_t b0 = (init_kind == QAS_INIT_BASIS) ? init_index : 0u;
@@ -343,28 +352,28 @@ QAS_HD void qas_plan_supports(const uint32_t *ops, int nops, int ngroups, int n,
     Sin.clear();
     Sout.clear();
     int dc = 0, tot = 0, drank = 0;
-#pragma unroll
+QAS_PUNROLL
     for (int p = 0; p < NQ; ++p) drank += D.v[p] ? 1 : 0;
     if (drank == n) {     // the state is dense already: every coset is inside, one echelon pass
-#pragma unroll
+QAS_PUNROLL
       for (int p = 0; p < NQ; ++p)
         if (p < n) dc += qas_tab_add_lsb<NQ>(Sin, Sout, false, Sin, proj(1u << p)) ? 1 : 0;
       tot = dc;
     } else {
-#pragma unroll
+QAS_PUNROLL
       for (int p = 0; p < NQ; ++p)
         if (D.v[p]) dc += qas_tab_add_lsb<NQ>(Sin, Sout, false, Sin, proj(D.v[p])) ? 1 : 0;
       tot = dc;
-#pragma unroll
+QAS_PUNROLL
       for (int p = 0; p < NQ; ++p)
         if (p < n && tot < n - g) tot += qas_tab_add_lsb<NQ>(Sin, Sout, true, Sin, proj(1u << p)) ? 1 : 0;
     }
     d[0] = proj(b0);
     d[1] = (uint32_t)dc;
     int cnt = 0;
-#pragma unroll
+QAS_PUNROLL
     for (int p = 0; p < NQ; ++p) if (Sin.v[p]) d[QAS_GD_HDR + cnt++] = Sin.v[p];
-#pragma unroll
+QAS_PUNROLL
     for (int p = 0; p < NQ; ++p) if (Sout.v[p]) d[QAS_GD_HDR + cnt++] = Sout.v[p];
     qas_tab_add_msb<NQ>(D, m0);
     if (g > 1) qas_tab_add_msb<NQ>(D, m1);
@@ -376,38 +385,38 @@ QAS_HD void qas_plan_supports(const uint32_t *ops, int nops, int ngroups, int n,
   hd[1] = (uint32_t)nu;                           // dense unless shown otherwise
   if (!hi || !hi->enable || nu > NQ || 2 + 2 * nu > QAS_HD_WORDS) return;
   int drank = 0;
-#pragma unroll
+QAS_PUNROLL
   for (int p = 0; p < NQ; ++p) drank += D.v[p] ? 1 : 0;
   if (drank >= n) return;                         // the final state is dense
   QasPivTab<NQ> E;
   E.clear();
   int dbar = 0;
-#pragma unroll
+QAS_PUNROLL
   for (int p = 0; p < NQ; ++p)
     if (D.v[p]) dbar += qas_tab_add_msb<NQ>(E, qas_ubar(*hi, D.v[p])) ? 1 : 0;
   if (dbar >= nu) return;
   // reduced echelon form: clear every pivot bit from the other basis vectors (ascending pivots, so the
   // vector xor-ed in is already free of lower pivot bits)
-#pragma unroll
+QAS_PUNROLL
   for (int p = 0; p < NQ; ++p)
     if (E.v[p]) {
-#pragma unroll
+QAS_PUNROLL
       for (int p2 = 0; p2 < NQ; ++p2)
         if (p2 > p && ((E.v[p2] >> p) & 1u)) E.v[p2] ^= E.v[p];
     }
   hd[0] = qas_ubar(*hi, b0);
   hd[1] = (uint32_t)dbar;
   int cnt = 0;
-#pragma unroll
+QAS_PUNROLL
   for (int p = 0; p < NQ; ++p) if (p < nu && E.v[p]) hd[2 + cnt++] = E.v[p];
-#pragma unroll
+QAS_PUNROLL
   for (int p = 0; p < NQ; ++p) if (p < nu && !E.v[p]) hd[2 + cnt++] = 1u << p;
   int kc = 0;
-#pragma unroll
+QAS_PUNROLL
   for (int f = 0; f < NQ; ++f)
     if (f < nu && !E.v[f]) {
       uint32_t chk = 1u << f;
-#pragma unroll
+QAS_PUNROLL
       for (int p = 0; p < NQ; ++p) if (E.v[p] && ((E.v[p] >> f) & 1u)) chk |= 1u << p;
       hd[2 + nu + kc++] = chk;
     }
