@@ -460,6 +460,8 @@ __device__ __forceinline__ void reduce_store_m(double (&acc)[8], int lane, uint3
 //   | Us [ops_cap][4] double2 (STAGE_U) | red [2][3][WPT][8] f64 (GRAD, multi-warp teams) | ered [WPT] f64
 //   | hx [QAS_HD_WORDS] u32 + tcls [32] u32 (shared-memory path: final-support descriptor, class coset ids)
 __host__ __device__ constexpr bool qas_stage_u(int N) { return N == 0 || N >= 7; }
+// support-restricted H application: below 8 qubits the whole register is a few warp iterations
+#define QAS_HSPARSE_MIN_N 8
 __host__ __device__ inline size_t eval_team_smem_bytes(int n, int T, bool grad, int ops_cap,
                                                        bool state_in_smem, bool stage_u) {
   const size_t dim = (size_t)1 << n;
@@ -472,7 +474,7 @@ __host__ __device__ inline size_t eval_team_smem_bytes(int n, int T, bool grad, 
   if (grad && wpt > 1) b += (size_t)2 * 3 * wpt * 64;
   b += (((size_t)wpt * 8) + 15) & ~(size_t)15;
   b += 16;                                   // the team's work-queue slot
-  if (state_in_smem) b += (size_t)(QAS_HD_WORDS + 32) * 4;
+  if (state_in_smem && n >= QAS_HSPARSE_MIN_N) b += (size_t)(QAS_HD_WORDS + 32) * 4;
   return b;
 }
 
@@ -541,7 +543,11 @@ __device__ __forceinline__ void adj_group(double2 *psi, double2 *lam, const uint
   // lambda_g inside the support of psi_g.  So lambda, like psi, is propagated inside the shrinking
   // support and whatever it holds outside is never read again.  (The bound is rounded up to whole
   // warps / teams so that the shuffles below see uniform trip counts.)
-  const uint32_t nper = min(DIM >> G, (gg.nsup + (uint32_t)(TW - 1)) & ~(uint32_t)(TW - 1));
+  // FULL: the support is everything (uniform start state, deep circuits) -- compile-time trip count, no
+  // inside/outside predicates
+  auto sweep = [&](auto full_tag) {
+  constexpr bool FULL = decltype(full_tag)::value;
+  const uint32_t nper = FULL ? (DIM >> G) : min(DIM >> G, (gg.nsup + (uint32_t)(TW - 1)) & ~(uint32_t)(TW - 1));
   constexpr int UNR = EACH ? 1 : ((4 >> G) > 0 ? (4 >> G) : 1);
 #pragma unroll UNR
   for (uint32_t t = tid; t < nper; t += T) {
@@ -549,8 +555,9 @@ __device__ __forceinline__ void adj_group(double2 *psi, double2 *lam, const uint
     if (G == 1 && rc && !(__popc(sw<SWZ>(P) & rc) & 1)) continue;   // rc is a mask over index bits
     // ins: this coset is inside the support (the rounding above admits a few that are not).  wins: some
     // lane of this warp is inside (warp-uniform for whole-warp teams; sub-warp teams always reduce)
-    const bool ins = t < gg.nsup;
-    const bool wins = T < 32 || (t & ~31u) < gg.nsup;
+    const bool ins = FULL || t < gg.nsup;
+    const bool wins = FULL || T < 32 || (t & ~31u) < gg.nsup;
+    (void)wins;
     double2 a[1 << G], l[1 << G];
 #pragma unroll
     for (int c = 0; c < (1 << G); ++c) {
@@ -593,6 +600,12 @@ __device__ __forceinline__ void adj_group(double2 *psi, double2 *lam, const uint
       lam[x] = l[c];
     }
   }
+  };
+  // the second copy only pays where the whole register is one or two iterations (n < 8; measured:
+  // QAOA-7q 0.299 -> 0.277 ms, but H2O-8q 1.05 -> 1.24 ms with both copies in the kernel)
+  constexpr bool DUP = NXS > 0 && NXS + G < 8;
+  if constexpr (DUP) { if (gg.nsup >= (DIM >> G)) sweep(std::true_type{}); else sweep(std::false_type{}); }
+  else sweep(std::false_type{});
   if constexpr (!EACH) {
     const bool wins0 = T < 32 || ((uint32_t)tid & ~31u) < gg.nsup;
     if (wins0) {
@@ -682,8 +695,10 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
         const uint32_t *ggd = grec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS;
         const int gused = (int)grec[3] * gstride;
         for (int w = tid; w < gused; w += T) gd16[w] = (uint16_t)ggd[w];
-        const uint32_t *ghd = grec + qas_rec_hd_offset(P.ops_cap, n);
-        for (int w = tid; w < QAS_HD_WORDS; w += T) hx[w] = ghd[w];
+        if constexpr (N >= QAS_HSPARSE_MIN_N) {
+          const uint32_t *ghd = grec + qas_rec_hd_offset(P.ops_cap, n);
+          for (int w = tid; w < QAS_HD_WORDS; w += T) hx[w] = ghd[w];
+        }
       }
       const double amp0 = (P.init_kind == QAS_INIT_PLUS) ? exp2(-0.5 * (double)n) : 0.0;
       for (uint32_t i = tid; i < DIM; i += T) psi[i] = make_double2(amp0, 0.0);
@@ -740,18 +755,8 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
       const uint32_t nrest = DIM >> RB;
       const char *psib = reinterpret_cast<const char *>(psi);
       const int C = P.C_real + P.C_imag;
-      // own amplitudes of coset sb16: energy contribution and lambda
-      auto finish = [&](uint32_t sb16, const double2 (&acc)[NB]) {
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          const uint32_t off = sb16 ^ P.wc16.w[j];
-          const double2 ai = *reinterpret_cast<const double2 *>(psib + off);
-          e_part = fma(ai.x, acc[j].x, fma(ai.y, acc[j].y, e_part));
-          if constexpr (GRAD) *reinterpret_cast<double2 *>(reinterpret_cast<char *>(lam) + off) = acc[j];
-        }
-      };
       bool sparse = false;
-      constexpr bool HSPARSE = N >= 8;      // below that the whole register fits a few warp iterations
+      constexpr bool HSPARSE = N >= QAS_HSPARSE_MIN_N;
       if constexpr (HSPARSE) sparse = P.hs_min > 0 && C <= 32 && (int)hx[1] + P.hs_min <= N - RB;
       if (sparse) {
         // Support-restricted application (tape.h, "Support of the FINAL state"): the cosets are walked in
@@ -799,7 +804,13 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
 #pragma unroll
               for (int jw = 0; jw < NB; ++jw) hacc_row<NB>(acc, a, v[jw], jw, imag);
             }
-            finish(sb16, acc);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              const uint32_t off = sb16 ^ P.wc16.w[j];
+              const double2 ai = *reinterpret_cast<const double2 *>(psib + off);
+              e_part = fma(ai.x, acc[j].x, fma(ai.y, acc[j].y, e_part));
+              if constexpr (GRAD) *reinterpret_cast<double2 *>(reinterpret_cast<char *>(lam) + off) = acc[j];
+            }
           }
         }
       } else {
@@ -830,7 +841,13 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
           }
           vp += (size_t)NB << n;
         }
-        finish(sb16, acc);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const uint32_t off = sb16 ^ P.wc16.w[j];
+          const double2 ai = *reinterpret_cast<const double2 *>(psib + off);
+          e_part = fma(ai.x, acc[j].x, fma(ai.y, acc[j].y, e_part));
+          if constexpr (GRAD) *reinterpret_cast<double2 *>(reinterpret_cast<char *>(lam) + off) = acc[j];
+        }
       }
       }
     }

@@ -1,5 +1,5 @@
 # the bench lines, launch list and ncu capture that go under profiles/ : bash tools/gpu/official.sh <tag>
-tag=${1:-r01g}
+tag=${1:-r01h}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&1; tail -1 gpurun_out/${tag}_pytest.log
 python bench.py > gpurun_out/${tag}_bench_lih_10q.json 2> gpurun_out/${tag}_bench_lih_10q.err; tail -c 300 gpurun_out/${tag}_bench_lih_10q.json
