@@ -631,8 +631,10 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     CK(ensure(&ctx->d_params, &ctx->cap_params, npar));
     CK(ensure(&ctx->d_energy, &ctx->cap_energy, (size_t)B));
     if (!(tiny && !want_grad && !small)) CK(cudaMemcpyAsync(ctx->d_k, k, nk * 4, cudaMemcpyHostToDevice, st));
-    {   // the reference's asserts on k (utils.py:12-15), checked while the copy is in flight;
-        // branch-free so that it vectorises
+    // the reference's asserts on k (utils.py:12-15).  Batches compiled on the host are checked now;
+    // for the others the device code tolerates any key (status word -> NaN energy), so the check
+    // runs on the host while the kernels do (below, before the results are copied back)
+    if (B <= 16) {
       uint32_t bad = 0;
       const uint32_t cu = (uint32_t)c;
       for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k[i] >= cu);
@@ -755,7 +757,8 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   stamp(5);
 
   if (grad_dense) {
-    const int chunk = 32;      // circuits per CTA of the first stage (2048 CTAs at B = 65536)
+    int chunk = 64;            // circuits per CTA of the first stage (1024 CTAs at B = 65536)
+    if (const char *ce = getenv("QAS_B200_REDUCE_CHUNK")) chunk = std::max(1, atoi(ce));   // tuning knob
     const int nchunks = (B + chunk - 1) / chunk;
     int depth_tile = p;
     while ((size_t)depth_tile * c * l * 8 > 96 * 1024 && depth_tile > 1) depth_tile = (depth_tile + 1) / 2;
@@ -788,6 +791,15 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
 
   if (!dev) {
     if (!tiny) CK(cudaEventRecord(ctx->ev1, st));
+    if (B > 16) {      // deferred range check of the structure lists; branch-free so that it vectorises
+      uint32_t bad = 0;
+      const uint32_t cu = (uint32_t)c;
+      for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k[i] >= cu);
+      if (bad) {
+        cudaStreamSynchronize(st);
+        return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
+      }
+    }
     CK(cudaMemcpyAsync(energy, denergy, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     if (grad_compact) CK(cudaMemcpyAsync(grad_compact, dgrad, ng * 8, cudaMemcpyDeviceToHost, st));
     if (grad_dense) CK(cudaMemcpyAsync(grad_dense, ddense, npar * 8, cudaMemcpyDeviceToHost, st));

@@ -1164,7 +1164,21 @@ __global__ void grad_chunk_reduce_kernel(const int32_t *k, const double *grad, i
   for (int x = threadIdx.x; x < nd * l; x += blockDim.x) {
     const int di = x / l, j = x % l;
     double *a = acc + (size_t)di * c * l + j;
-    for (int b = b_lo; b < b_hi; ++b) {
+    // four circuits' loads in flight per step; the accumulation order stays b ascending
+    int b = b_lo;
+    for (; b + 4 <= b_hi; b += 4) {
+      int key[4];
+      double gval[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        key[q] = k[(size_t)(b + q) * p + i0 + di];
+        gval[q] = grad[((size_t)(b + q) * p + i0 + di) * l + j];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (key[q] >= 0 && key[q] < c) a[key[q] * l] += nan_to_num_d(gval[q]);
+    }
+    for (; b < b_hi; ++b) {
       const int key = k[(size_t)b * p + i0 + di];
       const double gval = grad[((size_t)b * p + i0 + di) * l + j];
       if (key >= 0 && key < c) a[key * l] += nan_to_num_d(gval);
