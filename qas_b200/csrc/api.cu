@@ -722,7 +722,9 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   } else {
     const int cthr = 64;
     // ops in shared memory only while that keeps >= 8 CTAs per SM resident (short tapes)
-    const bool ops_smem = qas_compile_smem_words(ctx->n, P.ops_cap, p, true) * 4 * cthr <= 24 * 1024;
+    size_t ops_smem_limit = 24 * 1024;
+    if (const char *oe = getenv("QAS_B200_COMPILE_SMEM_KB")) ops_smem_limit = (size_t)std::max(0, atoi(oe)) * 1024;   // tuning knob
+    const bool ops_smem = qas_compile_smem_words(ctx->n, P.ops_cap, p, true) * 4 * cthr <= ops_smem_limit;
     const size_t csm = qas_compile_smem_words(ctx->n, P.ops_cap, p, ops_smem) * 4 * cthr;
     if (csm > 200 * 1024) return fail(ctx, QAS_ERR_UNSUPPORTED, "structure lists too long for the tape-compile kernel");
     if (ops_smem) {

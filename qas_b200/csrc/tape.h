@@ -452,6 +452,7 @@ QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax, int n, int init_ki
   if (!gd) return ngroups;
   if (n <= 5) qas_plan_supports<5>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
   else if (n <= 8) qas_plan_supports<8>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
+  else if (n <= 10) qas_plan_supports<10>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
   else if (n <= 12) qas_plan_supports<12>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
   else qas_plan_supports<QAS_MAX_QUBITS>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
   if (swizzled)
