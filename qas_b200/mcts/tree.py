@@ -131,9 +131,12 @@ class MCTSController():
         if missing:
             if hasattr(self.model, "evaluate_batch"):
                 out = self.model.evaluate_batch(np.array(missing, dtype=np.int32), params, self.pool, want_grad=False)
-                sign = getattr(self.model, "reward_sign", -1.0)
-                for k, e in zip(missing, out["energy"]):
-                    self.reward_cache[k] = sign * float(e)
+                if hasattr(self.model, "rewards_from_losses"):      # non-linear reward (VQLS: exp(-10 loss))
+                    rewards = self.model.rewards_from_losses(out["energy"])
+                else:
+                    rewards = getattr(self.model, "reward_sign", -1.0) * np.asarray(out["energy"])
+                for k, r in zip(missing, rewards):
+                    self.reward_cache[k] = float(r)
             else:
                 p, c, l = params.shape
                 for k in missing:

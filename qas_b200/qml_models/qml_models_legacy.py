@@ -9,6 +9,7 @@ five methods; only what they evaluate is declared here.
                                         reference's quoted SCF/FCI energies and its saved search result
   QAOAVQCDemo               :2328-2491  7 qubits, |+>^7 start, loss = -sum_e (1 - <ZZ>)/2, reward = -loss
   QAOAWeightedVQCDemo       :2493-2651  5 qubits, weighted edges
+  VQLSDemo, VQLSDemo5Q      :1807-2326  Hadamard-test cost as two Pauli-sum observables (vqls_model.py)
   TwoQubitH2                missing upstream (imported by search-scripts-legacy/two_qubit_h2.py:3); stand-in
 
 Upstream the QAOA objective runs one QNode per graph edge (:2377-2393); here the edge sum is
@@ -16,6 +17,7 @@ one diagonal Pauli-sum evaluated in the same launch as everything else.
 """
 from qas_b200.qml_models.hamiltonian_model import HamiltonianModel
 from qas_b200.qml_models.utils import extractParamIndicesQML  # noqa: F401  (re-exported upstream too)
+from qas_b200.qml_models.vqls_model import VQLSDemo, VQLSDemo5Q  # noqa: F401  (:1807-2326 upstream)
 
 
 class FourQubitH2(HamiltonianModel):
