@@ -274,6 +274,33 @@ def test_support_restricted_h_application_equals_dense(cfg, monkeypatch):
             assert abs(b["energy"][bi] - e) <= 1e-9
 
 
+def test_support_restricted_path_with_the_full_gate_vocabulary(monkeypatch):
+    """Controlled rotations, parity-diagonal (Ising) gates and swaps on 8 qubits, shallow enough that the
+    support stays small: restricted and dense H application agree and both match the oracle."""
+    from qas_b200.qml_models.qml_models_legacy import H2O
+    n, p, B = 8, 5, 768
+    pool = helpers.full_vocab_pool(n)
+    c = len(pool)
+    rng = np.random.default_rng(12)
+    ks = rng.integers(0, c, size=(B, p)).astype(np.int32)
+    params = rng.standard_normal((p, c, 3))
+    res = {}
+    for hs in ("0", "1"):
+        monkeypatch.setenv("QAS_B200_HSPARSE", hs)
+        ev = BatchEvaluator(n, H2O.terms(), pool, init=("basis", 0b10100110))
+        res[hs] = ev.evaluate(ks, params, want_grad=True, dense=True, compact=True)
+        ev.close()
+    assert np.max(np.abs(res["0"]["energy"] - res["1"]["energy"])) <= 1e-12
+    assert np.max(np.abs(res["0"]["grad_compact"] - res["1"]["grad_compact"])) <= 1e-12
+    for b in range(0, B, 96):
+        k = [int(x) for x in ks[b]]
+        e = sim.energy(n, k, pool.pool, params, H2O.terms(), ("basis", 0b10100110))
+        g = sim.grad_adjoint(n, k, pool.pool, params, H2O.terms(), ("basis", 0b10100110))
+        assert abs(res["1"]["energy"][b] - e) <= E_TOL
+        for i, key in enumerate(k):
+            assert np.max(np.abs(res["1"]["grad_compact"][b, i] - g[i, key])) <= G_TOL
+
+
 def test_linearity_in_hamiltonian():
     """E_{H1+H2} = E_{H1} + E_{H2} for the same circuits (X-mask grouping must not mix terms)."""
     from qas_b200.qml_models.qml_models_legacy import H2O

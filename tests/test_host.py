@@ -226,10 +226,14 @@ def test_final_support_descriptor_of_the_h_application():
     restricted = 0
     for trial in range(40):
         n = [8, 9, 10][trial % 3]
-        pool = helpers.near_cx_pool(n)
-        p = int(rng.integers(4, 14))
+        full_vocab = trial % 5 == 4          # controlled rotations, Ising gates, swaps ... as well
+        pool = helpers.full_vocab_pool(n) if full_vocab else helpers.near_cx_pool(n)
+        p = int(rng.integers(3, 7)) if full_vocab else int(rng.integers(4, 14))
         init = ("zero", 0) if trial % 4 else ("basis", int(rng.integers(0, 1 << n)))
-        k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": p // 2}, 1, seed=100 + trial)[0]]
+        if full_vocab:
+            k = [int(x) for x in rng.integers(0, len(pool), size=p)]
+        else:
+            k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": p // 2}, 1, seed=100 + trial)[0]]
         ops, idx = compile_tape_host(n, pool, k, init[1] if init[0] == "basis" else 0)
         # a register subspace W in reduced echelon form (highest-bit pivots ascending)
         rb_count = int(rng.integers(0, 4))
