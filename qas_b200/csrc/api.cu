@@ -158,7 +158,7 @@ static int team_threads_for(int n, int shift) {
   const int t = team_threads(n);
   // QAS_B200_TEAM_SHIFT=1: the doubled team in a 256-thread CTA (compiled for n = 8..11, see launch_eval)
   if (shift > 0 && n >= 8 && n <= 11) return t * 2;
-  if (shift < 0 && (n == 10 || n == 9)) return 32;      // QAS_B200_TEAM_SHIFT=-1: one warp per circuit, no team barriers
+  if (shift < 0 && n == 10) return 32;      // QAS_B200_TEAM_SHIFT=-1: one warp per circuit, no team barriers
   return t;
 }
 
@@ -277,7 +277,6 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   cx->T = team_threads_for(n_qubits, cx->team_shift);
   cx->blk = cx->team_shift > 0 ? 256 : team_blk(n_qubits);
   if (cx->team_shift < 0 && n_qubits == 10) cx->blk = 64;
-  if (cx->team_shift < 0 && n_qubits == 9) cx->blk = 128;
   cx->GMAX = qas_gmax(n_qubits <= 13 ? n_qubits : 20, cx->T);
   cx->RB = qas_hrb(n_qubits <= 13 ? n_qubits : 20, cx->T);
   cx->PD = qas_hpd(n_qubits <= 13 ? n_qubits : 20, cx->T);
@@ -553,7 +552,7 @@ static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
       QAS_CASE(2, 8, 256) QAS_CASE(3, 8, 256) QAS_CASE(4, 8, 256) QAS_CASE(5, 16, 256) QAS_CASE(6, 32, 256)
       QAS_CASE(7, 32, 256) QAS_CASE(8, 32, 256) QAS_CASE(9, 64, 256) QAS_CASE(10, 64, 128) QAS_CASE(11, 128, 128)
       QAS_CASE(12, 256, 256)
-      QAS_CASE(10, 32, 64) QAS_CASE(9, 32, 128)                                                    // QAS_B200_TEAM_SHIFT=-1
+      QAS_CASE(10, 32, 64)                                                                          // energy-only launches; QAS_B200_TEAM_SHIFT=-1
       QAS_CASE(8, 64, 256) QAS_CASE(9, 128, 256) QAS_CASE(10, 128, 256) QAS_CASE(11, 256, 256)     // QAS_B200_TEAM_SHIFT=1
 #undef QAS_CASE
       if constexpr (!GRAD) { if (P.n == 13 && T == 256) return launch_smem<13, 256, false, qas_hrb(13, 256), qas_hpd(13, 256)>(ctx, P, st); }
