@@ -293,3 +293,37 @@ def test_final_support_descriptor_of_the_h_application():
         assert int(hd[0]) == ubar(int(idx))
         assert all((ubar(i) ^ int(hd[0])) in dspan for i in support)
     assert restricted >= 10
+
+
+def test_support_compressed_register_prototype_matches_oracle():
+    """the evaluation of a shallow circuit on n qubits equals that of a
+    d = dim(support span) qubit register after translating the tape and the Hamiltonian into support
+    coordinates (tests/compressed_register.py) -- energies and every derivative."""
+    import compressed_register as CR
+    rng = np.random.default_rng(11)
+    saved = 0
+    for trial in range(10):
+        n = [8, 10][trial % 2]
+        full_vocab = trial % 5 == 4
+        pool = helpers.full_vocab_pool(n) if full_vocab else helpers.near_cx_pool(n)
+        c = len(pool)
+        p = int(rng.integers(3, 6)) if full_vocab else int(rng.integers(5, 14))
+        init = ("zero", 0) if trial % 3 else ("basis", int(rng.integers(0, 1 << n)))
+        if full_vocab:
+            k = [int(x) for x in rng.integers(0, c, size=p)]
+        else:
+            k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": p // 2}, 1, seed=300 + trial)[0]]
+        params = rng.standard_normal((p, c, 3))
+        terms = [(float(cf), w) for cf, w in helpers.get_model("LiH" if n == 10 else "H2O").terms()]
+        ops, idx = compile_tape_host(n, pool, k, init[1] if init[0] == "basis" else 0)
+        d, cops, cterms = CR.compress(ops, idx, terms)
+        assert d <= n and len(cterms) <= len(terms)
+        saved += n - d
+        e, gr = CR.run(d, cops, cterms, pool.pool, c, params)
+        assert abs(e - sim.energy(n, k, pool.pool, params, terms, init)) < 1e-10
+        ga = sim.grad_adjoint(n, k, pool.pool, params, terms, init)
+        got = np.zeros_like(ga)
+        for (dep, j), v in gr.items():
+            got[dep, k[dep], j] = v
+        assert np.max(np.abs(got - ga)) < 1e-9
+    assert saved >= 10          # the registers really are smaller
