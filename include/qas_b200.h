@@ -160,6 +160,18 @@ int qas_plan_hsupport_host(int n_qubits, const uint32_t *ops, int num_ops, int i
                            uint32_t init_index, int w_rank, const int *w_pivots,
                            const uint32_t *w_basis, uint32_t *hdesc, int hdesc_words);
 
+/* Support-compressed register (host-side planner; the evaluation kernels do not consume it yet):
+ * rewrites a compiled tape (qas_compile_tape_host, before qas_plan_passes_host) in coordinates of the
+ * span D of its xor masks, i(t) = init_index ^ xor_k t_k basis[k]:  ops[j] = {m', r', rc', tab, meta}
+ * with meta bit 28 / 29 = constant flip of the logical / control bit (parity of init_index with r / rc;
+ * rc' = 0x80000000 marks a control that is constant on the support).  dim_out = dim D, basis_out
+ * (>= n_qubits words) the basis by ascending pivot, xcoords_out[s] = coordinates of xmasks[s] or
+ * 0xffffffff when that X mask leaves the support (it then drops out of energy and gradient).
+ * No reference counterpart.                                                                     */
+int qas_compress_tape_host(int n_qubits, uint32_t *ops, int num_ops, uint32_t init_index,
+                           const uint32_t *xmasks, int num_xmasks, int *dim_out,
+                           uint32_t *basis_out, uint32_t *xcoords_out);
+
 /* Counters since context creation: evaluations and kernel launches; device time of the
  * last call's kernels (ms, CUDA events on the launch stream; host-pointer calls only) and of
  * the last evaluation kernel alone (any call; qas_get_stats waits for that kernel).         */

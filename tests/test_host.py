@@ -327,3 +327,68 @@ def test_support_compressed_register_prototype_matches_oracle():
             got[dep, k[dep], j] = v
         assert np.max(np.abs(got - ga)) < 1e-9
     assert saved >= 10          # the registers really are smaller
+
+
+def test_compressed_register_translation_in_the_library_matches_oracle():
+    """qas_compress_tape_host (the C side of DESIGN.md section 6 item 1): its translated tape, run by the
+    NumPy interpreter of tests/compressed_register.py on the d-qubit register, gives the oracle's energy
+    and derivatives; X masks it reports as outside the support are exactly the ones that drop out."""
+    import ctypes
+    import compressed_register as CR
+    from qas_b200 import _lib
+    from qas_b200 import hamiltonians as HM
+    lib = _lib.load()
+    rng = np.random.default_rng(21)
+    for trial in range(10):
+        n = [8, 10][trial % 2]
+        full_vocab = trial % 5 == 3
+        pool = helpers.full_vocab_pool(n) if full_vocab else helpers.near_cx_pool(n)
+        c = len(pool)
+        p = int(rng.integers(3, 6)) if full_vocab else int(rng.integers(5, 14))
+        init = ("zero", 0) if trial % 3 else ("basis", int(rng.integers(0, 1 << n)))
+        if full_vocab:
+            k = [int(x) for x in rng.integers(0, c, size=p)]
+        else:
+            k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": p // 2}, 1, seed=500 + trial)[0]]
+        params = rng.standard_normal((p, c, 3))
+        terms = [(float(cf), w) for cf, w in helpers.get_model("LiH" if n == 10 else "H2O").terms()]
+        ops, idx = compile_tape_host(n, pool, k, init[1] if init[0] == "basis" else 0)
+        xs = np.array(sorted({HM.word_to_masks(w)[0] for _, w in terms}), dtype=np.uint32)
+        cops_arr = np.ascontiguousarray(ops, dtype=np.uint32).copy()
+        d = ctypes.c_int(0)
+        basis = np.zeros(n, dtype=np.uint32)
+        xc = np.zeros(len(xs), dtype=np.uint32)
+        rc = lib.qas_compress_tape_host(n, cops_arr.ctypes.data, len(cops_arr), int(idx), xs.ctypes.data, len(xs),
+                                        ctypes.byref(d), basis.ctypes.data, xc.ctypes.data)
+        assert rc == 0
+        d = d.value
+        B = [int(v) for v in basis[:d]]
+        assert [v.bit_length() for v in B] == sorted(v.bit_length() for v in B)          # ascending pivots
+        # the Python prototype finds the same dimension and the same set of X masks inside the span
+        d_py, _, cterms_py = CR.compress(ops, idx, terms)
+        assert d == d_py
+        inside = {int(x) for x, t in zip(xs, xc) if t != 0xffffffff}
+        assert len({(HM.word_to_masks(w)[0]) for _, w in terms} & inside) == len(inside)
+        xmap = {int(x): int(t) for x, t in zip(xs, xc)}
+        # Hamiltonian in the library's coordinates
+        cterms = []
+        for coeff, word in terms:
+            x, z = sim.word_to_masks(word)
+            if xmap[x] == 0xffffffff:
+                continue
+            zp = sum((bin(B[kk] & z).count("1") & 1) << kk for kk in range(d))
+            cterms.append((xmap[x], zp, coeff * (-1.0 if bin(idx & z).count("1") & 1 else 1.0), bin(x & z).count("1")))
+        assert len(cterms) == len(cterms_py)
+        cops = []
+        for o in cops_arr:
+            m, r, rcm, tab, meta = (int(v) for v in o)
+            has_c = rcm != 0
+            rcp = 0 if rcm == 0x80000000 else rcm
+            cops.append((m, r, (meta >> 28) & 1, rcp, (meta >> 29) & 1, has_c, tab, meta & 0x0fffffff))
+        e, gr = CR.run(d, cops, cterms, pool.pool, c, params)
+        assert abs(e - sim.energy(n, k, pool.pool, params, terms, init)) < 1e-10
+        ga = sim.grad_adjoint(n, k, pool.pool, params, terms, init)
+        got = np.zeros_like(ga)
+        for (dep, j), v in gr.items():
+            got[dep, k[dep], j] = v
+        assert np.max(np.abs(got - ga)) < 1e-9
