@@ -267,9 +267,13 @@ def run_tape_planned(n, ops, gds, init, init_index, pool, c, params, terms, want
             state["psi"] = np.where(par(idx & r) == 1, u[1, 1], u[0, 0]) * state["psi"]
     psi = state["psi"]
     lam = np.zeros(dim, dtype=np.complex128)
-    for coeff, word in terms:
-        x, z = sim.word_to_masks(word)
-        ny = bin(x & z).count("1")
+    for term in terms:
+        if len(term) == 2:                       # (coeff, Pauli word)
+            coeff, word = term
+            x, z = sim.word_to_masks(word)
+            ny = bin(x & z).count("1")
+        else:                                    # (x mask, z mask, coeff, number of Y's): compressed registers
+            x, z, coeff, ny = term
         jx = idx ^ x
         lam += coeff * (1j ** ny) * np.where(par(jx & z) == 1, -1.0, 1.0) * psi[jx]
     energy = float(np.vdot(psi, lam).real)

@@ -392,3 +392,53 @@ def test_compressed_register_translation_in_the_library_matches_oracle():
         for (dep, j), v in gr.items():
             got[dep, k[dep], j] = v
         assert np.max(np.abs(got - ga)) < 1e-9
+
+
+@pytest.mark.parametrize("gmax", [1, 2])
+def test_compressed_tapes_run_through_the_existing_pass_planner(gmax):
+    """The register-fused, support-restricted passes of the evaluation kernel (qas_plan_groups + the
+    kernel's coset enumeration, restated in tape_interp.run_tape_planned) work unchanged on a tape that
+    qas_compress_tape_host rewrote for its d-qubit register -- all-zero start, so no role flips."""
+    import ctypes
+    from qas_b200 import _lib
+    from qas_b200 import hamiltonians as HM
+    lib = _lib.load()
+    rng = np.random.default_rng(31)
+    for trial in range(6):
+        n = [8, 10][trial % 2]
+        pool = helpers.near_cx_pool(n)
+        c = len(pool)
+        p = int(rng.integers(5, 14))
+        k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": p // 2}, 1, seed=700 + trial)[0]]
+        params = rng.standard_normal((p, c, 3))
+        terms = [(float(cf), w) for cf, w in helpers.get_model("LiH" if n == 10 else "H2O").terms()]
+        ops, idx = compile_tape_host(n, pool, k, 0)
+        assert idx == 0
+        xs = np.array(sorted({HM.word_to_masks(w)[0] for _, w in terms}), dtype=np.uint32)
+        cops = np.ascontiguousarray(ops, dtype=np.uint32).copy()
+        d = ctypes.c_int(0)
+        basis = np.zeros(n, dtype=np.uint32)
+        xc = np.zeros(len(xs), dtype=np.uint32)
+        assert lib.qas_compress_tape_host(n, cops.ctypes.data, len(cops), 0, xs.ctypes.data, len(xs),
+                                          ctypes.byref(d), basis.ctypes.data, xc.ctypes.data) == 0
+        d = d.value
+        if d < 2:
+            continue
+        assert not np.any(cops[:, 4] & np.uint32(3 << 28))             # no flips from |0..0>
+        B = [int(v) for v in basis[:d]]
+        xmap = {int(x): int(t) for x, t in zip(xs, xc)}
+        cterms = []
+        for coeff, word in terms:
+            x, z = sim.word_to_masks(word)
+            if xmap[x] != 0xffffffff:
+                cterms.append((xmap[x], sum((bin(B[q] & z).count("1") & 1) << q for q in range(d)), coeff,
+                               bin(x & z).count("1")))
+        swz = bool(trial & 1)                                            # both index layouts of the kernel
+        pops, ng, gds = TI.plan_passes(d, cops, gmax, ("zero", 0), 0, swizzled=swz)
+        e, gr = TI.run_tape_planned(d, pops, gds, ("zero", 0), 0, pool.pool, c, params, cterms, swizzled=swz)
+        assert abs(e - sim.energy(n, k, pool.pool, params, terms, ("zero", 0))) < 1e-10
+        ga = sim.grad_adjoint(n, k, pool.pool, params, terms, ("zero", 0))
+        got = np.zeros_like(ga)
+        for (dep, j), v in gr.items():
+            got[dep, k[dep], j] = v
+        assert np.max(np.abs(got - ga)) < 1e-9
