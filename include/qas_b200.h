@@ -160,17 +160,22 @@ int qas_plan_hsupport_host(int n_qubits, const uint32_t *ops, int num_ops, int i
                            uint32_t init_index, int w_rank, const int *w_pivots,
                            const uint32_t *w_basis, uint32_t *hdesc, int hdesc_words);
 
-/* Support-compressed register (host-side planner; the evaluation kernels do not consume it yet):
- * rewrites a compiled tape (qas_compile_tape_host, before qas_plan_passes_host) in coordinates of the
- * span D of its xor masks, i(t) = init_index ^ xor_k t_k basis[k]:  ops[j] = {m', r', rc', tab, meta}
- * with meta bit 28 / 29 = constant flip of the logical / control bit (parity of init_index with r / rc;
- * rc' = 0x80000000 marks a control that is constant on the support).  dim_out = dim D, basis_out
- * (>= n_qubits words) the basis by ascending pivot, xcoords_out[s] = coordinates of xmasks[s] or
- * 0xffffffff when that X mask leaves the support (it then drops out of energy and gradient).
- * No reference counterpart.                                                                     */
-int qas_compress_tape_host(int n_qubits, uint32_t *ops, int num_ops, uint32_t init_index,
-                           const uint32_t *xmasks, int num_xmasks, int *dim_out,
-                           uint32_t *basis_out, uint32_t *xcoords_out);
+/* Support-compressed tape ("c-tape"; host run of the code the tape-compile kernel executes for all-zero
+ * start states).  From |0..0> a circuit only populates D = span of the xor masks of its 2x2 ops, and after
+ * its first j ops only the span D_j of the first j masks.  The c-tape rewrites the compiled, grouped tape in
+ * a TIME-ADAPTED basis of D (B_k = mask of the k-th op, in time order, that enlarges the span): with
+ * i(t) = xor_k t_k B_k the support after j ops is the prefix t < 2^{d_j} of a 2^d-amplitude register.
+ * out_ops[j] = {m', r', rc', table index, meta} with meta bits 24-27 = group marks, bits 28-31 = d_j;
+ * controlled ops whose control is constant on the support are dropped.  *dim = d = dim D, or -1 when
+ * d == n_qubits (nothing to compress: out_ops is the grouped classic tape), -2 when d > max_d (<= 12).
+ * basis_out (n_qubits words) = B_0 .. B_{d-1}; list_out[s'] = x' | s << 16 for every X mask
+ * xmasks[s] inside D (x' = its coordinates); X masks outside D connect the support to amplitudes
+ * that are exactly zero and drop out of the energy and of every derivative.
+ * No reference counterpart (PennyLane keeps the dense 2^n state for every circuit).             */
+int qas_compile_ctape_host(int n_qubits, const qas_pool_entry *pool, int c, int p, const int32_t *k,
+                           int gmax, const uint32_t *xmasks, int num_xmasks, int max_d,
+                           uint32_t *out_ops, int max_ops, int *num_ops, int *num_groups, int *dim,
+                           uint32_t *basis_out, uint32_t *list_out, int *num_list);
 
 /* Counters since context creation: evaluations and kernel launches; device time of the
  * last call's kernels (ms, CUDA events on the launch stream; host-pointer calls only) and of

@@ -72,7 +72,7 @@ _lib = None
 EXPORTS = [
     "qas_abi_version", "qas_build_info", "qas_ctx_create", "qas_ctx_destroy", "qas_last_error",
     "qas_eval_batch", "qas_compile_tape", "qas_compile_tape_host", "qas_plan_passes_host",
-    "qas_plan_hsupport_host", "qas_compress_tape_host",
+    "qas_plan_hsupport_host", "qas_compile_ctape_host",
     "qas_get_stats", "qas_debug_phase_clocks", "qas_adam_step", "qas_set_params",
     "qas_fp64_peak_tflops",
 ]
@@ -118,9 +118,11 @@ def load():
     lib.qas_plan_hsupport_host.restype = ctypes.c_int
     lib.qas_plan_hsupport_host.argtypes = [ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_int,
                                            vp, vp, vp, ctypes.c_int]
-    lib.qas_compress_tape_host.restype = ctypes.c_int
-    lib.qas_compress_tape_host.argtypes = [ctypes.c_int, vp, ctypes.c_int, ctypes.c_uint32, vp, ctypes.c_int,
-                                           ctypes.POINTER(ctypes.c_int), vp, vp]
+    pi = ctypes.POINTER(ctypes.c_int)
+    lib.qas_compile_ctape_host.restype = ctypes.c_int
+    lib.qas_compile_ctape_host.argtypes = [ctypes.c_int, ctypes.POINTER(PoolEntry), ctypes.c_int, ctypes.c_int, vp,
+                                           ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
+                                           pi, pi, pi, vp, vp, pi]
     lib.qas_set_params.restype = ctypes.c_int
     lib.qas_set_params.argtypes = [vp, ctypes.c_int, vp]
     lib.qas_adam_step.restype = ctypes.c_int

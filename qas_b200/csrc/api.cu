@@ -1,93 +1,9 @@
 // api.cu -- host side of libqas_b200.so: context, launch logic and the extern "C" ABI declared
 // in include/qas_b200.h.  No torch types, no exceptions across the boundary.
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <string>
-#include <vector>
+#include "ctx.h"
+#include "launch_cfg.h"
 
-#include "kernels.cuh"
-
-static thread_local std::string g_create_error;
-
-struct qas_ctx {
-  int device = 0, n = 0, init_kind = 0, c = 0, l = 0, num_sms = 0;
-  uint64_t init_basis = 0;
-  std::vector<qas_pool_entry> pool;
-  int max_expansion = 1;
-  int S = 0;                       // number of sign-table slices
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ek0 = nullptr, ek1 = nullptr;
-  bool ek_pending = false;
-  // device buffers owned by the context
-  qas_pool_entry *d_pool = nullptr;
-  double *d_vtab = nullptr;
-  uint32_t *d_sdesc = nullptr;
-  int team_shift = 0;              // QAS_B200_TEAM_SHIFT: threads per team = default << shift (tuning)
-  int T = 0, RB = 0, GMAX = 1, rb[3] = {0, 0, 0};
-  WComb wc{};                      // register subspace W of the H-apply blocking (kernels.cuh)
-  int num_classes = 0, C_real = 0, C_imag = 0;
-  uint32_t *d_cdesc_plain = nullptr;
-  uint32_t *d_cdesc_u = nullptr;   // class representatives in quotient coordinates (support-restricted H application)
-  QasHInfo hinfo{};                // register subspace W for the planner's final-support descriptor
-  int hs_min = 1;                  // QAS_B200_HSPARSE: minimum log2 saving for the support-restricted path (0 = off)
-  double *d_mout = nullptr; size_t cap_mout = 0;
-  unsigned long long *d_phase = nullptr;   // QAS_B200_PHASE_CLOCKS=1: per-phase clock sums (diagnostic)
-  bool stage_times = false;                // QAS_B200_STAGE_TIMES=1: print per-kernel stream times of every call
-  cudaEvent_t sev[8] = {nullptr};
-  int PD = 1;                      // H-apply prefetch depth (rows)
-  bool small_kernel = true;        // n <= 5: thread-per-circuit kernel (QAS_B200_SMALL=0 disables)
-  bool small_now = false;          // ... and chosen for the call in progress
-  int *d_counter = nullptr;        // work-queue head of the team kernels
-  int blk = 256;                   // threads per CTA of the team kernel
-  GateTab *d_U = nullptr;
-  GateDTab *d_dU = nullptr;
-  int tab_p = 0;
-  int resident_p = 0;              // depth of the parameter super-set left on the device by qas_set_params (0: none)
-  int32_t *d_k = nullptr;  size_t cap_k = 0;
-  double *d_params = nullptr; size_t cap_params = 0;
-  double *d_energy = nullptr; size_t cap_energy = 0;
-  double *d_grad = nullptr; size_t cap_grad = 0;
-  double *d_partial = nullptr; size_t cap_partial = 0;
-  double *d_dense = nullptr; size_t cap_dense = 0;
-  double2 *d_gstate = nullptr; size_t cap_gstate = 0;
-  uint32_t *d_tape = nullptr; size_t cap_tape = 0;
-  uint32_t *h_tape = nullptr; size_t cap_htape = 0;   // pinned staging for host-compiled tapes (tiny batches)
-  qas_stats stats{};
-  mutable std::string err;
-};
-
-#define CK(call)                                                                              \
-  do {                                                                                        \
-    cudaError_t e_ = (call);                                                                  \
-    if (e_ != cudaSuccess) {                                                                  \
-      char buf_[512];                                                                         \
-      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),     \
-               __FILE__, __LINE__);                                                           \
-      if (ctx) ctx->err = buf_; else g_create_error = buf_;                                   \
-      return QAS_ERR_CUDA;                                                                    \
-    }                                                                                         \
-  } while (0)
-
-static int fail(const qas_ctx *ctx, int code, const std::string &msg) {
-  if (ctx) ctx->err = msg; else g_create_error = msg;
-  return code;
-}
-
-template <typename Tp>
-static cudaError_t ensure(Tp **ptr, size_t *cap, size_t need_elems) {
-  if (*cap >= need_elems && *ptr) return cudaSuccess;
-  if (*ptr) cudaFree(*ptr);
-  *ptr = nullptr;
-  *cap = 0;
-  size_t want = std::max<size_t>(need_elems, 16);
-  cudaError_t e = cudaMalloc((void **)ptr, want * sizeof(Tp));
-  if (e == cudaSuccess) *cap = want;
-  return e;
-}
+thread_local std::string g_create_error;
 
 // ---------------------------------------------------------------------------------- info
 extern "C" int qas_abi_version(void) { return QAS_ABI_VERSION; }
@@ -139,27 +55,6 @@ static void fill_const_table(std::vector<GateTab> &t) {
   // parity-diagonal core of exp(+i pi/8 PP) = Ising(-pi/4): diag(e^{+i pi/8}, e^{-i pi/8})
   const double cs = std::cos(M_PI / 8), sn = std::sin(M_PI / 8);
   set(QAS_C_ZZ_MPI4, make_double2(cs, sn), Z0, Z0, make_double2(cs, -sn));
-}
-
-// threads per team and threads per CTA by qubit count (n <= 5 normally run the thread-per-circuit
-// kernel).  n = 10, 11: two-warp / four-warp teams in 128-thread CTAs -- six / three circuits in flight
-// per SM instead of four / two, and less waiting inside a team for the warp that owns the in-support
-// cosets of the adjoint sweep (LiH-10q: 2.46 -> 2.23 ms against 128-thread teams in 256-thread CTAs).
-constexpr int team_threads(int n) {
-  return n <= 4 ? 8 : n == 5 ? 16 : n <= 8 ? 32 : n <= 10 ? 64 : n == 11 ? 128 : 256;
-}
-constexpr int team_blk(int n) { return (n == 10 || n == 11) ? 128 : 256; }
-constexpr int qas_gmax(int n, int T) { return qas_block_bits(n, T) >= 2 ? 2 : 1; }
-// H application: 4 amplitudes per thread and a 2-deep prefetch ring where the team has the
-// amplitudes for it (measured best on LiH-10q / H2O-8q among (3,1) (3,2) (2,2) (2,4))
-constexpr int qas_hrb(int n, int T) { return qas_block_bits(n, T) >= 2 ? 2 : qas_block_bits(n, T); }
-constexpr int qas_hpd(int n, int T) { return qas_hrb(n, T) >= 1 ? 2 : 1; }   // PD must divide 2^RB
-static int team_threads_for(int n, int shift) {
-  const int t = team_threads(n);
-  // QAS_B200_TEAM_SHIFT=1: the doubled team in a 256-thread CTA (compiled for n = 8..11, see launch_eval)
-  if (shift > 0 && n >= 8 && n <= 11) return t * 2;
-  if (shift < 0 && n == 10) return 32;      // QAS_B200_TEAM_SHIFT=-1: one warp per circuit, no team barriers
-  return t;
 }
 
 // ---- register subspace W of the H application -------------------------------------------------
@@ -369,7 +264,43 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   guard(cudaEventCreate(&cx->ek0), "cudaEventCreate");
   guard(cudaEventCreate(&cx->ek1), "cudaEventCreate");
   guard(cudaMalloc(&cx->d_pool, sizeof(qas_pool_entry) * c), "cudaMalloc pool");
-  guard(cudaMalloc(&cx->d_counter, sizeof(int)), "cudaMalloc work counter");
+  guard(cudaMalloc(&cx->d_bins, sizeof(int) * 2 * QAS_MAX_BINS), "cudaMalloc bins");
+  // support-compressed path: all-zero start states only (a basis start needs role flips the kernel does not implement)
+  {
+    const char *ce = getenv("QAS_B200_COMPRESS");
+    cx->compress = (!ce || atoi(ce) != 0) && init_kind == QAS_INIT_ZERO && n_qubits >= 7;
+    if (const char *de = getenv("QAS_B200_COMPRESS_DMIN")) cx->c_dmin = std::max(1, std::min(QAS_CT_MAX_D, atoi(de)));
+    cx->c_maxd = std::min(QAS_CT_MAX_D, n_qubits - 1);
+    cx->c_dmin = std::min(cx->c_dmin, cx->c_maxd);
+    cx->c_nbins = cx->c_maxd - cx->c_dmin + 1;
+  }
+  cx->d_counter = cx->d_bins ? cx->d_bins + QAS_MAX_BINS + cx->c_nbins : nullptr;
+  std::vector<uint32_t> fz;
+  std::vector<double> fc;
+  std::vector<int> fbegin;
+  if (cx->compress) {
+    for (int imag = 0; imag < 2; ++imag) {
+      for (auto &kv : slices) {
+        if (kv.first.second != imag) continue;
+        cx->sxflat.push_back((uint32_t)kv.first.first);
+        fbegin.push_back((int)fz.size());
+        for (auto &zc : kv.second) { fz.push_back(zc.first); fc.push_back(zc.second); }
+      }
+      if (!imag) cx->S_real_flat = (int)cx->sxflat.size();
+    }
+    fbegin.push_back((int)fz.size());
+    cx->S_flat = (int)cx->sxflat.size();
+    if (cx->S_flat > 65535 || (double)cx->S_flat * (double)dim * 8.0 > 4.0e9) cx->compress = false;
+  }
+  if (cx->compress) {
+    guard(cudaMalloc(&cx->d_vflat, sizeof(double) * dim * cx->S_flat), "cudaMalloc flat sign tables");
+    guard(cudaMalloc(&cx->d_sxflat, 4 * (size_t)cx->S_flat), "cudaMalloc sxflat");
+    guard(cudaEventCreateWithFlags(&cx->fork_ev, cudaEventDisableTiming), "cudaEventCreate");
+    for (int i = 0; i <= cx->c_nbins && i < QAS_MAX_BINS; ++i) {
+      guard(cudaStreamCreateWithFlags(&cx->side[i], cudaStreamNonBlocking), "cudaStreamCreate");
+      guard(cudaEventCreateWithFlags(&cx->join_ev[i], cudaEventDisableTiming), "cudaEventCreate");
+    }
+  }
   if (want_phase) {
     guard(cudaMalloc(&cx->d_phase, 8 * sizeof(unsigned long long)), "cudaMalloc phase clocks");
     guard(cudaMemset(cx->d_phase, 0, 8 * sizeof(unsigned long long)), "cudaMemset phase clocks");
@@ -397,6 +328,25 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
         n_qubits, cx->S, cx->RB, cx->rb[0], cx->rb[1], cx->rb[2], cx->wc, d_sx, d_sbegin, d_tz, d_tc, cx->d_vtab);
     guard(cudaGetLastError(), "build_sign_tables launch");
     guard(cudaStreamSynchronize(cx->stream), "build_sign_tables");
+    if (cx->compress) {     // flat rows [slice][physical index] for the compressed path (RB = 0 layout)
+      uint32_t *d_fz = nullptr; double *d_fc = nullptr; int *d_fb = nullptr;
+      guard(cudaMalloc(&d_fz, 4 * std::max<size_t>(fz.size(), 1)), "cudaMalloc fz");
+      guard(cudaMalloc(&d_fc, 8 * std::max<size_t>(fc.size(), 1)), "cudaMalloc fc");
+      guard(cudaMalloc(&d_fb, 4 * fbegin.size()), "cudaMalloc fbegin");
+      if (rc == QAS_OK) {
+        guard(cudaMemcpy(cx->d_sxflat, cx->sxflat.data(), 4 * cx->sxflat.size(), cudaMemcpyHostToDevice), "copy sxflat");
+        guard(cudaMemcpy(d_fz, fz.data(), 4 * fz.size(), cudaMemcpyHostToDevice), "copy fz");
+        guard(cudaMemcpy(d_fc, fc.data(), 8 * fc.size(), cudaMemcpyHostToDevice), "copy fc");
+        guard(cudaMemcpy(d_fb, fbegin.data(), 4 * fbegin.size(), cudaMemcpyHostToDevice), "copy fbegin");
+        const size_t ftotal = dim * cx->S_flat;
+        WComb nowc{};
+        build_sign_tables_kernel<<<(unsigned)((ftotal + 255) / 256), 256, 0, cx->stream>>>(
+            n_qubits, cx->S_flat, 0, 0, 0, 0, nowc, cx->d_sxflat, d_fb, d_fz, d_fc, cx->d_vflat);
+        guard(cudaGetLastError(), "build flat sign tables launch");
+        guard(cudaStreamSynchronize(cx->stream), "build flat sign tables");
+      }
+      cudaFree(d_fz); cudaFree(d_fc); cudaFree(d_fb);
+    }
   }
   cudaFree(d_tz); cudaFree(d_tc); cudaFree(d_sbegin); cudaFree(d_sx);
   if (rc != QAS_OK) { qas_ctx_destroy(cx); return rc; }
@@ -407,7 +357,14 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
 extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   if (!ctx) return QAS_OK;
   cudaSetDevice(ctx->device);
-  cudaFree(ctx->d_counter); cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_cdesc_plain); cudaFree(ctx->d_cdesc_u);
+  cudaFree(ctx->d_bins); cudaFree(ctx->d_order); cudaFree(ctx->d_vflat); cudaFree(ctx->d_sxflat);
+  if (ctx->h_bins) cudaFreeHost(ctx->h_bins);
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  for (int i = 0; i < QAS_MAX_BINS; ++i) {
+    if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+  }
+  cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_cdesc_plain); cudaFree(ctx->d_cdesc_u);
   cudaFree(ctx->d_U); cudaFree(ctx->d_dU); cudaFree(ctx->d_k); cudaFree(ctx->d_params);
   cudaFree(ctx->d_energy); cudaFree(ctx->d_grad); cudaFree(ctx->d_partial); cudaFree(ctx->d_dense);
   cudaFree(ctx->d_gstate); cudaFree(ctx->d_mout); cudaFree(ctx->d_tape); cudaFree(ctx->d_phase);
@@ -446,121 +403,6 @@ extern "C" int qas_get_stats(const qas_ctx *cctx, qas_stats *out) {
   }
   *out = ctx->stats;
   return QAS_OK;
-}
-
-// ---------------------------------------------------------------------------------- launch
-static size_t sdesc_bytes(int S) { return (((size_t)S * 4) + 15) & ~(size_t)15; }
-
-// CTAs per SM the register allocation is bounded for: the 3-gate adjoint pass holds 8 + 8
-// amplitudes and a 2x2 cross matrix in registers (128-register budget)
-constexpr int qas_minb(int n, int T, int blk) { return blk == 128 ? 3 : (qas_block_bits(n, T) >= 2 ? 2 : 3); }
-
-template <int N, int T, bool GRAD, int RBH, int PD, int GMAX_ = 0, int MINB_ = 0, int BLK = 256>
-static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t st) {
-  constexpr int TEAMS = BLK / T;
-  const size_t smem = eval_team_smem_bytes(N, T, GRAD, P.ops_cap, true, qas_stage_u(N)) * TEAMS + sdesc_bytes(P.C_real + P.C_imag);
-  auto kern = eval_kernel<N, T, GRAD, (GMAX_ ? GMAX_ : qas_gmax(N, T)), RBH, PD, (MINB_ ? MINB_ : qas_minb(N, T, BLK)), BLK>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLK, smem);
-  const int grid = std::min((P.B + TEAMS - 1) / TEAMS, std::max(1, occ) * ctx->num_sms);   // persistent CTAs, queue-fed
-  e = cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st);
-  if (e != cudaSuccess) return e;
-  ctx->stats.teams_per_cta = TEAMS;
-  ctx->stats.threads_per_team = T;
-  ctx->stats.ctas_per_sm = occ;
-  ctx->stats.smem_bytes_per_cta = (int)smem;
-  ctx->stats.path = 0;
-  kern<<<grid, BLK, smem, st>>>(P);
-  return cudaGetLastError();
-}
-
-template <bool GRAD>
-static cudaError_t launch_gmem(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
-  const size_t smem = eval_team_smem_bytes(P.n, 256, GRAD, P.ops_cap, false, true) + sdesc_bytes(P.C_real + P.C_imag);
-  auto kern = eval_kernel<0, 256, GRAD, 2, 2, 2, 2>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
-  occ = std::max(1, std::min(occ, 4));
-  const size_t per_cta = ((size_t)1 << P.n) * (GRAD ? 2 : 1);
-  int grid = std::min(P.B, ctx->num_sms * occ);
-  while (grid > 1 && per_cta * grid * 16 > ((size_t)8 << 30)) grid /= 2;
-  e = ensure(&ctx->d_gstate, &ctx->cap_gstate, per_cta * grid);
-  if (e != cudaSuccess) return e;
-  P.gstate = ctx->d_gstate;
-  e = cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st);
-  if (e != cudaSuccess) return e;
-  ctx->stats.teams_per_cta = 1;
-  ctx->stats.threads_per_team = 256;
-  ctx->stats.ctas_per_sm = occ;
-  ctx->stats.smem_bytes_per_cta = (int)smem;
-  ctx->stats.path = 1;
-  kern<<<grid, 256, smem, st>>>(P);
-  return cudaGetLastError();
-}
-
-// (N, T) instantiations: the default team size of each qubit count plus tuning alternatives
-// n <= 5: thread-per-circuit kernel (eval_small_kernel); QAS_B200_SMALL=0 keeps the team kernel
-static bool use_small_kernel(const qas_ctx *ctx) { return ctx->n <= 5 && ctx->small_kernel; }
-// ... and the packed tape must fit next to the statevectors (very deep circuits fall back to the team kernel)
-static bool small_fits(const qas_ctx *ctx, int ops_cap) {
-  return eval_small_smem_bytes(ctx->n, ctx->n <= 4 ? 128 : 64, true, ops_cap, ctx->c) <= 200 * 1024;
-}
-
-template <int N, bool GRAD>
-static cudaError_t launch_small(qas_ctx *ctx, const EvalParams &P, cudaStream_t st) {
-  constexpr int BLK = N <= 4 ? 128 : 64;
-  const size_t smem = eval_small_smem_bytes(N, BLK, GRAD, P.ops_cap, P.c);
-  auto kern = eval_small_kernel<N, GRAD, BLK>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLK, smem);
-  ctx->stats.teams_per_cta = BLK;
-  ctx->stats.threads_per_team = 1;
-  ctx->stats.ctas_per_sm = occ;
-  ctx->stats.smem_bytes_per_cta = (int)smem;
-  ctx->stats.path = 2;
-  kern<<<(P.B + BLK - 1) / BLK, BLK, smem, st>>>(P);
-  return cudaGetLastError();
-}
-
-template <bool GRAD>
-static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
-  if (ctx->small_now) {
-    switch (P.n) {
-      case 2: return launch_small<2, GRAD>(ctx, P, st);
-      case 3: return launch_small<3, GRAD>(ctx, P, st);
-      case 4: return launch_small<4, GRAD>(ctx, P, st);
-      default: return launch_small<5, GRAD>(ctx, P, st);
-    }
-  }
-  const int nmax_smem = GRAD ? 12 : 13;
-  int T = ctx->T, blk = ctx->blk;
-  // energy-only launches at n = 10: one warp per circuit (no team barriers; same GMAX / RB / PD, so tapes
-  // and sign tables are shared with the gradient launches).  LiH reward-only 72 -> 84 M evals/s; the
-  // gradient kernel is slower that way (1.15 -> 1.44 ms: the dense tail of the batch runs on one warp).
-  if (!GRAD && P.n == 10 && ctx->team_shift == 0 && T == 64 && blk == 128) { T = 32; blk = 64; }
-  if (P.n <= nmax_smem) {
-    const size_t smem = eval_team_smem_bytes(P.n, T, GRAD, P.ops_cap, true, qas_stage_u(P.n)) * (blk / T) + sdesc_bytes(P.C_real + P.C_imag);
-    if (smem <= 227 * 1024) {
-#define QAS_CASE(N_, T_, BLK_) \
-  if (P.n == N_ && T == T_ && blk == BLK_) return launch_smem<N_, T_, GRAD, qas_hrb(N_, T_), qas_hpd(N_, T_), 0, 0, BLK_>(ctx, P, st);
-      QAS_CASE(2, 8, 256) QAS_CASE(3, 8, 256) QAS_CASE(4, 8, 256) QAS_CASE(5, 16, 256) QAS_CASE(6, 32, 256)
-      QAS_CASE(7, 32, 256) QAS_CASE(8, 32, 256) QAS_CASE(9, 64, 256) QAS_CASE(10, 64, 128) QAS_CASE(11, 128, 128)
-      QAS_CASE(12, 256, 256)
-      QAS_CASE(10, 32, 64)                                                                          // energy-only launches; QAS_B200_TEAM_SHIFT=-1
-      QAS_CASE(8, 64, 256) QAS_CASE(9, 128, 256) QAS_CASE(10, 128, 256) QAS_CASE(11, 256, 256)     // QAS_B200_TEAM_SHIFT=1
-#undef QAS_CASE
-      if constexpr (!GRAD) { if (P.n == 13 && T == 256) return launch_smem<13, 256, false, qas_hrb(13, 256), qas_hpd(13, 256)>(ctx, P, st); }
-    }
-  }
-  // the global-memory instantiation is compiled for 256-thread teams, 3-gate passes, 4-amplitude H rows
-  if (ctx->T != 256 || ctx->RB != 2 || ctx->PD != 2 || ctx->GMAX != 2) return cudaErrorInvalidConfiguration;
-  return launch_gmem<GRAD>(ctx, P, st);
 }
 
 // gate tables sized for depth p (constant rows filled once)
@@ -647,18 +489,31 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     dgrad = nullptr;
     if (grad_dense) { CK(ensure(&ctx->d_dense, &ctx->cap_dense, npar)); ddense = ctx->d_dense; }
   }
-  if (want_grad && (!dev || !grad_compact)) {
+  ctx->small_now = small;
+  const int ops_cap = std::max(1, p * ctx->max_expansion);
+  // ---- which kernels evaluate this call, decided once: the tape planner, the class descriptors and the
+  // launches must agree on the index layout (swizzled shared-memory states vs the plain global-memory slab)
+  int cT = 0, cblk = 0;
+  const int cpath = small ? 2 : qas_classic_path(ctx, want_grad, ops_cap, &cT, &cblk);
+  if (cpath < 0)
+    return fail(ctx, QAS_ERR_UNSUPPORTED, "tapes of this depth do not fit the shared-memory kernel of this register size and the "
+                                          "global-memory kernel is not compiled for its pass / H-row configuration");
+  const bool smem_path = cpath == 0;
+  const int swz_plan = smem_path ? 1 : 0;
+  // support-compressed path: every circuit is binned by the dimension d of its support span; d < n goes to the
+  // compressed kernel of its bin, d == n stays with the classic kernel (the full bin)
+  const bool use_c = ctx->compress && !small && qas_ccompile_smem_bytes(ctx, ops_cap, p) <= 96 * 1024;
+  const bool fused_reduce = grad_dense && !grad_compact && !small;   // batch mean only: no per-circuit gradients
+  if (want_grad && !fused_reduce && (!dev || !grad_compact)) {
     CK(ensure(&ctx->d_grad, &ctx->cap_grad, ng));
     dgrad = ctx->d_grad;
   }
 
-  ctx->small_now = small;
   EvalParams P{};
   P.k = dk; P.pool = ctx->d_pool; P.U = ctx->d_U; P.dU = ctx->d_dU; P.grad = dgrad;
   P.vtab = ctx->d_vtab; P.rb0 = ctx->rb[0]; P.rb1 = ctx->rb[1]; P.rb2 = ctx->rb[2];
   P.C_real = ctx->C_real; P.C_imag = ctx->C_imag;
   {   // class descriptors and W combinations as byte offsets, swizzled for the shared-memory path
-    const bool smem_path = ctx->n <= (want_grad ? 12 : 13) && !small;
     P.cdesc = smem_path ? ctx->d_sdesc : ctx->d_cdesc_plain;
     P.cdesc_u = ctx->d_cdesc_u;
     P.hs_min = smem_path ? ctx->hs_min : 0;
@@ -670,15 +525,22 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   P.energy = denergy; P.gstate = nullptr; P.mout = nullptr; P.phase_clk = ctx->d_phase; P.work_counter = ctx->d_counter;
   P.init_basis = ctx->init_basis;
   P.B = B; P.p = p; P.c = c; P.l = l; P.n = ctx->n;
-  P.ops_cap = std::max(1, p * ctx->max_expansion);
+  P.ops_cap = ops_cap;
   P.init_kind = ctx->init_kind;
 
-  const size_t rec_words = qas_rec_words(P.ops_cap, ctx->n);
+  const size_t rec_words = std::max(qas_rec_words(ops_cap, ctx->n),
+                                    use_c ? (size_t)QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS + qas_cinfo_words(ctx->n, ctx->S_flat) : (size_t)0);
   CK(ensure(&ctx->d_tape, &ctx->cap_tape, rec_words * (size_t)B));
   P.tape = ctx->d_tape;
+  P.rec_stride = rec_words;
+  if (use_c) {
+    CK(ensure(&ctx->d_order, &ctx->cap_order, (size_t)QAS_MAX_BINS * B));
+    P.order = ctx->d_order + (size_t)ctx->c_nbins * B;
+    P.count = ctx->d_bins + ctx->c_nbins;
+  }
 
   if (want_grad) {
-    CK(ensure(&ctx->d_mout, &ctx->cap_mout, (size_t)B * P.ops_cap * 8));
+    CK(ensure(&ctx->d_mout, &ctx->cap_mout, (size_t)B * ops_cap * 8));
     P.mout = ctx->d_mout;
   }
 
@@ -689,15 +551,17 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   };
   if (!dev && !tiny) CK(cudaEventRecord(ctx->ev0, st));
   stamp(0);
-  if (want_grad) CK(cudaMemsetAsync(dgrad, 0, ng * 8, st));
+  if (want_grad && !fused_reduce) { CK(cudaMemsetAsync(dgrad, 0, ng * 8, st)); ctx->stats.launches += 1; }
+  if (!small) CK(cudaMemsetAsync(ctx->d_bins, 0, sizeof(int) * 2 * QAS_MAX_BINS, st));   // bin counts + work-queue heads
   stamp(1);
   // Tiny host-pointer batches (the one-reward-at-a-time rollouts of the tree search): the tape
   // compiler and pass planner are host-callable, and one CPU core runs them in a few microseconds,
   // whereas a single GPU thread needs tens -- compile here and upload the records.
-  const int swz_plan = (ctx->n <= (want_grad ? 12 : 13) && !small) ? 1 : 0;
+  const bool host_compile = !small && !dev && B <= 16;
+  int h_count[QAS_MAX_BINS] = {0};
   if (small) {
     // the thread-per-circuit kernel compiles its own tapes
-  } else if (!dev && B <= 16) {
+  } else if (host_compile) {
     const size_t words = rec_words * (size_t)B;
     if (ctx->cap_htape < words) {
       if (ctx->h_tape) cudaFreeHost(ctx->h_tape);
@@ -705,59 +569,125 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
       CK(cudaHostAlloc((void **)&ctx->h_tape, std::max<size_t>(words, 4096) * 4, cudaHostAllocDefault));
       ctx->cap_htape = std::max<size_t>(words, 4096);
     }
-    uint32_t col[32], row[32];
+    const size_t bwords = (size_t)QAS_MAX_BINS * (1 + (size_t)B);
+    if (use_c && ctx->cap_hbins < bwords) {
+      if (ctx->h_bins) cudaFreeHost(ctx->h_bins);
+      ctx->h_bins = nullptr; ctx->cap_hbins = 0;
+      CK(cudaHostAlloc((void **)&ctx->h_bins, std::max<size_t>(bwords, 1024) * 4, cudaHostAllocDefault));
+      ctx->cap_hbins = std::max<size_t>(bwords, 1024);
+    }
+    uint32_t col[32], row[32], ev[32], ec[32];
+    std::vector<uint32_t> mt((size_t)ops_cap);
     for (int b = 0; b < B; ++b) {
       uint32_t *rec = ctx->h_tape + (size_t)b * rec_words;
-      QasTapeSink sink{rec + QAS_REC_HDR, P.ops_cap, 0, 0};
+      uint32_t *rops = rec + QAS_REC_HDR, *rci = rops + (size_t)ops_cap * QAS_OP_WORDS;
+      QasTapeSink sink{rops, ops_cap, 0, 0};
       const int stc = qas_compile_circuit(k + (size_t)b * p, p, ctx->pool.data(), c, ctx->n, col, row, sink);
-      const int nops = stc ? 0 : sink.n;
+      int nops = stc ? 0 : sink.n;
       const uint32_t init_index = (ctx->init_kind == QAS_INIT_BASIS && !stc) ? qas_frame_map_basis(col, ctx->n, ctx->init_basis) : 0u;
-      rec[0] = (uint32_t)nops; rec[1] = (uint32_t)stc; rec[2] = init_index;
-      rec[3] = (uint32_t)qas_plan_groups(rec + QAS_REC_HDR, nops, ctx->GMAX, ctx->n, ctx->init_kind, init_index,
-                                         rec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS, swz_plan,
-                                         &ctx->hinfo, rec + qas_rec_hd_offset(P.ops_cap, ctx->n));
+      int ngroups = qas_mark_groups(rops, nops, ctx->GMAX);
+      int d = QAS_CT_FULL;
+      if (use_c) d = qas_compress_tape(rops, &nops, &ngroups, ctx->n, ctx->sxflat.data(), ctx->S_flat, ev, ec, mt.data(), rci,
+                                       rci + 1 + ctx->n, ctx->c_maxd);
+      rec[0] = (uint32_t)nops; rec[1] = (uint32_t)stc; rec[3] = (uint32_t)ngroups;
+      if (d >= 0) {
+        rec[2] = (uint32_t)d;
+      } else {
+        rec[2] = init_index;
+        qas_plan_marked(rops, nops, ngroups, ctx->n, ctx->init_kind, init_index, rci, swz_plan, &ctx->hinfo,
+                        rec + qas_rec_hd_offset(ops_cap, ctx->n));
+      }
+      if (use_c) {
+        const int bin = d >= 0 ? std::max(d, ctx->c_dmin) - ctx->c_dmin : ctx->c_nbins;
+        ctx->h_bins[QAS_MAX_BINS + (size_t)bin * B + h_count[bin]++] = b;
+      }
     }
     CK(cudaMemcpyAsync(ctx->d_tape, ctx->h_tape, words * 4, cudaMemcpyHostToDevice, st));
-  } else {
-    const int cthr = 64;
-    // ops in shared memory only while that keeps >= 8 CTAs per SM resident (short tapes)
-    size_t ops_smem_limit = 24 * 1024;
-    if (const char *oe = getenv("QAS_B200_COMPILE_SMEM_KB")) ops_smem_limit = (size_t)std::max(0, atoi(oe)) * 1024;   // tuning knob
-    const bool ops_smem = qas_compile_smem_words(ctx->n, P.ops_cap, p, true) * 4 * cthr <= ops_smem_limit;
-    const size_t csm = qas_compile_smem_words(ctx->n, P.ops_cap, p, ops_smem) * 4 * cthr;
-    if (csm > 200 * 1024) return fail(ctx, QAS_ERR_UNSUPPORTED, "structure lists too long for the tape-compile kernel");
-    if (ops_smem) {
-      CK(cudaFuncSetAttribute(compile_tapes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-      compile_tapes_kernel<true><<<(B + cthr - 1) / cthr, cthr, csm, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap, ctx->init_kind,
-                                                                         ctx->init_basis, ctx->GMAX, swz_plan, ctx->hinfo, ctx->d_tape);
-    } else {
-      CK(cudaFuncSetAttribute(compile_tapes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-      compile_tapes_kernel<false><<<(B + cthr - 1) / cthr, cthr, csm, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, P.ops_cap, ctx->init_kind,
-                                                                          ctx->init_basis, ctx->GMAX, swz_plan, ctx->hinfo, ctx->d_tape);
+    if (use_c) {
+      for (int i = 0; i < QAS_MAX_BINS; ++i) ctx->h_bins[i] = h_count[i];
+      CK(cudaMemcpyAsync(ctx->d_bins, ctx->h_bins, sizeof(int) * QAS_MAX_BINS, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(ctx->d_order, ctx->h_bins + QAS_MAX_BINS, sizeof(int) * (size_t)(ctx->c_nbins + 1) * B, cudaMemcpyHostToDevice, st));
     }
+  } else if (use_c) {
+    CompileCParams C{};
+    C.k = dk; C.pool = ctx->d_pool; C.sxflat = ctx->d_sxflat; C.tape = ctx->d_tape; C.bin_count = ctx->d_bins;
+    C.bin_order = ctx->d_order; C.B = B; C.p = p; C.c = c; C.n = ctx->n; C.ops_cap = ops_cap; C.S = ctx->S_flat;
+    C.gmax = ctx->GMAX; C.dmin = ctx->c_dmin; C.max_d = ctx->c_maxd; C.full_bin = ctx->c_nbins; C.rec_stride = rec_words;
+    CK(qas_launch_compile_c(ctx, C, st));
+    CK(qas_launch_plan_full(ctx, ctx->d_tape, rec_words, P.count, P.order, B, ops_cap, swz_plan, st));
+    ctx->stats.launches += 2;
+  } else {
+    { const int rc_ = qas_launch_compile_classic(ctx, dk, B, p, ops_cap, swz_plan, rec_words, st); if (rc_ != QAS_OK) return rc_; }
+    ctx->stats.launches += 1;
   }
   CK(cudaGetLastError());
   stamp(2);
   if (!resident) {
     build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
     CK(cudaGetLastError());
+    ctx->stats.launches += 1;
   }
   if (!tiny) CK(cudaEventRecord(ctx->ek0, st));
   stamp(3);
-  if (want_grad) CK(launch_eval<true>(ctx, P, st)); else CK(launch_eval<false>(ctx, P, st));
+  auto launch_classic = [&](cudaStream_t s_) { return want_grad ? qas_launch_eval_grad(ctx, P, s_) : qas_launch_eval_nograd(ctx, P, s_); };
+  if (!use_c) {
+    CK(launch_classic(st));
+    ctx->stats.launches += 1;
+  } else {
+    // one launch per bin, largest registers first.  Device-compiled batches do not know the bin counts on the
+    // host: every bin is launched (an empty one exits at once), each on its own forked stream so that the
+    // persistent CTAs of a small bin fill the tail of a large one.  Host-compiled batches launch the non-empty
+    // bins back to back on the call's stream.
+    EvalCParams Q{};
+    Q.tape = ctx->d_tape; Q.U = ctx->d_U; Q.vflat = ctx->d_vflat; Q.energy = denergy; Q.mout = P.mout;
+    Q.rec_stride = rec_words; Q.n = ctx->n; Q.ops_cap = ops_cap; Q.S = ctx->S_flat; Q.S_real = ctx->S_real_flat;
+    const bool fork = !host_compile;
+    if (fork) CK(cudaEventRecord(ctx->fork_ev, st));
+    int nside = 0;
+    for (int bin = ctx->c_nbins; bin >= 0; --bin) {
+      if (host_compile && h_count[bin] == 0) continue;
+      const int max_work = host_compile ? h_count[bin] : B;
+      cudaStream_t s_ = st;
+      if (fork && bin != ctx->c_nbins) {
+        s_ = ctx->side[nside];
+        CK(cudaStreamWaitEvent(s_, ctx->fork_ev, 0));
+      }
+      if (bin == ctx->c_nbins) {
+        if (host_compile) { const int keepB = P.B; P.B = max_work; const cudaError_t le = launch_classic(s_); P.B = keepB; CK(le); }
+        else CK(launch_classic(s_));
+      } else {
+        Q.slot_bits = ctx->c_dmin + bin;
+        Q.order = ctx->d_order + (size_t)bin * B;
+        Q.count = ctx->d_bins + bin;
+        Q.work_counter = ctx->d_bins + QAS_MAX_BINS + bin;
+        CK(qas_launch_evalc(ctx, Q, max_work, want_grad, s_));
+      }
+      ctx->stats.launches += 1;
+      if (fork && bin != ctx->c_nbins) {
+        CK(cudaEventRecord(ctx->join_ev[nside], s_));
+        CK(cudaStreamWaitEvent(st, ctx->join_ev[nside], 0));
+        ++nside;
+      }
+    }
+  }
   if (!tiny) { CK(cudaEventRecord(ctx->ek1, st)); ctx->ek_pending = true; }
   stamp(4);
-  ctx->stats.launches += 3;
-  if (want_grad && !small) {
-    const size_t nthr = (size_t)B * P.ops_cap;
-    grad_finalize_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ctx->d_tape, ctx->d_mout, ctx->d_dU, B, p, l,
-                                                                        P.ops_cap, ctx->n, dgrad);
+  if (want_grad && !small && !fused_reduce) {
+    const size_t nthr = (size_t)B * ops_cap;
+    grad_finalize_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ctx->d_tape, rec_words, ctx->d_mout, ctx->d_dU, B, p, l,
+                                                                        ops_cap, dgrad);
     CK(cudaGetLastError());
     ctx->stats.launches += 1;
   }
   stamp(5);
 
-  if (grad_dense) {
+  if (fused_reduce) {
+    const double scale = (flags & QAS_F_GRAD_SUM) ? 1.0 : 1.0 / (double)B;
+    CK(qas_launch_finalize_reduce(ctx, ctx->d_tape, rec_words, ctx->d_mout, B, p, ops_cap, scale, ddense, st));
+    ctx->stats.launches += 2;
+    stamp(6);
+    stamp(7);
+  } else if (grad_dense) {
     int chunk = 64;            // circuits per CTA of the first stage (1024 CTAs at B = 65536)
     if (const char *ce = getenv("QAS_B200_REDUCE_CHUNK")) chunk = std::max(1, atoi(ce));   // tuning knob
     const int nchunks = (B + chunk - 1) / chunk;
@@ -854,6 +784,39 @@ extern "C" int qas_plan_hsupport_host(int n_qubits, const uint32_t *ops, int num
   std::vector<uint32_t> gd((size_t)std::max(1, num_ops) * QAS_GD_STRIDE(n_qubits));
   for (int w = 0; w < QAS_HD_WORDS; ++w) hdesc[w] = 0u;
   qas_plan_groups(tmp.data(), num_ops, 2, n_qubits, init_kind, init_index, gd.data(), 0, &hi, hdesc);
+  return QAS_OK;
+}
+
+extern "C" int qas_compile_ctape_host(int n_qubits, const qas_pool_entry *pool, int c, int p, const int32_t *k,
+                                      int gmax, const uint32_t *xmasks, int num_xmasks, int max_d,
+                                      uint32_t *out_ops, int max_ops, int *num_ops, int *num_groups, int *dim,
+                                      uint32_t *basis_out, uint32_t *list_out, int *num_list) {
+  if (n_qubits < 1 || n_qubits > QAS_MAX_QUBITS || !pool || c <= 0 || p <= 0 || !k || !out_ops || !num_ops || !num_groups ||
+      !dim || !basis_out || gmax < 1 || gmax > 3 || num_xmasks < 0 || (num_xmasks > 0 && (!xmasks || !list_out)) || !num_list ||
+      max_d < 1 || max_d > QAS_CT_MAX_D)
+    return QAS_ERR_INVALID;
+  std::string why;
+  int me = 1;
+  if (validate_pool(pool, c, n_qubits, 3, why, &me)) { g_create_error = why; return QAS_ERR_INVALID; }
+  uint32_t col[32], row[32];
+  QasTapeSink sink{out_ops, max_ops, 0, 0};
+  const int st = qas_compile_circuit(k, p, pool, c, n_qubits, col, row, sink);
+  if (st == 1) { g_create_error = "structure list entry out of range"; return QAS_ERR_INVALID; }
+  if (st == 2) { g_create_error = "tape buffer too small"; return QAS_ERR_NOMEM; }
+  int nops = sink.n;
+  int ngroups = qas_mark_groups(out_ops, nops, gmax);
+  std::vector<uint32_t> ev(n_qubits), ec(n_qubits), mt((size_t)std::max(1, nops)), cinfo(qas_cinfo_words(n_qubits, num_xmasks));
+  const int d = qas_compress_tape(out_ops, &nops, &ngroups, n_qubits, xmasks, num_xmasks, ev.data(), ec.data(), mt.data(),
+                                  cinfo.data(), cinfo.data() + 1 + n_qubits, max_d);
+  *num_ops = nops;
+  *num_groups = ngroups;
+  *dim = d;
+  *num_list = 0;
+  if (d >= 0) {
+    for (int q = 0; q < n_qubits; ++q) basis_out[q] = cinfo[1 + q];
+    *num_list = (int)cinfo[0];
+    for (int s = 0; s < *num_list; ++s) list_out[s] = cinfo[1 + n_qubits + s];
+  }
   return QAS_OK;
 }
 

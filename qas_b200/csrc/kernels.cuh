@@ -42,7 +42,10 @@ struct EvalParams {
   double *grad;                // [B][p][l] compact gradients, zero-filled (thread-per-circuit kernel only)
   unsigned long long *phase_clk;   // diagnostic: summed per-team clock64 deltas [prologue, forward, H, adjoint] or null
   int *work_counter;           // global queue head of the team kernels (zeroed before every launch)
-  const uint32_t *tape;        // [B][4 + ops_cap*5] compiled tape records (compile_tapes_kernel)
+  const uint32_t *tape;        // [B][rec_stride] compiled tape records (compile_tapes_kernel / compile_ctapes_kernel)
+  size_t rec_stride;           // words per record
+  const int *order;            // circuit indices of the work queue (null: 0 .. B-1)
+  const int *count;            // ... and how many (null: B)
   uint64_t init_basis;
   int B, p, c, l, n, ops_cap, init_kind;
 };
@@ -96,7 +99,7 @@ __device__ __forceinline__ double2 cexpi(double t) {
 __device__ __forceinline__ double2 cscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
 __device__ __forceinline__ double2 cmuli(double2 a) { return make_double2(-a.y, a.x); }   // i*a
 
-__global__ void build_gate_table_kernel(const qas_pool_entry *pool, int c, int p, int l,
+static __global__ void build_gate_table_kernel(const qas_pool_entry *pool, int c, int p, int l,
                                         const double *params, GateTab *U, GateDTab *dU) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p * c) return;
@@ -218,7 +221,7 @@ __host__ __device__ __forceinline__ uint32_t qas_deposit_rest(uint32_t u, int RB
   return u;
 }
 
-__global__ void build_sign_tables_kernel(int n, int S, int RB, int rb0, int rb1, int rb2, WComb wc,
+static __global__ void build_sign_tables_kernel(int n, int S, int RB, int rb0, int rb1, int rb2, WComb wc,
                                          const uint32_t *sx, const int *sbegin, const uint32_t *tz,
                                          const double *tc, double *vtab) {
   const size_t dim = (size_t)1 << n;
@@ -298,63 +301,6 @@ __host__ __device__ __forceinline__ size_t qas_rec_words(int ops_cap, int n) {
 __host__ __device__ __forceinline__ size_t qas_rec_hd_offset(int ops_cap, int n) {
   return (size_t)QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS + (size_t)ops_cap * QAS_GD_STRIDE(n);
 }
-// OPS_SMEM: the ops are built and planned in shared memory (the planner reads them back many
-// times; from global memory every read is a dependent L2 round trip) and copied out warp-
-// cooperatively, coalesced.  Per thread: frame (2n+1 words) | ops (ops_cap*5 words, odd stride).
-// plus the circuit's structure list (p words, odd stride), staged coalesced by the whole CTA.
-__host__ __device__ __forceinline__ size_t qas_compile_smem_words(int n, int ops_cap, int p, bool ops_smem) {
-  return (size_t)(2 * n + 1) + (size_t)(p | 1) + (ops_smem ? (size_t)((ops_cap * QAS_OP_WORDS) | 1) : 0);
-}
-template <bool OPS_SMEM>
-__global__ void compile_tapes_kernel(const int32_t *k, const qas_pool_entry *pool, int B, int p, int c,
-                                     int n, int ops_cap, int init_kind, uint64_t init_basis,
-                                     int gmax, int swizzled, QasHInfo hinfo, uint32_t *tape) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = b < B;
-  // GF(2) frame (col / row, indexed by wire at run time): shared memory, odd stride per thread
-  extern __shared__ uint32_t frame_smem[];
-  const size_t stride = qas_compile_smem_words(n, ops_cap, p, OPS_SMEM);
-  uint32_t *mine = frame_smem + (size_t)threadIdx.x * stride;
-  uint32_t *col = mine, *row = col + n;
-  int32_t *ks = reinterpret_cast<int32_t *>(mine + (2 * n + 1));
-  uint32_t *rec = tape + (size_t)(live ? b : 0) * qas_rec_words(ops_cap, n);
-  uint32_t *ops = OPS_SMEM ? mine + (2 * n + 1) + (p | 1) : rec + QAS_REC_HDR;
-  {   // the CTA's structure lists are contiguous in global memory: coalesced copy, row t -> thread t
-    const size_t first = (size_t)blockIdx.x * blockDim.x * p;
-    const size_t count = (size_t)min((int)blockDim.x, B - (int)(blockIdx.x * blockDim.x)) * p;
-    for (size_t w = threadIdx.x; w < count; w += blockDim.x) {
-      const size_t t = w / p, i = w - t * p;
-      reinterpret_cast<int32_t *>(frame_smem + t * stride + (2 * n + 1))[i] = k[first + w];
-    }
-    __syncthreads();
-  }
-  int nops = 0;
-  if (live) {
-    QasTapeSink sink{ops, ops_cap, 0, 0};
-    const int st = qas_compile_circuit(ks, p, pool, c, n, col, row, sink);
-    nops = st ? 0 : sink.n;
-    const uint32_t init_index = (init_kind == QAS_INIT_BASIS && !st) ? qas_frame_map_basis(col, n, init_basis) : 0u;
-    rec[0] = (uint32_t)nops;
-    rec[1] = (uint32_t)st;
-    rec[2] = init_index;
-    rec[3] = (uint32_t)qas_plan_groups(ops, nops, gmax, n, init_kind, init_index,
-                                       rec + QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS, swizzled,   // passes per sweep
-                                       &hinfo, rec + qas_rec_hd_offset(ops_cap, n));
-  }
-  if constexpr (OPS_SMEM) {
-    __syncwarp();
-    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
-    for (int t = 0; t < 32; ++t) {
-      const int words = __shfl_sync(0xffffffffu, nops, t) * QAS_OP_WORDS;
-      const int bt = blockIdx.x * blockDim.x + wbase + t;
-      if (bt >= B) break;
-      const uint32_t *src = frame_smem + (size_t)(wbase + t) * stride + (2 * n + 1) + (p | 1);
-      uint32_t *dst = tape + (size_t)bt * qas_rec_words(ops_cap, n) + QAS_REC_HDR;
-      for (int w = lane; w < words; w += 32) dst[w] = src[w];
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------ evaluation
 // Shared-memory statevectors are stored swizzled (qas_swz, tape.h): a pass whose cosets differ
 // only in high index bits would otherwise put the lanes of a quarter-warp on the same 16-byte bank
@@ -649,7 +595,7 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
     if constexpr (GRAD) lam = psi + DIM;
   }
   const int rec_words = QAS_REC_HDR + P.ops_cap * QAS_OP_WORDS;       // staged part of a tape record
-  const size_t grec_words = qas_rec_words(P.ops_cap, n);              // its full length in global memory
+  const size_t grec_words = P.rec_stride;                             // its full length in global memory
   const int gstride = QAS_GD_STRIDE(n);
   uint32_t *rec = reinterpret_cast<uint32_t *>(base);
   uint32_t *ops = rec + QAS_REC_HDR;
@@ -680,8 +626,9 @@ __global__ void __launch_bounds__(BLK, MINB) eval_kernel(const EvalParams P) {
   for (;;) {
     if (tid == 0) *bslot = atomicAdd(P.work_counter, 1);
     team_sync<T>(team, tmask);
-    const int b = *bslot;
-    if (b >= P.B) break;
+    const int qslot = *bslot;
+    if (qslot >= (P.count ? *P.count : P.B)) break;
+    const int b = P.order ? P.order[qslot] : qslot;
     constexpr bool active = true;
 
     long long clk_prev = 0;
@@ -1117,12 +1064,12 @@ __global__ void __launch_bounds__(BLK) eval_small_kernel(const EvalParams P) {
 // dE/dtheta_j = 2 Re sum_ab (dU_j)_ab M_ab for every parametrised op of every circuit: one thread
 // per (circuit, tape op), all of its <= 3 parameter slots.  Kept out of the evaluation kernel so that no team
 // waits on the dU table (L2 latency) between passes.  grad must be zero-filled beforehand.
-__global__ void grad_finalize_kernel(const uint32_t *tape, const double *mout, const GateDTab *dU, int B,
-                                     int p, int l, int ops_cap, int n, double *grad) {
+static __global__ void grad_finalize_kernel(const uint32_t *tape, size_t rec_stride, const double *mout, const GateDTab *dU, int B,
+                                     int p, int l, int ops_cap, double *grad) {
   const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= (size_t)B * ops_cap) return;
   const int b = (int)(x / ops_cap), oi = (int)(x % ops_cap);
-  const uint32_t *rec = tape + (size_t)b * qas_rec_words(ops_cap, n);
+  const uint32_t *rec = tape + (size_t)b * rec_stride;
   if (oi >= (int)rec[0] || rec[1]) return;
   const uint32_t *o = rec + QAS_REC_HDR + (size_t)oi * QAS_OP_WORDS;
   const uint32_t mt = o[4];
@@ -1153,7 +1100,7 @@ __device__ __forceinline__ double nan_to_num_d(double x) {
   return x;
 }
 
-__global__ void grad_chunk_reduce_kernel(const int32_t *k, const double *grad, int B, int p, int c,
+static __global__ void grad_chunk_reduce_kernel(const int32_t *k, const double *grad, int B, int p, int c,
                                          int l, int chunk, int depth_tile, double *partial) {
   extern __shared__ double acc[];                 // [depth_tile][c][l]
   const int ch = blockIdx.x, i0 = blockIdx.y * depth_tile;
@@ -1191,7 +1138,7 @@ __global__ void grad_chunk_reduce_kernel(const int32_t *k, const double *grad, i
 
 // one warp per output element: lane q sums chunks q, q+32, ... in order, then a fixed shuffle tree
 // combines the 32 lanes -- the summation order depends only on (nchunks), never on scheduling
-__global__ void grad_final_reduce_kernel(const double *partial, int nchunks, size_t total,
+static __global__ void grad_final_reduce_kernel(const double *partial, int nchunks, size_t total,
                                          double scale, double *out) {
   const size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -1210,7 +1157,7 @@ __global__ void grad_final_reduce_kernel(const double *partial, int nchunks, siz
 //   g <- nan_to_num(grad) + noise_factor * noise        (mcts.py:346,349-350 / :404-406)
 //   m <- b1 m + (1-b1) g ;  v <- b2 v + (1-b2) g g ;  x <- x - step * m / (sqrt(v) + eps)
 // step = stepsize * sqrt(1 - b2^t) / (1 - b1^t) is computed on the host in double precision.
-__global__ void adam_step_kernel(double *x, const double *grad, double *m, double *v, const double *noise,
+static __global__ void adam_step_kernel(double *x, const double *grad, double *m, double *v, const double *noise,
                                  size_t n, double step, double b1, double b2, double eps, double noise_factor) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1225,7 +1172,7 @@ __global__ void adam_step_kernel(double *x, const double *grad, double *m, doubl
 
 // ------------------------------------------------------------------------------ FP64 peak
 // 8 independent DFMA chains per thread; 2 flop per DFMA.
-__global__ void dfma_peak_kernel(double *out, int iters, double a, double b) {
+static __global__ void dfma_peak_kernel(double *out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
          x6 = x0 + 6, x7 = x0 + 7;
   for (int i = 0; i < iters; ++i) {

@@ -1,0 +1,482 @@
+// kernels_c.cuh -- support-compressed evaluation path (sm_100a): c-tape compile kernel, the compressed
+// evaluation kernel and the fused gradient finalize + batch reduction.
+//
+// For all-zero start states a circuit with support span D (dim d) is evaluated as a d-qubit register in
+// the time-adapted basis of D (tape.h, "support-compressed tapes"): the support after j ops is the
+// prefix t < 2^{d_j} of a 2^d-amplitude register, so
+//   * a LiH-10q circuit (d = 3..10, mean 7) owns 2^d instead of 2^10 amplitudes of psi and lambda,
+//     one warp evaluates it without team barriers, and an SM holds 16-20 of them instead of 6;
+//   * passes need no planner descriptors: the cosets of a group are enumerated by inserting zeros at the
+//     pivots of its masks inside the prefix and projected onto the common kernel of the parity masks
+//     with two popcounts;
+//   * lambda = H psi reads the sign tables at the physical index i(t) = xor_k t_k B_k, only for the X masks
+//     inside D (the others connect the support to exact zeros).
+// Circuits are binned by d (one launch per bin, each with its own work queue, launched on forked streams
+// so that a small bin fills the tail of a large one); circuits with d == n keep the classic path
+// (kernels.cuh), fed from the same binning.
+// What the reference does instead: the dense 2^n state of PennyLane's default.qubit for every circuit
+// (qas/qml_models/hamiltonian_model.py:43-91).
+#pragma once
+#include "kernels.cuh"
+
+#define QAS_MAX_BINS 16
+
+struct CompileCParams {
+  const int32_t *k;
+  const qas_pool_entry *pool;
+  const uint32_t *sxflat;      // [S] X masks of the flat sign-table rows (real slices first)
+  uint32_t *tape;              // [B][rec_stride]
+  int *bin_count;              // [QAS_MAX_BINS]
+  int *bin_order;              // [QAS_MAX_BINS][B]
+  int B, p, c, n, ops_cap, S, gmax, dmin, max_d, full_bin;
+  size_t rec_stride;
+};
+
+// per-thread shared-memory words of the c-tape compile kernel:
+// col[n] row[n] ev[n] ec[n] | ks[p|1] | ops[(cap*5)|1] | mt[cap] | cinfo head [1 + n]
+__host__ __device__ __forceinline__ size_t qas_ccompile_smem_words(int n, int ops_cap, int p) {
+  return ((size_t)(4 * n) + (size_t)(p | 1) + (size_t)((ops_cap * QAS_OP_WORDS) | 1) + (size_t)ops_cap + (size_t)(1 + n)) | 1;
+}
+
+// One thread per circuit: CNOT-folded tape (tape.h), group marks, c-tape translation, record write,
+// bin assignment.  Record: [nops, status, d (or 0x80000000 | 0 for a classic record), ngroups | ops |
+// cinfo = nsl, B_0..B_{n-1}, list[nsl]].
+template <int CTHREADS>
+__global__ void __launch_bounds__(CTHREADS) compile_ctapes_kernel(const CompileCParams P) {
+  extern __shared__ uint32_t csm[];
+  const int b = blockIdx.x * CTHREADS + threadIdx.x;
+  const bool live = b < P.B;
+  const int n = P.n;
+  const size_t stride = qas_ccompile_smem_words(n, P.ops_cap, P.p);
+  uint32_t *mine = csm + (size_t)threadIdx.x * stride;
+  uint32_t *col = mine, *row = col + n, *ev = row + n, *ec = ev + n;
+  int32_t *ks = reinterpret_cast<int32_t *>(ec + n);
+  uint32_t *ops = reinterpret_cast<uint32_t *>(ks) + (P.p | 1);
+  uint32_t *mt = ops + ((P.ops_cap * QAS_OP_WORDS) | 1);
+  uint32_t *chead = mt + P.ops_cap;
+  {   // the CTA's structure lists are contiguous in global memory: coalesced copy, row t -> thread t
+    const size_t first = (size_t)blockIdx.x * CTHREADS * P.p;
+    const size_t count = (size_t)min(CTHREADS, P.B - (int)(blockIdx.x * CTHREADS)) * P.p;
+    for (size_t w = threadIdx.x; w < count; w += CTHREADS) {
+      const size_t t = w / P.p, i = w - t * P.p;
+      reinterpret_cast<int32_t *>(csm + t * stride + 4 * n)[i] = P.k[first + w];
+    }
+    __syncthreads();
+  }
+  uint32_t *rec = P.tape + (size_t)(live ? b : 0) * P.rec_stride;
+  int nops = 0, d = QAS_CT_FULL, bin = -1;
+  if (live) {
+    QasTapeSink sink{ops, P.ops_cap, 0, 0};
+    const int st = qas_compile_circuit(ks, P.p, P.pool, P.c, n, col, row, sink);
+    nops = st ? 0 : sink.n;
+    int ngroups = qas_mark_groups(ops, nops, P.gmax);
+    // cinfo: the head (nsl, basis) in shared memory, the slice list straight to the record
+    uint32_t *glist = rec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS;
+    d = qas_compress_tape(ops, &nops, &ngroups, n, P.sxflat, P.S, ev, ec, mt, chead, glist + 1 + n, P.max_d);
+    rec[0] = (uint32_t)nops;
+    rec[1] = (uint32_t)st;
+    rec[2] = d >= 0 ? (uint32_t)d : 0x80000000u;
+    rec[3] = (uint32_t)ngroups;
+    if (d >= 0) {
+      for (int q = 0; q <= n; ++q) glist[q] = chead[q];
+      bin = max(d, P.dmin) - P.dmin;
+    } else {
+      bin = P.full_bin;
+    }
+  }
+  // bin assignment, one atomic per (warp, bin)
+  {
+    const uint32_t act = __ballot_sync(0xffffffffu, live);
+    if (live) {
+      const uint32_t peers = __match_any_sync(act, bin);
+      const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(P.bin_count + bin, __popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      P.bin_order[(size_t)bin * P.B + base + __popc(peers & ((1u << lane) - 1u))] = b;
+    }
+  }
+  // ops -> record, warp-cooperative and coalesced
+  __syncwarp();
+  {
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    for (int t = 0; t < 32; ++t) {
+      const int words = __shfl_sync(0xffffffffu, nops, t) * QAS_OP_WORDS;
+      const int bt = blockIdx.x * CTHREADS + wbase + t;
+      if (bt >= P.B) break;
+      const uint32_t *src = csm + (size_t)(wbase + t) * stride + 4 * n + (P.p | 1);
+      uint32_t *dst = P.tape + (size_t)bt * P.rec_stride + QAS_REC_HDR;
+      for (int w = lane; w < words; w += 32) dst[w] = src[w];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ compressed evaluation
+struct EvalCParams {
+  const uint32_t *tape;        // [B][rec_stride]
+  const GateTab *U;
+  const double *vflat;         // [S][2^n] flat sign tables, row s = slice s (real slices first)
+  const int *order;            // this bin's circuit indices
+  const int *count;            // ... and how many
+  int *work_counter;           // this bin's queue head (zeroed before the launch)
+  double *energy;              // [B]
+  double *mout;                // [B][ops_cap][8]
+  size_t rec_stride;
+  int n, ops_cap, S, S_real, slot_bits;
+};
+
+__host__ __device__ inline size_t evalc_team_smem_bytes(int slot_bits, int T, bool grad, int ops_cap, int S) {
+  const int wpt = T >= 32 ? T / 32 : 1;
+  size_t b = ((size_t)16 << slot_bits) * (grad ? 2 : 1);
+  b += (((size_t)(QAS_REC_HDR + ops_cap * QAS_OP_WORDS) * 4) + 15) & ~(size_t)15;
+  b += 16 * 4;                                         // nsl + basis (<= QAS_CT_MAX_D words)
+  b += (((size_t)S * 4) + 15) & ~(size_t)15;           // slice list
+  b += (size_t)ops_cap * 64;                           // staged gate matrices
+  if (grad && wpt > 1) b += (size_t)2 * 2 * wpt * 64;  // cross-matrix ring (two buffers, <= 2 gates per pass)
+  b += (((size_t)wpt * 8) + 15) & ~(size_t)15;
+  b += 16;                                             // the team's work-queue slot
+  return b;
+}
+
+// coset geometry of a pass of G gates inside the support prefix: pivots of the echelonised masks
+template <int G>
+struct CGeom {
+  uint32_t m[G], r[G], xm[1 << G];
+  int qlo, qhi;
+  __device__ __forceinline__ void load(const uint32_t *o) {
+#pragma unroll
+    for (int q = 0; q < G; ++q) { m[q] = o[q * QAS_OP_WORDS]; r[q] = o[q * QAS_OP_WORDS + 1]; }
+    const int q0 = 31 - __clz(m[0]);
+    qlo = qhi = q0;
+    if constexpr (G == 2) {
+      const uint32_t e1 = ((m[1] >> q0) & 1u) ? (m[1] ^ m[0]) : m[1];
+      const int q1 = 31 - __clz(e1);
+      qlo = min(q0, q1);
+      qhi = max(q0, q1);
+    }
+    xm[0] = 0u;
+#pragma unroll
+    for (int c = 1; c < (1 << G); ++c) {
+      const int q = c >= 2 ? 1 : 0;
+      xm[c] = xm[c & ~(1 << q)] ^ m[q];
+    }
+  }
+  // representative of coset c, projected onto the common kernel of the r's (slot bits = logical bits)
+  __device__ __forceinline__ uint32_t rep(uint32_t c) const {
+    uint32_t t = insert_zero(c, qlo);
+    if constexpr (G == 2) t = insert_zero(t, qhi);
+    uint32_t P = t;
+#pragma unroll
+    for (int q = 0; q < G; ++q) P ^= (__popc(t & r[q]) & 1) ? m[q] : 0u;
+    return P;
+  }
+};
+
+template <int G, int T>
+__device__ __forceinline__ void c_fwd_group(double2 *psi, const uint32_t *o, int dj, const double2 *Us, int tid) {
+  CGeom<G> gg;
+  gg.load(o);
+  double2 u[G][4];
+#pragma unroll
+  for (int q = 0; q < G; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) u[q][e] = Us[4 * q + e];
+  const uint32_t rc = (G == 1) ? o[2] : 0u;
+  const uint32_t ncos = 1u << (dj - G);
+  for (uint32_t c = tid; c < ncos; c += T) {
+    const uint32_t P = gg.rep(c);
+    if (G == 1 && rc && !(__popc(P & rc) & 1)) continue;
+    double2 a[1 << G];
+#pragma unroll
+    for (int s = 0; s < (1 << G); ++s) a[s] = psi[P ^ gg.xm[s]];
+#pragma unroll
+    for (int q = G - 1; q >= 0; --q) {       // time order = descending tape index
+#pragma unroll
+      for (int s = 0; s < (1 << G); ++s)
+        if (!((s >> q) & 1)) apply_u(a[s], a[s | (1 << q)], u[q]);
+    }
+#pragma unroll
+    for (int s = 0; s < (1 << G); ++s) psi[P ^ gg.xm[s]] = a[s];
+  }
+}
+
+// adjoint pass of a group (tape order): psi <- U^ psi ; M += conj(lam) psi ; lam <- U^ lam over the cosets
+// inside the support AFTER the group.  Every lane of the team runs the same trip count (the cross-matrix
+// reduction shuffles), lanes beyond the support contribute zeros.
+template <int G, int T, int TW, int WPT>
+__device__ __forceinline__ void c_adj_group(double2 *psi, double2 *lam, const uint32_t *o, int dj, const double2 *Us,
+                                            int tid, int lane, int warp_in_team, uint32_t tmask, double *ring,
+                                            double *mout_op) {
+  CGeom<G> gg;
+  gg.load(o);
+  int npar[G];
+#pragma unroll
+  for (int q = 0; q < G; ++q) npar[q] = qas_meta_npar(o[q * QAS_OP_WORDS + 4]);
+  double M[G][8];
+#pragma unroll
+  for (int q = 0; q < G; ++q)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) M[q][e] = 0.0;
+  const uint32_t rc = (G == 1) ? o[2] : 0u;
+  const uint32_t ncos = 1u << (dj - G);
+  for (uint32_t c0 = 0; c0 < ncos; c0 += T) {
+    const uint32_t c = c0 + tid;
+    if (c >= ncos) continue;
+    const uint32_t P = gg.rep(c);
+    if (G == 1 && rc && !(__popc(P & rc) & 1)) continue;
+    double2 a[1 << G], l[1 << G];
+#pragma unroll
+    for (int s = 0; s < (1 << G); ++s) {
+      const uint32_t x = P ^ gg.xm[s];
+      a[s] = psi[x];
+      l[s] = lam[x];
+    }
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      double2 u[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) u[e] = Us[4 * q + e];
+#pragma unroll
+      for (int s = 0; s < (1 << G); ++s) {
+        if ((s >> q) & 1) continue;
+        const int s1 = s | (1 << q);
+        apply_udag(a[s], a[s1], u);
+        if (npar[q]) macc(M[q], l[s], l[s1], a[s], a[s1]);
+        apply_udag(l[s], l[s1], u);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < (1 << G); ++s) {
+      const uint32_t x = P ^ gg.xm[s];
+      psi[x] = a[s];
+      lam[x] = l[s];
+    }
+  }
+  __syncwarp(tmask);
+#pragma unroll
+  for (int q = 0; q < G; ++q)
+    if (npar[q]) reduce_store_m<TW, false>(M[q], lane, tmask, WPT == 1 ? mout_op + (size_t)q * 8
+                                                                        : ring + ((size_t)q * WPT + warp_in_team) * 8, false);
+}
+
+template <int T, bool GRAD, int BLK, int MINB>
+__global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
+  constexpr int WPT = T >= 32 ? T / 32 : 1;
+  constexpr int TW = T >= 32 ? 32 : T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int team = threadIdx.x / T, tid = threadIdx.x % T;
+  const int lane = threadIdx.x & 31, warp_in_team = tid >> 5;
+  const uint32_t tmask = T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << ((lane / TW) * TW));
+  const size_t team_bytes = evalc_team_smem_bytes(P.slot_bits, T, GRAD, P.ops_cap, P.S);
+  unsigned char *base = smem_raw + (size_t)team * team_bytes;
+  double2 *psi = reinterpret_cast<double2 *>(base), *lam = nullptr;
+  base += (size_t)16 << P.slot_bits;
+  if constexpr (GRAD) { lam = reinterpret_cast<double2 *>(base); base += (size_t)16 << P.slot_bits; }
+  uint32_t *rec = reinterpret_cast<uint32_t *>(base);
+  uint32_t *ops = rec + QAS_REC_HDR;
+  base += (((size_t)(QAS_REC_HDR + P.ops_cap * QAS_OP_WORDS) * 4) + 15) & ~(size_t)15;
+  uint32_t *chead = reinterpret_cast<uint32_t *>(base);          // nsl, B_0 ..
+  base += 16 * 4;
+  uint32_t *list = reinterpret_cast<uint32_t *>(base);
+  base += (((size_t)P.S * 4) + 15) & ~(size_t)15;
+  double2 *Us = reinterpret_cast<double2 *>(base);
+  base += (size_t)P.ops_cap * 64;
+  double *red = nullptr;
+  if constexpr (GRAD && WPT > 1) { red = reinterpret_cast<double *>(base); base += (size_t)2 * 2 * WPT * 64; }
+  double *ered = reinterpret_cast<double *>(base);
+  base += (((size_t)WPT * 8) + 15) & ~(size_t)15;
+  int *bslot = reinterpret_cast<int *>(base);
+  const int count = *P.count;
+  const int n = P.n;
+
+  for (;;) {
+    if (tid == 0) *bslot = atomicAdd(P.work_counter, 1);
+    team_sync<T>(team, tmask);
+    const int qi = *bslot;
+    if (qi >= count) break;
+    const int b = P.order[qi];
+    // ---- 1. fetch the record, zero the support
+    const uint32_t *grec = P.tape + (size_t)b * P.rec_stride;
+    const uint32_t *gci = grec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS;
+    const int nops = (int)grec[0], status = (int)grec[1], d = (int)grec[2], ngroups = (int)grec[3], nsl = (int)gci[0];
+    {
+      const int used = QAS_REC_HDR + nops * QAS_OP_WORDS;
+      for (int w = tid; w < used; w += T) rec[w] = grec[w];
+      for (int w = tid; w <= d; w += T) chead[w] = gci[w];
+      for (int w = tid; w < nsl; w += T) list[w] = gci[1 + n + w];
+      const uint32_t dim = 1u << d;
+      for (uint32_t i = tid; i < dim; i += T) psi[i] = make_double2(i == 0u ? 1.0 : 0.0, 0.0);
+    }
+    team_sync<T>(team, tmask);
+    for (int w = tid; w < nops * 4; w += T) Us[w] = P.U[ops[(w >> 2) * QAS_OP_WORDS + 3]].u[w & 3];
+    team_sync<T>(team, tmask);
+
+    // ---- 2. forward sweep (tape is stored last-gate-first: walk the groups from the end)
+    {
+      int e = nops - 1;
+      for (int it = 0; it < ngroups; ++it) {
+        const int g = (int)QAS_META_GLAST(ops[(size_t)e * QAS_OP_WORDS + 4]);
+        const int j = e - g + 1;
+        const uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
+        const int dj = (int)QAS_META_DJ(o[4]);
+        if (qas_meta_kind(o[4]) == QAS_K_U1) {
+          if (g == 2) c_fwd_group<2, T>(psi, o, dj, Us + 4 * j, tid);
+          else c_fwd_group<1, T>(psi, o, dj, Us + 4 * j, tid);
+        } else {
+          const double2 d0 = Us[4 * j], d1 = Us[4 * j + 3];
+          const uint32_t r = o[1], sup = 1u << dj;
+          for (uint32_t i = tid; i < sup; i += T) psi[i] = cmul((__popc(i & r) & 1) ? d1 : d0, psi[i]);
+        }
+        e = j - 1;
+        team_sync<T>(team, tmask);
+      }
+    }
+
+    // ---- 3. lambda = H psi on the support, E = Re <psi|lambda>
+    double e_part = 0.0;
+    {
+      const uint32_t dim = 1u << d;
+      for (uint32_t t = tid; t < dim; t += T) {
+        uint32_t i = 0u;
+        for (int kk = 0; kk < d; ++kk) i ^= ((t >> kk) & 1u) ? chead[1 + kk] : 0u;
+        const double *vrow = P.vflat + i;
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll 4
+        for (int s = 0; s < nsl; ++s) {
+          const uint32_t ent = list[s];
+          const uint32_t si = ent >> 16;
+          const double2 a = psi[t ^ (ent & 0xffffu)];
+          const double v = __ldg(vrow + ((size_t)si << n));
+          if ((int)si < P.S_real) { acc.x = fma(v, a.x, acc.x); acc.y = fma(v, a.y, acc.y); }
+          else { acc.x = fma(-v, a.y, acc.x); acc.y = fma(v, a.x, acc.y); }
+        }
+        const double2 ai = psi[t];
+        e_part = fma(ai.x, acc.x, fma(ai.y, acc.y, e_part));
+        if constexpr (GRAD) lam[t] = acc;
+      }
+    }
+#pragma unroll
+    for (int off = TW / 2; off > 0; off >>= 1) e_part += shfl_xor_d(e_part, off, tmask);
+    if constexpr (WPT > 1) {
+      if (lane == 0) ered[warp_in_team] = e_part;
+      team_sync<T>(team, tmask);
+      if (tid == 0) {
+        double e = 0.0;
+#pragma unroll
+        for (int w = 0; w < WPT; ++w) e += ered[w];
+        e_part = e;
+      }
+    } else if constexpr (GRAD) {
+      team_sync<T>(team, tmask);
+    }
+    if (tid == 0) P.energy[b] = status ? __longlong_as_double(0x7ff8000000000000ll) : e_part;
+
+    // ---- 4. adjoint sweep (tape order = reverse time order)
+    if constexpr (GRAD) {
+      int j = 0;
+      for (int it = 0; it < ngroups; ++it) {
+        const uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
+        const int g = (int)QAS_META_GFIRST(o[4]);
+        const int dj = (int)QAS_META_DJ(o[4]);
+        double *ring = WPT > 1 ? red + (size_t)(it & 1) * 2 * WPT * 8 : nullptr;
+        double *mop = P.mout + ((size_t)b * P.ops_cap + j) * 8;
+        if (qas_meta_kind(o[4]) == QAS_K_U1) {
+          if (g == 2) c_adj_group<2, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
+          else c_adj_group<1, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
+        } else {
+          const double2 d0 = Us[4 * j], d1 = Us[4 * j + 3];
+          const uint32_t r = o[1], sup = 1u << dj;
+          const int npar = qas_meta_npar(o[4]);
+          double acc[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+          for (uint32_t i = tid; i < sup; i += T) {
+            const bool hi = __popc(i & r) & 1;
+            const double2 dd = hi ? d1 : d0;
+            const double2 q = cmul_conj(dd, psi[i]);
+            const double2 lv = lam[i];
+            psi[i] = q;
+            if (npar) {
+              const double re = fma(lv.x, q.x, lv.y * q.y), im = fma(lv.x, q.y, -lv.y * q.x);
+              if (hi) { acc[6] += re; acc[7] += im; } else { acc[0] += re; acc[1] += im; }
+            }
+            lam[i] = cmul_conj(dd, lv);
+          }
+          __syncwarp(tmask);
+          if (npar) reduce_store_m<TW, false>(acc, lane, tmask, WPT == 1 ? mop : ring + (size_t)warp_in_team * 8, false);
+        }
+        if constexpr (WPT > 1) {
+          team_sync<T>(team, tmask);
+          if (tid < 8 * g) {
+            const int q = tid >> 3, v = tid & 7;
+            if (qas_meta_npar(o[q * QAS_OP_WORDS + 4])) {
+              double m = 0.0;
+              for (int wp = 0; wp < WPT; ++wp) m += ring[((size_t)q * WPT + wp) * 8 + v];
+              mop[(size_t)q * 8 + v] = m;
+            }
+          }
+        } else {
+          team_sync<T>(team, tmask);
+        }
+        j += g;
+      }
+    }
+    team_sync<T>(team, tmask);   // state buffers are reused by the next circuit of this team
+  }
+}
+
+// ------------------------------------------------------------------------------ fused finalize + reduce
+// When the caller only wants the batch mean of the dense gradient (search(), qas/mcts/mcts.py:340-347),
+// the per-circuit compact gradients never need to exist: one CTA per chunk of circuits contracts the
+// cross matrices with dU/dtheta and accumulates straight into the dense (depth, key, slot) layout --
+// the table index of an op IS its (depth, key).  Thread (op slot, j) walks the chunk's circuits in order
+// (deterministic); ops of one circuit sit at distinct depths, so there are no collisions inside a
+// circuit, and __syncthreads separates the circuits.  partial[chunk][p*c*l] feeds grad_final_reduce_kernel.
+static __global__ void grad_finalize_reduce_kernel(const uint32_t *tape, size_t rec_stride, const double *mout,
+                                            const GateDTab *dU, int B, int p, int c, int l, int ops_cap,
+                                            int chunk, int depth_tile, double *partial) {
+  extern __shared__ double acc_all[];             // [warps][depth_tile][c][l]
+  const int depth0 = blockIdx.y * depth_tile;
+  const int nd = min(depth_tile, p - depth0);
+  const int nw = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int words = nd * c * l;
+  for (int x = threadIdx.x; x < words * nw; x += blockDim.x) acc_all[x] = 0.0;
+  __syncthreads();
+  double *acc = acc_all + (size_t)wid * words;
+  const int b_lo = blockIdx.x * chunk, b_hi = min(B, b_lo + chunk);
+  // warp w takes circuits b_lo + w, b_lo + w + nw, ... in order; lanes take the circuit's ops (distinct depths)
+  for (int b = b_lo + wid; b < b_hi; b += nw) {
+    const uint32_t *rec = tape + (size_t)b * rec_stride;
+    const int nops = rec[1] ? 0 : (int)rec[0];
+    for (int oi = lane; oi < nops; oi += 32) {
+      const uint32_t *o = rec + QAS_REC_HDR + (size_t)oi * QAS_OP_WORDS;
+      const uint32_t mt = o[4];
+      const int npar = min(qas_meta_npar(mt), l);
+      const int depth = qas_meta_depth(mt);
+      if (!npar || depth < depth0 || depth >= depth0 + nd) continue;
+      const double2 *mp = reinterpret_cast<const double2 *>(mout + ((size_t)b * ops_cap + oi) * 8);
+      double2 m[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) m[q] = mp[q];
+      const uint32_t tab = o[3];
+      const int key = (int)((tab - QAS_NCONST) % (uint32_t)c);
+      double *a = acc + ((size_t)(depth - depth0) * c + key) * l;
+      for (int jj = 0; jj < npar; ++jj) {
+        const double2 *dd = dU[tab].d[jj];
+        double part = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) part += dd[q].x * m[q].x - dd[q].y * m[q].y;
+        a[jj] += nan_to_num_d(2.0 * part);
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // fixed-order sum of the warps' copies
+  double *out = partial + ((size_t)blockIdx.x * p + depth0) * c * l;
+  for (int x = threadIdx.x; x < words; x += blockDim.x) {
+    double v = 0.0;
+    for (int w = 0; w < nw; ++w) v += acc_all[(size_t)w * words + x];
+    out[x] = v;
+  }
+}

@@ -1,0 +1,70 @@
+// launch_c.cu -- launches of the support-compressed path (kernels_c.cuh): c-tape compile kernel,
+// compressed evaluation kernel per bin, fused gradient finalize + batch reduction.
+#include "ctx.h"
+
+size_t qas_ccompile_smem_bytes(const qas_ctx *ctx, int ops_cap, int p) {
+  return qas_ccompile_smem_words(ctx->n, ops_cap, p) * 4 * 32;
+}
+
+cudaError_t qas_launch_compile_c(qas_ctx *ctx, const CompileCParams &P, cudaStream_t st) {
+  constexpr int CT = 32;
+  const size_t smem = qas_ccompile_smem_bytes(ctx, P.ops_cap, P.p);
+  cudaError_t e = cudaFuncSetAttribute(compile_ctapes_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  compile_ctapes_kernel<CT><<<(P.B + CT - 1) / CT, CT, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+template <int T, bool GRAD, int BLK, int MINB>
+static cudaError_t launch_evalc_t(qas_ctx *ctx, const EvalCParams &P, int max_work, cudaStream_t st) {
+  constexpr int TEAMS = BLK / T;
+  const size_t smem = evalc_team_smem_bytes(P.slot_bits, T, GRAD, P.ops_cap, P.S) * TEAMS;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  auto kern = evalc_kernel<T, GRAD, BLK, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLK, smem);
+  const int grid = std::min((max_work + TEAMS - 1) / TEAMS, std::max(1, occ) * ctx->num_sms);   // persistent CTAs, queue-fed
+  ctx->stats.teams_per_cta = TEAMS;
+  ctx->stats.threads_per_team = T;
+  ctx->stats.ctas_per_sm = occ;
+  ctx->stats.smem_bytes_per_cta = (int)smem;
+  ctx->stats.path = 3;
+  kern<<<grid, BLK, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+// threads per team of a compressed bin by its slot size (log2 amplitudes)
+int qas_evalc_team_threads(int slot_bits) { return slot_bits <= 8 ? 32 : slot_bits <= 10 ? 64 : slot_bits == 11 ? 128 : 256; }
+
+cudaError_t qas_launch_evalc(qas_ctx *ctx, const EvalCParams &P, int max_work, bool grad, cudaStream_t st) {
+  const int T = qas_evalc_team_threads(P.slot_bits);
+#define QAS_CCASE(T_, BLK_, MINB_) \
+  if (T == T_) return grad ? launch_evalc_t<T_, true, BLK_, MINB_>(ctx, P, max_work, st) : launch_evalc_t<T_, false, BLK_, MINB_>(ctx, P, max_work, st);
+  QAS_CCASE(32, 128, 4) QAS_CCASE(64, 128, 4) QAS_CCASE(128, 128, 3) QAS_CCASE(256, 256, 1)
+#undef QAS_CCASE
+  return cudaErrorInvalidConfiguration;
+}
+
+cudaError_t qas_launch_finalize_reduce(qas_ctx *ctx, const uint32_t *tape, size_t rec_stride, const double *mout, int B, int p,
+                                       int ops_cap, double scale, double *dense, cudaStream_t st) {
+  const int c = ctx->c, l = ctx->l;
+  const size_t npar = (size_t)p * c * l;
+  const int nw = 4, chunk = 64;
+  const int nchunks = (B + chunk - 1) / chunk;
+  int depth_tile = p;
+  while ((size_t)depth_tile * c * l * 8 * nw > 96 * 1024 && depth_tile > 1) depth_tile = (depth_tile + 1) / 2;
+  const size_t sm = (size_t)depth_tile * c * l * 8 * nw;
+  cudaError_t e = ensure(&ctx->d_partial, &ctx->cap_partial, (size_t)nchunks * npar);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(grad_finalize_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return e;
+  dim3 grid(nchunks, (p + depth_tile - 1) / depth_tile);
+  grad_finalize_reduce_kernel<<<grid, nw * 32, sm, st>>>(tape, rec_stride, mout, ctx->d_dU, B, p, c, l, ops_cap, chunk, depth_tile,
+                                                        ctx->d_partial);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  grad_final_reduce_kernel<<<(unsigned)((npar * 32 + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, scale, dense);
+  return cudaGetLastError();
+}

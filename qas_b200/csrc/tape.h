@@ -425,8 +425,8 @@ QAS_PUNROLL
 // Returns the number of groups.  gd receives one descriptor of QAS_GD_STRIDE(n) words per group,
 // in TAPE order of the groups (may be null: grouping only).  swizzled: the statevector lives in
 // shared memory; descriptors and the ops' xor masks are then written in slot coordinates.
-QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax, int n, int init_kind, uint32_t init_index,
-                           uint32_t *gd, int swizzled, const QasHInfo *hi = nullptr, uint32_t *hd = nullptr) {
+// grouping only: marks the meta words, returns the number of groups
+QAS_HD int qas_mark_groups(uint32_t *ops, int nops, int gmax) {
   int ngroups = 0;
   for (int j = 0; j < nops;) {
     uint32_t *a = ops + (size_t)j * QAS_OP_WORDS;
@@ -449,7 +449,11 @@ QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax, int n, int init_ki
     j += g;
     ++ngroups;
   }
-  if (!gd) return ngroups;
+  return ngroups;
+}
+// support descriptors of an already grouped tape (+ the ops' xor masks to slot coordinates when swizzled)
+QAS_HD void qas_plan_marked(uint32_t *ops, int nops, int ngroups, int n, int init_kind, uint32_t init_index,
+                            uint32_t *gd, int swizzled, const QasHInfo *hi = nullptr, uint32_t *hd = nullptr) {
   if (n <= 5) qas_plan_supports<5>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
   else if (n <= 8) qas_plan_supports<8>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
   else if (n <= 10) qas_plan_supports<10>(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
@@ -460,6 +464,11 @@ QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax, int n, int init_ki
       uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
       if (qas_meta_kind(o[4]) == QAS_K_U1) o[0] = qas_swz(o[0]);
     }
+}
+QAS_HD int qas_plan_groups(uint32_t *ops, int nops, int gmax, int n, int init_kind, uint32_t init_index,
+                           uint32_t *gd, int swizzled, const QasHInfo *hi = nullptr, uint32_t *hd = nullptr) {
+  const int ngroups = qas_mark_groups(ops, nops, gmax);
+  if (gd) qas_plan_marked(ops, nops, ngroups, n, init_kind, init_index, gd, swizzled, hi, hd);
   return ngroups;
 }
 
@@ -469,4 +478,89 @@ QAS_HD uint32_t qas_frame_map_basis(const uint32_t *col, int n, uint64_t basis) 
   for (int q = 0; q < n; ++q)
     if ((basis >> (n - 1 - q)) & 1ull) out ^= col[q];
   return out;
+}
+
+// ---- support-compressed tapes ("c-tapes") -----------------------------------------------------
+// From the all-zero state a circuit only populates D = span of the xor masks of its 2x2 ops, and
+// the support after the first j ops (time order) is the span D_j of the first j masks.  The c-tape
+// expresses the circuit in a TIME-ADAPTED basis of D: B_k = mask of the k-th op (time order) that
+// enlarges the span.  With i(t) = xor_k t_k B_k the support after j ops is simply {t < 2^{d_j}} --
+// a contiguous prefix of a 2^d-amplitude register -- and
+//   m  -> m' = coordinates of m (the op that creates B_k gets the unit vector e_k),
+//   r  -> r',  r'_k = parity(B_k & r)   (logical-bit parity mask; likewise rc -> rc'),
+//   X mask x of the Hamiltonian -> x' = coordinates of x, or "outside D": such a slice connects the
+//   support to amplitudes that are exactly zero and drops out of the energy and of every derivative.
+// The evaluation kernel (evalc_kernel, kernels_c.cuh) then needs no per-pass descriptors: the cosets
+// of a pass are enumerated by inserting zeros at the pivots of the pass's masks inside the prefix
+// 2^{d_j}, and the representative is projected onto the common kernel of the r's at run time.
+// A controlled op whose control parity mask vanishes on D never fires (control bit constant 0 on the
+// support) and is dropped from the tape; its parameters keep their zero gradient.
+// Group sizes (meta bits 24-27) must have been set on the ORIGINAL tape (qas_plan_groups with
+// gd == nullptr): the no-cross-term test needs complete parity masks.
+// meta bits 28-31 of every op = d_j after that op.
+#define QAS_CT_MAX_D 12
+#define QAS_META_DJ(m) ((m) >> 28)
+#define QAS_CT_FULL (-1)          // d == n: nothing to compress, the classic path evaluates it
+#define QAS_CT_TOO_BIG (-2)       // d > QAS_CT_MAX_D
+// cinfo block of a c-tape record, right after the ops area: head [nsl, B_0 .. B_{n-1}] | list[nsl]
+// list entry = x' | slice index << 16
+QAS_HD size_t qas_cinfo_words(int n, int S) { return (size_t)1 + (size_t)n + (size_t)S; }
+
+// scratch: ev[n], ec[n] (echelon vectors by highest-bit pivot and their coordinates), mt[nops]
+// (per-op m' | d_j << 16).  On success ops / *nops / *ngroups are rewritten in place, chead (1 + n
+// words) and list (<= S words) are filled; on QAS_CT_FULL / QAS_CT_TOO_BIG the ops are untouched.
+QAS_HD int qas_compress_tape(uint32_t *ops, int *nops_io, int *ngroups_io, int n, const uint32_t *xs, int S,
+                             uint32_t *ev, uint32_t *ec, uint32_t *mt, uint32_t *chead, uint32_t *list, int max_d) {
+  const int nops = *nops_io;
+  uint32_t *basis = chead + 1;
+  for (int p = 0; p < n; ++p) ev[p] = ec[p] = 0u;
+  int d = 0;
+  for (int j = nops - 1; j >= 0; --j) {            // time order
+    const uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
+    uint32_t c = 0u;
+    if (qas_meta_kind(o[4]) == QAS_K_U1) {
+      uint32_t x = o[0];
+      while (x) {
+        const int p = qas_msb32(x);
+        if (ev[p]) { x ^= ev[p]; c ^= ec[p]; }
+        else {
+          if (d >= max_d || d >= n - 1) return d >= n - 1 ? QAS_CT_FULL : QAS_CT_TOO_BIG;
+          ev[p] = x; ec[p] = c | (1u << d); basis[d] = o[0]; c = 1u << d; ++d;
+          break;
+        }
+      }
+    }
+    mt[j] = c | ((uint32_t)d << 16);
+  }
+  // translate in place, dropping controlled ops whose control is constant on the support
+  int w = 0, ndrop_groups = 0;
+  for (int j = 0; j < nops; ++j) {
+    const uint32_t *o = ops + (size_t)j * QAS_OP_WORDS;
+    const uint32_t r = o[1], rc = o[2];
+    uint32_t rp = 0u, rcp = 0u;
+    for (int k = 0; k < d; ++k) {
+      rp |= (uint32_t)qas_parity32(basis[k] & r) << k;
+      rcp |= (uint32_t)qas_parity32(basis[k] & rc) << k;
+    }
+    if (rc && !rcp) { ++ndrop_groups; continue; }  // controlled ops are always one-op groups
+    const uint32_t tab = o[3], meta = (o[4] & 0x0fffffffu) | ((mt[j] >> 16) << 28);
+    uint32_t *q = ops + (size_t)w * QAS_OP_WORDS;
+    q[0] = mt[j] & 0xffffu; q[1] = rp; q[2] = rcp; q[3] = tab; q[4] = meta;
+    ++w;
+  }
+  *nops_io = w;
+  *ngroups_io -= ndrop_groups;
+  int nsl = 0;
+  for (int s = 0; s < S; ++s) {
+    uint32_t x = xs[s], c = 0u;
+    while (x) {
+      const int p = qas_msb32(x);
+      if (!ev[p]) break;
+      x ^= ev[p]; c ^= ec[p];
+    }
+    if (!x) list[nsl++] = c | ((uint32_t)s << 16);
+  }
+  chead[0] = (uint32_t)nsl;
+  for (int k = d; k < n; ++k) basis[k] = 0u;
+  return d;
 }

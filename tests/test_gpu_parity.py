@@ -301,6 +301,112 @@ def test_support_restricted_path_with_the_full_gate_vocabulary(monkeypatch):
             assert np.max(np.abs(res["1"]["grad_compact"][b, i] - g[i, key])) <= G_TOL
 
 
+def _eval_both_paths(monkeypatch, n, terms, pool, init, cases, B):
+    """The same batches through the support-compressed path (default) and the classic path (QAS_B200_COMPRESS=0)."""
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("QAS_B200_COMPRESS", flag)
+        ev = BatchEvaluator(n, terms, pool, init=init)
+        res = []
+        for ks, params in cases:
+            full = ev.evaluate(ks, params, want_grad=True, dense=True, compact=True)
+            mean_only = ev.evaluate(ks, params, want_grad=True, dense=True, compact=False)      # fused finalize + reduce
+            reward = ev.evaluate(ks, params, want_grad=False)
+            tiny = ev.evaluate(ks[:5], params, want_grad=True, dense=True, compact=True)         # host-compiled records
+            res.append((full, mean_only, reward, tiny))
+        outs[flag] = (res, ev.stats()["path"])
+        ev.close()
+    return outs
+
+
+@pytest.mark.parametrize("cfg", ["lih_10q", "h2o_8q"])
+def test_support_compressed_path_equals_classic_and_oracle(cfg, monkeypatch):
+    """Support-compressed evaluation (c-tapes, one launch per bin of the support dimension, sign tables read at
+    the physical index) == classic support-restricted evaluation <= 1e-12 on whole batches of several depths,
+    == oracle <= 1e-9 / 1e-8 on a sample; the fused finalize + batch-mean kernel and the host-compiled
+    (<= 16 circuits) records give the same numbers."""
+    name, n, p, mkpool, lim = helpers.CONFIGS[cfg]
+    model = helpers.get_model(name)
+    pool = mkpool()
+    B = 2048
+    cases = []
+    for depth, seed in ((p, 5), (max(4, p // 3), 6), (3, 7)):
+        params = np.random.default_rng(seed).standard_normal((depth, len(pool), 3))
+        cases.append((sample_structure_lists(pool, depth, {"CNOT": depth // 2}, B, seed=seed), params))
+    outs = _eval_both_paths(monkeypatch, n, model.terms(), pool, model.init_state, cases, B)
+    assert outs["1"][1] == 3 and outs["0"][1] == 0           # the compressed kernel really ran
+    for (ks, params), a, b in zip(cases, outs["0"][0], outs["1"][0]):
+        assert np.max(np.abs(a[0]["energy"] - b[0]["energy"])) <= 1e-12
+        assert np.max(np.abs(a[0]["grad_compact"] - b[0]["grad_compact"])) <= 1e-12
+        assert np.max(np.abs(a[0]["grad_dense"] - b[0]["grad_dense"])) <= 1e-12
+        for r in (a, b):
+            assert np.max(np.abs(r[1]["grad_dense"] - r[0]["grad_dense"])) <= 1e-13
+            assert np.array_equal(r[1]["energy"], r[0]["energy"])
+            assert np.max(np.abs(r[2]["energy"] - r[0]["energy"])) <= 1e-12
+            assert np.max(np.abs(r[3]["energy"] - r[0]["energy"][:5])) <= 1e-12
+            assert np.max(np.abs(r[3]["grad_compact"] - r[0]["grad_compact"][:5])) <= 1e-12
+        for bi in range(0, B, 256):
+            k = [int(x) for x in ks[bi]]
+            e = sim.energy(n, k, pool.pool, params, model.terms(), model.init_state)
+            g = sim.grad_adjoint(n, k, pool.pool, params, model.terms(), model.init_state)
+            assert abs(b[0]["energy"][bi] - e) <= E_TOL
+            for i, key in enumerate(k):
+                assert np.max(np.abs(b[0]["grad_compact"][bi, i] - g[i, key])) <= G_TOL
+
+
+def test_support_compressed_path_with_the_full_gate_vocabulary(monkeypatch):
+    """Every gate of the vocabulary from the all-zero state on 8 and 11 qubits (single- and multi-warp teams):
+    controlled gates whose control never fires on the support, Ising phases, swaps."""
+    from qas_b200.qml_models.qml_models_legacy import H2O
+    rng = np.random.default_rng(21)
+    for n, p, B in ((8, 6, 1024), (11, 9, 512)):
+        pool = helpers.full_vocab_pool(n)
+        c = len(pool)
+        if n == 8:
+            terms = H2O.terms()
+        else:
+            words = ["".join(rng.choice(list("IXYZ"), size=n)) for _ in range(40)] + ["I" * n, "Z" + "I" * (n - 1)]
+            terms = [(float(rng.standard_normal()), w) for w in words]
+        ks = rng.integers(0, c, size=(B, p)).astype(np.int32)
+        params = rng.standard_normal((p, c, 3))
+        outs = _eval_both_paths(monkeypatch, n, terms, pool, ("zero", 0), [(ks, params)], B)
+        a, b = outs["0"][0][0], outs["1"][0][0]
+        assert np.max(np.abs(a[0]["energy"] - b[0]["energy"])) <= 1e-12
+        assert np.max(np.abs(a[0]["grad_compact"] - b[0]["grad_compact"])) <= 1e-12
+        assert np.max(np.abs(b[1]["grad_dense"] - b[0]["grad_dense"])) <= 1e-13
+        assert np.max(np.abs(b[3]["grad_compact"] - b[0]["grad_compact"][:5])) <= 1e-12
+        for bi in range(0, B, 128):
+            k = [int(x) for x in ks[bi]]
+            e = sim.energy(n, k, pool.pool, params, terms, ("zero", 0))
+            g = sim.grad_adjoint(n, k, pool.pool, params, terms, ("zero", 0))
+            assert abs(b[0]["energy"][bi] - e) <= E_TOL
+            for i, key in enumerate(k):
+                assert np.max(np.abs(b[0]["grad_compact"][bi, i] - g[i, key])) <= G_TOL
+
+
+def test_deep_tapes_fall_back_to_the_global_memory_kernel_with_a_consistent_layout():
+    """the index layout (swizzled shared memory vs plain global slab) is decided once per call from the
+    shared-memory fit, not from the qubit count: an n = 12 batch whose tapes are too long for the shared-memory
+    kernel runs on the global-memory kernel and still matches the oracle."""
+    n, p, B = 12, 900, 3
+    pool = helpers.near_cx_pool(n)
+    rng = np.random.default_rng(33)
+    words = ["".join(rng.choice(list("IXYZ"), size=n)) for _ in range(12)]
+    terms = [(float(rng.standard_normal()), w) for w in words]
+    params = rng.standard_normal((p, len(pool), 3))
+    ks = sample_structure_lists(pool, p, {"CNOT": p // 2}, B, seed=33)
+    ev = BatchEvaluator(n, terms, pool, init=("basis", 0b101010101010))
+    out = ev.evaluate(ks, params, want_grad=True, dense=False, compact=True)
+    assert ev.stats()["path"] == 1
+    ev.close()
+    for b in range(B):
+        k = [int(x) for x in ks[b]]
+        assert abs(out["energy"][b] - sim.energy(n, k, pool.pool, params, terms, ("basis", 0b101010101010))) <= E_TOL
+        g = sim.grad_adjoint(n, k, pool.pool, params, terms, ("basis", 0b101010101010))
+        for i, key in enumerate(k):
+            assert np.max(np.abs(out["grad_compact"][b, i] - g[i, key])) <= G_TOL
+
+
 def test_linearity_in_hamiltonian():
     """E_{H1+H2} = E_{H1} + E_{H2} for the same circuits (X-mask grouping must not mix terms)."""
     from qas_b200.qml_models.qml_models_legacy import H2O

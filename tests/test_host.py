@@ -295,150 +295,78 @@ def test_final_support_descriptor_of_the_h_application():
     assert restricted >= 10
 
 
-def test_support_compressed_register_prototype_matches_oracle():
-    """the evaluation of a shallow circuit on n qubits equals that of a
-    d = dim(support span) qubit register after translating the tape and the Hamiltonian into support
-    coordinates (tests/compressed_register.py) -- energies and every derivative."""
-    import compressed_register as CR
-    rng = np.random.default_rng(11)
-    saved = 0
-    for trial in range(10):
-        n = [8, 10][trial % 2]
-        full_vocab = trial % 5 == 4
-        pool = helpers.full_vocab_pool(n) if full_vocab else helpers.near_cx_pool(n)
-        c = len(pool)
-        p = int(rng.integers(3, 6)) if full_vocab else int(rng.integers(5, 14))
-        init = ("zero", 0) if trial % 3 else ("basis", int(rng.integers(0, 1 << n)))
-        if full_vocab:
-            k = [int(x) for x in rng.integers(0, c, size=p)]
+# ------------------------------------------------------------------------------------------------
+# support-compressed tapes (tape.h qas_compress_tape; kernel algorithm restated in tests/ctape_interp.py)
+def _ctape_case(n, pool, p, lim, terms, seeds, k_override=None):
+    import ctape_interp as CT
+    c = len(pool)
+    xs, imag, V = CT.sign_tables(n, terms)
+    rng = np.random.default_rng(17)
+    stats = {"compressed": 0, "full": 0, "dims": set(), "dropped_slices": 0}
+    for seed in seeds:
+        if k_override is None:
+            k = [int(x) for x in sample_structure_lists(pool, p, lim, 1, seed=seed)[0]]
         else:
-            k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": p // 2}, 1, seed=300 + trial)[0]]
+            k = k_override(rng)
         params = rng.standard_normal((p, c, 3))
-        terms = [(float(cf), w) for cf, w in helpers.get_model("LiH" if n == 10 else "H2O").terms()]
-        ops, idx = compile_tape_host(n, pool, k, init[1] if init[0] == "basis" else 0)
-        d, cops, cterms = CR.compress(ops, idx, terms)
-        assert d <= n and len(cterms) <= len(terms)
-        saved += n - d
-        e, gr = CR.run(d, cops, cterms, pool.pool, c, params)
-        assert abs(e - sim.energy(n, k, pool.pool, params, terms, init)) < 1e-10
-        ga = sim.grad_adjoint(n, k, pool.pool, params, terms, init)
-        got = np.zeros_like(ga)
-        for (dep, j), v in gr.items():
-            got[dep, k[dep], j] = v
-        assert np.max(np.abs(got - ga)) < 1e-9
-    assert saved >= 10          # the registers really are smaller
-
-
-def test_compressed_register_translation_in_the_library_matches_oracle():
-    """qas_compress_tape_host (the C side of DESIGN.md section 6 item 1): its translated tape, run by the
-    NumPy interpreter of tests/compressed_register.py on the d-qubit register, gives the oracle's energy
-    and derivatives; X masks it reports as outside the support are exactly the ones that drop out."""
-    import ctypes
-    import compressed_register as CR
-    from qas_b200 import _lib
-    from qas_b200 import hamiltonians as HM
-    lib = _lib.load()
-    rng = np.random.default_rng(21)
-    for trial in range(10):
-        n = [8, 10][trial % 2]
-        full_vocab = trial % 5 == 3
-        pool = helpers.full_vocab_pool(n) if full_vocab else helpers.near_cx_pool(n)
-        c = len(pool)
-        p = int(rng.integers(3, 6)) if full_vocab else int(rng.integers(5, 14))
-        init = ("zero", 0) if trial % 3 else ("basis", int(rng.integers(0, 1 << n)))
-        if full_vocab:
-            k = [int(x) for x in rng.integers(0, c, size=p)]
-        else:
-            k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": p // 2}, 1, seed=500 + trial)[0]]
-        params = rng.standard_normal((p, c, 3))
-        terms = [(float(cf), w) for cf, w in helpers.get_model("LiH" if n == 10 else "H2O").terms()]
-        ops, idx = compile_tape_host(n, pool, k, init[1] if init[0] == "basis" else 0)
-        xs = np.array(sorted({HM.word_to_masks(w)[0] for _, w in terms}), dtype=np.uint32)
-        cops_arr = np.ascontiguousarray(ops, dtype=np.uint32).copy()
-        d = ctypes.c_int(0)
-        basis = np.zeros(n, dtype=np.uint32)
-        xc = np.zeros(len(xs), dtype=np.uint32)
-        rc = lib.qas_compress_tape_host(n, cops_arr.ctypes.data, len(cops_arr), int(idx), xs.ctypes.data, len(xs),
-                                        ctypes.byref(d), basis.ctypes.data, xc.ctypes.data)
-        assert rc == 0
-        d = d.value
-        B = [int(v) for v in basis[:d]]
-        assert [v.bit_length() for v in B] == sorted(v.bit_length() for v in B)          # ascending pivots
-        # the Python prototype finds the same dimension and the same set of X masks inside the span
-        d_py, _, cterms_py = CR.compress(ops, idx, terms)
-        assert d == d_py
-        inside = {int(x) for x, t in zip(xs, xc) if t != 0xffffffff}
-        assert len({(HM.word_to_masks(w)[0]) for _, w in terms} & inside) == len(inside)
-        xmap = {int(x): int(t) for x, t in zip(xs, xc)}
-        # Hamiltonian in the library's coordinates
-        cterms = []
-        for coeff, word in terms:
-            x, z = sim.word_to_masks(word)
-            if xmap[x] == 0xffffffff:
-                continue
-            zp = sum((bin(B[kk] & z).count("1") & 1) << kk for kk in range(d))
-            cterms.append((xmap[x], zp, coeff * (-1.0 if bin(idx & z).count("1") & 1 else 1.0), bin(x & z).count("1")))
-        assert len(cterms) == len(cterms_py)
-        cops = []
-        for o in cops_arr:
-            m, r, rcm, tab, meta = (int(v) for v in o)
-            has_c = rcm != 0
-            rcp = 0 if rcm == 0x80000000 else rcm
-            cops.append((m, r, (meta >> 28) & 1, rcp, (meta >> 29) & 1, has_c, tab, meta & 0x0fffffff))
-        e, gr = CR.run(d, cops, cterms, pool.pool, c, params)
-        assert abs(e - sim.energy(n, k, pool.pool, params, terms, init)) < 1e-10
-        ga = sim.grad_adjoint(n, k, pool.pool, params, terms, init)
-        got = np.zeros_like(ga)
-        for (dep, j), v in gr.items():
-            got[dep, k[dep], j] = v
-        assert np.max(np.abs(got - ga)) < 1e-9
-
-
-@pytest.mark.parametrize("gmax", [1, 2])
-def test_compressed_tapes_run_through_the_existing_pass_planner(gmax):
-    """The register-fused, support-restricted passes of the evaluation kernel (qas_plan_groups + the
-    kernel's coset enumeration, restated in tape_interp.run_tape_planned) work unchanged on a tape that
-    qas_compress_tape_host rewrote for its d-qubit register -- all-zero start, so no role flips."""
-    import ctypes
-    from qas_b200 import _lib
-    from qas_b200 import hamiltonians as HM
-    lib = _lib.load()
-    rng = np.random.default_rng(31)
-    for trial in range(6):
-        n = [8, 10][trial % 2]
-        pool = helpers.near_cx_pool(n)
-        c = len(pool)
-        p = int(rng.integers(5, 14))
-        k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": p // 2}, 1, seed=700 + trial)[0]]
-        params = rng.standard_normal((p, c, 3))
-        terms = [(float(cf), w) for cf, w in helpers.get_model("LiH" if n == 10 else "H2O").terms()]
-        ops, idx = compile_tape_host(n, pool, k, 0)
-        assert idx == 0
-        xs = np.array(sorted({HM.word_to_masks(w)[0] for _, w in terms}), dtype=np.uint32)
-        cops = np.ascontiguousarray(ops, dtype=np.uint32).copy()
-        d = ctypes.c_int(0)
-        basis = np.zeros(n, dtype=np.uint32)
-        xc = np.zeros(len(xs), dtype=np.uint32)
-        assert lib.qas_compress_tape_host(n, cops.ctypes.data, len(cops), 0, xs.ctypes.data, len(xs),
-                                          ctypes.byref(d), basis.ctypes.data, xc.ctypes.data) == 0
-        d = d.value
-        if d < 2:
+        ct = CT.compile_ctape(n, pool, k, xs, gmax=2)
+        if ct["d"] < 0:
+            stats["full"] += 1
+            # the classic tape comes back grouped and otherwise untouched
+            ops, _ = compile_tape_host(n, pool, k, 0)
+            assert np.array_equal(ct["ops"][:, :4], ops[:, :4])
+            assert np.array_equal(ct["ops"][:, 4] & 0xFFFFFF, ops[:, 4])
             continue
-        assert not np.any(cops[:, 4] & np.uint32(3 << 28))             # no flips from |0..0>
-        B = [int(v) for v in basis[:d]]
-        xmap = {int(x): int(t) for x, t in zip(xs, xc)}
-        cterms = []
-        for coeff, word in terms:
-            x, z = sim.word_to_masks(word)
-            if xmap[x] != 0xffffffff:
-                cterms.append((xmap[x], sum((bin(B[q] & z).count("1") & 1) << q for q in range(d)), coeff,
-                               bin(x & z).count("1")))
-        swz = bool(trial & 1)                                            # both index layouts of the kernel
-        pops, ng, gds = TI.plan_passes(d, cops, gmax, ("zero", 0), 0, swizzled=swz)
-        e, gr = TI.run_tape_planned(d, pops, gds, ("zero", 0), 0, pool.pool, c, params, cterms, swizzled=swz)
-        assert abs(e - sim.energy(n, k, pool.pool, params, terms, ("zero", 0))) < 1e-10
+        stats["compressed"] += 1
+        stats["dims"].add(ct["d"])
+        stats["dropped_slices"] += len(xs) - len(ct["slices"])
+        assert 0 <= ct["d"] < n
+        e, gr = CT.run_ctape(ct, n, pool.pool, c, params, xs, imag, V)
+        assert abs(e - sim.energy(n, k, pool.pool, params, terms, ("zero", 0))) < 1e-11
         ga = sim.grad_adjoint(n, k, pool.pool, params, terms, ("zero", 0))
         got = np.zeros_like(ga)
-        for (dep, j), v in gr.items():
-            got[dep, k[dep], j] = v
-        assert np.max(np.abs(got - ga)) < 1e-9
+        for (dd, j), v in gr.items():
+            got[dd, k[dd], j] = v
+        assert np.max(np.abs(got - ga)) < 1e-10
+    return stats
+
+
+def test_ctape_lih_and_h2o_batches_match_oracle():
+    """c-tapes of LiH-10q / H2O-8q near_cx circuits: the compressed register evaluated with the kernel's
+    algorithm gives the oracle's energy and every derivative; X masks outside the support span drop out."""
+    from qas_b200.qml_models.qml_models_legacy import H2O, LiH
+    st = _ctape_case(10, helpers.near_cx_pool(10), 20, {"CNOT": 10}, LiH.terms(), range(10))
+    assert st["compressed"] >= 8 and len(st["dims"]) >= 3 and st["dropped_slices"] > 0
+    st = _ctape_case(8, helpers.near_cx_pool(8), 50, {"CNOT": 25}, H2O.terms(), range(6))
+    assert st["compressed"] + st["full"] == 6
+
+
+def test_ctape_full_vocabulary_random_circuits():
+    """Every gate of the vocabulary through the c-tape path: controlled gates whose control never fires on the
+    support are dropped, parity-diagonal ops act on the prefix, fused groups use run-time projection."""
+    n = 6
+    pool = helpers.full_vocab_pool(n)
+    c = len(pool)
+    rng0 = np.random.default_rng(3)
+    words = ["".join(rng0.choice(list("IXYZ"), size=n)) for _ in range(10)] + ["ZZIIII", "IIIIII", "XXIIII", "YYIIII"]
+    terms = [(float(rng0.standard_normal()), w) for w in words]
+    st = _ctape_case(n, pool, 9, None, terms, range(40), k_override=lambda rng: [int(x) for x in rng.integers(0, c, size=9)])
+    assert st["compressed"] >= 10 and len(st["dims"]) >= 2
+
+
+def test_ctape_edge_cases():
+    import ctape_interp as CT
+    n = 7
+    pool = helpers.near_cx_pool(n)
+    terms = [(0.7, "ZIIIIII"), (0.2, "XXIIIII"), (-0.4, "IIIIIII")]
+    xs, imag, V = CT.sign_tables(n, terms)
+    # all PlaceHolders: d = 0, one amplitude, only the diagonal slice survives
+    k = [1] * 5
+    ct = CT.compile_ctape(n, pool, k, xs)
+    assert ct["d"] == 0 and len(ct["ops"]) == 0 and [s for _, s in ct["slices"]] == [0]
+    e, gr = CT.run_ctape(ct, n, pool.pool, len(pool), np.zeros((5, len(pool), 3)), xs, imag, V)
+    assert abs(e - 0.3) < 1e-15 and gr == {}
+    # max_d below the circuit's span: not compressed
+    k = [0, 2, 4, 6, 8]
+    assert CT.compile_ctape(n, pool, k, xs, max_d=3)["d"] == CT.CT_TOO_BIG
+    assert CT.compile_ctape(n, pool, k, xs, max_d=5)["d"] == 5
