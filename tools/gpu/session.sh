@@ -1,0 +1,46 @@
+#!/bin/bash
+# One gpurun session: a list of steps, each under its own timeout, logs under gpurun_out/<tag>/.
+#   tools/gpu/session.sh <tag> <step> [<step> ...]
+# steps: tests | tests:<pytest -k expr> | bench:<workload>[:<env assignments,comma separated>] | stages:<workload>
+#        | launches:<workload> | ncu:<workload>:<kernel regex> | sanity
+set -u
+tag=$1; shift
+out=gpurun_out/$tag
+mkdir -p "$out"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$out/smi.csv" 2>&1
+for step in "$@"; do
+  IFS=: read -r kind a b <<< "$step"
+  name=$(echo "$step" | tr ':/ =,*|()' '_________')
+  echo "== $step" | tee -a "$out/steps.log"
+  envs=""
+  case $kind in
+    tests)
+      if [ -n "${a:-}" ]; then timeout 1500 python -m pytest tests -x -q -m gpu -k "$a" > "$out/$name.log" 2>&1
+      else timeout 2400 python -m pytest tests -x -q -m gpu > "$out/$name.log" 2>&1; fi
+      echo "rc=$?" | tee -a "$out/steps.log"; tail -5 "$out/$name.log" ;;
+    bench)
+      envs=$(echo "${b:-}" | tr ',' ' ')
+      env $envs timeout 600 python bench.py --workload "$a" --steps 20 --warmup 5 --tune > "$out/$name.json" 2> "$out/$name.err"
+      echo "rc=$?" | tee -a "$out/steps.log"; python tools/bench_brief.py "$out/$name.json" ;;
+    fullbench)
+      envs=$(echo "${b:-}" | tr ',' ' ')
+      env $envs timeout 900 python bench.py --workload "$a" --steps 20 --warmup 5 > "$out/$name.json" 2> "$out/$name.err"
+      echo "rc=$?" | tee -a "$out/steps.log"; python tools/bench_brief.py "$out/$name.json" ;;
+    stages)
+      envs=$(echo "${b:-}" | tr ',' ' ')
+      env $envs QAS_B200_STAGE_TIMES=1 timeout 300 python bench.py --workload "$a" --steps 3 --warmup 3 --tune > "$out/$name.json" 2> "$out/$name.err"
+      echo "rc=$?" | tee -a "$out/steps.log"; grep "stage times" "$out/$name.err" | sort | uniq -c | sort -rn | head -4 ;;
+    launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/$name.csv" \
+        python bench.py --workload "$a" --steps 2 --warmup 3 --tune > "$out/$name.log" 2>&1
+      echo "rc=$?" | tee -a "$out/steps.log"; python tools/launch_table.py "$out/$name.csv" | tail -25 ;;
+    ncu)
+      timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$b" -s 6 -c 1 -o "$out/$name" -f \
+        python bench.py --workload "$a" --steps 2 --warmup 3 --tune > "$out/$name.log" 2>&1
+      echo "rc=$?" | tee -a "$out/steps.log" ;;
+    sanity)
+      timeout 600 python tools/gpu/sanity.py > "$out/$name.log" 2>&1
+      echo "rc=$?" | tee -a "$out/steps.log"; tail -3 "$out/$name.log" ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
