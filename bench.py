@@ -139,7 +139,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -264,26 +264,67 @@ def run_b200(args):
     ev = model.evaluator(pool, 3, local)
     T = len(model.terms())
 
+    import ctypes
+    from qas_b200 import _lib
+    lib = _lib.load()
+    npar = p * c * 3
     d_k = torch.from_numpy(ks).to(dev)
     d_params = torch.from_numpy(params).to(dev)
-    d_energy = torch.empty(B, dtype=torch.float64, device=dev)
-    d_gc = torch.empty(B, p, 3, dtype=torch.float64, device=dev)
-    d_gd = torch.empty(p, c, 3, dtype=torch.float64, device=dev)
-    d_all_e = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
+    d_gc = torch.empty(B, p, 3, dtype=torch.float64, device=dev) if args.compact else None
+    # Each rank writes [energies | dense gradient] into ONE buffer, so that the exchange step is one collective:
+    # all_gather of the packed rows, then a fixed-order sum of the gathered gradient rows scaled by 1 / (B * world)
+    # (qas_reduce_rows: bit-identical on every rank).  Two send / receive buffers alternate so that the exchange of
+    # step i runs on a side stream while the kernels of step i + 1 do.
+    packs = [torch.empty(B + npar, dtype=torch.float64, device=dev) for _ in range(2 if world > 1 else 1)]
+    gathered = [torch.empty(world * (B + npar), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    d_mean = torch.empty(p, c, 3, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
     stream = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
 
-    def step():
-        ev.evaluate_device(d_k, d_params, d_energy, d_gc, d_gd, avg=(world == 1), stream=stream)
-        if world > 1:   # the exchange step: rewards gathered, gradient summed then / (B*world)
-            dist.all_gather_into_tensor(d_all_e, d_energy)
-            dist.all_reduce(d_gd)
-            d_gd.mul_(1.0 / (B * world))
+    def compute(i, kk=None):
+        pk = packs[i % len(packs)]
+        kk = d_k if kk is None else kk
+        nb = kk.shape[0]
+        # per-circuit energies + the batch-mean dense gradient, which is all search() consumes (mcts.py:340-347);
+        # --compact also materialises the per-circuit [B][p][l] gradients.  Multi-GPU: gradient SUM per rank.
+        ev.evaluate_device(kk, d_params, pk[:nb], d_gc if (args.compact and nb == B) else None, pk[B:].view(p, c, 3),
+                           avg=(world == 1), stream=stream)
 
-    for _ in range(args.warmup):
+    def exchange(i, nb_total):
+        """the exchange step on the CURRENT stream: one all-gather + the fixed-order mean of the gradient rows"""
+        g = gathered[i % 2]
+        dist.all_gather_into_tensor(g, packs[i % 2])
+        rc = lib.qas_reduce_rows(g.data_ptr() + 8 * B, world, B + npar, npar, 1.0 / nb_total, d_mean.data_ptr(),
+                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+
+    def step_sync(i, kk=None, nb_total=None):
+        compute(i, kk)
+        if world > 1:
+            exchange(i, nb_total if nb_total is not None else B * world)
+
+    for i in range(args.warmup):
         flush.zero_()
-        step()
+        step_sync(i)
     torch.cuda.synchronize()
+
+    # ---- multi-GPU parity self-check (untimed): the sharded batch and the sharded statevector against one GPU
+    parity = None
+    if world > 1:
+        parity = multi_gpu_parity_check(args, name, model, pool, ev, B, p, c, rank, world, dev, packs, gathered, d_mean,
+                                        d_params, step_sync, lib)
+        flag = torch.tensor([0 if (rank != 0 or parity["ok"]) else 1], device=dev)
+        dist.all_reduce(flag)
+        if int(flag.item()):
+            if rank == 0:
+                print(json.dumps({"parity_check": parity, "error": "multi-GPU parity check failed"}), flush=True)
+            dist.destroy_process_group()
+            sys.exit(3)
+        for i in range(2):
+            step_sync(i)
+        torch.cuda.synchronize()
+
     launches0 = ev.stats()["launches"]
     sampler = ClockSampler(local)
     if rank == 0:
@@ -293,25 +334,48 @@ def run_b200(args):
     torch.cuda.synchronize()
     e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    x0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    x1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    fl = [torch.cuda.Event() for _ in range(args.steps)]
     eval_ms = []
+    # Timed region.  Every step is bracketed by its own event pair; the 256 MB L2 flush sits between the pairs.
+    # Multi-GPU: the exchange of step i runs on the side stream and may only START after the flush that follows
+    # step i (so the untimed flush never hides it) and must be FINISHED before the end event of step i + 1 (so
+    # it is either overlapped with timed kernels or shows up in that step's time); the exchange of the last step
+    # has nothing to hide behind and is added in full.
+    flush.zero_()
     for i in range(args.steps):
-        flush.zero_()                     # L2 flush between timed iterations (outside the event pair)
         e0[i].record(stream)
-        step()
+        compute(i)
+        if world > 1 and i >= 1:
+            stream.wait_event(x1[i - 1])
         e1[i].record(stream)
+        flush.zero_()
+        if world > 1:
+            fl[i].record(stream)
+            with torch.cuda.stream(side):
+                side.wait_event(fl[i])
+                x0[i].record(side)
+                exchange(i, B * world)
+                x1[i].record(side)
         e1[i].synchronize()
         eval_ms.append(ev.stats()["last_eval_kernel_ms"])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     step_ms = [a.elapsed_time(b) for a, b in zip(e0, e1)]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    comm_ms = [a.elapsed_time(b) for a, b in zip(x0, x1)] if world > 1 else []
+    # the exchange of the last step has nothing left to hide behind: its whole duration is exposed
+    tail_ms = comm_ms[-1] if comm_ms else 0.0
+    total_ms = torch.tensor([sum(step_ms) + tail_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     launches = ev.stats()["launches"] - launches0        # this library's kernels only
+    launches += args.steps if world > 1 else 0            # + qas_reduce_rows per exchange
     total_s = float(total_ms.item()) * 1e-3
     value = world * B * args.steps / total_s
+    d_energy = packs[0][:B]
 
     # ---- reward-only evaluations (energy without gradient): rewards outnumber gradients 10-170x in a
     # real search, so their rate is reported next to the headline metric
@@ -348,6 +412,19 @@ def run_b200(args):
     e2e_value = world * B * args.steps / float(e2e_s.item())
     h2d = ks.nbytes + params.nbytes
     d2h = out["energy"].nbytes + out["grad_dense"].nbytes
+    # ... and with plain (pageable) NumPy arrays, which is what the drop-in model classes receive from search()
+    pk_np, pp_np = ks.copy(), params.copy()
+    for _ in range(2):
+        model.evaluate_batch(pk_np, pp_np, pool, want_grad=True)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.evaluate_batch(pk_np, pp_np, pool, want_grad=True)
+    e2e_p = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_p, op=dist.ReduceOp.MAX)
+    e2e_pageable = world * B * args.steps / float(e2e_p.item())
 
     if rank != 0:
         if world > 1:
@@ -408,6 +485,8 @@ def run_b200(args):
                    "source": "search-scripts-legacy/" + WORKLOADS[name][7], "l2_flush_between_steps": True,
                    "parallelism": "circuits sharded over %d GPU(s); all_gather rewards + all_reduce gradient" % world},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e_pageable": {"value": e2e_pageable, "unit": "evals/s",
+                         "note": "same call with pageable NumPy arrays (what search() hands the drop-in classes)"},
         "reward_only": {"value": reward_value, "unit": "evals/s", "ms_per_step": float(reward_ms.item()) / args.steps,
                         "note": "energy without gradient (getReward), same batch, device-resident inputs"},
         "gpu_launches": int(launches),
@@ -415,9 +494,57 @@ def run_b200(args):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
+    if world > 1:
+        line["parity_check"] = parity
+        line["comm_us_per_step"] = 1e3 * statistics.mean(comm_ms)
+        line["comm_exposed_us_per_step"] = 1e3 * tail_ms / args.steps
+        line["config"]["exchange"] = ("one all_gather of [rewards | gradient sum] per rank (%d B) + fixed-order reduction kernel, on a "
+                                      "side stream overlapped with the next step's kernels" % (8 * (B + npar)))
+    elif not args.tune and not args.no_others:
+        line["other_workloads"] = {w: secondary_workload(w, args, dev, local, flush, peak) for w in ("h2o_8q", "qaoa_7q", "h2_4q")
+                                   if w != name}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_workload(name, args, dev, local, flush, peak):
+    """The other BASELINE configurations in the same run (same box, same clocks record): device-timed value,
+    evaluation-kernel time and roofline fraction, measured like the headline workload (fewer steps)."""
+    import torch
+    mname, n, p = WORKLOADS[name][:3]
+    B = args.batch
+    model, pool, params, ks = make_workload(name, B, args.seed)
+    c = len(pool)
+    ev = model.evaluator(pool, 3, local)
+    d_k = torch.from_numpy(ks).to(dev)
+    d_params = torch.from_numpy(params).to(dev)
+    d_e = torch.empty(B, dtype=torch.float64, device=dev)
+    d_gd = torch.empty(p, c, 3, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    steps = max(5, args.steps // 2)
+    for _ in range(3):
+        flush.zero_()
+        ev.evaluate_device(d_k, d_params, d_e, None, d_gd, stream=stream)
+    torch.cuda.synchronize()
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    k_ms = []
+    for i in range(steps):
+        flush.zero_()
+        e0[i].record(stream)
+        ev.evaluate_device(d_k, d_params, d_e, None, d_gd, stream=stream)
+        e1[i].record(stream)
+        e1[i].synchronize()
+        k_ms.append(ev.stats()["last_eval_kernel_ms"])
+    ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1)) / steps
+    from qas_b200 import hamiltonians as _H
+    xmasks = sorted({_H.word_to_masks(w)[0] for _, w in model.terms()})
+    f_supp = support_flops(ks, pool, n, xmasks, model.init_state, nsample=1024) * len(ks)
+    km = statistics.mean(k_ms)
+    return {"value": B / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms, "kernel_ms": km, "steps": steps,
+            "frac": f_supp / (km * 1e-3) / 1e12 / peak, "n_qubits": n, "depth_p": p, "circuits_per_step": B,
+            "source": "search-scripts-legacy/" + WORKLOADS[name][7]}
 
 
 # ------------------------------------------------------------------------------- search epoch
@@ -508,18 +635,97 @@ def run_search_epoch(args):
     print(json.dumps(line), flush=True)
 
 
+def multi_gpu_parity_check(args, name, model, pool, ev, B, p, c, rank, world, dev, packs, gathered, d_mean, d_params,
+                           step_sync, lib):
+    """Untimed self-check of both NCCL paths on the hardware the bench runs on (the GPU tests that cover them
+    need >= 2 GPUs and are skipped on a one-GPU test box).
+      batch: rank 0 re-evaluates, on its own GPU, the first 1024 / world circuits of EVERY rank's shard and compares
+             them with the all-gathered rewards of a step;
+      grad:  a 4096-circuit batch, sharded round-robin, packed all-gather + fixed-order reduction, against the same
+             batch evaluated on rank 0 alone -- the reduction is np.mean(np.nan_to_num(stack), axis=0) of
+             qas/mcts/mcts.py:345-347;
+      sv:    a (26 + log2 world)-qubit HEA (L = 2) statevector sharded over all ranks with NCCL qubit swaps against
+             the unsharded run on rank 0.
+    Returns the report on rank 0 ({} elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    from qas_b200.largestate import LargeStateSimulator, hea_gate_list, zz_chain_terms
+    npar = p * c * 3
+    rep = {}
+    # ---- (1) rewards of the sharded bench batch
+    step_sync(0)
+    torch.cuda.synchronize()
+    all_e = gathered[0].view(world, B + npar)[:, :B].cpu().numpy()
+    m = max(1, 1024 // world)
+    if rank == 0:
+        worst = 0.0
+        for r in range(world):
+            ks_r = make_workload(name, B, args.seed + 1000 * r)[3][:m]
+            e_r = ev.evaluate(ks_r, d_params.cpu().numpy(), want_grad=False)["energy"]
+            worst = max(worst, float(np.max(np.abs(e_r - all_e[r, :m]))))
+        rep["batch_max_abs"] = worst
+        rep["batch_circuits_checked"] = m * world
+    dist.barrier()
+    # ---- (2) mean gradient of a small full batch
+    Bs = 4096
+    ks_s = make_workload(name, Bs, args.seed + 77)[3]
+    mine = torch.from_numpy(np.ascontiguousarray(ks_s[rank::world])).to(dev)
+    step_sync(0, mine, Bs)
+    torch.cuda.synchronize()
+    if rank == 0:
+        single = ev.evaluate(ks_s, d_params.cpu().numpy(), want_grad=True, dense=True, compact=False)
+        rep["grad_max_abs"] = float(np.max(np.abs(single["grad_dense"] - d_mean.cpu().numpy())))
+        e_sh = gathered[0].view(world, B + npar)[:, :Bs // world].cpu().numpy()
+        e_full = np.empty(Bs)
+        for r in range(world):
+            e_full[r::world] = e_sh[r]
+        rep["grad_batch_energy_max_abs"] = float(np.max(np.abs(e_full - single["energy"])))
+    dist.barrier()
+    # ---- (3) sharded statevector against the unsharded one
+    n_sv = 26 + int(round(np.log2(world)))
+    gl = hea_gate_list(n_sv, 2, seed=0)
+    terms = zz_chain_terms(n_sv)
+    solo = dist.new_group([0])
+    sim = LargeStateSimulator(n_sv, device=dev.index)
+    sim.run(gl)
+    e_sharded = sim.expval(terms)
+    torch.cuda.synchronize()
+    swaps = sim.swaps
+    del sim
+    torch.cuda.empty_cache()
+    if rank == 0:
+        one = LargeStateSimulator(n_sv, device=dev.index, group=solo)
+        one.run(gl)
+        e_one = one.expval(terms)
+        del one
+        torch.cuda.empty_cache()
+        rep["sv_abs"] = abs(e_sharded - e_one)
+        rep["sv_qubits"] = n_sv
+        rep["sv_swaps"] = swaps
+        rep["sv_energy"] = e_one
+        rep["ok"] = bool(rep["batch_max_abs"] <= 1e-12 and rep["grad_max_abs"] <= 1e-12 and
+                         rep["grad_batch_energy_max_abs"] <= 1e-12 and rep["sv_abs"] <= 1e-9)
+        rep["tolerances"] = {"batch_max_abs": 1e-12, "grad_max_abs": 1e-12, "sv_abs": 1e-9}
+    dist.barrier()
+    return rep
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help="default: 600 (b200 arm: >= 0.5 s of timed region), 10 (reference arm)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="lih_10q", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=65536, help="circuits per GPU per step")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--tune", action="store_true", help="kernel tuning: skip the CPU-baseline leg")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads block of the default line")
+    ap.add_argument("--compact", action="store_true", help="also write the per-circuit compact gradients [B][p][l] in the timed step")
     ap.add_argument("--search-epoch", action="store_true", help="time whole search() epochs instead (SURVEY 8d)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 600 if (args.impl == "b200" and not args.search_epoch) else 10
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.search_epoch:
         run_search_epoch(args)

@@ -204,6 +204,15 @@ int qas_adam_step(void *params, const void *grad, void *m, void *v, const void *
                   int t, double stepsize, double beta1, double beta2, double eps, double noise_factor,
                   void *stream);
 
+/* Fixed-order reduction of per-shard partial results: out[x] = scale * sum_r rows[r * row_stride + x],
+ * x < total (device pointers; rows are summed lane-strided in ascending r, then by a fixed shuffle tree, so
+ * every rank that reduces the same gathered buffer gets bit-identical numbers).  This is the multi-GPU end of
+ * the batch mean of mcts.py:345-347: each rank writes [energies | gradient sum] into one buffer, ONE
+ * all-gather moves it, and this kernel turns the gathered gradient sums into the mean (scale = 1 / B_total).
+ * Asynchronous on `stream`.                                                                       */
+int qas_reduce_rows(const void *rows, int nrows, uint64_t row_stride, uint64_t total, double scale, void *out,
+                    void *stream);
+
 /* Diagnostic (contexts created with the environment variable QAS_B200_PHASE_CLOCKS=1 only): sums,
  * over all circuits evaluated so far, of the SM clock cycles a team spent in the four phases of the
  * evaluation kernel -- out4 = {prologue, forward sweep, H application + energy, adjoint sweep}.

@@ -702,7 +702,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     CK(cudaGetLastError());
     stamp(6);
     const double scale = (flags & QAS_F_GRAD_SUM) ? 1.0 : 1.0 / (double)B;
-    grad_final_reduce_kernel<<<(unsigned)((npar * 32 + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, scale, ddense);
+    grad_final_reduce_kernel<<<(unsigned)((npar * 32 + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, npar, scale, ddense);
     CK(cudaGetLastError());
     ctx->stats.launches += 2;
     stamp(7);
@@ -838,6 +838,17 @@ extern "C" int qas_adam_step(void *params, const void *grad, void *m, void *v, c
       beta2, eps, noise_factor);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_create_error = std::string("adam_step_kernel: ") + cudaGetErrorString(e); return QAS_ERR_CUDA; }
+  return QAS_OK;
+}
+
+// ---------------------------------------------------------------------------------- shard reduction
+extern "C" int qas_reduce_rows(const void *rows, int nrows, uint64_t row_stride, uint64_t total, double scale, void *out,
+                               void *stream) {
+  if (!rows || !out || nrows <= 0 || total == 0 || row_stride < total) { g_create_error = "bad arguments to qas_reduce_rows"; return QAS_ERR_INVALID; }
+  grad_final_reduce_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const double *)rows, nrows, (size_t)row_stride, (size_t)total, scale, (double *)out);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_create_error = std::string("grad_final_reduce_kernel: ") + cudaGetErrorString(e); return QAS_ERR_CUDA; }
   return QAS_OK;
 }
 

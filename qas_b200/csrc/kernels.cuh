@@ -1138,13 +1138,13 @@ static __global__ void grad_chunk_reduce_kernel(const int32_t *k, const double *
 
 // one warp per output element: lane q sums chunks q, q+32, ... in order, then a fixed shuffle tree
 // combines the 32 lanes -- the summation order depends only on (nchunks), never on scheduling
-static __global__ void grad_final_reduce_kernel(const double *partial, int nchunks, size_t total,
-                                         double scale, double *out) {
+static __global__ void grad_final_reduce_kernel(const double *partial, int nchunks, size_t stride, size_t total,
+                                                double scale, double *out) {
   const size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (x >= total) return;
   double s = 0.0;
-  for (int ch = lane; ch < nchunks; ch += 32) s += partial[(size_t)ch * total + x];
+  for (int ch = lane; ch < nchunks; ch += 32) s += partial[(size_t)ch * stride + x];
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   if (lane == 0) out[x] = s * scale;

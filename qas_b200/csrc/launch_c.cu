@@ -65,6 +65,6 @@ cudaError_t qas_launch_finalize_reduce(qas_ctx *ctx, const uint32_t *tape, size_
                                                         ctx->d_partial);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  grad_final_reduce_kernel<<<(unsigned)((npar * 32 + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, scale, dense);
+  grad_final_reduce_kernel<<<(unsigned)((npar * 32 + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, npar, scale, dense);
   return cudaGetLastError();
 }
