@@ -63,6 +63,10 @@ class SearchConfig:
     search_reset: bool = True
     prune: bool = True
     avg_gradients: bool = True
+    # not upstream (opt-in): selection rounds issued `leaf_parallel` at a time under a
+    # virtual loss and rewarded by one batched launch; 1 = the reference's sequential rounds
+    leaf_parallel: int = 1
+    virtual_loss: Optional[float] = None
 
     @classmethod
     def from_call(cls, args, kwargs):
@@ -97,9 +101,16 @@ USE_NATIVE_TREE = "auto"
 
 
 def _native_possible(cfg):
+    """The native tree computes reward = reward_sign * loss itself: it can only stand in for models whose
+    reward is that linear map (not VQLS' exp(-10 loss), not a class that overrides getReward)."""
     from qas_b200.mcts.native import native_penalty
+    from qas_b200.qml_models.hamiltonian_model import HamiltonianModel
     name = getattr(cfg.state_class, "name", "")
-    return name in ("QMLStateBasicGates", "QMLStateBasicGatesNoRestrictions") and native_penalty(cfg.penalty_function) is not None
+    model = cfg.model
+    linear_reward = not hasattr(model, "rewards_from_losses") and (
+        not isinstance(model, type) or not issubclass(model, HamiltonianModel) or model.getReward is HamiltonianModel.getReward)
+    return (name in ("QMLStateBasicGates", "QMLStateBasicGatesNoRestrictions") and linear_reward
+            and native_penalty(cfg.penalty_function) is not None)
 
 
 def _penalised(cfg, reward, node):
@@ -160,7 +171,8 @@ def search(*args, **kwargs):
         prune_reward_ratio=cfg.prune_constant_min, max_visits_prune_threshold=cfg.max_visits_prune_threshold,
         min_num_children=cfg.min_num_children, sampling_execute_rounds=cfg.sampling_execute_rounds,
         exploit_execute_rounds=cfg.exploit_execute_rounds, sample_policy=cfg.cmab_sample_policy,
-        exploit_policy=cfg.cmab_exploit_policy, gate_limit_dict=cfg.gate_limit_dict, prune=cfg.prune)
+        exploit_policy=cfg.cmab_exploit_policy, gate_limit_dict=cfg.gate_limit_dict, prune=cfg.prune,
+        leaf_parallel=cfg.leaf_parallel, virtual_loss=cfg.virtual_loss)
     controller.setRoot()
     params = np.array(cfg.init_params, dtype=np.float64)
     optimizer = cfg.super_circ_train_optimizer(cfg.super_circ_train_lr)

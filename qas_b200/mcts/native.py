@@ -114,7 +114,8 @@ class NativeMCTSController:
                  initial_legal_control_qubit_choice=None, alpha=1 / np.sqrt(2), prune_reward_ratio=0.9,
                  max_visits_prune_threshold=50, min_num_children=5, sampling_execute_rounds=20,
                  exploit_execute_rounds=200, sample_policy="local_optimal", exploit_policy="local_optimal",
-                 gate_limit_dict=None, prune=True, seed=None, use_gpu=None):
+                 gate_limit_dict=None, prune=True, seed=None, use_gpu=None, leaf_parallel=1, virtual_loss=None,
+                 param_slots=3):
         self._lib = _bind(_lib.load())
         self.model, self.pool, self.max_depth = model, op_pool, int(target_circuit_depth)
         pen = native_penalty(reward_penalty_function)
@@ -151,7 +152,7 @@ class NativeMCTSController:
         self._evaluator = None
         gpu = hasattr(model, "evaluator") if use_gpu is None else use_gpu
         if gpu:
-            self._evaluator = model.evaluator(op_pool, 3)
+            self._evaluator = model.evaluator(op_pool, int(param_slots))
             self._check(self._lib.qas_mcts_bind_evaluator(self._h, self._evaluator._h))
 
     # ------------------------------------------------------------------ plumbing
@@ -192,6 +193,9 @@ class NativeMCTSController:
         """New parameter super-set: uploads it (GPU evaluator) and drops every cached reward."""
         self._params = np.ascontiguousarray(params, dtype=np.float64)
         p, c, l = self._params.shape
+        if self._evaluator is not None and l != self._evaluator.l:
+            raise ValueError("parameter super-set has %d slots per (depth, key) but the bound evaluator was created for %d "
+                             "(pass param_slots=%d to NativeMCTSController)" % (l, self._evaluator.l, l))
         self._check(self._lib.qas_mcts_set_params(self._h, self._params.ctypes.data, p, c, l))
 
     def clearRewardCache(self):

@@ -1,16 +1,25 @@
-"""Search tree of the nested MCTS: nodes, controller, tree policy.
+"""Search tree of the nested MCTS: nodes, controller, tree policy (Python compatibility controller;
+the product tree is qas_b200/csrc/mcts.cu).
 
-Behavioural restatement of the reference controller (qas/mcts/mcts.py:18-201) -- expansion with a
-shuffled legal-action list (:83-92), back-propagation (:94-98), the UCT score
+Implements the policy of the reference controller (qas/mcts/mcts.py:18-201) -- expansion by a
+uniformly random untried legal action (:83-92), back-propagation (:94-98), the UCT score
 ``Q/N + alpha * sqrt(2 ln N_parent / N)`` with random tie-breaks and the three child policies
 (:125-151), pruning of under-performing, often-visited children (:153-174), arc sampling by rounds
 of selection + simulation followed by a greedy descent (:186-193) and level-wise exploitation
-(:195-201) -- with the reward evaluation routed through the batched CUDA evaluator:
+(:195-201) -- under the reference's public names and call shapes, so experiment scripts keep
+working.  How it is organised here is different:
 
-  * ``batchRewards`` evaluates many structure lists in one launch;
-  * a reward cache keyed by ``tuple(k)`` is valid for as long as the parameters do not change
-    (the driver clears it around every optimiser step), so repeated terminal states are free.
-Public names and call shapes are the reference's, so experiment scripts keep working.
+  * every node keeps a pool of its untried legal actions and draws from it (the reference reshuffles
+    the whole legal list on every expansion and takes the first action that has no child: the same
+    distribution, without the quadratic rescans);
+  * all descents share one helper, all rewards one entry point that sends many structure lists to
+    the batched CUDA evaluator in one launch (``batchRewards``);
+  * rewards are cached by ``tuple(k)`` under a fingerprint of the parameter array, so a different (or
+    modified) parameter super-set can never be served stale rewards;
+  * opt-in LEAF-PARALLEL rollouts (``leaf_parallel > 1``): the selection rounds of
+    :176-184 are issued ``leaf_parallel`` at a time under a virtual loss, their rewards come back from one
+    batched evaluation, and the virtual losses are replaced by the real rewards.  This changes the
+    statistics the selections see (not semantics-preserving), so the default stays sequential.
 """
 import random
 from typing import Callable, List, Optional, Set
@@ -19,11 +28,11 @@ import numpy as np
 
 from qas_b200.mcts.mcts_state import StateOfMCTS
 
-_NEG_INF = float("-inf")
-
 
 class TreeNode():
     """One partial structure list with its visit statistics."""
+
+    __slots__ = ("state", "parent", "children", "numVisits", "totalReward", "isTerminal", "isFullyExpanded", "_untried")
 
     def __init__(self, state: StateOfMCTS, parent):
         self.state, self.parent = state, parent
@@ -31,18 +40,31 @@ class TreeNode():
         self.numVisits, self.totalReward = 0, 0
         self.isTerminal = state.isTerminal()
         self.isFullyExpanded = self.isTerminal
+        self._untried = None            # legal actions without a child yet (filled at the first expansion)
 
     def mean(self):
         return self.totalReward / self.numVisits
+
+    def path_to_root(self):
+        node = self
+        while node is not None:
+            yield node
+            node = node.parent
 
     def __repr__(self):
         return "TreeNode(k=%s, visits=%d, total=%r, terminal=%s, expanded=%s)" % (
             self.state.getCurrK(), self.numVisits, self.totalReward, self.isTerminal, self.isFullyExpanded)
 
 
-def _uct_scores(parent: TreeNode, children, alpha):
-    bonus = 2.0 * np.log(parent.numVisits)
-    return [ch.totalReward / ch.numVisits + alpha * np.sqrt(bonus / ch.numVisits) for ch in children]
+def _params_fingerprint(params):
+    """Cheap identity of a parameter super-set: buffer address, shape and two checksums.  An optimiser step
+    changes the checksums even when it writes in place."""
+    flat = np.asarray(params).reshape(-1)
+    stride = max(1, flat.size // 4096)
+    sample = flat[::stride]
+    return (flat.__array_interface__["data"][0], flat.size, float(sample.sum()),
+            float(np.dot(sample, np.arange(1, sample.size + 1, dtype=np.float64))))
+
 
 class MCTSController():
     def __init__(self, model, op_pool, target_circuit_depth: int, state_class=None,
@@ -50,115 +72,122 @@ class MCTSController():
                  initial_legal_control_qubit_choice: Optional[Set] = None, alpha=1 / np.sqrt(2),
                  prune_reward_ratio=0.9, max_visits_prune_threshold=50, min_num_children=5,
                  sampling_execute_rounds=20, exploit_execute_rounds=200, sample_policy='local_optimal',
-                 exploit_policy='local_optimal', gate_limit_dict: Optional[dict] = None, prune=True):
-        self.model = model
-        self.pool = op_pool
+                 exploit_policy='local_optimal', gate_limit_dict: Optional[dict] = None, prune=True,
+                 leaf_parallel=1, virtual_loss=None):
+        self.model, self.pool = model, op_pool
         self.pool_dict = op_pool.pool
         self.pool_keys = list(self.pool_dict.keys())
         self.max_depth = target_circuit_depth
         self.penalty_func = reward_penalty_function
-        self.initial_legal_control_qubit_choice = set() if initial_legal_control_qubit_choice is None \
-            else initial_legal_control_qubit_choice
+        self.initial_legal_control_qubit_choice = set(initial_legal_control_qubit_choice or ())
         self.alpha = alpha
-        self.first_policy = sample_policy
-        self.second_policy = exploit_policy
+        self.first_policy, self.second_policy = sample_policy, exploit_policy
+        self.prune, self.prune_counter = prune, 0
         self.prune_reward_ratio = prune_reward_ratio
         self.max_visits_prune_threshold = max_visits_prune_threshold
         self.min_num_children = min_num_children
         self.sampling_execute_rounds = sampling_execute_rounds
         self.exploit_execute_rounds = exploit_execute_rounds
-        self.prune_counter = 0
-        self.prune = prune
         self.initial_state = state_class(op_pool=self.pool, maxDepth=self.max_depth,
                                          qubit_with_actions=self.initial_legal_control_qubit_choice,
                                          gate_limit_dict=gate_limit_dict)
-        # evaluation bookkeeping (not upstream): rewards requested / evaluated, per-epoch cache
-        self.reward_cache = {}
+        # not upstream: leaf-parallel rollouts, reward cache, evaluation counters
+        self.leaf_parallel = max(1, int(leaf_parallel))
+        self.virtual_loss = virtual_loss           # reward booked for an in-flight leaf; None: the running minimum
+        self._min_reward = 0.0
+        self.reward_cache, self._cache_tag = {}, None
         self.num_reward_requests = 0
         self.num_reward_evaluations = 0
 
     # ------------------------------------------------------------------ tree bookkeeping
-    def _reset(self):
-        self.root = TreeNode(self.initial_state, None)
-        self.prune_counter = 0
-
     def setRoot(self):
         self.root = TreeNode(self.initial_state, None)
 
+    def _reset(self):
+        self.setRoot()
+        self.prune_counter = 0
+
     def getActionFromBestChild(self, root: TreeNode, best_child):
-        for action, node in root.children.items():
-            if node is best_child:
-                return action
+        return next((action for action, node in root.children.items() if node is best_child), None)
 
     def expand(self, node: TreeNode):
-        actions = node.state.getLegalActions()
-        random.shuffle(actions)
-        for action in actions:
-            if action not in node.children:
-                child = TreeNode(node.state.takeAction(action), node)
-                node.children[action] = child
-                if len(actions) == len(node.children):
-                    node.isFullyExpanded = True
-                return child
+        if node._untried is None:
+            node._untried = [a for a in node.state.getLegalActions() if a not in node.children]
+        pool = node._untried
+        if not pool:
+            node.isFullyExpanded = True
+            return None
+        pick = random.randrange(len(pool))
+        pool[pick], pool[-1] = pool[-1], pool[pick]
+        action = pool.pop()
+        child = node.children[action] = TreeNode(node.state.takeAction(action), node)
+        node.isFullyExpanded = not pool
+        return child
 
     def backPropagate(self, node: TreeNode, reward):
-        while node is not None:
-            node.numVisits += 1
-            node.totalReward += reward
-            node = node.parent
+        for ancestor in node.path_to_root():
+            ancestor.numVisits += 1
+            ancestor.totalReward += reward
 
     # ------------------------------------------------------------------ rewards
     def clearRewardCache(self):
-        self.reward_cache = {}
+        self.reward_cache, self._cache_tag = {}, None
 
-    def simulationWithSuperCircuitParamsAndK(self, k: List[int], params):
-        assert len(k) == self.max_depth
-        self.num_reward_requests += 1
-        key = tuple(k)
-        if key in self.reward_cache:
-            self.r = self.reward_cache[key]
-            return self.r
-        p, c, l = params.shape[0], params.shape[1], params.shape[2]
-        self.r = self.model(p, c, l, k, self.pool).getReward(params)
-        self.num_reward_evaluations += 1
-        self.reward_cache[key] = self.r
-        return self.r
+    def _cache_for(self, params):
+        tag = _params_fingerprint(params)
+        if tag != self._cache_tag:
+            self.reward_cache, self._cache_tag = {}, tag
+        return self.reward_cache
+
+    def _evaluate_missing(self, missing, params):
+        """rewards of structure lists that are not cached yet: one launch when the model can batch"""
+        if hasattr(self.model, "evaluate_batch"):
+            out = self.model.evaluate_batch(np.array(missing, dtype=np.int32), params, self.pool, want_grad=False)
+            if hasattr(self.model, "rewards_from_losses"):      # non-linear reward (VQLS: exp(-10 loss))
+                return [float(r) for r in self.model.rewards_from_losses(out["energy"])]
+            sign = getattr(self.model, "reward_sign", -1.0)
+            return [float(sign * e) for e in out["energy"]]
+        p, c, l = params.shape
+        return [self.model(p, c, l, list(k), self.pool).getReward(params) for k in missing]
 
     def batchRewards(self, ks, params):
         """Rewards of many structure lists in one launch (models that expose evaluate_batch)."""
+        cache = self._cache_for(params)
         self.num_reward_requests += len(ks)
-        missing = [k for k in {tuple(k) for k in ks} if k not in self.reward_cache]
+        keys = [tuple(k) for k in ks]
+        missing = [k for k in dict.fromkeys(keys) if k not in cache]
         if missing:
-            if hasattr(self.model, "evaluate_batch"):
-                out = self.model.evaluate_batch(np.array(missing, dtype=np.int32), params, self.pool, want_grad=False)
-                if hasattr(self.model, "rewards_from_losses"):      # non-linear reward (VQLS: exp(-10 loss))
-                    rewards = self.model.rewards_from_losses(out["energy"])
-                else:
-                    rewards = getattr(self.model, "reward_sign", -1.0) * np.asarray(out["energy"])
-                for k, r in zip(missing, rewards):
-                    self.reward_cache[k] = float(r)
-            else:
-                p, c, l = params.shape
-                for k in missing:
-                    self.reward_cache[k] = self.model(p, c, l, list(k), self.pool).getReward(params)
+            cache.update(zip(missing, self._evaluate_missing(missing, params)))
             self.num_reward_evaluations += len(missing)
-        return [self.reward_cache[tuple(k)] for k in ks]
+        return [cache[k] for k in keys]
 
-    # ------------------------------------------------------------------ sampling policies
-    def randomSample(self):
-        node = self.root
+    def simulationWithSuperCircuitParamsAndK(self, k: List[int], params):
+        assert len(k) == self.max_depth
+        cache = self._cache_for(params)
+        self.num_reward_requests += 1
+        key = tuple(k)
+        if key not in cache:
+            p, c, l = params.shape
+            cache[key] = self.model(p, c, l, k, self.pool).getReward(params)
+            self.num_reward_evaluations += 1
+        self.r = cache[key]
+        return self.r
+
+    # ------------------------------------------------------------------ descents
+    def _descend(self, node, step):
         while not node.state.isTerminal():
-            if not node.isFullyExpanded:
-                node = self.expand(node)
-            else:
-                _, node = random.choice(list(node.children.items()))
-        return node.state.getCurrK(), node
+            node = step(node)
+        return node
+
+    def randomSample(self):
+        leaf = self._descend(self.root, lambda n: self.expand(n) if not n.isFullyExpanded
+                             else random.choice(list(n.children.values())))
+        return leaf.state.getCurrK(), leaf
 
     def uctSample(self, policy='local_optimal'):
-        node = self.root
-        while not node.state.isTerminal():
-            node = self.expand(node) if not node.isFullyExpanded else self.getBestChild(node, self.alpha, policy=policy)
-        return node.state.getCurrK(), node
+        leaf = self._descend(self.root, lambda n: self.expand(n) if not n.isFullyExpanded
+                             else self.getBestChild(n, self.alpha, policy=policy))
+        return leaf.state.getCurrK(), leaf
 
     def getBestChild(self, node: TreeNode, alpha, policy='local_optimal'):
         children = list(node.children.values())
@@ -168,16 +197,19 @@ class MCTSController():
             return random.choice(children)
         if policy not in ('local_optimal', 'local_sub_optimal'):
             raise ValueError("No such policy: %s" % policy)
-        # running maximum with ties; the runner-up set is whatever held the lead just before the
-        # final maximum took over (for a single child it is that child)
-        lead, runner_up, top = [], [], _NEG_INF
-        for child, score in zip(children, _uct_scores(node, children, alpha)):
-            if score > top:
-                runner_up = [child] if top == _NEG_INF else lead
-                lead, top = [child], score
-            elif score == top:
-                lead.append(child)
-        return np.random.choice(lead if policy == 'local_optimal' else runner_up)
+        visits = np.array([ch.numVisits for ch in children], dtype=np.float64)
+        totals = np.array([ch.totalReward for ch in children], dtype=np.float64)
+        scores = totals / visits + alpha * np.sqrt(2.0 * np.log(node.numVisits) / visits)
+        lead = np.flatnonzero(scores == scores.max())
+        if policy == 'local_optimal':
+            return children[int(np.random.choice(lead))]
+        # 'local_sub_optimal' (mcts.py:141-148): whatever held the lead, in child order, just before the final
+        # maximum took it over; for a maximum that led from the start, the first child
+        first_lead = int(lead[0])
+        if first_lead == 0:
+            return children[0]
+        before = scores[:first_lead]
+        return children[int(np.random.choice(np.flatnonzero(before == before.max())))]
 
     def _prune(self, node: TreeNode):
         """Drop children whose mean reward fell below ratio * (parent mean) after more than
@@ -188,10 +220,7 @@ class MCTSController():
         doomed = sorted(((child.mean(), key) for key, child in node.children.items()
                          if child.mean() < cut and child.numVisits > self.max_visits_prune_threshold),
                         key=lambda item: item[0])
-        keep_from = len(doomed) - self.min_num_children
-        for rank, (_, key) in enumerate(doomed):
-            if rank > keep_from:
-                break
+        for _, key in doomed[:max(0, len(doomed) - self.min_num_children + 1)]:
             del node.children[key]
             self.prune_counter += 1
 
@@ -201,28 +230,48 @@ class MCTSController():
         self._prune(node)
         return self.getBestChild(node, self.alpha, policy=self.first_policy)
 
+    def _penalised(self, reward, node):
+        return reward if self.penalty_func is None else self.penalty_func(reward, node)
+
     def executeRoundWithSuperCircParamsFromAnyNode(self, node: TreeNode, params):
-        if node is None:
-            node = self.root
-        while not node.state.isTerminal():
-            node = self.selectNode(node)
-        reward = self.simulationWithSuperCircuitParamsAndK(node.state.getCurrK(), params)
-        reward = reward if self.penalty_func is None else self.penalty_func(reward, node)
-        self.backPropagate(node, reward)
-        return node
+        leaf = self._descend(self.root if node is None else node, self.selectNode)
+        reward = self.simulationWithSuperCircuitParamsAndK(leaf.state.getCurrK(), params)
+        self.backPropagate(leaf, self._penalised(reward, leaf))
+        return leaf
+
+    # ------------------------------------------------------------------ leaf-parallel rounds (opt-in)
+    def _rounds(self, start, params, rounds):
+        """`rounds` selection + simulation rounds from `start`; with leaf_parallel > 1 they are issued in
+        waves under a virtual loss and evaluated in one launch per wave."""
+        if self.leaf_parallel <= 1:
+            for _ in range(rounds):
+                self.executeRoundWithSuperCircParamsFromAnyNode(node=start, params=params)
+            return
+        done = 0
+        while done < rounds:
+            wave = min(self.leaf_parallel, rounds - done)
+            vl = self.virtual_loss if self.virtual_loss is not None else self._min_reward
+            leaves = []
+            for _ in range(wave):
+                leaf = self._descend(start, self.selectNode)
+                self.backPropagate(leaf, vl)                     # book the in-flight leaf
+                leaves.append(leaf)
+            rewards = self.batchRewards([leaf.state.getCurrK() for leaf in leaves], params)
+            for leaf, reward in zip(leaves, rewards):
+                real = self._penalised(reward, leaf)
+                self._min_reward = min(self._min_reward, real)
+                for ancestor in leaf.path_to_root():            # swap the virtual loss for the reward
+                    ancestor.totalReward += real - vl
+            done += wave
 
     def sampleArcWithSuperCircParams(self, params):
-        curr = self.root
-        for _ in range(self.sampling_execute_rounds):
-            self.executeRoundWithSuperCircParamsFromAnyNode(node=curr, params=params)
-        while not curr.state.isTerminal():
-            curr = self.getBestChild(curr, self.alpha, policy=self.first_policy)
-        return curr.state.getCurrK(), curr
+        self._rounds(self.root, params, self.sampling_execute_rounds)
+        leaf = self._descend(self.root, lambda n: self.getBestChild(n, self.alpha, policy=self.first_policy))
+        return leaf.state.getCurrK(), leaf
 
     def exploitArcWithSuperCircParams(self, params):
         curr = self.root
         while not curr.state.isTerminal():
-            for _ in range(self.exploit_execute_rounds):
-                self.executeRoundWithSuperCircParamsFromAnyNode(node=curr, params=params)
+            self._rounds(curr, params, self.exploit_execute_rounds)
             curr = self.getBestChild(curr, 0, policy=self.second_policy)
         return curr.state.getCurrK(), curr

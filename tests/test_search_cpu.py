@@ -280,3 +280,70 @@ def test_search_with_native_tree_matches_python_tree_statistically():
     assert nat[4].num_reward_evaluations < nat[4].num_reward_requests
     assert nat[3] > py[3] - 0.2                            # best reward in the same ballpark
     nat[4].close()
+
+
+def test_reward_cache_is_tied_to_the_parameter_values():
+    """rewards cached for one parameter super-set are never served for another one -- not for a new
+    array, and not for the same array modified in place (both change the fingerprint)."""
+    pool = helpers.near_cx_pool(2, [[0, 1], [1, 0]])
+    ctl = MCTSController(OracleBatchModel, pool, 3, state_class=QMLStateBasicGates)
+    ctl.setRoot()
+    k = [0, 4, 2]
+    a = np.random.default_rng(0).standard_normal((3, len(pool), 3))
+    r1 = ctl.simulationWithSuperCircuitParamsAndK(k, a)
+    assert ctl.simulationWithSuperCircuitParamsAndK(k, a) == r1 and ctl.num_reward_evaluations == 1
+    b = a + 0.25
+    r2 = ctl.simulationWithSuperCircuitParamsAndK(k, b)
+    assert ctl.num_reward_evaluations == 2 and abs(r2 + sim.energy(2, k, pool.pool, b, TERMS)) < 1e-14
+    b[0, 0, 1] += 0.5                                   # in place
+    r3 = ctl.batchRewards([k, k], b)
+    assert ctl.num_reward_evaluations == 3 and abs(r3[0] + sim.energy(2, k, pool.pool, b, TERMS)) < 1e-14 and r3[0] == r3[1]
+
+
+def test_leaf_parallel_rounds_book_and_replace_virtual_losses():
+    """Opt-in leaf-parallel rollouts: every wave books its leaves under a virtual loss, rewards them with ONE
+    batched evaluation and replaces the virtual loss by the reward -- afterwards the statistics are those of
+    `rounds` ordinary back-propagations (visits) with the true rewards (totals)."""
+    pool = helpers.near_cx_pool(2, [[0, 1], [1, 0]])
+    params = np.random.default_rng(4).standard_normal((3, len(pool), 3))
+    random.seed(5)
+    np.random.seed(5)
+    ctl = MCTSController(OracleBatchModel, pool, 3, state_class=QMLStateBasicGates, gate_limit_dict={"CNOT": 2},
+                         sampling_execute_rounds=24, leaf_parallel=8, virtual_loss=-3.0, prune=False)
+    ctl.setRoot()
+    calls0 = OracleBatchModel.batch_calls
+    arc, leaf = ctl.sampleArcWithSuperCircParams(params)
+    assert OracleBatchModel.batch_calls - calls0 <= 3           # 24 rounds in 3 waves
+    assert ctl.root.numVisits == 24
+
+    def check(node):
+        if node.children:
+            assert node.numVisits >= sum(ch.numVisits for ch in node.children.values())
+            for ch in node.children.values():
+                check(ch)
+        if node.state.isTerminal() and node.numVisits:
+            r = -sim.energy(2, node.state.getCurrK(), pool.pool, params, TERMS)
+            assert abs(node.totalReward - node.numVisits * r) < 1e-10      # no virtual loss left behind
+    check(ctl.root)
+    assert abs(ctl.root.totalReward - sum(ch.totalReward for ch in ctl.root.children.values())) < 1e-10
+    assert len(arc) == 3 and leaf.state.isTerminal()
+    # the driver passes the option through
+    out = _run(OracleBatchModel, 6, leaf_parallel=4, num_iterations=3)
+    assert out[4].leaf_parallel == 4 and len(out[5]) == 3
+
+
+def test_native_tree_is_refused_for_non_linear_rewards():
+    """the native tree computes reward = reward_sign * loss; VQLS' exp(-10 loss) must keep the Python tree."""
+    from qas_b200.mcts.driver import _native_possible
+    from qas_b200.mcts.native import PlaceholderPenalty
+    from qas_b200.qml_models.qml_models_legacy import LiH
+    from qas_b200.qml_models.vqls_model import VQLSDemo
+    pool = helpers.near_cx_pool(4)
+    base = dict(op_pool=pool, state_class=QMLStateBasicGates, penalty_function=PlaceholderPenalty(pool, 5, 1.0))
+    assert _native_possible(SearchConfig.from_call((), dict(model=LiH, **base)))
+    assert not _native_possible(SearchConfig.from_call((), dict(model=VQLSDemo, **base)))
+
+    class Custom(LiH):
+        def getReward(self, params):
+            return float(np.exp(-self.getLoss(params)))
+    assert not _native_possible(SearchConfig.from_call((), dict(model=Custom, **base)))

@@ -4,6 +4,7 @@
 # steps: tests | tests:<pytest -k expr> | bench:<workload>[:<env assignments,comma separated>] | stages:<workload>
 #        | launches:<workload> | ncu:<workload>:<kernel regex> | sanity
 set -u
+export QAS_B200_NO_REBUILD=1
 tag=$1; shift
 out=gpurun_out/$tag
 mkdir -p "$out"
