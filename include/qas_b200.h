@@ -68,8 +68,11 @@ typedef struct {
 
 /* flags of qas_eval_batch */
 #define QAS_F_DEVICE_PTRS 0x1u /* k, params, energy, grad_* are device pointers; the call is    */
-                               /* asynchronous on `stream`. Otherwise host pointers: the call    */
-                               /* stages them through pinned memory and returns synchronously.   */
+                               /* asynchronous on `stream`. Otherwise host pointers: they are    */
+                               /* copied straight from / to the caller's memory with              */
+                               /* cudaMemcpyAsync (truly asynchronous only for pinned memory;     */
+                               /* pageable memory works and is staged by the CUDA driver) and    */
+                               /* the call returns synchronously.                                */
 #define QAS_F_GRAD_SUM 0x2u    /* grad_dense = sum over the batch instead of mean                */
                                /* (search(..., avg_gradients=False), mcts.py:347)                */
 
@@ -78,6 +81,12 @@ typedef struct {
                                   /* one-reward-at-a-time rollouts of mcts.py:100-105,181 then cost   */
                                   /* one k upload, the kernels and an 8-byte read-back                */
 
+/* Threading / stream contract: a context is NOT thread-safe and owns one set of scratch buffers (tape records,
+ * gate tables, cross matrices, bin queues, reduction partials).  Use it from one thread and one stream at a
+ * time: a second call may only be issued on another stream after the first one has completed (device-pointer
+ * calls are asynchronous -- synchronise or chain the streams with an event).  A call without
+ * QAS_F_PARAMS_RESIDENT rebuilds the gate table and so invalidates a table left by qas_set_params.  Use one
+ * context per stream for concurrent work.                                                          */
 typedef struct qas_ctx qas_ctx;
 
 /* Library / build info. */
@@ -203,6 +212,19 @@ int qas_get_stats(const qas_ctx *ctx, qas_stats *out);
 int qas_adam_step(void *params, const void *grad, void *m, void *v, const void *noise, uint64_t n,
                   int t, double stepsize, double beta1, double beta2, double eps, double noise_factor,
                   void *stream);
+
+/* Batch mean of per-circuit compact gradients that already sit on the device (device pointers; asynchronous on
+ * `stream`): grad_dense[p][c][l] = mean | sum over b of scatter(nan_to_num(grad_compact[b])) by k[b] -- the
+ * reduction of mcts.py:345-347 with the deterministic two-stage summation qas_eval_batch uses.  For costs whose
+ * per-circuit gradient is assembled outside the evaluator (VQLS).                                  */
+int qas_batch_mean(qas_ctx *ctx, int B, int p, const int32_t *k, const double *grad_compact, double *grad_dense,
+                   uint32_t flags, void *stream);
+
+/* VQLS cost from its two Pauli-sum expectations (VQLSDemo, qml_models_legacy.py:1880-1951,1969-1972):
+ * loss[b] = 1/2 - |N_b| / (2 n |D_b|) and, when pl > 0, the quotient rule on the two compact gradients
+ * gN, gD [B][pl] (gN is overwritten with dloss).  Device pointers; asynchronous on `stream`.      */
+int qas_vqls_combine(const void *N, const void *D, void *gN, const void *gD, int B, int pl, int n_qubits, void *loss,
+                     void *stream);
 
 /* Fixed-order reduction of per-shard partial results: out[x] = scale * sum_r rows[r * row_stride + x],
  * x < total (device pointers; rows are summed lane-strided in ascending r, then by a fixed shuffle tree, so

@@ -75,6 +75,13 @@ int qas_mcts_set_params(qas_mcts *m, const double *params, int p, int c, int l);
 int qas_mcts_reset(qas_mcts *m);                       /* _reset: fresh root, prune counter = 0   */
 int qas_mcts_set_alpha(qas_mcts *m, double alpha);
 int qas_mcts_set_prune_ratio(qas_mcts *m, double ratio);
+/* Leaf-parallel rounds (opt-in, not semantics-preserving): the selection + simulation
+ * rounds of sampleArc / exploitArc (mcts.py:176-184,187-188,198-199) are issued `leaves` at a time; every
+ * selected leaf is booked at once with one visit and a virtual loss (fixed_virtual_loss != 0: `virtual_loss`,
+ * else the smallest penalised reward seen so far), the wave's rewards come from ONE batched evaluation, and
+ * the virtual losses are then replaced by the real rewards.  leaves = 1 (default) = the reference's sequential
+ * rounds.                                                                                         */
+int qas_mcts_set_leaf_parallel(qas_mcts *m, int leaves, int fixed_virtual_loss, double virtual_loss);
 
 /* warm-up epoch (mcts.py:298-305): draw B arcs with randomSample, evaluate them in ONE batch,
  * back-propagate the (penalised) rewards.  out_ks: int32 [B][p]; out_rewards: double [B] raw.   */
@@ -96,6 +103,7 @@ typedef struct {
   uint64_t expansions;
   int32_t prune_counter;
   int32_t root_visits;
+  uint64_t reward_batches;      /* batched evaluator calls issued by leaf-parallel waves / warm-up   */
 } qas_mcts_stats;
 int qas_mcts_get_stats(const qas_mcts *m, qas_mcts_stats *out);
 

@@ -841,6 +841,61 @@ extern "C" int qas_adam_step(void *params, const void *grad, void *m, void *v, c
   return QAS_OK;
 }
 
+// ---------------------------------------------------------------------------------- batch mean of given gradients
+// stack -> nan_to_num -> mean | sum (mcts.py:345-347) of per-circuit compact gradients that are already on the
+// device, with the deterministic two-stage reduction of qas_eval_batch.  Used where the per-circuit gradient is
+// not a plain adjoint gradient (VQLS: quotient rule of two Pauli sums).
+extern "C" int qas_batch_mean(qas_ctx *ctx, int B, int p, const int32_t *k, const double *grad_compact,
+                              double *grad_dense, uint32_t flags, void *stream) {
+  if (!ctx || B <= 0 || p <= 0 || !k || !grad_compact || !grad_dense) return fail(ctx, QAS_ERR_INVALID, "bad arguments to qas_batch_mean");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int c = ctx->c, l = ctx->l;
+  const size_t npar = (size_t)p * c * l;
+  const int chunk = 64, nchunks = (B + chunk - 1) / chunk;
+  int depth_tile = p;
+  while ((size_t)depth_tile * c * l * 8 > 96 * 1024 && depth_tile > 1) depth_tile = (depth_tile + 1) / 2;
+  const size_t sm = (size_t)depth_tile * c * l * 8;
+  CK(ensure(&ctx->d_partial, &ctx->cap_partial, (size_t)nchunks * npar));
+  CK(cudaFuncSetAttribute(grad_chunk_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  dim3 grid(nchunks, (p + depth_tile - 1) / depth_tile);
+  const int cthreads = std::min(256, std::max(64, ((std::min(depth_tile, p) * l + 31) / 32) * 32));
+  grad_chunk_reduce_kernel<<<grid, cthreads, sm, st>>>(k, grad_compact, B, p, c, l, chunk, depth_tile, ctx->d_partial);
+  CK(cudaGetLastError());
+  const double scale = (flags & QAS_F_GRAD_SUM) ? 1.0 : 1.0 / (double)B;
+  grad_final_reduce_kernel<<<(unsigned)((npar * 32 + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, npar, scale, grad_dense);
+  CK(cudaGetLastError());
+  ctx->stats.launches += 2;
+  return QAS_OK;
+}
+
+// VQLS cost (qml_models_legacy.py:1880-1951 restated as two Pauli-sum expectations N, D on n qubits):
+//   loss = 1/2 - |N| / (2 n |D|),   dloss = -sign(N) / (2 n |D|) dN + |N| sign(D) / (2 n D^2) dD
+// elementwise over the batch; gN is overwritten with the loss gradient (device pointers, asynchronous).
+static __global__ void vqls_combine_kernel(const double *N, const double *D, double *gN, const double *gD, int B, int pl,
+                                           double nq, double *loss) {
+  const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= (size_t)B * (size_t)(pl > 0 ? pl : 1)) return;
+  const int b = (int)(pl > 0 ? x / pl : x);
+  const double nv = N[b], dv = D[b], an = fabs(nv), ad = fabs(dv);
+  if (pl == 0 || x % pl == 0) loss[b] = 0.5 - 0.5 * an / (nq * ad);
+  if (pl > 0) {
+    const double sn = nv > 0.0 ? 1.0 : (nv < 0.0 ? -1.0 : 0.0), sd = dv > 0.0 ? 1.0 : (dv < 0.0 ? -1.0 : 0.0);
+    const double wN = (-0.5 / nq) * sn / ad, wD = (0.5 / nq) * an * sd / (ad * ad);
+    gN[x] = wN * gN[x] + wD * gD[x];
+  }
+}
+extern "C" int qas_vqls_combine(const void *N, const void *D, void *gN, const void *gD, int B, int pl, int n_qubits,
+                                void *loss, void *stream) {
+  if (!N || !D || !loss || B <= 0 || pl < 0 || n_qubits < 1 || (pl > 0 && (!gN || !gD))) { g_create_error = "bad arguments to qas_vqls_combine"; return QAS_ERR_INVALID; }
+  const size_t total = (size_t)B * (size_t)(pl > 0 ? pl : 1);
+  vqls_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const double *)N, (const double *)D, (double *)gN, (const double *)gD, B, pl, (double)n_qubits, (double *)loss);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_create_error = std::string("vqls_combine_kernel: ") + cudaGetErrorString(e); return QAS_ERR_CUDA; }
+  return QAS_OK;
+}
+
 // ---------------------------------------------------------------------------------- shard reduction
 extern "C" int qas_reduce_rows(const void *rows, int nrows, uint64_t row_stride, uint64_t total, double scale, void *out,
                                void *stream) {

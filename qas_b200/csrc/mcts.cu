@@ -74,7 +74,12 @@ struct qas_mcts {
   int prune_counter = 0;
   std::mt19937_64 rng;
   std::unordered_map<std::vector<int32_t>, double, KeyHash> cache;
-  uint64_t reward_requests = 0, reward_evaluations = 0, expansions = 0;
+  uint64_t reward_requests = 0, reward_evaluations = 0, expansions = 0, reward_batches = 0;
+  // leaf-parallel rounds (opt-in, qas_mcts_set_leaf_parallel): selection rounds are issued `leaf_parallel` at a
+  // time under a virtual loss and rewarded by ONE batched evaluation
+  int leaf_parallel = 1;
+  bool vl_fixed = false;
+  double virtual_loss = 0.0, min_reward = 0.0;
   mutable std::string err;
 
   int fail(int code, const std::string &msg) const { err = msg; return code; }
@@ -281,6 +286,70 @@ struct qas_mcts {
     back_propagate(ni, penalised(r, k));
     return QAS_OK;
   }
+  // rewards of many arcs: the ones the cache does not hold go to the evaluator in ONE batch
+  int rewards_of(const std::vector<std::vector<int32_t>> &ks, std::vector<double> &out) {
+    const int p = cfg.max_depth;
+    std::vector<int32_t> need;
+    std::vector<const std::vector<int32_t> *> need_keys;
+    std::unordered_map<std::vector<int32_t>, int, KeyHash> pending;
+    for (const auto &k : ks) {
+      ++reward_requests;
+      if (cache.count(k) || pending.count(k)) continue;
+      pending.emplace(k, (int)need_keys.size());
+      need.insert(need.end(), k.begin(), k.end());
+      need_keys.push_back(&k);
+    }
+    if (!need_keys.empty()) {
+      std::vector<double> e(need_keys.size());
+      const int rc = energies(need.data(), (int)need_keys.size(), e.data());
+      if (rc != QAS_OK) return rc;
+      (void)p;
+      reward_evaluations += need_keys.size();
+      ++reward_batches;
+      for (size_t i = 0; i < need_keys.size(); ++i) cache.emplace(*need_keys[i], reward_sign * e[i]);
+    }
+    out.resize(ks.size());
+    for (size_t i = 0; i < ks.size(); ++i) out[i] = cache[ks[i]];
+    return QAS_OK;
+  }
+  // `rounds` rounds of executeRoundWithSuperCircParamsFromAnyNode from `from` (mcts.py:176-184, the loops at
+  // :187-188 and :198-199).  leaf_parallel > 1: in waves -- every selected leaf is booked at once with a virtual
+  // loss (one visit, reward = virtual_loss), so the following selections of the wave steer away from it; the
+  // wave's rewards come from one batched evaluation and replace the virtual losses.
+  int run_rounds(int from, int rounds) {
+    if (leaf_parallel <= 1) {
+      for (int r = 0; r < rounds; ++r) { const int rc = execute_round(from); if (rc != QAS_OK) return rc; }
+      return QAS_OK;
+    }
+    std::vector<int> leaves;
+    std::vector<std::vector<int32_t>> ks;
+    std::vector<double> rs;
+    for (int done = 0; done < rounds;) {
+      const int wave = std::min(leaf_parallel, rounds - done);
+      const double vl = vl_fixed ? virtual_loss : min_reward;
+      leaves.clear();
+      ks.clear();
+      for (int w = 0; w < wave; ++w) {
+        int ni = from;
+        while (!nodes[ni].terminal) {
+          ni = select_node(ni);
+          if (ni < 0) return fail(QAS_ERR_INVALID, "no legal child: the legality rules left a node without actions");
+        }
+        back_propagate(ni, vl);
+        leaves.push_back(ni);
+        ks.push_back(path_of(ni));
+      }
+      const int rc = rewards_of(ks, rs);
+      if (rc != QAS_OK) return rc;
+      for (int w = 0; w < wave; ++w) {
+        const double real = penalised(rs[w], ks[w]);
+        min_reward = std::min(min_reward, real);
+        for (int i = leaves[w]; i >= 0; i = nodes[i].parent) nodes[i].total += real - vl;
+      }
+      done += wave;
+    }
+    return QAS_OK;
+  }
 };
 
 // ------------------------------------------------------------------------------------- C ABI
@@ -343,6 +412,13 @@ extern "C" int qas_mcts_set_params(qas_mcts *m, const double *params, int p, int
 
 extern "C" int qas_mcts_reset(qas_mcts *m) { if (!m) return QAS_ERR_INVALID; m->reset(); return QAS_OK; }
 extern "C" int qas_mcts_set_alpha(qas_mcts *m, double alpha) { if (!m) return QAS_ERR_INVALID; m->cfg.alpha = alpha; return QAS_OK; }
+extern "C" int qas_mcts_set_leaf_parallel(qas_mcts *m, int leaves, int fixed_virtual_loss, double virtual_loss) {
+  if (!m || leaves < 1) return QAS_ERR_INVALID;
+  m->leaf_parallel = leaves;
+  m->vl_fixed = fixed_virtual_loss != 0;
+  m->virtual_loss = virtual_loss;
+  return QAS_OK;
+}
 extern "C" int qas_mcts_set_prune_ratio(qas_mcts *m, double ratio) { if (!m) return QAS_ERR_INVALID; m->cfg.prune_reward_ratio = ratio; return QAS_OK; }
 
 extern "C" int qas_mcts_warmup_batch(qas_mcts *m, int B, int32_t *out_ks, double *out_rewards) {
@@ -393,8 +469,8 @@ extern "C" int qas_mcts_warmup_batch(qas_mcts *m, int B, int32_t *out_ks, double
 
 extern "C" int qas_mcts_sample_arc(qas_mcts *m, int32_t *out_k, double *out_reward) {
   if (!m || !out_k) return QAS_ERR_INVALID;
-  for (int r = 0; r < m->cfg.sampling_execute_rounds; ++r) {     // sampleArcWithSuperCircParams (mcts.py:186-193)
-    const int rc = m->execute_round(m->root);
+  {                                                              // sampleArcWithSuperCircParams (mcts.py:186-193)
+    const int rc = m->run_rounds(m->root, m->cfg.sampling_execute_rounds);
     if (rc != QAS_OK) return rc;
   }
   int ni = m->root;
@@ -416,8 +492,8 @@ extern "C" int qas_mcts_exploit_arc(qas_mcts *m, int32_t *out_k, double *out_rew
   if (!m || !out_k) return QAS_ERR_INVALID;
   int ni = m->root;
   while (!m->nodes[ni].terminal) {                               // exploitArcWithSuperCircParams (mcts.py:195-201)
-    for (int r = 0; r < m->cfg.exploit_execute_rounds; ++r) {
-      const int rc = m->execute_round(ni);
+    {
+      const int rc = m->run_rounds(ni, m->cfg.exploit_execute_rounds);
       if (rc != QAS_OK) return rc;
     }
     ni = m->best_child(ni, 0.0, m->cfg.exploit_policy);
@@ -454,5 +530,6 @@ extern "C" int qas_mcts_get_stats(const qas_mcts *m, qas_mcts_stats *out) {
   out->expansions = m->expansions;
   out->prune_counter = m->prune_counter;
   out->root_visits = (int32_t)m->nodes[m->root].visits;
+  out->reward_batches = m->reward_batches;
   return QAS_OK;
 }

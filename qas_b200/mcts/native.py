@@ -34,7 +34,8 @@ class MctsConfig(ctypes.Structure):
 
 class MctsStats(ctypes.Structure):
     _fields_ = [("nodes", ctypes.c_uint64), ("reward_requests", ctypes.c_uint64), ("reward_evaluations", ctypes.c_uint64),
-                ("expansions", ctypes.c_uint64), ("prune_counter", ctypes.c_int32), ("root_visits", ctypes.c_int32)]
+                ("expansions", ctypes.c_uint64), ("prune_counter", ctypes.c_int32), ("root_visits", ctypes.c_int32),
+                ("reward_batches", ctypes.c_uint64)]
 
 
 ENERGY_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_int,
@@ -42,7 +43,7 @@ ENERGY_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctype
 MCTS_EXPORTS = ["qas_mcts_create", "qas_mcts_destroy", "qas_mcts_last_error", "qas_mcts_bind_evaluator",
                 "qas_mcts_set_params", "qas_mcts_reset", "qas_mcts_set_alpha", "qas_mcts_set_prune_ratio",
                 "qas_mcts_warmup_batch", "qas_mcts_sample_arc", "qas_mcts_exploit_arc", "qas_mcts_legal_actions",
-                "qas_mcts_get_stats"]
+                "qas_mcts_get_stats", "qas_mcts_set_leaf_parallel"]
 
 
 def _bind(lib):
@@ -65,6 +66,7 @@ def _bind(lib):
     lib.qas_mcts_exploit_arc.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.qas_mcts_legal_actions.argtypes = [vp, vp, ctypes.c_int, vp]
     lib.qas_mcts_get_stats.argtypes = [vp, ctypes.POINTER(MctsStats)]
+    lib.qas_mcts_set_leaf_parallel.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double]
     lib._mcts_bound = True
     return lib
 
@@ -148,6 +150,10 @@ class NativeMCTSController:
         if rc != 0:
             raise RuntimeError("qas_mcts_create failed (%d): %s" % (rc, self._lib.qas_mcts_last_error(None).decode()))
         self._h = h
+        self.leaf_parallel = max(1, int(leaf_parallel))
+        if self.leaf_parallel > 1:      # opt-in: waves of selections under a virtual loss, one batched reward call per wave
+            self._check(self._lib.qas_mcts_set_leaf_parallel(self._h, self.leaf_parallel, 0 if virtual_loss is None else 1,
+                                                             0.0 if virtual_loss is None else float(virtual_loss)))
         # GPU-backed model classes: rewards straight from their evaluator, parameters resident
         self._evaluator = None
         gpu = hasattr(model, "evaluator") if use_gpu is None else use_gpu

@@ -16,10 +16,12 @@ so one loss is two evaluations of the ansatz on n qubits instead of 160 on n + 1
 candidate circuits is two launches of the batched evaluator (uniform start state).  The gradient follows
 from the quotient rule on the two adjoint gradients.  reward = exp(-10 loss) (:1969-1972).
 """
+import ctypes
 from typing import List, Sequence, Union
 
 import numpy as np
 
+from qas_b200 import _lib
 from qas_b200.evaluator import BatchEvaluator
 from qas_b200.models import ModelFromK
 from qas_b200.qml_models.hamiltonian_model import default_device
@@ -104,8 +106,9 @@ class _VQLSModel(ModelFromK):
     @classmethod
     def evaluate_batch(cls, ks, super_circ_params, op_pool, want_grad=True, avg=True, compact=False):
         """Losses [B] and the batch-mean (or sum) dense gradient [p, c, l] (mcts.py:340-347).  Two
-        evaluator launches on device buffers; the quotient rule and the scatter into (p, c, l) run on the
-        GPU as well (torch), so only the losses and the dense gradient come back."""
+        evaluator launches on device buffers; the quotient rule (qas_vqls_combine) and the batch mean
+        (qas_batch_mean: the evaluator's deterministic two-stage reduction) are library kernels too, so only the
+        losses and the dense gradient come back."""
         import torch
         ks = np.ascontiguousarray(np.asarray(ks, dtype=np.int32))
         if ks.ndim == 1:
@@ -128,22 +131,24 @@ class _VQLSModel(ModelFromK):
             gD = torch.empty(B, p, l, dtype=torch.float64, device=dev) if want_grad else None
             ev_n.evaluate_device(d_k, d_p, N, gN, None, stream=stream)
             ev_d.evaluate_device(d_k, d_p, D, gD, None, stream=stream)
-            aN, aD = N.abs(), D.abs()
-            loss = 0.5 - 0.5 * aN / (cls.n_qubits * aD)
+            # loss and quotient rule in one library kernel (gN becomes dloss), batch mean by the library's
+            # deterministic two-stage reduction (nan_to_num -> mean | sum, mcts.py:345-347)
+            lib = ev_n._lib
+            sp = ctypes.c_void_p(stream.cuda_stream)
+            loss = torch.empty(B, dtype=torch.float64, device=dev)
+            rc = lib.qas_vqls_combine(N.data_ptr(), D.data_ptr(), gN.data_ptr() if want_grad else None,
+                                      gD.data_ptr() if want_grad else None, B, p * l if want_grad else 0, cls.n_qubits,
+                                      loss.data_ptr(), sp)
+            if rc != 0:
+                raise RuntimeError("qas_vqls_combine failed (%d)" % rc)
             out = {"energy": loss.cpu().numpy(), "grad_dense": None, "grad_compact": None}
             if want_grad:
-                wN = (-0.5 / cls.n_qubits) * torch.sign(N) / aD
-                wD = (0.5 / cls.n_qubits) * aN * torch.sign(D) / (aD * aD)
-                gl = wN[:, None, None] * gN + wD[:, None, None] * gD
-                g0 = torch.nan_to_num(gl)                                                     # mcts.py:346
-                idx = (torch.arange(p, device=dev, dtype=torch.int64)[None, :] * c + d_k.to(torch.int64)).reshape(-1)
-                dense = torch.zeros(p * c, l, dtype=torch.float64, device=dev)
-                dense.index_add_(0, idx, g0.reshape(B * p, l))
-                if avg:
-                    dense /= B
-                out["grad_dense"] = dense.reshape(p, c, l).cpu().numpy()
+                dense = torch.empty(p, c, l, dtype=torch.float64, device=dev)
+                ev_n._check(lib.qas_batch_mean(ev_n._h, B, p, d_k.data_ptr(), gN.data_ptr(), dense.data_ptr(),
+                                               0 if avg else _lib.QAS_F_GRAD_SUM, sp))
+                out["grad_dense"] = dense.cpu().numpy()
                 if compact:
-                    out["grad_compact"] = gl.cpu().numpy()
+                    out["grad_compact"] = gN.cpu().numpy()
         return out
 
     # ------------------------------------------------------------------ ModelFromK interface

@@ -347,3 +347,30 @@ def test_native_tree_is_refused_for_non_linear_rewards():
         def getReward(self, params):
             return float(np.exp(-self.getLoss(params)))
     assert not _native_possible(SearchConfig.from_call((), dict(model=Custom, **base)))
+
+
+def test_native_tree_leaf_parallel_rounds():
+    """qas_mcts_set_leaf_parallel: waves of selections under a virtual loss, one batched reward call per wave; the
+    tree ends with `rounds` visits at the root and no virtual loss left behind (every terminal's total = visits x
+    its penalised reward)."""
+    from qas_b200.mcts.native import NativeMCTSController
+    pool = helpers.near_cx_pool(2, [[0, 1], [1, 0]])
+    p = 3
+    params = np.random.default_rng(8).standard_normal((p, len(pool), 3))
+    seq = NativeMCTSController(OracleBatchModel, pool, p, state_class=QMLStateBasicGates, gate_limit_dict={"CNOT": 2},
+                               sampling_execute_rounds=40, seed=11, use_gpu=False, prune=False)
+    par = NativeMCTSController(OracleBatchModel, pool, p, state_class=QMLStateBasicGates, gate_limit_dict={"CNOT": 2},
+                               sampling_execute_rounds=40, seed=11, use_gpu=False, prune=False, leaf_parallel=8,
+                               virtual_loss=-2.0)
+    for ctl in (seq, par):
+        ctl.setRoot()
+        ctl.setParams(params)
+    k_seq = seq.sampleArcAndBackPropagate()[0]
+    k_par = par.sampleArcAndBackPropagate()[0]
+    s_seq, s_par = seq.stats(), par.stats()
+    assert s_seq["root_visits"] == s_par["root_visits"] == 41          # 40 rounds + the arc's own reward
+    assert s_par["reward_batches"] <= 5 and s_seq["reward_batches"] == 0
+    assert len(k_seq) == len(k_par) == p
+    # both trees hold real rewards only: the root's mean is a mean of genuine rewards of legal arcs
+    lo = min(-sim.energy(2, [0, 4, 2], pool.pool, params, TERMS), -1.5)
+    assert s_par["reward_requests"] >= 41 and lo < 10
