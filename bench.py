@@ -547,6 +547,121 @@ def secondary_workload(name, args, dev, local, flush, peak):
             "source": "search-scripts-legacy/" + WORKLOADS[name][7]}
 
 
+# ------------------------------------------------------------------------------- large-state mode
+LARGE_WORKLOADS = {"hea_24q": (24, 4), "hea_26q": (26, 4), "hea_28q": (28, 4), "hea_30q": (30, 4)}
+
+
+def run_largestate(args):
+    """--workload hea_NNq: BASELINE.json config 5 -- one statevector of NN qubits (hardware-efficient ansatz, L = 4
+    layers of Rot on every wire + nearest-neighbour CNOT ladder, observable sum Z_i Z_{i+1}), on one
+    GPU or sharded over --gpus N with NCCL qubit swaps.  One step = reset + all gate passes + expectation value.
+    HBM roofline of the gate passes: passes * 32 * 2^n_local bytes per GPU / device time of the pass kernels."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        ge.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        dist.barrier()
+    if rank != 0:
+        ge.build()
+    from qas_b200.largestate import LargeStateSimulator, hea_gate_list, zz_chain_terms
+    n, layers = LARGE_WORKLOADS[args.workload]
+    gl = hea_gate_list(n, layers, seed=args.seed)
+    terms = zz_chain_terms(n)
+    sim = LargeStateSimulator(n, device=local)
+    solo = dist.new_group([0]) if world > 1 else None          # collective: every rank takes part
+    steps = min(args.steps, 20)
+    sampler = ClockSampler(local)
+
+    def one():
+        sim.reset()
+        sim.run(gl)
+        return sim.expval(terms)
+
+    for _ in range(max(2, min(args.warmup, 3))):
+        energy = one()
+    torch.cuda.synchronize()
+    be = sim.backend
+    be.passes, be.tma_passes, be.kernel_ms, be.bytes, sim.swaps = 0, 0, 0.0, 0.0, 0
+    if world > 1:
+        be.swap_ms()
+        dist.barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        energy = one()
+    e1.record()
+    torch.cuda.synchronize()
+    total_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    swap_ms = be.swap_ms() if world > 1 else 0.0
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    total_s = float(total_ms.item()) * 1e-3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = be.bytes / (be.kernel_ms * 1e-3) / 1e9
+    # CPU baseline: the same algorithm through the NumPy slab backend (tests/sv_numpy_backend.py) on a 22-qubit,
+    # one-layer sample, scaled by 2^(n - 22) * L (the work is linear in both)
+    cpu_baseline = None
+    if not args.tune:
+        from sv_numpy_backend import NumpySvBackend
+        ns, ls = 22, 1
+        cs = LargeStateSimulator(ns, backend=NumpySvBackend(), group=solo)
+        t0 = time.perf_counter()
+        cs.run(hea_gate_list(ns, ls, seed=args.seed))
+        cs.expval(zz_chain_terms(ns))
+        dt = time.perf_counter() - t0
+        scaled = dt * (2.0 ** (n - ns)) * layers / ls
+        cpu_baseline = {"value": 1.0 / scaled, "unit": "evals/s", "cores": 1, "kind": "port",
+                        "sample": "%d-qubit, %d-layer HEA through the NumPy slab backend (%.1f s), scaled by 2^%d x %d" % (ns, ls, dt, n - ns, layers)}
+    line = {
+        "metric": "large-state HEA energy evaluations/sec", "value": steps / total_s, "unit": "evals/s", "n_gpus": world,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / steps, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "n_qubits": n, "layers": layers, "gates": len(gl), "n_local": sim.n_local,
+                   "observable": "sum_i Z_i Z_{i+1}", "state_bytes_per_gpu": 16 * 2 ** sim.n_local,
+                   "inputs_larger_than_l2": True,
+                   "parallelism": "one statevector sharded over %d GPU(s), NCCL all-to-all qubit swaps" % world},
+        "energy": energy,
+        "e2e": {"value": steps / total_s, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+                "note": "the public call takes a gate list and returns one double: end to end = the timed region"},
+        "gpu_launches": int(be.passes + 2 * steps),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "sv_block_kernel", "kernel_ms": be.kernel_ms / steps, "passes_per_step": be.passes / steps,
+                     "tma_passes_per_step": be.tma_passes / steps,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                     "note": "algorithmic bytes = passes * 32 * 2^n_local per GPU (one read + one write of the slab per pass)"},
+        "cpu_baseline": cpu_baseline,
+    }
+    if world > 1:
+        per_swap = 16.0 * 2 ** sim.n_local * (world - 1) / world
+        line["swaps_per_step"] = sim.swaps / steps
+        line["swap"] = {"ms_per_swap": swap_ms / max(1, sim.swaps), "gb_per_s_per_direction": per_swap * sim.swaps / (swap_ms * 1e-3) / 1e9 if swap_ms else None,
+                        "nvlink_gb_per_s_per_direction": 900.0, "bytes_sent_per_gpu_per_swap": per_swap}
+        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------- search epoch
 # per workload: (search batch, sampling rounds, exploit rounds, warm-up batch, lr, placeholder-penalty scale)
 # from the reference scripts (SURVEY.md 3.1): four_qubit_h2_only_near_cnot.py:88-97, search_LiH_near_cx.py:107-116,
@@ -716,7 +831,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None, help="default: 600 (b200 arm: >= 0.5 s of timed region), 10 (reference arm)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="lih_10q", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="lih_10q", choices=sorted(WORKLOADS) + sorted(LARGE_WORKLOADS))
     ap.add_argument("--batch", type=int, default=65536, help="circuits per GPU per step")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--tune", action="store_true", help="kernel tuning: skip the CPU-baseline leg")
@@ -727,7 +842,9 @@ def main():
     if args.steps is None:
         args.steps = 600 if (args.impl == "b200" and not args.search_epoch) else 10
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.search_epoch:
+    if args.workload in LARGE_WORKLOADS and args.impl == "b200":
+        run_largestate(args)
+    elif args.search_epoch:
         run_search_epoch(args)
     elif args.impl == "reference":
         run_reference(args)

@@ -180,11 +180,14 @@ int qas_plan_hsupport_host(int n_qubits, const uint32_t *ops, int num_ops, int i
  * basis_out (n_qubits words) = B_0 .. B_{d-1}; list_out[s'] = x' | s << 16 for every X mask
  * xmasks[s] inside D (x' = its coordinates); X masks outside D connect the support to amplitudes
  * that are exactly zero and drop out of the energy and of every derivative.
+ * variant 0 = the reference formulation (echelon tables in memory; also what qas_eval_batch runs on the host
+ * for batches of <= 16 circuits), 1 = the formulation the tape-compile kernel runs (packed ops, reduced
+ * echelon basis in registers; n_qubits <= 16): both must produce identical records.
  * No reference counterpart (PennyLane keeps the dense 2^n state for every circuit).             */
 int qas_compile_ctape_host(int n_qubits, const qas_pool_entry *pool, int c, int p, const int32_t *k,
                            int gmax, const uint32_t *xmasks, int num_xmasks, int max_d,
                            uint32_t *out_ops, int max_ops, int *num_ops, int *num_groups, int *dim,
-                           uint32_t *basis_out, uint32_t *list_out, int *num_list);
+                           uint32_t *basis_out, uint32_t *list_out, int *num_list, int variant);
 
 /* Counters since context creation: evaluations and kernel launches; device time of the
  * last call's kernels (ms, CUDA events on the launch stream; host-pointer calls only) and of
@@ -240,6 +243,9 @@ int qas_reduce_rows(const void *rows, int nrows, uint64_t row_stride, uint64_t t
  * evaluation kernel -- out4 = {prologue, forward sweep, H application + energy, adjoint sweep}.
  * Synchronises the device.  Used by tools/phase_clocks.py to see where a circuit's latency goes.   */
 int qas_debug_phase_clocks(qas_ctx *ctx, uint64_t *out4, int reset);
+/* ... and of the compressed kernel, per bin: out[bin * 8 + 0..3] = the four phase sums, out[bin * 8 + 4] = circuits
+ * evaluated; bin i holds the circuits whose support dimension is *dmin + i (the first bin also the smaller ones). */
+int qas_debug_phase_clocks_c(qas_ctx *ctx, uint64_t *out, int max_bins, int *dmin, int reset);
 
 /* Measured FP64 roofline denominator: runs a dependent-chain-free DFMA micro-benchmark on
  * `device` and returns the best of `reps` timings in TFLOP/s (2 flop per DFMA).            */

@@ -38,6 +38,7 @@ typedef struct {
   int tile_bits;              /* log2 amplitudes per shared-memory tile */
   double bytes_per_pass;      /* 32 * 2^n_local (read + write) */
   double last_ms;             /* device time of the whole call (CUDA events), host-sync calls only */
+  int tma_passes;             /* passes whose tiles moved by cp.async.bulk.tensor (TMA); the others used cp.async */
 } qas_sv_info;
 
 /* |state> <- amp * |index>  (index < 0: every amplitude = amp, i.e. the uniform state) */
@@ -46,7 +47,12 @@ int qas_sv_init(void *state, int n_local, int64_t index, double amp_re, double a
 /* Apply `ngates` gates (host array) in order.  The call blocks them into passes: each pass
  * stages tiles of 2^tile_bits amplitudes (tile_bits <= 13; 0 = default) in shared memory,
  * applies every gate of the block and writes the tile back -- one HBM read+write per pass.
- * Asynchronous on `stream` unless info != NULL and sync != 0.                               */
+ * Tiles move by TMA (cp.async.bulk.tensor, completion on an mbarrier) whenever the tile bits can
+ * be described by a 5-d tensor map of the slab, else by cp.async.  The work is enqueued on
+ * `stream`, and the call returns after it has completed (it synchronises the stream: the
+ * per-pass gate lists are staged through module-level constant memory, which also makes
+ * concurrent calls serialise on an internal mutex); with info != NULL and sync != 0 the device
+ * time of the call is measured with CUDA events and returned in info->last_ms.               */
 int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, int ngates, int tile_bits,
                  void *stream, int sync, qas_sv_info *info);
 

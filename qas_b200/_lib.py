@@ -60,7 +60,7 @@ class SvGate(ctypes.Structure):
 
 class SvInfo(ctypes.Structure):
     _fields_ = [("passes", ctypes.c_int), ("tile_bits", ctypes.c_int), ("bytes_per_pass", ctypes.c_double),
-                ("last_ms", ctypes.c_double)]
+                ("last_ms", ctypes.c_double), ("tma_passes", ctypes.c_int)]
 
 
 QAS_SV_U1 = 0
@@ -73,7 +73,7 @@ EXPORTS = [
     "qas_abi_version", "qas_build_info", "qas_ctx_create", "qas_ctx_destroy", "qas_last_error",
     "qas_eval_batch", "qas_compile_tape", "qas_compile_tape_host", "qas_plan_passes_host",
     "qas_plan_hsupport_host", "qas_compile_ctape_host",
-    "qas_get_stats", "qas_debug_phase_clocks", "qas_adam_step", "qas_set_params",
+    "qas_get_stats", "qas_debug_phase_clocks", "qas_debug_phase_clocks_c", "qas_adam_step", "qas_set_params",
     "qas_fp64_peak_tflops", "qas_reduce_rows", "qas_batch_mean", "qas_vqls_combine",
 ]
 # include/qas_b200_sv.h
@@ -122,7 +122,7 @@ def load():
     lib.qas_compile_ctape_host.restype = ctypes.c_int
     lib.qas_compile_ctape_host.argtypes = [ctypes.c_int, ctypes.POINTER(PoolEntry), ctypes.c_int, ctypes.c_int, vp,
                                            ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
-                                           pi, pi, pi, vp, vp, pi]
+                                           pi, pi, pi, vp, vp, pi, ctypes.c_int]
     lib.qas_set_params.restype = ctypes.c_int
     lib.qas_set_params.argtypes = [vp, ctypes.c_int, vp]
     lib.qas_adam_step.restype = ctypes.c_int
@@ -136,6 +136,8 @@ def load():
     lib.qas_vqls_combine.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
     lib.qas_debug_phase_clocks.restype = ctypes.c_int
     lib.qas_debug_phase_clocks.argtypes = [vp, vp, ctypes.c_int]
+    lib.qas_debug_phase_clocks_c.restype = ctypes.c_int
+    lib.qas_debug_phase_clocks_c.argtypes = [vp, vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
     lib.qas_get_stats.restype = ctypes.c_int
     lib.qas_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
     lib.qas_fp64_peak_tflops.restype = ctypes.c_int

@@ -268,7 +268,11 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   // support-compressed path: all-zero start states only (a basis start needs role flips the kernel does not implement)
   {
     const char *ce = getenv("QAS_B200_COMPRESS");
-    cx->compress = (!ce || atoi(ce) != 0) && init_kind == QAS_INIT_ZERO && n_qubits >= 7;
+    // below 9 qubits the classic team kernels already run one warp per circuit and most circuits span the whole
+    // register (H2O-8q: 76 %), so binning costs more than it saves; the packed tape format holds 16 qubits
+    int cmin = 9;
+    if (const char *me = getenv("QAS_B200_COMPRESS_MIN_N")) cmin = std::max(7, atoi(me));
+    cx->compress = (!ce || atoi(ce) != 0) && init_kind == QAS_INIT_ZERO && n_qubits >= cmin && n_qubits <= 16;
     if (const char *de = getenv("QAS_B200_COMPRESS_DMIN")) cx->c_dmin = std::max(1, std::min(QAS_CT_MAX_D, atoi(de)));
     cx->c_maxd = std::min(QAS_CT_MAX_D, n_qubits - 1);
     cx->c_dmin = std::min(cx->c_dmin, cx->c_maxd);
@@ -302,8 +306,8 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
     }
   }
   if (want_phase) {
-    guard(cudaMalloc(&cx->d_phase, 8 * sizeof(unsigned long long)), "cudaMalloc phase clocks");
-    guard(cudaMemset(cx->d_phase, 0, 8 * sizeof(unsigned long long)), "cudaMemset phase clocks");
+    guard(cudaMalloc(&cx->d_phase, 8 * (QAS_MAX_BINS + 1) * sizeof(unsigned long long)), "cudaMalloc phase clocks");
+    guard(cudaMemset(cx->d_phase, 0, 8 * (QAS_MAX_BINS + 1) * sizeof(unsigned long long)), "cudaMemset phase clocks");
   }
   guard(cudaMalloc(&cx->d_vtab, sizeof(double) * dim * cx->S), "cudaMalloc sign tables");
   guard(cudaMalloc(&cx->d_sdesc, 4 * std::max<size_t>(cdesc_swz.size(), 1)), "cudaMalloc cdesc");
@@ -384,9 +388,23 @@ extern "C" int qas_debug_phase_clocks(qas_ctx *ctx, uint64_t *out4, int reset) {
   if (!ctx->d_phase) return fail(ctx, QAS_ERR_UNSUPPORTED, "create the context with QAS_B200_PHASE_CLOCKS=1");
   CK(cudaSetDevice(ctx->device));
   CK(cudaDeviceSynchronize());
-  unsigned long long h[8];
+  unsigned long long h[8 * (QAS_MAX_BINS + 1)];
   CK(cudaMemcpy(h, ctx->d_phase, sizeof h, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; ++i) out4[i] = h[i];
+  if (reset) CK(cudaMemset(ctx->d_phase, 0, sizeof h));
+  return QAS_OK;
+}
+// per-bin clocks of the compressed kernel: out[bin][0..3] = phase sums, out[bin][4] = circuits; bins = slots c_dmin ..
+extern "C" int qas_debug_phase_clocks_c(qas_ctx *ctx, uint64_t *out, int max_bins, int *dmin, int reset) {
+  if (!ctx || !out || max_bins < 1) return QAS_ERR_INVALID;
+  if (!ctx->d_phase) return fail(ctx, QAS_ERR_UNSUPPORTED, "create the context with QAS_B200_PHASE_CLOCKS=1");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  unsigned long long h[8 * (QAS_MAX_BINS + 1)];
+  CK(cudaMemcpy(h, ctx->d_phase, sizeof h, cudaMemcpyDeviceToHost));
+  for (int b_ = 0; b_ < std::min(max_bins, QAS_MAX_BINS); ++b_)
+    for (int i = 0; i < 8; ++i) out[b_ * 8 + i] = h[8 * (1 + b_) + i];
+  if (dmin) *dmin = ctx->c_dmin;
   if (reset) CK(cudaMemset(ctx->d_phase, 0, sizeof h));
   return QAS_OK;
 }
@@ -502,7 +520,8 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   const int swz_plan = smem_path ? 1 : 0;
   // support-compressed path: every circuit is binned by the dimension d of its support span; d < n goes to the
   // compressed kernel of its bin, d == n stays with the classic kernel (the full bin)
-  const bool use_c = ctx->compress && !small && qas_ccompile_smem_bytes(ctx, ops_cap, p) <= 96 * 1024;
+  const bool use_c = ctx->compress && !small && qas_ccompile_smem_bytes(ctx, ops_cap, p) <= 96 * 1024 &&
+                     (size_t)QAS_NCONST + (size_t)p * c <= 65535;
   const bool fused_reduce = grad_dense && !grad_compact && !small;   // batch mean only: no per-circuit gradients
   if (want_grad && !fused_reduce && (!dev || !grad_compact)) {
     CK(ensure(&ctx->d_grad, &ctx->cap_grad, ng));
@@ -614,8 +633,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     C.bin_order = ctx->d_order; C.B = B; C.p = p; C.c = c; C.n = ctx->n; C.ops_cap = ops_cap; C.S = ctx->S_flat;
     C.gmax = ctx->GMAX; C.dmin = ctx->c_dmin; C.max_d = ctx->c_maxd; C.full_bin = ctx->c_nbins; C.rec_stride = rec_words;
     CK(qas_launch_compile_c(ctx, C, st));
-    CK(qas_launch_plan_full(ctx, ctx->d_tape, rec_words, P.count, P.order, B, ops_cap, swz_plan, st));
-    ctx->stats.launches += 2;
+    ctx->stats.launches += 1;
   } else {
     { const int rc_ = qas_launch_compile_classic(ctx, dk, B, p, ops_cap, swz_plan, rec_words, st); if (rc_ != QAS_OK) return rc_; }
     ctx->stats.launches += 1;
@@ -644,26 +662,41 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     const bool fork = !host_compile;
     if (fork) CK(cudaEventRecord(ctx->fork_ev, st));
     int nside = 0;
+    bool main_used = false;
     for (int bin = ctx->c_nbins; bin >= 0; --bin) {
       if (host_compile && h_count[bin] == 0) continue;
       const int max_work = host_compile ? h_count[bin] : B;
+      const bool full = bin == ctx->c_nbins;
+      // the call's own stream takes the first compressed bin (the largest registers); the full bin -- classic
+      // planning of its circuits, then the classic kernel -- and the smaller bins run on forked streams
       cudaStream_t s_ = st;
-      if (fork && bin != ctx->c_nbins) {
+      const bool on_side = fork && (full || main_used);
+      if (on_side) {
         s_ = ctx->side[nside];
         CK(cudaStreamWaitEvent(s_, ctx->fork_ev, 0));
+      } else if (!full) {
+        main_used = true;
       }
-      if (bin == ctx->c_nbins) {
-        if (host_compile) { const int keepB = P.B; P.B = max_work; const cudaError_t le = launch_classic(s_); P.B = keepB; CK(le); }
-        else CK(launch_classic(s_));
+      if (full) {
+        if (!host_compile) {
+          CK(qas_launch_plan_full(ctx, ctx->d_tape, rec_words, P.count, P.order, B, ops_cap, swz_plan, s_));
+          ctx->stats.launches += 1;
+        }
+        const int keepB = P.B;
+        if (host_compile) P.B = max_work;
+        const cudaError_t le = launch_classic(s_);
+        P.B = keepB;
+        CK(le);
       } else {
         Q.slot_bits = ctx->c_dmin + bin;
         Q.order = ctx->d_order + (size_t)bin * B;
         Q.count = ctx->d_bins + bin;
         Q.work_counter = ctx->d_bins + QAS_MAX_BINS + bin;
+        Q.phase_clk = ctx->d_phase ? ctx->d_phase + 8 * (1 + bin) : nullptr;      // per-bin diagnostic clocks
         CK(qas_launch_evalc(ctx, Q, max_work, want_grad, s_));
       }
       ctx->stats.launches += 1;
-      if (fork && bin != ctx->c_nbins) {
+      if (on_side) {
         CK(cudaEventRecord(ctx->join_ev[nside], s_));
         CK(cudaStreamWaitEvent(st, ctx->join_ev[nside], 0));
         ++nside;
@@ -790,24 +823,40 @@ extern "C" int qas_plan_hsupport_host(int n_qubits, const uint32_t *ops, int num
 extern "C" int qas_compile_ctape_host(int n_qubits, const qas_pool_entry *pool, int c, int p, const int32_t *k,
                                       int gmax, const uint32_t *xmasks, int num_xmasks, int max_d,
                                       uint32_t *out_ops, int max_ops, int *num_ops, int *num_groups, int *dim,
-                                      uint32_t *basis_out, uint32_t *list_out, int *num_list) {
+                                      uint32_t *basis_out, uint32_t *list_out, int *num_list, int variant) {
   if (n_qubits < 1 || n_qubits > QAS_MAX_QUBITS || !pool || c <= 0 || p <= 0 || !k || !out_ops || !num_ops || !num_groups ||
       !dim || !basis_out || gmax < 1 || gmax > 3 || num_xmasks < 0 || (num_xmasks > 0 && (!xmasks || !list_out)) || !num_list ||
-      max_d < 1 || max_d > QAS_CT_MAX_D)
+      max_d < 1 || max_d > QAS_CT_MAX_D || variant < 0 || variant > 1)
     return QAS_ERR_INVALID;
   std::string why;
   int me = 1;
   if (validate_pool(pool, c, n_qubits, 3, why, &me)) { g_create_error = why; return QAS_ERR_INVALID; }
   uint32_t col[32], row[32];
-  QasTapeSink sink{out_ops, max_ops, 0, 0};
-  const int st = qas_compile_circuit(k, p, pool, c, n_qubits, col, row, sink);
-  if (st == 1) { g_create_error = "structure list entry out of range"; return QAS_ERR_INVALID; }
-  if (st == 2) { g_create_error = "tape buffer too small"; return QAS_ERR_NOMEM; }
-  int nops = sink.n;
-  int ngroups = qas_mark_groups(out_ops, nops, gmax);
-  std::vector<uint32_t> ev(n_qubits), ec(n_qubits), mt((size_t)std::max(1, nops)), cinfo(qas_cinfo_words(n_qubits, num_xmasks));
-  const int d = qas_compress_tape(out_ops, &nops, &ngroups, n_qubits, xmasks, num_xmasks, ev.data(), ec.data(), mt.data(),
-                                  cinfo.data(), cinfo.data() + 1 + n_qubits, max_d);
+  int nops = 0, ngroups = 0, d = QAS_CT_FULL;
+  std::vector<uint32_t> cinfo(qas_cinfo_words(n_qubits, num_xmasks));
+  if (variant == 0) {        // reference formulation (also the host path of tiny batches)
+    QasTapeSink sink{out_ops, max_ops, 0, 0};
+    const int st = qas_compile_circuit(k, p, pool, c, n_qubits, col, row, sink);
+    if (st == 1) { g_create_error = "structure list entry out of range"; return QAS_ERR_INVALID; }
+    if (st == 2) { g_create_error = "tape buffer too small"; return QAS_ERR_NOMEM; }
+    nops = sink.n;
+    ngroups = qas_mark_groups(out_ops, nops, gmax);
+    std::vector<uint32_t> ev(n_qubits), ec(n_qubits), mt((size_t)std::max(1, nops));
+    d = qas_compress_tape(out_ops, &nops, &ngroups, n_qubits, xmasks, num_xmasks, ev.data(), ec.data(), mt.data(),
+                          cinfo.data(), cinfo.data() + 1 + n_qubits, max_d);
+  } else {                   // device formulation: packed ops, reduced echelon basis in registers
+    if (n_qubits > 16 || (size_t)QAS_NCONST + (size_t)p * c > 65535) { g_create_error = "packed c-tape compiler needs n <= 16 and p * c < 65524"; return QAS_ERR_UNSUPPORTED; }
+    std::vector<uint32_t> pk((size_t)std::max(1, max_ops) * QAS_PK_WORDS);
+    QasPackedDualSink sink{out_ops, pk.data(), max_ops, 0, 0};
+    const int st = qas_compile_circuit(k, p, pool, c, n_qubits, col, row, sink);
+    if (st == 1) { g_create_error = "structure list entry out of range"; return QAS_ERR_INVALID; }
+    if (st == 2) { g_create_error = "tape buffer too small"; return QAS_ERR_NOMEM; }
+    nops = sink.n;
+    ngroups = qas_mark_groups_packed(pk.data(), nops, gmax, out_ops);
+    if (n_qubits <= 10) d = qas_compress_packed<10>(pk.data(), out_ops, &nops, &ngroups, n_qubits, xmasks, num_xmasks, cinfo.data(), cinfo.data() + 1 + n_qubits, max_d);
+    else if (n_qubits <= 12) d = qas_compress_packed<12>(pk.data(), out_ops, &nops, &ngroups, n_qubits, xmasks, num_xmasks, cinfo.data(), cinfo.data() + 1 + n_qubits, max_d);
+    else d = qas_compress_packed<16>(pk.data(), out_ops, &nops, &ngroups, n_qubits, xmasks, num_xmasks, cinfo.data(), cinfo.data() + 1 + n_qubits, max_d);
+  }
   *num_ops = nops;
   *num_groups = ngroups;
   *dim = d;

@@ -32,16 +32,18 @@ struct CompileCParams {
   size_t rec_stride;
 };
 
-// per-thread shared-memory words of the c-tape compile kernel:
-// col[n] row[n] ev[n] ec[n] | ks[p|1] | ops[(cap*5)|1] | mt[cap] | cinfo head [1 + n]
+// per-thread shared-memory words of the c-tape compile kernel: col[n] row[n] | packed ops [cap * 3]  (odd stride)
 __host__ __device__ __forceinline__ size_t qas_ccompile_smem_words(int n, int ops_cap, int p) {
-  return ((size_t)(4 * n) + (size_t)(p | 1) + (size_t)((ops_cap * QAS_OP_WORDS) | 1) + (size_t)ops_cap + (size_t)(1 + n)) | 1;
+  (void)p;
+  return ((size_t)(2 * n) + (size_t)ops_cap * QAS_PK_WORDS) | 1;
 }
 
-// One thread per circuit: CNOT-folded tape (tape.h), group marks, c-tape translation, record write,
-// bin assignment.  Record: [nops, status, d (or 0x80000000 | 0 for a classic record), ngroups | ops |
-// cinfo = nsl, B_0..B_{n-1}, list[nsl]].
-template <int CTHREADS>
+// One thread per circuit: CNOT-folded tape (tape.h) -> record (5-word ops) + packed copy in shared memory, group
+// marks, c-tape translation with register-resident tables (qas_compress_packed), bin assignment.
+// Record: [nops, status, d (0x80000000 for a classic record), ngroups | ops | cinfo = nsl, B_0..B_{n-1}, list[nsl]].
+// The frame (col / row, indexed by wire at run time) and the packed ops are the only per-thread shared memory;
+// structure lists and pool entries come straight from global memory (L1-resident).
+template <int CTHREADS, int NQ>
 __global__ void __launch_bounds__(CTHREADS) compile_ctapes_kernel(const CompileCParams P) {
   extern __shared__ uint32_t csm[];
   const int b = blockIdx.x * CTHREADS + threadIdx.x;
@@ -49,65 +51,32 @@ __global__ void __launch_bounds__(CTHREADS) compile_ctapes_kernel(const CompileC
   const int n = P.n;
   const size_t stride = qas_ccompile_smem_words(n, P.ops_cap, P.p);
   uint32_t *mine = csm + (size_t)threadIdx.x * stride;
-  uint32_t *col = mine, *row = col + n, *ev = row + n, *ec = ev + n;
-  int32_t *ks = reinterpret_cast<int32_t *>(ec + n);
-  uint32_t *ops = reinterpret_cast<uint32_t *>(ks) + (P.p | 1);
-  uint32_t *mt = ops + ((P.ops_cap * QAS_OP_WORDS) | 1);
-  uint32_t *chead = mt + P.ops_cap;
-  {   // the CTA's structure lists are contiguous in global memory: coalesced copy, row t -> thread t
-    const size_t first = (size_t)blockIdx.x * CTHREADS * P.p;
-    const size_t count = (size_t)min(CTHREADS, P.B - (int)(blockIdx.x * CTHREADS)) * P.p;
-    for (size_t w = threadIdx.x; w < count; w += CTHREADS) {
-      const size_t t = w / P.p, i = w - t * P.p;
-      reinterpret_cast<int32_t *>(csm + t * stride + 4 * n)[i] = P.k[first + w];
-    }
-    __syncthreads();
-  }
-  uint32_t *rec = P.tape + (size_t)(live ? b : 0) * P.rec_stride;
-  int nops = 0, d = QAS_CT_FULL, bin = -1;
+  uint32_t *col = mine, *row = col + n, *pk = row + n;
+  int bin = -1;
   if (live) {
-    QasTapeSink sink{ops, P.ops_cap, 0, 0};
-    const int st = qas_compile_circuit(ks, P.p, P.pool, P.c, n, col, row, sink);
-    nops = st ? 0 : sink.n;
-    int ngroups = qas_mark_groups(ops, nops, P.gmax);
-    // cinfo: the head (nsl, basis) in shared memory, the slice list straight to the record
-    uint32_t *glist = rec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS;
-    d = qas_compress_tape(ops, &nops, &ngroups, n, P.sxflat, P.S, ev, ec, mt, chead, glist + 1 + n, P.max_d);
+    uint32_t *rec = P.tape + (size_t)b * P.rec_stride;
+    uint32_t *gops = rec + QAS_REC_HDR;
+    uint32_t *gci = gops + (size_t)P.ops_cap * QAS_OP_WORDS;
+    QasPackedDualSink sink{gops, pk, P.ops_cap, 0, 0};
+    const int st = qas_compile_circuit(P.k + (size_t)b * P.p, P.p, P.pool, P.c, n, col, row, sink);
+    int nops = st ? 0 : sink.n;
+    int ngroups = qas_mark_groups_packed(pk, nops, P.gmax, gops);
+    const int d = qas_compress_packed<NQ>(pk, gops, &nops, &ngroups, n, P.sxflat, P.S, gci, gci + 1 + n, P.max_d);
     rec[0] = (uint32_t)nops;
     rec[1] = (uint32_t)st;
     rec[2] = d >= 0 ? (uint32_t)d : 0x80000000u;
     rec[3] = (uint32_t)ngroups;
-    if (d >= 0) {
-      for (int q = 0; q <= n; ++q) glist[q] = chead[q];
-      bin = max(d, P.dmin) - P.dmin;
-    } else {
-      bin = P.full_bin;
-    }
+    bin = d >= 0 ? max(d, P.dmin) - P.dmin : P.full_bin;
   }
   // bin assignment, one atomic per (warp, bin)
-  {
-    const uint32_t act = __ballot_sync(0xffffffffu, live);
-    if (live) {
-      const uint32_t peers = __match_any_sync(act, bin);
-      const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
-      int base = 0;
-      if (lane == leader) base = atomicAdd(P.bin_count + bin, __popc(peers));
-      base = __shfl_sync(peers, base, leader);
-      P.bin_order[(size_t)bin * P.B + base + __popc(peers & ((1u << lane) - 1u))] = b;
-    }
-  }
-  // ops -> record, warp-cooperative and coalesced
-  __syncwarp();
-  {
-    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
-    for (int t = 0; t < 32; ++t) {
-      const int words = __shfl_sync(0xffffffffu, nops, t) * QAS_OP_WORDS;
-      const int bt = blockIdx.x * CTHREADS + wbase + t;
-      if (bt >= P.B) break;
-      const uint32_t *src = csm + (size_t)(wbase + t) * stride + 4 * n + (P.p | 1);
-      uint32_t *dst = P.tape + (size_t)bt * P.rec_stride + QAS_REC_HDR;
-      for (int w = lane; w < words; w += 32) dst[w] = src[w];
-    }
+  const uint32_t act = __ballot_sync(0xffffffffu, live);
+  if (live) {
+    const uint32_t peers = __match_any_sync(act, bin);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(P.bin_count + bin, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    P.bin_order[(size_t)bin * P.B + base + __popc(peers & ((1u << lane) - 1u))] = b;
   }
 }
 
@@ -121,6 +90,7 @@ struct EvalCParams {
   int *work_counter;           // this bin's queue head (zeroed before the launch)
   double *energy;              // [B]
   double *mout;                // [B][ops_cap][8]
+  unsigned long long *phase_clk;   // diagnostic: summed per-team clock64 deltas [prologue, forward, H, adjoint] at +4*.. or null
   size_t rec_stride;
   int n, ops_cap, S, S_real, slot_bits;
 };
@@ -295,6 +265,8 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
     const int qi = *bslot;
     if (qi >= count) break;
     const int b = P.order[qi];
+    long long clk_prev = 0;
+    if (P.phase_clk && tid == 0) clk_prev = clock64();
     // ---- 1. fetch the record, zero the support
     const uint32_t *grec = P.tape + (size_t)b * P.rec_stride;
     const uint32_t *gci = grec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS;
@@ -311,6 +283,7 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
     for (int w = tid; w < nops * 4; w += T) Us[w] = P.U[ops[(w >> 2) * QAS_OP_WORDS + 3]].u[w & 3];
     team_sync<T>(team, tmask);
 
+    if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 0, (unsigned long long)(c_ - clk_prev)); clk_prev = c_; }
     // ---- 2. forward sweep (tape is stored last-gate-first: walk the groups from the end)
     {
       int e = nops - 1;
@@ -332,27 +305,52 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
       }
     }
 
+    if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 1, (unsigned long long)(c_ - clk_prev)); clk_prev = c_; }
     // ---- 3. lambda = H psi on the support, E = Re <psi|lambda>
+    // A thread takes up to HA amplitudes at a time (t = t0 + T a) and walks the in-span slices ONCE for all of
+    // them: per slice HA independent sign-table loads (L2) and HA partner loads (shared memory) are in flight
+    // together -- the look-ups are latency-, not bandwidth-bound.
     double e_part = 0.0;
     {
+      constexpr int HA = 8;
       const uint32_t dim = 1u << d;
-      for (uint32_t t = tid; t < dim; t += T) {
-        uint32_t i = 0u;
-        for (int kk = 0; kk < d; ++kk) i ^= ((t >> kk) & 1u) ? chead[1 + kk] : 0u;
-        const double *vrow = P.vflat + i;
-        double2 acc = make_double2(0.0, 0.0);
-#pragma unroll 4
+      for (uint32_t t0 = tid; t0 < dim; t0 += T * HA) {
+        uint32_t ph[HA];
+        double2 acc[HA];
+#pragma unroll
+        for (int a = 0; a < HA; ++a) {
+          const uint32_t t = t0 + (uint32_t)(T * a);
+          uint32_t i = 0u;
+          for (int kk = 0; kk < d; ++kk) i ^= ((t >> kk) & 1u) ? chead[1 + kk] : 0u;
+          ph[a] = i;
+          acc[a] = make_double2(0.0, 0.0);
+        }
+#pragma unroll 2
         for (int s = 0; s < nsl; ++s) {
           const uint32_t ent = list[s];
-          const uint32_t si = ent >> 16;
-          const double2 a = psi[t ^ (ent & 0xffffu)];
-          const double v = __ldg(vrow + ((size_t)si << n));
-          if ((int)si < P.S_real) { acc.x = fma(v, a.x, acc.x); acc.y = fma(v, a.y, acc.y); }
-          else { acc.x = fma(-v, a.y, acc.x); acc.y = fma(v, a.x, acc.y); }
+          const uint32_t xp = ent & 0xffffu;
+          const double *vrow = P.vflat + ((size_t)(ent >> 16) << n);
+          const bool imag = (int)(ent >> 16) >= P.S_real;
+#pragma unroll
+          for (int a = 0; a < HA; ++a) {
+            const uint32_t t = t0 + (uint32_t)(T * a);
+            if (t < dim) {
+              const double v = __ldg(vrow + ph[a]);
+              const double2 pa = psi[t ^ xp];
+              if (!imag) { acc[a].x = fma(v, pa.x, acc[a].x); acc[a].y = fma(v, pa.y, acc[a].y); }
+              else { acc[a].x = fma(-v, pa.y, acc[a].x); acc[a].y = fma(v, pa.x, acc[a].y); }
+            }
+          }
         }
-        const double2 ai = psi[t];
-        e_part = fma(ai.x, acc.x, fma(ai.y, acc.y, e_part));
-        if constexpr (GRAD) lam[t] = acc;
+#pragma unroll
+        for (int a = 0; a < HA; ++a) {
+          const uint32_t t = t0 + (uint32_t)(T * a);
+          if (t < dim) {
+            const double2 ai = psi[t];
+            e_part = fma(ai.x, acc[a].x, fma(ai.y, acc[a].y, e_part));
+            if constexpr (GRAD) lam[t] = acc[a];
+          }
+        }
       }
     }
 #pragma unroll
@@ -371,6 +369,7 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
     }
     if (tid == 0) P.energy[b] = status ? __longlong_as_double(0x7ff8000000000000ll) : e_part;
 
+    if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 2, (unsigned long long)(c_ - clk_prev)); clk_prev = c_; }
     // ---- 4. adjoint sweep (tape order = reverse time order)
     if constexpr (GRAD) {
       int j = 0;
@@ -421,6 +420,7 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
         j += g;
       }
     }
+    if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 3, (unsigned long long)(c_ - clk_prev)); atomicAdd(P.phase_clk + 4, 1ull); }
     team_sync<T>(team, tmask);   // state buffers are reused by the next circuit of this team
   }
 }
@@ -444,32 +444,52 @@ static __global__ void grad_finalize_reduce_kernel(const uint32_t *tape, size_t 
   __syncthreads();
   double *acc = acc_all + (size_t)wid * words;
   const int b_lo = blockIdx.x * chunk, b_hi = min(B, b_lo + chunk);
-  // warp w takes circuits b_lo + w, b_lo + w + nw, ... in order; lanes take the circuit's ops (distinct depths)
-  for (int b = b_lo + wid; b < b_hi; b += nw) {
-    const uint32_t *rec = tape + (size_t)b * rec_stride;
-    const int nops = rec[1] ? 0 : (int)rec[0];
-    for (int oi = lane; oi < nops; oi += 32) {
-      const uint32_t *o = rec + QAS_REC_HDR + (size_t)oi * QAS_OP_WORDS;
-      const uint32_t mt = o[4];
-      const int npar = min(qas_meta_npar(mt), l);
-      const int depth = qas_meta_depth(mt);
-      if (!npar || depth < depth0 || depth >= depth0 + nd) continue;
-      const double2 *mp = reinterpret_cast<const double2 *>(mout + ((size_t)b * ops_cap + oi) * 8);
-      double2 m[4];
+  // Warp w takes the chunk's circuits b_lo + 4 (w + nw i) + s, s = 0..3: four circuits at a time, eight lanes each
+  // (lane = 8 s + op slot), so that four circuits' record / cross-matrix / dU loads are in flight together; the
+  // contributions are then added one circuit after the other, in circuit order -- the summation order of every
+  // accumulator depends only on (B, chunk), never on scheduling.  Ops of one circuit sit at distinct depths.
+  const int sub = lane >> 3, slot = lane & 7;
+  for (int b0 = b_lo + 4 * wid; b0 < b_hi; b0 += 4 * nw) {
+    const int b = b0 + sub;
+    const bool live = b < b_hi;
+    const uint32_t *rec = tape + (size_t)(live ? b : b_lo) * rec_stride;
+    const int nops = (live && !rec[1]) ? (int)rec[0] : 0;
+    int nmax = nops;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) m[q] = mp[q];
-      const uint32_t tab = o[3];
-      const int key = (int)((tab - QAS_NCONST) % (uint32_t)c);
-      double *a = acc + ((size_t)(depth - depth0) * c + key) * l;
-      for (int jj = 0; jj < npar; ++jj) {
-        const double2 *dd = dU[tab].d[jj];
-        double part = 0.0;
+    for (int off = 8; off < 32; off <<= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, off));
+    for (int o0 = 0; o0 < nmax; o0 += 8) {
+      const int oi = o0 + slot;
+      double g[3] = {0.0, 0.0, 0.0};
+      int npar = 0;
+      double *a = acc;
+      if (oi < nops) {
+        const uint32_t *o = rec + QAS_REC_HDR + (size_t)oi * QAS_OP_WORDS;
+        const uint32_t mt = o[4], tab = o[3];
+        const int depth = qas_meta_depth(mt);
+        npar = min(qas_meta_npar(mt), l);
+        if (depth < depth0 || depth >= depth0 + nd) npar = 0;
+        if (npar) {
+          const double2 *mp = reinterpret_cast<const double2 *>(mout + ((size_t)b * ops_cap + oi) * 8);
+          double2 m[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) part += dd[q].x * m[q].x - dd[q].y * m[q].y;
-        a[jj] += nan_to_num_d(2.0 * part);
+          for (int q = 0; q < 4; ++q) m[q] = mp[q];
+          a = acc + ((size_t)(depth - depth0) * c + (int)((tab - QAS_NCONST) % (uint32_t)c)) * l;
+          for (int jj = 0; jj < npar; ++jj) {
+            const double2 *dd = dU[tab].d[jj];
+            double part = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) part += dd[q].x * m[q].x - dd[q].y * m[q].y;
+            g[jj] = nan_to_num_d(2.0 * part);
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (sub == s)
+          for (int jj = 0; jj < npar; ++jj) a[jj] += g[jj];
+        __syncwarp();
       }
     }
-    __syncwarp();
   }
   __syncthreads();
   // fixed-order sum of the warps' copies

@@ -62,15 +62,20 @@ __global__ void compile_tapes_kernel(const int32_t *k, const qas_pool_entry *poo
 }
 
 // Classic planning of the circuits the binning left in the full bin (d == n): support descriptors and
-// final-support descriptor of the already grouped tape, in place in the record (kernels.cuh layout).
+// final-support descriptor of the already grouped tape, written to the record (kernels.cuh layout).  The planner
+// re-reads the ops many times: they are staged in shared memory (from global memory every read is an L2 round trip).
+// dynamic shared memory: [blockDim.x][(ops_cap * 5) | 1] words
 __global__ void plan_full_kernel(uint32_t *tape, size_t rec_stride, const int *bin_count, const int *order,
                                  int n, int ops_cap, int init_kind, int swizzled, QasHInfo hinfo) {
+  extern __shared__ uint32_t psm[];
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= *bin_count) return;
   uint32_t *rec = tape + (size_t)order[q] * rec_stride;
   const int nops = (int)rec[0];
+  uint32_t *ops = psm + (size_t)threadIdx.x * ((ops_cap * QAS_OP_WORDS) | 1);
+  for (int w = 0; w < nops * QAS_OP_WORDS; ++w) ops[w] = rec[QAS_REC_HDR + w];
   rec[2] = 0u;                                    // init_index of the all-zero start
-  qas_plan_marked(rec + QAS_REC_HDR, nops, (int)rec[3], n, init_kind, 0u,
+  qas_plan_marked(ops, nops, (int)rec[3], n, init_kind, 0u,
                   rec + QAS_REC_HDR + (size_t)ops_cap * QAS_OP_WORDS, swizzled, &hinfo, rec + qas_rec_hd_offset(ops_cap, n));
+  for (int w = 0; w < nops * QAS_OP_WORDS; ++w) rec[QAS_REC_HDR + w] = ops[w];
 }
-

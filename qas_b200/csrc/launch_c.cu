@@ -3,16 +3,22 @@
 #include "ctx.h"
 
 size_t qas_ccompile_smem_bytes(const qas_ctx *ctx, int ops_cap, int p) {
-  return qas_ccompile_smem_words(ctx->n, ops_cap, p) * 4 * 32;
+  return qas_ccompile_smem_words(ctx->n, ops_cap, p) * 4 * 64;
 }
 
-cudaError_t qas_launch_compile_c(qas_ctx *ctx, const CompileCParams &P, cudaStream_t st) {
-  constexpr int CT = 32;
-  const size_t smem = qas_ccompile_smem_bytes(ctx, P.ops_cap, P.p);
-  cudaError_t e = cudaFuncSetAttribute(compile_ctapes_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int NQ>
+static cudaError_t launch_compile_c_t(qas_ctx *ctx, const CompileCParams &P, cudaStream_t st) {
+  constexpr int CT = 64;
+  const size_t smem = qas_ccompile_smem_words(ctx->n, P.ops_cap, P.p) * 4 * CT;
+  cudaError_t e = cudaFuncSetAttribute(compile_ctapes_kernel<CT, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  compile_ctapes_kernel<CT><<<(P.B + CT - 1) / CT, CT, smem, st>>>(P);
+  compile_ctapes_kernel<CT, NQ><<<(P.B + CT - 1) / CT, CT, smem, st>>>(P);
   return cudaGetLastError();
+}
+cudaError_t qas_launch_compile_c(qas_ctx *ctx, const CompileCParams &P, cudaStream_t st) {
+  if (ctx->n <= 10) return launch_compile_c_t<10>(ctx, P, st);
+  if (ctx->n <= 12) return launch_compile_c_t<12>(ctx, P, st);
+  return launch_compile_c_t<16>(ctx, P, st);
 }
 
 template <int T, bool GRAD, int BLK, int MINB>

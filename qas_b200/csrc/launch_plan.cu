@@ -27,7 +27,10 @@ int qas_launch_compile_classic(qas_ctx *ctx, const int32_t *dk, int B, int p, in
 
 cudaError_t qas_launch_plan_full(qas_ctx *ctx, uint32_t *tape, size_t rec_stride, const int *count, const int *order, int B,
                                  int ops_cap, int swizzled, cudaStream_t st) {
-  plan_full_kernel<<<(B + 63) / 64, 64, 0, st>>>(tape, rec_stride, count, order, ctx->n, ops_cap, ctx->init_kind, swizzled, ctx->hinfo);
+  const int thr = 32;
+  const size_t smem = (size_t)thr * ((ops_cap * QAS_OP_WORDS) | 1) * 4;
+  cudaError_t e = cudaFuncSetAttribute(plan_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  plan_full_kernel<<<(B + thr - 1) / thr, thr, smem, st>>>(tape, rec_stride, count, order, ctx->n, ops_cap, ctx->init_kind, swizzled, ctx->hinfo);
   return cudaGetLastError();
 }
-

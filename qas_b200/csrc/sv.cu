@@ -11,6 +11,9 @@
 #include <string>
 #include <vector>
 
+#include <mutex>
+
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../include/qas_b200_sv.h"
 
@@ -62,7 +65,9 @@ struct __align__(16) SvTileGate {
 struct SvGroup {
   int first, ngates;
   uint32_t m[3];       // xor masks (tile positions) of the three logical bits held in registers
-  uint32_t w[3];       // sv_swz(m[q])
+  uint32_t w[3];       // swizzle(m[q])
+  int simple;          // != 0: the group is at most one uncontrolled 2x2 per register slot (products formed on the
+                       // host; bit q set = slot q has one, stored in slot order from `first`): straight-line fast path
 };
 
 // The gate list and the groups of the pass being executed live in constant memory: every thread of
@@ -76,13 +81,15 @@ __constant__ SvGroup c_sv_groups[SV_CONST_GROUPS];
 
 struct SvBlockParams {
   double2 *state;
-  const SvTileGate *gates;
-  const SvGroup *groups;
   const unsigned short *ctab;  // [ngroups][2^(kb-3)] swizzled tile index of every coset representative
   int n_local, kb, c, ngates, ngroups;
   unsigned char bits[16];      // ascending slab positions of the tile bits; bits[0..c-1] = 0..c-1
   unsigned short ainv[16];     // columns of A^-1 at the end of the pass (tile position of logical bit q)
   int framed;                  // 0: the frame is the identity at the end of the pass
+  // TMA path: the tile is the box (run 0 = slab bits [0, a0)) x (run 1 = slab bits [s1, s1 + l1)) of a 5-d tensor
+  // map over the slab, repeated for every combination of the nh remaining (higher) tile bits hib[]
+  int a0, s1, l1, nh;
+  unsigned char hib[16];
 };
 
 __device__ __forceinline__ double2 sv_cmul(double2 a, double2 b) {
@@ -105,6 +112,14 @@ __device__ __forceinline__ uint32_t sv_swz(uint32_t j) {
   f ^= f >> 6;
   return j ^ (f & 7u);
 }
+// TMA path: the layout cp.async.bulk.tensor writes with CU_TENSOR_MAP_SWIZZLE_128B -- the 16-byte chunk index inside
+// a 128-byte row is xor-ed with the row index mod 8 (xor-linear and an involution, like sv_swz)
+__device__ __forceinline__ uint32_t sv_swz_tma(uint32_t j) { return j ^ ((j >> 3) & 7u); }
+template <bool TMA>
+__device__ __forceinline__ uint32_t sv_sw(uint32_t j) {
+  if constexpr (TMA) return sv_swz_tma(j);
+  return sv_swz(j);
+}
 __device__ __forceinline__ uint32_t sv_swapbits(uint32_t t, int a, int b) {
   const uint32_t x = ((t >> a) ^ (t >> b)) & 1u;
   return t ^ ((x << a) | (x << b));
@@ -116,6 +131,18 @@ __device__ __forceinline__ void sv_apply_slot(double2 (&a)[8], const double2 (&u
   for (int c = 0; c < 8; ++c) {
     if ((c >> Q) & 1) continue;
     if ((c & cm) != cm) continue;
+    const int c1 = c | (1 << Q);
+    const double2 a0 = a[c], a1 = a[c1];
+    a[c] = sv_cfma(u[1], a1, sv_cmul(u[0], a0));
+    a[c1] = sv_cfma(u[3], a1, sv_cmul(u[2], a0));
+  }
+}
+// uncontrolled 2x2 on register slot bit Q (fast path of simple groups)
+template <int Q>
+__device__ __forceinline__ void sv_apply_slot_nc(double2 (&a)[8], const double2 (&u)[4]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if ((c >> Q) & 1) continue;
     const int c1 = c | (1 << Q);
     const double2 a0 = a[c], a1 = a[c1];
     a[c] = sv_cfma(u[1], a1, sv_cmul(u[0], a0));
@@ -136,14 +163,51 @@ __device__ __forceinline__ void sv_swap_slot(double2 (&a)[8], uint32_t cm) {
   }
 }
 
-// One CTA per tile.  Tile element j (kb bits) lives at slab index base | spread(j): the low c
+// ---- TMA / mbarrier primitives (PTX as issued by CUTLASS' SM90_TMA_LOAD_5D / SM90_TMA_STORE_5D / ClusterBarrier) ----
+__device__ __forceinline__ uint32_t sv_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sv_mbar_init(unsigned long long *mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(sv_smem_u32(mbar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void sv_mbar_expect_tx(unsigned long long *mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(sv_smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void sv_mbar_wait(unsigned long long *mbar, uint32_t phase) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "SV_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra SV_DONE;\n\t"
+      "bra SV_WAIT;\n\t"
+      "SV_DONE:\n\t"
+      "}" ::"r"(sv_smem_u32(mbar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void sv_tma_load_5d(const void *tmap, unsigned long long *mbar, void *dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(sv_smem_u32(dst)), "l"((unsigned long long)tmap), "r"(sv_smem_u32(mbar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void sv_tma_store_5d(const void *tmap, const void *src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"((unsigned long long)tmap), "r"(sv_smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void sv_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Persistent CTAs, one tile at a time.  Tile element j (kb bits) lives at slab index base | spread(j): the low c
 // bits are contiguous (coalesced 16*2^c-byte runs), the others are scattered by offs[].
-// dynamic shared memory: tile [2^kb] double2
-template <int MINB>
-__global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBlockParams P) {
-  extern __shared__ __align__(16) double2 tile[];
-  __shared__ unsigned long long offs[1 << (SV_MAX_TILE_BITS - 5)];
+// TMA = true: the tile is fetched by cp.async.bulk.tensor from a 5-d tensor map of the slab (one box per
+// combination of the tile bits beyond its first two runs of consecutive positions), completion on an mbarrier,
+// shared-memory layout = the TMA 128-byte swizzle; a pass that ends with the identity frame is written back with
+// cp.async.bulk.tensor as well, a framed pass by the threads (the frame is undone by the store addresses).
+// TMA = false: cp.async staging with the fold-all swizzle (tiles the tensor map cannot describe, test sizes).
+// dynamic shared memory: tile [2^kb] double2 (1024-byte aligned for the TMA swizzle)
+template <int MINB, bool TMA>
+__global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBlockParams P, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) double2 tile[];
+  __shared__ unsigned long long offs[1 << 8];
   __shared__ unsigned long long s_base;
+  __shared__ __align__(8) unsigned long long s_mbar;
   const int kb = P.kb, c = P.c;
   const uint32_t tsize = 1u << kb, nhi = 1u << (kb - c), lowmask = (1u << c) - 1u;
   for (uint32_t h = threadIdx.x; h < nhi; h += SV_THREADS) {
@@ -151,6 +215,10 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
     for (int q = c; q < kb; ++q) o |= (unsigned long long)((h >> (q - c)) & 1u) << P.bits[q];
     offs[h] = o;
   }
+  if constexpr (TMA) {
+    if (threadIdx.x == 0) sv_mbar_init(&s_mbar, 1);
+  }
+  uint32_t phase = 0;
   const unsigned long long ntiles = 1ull << (P.n_local - kb);
   for (unsigned long long tid_ = blockIdx.x; tid_ < ntiles; tid_ += gridDim.x) {
     if (threadIdx.x == 0) {
@@ -166,9 +234,25 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
     __syncthreads();
     const unsigned long long base = s_base;
     double2 *g = P.state + base;
-    // HBM -> shared memory with cp.async: every thread has all of its 16-byte copies in flight at
-    // once (the register-staged loop kept 4, which left the kernel latency-bound at ~1.5 TB/s)
-    {
+    const int ncombo = 1 << P.nh;
+    const uint32_t box_amps = 1u << (P.a0 + P.l1);
+    if constexpr (TMA) {
+      // one warp issues the tile's boxes; every thread then waits on the mbarrier's phase
+      if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) sv_mbar_expect_tx(&s_mbar, 16u << kb);
+        __syncwarp();
+        for (int ci = threadIdx.x; ci < ncombo; ci += 32) {
+          unsigned long long hi = base;
+          for (int q = 0; q < P.nh; ++q) hi |= (unsigned long long)((ci >> q) & 1) << P.hib[q];
+          const int c2 = (int)((hi >> P.a0) & ((1ull << (P.s1 - P.a0)) - 1ull));
+          const int c4 = (int)(hi >> (P.s1 + P.l1));
+          sv_tma_load_5d(&tmap, &s_mbar, tile + (size_t)ci * box_amps, 0, 0, c2, 0, c4);
+        }
+      }
+      sv_mbar_wait(&s_mbar, phase);
+      phase ^= 1u;
+    } else {
+      // HBM -> shared memory with cp.async: every thread has all of its 16-byte copies in flight at once
       const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
       const uint32_t sw0 = sv_swz(threadIdx.x) * 16u;
 #pragma unroll 4
@@ -180,24 +264,49 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
     }
-    __syncthreads();
     for (int gr = 0; gr < P.ngroups; ++gr) {
       const SvGroup &grp = c_sv_groups[gr];
       const uint32_t s1 = grp.m[0], s2 = grp.m[1], s4 = grp.m[2];
       const uint32_t w1 = grp.w[0], w2 = grp.w[1], w4 = grp.w[2];           // the swizzle is xor-linear
+      const int simple = grp.simple;
       const unsigned short *ctab = P.ctab + ((size_t)gr << (kb - 3));
       for (uint32_t t = threadIdx.x; t < (tsize >> 3); t += SV_THREADS) {
         // coset representative from the host-built table (the index arithmetic -- bit swaps, zero
         // insertion, swizzle -- was a third of the kernel's instructions)
         const uint32_t Ps = __ldg(ctab + t);
-        const uint32_t Pj = sv_swz(Ps);       // the swizzle is an involution
         uint32_t sm[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) sm[q] = Ps ^ ((q & 1) ? w1 : 0u) ^ ((q & 2) ? w2 : 0u) ^ ((q & 4) ? w4 : 0u);
         double2 a[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) a[q] = tile[sm[q]];
+        if (simple) {
+          // at most one uncontrolled 2x2 per register slot, in slot order: no descriptor decoding
+          const SvTileGate *gt = c_sv_gates + grp.first;
+          if (simple & 1) {
+            double2 u[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) u[e] = gt->u[e];
+            sv_apply_slot_nc<0>(a, u);
+            ++gt;
+          }
+          if (simple & 2) {
+            double2 u[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) u[e] = gt->u[e];
+            sv_apply_slot_nc<1>(a, u);
+            ++gt;
+          }
+          if (simple & 4) {
+            double2 u[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) u[e] = gt->u[e];
+            sv_apply_slot_nc<2>(a, u);
+          }
+        } else {
+        const uint32_t Pj = sv_sw<TMA>(Ps);   // the swizzle is an involution
         for (int gi = grp.first; gi < grp.first + grp.ngates; ++gi) {
           const SvTileGate *gt = c_sv_gates + gi;
           const int kind = gt->kind;
@@ -233,24 +342,42 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
             }
           }
         }
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) tile[sm[q]] = a[q];
       }
       __syncthreads();
     }
     if (!P.framed) {
-      const uint32_t sw0 = sv_swz(threadIdx.x);
+      if constexpr (TMA) {
+        // shared memory (generic-proxy writes) -> async proxy, then one warp stores the boxes back
+        sv_fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x < 32) {
+          for (int ci = threadIdx.x; ci < ncombo; ci += 32) {
+            unsigned long long hi = base;
+            for (int q = 0; q < P.nh; ++q) hi |= (unsigned long long)((ci >> q) & 1) << P.hib[q];
+            const int c2 = (int)((hi >> P.a0) & ((1ull << (P.s1 - P.a0)) - 1ull));
+            const int c4 = (int)(hi >> (P.s1 + P.l1));
+            sv_tma_store_5d(&tmap, tile + (size_t)ci * box_amps, 0, 0, c2, 0, c4);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the tile may be overwritten again
+        }
+      } else {
+        const uint32_t sw0 = sv_swz(threadIdx.x);
 #pragma unroll 4
-      for (uint32_t k = 0; k < tsize; k += SV_THREADS) {
-        const uint32_t j = threadIdx.x | k;
-        if (j >= tsize) break;
-        g[(j & lowmask) | offs[j >> c]] = tile[sw0 ^ sv_swz(k)];
+        for (uint32_t k = 0; k < tsize; k += SV_THREADS) {
+          const uint32_t j = threadIdx.x | k;
+          if (j >= tsize) break;
+          g[(j & lowmask) | offs[j >> c]] = tile[sw0 ^ sv_swz(k)];
+        }
       }
     } else {     // undo the frame: logical index j sits at tile position A^-1 j
       uint32_t pt = 0;
 #pragma unroll
       for (int q = 0; q < 8; ++q) pt ^= ((threadIdx.x >> q) & 1u) ? (uint32_t)P.ainv[q] : 0u;
-      const uint32_t sw0 = sv_swz(pt);
+      const uint32_t sw0 = sv_sw<TMA>(pt);
 #pragma unroll 2
       for (uint32_t k = 0; k < tsize; k += SV_THREADS) {
         const uint32_t j = threadIdx.x | k;
@@ -258,10 +385,14 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
         uint32_t pk = 0;
 #pragma unroll
         for (int q = 8; q < SV_MAX_TILE_BITS; ++q) pk ^= ((k >> q) & 1u) ? (uint32_t)P.ainv[q] : 0u;
-        g[(j & lowmask) | offs[j >> c]] = tile[sw0 ^ sv_swz(pk)];
+        g[(j & lowmask) | offs[j >> c]] = tile[sw0 ^ sv_sw<TMA>(pk)];
       }
+      if constexpr (TMA) sv_fence_async_smem();     // these reads precede the next tile's async-proxy writes
     }
     __syncthreads();
+  }
+  if constexpr (TMA) {
+    if (threadIdx.x < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA exits
   }
 }
 
@@ -411,8 +542,70 @@ extern "C" int qas_sv_plan(int n_local, const qas_sv_gate *gates, int ngates, in
   return QAS_OK;
 }
 
+namespace {
+// The gate list and the groups of the pass being executed live in __constant__ symbols of this module: calls
+// from different threads / streams would overwrite each other's lists.  qas_sv_apply serialises itself.
+std::mutex g_sv_apply_mutex;
+
+typedef CUresult (*SvEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+SvEncodeTiledFn sv_encode_fn() {
+  static SvEncodeTiledFn fn = []() -> SvEncodeTiledFn {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (SvEncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// Tile geometry for the TMA path: run 0 = slab bits [0, a0), run 1 = [s1, s1 + l1), the other tile bits hib[].
+struct SvTmaGeom { int a0, s1, l1, nh; unsigned char hib[16]; };
+bool sv_tma_geometry(const std::vector<int> &bits, int kb, int n_local, SvTmaGeom *gm) {
+  if (kb < 7 || n_local < kb) return false;
+  int a0 = 0;
+  while (a0 < kb && a0 < 11 && bits[a0] == a0) ++a0;
+  if (a0 < 3) return false;                        // a 128-byte row = tile bits 0..2
+  int s1 = a0, l1 = 0;
+  if (a0 < kb) {
+    s1 = bits[a0];
+    while (a0 + l1 < kb && l1 < 8 && bits[a0 + l1] == s1 + l1) ++l1;
+  }
+  gm->a0 = a0; gm->s1 = s1; gm->l1 = l1; gm->nh = kb - a0 - l1;
+  for (int q = 0; q < 16; ++q) gm->hib[q] = 0;
+  for (int q = 0; q < gm->nh; ++q) gm->hib[q] = (unsigned char)bits[a0 + l1 + q];
+  return gm->nh <= 10;
+}
+// 5-d tensor map over the slab, innermost first: [16 doubles = bits 0..2][bits 3..a0-1][gap a0..s1-1][run 1][bits above run 1],
+// box = (16, 2^(a0-3), 1, 2^l1, 1), 128-byte swizzle
+bool sv_make_tensor_map(void *state, int n_local, const SvTmaGeom &gm, CUtensorMap *out) {
+  SvEncodeTiledFn enc = sv_encode_fn();
+  if (!enc) return false;
+  const int top = gm.s1 + gm.l1;
+  cuuint64_t gdim[5] = {16, 1ull << (gm.a0 - 3), 1ull << (gm.s1 - gm.a0), 1ull << gm.l1, 1ull << (n_local - top)};
+  cuuint64_t gstride[4] = {128, 16ull << gm.a0, 16ull << gm.s1, 16ull << top};
+  cuuint32_t box[5] = {16, 1u << (gm.a0 - 3), 1, 1u << gm.l1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, state, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+struct SvFreeList {       // device allocations and events of one call, released on every exit path
+  cudaStream_t st;
+  std::vector<void *> ptrs;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ~SvFreeList() {
+    for (void *q : ptrs) cudaFreeAsync(q, st);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  }
+};
+}  // namespace
+
 extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, int ngates, int tile_bits,
                             void *stream, int sync, qas_sv_info *info) {
+  std::lock_guard<std::mutex> serialise(g_sv_apply_mutex);
   if (!state || n_local < 1 || n_local > 34 || (ngates > 0 && !gates)) { g_sv_error = "bad arguments"; return QAS_ERR_INVALID; }
   for (int i = 0; i < ngates; ++i) {
     const qas_sv_gate &g = gates[i];
@@ -431,7 +624,7 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
   // c = contiguous low bits every tile contains (coalescing); leave at least one free tile bit
   int cwant = 5;
   if (const char *ce = getenv("QAS_B200_SV_C")) cwant = std::max(0, atoi(ce));   // tuning knob
-  const int c = std::max(0, std::min(cwant, kb - 1));
+  const int c = std::max(std::max(0, kb - 8), std::min(cwant, kb - 1));     // the kernel's offs[] table holds 2^(kb-c) <= 256 entries
   if (info) { info->passes = 0; info->tile_bits = kb; info->bytes_per_pass = 32.0 * (double)(1ull << n_local); info->last_ms = 0.0; }
   if (ngates == 0) return QAS_OK;
   std::vector<Block> blocks = plan_blocks(gates, ngates, n_local, kb, c);
@@ -441,7 +634,15 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
   std::vector<SvTileGate> tg;
   std::vector<SvGroup> groups;
   std::vector<unsigned short> ctab;      // per group: swizzled tile index of every coset representative
-  auto h_swz = [](uint32_t j) { uint32_t f = j >> 3; f ^= f >> 3; f ^= f >> 6; return j ^ (f & 7u); };
+  int use_tma = 1;
+  if (const char *te = getenv("QAS_B200_SV_TMA")) use_tma = atoi(te) != 0;     // tuning knob: 0 = cp.async staging for every pass
+  bool tma_mode = false;         // layout of the pass being translated
+  auto h_swz = [&tma_mode](uint32_t j) {
+    if (tma_mode) return j ^ ((j >> 3) & 7u);
+    uint32_t f = j >> 3; f ^= f >> 3; f ^= f >> 6; return j ^ (f & 7u);
+  };
+  std::vector<SvTmaGeom> geom(blocks.size());
+  std::vector<char> tma_of(blocks.size(), 0);
   auto h_par = [](uint32_t v) { return (uint32_t)(__builtin_popcount(v) & 1); };
   std::vector<int> first(blocks.size() + 1, 0), gfirst(blocks.size() + 1, 0);
   std::vector<std::array<unsigned short, 16>> ainv_of(blocks.size());
@@ -450,6 +651,8 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
   if (const char *fe = getenv("QAS_B200_SV_FOLD")) fold = atoi(fe) != 0;   // tuning knob: 0 executes every CNOT
   for (size_t bi = 0; bi < blocks.size(); ++bi) {
     const Block &blk = blocks[bi];
+    tma_of[bi] = use_tma && sv_tma_geometry(blk.bits, kb, n_local, &geom[bi]) && sv_encode_fn() != nullptr;
+    tma_mode = tma_of[bi] != 0;
     std::vector<int> tix(n_local, -1);
     for (size_t q = 0; q < blk.bits.size(); ++q) tix[blk.bits[q]] = (int)q;
     // frame of the pass: tile position p holds logical tile index A p.  arow[q] = row q of A (reads
@@ -459,7 +662,8 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
     const int gate0 = (int)tg.size();
     std::vector<int> cur_bits;      // logical tile bits (targets) of the open group
     int cur_first = 0;              // first gate (index relative to the block) of the open group
-    auto close_group = [&](int end_rel) {
+    auto close_group = [&]() {
+      int end_rel = (int)tg.size() - gate0;
       if (end_rel == cur_first) { cur_bits.clear(); return; }
       // pad the register bits with the highest free logical bits (low bits stay with the lanes)
       for (int b = kb - 1; b >= 0 && (int)cur_bits.size() < 3; --b)
@@ -508,6 +712,41 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
         std::sort(rest.begin(), rest.end());
         kern.insert(kern.end(), rest.begin(), rest.end());
       }
+      // simple group: nothing but uncontrolled 2x2s -> one product per register slot, in slot order
+      {
+        bool simple = true;
+        for (int r = cur_first; r < end_rel; ++r) {
+          const SvTileGate &t = tg[gate0 + r];
+          if (t.kind == SV_K_PDIAG || t.cslot >= 0 || t.crmask != 0u || t.cpos_out >= 0) simple = false;
+        }
+        if (simple) {
+          double2 acc[3][4];
+          bool has[3] = {false, false, false};
+          for (int r = cur_first; r < end_rel; ++r) {
+            const SvTileGate &t = tg[gate0 + r];
+            const int q = t.tslot;
+            if (!has[q]) { for (int e = 0; e < 4; ++e) acc[q][e] = t.u[e]; has[q] = true; continue; }
+            double2 n4[4];                       // later gate times what is there: U_r * acc
+            for (int i = 0; i < 2; ++i)
+              for (int j = 0; j < 2; ++j) {
+                const double2 x = t.u[2 * i], y = acc[q][j], z = t.u[2 * i + 1], w = acc[q][2 + j];
+                n4[2 * i + j] = make_double2(x.x * y.x - x.y * y.y + z.x * w.x - z.y * w.y, x.x * y.y + x.y * y.x + z.x * w.y + z.y * w.x);
+              }
+            for (int e = 0; e < 4; ++e) acc[q][e] = n4[e];
+          }
+          tg.resize((size_t)gate0 + cur_first);
+          for (int q = 0; q < 3; ++q) {
+            if (!has[q]) continue;
+            SvTileGate t{};
+            t.kind = SV_K_U1; t.tslot = q; t.cslot = -1; t.crmask = 0u; t.cpos_out = -1;
+            for (int e = 0; e < 4; ++e) t.u[e] = acc[q][e];
+            tg.push_back(t);
+            gr.simple |= 1 << q;
+          }
+          end_rel = (int)tg.size() - gate0;
+          gr.ngates = end_rel - cur_first;
+        }
+      }
       const int kd = (int)kern.size();       // = kb - 3
       for (uint32_t t = 0; t < (1u << (kb - 3)); ++t) {
         uint32_t P = 0;
@@ -518,7 +757,6 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
       cur_bits.clear();
       cur_first = end_rel;
     };
-    int rel = 0;
     for (int gi : blk.gates) {
       const qas_sv_gate &g = gates[gi];
       SvTileGate t{};
@@ -528,7 +766,7 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
                         g.m[2] == 1.0 && g.m[3] == 0.0 && g.m[4] == 1.0 && g.m[5] == 0.0;
       if (fold && is_x && g.control >= 0 && tix[g.control] >= 0) {
         // CNOT inside the tile: fold into the frame (A <- C A), nothing to execute
-        close_group(rel);
+        close_group();
         const int qt = tix[g.target], qc = tix[g.control];
         arow[qt] ^= arow[qc];
         acol[qc] ^= acol[qt];
@@ -538,7 +776,7 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
       if (g.kind == QAS_SV_U1) {
         const int tb_ = tix[g.target];
         if (std::find(cur_bits.begin(), cur_bits.end(), tb_) == cur_bits.end()) {
-          if ((int)cur_bits.size() == 3) close_group(rel);
+          if ((int)cur_bits.size() == 3) close_group();
           cur_bits.push_back(tb_);
         }
         t.tslot = tb_;
@@ -552,41 +790,43 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
       for (int q = 0; q < 4; ++q) t.u[q] = make_double2(g.m[2 * q], g.m[2 * q + 1]);
       if (is_x) t.kind = SV_K_SWAPX;        // PauliX / CNOT with an outside control: exchange the pair, no flops
       tg.push_back(t);
-      ++rel;
     }
-    close_group(rel);
+    close_group();
     for (int q = 0; q < 16; ++q) ainv_of[bi][q] = q < kb ? (unsigned short)acol[q] : (unsigned short)0;
     first[bi + 1] = (int)tg.size();
     gfirst[bi + 1] = (int)groups.size();
   }
+  SvFreeList owned{st};
   unsigned short *d_ctab = nullptr;
-  SVCK(cudaMallocAsync((void **)&d_ctab, ctab.size() * sizeof(unsigned short), st));
+  SVCK(cudaMallocAsync((void **)&d_ctab, std::max<size_t>(ctab.size(), 1) * sizeof(unsigned short), st));
+  owned.ptrs.push_back(d_ctab);
   SVCK(cudaMemcpyAsync(d_ctab, ctab.data(), ctab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, st));
-  SvGroup *d_groups = nullptr;
-  SVCK(cudaMallocAsync((void **)&d_groups, groups.size() * sizeof(SvGroup), st));
-  SVCK(cudaMemcpyAsync(d_groups, groups.data(), groups.size() * sizeof(SvGroup), cudaMemcpyHostToDevice, st));
-  SvTileGate *d_gates = nullptr;
-  SVCK(cudaMallocAsync((void **)&d_gates, tg.size() * sizeof(SvTileGate), st));
-  SVCK(cudaMemcpyAsync(d_gates, tg.data(), tg.size() * sizeof(SvTileGate), cudaMemcpyHostToDevice, st));
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (info && sync) { SVCK(cudaEventCreate(&e0)); SVCK(cudaEventCreate(&e1)); SVCK(cudaEventRecord(e0, st)); }
+  if (info && sync) { SVCK(cudaEventCreate(&owned.e0)); SVCK(cudaEventCreate(&owned.e1)); SVCK(cudaEventRecord(owned.e0, st)); }
   size_t max_gates = 0;
   for (size_t bi = 0; bi < blocks.size(); ++bi) max_gates = std::max<size_t>(max_gates, first[bi + 1] - first[bi]);
   size_t max_groups = 0;
   for (size_t bi = 0; bi < blocks.size(); ++bi) max_groups = std::max<size_t>(max_groups, gfirst[bi + 1] - gfirst[bi]);
   const size_t smem_max = (size_t)16 << kb;
+  int tma_passes = 0;
   if (max_gates > SV_CONST_GATES || max_groups > SV_CONST_GROUPS) { g_sv_error = "too many gates in one pass for the constant-memory gate list"; return QAS_ERR_UNSUPPORTED; }
   int minb = 3;
   if (const char *mb = getenv("QAS_B200_SV_MINB")) minb = atoi(mb) == 2 ? 2 : 3;   // tuning knob
-  SVCK(cudaFuncSetAttribute(sv_block_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  SVCK(cudaFuncSetAttribute(sv_block_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  SVCK(cudaFuncSetAttribute(sv_block_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  SVCK(cudaFuncSetAttribute(sv_block_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  SVCK(cudaFuncSetAttribute(sv_block_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  SVCK(cudaFuncSetAttribute(sv_block_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   const unsigned long long ntiles = 1ull << (n_local - kb);
-  const int grid = (int)std::min<unsigned long long>(ntiles, 1u << 20);
+  // persistent CTAs: as many as stay resident, each walks its tiles
+  int dev_id = 0, num_sms = 148;
+  cudaGetDevice(&dev_id);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev_id);
+  int occ = minb;
+  if (minb == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv_block_kernel<2, true>, SV_THREADS, smem_max);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv_block_kernel<3, true>, SV_THREADS, smem_max);
+  const int grid = (int)std::min<unsigned long long>(ntiles, (unsigned long long)std::max(1, occ) * num_sms);
   for (size_t bi = 0; bi < blocks.size(); ++bi) {
     SvBlockParams P{};
     P.state = (double2 *)state;
-    P.gates = d_gates + first[bi];
-    P.groups = d_groups + gfirst[bi];
     P.ctab = d_ctab + ((size_t)gfirst[bi] << (kb - 3));
     P.n_local = n_local; P.kb = kb; P.c = c; P.ngates = first[bi + 1] - first[bi];
     P.ngroups = gfirst[bi + 1] - gfirst[bi];
@@ -598,24 +838,35 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
     // stream-ordered: the copy waits for the previous pass's kernel, which still reads the old list
     SVCK(cudaMemcpyToSymbolAsync(c_sv_gates, tg.data() + first[bi], (size_t)P.ngates * sizeof(SvTileGate), 0, cudaMemcpyHostToDevice, st));
     SVCK(cudaMemcpyToSymbolAsync(c_sv_groups, groups.data() + gfirst[bi], (size_t)P.ngroups * sizeof(SvGroup), 0, cudaMemcpyHostToDevice, st));
-    if (minb == 2) sv_block_kernel<2><<<grid, SV_THREADS, smem, st>>>(P);
-    else sv_block_kernel<3><<<grid, SV_THREADS, smem, st>>>(P);
+    CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof tmap);
+    bool tma = tma_of[bi] != 0;
+    if (tma) {
+      P.a0 = geom[bi].a0; P.s1 = geom[bi].s1; P.l1 = geom[bi].l1; P.nh = geom[bi].nh;
+      for (int q = 0; q < 16; ++q) P.hib[q] = geom[bi].hib[q];
+      if (!sv_make_tensor_map(state, n_local, geom[bi], &tmap)) { g_sv_error = "cuTensorMapEncodeTiled failed for a tile geometry"; return QAS_ERR_CUDA; }
+    }
+    if (tma) {
+      if (minb == 2) sv_block_kernel<2, true><<<grid, SV_THREADS, smem, st>>>(P, tmap);
+      else sv_block_kernel<3, true><<<grid, SV_THREADS, smem, st>>>(P, tmap);
+      ++tma_passes;
+    } else {
+      if (minb == 2) sv_block_kernel<2, false><<<grid, SV_THREADS, smem, st>>>(P, tmap);
+      else sv_block_kernel<3, false><<<grid, SV_THREADS, smem, st>>>(P, tmap);
+    }
     SVCK(cudaGetLastError());
   }
   // the upload buffer must outlive the kernels: tg is host memory copied asynchronously from a
   // pageable vector, so wait for the copy before it goes out of scope
-  if (info && sync) SVCK(cudaEventRecord(e1, st));
-  SVCK(cudaFreeAsync(d_gates, st));
-  SVCK(cudaFreeAsync(d_groups, st));
-  SVCK(cudaFreeAsync(d_ctab, st));
+  if (info && sync) SVCK(cudaEventRecord(owned.e1, st));
   SVCK(cudaStreamSynchronize(st));
   if (info) {
     info->passes = (int)blocks.size();
+    info->tma_passes = tma_passes;
     if (sync) {
       float ms = 0.f;
-      cudaEventElapsedTime(&ms, e0, e1);
+      cudaEventElapsedTime(&ms, owned.e0, owned.e1);
       info->last_ms = ms;
-      cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
   }
   return QAS_OK;

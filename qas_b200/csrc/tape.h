@@ -564,3 +564,133 @@ QAS_HD int qas_compress_tape(uint32_t *ops, int *nops_io, int *ngroups_io, int n
   for (int k = d; k < n; ++k) basis[k] = 0u;
   return d;
 }
+
+// ---- c-tape compiler, device formulation ------------------------------------------------------------
+// Same result as qas_compress_tape, organised for one GPU thread per circuit without memory-latency chains:
+//   * ops live PACKED in shared memory, 3 words each (n <= 16, table index < 65536):
+//       w0 = m | r << 16,  w1 = rc | tab << 16,  w2 = meta
+//   * the echelon basis is kept in REDUCED form (every pivot bit occurs in its own vector only), so reducing a
+//     mask is one pass of independent select-xors over a register table of compile-time length NQ -- no
+//     data-dependent loop, no dynamic indexing -- and so are the dual masks r'_k = parity(B_k & r).
+// The caller has already written the ORIGINAL 5-word ops (with group marks) to the record; on success this
+// function overwrites them with the translated ops, on QAS_CT_FULL / QAS_CT_TOO_BIG it leaves the record alone.
+#define QAS_PK_WORDS 3
+struct QasPackedDualSink {        // tape-compiler sink: 5-word op to the record (global), packed copy to shared memory
+  uint32_t *gops;                 // record ops area
+  uint32_t *pk;                   // packed ops
+  int cap, n, overflow;
+  QAS_HD void emit(uint32_t m, uint32_t r, uint32_t rc, uint32_t tab, uint32_t meta) {
+    if (n >= cap) { overflow = 1; return; }
+    uint32_t *o = gops + (size_t)n * QAS_OP_WORDS;
+    o[0] = m; o[1] = r; o[2] = rc; o[3] = tab;       // o[4] follows once the groups are marked
+    uint32_t *q = pk + (size_t)n * QAS_PK_WORDS;
+    q[0] = m | (r << 16); q[1] = rc | (tab << 16); q[2] = meta;
+    n++;
+  }
+};
+// greedy grouping of qas_mark_groups on packed ops; writes the marked meta words to the record as well
+QAS_HD int qas_mark_groups_packed(uint32_t *pk, int nops, int gmax, uint32_t *gops) {
+  int ngroups = 0;
+  for (int j = 0; j < nops;) {
+    uint32_t *a = pk + (size_t)j * QAS_PK_WORDS;
+    int g = 1;
+    if (qas_meta_kind(a[2]) == QAS_K_U1 && (a[1] & 0xffffu) == 0u) {
+      while (g < gmax && j + g < nops) {
+        const uint32_t *b = pk + (size_t)(j + g) * QAS_PK_WORDS;
+        if (qas_meta_kind(b[2]) != QAS_K_U1 || (b[1] & 0xffffu) != 0u) break;
+        bool ok = true;
+        for (int q = 0; q < g; ++q) {
+          const uint32_t *e = pk + (size_t)(j + q) * QAS_PK_WORDS;
+          if (qas_parity32((e[0] & 0xffffu) & (b[0] >> 16)) || qas_parity32((b[0] & 0xffffu) & (e[0] >> 16))) ok = false;
+        }
+        if (!ok) break;
+        ++g;
+      }
+    }
+    a[2] |= (uint32_t)g << 24;
+    pk[(size_t)(j + g - 1) * QAS_PK_WORDS + 2] |= (uint32_t)g << 26;
+    j += g;
+    ++ngroups;
+  }
+  for (int j = 0; j < nops; ++j) gops[(size_t)j * QAS_OP_WORDS + 4] = pk[(size_t)j * QAS_PK_WORDS + 2];
+  return ngroups;
+}
+
+template <int NQ>
+QAS_HD int qas_compress_packed(uint32_t *pk, uint32_t *gops, int *nops_io, int *ngroups_io, int n, const uint32_t *xs, int S,
+                               uint32_t *chead, uint32_t *list, int max_d) {
+  const int nops = *nops_io;
+  uint32_t ev[NQ], ec[NQ], bs[NQ];
+QAS_PUNROLL
+  for (int p = 0; p < NQ; ++p) ev[p] = ec[p] = bs[p] = 0u;
+  int d = 0;
+  for (int j = nops - 1; j >= 0; --j) {            // time order
+    uint32_t *q = pk + (size_t)j * QAS_PK_WORDS;
+    uint32_t c = 0u;
+    if (qas_meta_kind(q[2]) == QAS_K_U1) {
+      const uint32_t m = q[0] & 0xffffu;
+      uint32_t x = m;
+QAS_PUNROLL
+      for (int p = 0; p < NQ; ++p) {               // one-shot reduction against the reduced echelon basis
+        const bool hit = ((m >> p) & 1u) && ev[p];
+        x ^= hit ? ev[p] : 0u;
+        c ^= hit ? ec[p] : 0u;
+      }
+      if (x) {                                     // enlarges the span: B_d = m, coordinates e_d
+        if (d >= max_d || d >= n - 1) return d >= n - 1 ? QAS_CT_FULL : QAS_CT_TOO_BIG;
+        const int pv = qas_msb32(x);
+        const uint32_t cv = c | (1u << d);
+QAS_PUNROLL
+        for (int p = 0; p < NQ; ++p) {
+          const bool has = (ev[p] >> pv) & 1u;     // keep the basis reduced: clear the new pivot everywhere else
+          ev[p] ^= has ? x : 0u;
+          ec[p] ^= has ? cv : 0u;
+          if (p == pv) { ev[p] = x; ec[p] = cv; }
+          if (p == d) bs[p] = m;
+        }
+        c = 1u << d;
+        ++d;
+      }
+    }
+    q[0] = (q[0] & 0xffff0000u) | c;               // m' in place of m
+    q[2] = (q[2] & 0x0fffffffu) | ((uint32_t)d << 28);
+  }
+  // translate, dropping controlled ops whose control is constant on the support
+  int w = 0, ndrop = 0;
+  for (int j = 0; j < nops; ++j) {
+    const uint32_t *q = pk + (size_t)j * QAS_PK_WORDS;
+    const uint32_t r = q[0] >> 16, rc = q[1] & 0xffffu;
+    uint32_t rp = 0u, rcp = 0u;
+QAS_PUNROLL
+    for (int k = 0; k < NQ; ++k) {
+      rp |= (uint32_t)qas_parity32(bs[k] & r) << k;
+      rcp |= (uint32_t)qas_parity32(bs[k] & rc) << k;
+    }
+    if (rc && !rcp) { ++ndrop; continue; }
+    uint32_t *o = gops + (size_t)w * QAS_OP_WORDS;
+    o[0] = q[0] & 0xffffu; o[1] = rp; o[2] = rcp; o[3] = q[1] >> 16; o[4] = q[2];
+    ++w;
+  }
+  *nops_io = w;
+  *ngroups_io -= ndrop;
+  int nsl = 0;
+  for (int s = 0; s < S; ++s) {
+    const uint32_t x0 = xs[s];
+    uint32_t x = x0, c = 0u;
+QAS_PUNROLL
+    for (int p = 0; p < NQ; ++p) {
+      const bool hit = ((x0 >> p) & 1u) && ev[p];
+      x ^= hit ? ev[p] : 0u;
+      c ^= hit ? ec[p] : 0u;
+    }
+    if (!x) list[nsl++] = c | ((uint32_t)s << 16);
+  }
+  chead[0] = (uint32_t)nsl;
+  for (int k = 0; k < n; ++k) {
+    uint32_t b = 0u;
+QAS_PUNROLL
+    for (int p = 0; p < NQ; ++p) b = (p == k) ? bs[p] : b;
+    chead[1 + k] = b;
+  }
+  return d;
+}

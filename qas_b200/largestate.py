@@ -151,8 +151,10 @@ class CudaSvBackend:
         self.device = torch.device("cuda", device)
         self.tile_bits = tile_bits
         self.passes = 0
+        self.tma_passes = 0
         self.kernel_ms = 0.0
         self.bytes = 0.0
+        self._swap_events = []
 
     def alloc(self, n_local):
         return self.torch.empty((1 << n_local, 2), dtype=self.torch.float64, device=self.device)
@@ -182,6 +184,7 @@ class CudaSvBackend:
         self._check(self.lib.qas_sv_apply(state.data_ptr(), n_local, arr, len(gates), self.tile_bits,
                                           self._stream(), 1, ctypes.byref(info)))
         self.passes += info.passes
+        self.tma_passes += info.tma_passes
         self.kernel_ms += info.last_ms
         self.bytes += info.passes * info.bytes_per_pass
 
@@ -194,7 +197,20 @@ class CudaSvBackend:
 
     def all_to_all(self, out, inp, group):
         import torch.distributed as dist
+        e0 = self.torch.cuda.Event(enable_timing=True)
+        e1 = self.torch.cuda.Event(enable_timing=True)
+        e0.record()
         dist.all_to_all_single(out.view(-1), inp.view(-1), group=group)
+        e1.record()
+        self._swap_events.append((e0, e1))
+
+    def swap_ms(self, reset=True):
+        """device time of the rank-bit swaps since the last call (synchronises)"""
+        self.torch.cuda.synchronize(self.device)
+        ms = sum(a.elapsed_time(b) for a, b in self._swap_events)
+        if reset:
+            self._swap_events = []
+        return ms
 
     def all_reduce_sum(self, value, group):
         import torch.distributed as dist

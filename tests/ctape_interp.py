@@ -19,7 +19,7 @@ from tape_interp import _parity, table_entry
 CT_FULL, CT_TOO_BIG = -1, -2
 
 
-def compile_ctape(n, op_pool, k, xmasks, gmax=2, max_d=12):
+def compile_ctape(n, op_pool, k, xmasks, gmax=2, max_d=12, variant=0):
     """-> dict(d, ops uint32[nops,5], ngroups, basis [d], slices [(x', s)]) ; d < 0: not compressed
     (ops is then the grouped classic tape)."""
     lib = _lib.load()
@@ -34,7 +34,7 @@ def compile_ctape(n, op_pool, k, xmasks, gmax=2, max_d=12):
     nops, ng, d, nl = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
     rc = lib.qas_compile_ctape_host(n, pool_arr, len(table), len(k), k.ctypes.data, gmax, xs.ctypes.data, len(xs), max_d,
                                     ops.ctypes.data, cap, ctypes.byref(nops), ctypes.byref(ng), ctypes.byref(d),
-                                    basis.ctypes.data, lst.ctypes.data, ctypes.byref(nl))
+                                    basis.ctypes.data, lst.ctypes.data, ctypes.byref(nl), variant)
     assert rc == 0, lib.qas_last_error(None).decode()
     return {"d": d.value, "ops": ops[:nops.value].copy(), "ngroups": ng.value,
             "basis": [int(b) for b in basis[:max(d.value, 0)]],

@@ -28,8 +28,12 @@ def _state(s):
     return s.state.cpu().numpy().view(np.complex128).reshape(-1)
 
 
-@pytest.mark.parametrize("n,tile_bits", [(6, 3), (9, 6), (12, 8), (14, 12), (15, 13)])
-def test_full_vocabulary_statevector_matches_oracle(n, tile_bits):
+@pytest.mark.parametrize("tma", ["1", "0"])
+@pytest.mark.parametrize("n,tile_bits", [(6, 3), (9, 6), (12, 8), (14, 12), (15, 13), (17, 9), (18, 12)])
+def test_full_vocabulary_statevector_matches_oracle(n, tile_bits, tma, monkeypatch):
+    """Tiles moved by TMA (cp.async.bulk.tensor + mbarrier, 128-byte swizzle; default wherever a 5-d tensor map can
+    describe the tile) and by cp.async (QAS_B200_SV_TMA=0, and tiles below 128 amplitudes) give the oracle's state."""
+    monkeypatch.setenv("QAS_B200_SV_TMA", tma)
     gl = _random_gate_list(n, 60, seed=n)
     rng = np.random.default_rng(n)
     terms = zz_chain_terms(n) + [(float(rng.standard_normal()), "".join(rng.choice(list("IXYZ"), size=n)))
@@ -40,6 +44,22 @@ def test_full_vocabulary_statevector_matches_oracle(n, tile_bits):
         ref = sim.run(n, gl, init).reshape(-1)
         assert np.max(np.abs(_state(s) - ref)) < 1e-12
         assert abs(s.expval(terms) - sim.expval(ref.reshape([2] * n), terms)) < 1e-10
+        assert (s.backend.tma_passes > 0) == (tma == "1" and tile_bits >= 7)
+
+
+def test_tma_and_cp_async_tiles_agree_on_hea_22q(monkeypatch):
+    """Same HEA circuit through both tile-movement paths: identical energies, and the TMA path really ran
+    (every pass of this circuit has a describable tile geometry)."""
+    n = 22
+    gl = hea_gate_list(n, 3, seed=1)
+    out = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("QAS_B200_SV_TMA", tma)
+        s = LargeStateSimulator(n).run(gl)
+        out[tma] = (s.expval(zz_chain_terms(n)), s.backend.tma_passes, s.backend.passes, _state(s)[:4096].copy())
+    assert abs(out["1"][0] - out["0"][0]) < 1e-11
+    assert np.max(np.abs(out["1"][3] - out["0"][3])) < 1e-13
+    assert out["1"][1] == out["1"][2] and out["0"][1] == 0
 
 
 def test_hea_20q_energy_matches_oracle():

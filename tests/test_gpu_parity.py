@@ -118,10 +118,14 @@ def test_full_vocabulary_random_circuits():
             ev.close()
 
 
-@pytest.mark.parametrize("n,grad", [(9, True), (11, True), (12, True), (13, False), (13, True), (14, True)])
-def test_qubit_count_sweep_including_global_memory_path(n, grad):
-    """11-12 qubits: 256-thread teams; 13 energy-only still shared-memory resident; 13 with
-    gradients and 14 fall to the global-memory path."""
+@pytest.mark.parametrize("compress", ["0", "1"])
+@pytest.mark.parametrize("n,grad", [(9, True), (11, True), (12, True), (13, False), (13, True), (14, True), (15, True), (16, True)])
+def test_qubit_count_sweep_including_global_memory_path(n, grad, compress, monkeypatch):
+    """Classic kernels (QAS_B200_COMPRESS=0): 11-12 qubits: 256-thread teams; 13 energy-only still shared-memory
+    resident; 13 with gradients and 14-16 fall to the global-memory path.  Default: these shallow circuits span
+    fewer than n dimensions, so every one of them -- up to 16 qubits -- runs as a compressed register in shared
+    memory (path 3)."""
+    monkeypatch.setenv("QAS_B200_COMPRESS", compress)
     rng = np.random.default_rng(n)
     pool = helpers.near_cx_pool(n)
     c = len(pool)
@@ -133,7 +137,7 @@ def test_qubit_count_sweep_including_global_memory_path(n, grad):
     params = rng.standard_normal((p, c, 3))
     out = ev.evaluate(ks, params, want_grad=grad, compact=grad)
     st = ev.stats()
-    assert st["path"] == (0 if n <= (12 if grad else 13) else 1)
+    assert st["path"] == (3 if compress == "1" else (0 if n <= (12 if grad else 13) else 1))
     e_ref, g_ref = _oracle_batch(n, ks, pool.pool, params, terms, ("zero", 0), grad)
     assert np.max(np.abs(out["energy"] - e_ref)) <= E_TOL
     if grad:

@@ -370,3 +370,34 @@ def test_ctape_edge_cases():
     k = [0, 2, 4, 6, 8]
     assert CT.compile_ctape(n, pool, k, xs, max_d=3)["d"] == CT.CT_TOO_BIG
     assert CT.compile_ctape(n, pool, k, xs, max_d=5)["d"] == 5
+
+
+def test_ctape_device_formulation_matches_reference_formulation():
+    """The c-tape compiler as the tape-compile kernel runs it (packed ops, reduced echelon basis in registers,
+    one-shot reductions) produces bit-identical records to the reference formulation, on chemistry batches and on
+    the full vocabulary, compressed and not."""
+    import ctape_interp as CT
+    from qas_b200.qml_models.qml_models_legacy import LiH
+    rng = np.random.default_rng(9)
+    cases = []
+    pool10 = helpers.near_cx_pool(10)
+    xs10, _, _ = CT.sign_tables(10, LiH.terms()[:60])
+    for k in sample_structure_lists(pool10, 20, {"CNOT": 10}, 60, seed=4):
+        cases.append((10, pool10, [int(x) for x in k], xs10, 12))
+    pool7 = helpers.full_vocab_pool(7)
+    xs7 = sorted({int(x) for x in rng.integers(0, 128, size=20)} | {0})
+    for _ in range(60):
+        cases.append((7, pool7, [int(x) for x in rng.integers(0, len(pool7), size=8)], xs7, 12))
+    pool14 = helpers.near_cx_pool(14)
+    xs14 = sorted({int(x) for x in rng.integers(0, 1 << 14, size=40)} | {0, 3, 5 << 7})
+    for k in sample_structure_lists(pool14, 24, {"CNOT": 12}, 30, seed=5):
+        cases.append((14, pool14, [int(x) for x in k], xs14, 9))
+    seen = set()
+    for n, pool, k, xs, max_d in cases:
+        a = CT.compile_ctape(n, pool, k, xs, gmax=2, max_d=max_d, variant=0)
+        b = CT.compile_ctape(n, pool, k, xs, gmax=2, max_d=max_d, variant=1)
+        seen.add(a["d"] if a["d"] >= 0 else a["d"])
+        assert a["d"] == b["d"] and a["ngroups"] == b["ngroups"]
+        assert np.array_equal(a["ops"], b["ops"])
+        assert a["basis"] == b["basis"] and a["slices"] == b["slices"]
+    assert CT.CT_TOO_BIG in seen and len([d for d in seen if d >= 0]) >= 5

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun session: a list of steps, each under its own timeout, logs under gpurun_out/<tag>/.
 #   tools/gpu/session.sh <tag> <step> [<step> ...]
-# steps: tests | tests:<pytest -k expr> | bench:<workload>[:<env assignments,comma separated>] | stages:<workload>
+# steps: tests | tests:<pytest -k expr> | bench:<workload>[:<env assignments,comma separated>] | stages:<workload> | phases:<workload> | svbench:<workload>[:envs]
 #        | launches:<workload> | ncu:<workload>:<kernel regex> | sanity
 set -u
 export QAS_B200_NO_REBUILD=1
@@ -39,6 +39,13 @@ for step in "$@"; do
       timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$b" -s 6 -c 1 -o "$out/$name" -f \
         python bench.py --workload "$a" --steps 2 --warmup 3 --tune > "$out/$name.log" 2>&1
       echo "rc=$?" | tee -a "$out/steps.log" ;;
+    phases)
+      timeout 300 python tools/phase_clocks.py --workload "$a" > "$out/$name.txt" 2>&1
+      echo "rc=$?" | tee -a "$out/steps.log"; tail -40 "$out/$name.txt" ;;
+    svbench)
+      envs=$(echo "${b:-}" | tr ',' ' ')
+      env $envs timeout 600 python bench.py --workload "$a" --steps 5 --warmup 3 --tune > "$out/$name.json" 2> "$out/$name.err"
+      echo "rc=$?" | tee -a "$out/steps.log"; tail -c 1500 "$out/$name.json"; tail -3 "$out/$name.err" ;;
     sanity)
       timeout 600 python tools/gpu/sanity.py > "$out/$name.log" 2>&1
       echo "rc=$?" | tee -a "$out/steps.log"; tail -3 "$out/$name.log" ;;

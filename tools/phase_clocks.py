@@ -26,16 +26,30 @@ def main():
     for rep in range(3):
         ev.evaluate(ks, params, want_grad=not args.no_grad)
         out = (ctypes.c_uint64 * 4)()
+        outc = (ctypes.c_uint64 * (8 * 16))()
+        dmin = ctypes.c_int(0)
+        rc = ev._lib.qas_debug_phase_clocks_c(ev._h, outc, 16, ctypes.byref(dmin), 0)
+        assert rc == 0, ev._lib.qas_last_error(ev._h)
         rc = ev._lib.qas_debug_phase_clocks(ev._h, out, 1)
         assert rc == 0, ev._lib.qas_last_error(ev._h)
     st = ev.stats()
     names = ["prologue", "forward", "H+energy", "adjoint"]
-    tot = sum(out)
-    print("%s: B=%d, team=%d threads, %d CTAs/SM x %d teams; eval kernel %.3f ms" % (
-        args.workload, len(ks), st["threads_per_team"], st["ctas_per_sm"], st["teams_per_cta"], st["last_eval_kernel_ms"]))
-    for n_, v in zip(names, out):
-        print("  %-10s %9.0f cycles/circuit  %5.1f%%" % (n_, v / len(ks), 100.0 * v / tot))
-    print("  %-10s %9.0f cycles/circuit" % ("total", tot / len(ks)))
+    print("%s: B=%d; eval kernels %.3f ms" % (args.workload, len(ks), st["last_eval_kernel_ms"]))
+    ncls = len(ks) - sum(int(outc[8 * b_ + 4]) for b_ in range(16))
+    if sum(out):
+        print("  classic kernel (full bin), %d circuits:" % ncls)
+        for n_, v in zip(names, out):
+            print("    %-10s %9.0f cycles/circuit  %5.1f%%" % (n_, v / max(1, ncls), 100.0 * v / sum(out)))
+        print("    %-10s %9.0f cycles/circuit" % ("total", sum(out) / max(1, ncls)))
+    for b_ in range(16):
+        cnt = int(outc[8 * b_ + 4])
+        if not cnt:
+            continue
+        v4 = [int(outc[8 * b_ + i]) for i in range(4)]
+        print("  compressed kernel, slot %d (%d circuits, %.1f%%):" % (dmin.value + b_, cnt, 100.0 * cnt / len(ks)))
+        for n_, v in zip(names, v4):
+            print("    %-10s %9.0f cycles/circuit  %5.1f%%" % (n_, v / cnt, 100.0 * v / max(1, sum(v4))))
+        print("    %-10s %9.0f cycles/circuit" % ("total", sum(v4) / cnt))
 
 
 if __name__ == "__main__":
