@@ -216,6 +216,19 @@ int qas_adam_step(void *params, const void *grad, void *m, void *v, const void *
                   int t, double stepsize, double beta1, double beta2, double eps, double noise_factor,
                   void *stream);
 
+/* The fine-tuning step of circuitModelTuning (mcts.py:381-412) in a form a CUDA graph can replay: nothing the
+ * captured work reads may live on the host, so the step counter t, the bias-corrected Adam step size and the
+ * loss history are device-resident.  qas_tuning_tick (one thread): t <- t + 1, *step_dev <- stepsize *
+ * sqrt(1 - beta2^t) / (1 - beta1^t), losses_dev[t - 1] <- *loss_dev.  qas_adam_step_dev: the update of
+ * qas_adam_step (no noise term) with the step size read from *step_dev.  Device pointers; asynchronous on
+ * `stream`.  A graph of { qas_eval_batch(QAS_F_DEVICE_PTRS) ; qas_tuning_tick ; qas_adam_step_dev } replayed
+ * num_epochs times is the whole loop without a host round trip per epoch (qas_eval_batch detects the capture
+ * and records no timing events).                                                                   */
+int qas_tuning_tick(void *t_dev, void *step_dev, const void *loss_dev, void *losses_dev, int max_losses,
+                    double stepsize, double beta1, double beta2, void *stream);
+int qas_adam_step_dev(void *params, const void *grad, void *m, void *v, uint64_t n, const void *step_dev,
+                      double beta1, double beta2, double eps, void *stream);
+
 /* Batch mean of per-circuit compact gradients that already sit on the device (device pointers; asynchronous on
  * `stream`): grad_dense[p][c][l] = mean | sum over b of scatter(nan_to_num(grad_compact[b])) by k[b] -- the
  * reduction of mcts.py:345-347 with the deterministic two-stage summation qas_eval_batch uses.  For costs whose

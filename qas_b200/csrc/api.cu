@@ -348,6 +348,55 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
             n_qubits, cx->S_flat, 0, 0, 0, 0, nowc, cx->d_sxflat, d_fb, d_fz, d_fc, cx->d_vflat);
         guard(cudaGetLastError(), "build flat sign tables launch");
         guard(cudaStreamSynchronize(cx->stream), "build flat sign tables");
+        // Slices whose Z masks span r <= 4 dimensions: V_s[i] = lut[parities of i with a basis zeta of that span].
+        // z_t = xor_q a_tq zeta_q  =>  parity((i ^ x_s) & z_t) = popc(a_t & (idx(i) ^ kappa)) mod 2, with
+        // idx(i) = sum_q parity(i & zeta_q) << q and kappa = idx(x_s) folded into the table.
+        std::vector<uint4> sinfo((size_t)cx->S_flat);
+        std::vector<double> slut((size_t)cx->S_flat * 16, 0.0);
+        int lut_max = 4;
+        if (const char *le = getenv("QAS_B200_C_LUT_RANK")) lut_max = std::max(0, std::min(4, atoi(le)));   // tuning knob: 0 = always the flat table
+        for (int s_ = 0; s_ < cx->S_flat; ++s_) {
+          // zeta: the masks chosen as basis; red[q]: zeta_q reduced against the earlier ones (echelon form, pivot =
+          // its highest bit); rco[q]: coordinates of red[q] in terms of the zetas
+          std::vector<uint32_t> zeta, red, rco;
+          auto reduce = [&](uint32_t x, uint32_t *a) {
+            for (size_t q = 0; q < red.size(); ++q)
+              if ((x >> (31 - __builtin_clz(red[q]))) & 1u) { x ^= red[q]; *a ^= rco[q]; }
+            return x;
+          };
+          bool small = lut_max > 0;
+          for (int t = fbegin[s_]; t < fbegin[s_ + 1] && small; ++t) {
+            uint32_t a = 0u;
+            const uint32_t x = reduce(fz[t], &a);
+            if (!x) continue;
+            if ((int)zeta.size() >= lut_max) { small = false; break; }
+            rco.push_back(a | (1u << zeta.size()));
+            zeta.push_back(fz[t]);
+            red.push_back(x);
+          }
+          if (!small) { sinfo[s_] = make_uint4(255u, 0u, 0u, 0u); continue; }
+          const int r = (int)zeta.size();
+          uint32_t kappa = 0u;
+          for (int q = 0; q < r; ++q) kappa |= (uint32_t)(__builtin_popcount(cx->sxflat[s_] & zeta[q]) & 1) << q;
+          for (uint32_t idx = 0; idx < 16u; ++idx) {
+            double v = 0.0;
+            for (int t = fbegin[s_]; t < fbegin[s_ + 1]; ++t) {
+              uint32_t at = 0u;
+              reduce(fz[t], &at);        // coordinates a_t of the term's mask (it lies in the span)
+              v += (__builtin_popcount(at & (idx ^ kappa) & ((1u << r) - 1u)) & 1) ? -fc[t] : fc[t];
+            }
+            slut[(size_t)s_ * 16 + idx] = v;
+          }
+          uint32_t z4[4] = {0u, 0u, 0u, 0u};
+          for (int q = 0; q < r; ++q) z4[q] = zeta[q];
+          sinfo[s_] = make_uint4((uint32_t)r, z4[0] | (z4[1] << 16), z4[2] | (z4[3] << 16), 0u);
+        }
+        guard(cudaMalloc(&cx->d_sinfo, sizeof(uint4) * sinfo.size()), "cudaMalloc sinfo");
+        guard(cudaMalloc(&cx->d_slut, sizeof(double) * slut.size()), "cudaMalloc slut");
+        if (rc == QAS_OK) {
+          guard(cudaMemcpy(cx->d_sinfo, sinfo.data(), sizeof(uint4) * sinfo.size(), cudaMemcpyHostToDevice), "copy sinfo");
+          guard(cudaMemcpy(cx->d_slut, slut.data(), sizeof(double) * slut.size(), cudaMemcpyHostToDevice), "copy slut");
+        }
       }
       cudaFree(d_fz); cudaFree(d_fc); cudaFree(d_fb);
     }
@@ -361,7 +410,7 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
 extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   if (!ctx) return QAS_OK;
   cudaSetDevice(ctx->device);
-  cudaFree(ctx->d_bins); cudaFree(ctx->d_order); cudaFree(ctx->d_vflat); cudaFree(ctx->d_sxflat);
+  cudaFree(ctx->d_bins); cudaFree(ctx->d_order); cudaFree(ctx->d_vflat); cudaFree(ctx->d_sxflat); cudaFree(ctx->d_sinfo); cudaFree(ctx->d_slut);
   if (ctx->h_bins) cudaFreeHost(ctx->h_bins);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   for (int i = 0; i < QAS_MAX_BINS; ++i) {
@@ -471,6 +520,13 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   // the context's own stream
   cudaStream_t st = (dev || stream) ? (cudaStream_t)stream : ctx->stream;
   const size_t nk = (size_t)B * p, npar = (size_t)p * c * l, ng = (size_t)B * p * l;
+  // a call enqueued on a stream that is being captured into a CUDA graph (qas_b200.mcts.driver tuning loop): no
+  // timing events (they could not be queried afterwards); every buffer must have been sized by an earlier call
+  bool capturing = false;
+  {
+    cudaStreamCaptureStatus cs_ = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs_) == cudaSuccess) capturing = cs_ != cudaStreamCaptureStatusNone;
+  }
 
   // one-reward-at-a-time rollouts: no timing events, no structure-list upload (the tapes are compiled
   // on the host and the reward path never reads k on the device)
@@ -568,7 +624,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     if (!ctx->sev[i]) cudaEventCreate(&ctx->sev[i]);
     cudaEventRecord(ctx->sev[i], st);
   };
-  if (!dev && !tiny) CK(cudaEventRecord(ctx->ev0, st));
+  if (!dev && !tiny && !capturing) CK(cudaEventRecord(ctx->ev0, st));
   stamp(0);
   if (want_grad && !fused_reduce) { CK(cudaMemsetAsync(dgrad, 0, ng * 8, st)); ctx->stats.launches += 1; }
   if (!small) CK(cudaMemsetAsync(ctx->d_bins, 0, sizeof(int) * 2 * QAS_MAX_BINS, st));   // bin counts + work-queue heads
@@ -645,7 +701,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     CK(cudaGetLastError());
     ctx->stats.launches += 1;
   }
-  if (!tiny) CK(cudaEventRecord(ctx->ek0, st));
+  if (!tiny && !capturing) CK(cudaEventRecord(ctx->ek0, st));
   stamp(3);
   auto launch_classic = [&](cudaStream_t s_) { return want_grad ? qas_launch_eval_grad(ctx, P, s_) : qas_launch_eval_nograd(ctx, P, s_); };
   if (!use_c) {
@@ -657,7 +713,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     // persistent CTAs of a small bin fill the tail of a large one.  Host-compiled batches launch the non-empty
     // bins back to back on the call's stream.
     EvalCParams Q{};
-    Q.tape = ctx->d_tape; Q.U = ctx->d_U; Q.vflat = ctx->d_vflat; Q.energy = denergy; Q.mout = P.mout;
+    Q.tape = ctx->d_tape; Q.U = ctx->d_U; Q.vflat = ctx->d_vflat; Q.sinfo = ctx->d_sinfo; Q.slut = ctx->d_slut; Q.energy = denergy; Q.mout = P.mout;
     Q.rec_stride = rec_words; Q.n = ctx->n; Q.ops_cap = ops_cap; Q.S = ctx->S_flat; Q.S_real = ctx->S_real_flat;
     const bool fork = !host_compile;
     if (fork) CK(cudaEventRecord(ctx->fork_ev, st));
@@ -703,7 +759,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
       }
     }
   }
-  if (!tiny) { CK(cudaEventRecord(ctx->ek1, st)); ctx->ek_pending = true; }
+  if (!tiny && !capturing) { CK(cudaEventRecord(ctx->ek1, st)); ctx->ek_pending = true; }
   stamp(4);
   if (want_grad && !small && !fused_reduce) {
     const size_t nthr = (size_t)B * ops_cap;
@@ -847,15 +903,24 @@ extern "C" int qas_compile_ctape_host(int n_qubits, const qas_pool_entry *pool, 
   } else {                   // device formulation: packed ops, reduced echelon basis in registers
     if (n_qubits > 16 || (size_t)QAS_NCONST + (size_t)p * c > 65535) { g_create_error = "packed c-tape compiler needs n <= 16 and p * c < 65524"; return QAS_ERR_UNSUPPORTED; }
     std::vector<uint32_t> pk((size_t)std::max(1, max_ops) * QAS_PK_WORDS);
-    QasPackedDualSink sink{out_ops, pk.data(), max_ops, 0, 0};
+    QasPk3Sink sink{pk.data(), max_ops, 0, 0};
     const int st = qas_compile_circuit(k, p, pool, c, n_qubits, col, row, sink);
     if (st == 1) { g_create_error = "structure list entry out of range"; return QAS_ERR_INVALID; }
     if (st == 2) { g_create_error = "tape buffer too small"; return QAS_ERR_NOMEM; }
     nops = sink.n;
-    ngroups = qas_mark_groups_packed(pk.data(), nops, gmax, out_ops);
+    ngroups = qas_mark_groups_packed(pk.data(), nops, gmax);
+    const int nops_raw = nops, ngroups_raw = ngroups;
     if (n_qubits <= 10) d = qas_compress_packed<10>(pk.data(), out_ops, &nops, &ngroups, n_qubits, xmasks, num_xmasks, cinfo.data(), cinfo.data() + 1 + n_qubits, max_d);
     else if (n_qubits <= 12) d = qas_compress_packed<12>(pk.data(), out_ops, &nops, &ngroups, n_qubits, xmasks, num_xmasks, cinfo.data(), cinfo.data() + 1 + n_qubits, max_d);
     else d = qas_compress_packed<16>(pk.data(), out_ops, &nops, &ngroups, n_qubits, xmasks, num_xmasks, cinfo.data(), cinfo.data() + 1 + n_qubits, max_d);
+    if (d < 0) {
+      QasPk3Sink again{pk.data(), max_ops, 0, 0};
+      qas_compile_circuit(k, p, pool, c, n_qubits, col, row, again);
+      qas_mark_groups_packed(pk.data(), nops_raw, gmax);
+      qas_unpack_ops(pk.data(), nops_raw, out_ops);
+      nops = nops_raw;
+      ngroups = ngroups_raw;
+    }
   }
   *num_ops = nops;
   *num_groups = ngroups;
@@ -887,6 +952,48 @@ extern "C" int qas_adam_step(void *params, const void *grad, void *m, void *v, c
       beta2, eps, noise_factor);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_create_error = std::string("adam_step_kernel: ") + cudaGetErrorString(e); return QAS_ERR_CUDA; }
+  return QAS_OK;
+}
+
+// ---------------------------------------------------------------------------------- graph-capturable tuning step
+// circuitModelTuning (mcts.py:381-412) as a replayable CUDA graph: nothing in the captured work may depend on
+// host state, so the step counter, the bias-corrected step size and the loss history live on the device.
+//   qas_tuning_tick:  t <- t + 1 ; step <- stepsize sqrt(1 - b2^t) / (1 - b1^t) ; losses[t - 1] <- *loss
+//   qas_adam_step_dev: the update of qas_adam_step with `step` read from the device
+static __global__ void tuning_tick_kernel(int *t, double *step, const double *loss, double *losses, int max_losses,
+                                          double stepsize, double b1, double b2) {
+  const int tt = *t + 1;
+  *t = tt;
+  *step = stepsize * sqrt(1.0 - pow(b2, (double)tt)) / (1.0 - pow(b1, (double)tt));
+  if (losses && tt - 1 < max_losses) losses[tt - 1] = *loss;
+}
+static __global__ void adam_step_dev_kernel(double *x, const double *grad, double *m, double *v, size_t n, const double *step,
+                                            double b1, double b2, double eps) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double g = nan_to_num_d(grad[i]);
+  const double mi = b1 * m[i] + (1.0 - b1) * g;
+  const double vi = b2 * v[i] + (1.0 - b2) * g * g;
+  m[i] = mi;
+  v[i] = vi;
+  x[i] = x[i] - *step * mi / (sqrt(vi) + eps);
+}
+extern "C" int qas_tuning_tick(void *t_dev, void *step_dev, const void *loss_dev, void *losses_dev, int max_losses,
+                               double stepsize, double beta1, double beta2, void *stream) {
+  if (!t_dev || !step_dev || !loss_dev) { g_create_error = "bad arguments to qas_tuning_tick"; return QAS_ERR_INVALID; }
+  tuning_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((int *)t_dev, (double *)step_dev, (const double *)loss_dev,
+                                                       (double *)losses_dev, max_losses, stepsize, beta1, beta2);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_create_error = std::string("tuning_tick_kernel: ") + cudaGetErrorString(e); return QAS_ERR_CUDA; }
+  return QAS_OK;
+}
+extern "C" int qas_adam_step_dev(void *params, const void *grad, void *m, void *v, uint64_t n, const void *step_dev,
+                                 double beta1, double beta2, double eps, void *stream) {
+  if (!params || !grad || !m || !v || n == 0 || !step_dev) { g_create_error = "bad arguments to qas_adam_step_dev"; return QAS_ERR_INVALID; }
+  adam_step_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (double *)params, (const double *)grad, (double *)m, (double *)v, (size_t)n, (const double *)step_dev, beta1, beta2, eps);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_create_error = std::string("adam_step_dev_kernel: ") + cudaGetErrorString(e); return QAS_ERR_CUDA; }
   return QAS_OK;
 }
 

@@ -51,6 +51,8 @@ struct qas_ctx {
   int *h_bins = nullptr; size_t cap_hbins = 0;    // pinned staging of counts + order for host-compiled batches
   double *d_vflat = nullptr;       // [S_flat][2^n] sign tables by physical index, one row per (X mask, real|imag) slice
   uint32_t *d_sxflat = nullptr;    // [S_flat] X masks of those rows
+  uint4 *d_sinfo = nullptr;        // [S_flat] Z-span rank and basis of every slice (kernels_c.cuh c_hphase)
+  double *d_slut = nullptr;        // [S_flat][16] sign of the slice as a function of the span parities
   std::vector<uint32_t> sxflat;
   int S_flat = 0, S_real_flat = 0;
   cudaStream_t side[QAS_MAX_BINS] = {nullptr};

@@ -52,16 +52,30 @@ __global__ void __launch_bounds__(CTHREADS) compile_ctapes_kernel(const CompileC
   const size_t stride = qas_ccompile_smem_words(n, P.ops_cap, P.p);
   uint32_t *mine = csm + (size_t)threadIdx.x * stride;
   uint32_t *col = mine, *row = col + n, *pk = row + n;
+  // the pool table is read at every depth step of every thread: one shared copy per CTA
+  qas_pool_entry *spool = reinterpret_cast<qas_pool_entry *>(csm + (size_t)CTHREADS * stride);
+  for (int x = threadIdx.x; x < P.c; x += CTHREADS) spool[x] = P.pool[x];
+  __syncthreads();
   int bin = -1;
   if (live) {
     uint32_t *rec = P.tape + (size_t)b * P.rec_stride;
     uint32_t *gops = rec + QAS_REC_HDR;
     uint32_t *gci = gops + (size_t)P.ops_cap * QAS_OP_WORDS;
-    QasPackedDualSink sink{gops, pk, P.ops_cap, 0, 0};
-    const int st = qas_compile_circuit(P.k + (size_t)b * P.p, P.p, P.pool, P.c, n, col, row, sink);
+    QasPk3Sink sink{pk, P.ops_cap, 0, 0};
+    const int32_t *kb = P.k + (size_t)b * P.p;
+    const int st = qas_compile_circuit(kb, P.p, spool, P.c, n, col, row, sink);
     int nops = st ? 0 : sink.n;
-    int ngroups = qas_mark_groups_packed(pk, nops, P.gmax, gops);
+    int ngroups = qas_mark_groups_packed(pk, nops, P.gmax);
+    const int nops_raw = nops, ngroups_raw = ngroups;
     const int d = qas_compress_packed<NQ>(pk, gops, &nops, &ngroups, n, P.sxflat, P.S, gci, gci + 1 + n, P.max_d);
+    if (d < 0) {       // classic path: the grouped original tape (the translation above stopped half-way: compile again)
+      QasPk3Sink again{pk, P.ops_cap, 0, 0};
+      qas_compile_circuit(kb, P.p, spool, P.c, n, col, row, again);
+      qas_mark_groups_packed(pk, nops_raw, P.gmax);
+      qas_unpack_ops(pk, nops_raw, gops);
+      nops = nops_raw;
+      ngroups = ngroups_raw;
+    }
     rec[0] = (uint32_t)nops;
     rec[1] = (uint32_t)st;
     rec[2] = d >= 0 ? (uint32_t)d : 0x80000000u;
@@ -85,6 +99,9 @@ struct EvalCParams {
   const uint32_t *tape;        // [B][rec_stride]
   const GateTab *U;
   const double *vflat;         // [S][2^n] flat sign tables, row s = slice s (real slices first)
+  const uint4 *sinfo;          // [S] per slice: x = rank r of the span of its Z masks (255: look the sign up in vflat),
+                               //     y = zeta_0 | zeta_1 << 16, z = zeta_2 | zeta_3 << 16 (basis of that span)
+  const double *slut;          // [S][16] V_s as a function of the r parities parity(i & zeta_q) (x_s folded in)
   const int *order;            // this bin's circuit indices
   const int *count;            // ... and how many
   int *work_counter;           // this bin's queue head (zeroed before the launch)
@@ -229,6 +246,76 @@ __device__ __forceinline__ void c_adj_group(double2 *psi, double2 *lam, const ui
                                                                         : ring + ((size_t)q * WPT + warp_in_team) * 8, false);
 }
 
+// lambda = H psi on the support (compressed coordinates), returns this thread's share of Re <psi|lambda>.
+// A thread takes HA amplitudes at a time (t = t0 + T a) and walks the in-span slices ONCE for all of them.  The
+// sign V_s[i] at the physical index i = xor_k t_k B_k comes
+//   * for slices whose Z masks span <= 4 dimensions (all the excitation slices of a chemistry Hamiltonian: 28 of
+//     35 for LiH) from a 16-entry table indexed by the parities of i with a basis of that span -- two sectors per
+//     warp instead of one scattered 8-byte look-up per lane (the scattered look-ups made this phase L1-request
+//     bound: one sector per lane per slice);
+//   * for the few slices with many Z masks (the diagonal one, the number-operator dressed single excitations) from
+//     the flat 2^n table.
+template <int HA, int T, bool GRAD>
+__device__ __forceinline__ double c_hphase(const EvalCParams &P, const double2 *psi, double2 *lam, const uint32_t *chead,
+                                           const uint32_t *list, int nsl, int d, int tid) {
+  double e_part = 0.0;
+  const uint32_t dim = 1u << d;
+  const int n = P.n;
+  for (uint32_t t0 = tid; t0 < dim; t0 += T * HA) {
+    uint32_t ph[HA];
+    double2 acc[HA];
+#pragma unroll
+    for (int a = 0; a < HA; ++a) {
+      const uint32_t t = t0 + (uint32_t)(T * a);
+      uint32_t i = 0u;
+      for (int kk = 0; kk < d; ++kk) i ^= ((t >> kk) & 1u) ? chead[1 + kk] : 0u;
+      ph[a] = i;
+      acc[a] = make_double2(0.0, 0.0);
+    }
+    for (int s = 0; s < nsl; ++s) {
+      const uint32_t ent = list[s];
+      const uint32_t xp = ent & 0xffffu, si = ent >> 16;
+      const bool imag = (int)si >= P.S_real;
+      const uint4 info = __ldg(P.sinfo + si);
+      double v[HA];
+      if (info.x <= 4u) {
+        const double *lut = P.slut + (size_t)si * 16;
+        const uint32_t z0 = info.y & 0xffffu, z1 = info.y >> 16, z2 = info.z & 0xffffu, z3 = info.z >> 16;
+#pragma unroll
+        for (int a = 0; a < HA; ++a) {
+          const uint32_t i = ph[a];
+          uint32_t idx = (__popc(i & z0) & 1) | ((__popc(i & z1) & 1) << 1);
+          if (info.x > 2u) idx |= ((__popc(i & z2) & 1) << 2) | ((__popc(i & z3) & 1) << 3);
+          v[a] = __ldg(lut + idx);
+        }
+      } else {
+        const double *vrow = P.vflat + ((size_t)si << n);
+#pragma unroll
+        for (int a = 0; a < HA; ++a) v[a] = (t0 + (uint32_t)(T * a) < dim) ? __ldg(vrow + ph[a]) : 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < HA; ++a) {
+        const uint32_t t = t0 + (uint32_t)(T * a);
+        if (t < dim) {
+          const double2 pa = psi[t ^ xp];
+          if (!imag) { acc[a].x = fma(v[a], pa.x, acc[a].x); acc[a].y = fma(v[a], pa.y, acc[a].y); }
+          else { acc[a].x = fma(-v[a], pa.y, acc[a].x); acc[a].y = fma(v[a], pa.x, acc[a].y); }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < HA; ++a) {
+      const uint32_t t = t0 + (uint32_t)(T * a);
+      if (t < dim) {
+        const double2 ai = psi[t];
+        e_part = fma(ai.x, acc[a].x, fma(ai.y, acc[a].y, e_part));
+        if constexpr (GRAD) lam[t] = acc[a];
+      }
+    }
+  }
+  return e_part;
+}
+
 template <int T, bool GRAD, int BLK, int MINB>
 __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
   constexpr int WPT = T >= 32 ? T / 32 : 1;
@@ -307,51 +394,12 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
 
     if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 1, (unsigned long long)(c_ - clk_prev)); clk_prev = c_; }
     // ---- 3. lambda = H psi on the support, E = Re <psi|lambda>
-    // A thread takes up to HA amplitudes at a time (t = t0 + T a) and walks the in-span slices ONCE for all of
-    // them: per slice HA independent sign-table loads (L2) and HA partner loads (shared memory) are in flight
-    // together -- the look-ups are latency-, not bandwidth-bound.
-    double e_part = 0.0;
+    double e_part;
     {
-      constexpr int HA = 8;
-      const uint32_t dim = 1u << d;
-      for (uint32_t t0 = tid; t0 < dim; t0 += T * HA) {
-        uint32_t ph[HA];
-        double2 acc[HA];
-#pragma unroll
-        for (int a = 0; a < HA; ++a) {
-          const uint32_t t = t0 + (uint32_t)(T * a);
-          uint32_t i = 0u;
-          for (int kk = 0; kk < d; ++kk) i ^= ((t >> kk) & 1u) ? chead[1 + kk] : 0u;
-          ph[a] = i;
-          acc[a] = make_double2(0.0, 0.0);
-        }
-#pragma unroll 2
-        for (int s = 0; s < nsl; ++s) {
-          const uint32_t ent = list[s];
-          const uint32_t xp = ent & 0xffffu;
-          const double *vrow = P.vflat + ((size_t)(ent >> 16) << n);
-          const bool imag = (int)(ent >> 16) >= P.S_real;
-#pragma unroll
-          for (int a = 0; a < HA; ++a) {
-            const uint32_t t = t0 + (uint32_t)(T * a);
-            if (t < dim) {
-              const double v = __ldg(vrow + ph[a]);
-              const double2 pa = psi[t ^ xp];
-              if (!imag) { acc[a].x = fma(v, pa.x, acc[a].x); acc[a].y = fma(v, pa.y, acc[a].y); }
-              else { acc[a].x = fma(-v, pa.y, acc[a].x); acc[a].y = fma(v, pa.x, acc[a].y); }
-            }
-          }
-        }
-#pragma unroll
-        for (int a = 0; a < HA; ++a) {
-          const uint32_t t = t0 + (uint32_t)(T * a);
-          if (t < dim) {
-            const double2 ai = psi[t];
-            e_part = fma(ai.x, acc[a].x, fma(ai.y, acc[a].y, e_part));
-            if constexpr (GRAD) lam[t] = acc[a];
-          }
-        }
-      }
+      const int per = (1 << d) / T;                 // amplitudes per thread
+      if (per <= 2) e_part = c_hphase<2, T, GRAD>(P, psi, lam, chead, list, nsl, d, tid);
+      else if (per <= 4) e_part = c_hphase<4, T, GRAD>(P, psi, lam, chead, list, nsl, d, tid);
+      else e_part = c_hphase<8, T, GRAD>(P, psi, lam, chead, list, nsl, d, tid);
     }
 #pragma unroll
     for (int off = TW / 2; off > 0; off >>= 1) e_part += shfl_xor_d(e_part, off, tmask);

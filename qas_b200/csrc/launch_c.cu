@@ -3,13 +3,13 @@
 #include "ctx.h"
 
 size_t qas_ccompile_smem_bytes(const qas_ctx *ctx, int ops_cap, int p) {
-  return qas_ccompile_smem_words(ctx->n, ops_cap, p) * 4 * 64;
+  return qas_ccompile_smem_words(ctx->n, ops_cap, p) * 4 * 64 + (size_t)ctx->c * sizeof(qas_pool_entry);
 }
 
 template <int NQ>
 static cudaError_t launch_compile_c_t(qas_ctx *ctx, const CompileCParams &P, cudaStream_t st) {
   constexpr int CT = 64;
-  const size_t smem = qas_ccompile_smem_words(ctx->n, P.ops_cap, P.p) * 4 * CT;
+  const size_t smem = qas_ccompile_smem_words(ctx->n, P.ops_cap, P.p) * 4 * CT + (size_t)P.c * sizeof(qas_pool_entry);
   cudaError_t e = cudaFuncSetAttribute(compile_ctapes_kernel<CT, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   compile_ctapes_kernel<CT, NQ><<<(P.B + CT - 1) / CT, CT, smem, st>>>(P);
@@ -46,9 +46,17 @@ int qas_evalc_team_threads(int slot_bits) { return slot_bits <= 8 ? 32 : slot_bi
 
 cudaError_t qas_launch_evalc(qas_ctx *ctx, const EvalCParams &P, int max_work, bool grad, cudaStream_t st) {
   const int T = qas_evalc_team_threads(P.slot_bits);
+  // QAS_B200_C_MINB (tuning knob, one-warp teams): CTAs per SM the register allocation is bounded for -- 4 (128
+  // registers, default), 6 (85) or 8 (64): more circuits in flight against spills in the two-gate adjoint pass
+  static const int minb32 = []() { const char *e = getenv("QAS_B200_C_MINB"); const int v = e ? atoi(e) : 4; return (v == 6 || v == 8) ? v : 4; }();
 #define QAS_CCASE(T_, BLK_, MINB_) \
-  if (T == T_) return grad ? launch_evalc_t<T_, true, BLK_, MINB_>(ctx, P, max_work, st) : launch_evalc_t<T_, false, BLK_, MINB_>(ctx, P, max_work, st);
-  QAS_CCASE(32, 128, 4) QAS_CCASE(64, 128, 4) QAS_CCASE(128, 128, 3) QAS_CCASE(256, 256, 1)
+  return grad ? launch_evalc_t<T_, true, BLK_, MINB_>(ctx, P, max_work, st) : launch_evalc_t<T_, false, BLK_, MINB_>(ctx, P, max_work, st);
+  if (T == 32 && minb32 == 6) { QAS_CCASE(32, 128, 6) }
+  if (T == 32 && minb32 == 8) { QAS_CCASE(32, 128, 8) }
+  if (T == 32) { QAS_CCASE(32, 128, 4) }
+  if (T == 64) { QAS_CCASE(64, 128, 4) }
+  if (T == 128) { QAS_CCASE(128, 128, 3) }
+  if (T == 256) { QAS_CCASE(256, 256, 1) }
 #undef QAS_CCASE
   return cudaErrorInvalidConfiguration;
 }

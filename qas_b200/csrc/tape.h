@@ -572,24 +572,30 @@ QAS_HD int qas_compress_tape(uint32_t *ops, int *nops_io, int *ngroups_io, int n
 //   * the echelon basis is kept in REDUCED form (every pivot bit occurs in its own vector only), so reducing a
 //     mask is one pass of independent select-xors over a register table of compile-time length NQ -- no
 //     data-dependent loop, no dynamic indexing -- and so are the dual masks r'_k = parity(B_k & r).
-// The caller has already written the ORIGINAL 5-word ops (with group marks) to the record; on success this
-// function overwrites them with the translated ops, on QAS_CT_FULL / QAS_CT_TOO_BIG it leaves the record alone.
+// On success the translated 5-word ops are written to the record (gops); on QAS_CT_FULL / QAS_CT_TOO_BIG nothing is
+// written and the packed ops are left half-translated: the caller compiles the circuit again and hands the grouped
+// original tape to the classic path (qas_unpack_ops).
 #define QAS_PK_WORDS 3
-struct QasPackedDualSink {        // tape-compiler sink: 5-word op to the record (global), packed copy to shared memory
-  uint32_t *gops;                 // record ops area
-  uint32_t *pk;                   // packed ops
+struct QasPk3Sink {            // tape-compiler sink: packed ops in shared memory
+  uint32_t *pk;
   int cap, n, overflow;
   QAS_HD void emit(uint32_t m, uint32_t r, uint32_t rc, uint32_t tab, uint32_t meta) {
     if (n >= cap) { overflow = 1; return; }
-    uint32_t *o = gops + (size_t)n * QAS_OP_WORDS;
-    o[0] = m; o[1] = r; o[2] = rc; o[3] = tab;       // o[4] follows once the groups are marked
     uint32_t *q = pk + (size_t)n * QAS_PK_WORDS;
     q[0] = m | (r << 16); q[1] = rc | (tab << 16); q[2] = meta;
     n++;
   }
 };
-// greedy grouping of qas_mark_groups on packed ops; writes the marked meta words to the record as well
-QAS_HD int qas_mark_groups_packed(uint32_t *pk, int nops, int gmax, uint32_t *gops) {
+// packed ops -> 5-word ops of a classic record (circuits the c-tape compiler leaves to the classic path)
+QAS_HD void qas_unpack_ops(const uint32_t *pk, int nops, uint32_t *gops) {
+  for (int j = 0; j < nops; ++j) {
+    const uint32_t *q = pk + (size_t)j * QAS_PK_WORDS;
+    uint32_t *o = gops + (size_t)j * QAS_OP_WORDS;
+    o[0] = q[0] & 0xffffu; o[1] = q[0] >> 16; o[2] = q[1] & 0xffffu; o[3] = q[1] >> 16; o[4] = q[2];
+  }
+}
+// greedy grouping of qas_mark_groups on packed ops
+QAS_HD int qas_mark_groups_packed(uint32_t *pk, int nops, int gmax) {
   int ngroups = 0;
   for (int j = 0; j < nops;) {
     uint32_t *a = pk + (size_t)j * QAS_PK_WORDS;
@@ -612,7 +618,6 @@ QAS_HD int qas_mark_groups_packed(uint32_t *pk, int nops, int gmax, uint32_t *go
     j += g;
     ++ngroups;
   }
-  for (int j = 0; j < nops; ++j) gops[(size_t)j * QAS_OP_WORDS + 4] = pk[(size_t)j * QAS_PK_WORDS + 2];
   return ngroups;
 }
 

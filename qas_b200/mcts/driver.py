@@ -246,38 +246,84 @@ def circuitModelTuning(initial_params=None, model=None, num_epochs: int = None, 
 
 
 def circuitModelTuningDevice(initial_params=None, model=None, num_epochs: int = None, k=None, op_pool=None, lr=0.01,
-                             grad_noise_factor=0.0, verbose=0, early_stop_threshold=1e-15, check_every=1, seed=None):
+                             grad_noise_factor=0.0, verbose=0, early_stop_threshold=1e-15, check_every=1, seed=None,
+                             use_graph=True):
     """circuitModelTuning (reference :381-412) with the whole loop on the GPU: the parameter tensor,
-    the Adam moments and the gradient never leave HBM; per epoch the host reads back one double (the
-    loss, every ``check_every`` epochs) for the early-stop test.  Noise, when requested, comes from
-    torch's CUDA generator (a different stream of random numbers than np.random.randn upstream).
-    Returns (theta as ndarray, losses)."""
+    the Adam moments, the gradient, the step counter and the loss history never leave HBM.
+
+    Without gradient noise (the default here) one epoch -- evaluation kernels, loss record, Adam step -- is
+    captured ONCE into a CUDA graph and replayed; the host only reads the losses back every ``check_every``
+    epochs for the early-stop test (``check_every=1`` reproduces the reference's stopping epoch exactly; a
+    larger value may run up to ``check_every - 1`` epochs past it).  With noise, or ``use_graph=False``, the
+    epochs are launched one by one (noise from torch's CUDA generator: a different stream of random numbers
+    than np.random.randn upstream).  Returns (theta as ndarray, losses)."""
+    import ctypes
     import torch
     from qas_b200.optim import DeviceAdam
     p, c, l = initial_params.shape
     ev = model.evaluator(op_pool, l)
     dev = torch.device("cuda", ev.device)
-    stream = torch.cuda.current_stream(dev)
     theta = torch.as_tensor(np.ascontiguousarray(initial_params, dtype=np.float64)).to(dev)
     d_k = torch.as_tensor(np.ascontiguousarray(np.asarray(k, dtype=np.int32)[None, :])).to(dev)
     d_e = torch.empty(1, dtype=torch.float64, device=dev)
     d_g = torch.empty(p, c, l, dtype=torch.float64, device=dev)
-    d_losses = torch.empty(num_epochs, dtype=torch.float64, device=dev)
+    d_losses = torch.zeros(max(1, num_epochs), dtype=torch.float64, device=dev)
+    opt = DeviceAdam(theta, stepsize=lr)
+    check_every = max(1, int(check_every))
+    if use_graph and not grad_noise_factor:
+        lib = ev._lib
+        d_t = torch.zeros(1, dtype=torch.int32, device=dev)
+        d_step = torch.zeros(1, dtype=torch.float64, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            ev.evaluate_device(d_k, theta, d_e, None, d_g, avg=True, stream=side)        # sizes every scratch buffer
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            cur = torch.cuda.current_stream(dev)
+            sp = ctypes.c_void_p(cur.cuda_stream)
+            ev.evaluate_device(d_k, theta, d_e, None, d_g, avg=True, stream=cur)
+            rc = lib.qas_tuning_tick(d_t.data_ptr(), d_step.data_ptr(), d_e.data_ptr(), d_losses.data_ptr(), num_epochs,
+                                     float(lr), opt.beta1, opt.beta2, sp)
+            assert rc == 0
+            rc = lib.qas_adam_step_dev(theta.data_ptr(), d_g.data_ptr(), opt.fm.data_ptr(), opt.sm.data_ptr(), theta.numel(),
+                                       d_step.data_ptr(), opt.beta1, opt.beta2, opt.eps, sp)
+            assert rc == 0
+        done, stop_at = 0, None
+        while done < num_epochs and stop_at is None:
+            burst = min(check_every, num_epochs - done)
+            for _ in range(burst):
+                graph.replay()
+            chunk = d_losses[done:done + burst].cpu().numpy()
+            done += burst
+            hit = np.nonzero(chunk <= early_stop_threshold)[0]
+            if len(hit):
+                stop_at = done - burst + int(hit[0]) + 1
+        kept = done if stop_at is None else stop_at
+        if stop_at is not None and verbose:
+            print("early stop at epoch %d" % stop_at)
+        losses = [float(x) for x in d_losses[:kept].cpu().numpy()]
+        return theta.cpu().numpy(), losses
+    stream = torch.cuda.current_stream(dev)
     gen = None
     if grad_noise_factor:
         gen = torch.Generator(device=dev)
         gen.manual_seed(0 if seed is None else int(seed))
-    opt = DeviceAdam(theta, stepsize=lr)
-    done = 0
+    done, stop_at = 0, None
     for epoch in range(num_epochs):
         ev.evaluate_device(d_k, theta, d_e, None, d_g, avg=True, stream=stream)
         d_losses[epoch:epoch + 1].copy_(d_e)
         noise = torch.randn(p, c, l, dtype=torch.float64, device=dev, generator=gen) if gen is not None else None
         opt.step(d_g, noise, grad_noise_factor, stream)
         done = epoch + 1
-        if (epoch + 1) % check_every == 0 and float(d_e.item()) <= early_stop_threshold:
-            if verbose:
-                print("early stop at epoch %d" % (epoch + 1))
-            break
-    losses = [float(x) for x in d_losses[:done].cpu().numpy()]
+        if done % check_every == 0 or done == num_epochs:
+            lo = done - ((done - 1) % check_every + 1)
+            hit = np.nonzero(d_losses[lo:done].cpu().numpy() <= early_stop_threshold)[0]
+            if len(hit):
+                stop_at = lo + int(hit[0]) + 1
+                if verbose:
+                    print("early stop at epoch %d" % stop_at)
+                break
+    losses = [float(x) for x in d_losses[:(done if stop_at is None else stop_at)].cpu().numpy()]
     return theta.cpu().numpy(), losses

@@ -308,6 +308,7 @@ def test_support_restricted_path_with_the_full_gate_vocabulary(monkeypatch):
 def _eval_both_paths(monkeypatch, n, terms, pool, init, cases, B):
     """The same batches through the support-compressed path (default) and the classic path (QAS_B200_COMPRESS=0)."""
     outs = {}
+    monkeypatch.setenv("QAS_B200_COMPRESS_MIN_N", "7")       # by default registers below 9 qubits keep the classic path
     for flag in ("0", "1"):
         monkeypatch.setenv("QAS_B200_COMPRESS", flag)
         ev = BatchEvaluator(n, terms, pool, init=init)
@@ -338,7 +339,7 @@ def test_support_compressed_path_equals_classic_and_oracle(cfg, monkeypatch):
         params = np.random.default_rng(seed).standard_normal((depth, len(pool), 3))
         cases.append((sample_structure_lists(pool, depth, {"CNOT": depth // 2}, B, seed=seed), params))
     outs = _eval_both_paths(monkeypatch, n, model.terms(), pool, model.init_state, cases, B)
-    assert outs["1"][1] == 3 and outs["0"][1] == 0           # the compressed kernel really ran
+    assert outs["1"][1] == 3 and outs["0"][1] == 0           # the compressed kernel really ran (min-n knob for 8 qubits)
     for (ks, params), a, b in zip(cases, outs["0"][0], outs["1"][0]):
         assert np.max(np.abs(a[0]["energy"] - b[0]["energy"])) <= 1e-12
         assert np.max(np.abs(a[0]["grad_compact"] - b[0]["grad_compact"])) <= 1e-12
@@ -546,24 +547,35 @@ def test_device_adam_step_matches_numpy_rule():
         assert np.max(np.abs(xd.cpu().numpy() - xh)) <= 1e-13 * max(1.0, np.max(np.abs(xh)))
 
 
-def test_device_tuning_loop_matches_host_loop():
-    """circuitModelTuningDevice (loop resident on the GPU) follows the host loop of
-    circuitModelTuning (reference mcts.py:381-412) step for step when no noise is injected."""
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_device_tuning_loop_matches_host_loop(use_graph):
+    """circuitModelTuningDevice (loop resident on the GPU; one epoch captured into a CUDA graph and replayed, or
+    launched epoch by epoch) follows the host loop of circuitModelTuning (reference mcts.py:381-412) step for
+    step when no noise is injected -- 4 qubits (thread-per-circuit kernel) and LiH-10q (binned compressed path,
+    forked streams inside the captured graph)."""
     from qas_b200.mcts.mcts import circuitModelTuning, circuitModelTuningDevice
-    from qas_b200.qml_models.qml_models_legacy import FourQubitH2
-    pool = helpers.near_cx_pool(4)
-    c = len(pool)
-    p = 8
-    k = [0, 2, 8, 4, 6, 10, 3, 12]
-    params = np.random.default_rng(11).standard_normal((p, c, 3))
-    th_h, loss_h = circuitModelTuning(params, FourQubitH2, 12, k, pool, lr=0.05, grad_noise_factor=0.0, verbose=0,
-                                      early_stop_threshold=-1e9)
-    th_d, loss_d = circuitModelTuningDevice(params, FourQubitH2, 12, k, pool, lr=0.05, grad_noise_factor=0.0,
-                                            early_stop_threshold=-1e9)
-    assert len(loss_h) == len(loss_d) == 12
-    assert np.max(np.abs(np.array(loss_h) - np.array(loss_d))) <= 1e-9
-    assert np.max(np.abs(th_h - th_d)) <= 1e-9
-    assert loss_d[-1] < loss_d[0]
+    from qas_b200.qml_models.qml_models_legacy import FourQubitH2, LiH
+    for model, n, p, k, epochs in ((FourQubitH2, 4, 8, [0, 2, 8, 4, 6, 10, 3, 12], 12),
+                                   (LiH, 10, 10, None, 40)):
+        pool = helpers.near_cx_pool(n)
+        c = len(pool)
+        if k is None:
+            k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": 5}, 1, seed=2)[0]]
+        params = np.random.default_rng(11).standard_normal((p, c, 3))
+        th_h, loss_h = circuitModelTuning(params, model, epochs, k, pool, lr=0.05, grad_noise_factor=0.0, verbose=0,
+                                          early_stop_threshold=-1e9)
+        th_d, loss_d = circuitModelTuningDevice(params, model, epochs, k, pool, lr=0.05, grad_noise_factor=0.0,
+                                                early_stop_threshold=-1e9, use_graph=use_graph, check_every=7)
+        assert len(loss_h) == len(loss_d) == epochs
+        assert np.max(np.abs(np.array(loss_h) - np.array(loss_d))) <= 1e-9
+        assert np.max(np.abs(th_h - th_d)) <= 1e-9
+        assert loss_d[-1] < loss_d[0]
+    # early stop: the graph loop reports the reference's stopping epoch
+    thr = loss_h[5]
+    _, l_stop = circuitModelTuningDevice(params, model, epochs, k, pool, lr=0.05, early_stop_threshold=thr,
+                                         use_graph=use_graph, check_every=4)
+    first = int(np.nonzero(np.array(loss_h) <= thr)[0][0]) + 1
+    assert len(l_stop) == first and np.max(np.abs(np.array(l_stop) - np.array(loss_h[:first]))) <= 1e-9
 
 
 def test_native_tree_with_resident_parameters_on_gpu():
@@ -595,3 +607,33 @@ def test_native_tree_with_resident_parameters_on_gpu():
     assert abs(leaf2.reward + sim.energy(4, k2, pool.pool, params, terms, FourQubitH2.init_state)) <= E_TOL
     assert ctl.stats()["reward_evaluations"] < ctl.stats()["reward_requests"]
     ctl.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# property test (hypothesis): random registers, start states, depths and legal structure lists, kernel vs oracle
+from hypothesis import HealthCheck, given, settings, strategies as st_
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(n=st_.integers(2, 11), p=st_.integers(1, 16), seed=st_.integers(0, 10 ** 6), init_kind=st_.sampled_from(["zero", "basis", "plus"]),
+       B=st_.sampled_from([1, 7, 40]))
+def test_property_random_legal_structure_lists_match_oracle(n, p, seed, init_kind, B):
+    """Whatever the register size (thread-per-circuit, team, compressed kernels), start state, depth and batch size
+    (host- and device-compiled tapes): energies and every derivative equal the oracle's."""
+    rng = np.random.default_rng(seed)
+    pool = helpers.near_cx_pool(n)
+    c = len(pool)
+    init = (init_kind, int(rng.integers(0, 1 << n)) if init_kind == "basis" else 0)
+    words = ["".join(rng.choice(list("IXYZ"), size=n, p=[.4, .2, .2, .2])) for _ in range(6)] + ["I" * n]
+    terms = [(float(rng.standard_normal()), w) for w in words]
+    ks = sample_structure_lists(pool, p, {"CNOT": max(1, p // 2)}, B, seed=seed)
+    params = rng.standard_normal((p, c, 3))
+    ev = BatchEvaluator(n, terms, pool, init=init)
+    out = ev.evaluate(ks, params, want_grad=True, dense=True, compact=True)
+    ev.close()
+    for b in sorted({0, B // 2, B - 1}):
+        k = [int(x) for x in ks[b]]
+        assert abs(out["energy"][b] - sim.energy(n, k, pool.pool, params, terms, init)) <= E_TOL
+        g = sim.grad_adjoint(n, k, pool.pool, params, terms, init)
+        for i, key in enumerate(k):
+            assert np.max(np.abs(out["grad_compact"][b, i] - g[i, key])) <= G_TOL

@@ -401,3 +401,42 @@ def test_ctape_device_formulation_matches_reference_formulation():
         assert np.array_equal(a["ops"], b["ops"])
         assert a["basis"] == b["basis"] and a["slices"] == b["slices"]
     assert CT.CT_TOO_BIG in seen and len([d for d in seen if d >= 0]) >= 5
+
+
+# ------------------------------------------------------------------------------------------------
+# property tests (hypothesis): random registers, pools, depths and structure lists
+from hypothesis import HealthCheck, given, settings, strategies as st_
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(n=st_.integers(3, 8), p=st_.integers(1, 14), seed=st_.integers(0, 10 ** 6), vocab=st_.booleans())
+def test_property_tape_paths_agree_with_oracle(n, p, seed, vocab):
+    """For any register size, depth and (legal or arbitrary) structure list from the all-zero state: classic tape +
+    kernel algorithm == c-tape (both formulations, bit-identical records) + compressed kernel algorithm == oracle."""
+    import ctape_interp as CT
+    rng = np.random.default_rng(seed)
+    pool = helpers.full_vocab_pool(n) if (vocab and n <= 5) else helpers.near_cx_pool(n)
+    c = len(pool)
+    if vocab and n <= 5:
+        k = [int(x) for x in rng.integers(0, c, size=p)]
+    else:
+        k = [int(x) for x in sample_structure_lists(pool, p, {"CNOT": max(1, p // 2)}, 1, seed=seed)[0]]
+    params = rng.standard_normal((p, c, 3))
+    words = ["".join(rng.choice(list("IXYZ"), size=n)) for _ in range(5)] + ["I" * n]
+    terms = [(float(rng.standard_normal()), w) for w in words]
+    e_ref = sim.energy(n, k, pool.pool, params, terms, ("zero", 0))
+    g_ref = sim.grad_adjoint(n, k, pool.pool, params, terms, ("zero", 0))
+    ops, idx = compile_tape_host(n, pool, k, 0)
+    e1, gr1 = TI.run_tape(n, ops, ("zero", 0), idx, pool.pool, c, params, terms)
+    assert abs(e1 - e_ref) < 1e-10
+    xs, imag, V = CT.sign_tables(n, terms)
+    a = CT.compile_ctape(n, pool, k, xs, variant=0)
+    b = CT.compile_ctape(n, pool, k, xs, variant=1)
+    assert a["d"] == b["d"] and np.array_equal(a["ops"], b["ops"]) and a["slices"] == b["slices"] and a["basis"] == b["basis"]
+    if a["d"] >= 0:
+        e2, gr2 = CT.run_ctape(a, n, pool.pool, c, params, xs, imag, V)
+        assert abs(e2 - e_ref) < 1e-10
+        got = np.zeros_like(g_ref)
+        for (dd, j), v in gr2.items():
+            got[dd, k[dd], j] = v
+        assert np.max(np.abs(got - g_ref)) < 1e-9

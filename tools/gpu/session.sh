@@ -35,10 +35,11 @@ for step in "$@"; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/$name.csv" \
         python bench.py --workload "$a" --steps 2 --warmup 3 --tune > "$out/$name.log" 2>&1
       echo "rc=$?" | tee -a "$out/steps.log"; python tools/launch_table.py "$out/$name.csv" | tail -25 ;;
-    ncu)
-      timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$b" -s 6 -c 1 -o "$out/$name" -f \
-        python bench.py --workload "$a" --steps 2 --warmup 3 --tune > "$out/$name.log" 2>&1
-      echo "rc=$?" | tee -a "$out/steps.log" ;;
+    ncu)     # ncu:<workload>:<kernel base name>:<launches to skip>
+      IFS=: read -r _k _w kname skip <<< "$step"
+      timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$kname" -s "${skip:-6}" -c 1 -o "$out/$name" -f \
+        python bench.py --workload "$_w" --steps 2 --warmup 3 --tune --no-others > "$out/$name.log" 2>&1
+      echo "rc=$?" | tee -a "$out/steps.log"; python tools/ncu_summary.py "$out/$name.ncu-rep" > "$out/$name.txt" 2>&1; head -60 "$out/$name.txt" ;;
     phases)
       timeout 300 python tools/phase_clocks.py --workload "$a" > "$out/$name.txt" 2>&1
       echo "rc=$?" | tee -a "$out/steps.log"; tail -40 "$out/$name.txt" ;;
