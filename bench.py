@@ -713,7 +713,7 @@ def run_search_epoch(args):
         def toList(self, params):
             return []
 
-    def epochs(mdl, n_warm, n_search, wbs, native):
+    def epochs(mdl, n_warm, n_search, wbs, native, leaves=1):
         driver.USE_NATIVE_TREE = native
         np.random.seed(args.seed)
         random.seed(args.seed)
@@ -727,12 +727,14 @@ def run_search_epoch(args):
                    gate_limit_dict={"CNOT": cx_lim}, warmup_arc_batchsize=wbs, search_arc_batchsize=bs, alpha_max=2,
                    alpha_decay_rate=0.99, prune_constant_max=0.99, prune_constant_min=0.80,
                    max_visits_prune_threshold=20, min_num_children=c // 2 + 1, sampling_execute_rounds=rs,
-                   exploit_execute_rounds=re_, verbose=1, state_class=QMLStateBasicGates, search_reset=True)
+                   exploit_execute_rounds=re_, verbose=1, state_class=QMLStateBasicGates, search_reset=True,
+                   leaf_parallel=leaves)
         secs = [float(x) for x in re.findall(r"\| ([0-9.]+) s", buf.getvalue())]
         return secs[:n_warm], secs[n_warm:]
 
     epochs(model, 1, 1, warm_bs, True)                       # first-call costs (context, tables)
     gw, gs = epochs(model, 2, 3, warm_bs, True)              # native tree policy (C++), rewards resident on the GPU
+    lw, ls = epochs(model, 2, 3, warm_bs, True, args.leaves)  # ... with leaf-parallel rounds under a virtual loss (opt-in)
     pw, ps = epochs(model, 2, 3, warm_bs, False)             # the reference's tree policy in Python, GPU rewards
     cpu_wbs = max(10, warm_bs // 10)
     cw, cs = epochs(RefPatternModel, 1, 1, cpu_wbs, False)   # CPU: a tenth of the warm-up batch, scaled below
@@ -741,6 +743,8 @@ def run_search_epoch(args):
             "config": {"workload": name, "model": mname, "depth_p": p, "search_arc_batchsize": bs, "sampling_rounds": rs,
                        "exploit_rounds": re_, "warmup_arc_batchsize": warm_bs, "source": "search-scripts-legacy/" + WORKLOADS[name][7]},
             "b200": {"warmup_epoch_s": min(gw), "search_epoch_s": statistics.median(gs), "tree": "native (libqas_b200 qas_mcts_*)"},
+            "b200_leaf_parallel": {"warmup_epoch_s": min(lw), "search_epoch_s": statistics.median(ls), "leaves_per_wave": args.leaves,
+                                   "note": "opt-in, not semantics-preserving (virtual loss); final energies over 20 seeds: tools/leaf_parallel_study.py"},
             "b200_python_tree": {"warmup_epoch_s": min(pw), "search_epoch_s": statistics.median(ps)},
             "cpu_reference_pattern": {"warmup_epoch_s_scaled": cw[0] * warm_bs / cpu_wbs, "search_epoch_s": cs[0], "cores": 1,
                                       "note": "oracle in the reference call pattern (%s gradient); warm-up epoch run with %d "
@@ -838,6 +842,7 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads block of the default line")
     ap.add_argument("--compact", action="store_true", help="also write the per-circuit compact gradients [B][p][l] in the timed step")
     ap.add_argument("--search-epoch", action="store_true", help="time whole search() epochs instead (SURVEY 8d)")
+    ap.add_argument("--leaves", type=int, default=8, help="--search-epoch: selection rounds per wave of the leaf-parallel mode")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 600 if (args.impl == "b200" and not args.search_epoch) else 10

@@ -578,8 +578,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   // compressed kernel of its bin, d == n stays with the classic kernel (the full bin)
   const bool use_c = ctx->compress && !small && qas_ccompile_smem_bytes(ctx, ops_cap, p) <= 96 * 1024 &&
                      (size_t)QAS_NCONST + (size_t)p * c <= 65535;
-  const bool fused_reduce = grad_dense && !grad_compact && !small;   // batch mean only: no per-circuit gradients
-  if (want_grad && !fused_reduce && (!dev || !grad_compact)) {
+  if (want_grad && (!dev || !grad_compact)) {
     CK(ensure(&ctx->d_grad, &ctx->cap_grad, ng));
     dgrad = ctx->d_grad;
   }
@@ -626,7 +625,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   };
   if (!dev && !tiny && !capturing) CK(cudaEventRecord(ctx->ev0, st));
   stamp(0);
-  if (want_grad && !fused_reduce) { CK(cudaMemsetAsync(dgrad, 0, ng * 8, st)); ctx->stats.launches += 1; }
+  if (want_grad) { CK(cudaMemsetAsync(dgrad, 0, ng * 8, st)); ctx->stats.launches += 1; }
   if (!small) CK(cudaMemsetAsync(ctx->d_bins, 0, sizeof(int) * 2 * QAS_MAX_BINS, st));   // bin counts + work-queue heads
   stamp(1);
   // Tiny host-pointer batches (the one-reward-at-a-time rollouts of the tree search): the tape
@@ -653,6 +652,9 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     }
     uint32_t col[32], row[32], ev[32], ec[32];
     std::vector<uint32_t> mt((size_t)ops_cap);
+    // a handful of circuits: ONE compressed launch sized for the largest support among them (the kernel's loops
+    // follow every circuit's own d), instead of one launch per bin
+    int hd_[16], dmax_ = 0;
     for (int b = 0; b < B; ++b) {
       uint32_t *rec = ctx->h_tape + (size_t)b * rec_words;
       uint32_t *rops = rec + QAS_REC_HDR, *rci = rops + (size_t)ops_cap * QAS_OP_WORDS;
@@ -672,8 +674,13 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
         qas_plan_marked(rops, nops, ngroups, ctx->n, ctx->init_kind, init_index, rci, swz_plan, &ctx->hinfo,
                         rec + qas_rec_hd_offset(ops_cap, ctx->n));
       }
-      if (use_c) {
-        const int bin = d >= 0 ? std::max(d, ctx->c_dmin) - ctx->c_dmin : ctx->c_nbins;
+      hd_[b] = d;
+      if (d > dmax_) dmax_ = d;
+    }
+    if (use_c) {
+      const int cbin = std::max(dmax_, ctx->c_dmin) - ctx->c_dmin;
+      for (int b = 0; b < B; ++b) {
+        const int bin = hd_[b] >= 0 ? cbin : ctx->c_nbins;
         ctx->h_bins[QAS_MAX_BINS + (size_t)bin * B + h_count[bin]++] = b;
       }
     }
@@ -713,7 +720,8 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     // persistent CTAs of a small bin fill the tail of a large one.  Host-compiled batches launch the non-empty
     // bins back to back on the call's stream.
     EvalCParams Q{};
-    Q.tape = ctx->d_tape; Q.U = ctx->d_U; Q.vflat = ctx->d_vflat; Q.sinfo = ctx->d_sinfo; Q.slut = ctx->d_slut; Q.energy = denergy; Q.mout = P.mout;
+    Q.tape = ctx->d_tape; Q.U = ctx->d_U; Q.vflat = ctx->d_vflat; Q.sinfo = ctx->d_sinfo; Q.slut = ctx->d_slut; Q.energy = denergy;
+    Q.dU = ctx->d_dU; Q.grad = dgrad; Q.p = p; Q.l = l;
     Q.rec_stride = rec_words; Q.n = ctx->n; Q.ops_cap = ops_cap; Q.S = ctx->S_flat; Q.S_real = ctx->S_real_flat;
     const bool fork = !host_compile;
     if (fork) CK(cudaEventRecord(ctx->fork_ev, st));
@@ -743,6 +751,13 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
         const cudaError_t le = launch_classic(s_);
         P.B = keepB;
         CK(le);
+        if (want_grad) {     // cross matrices of the full bin's circuits -> compact gradients, on the same stream
+          const size_t nthr = (size_t)max_work * ops_cap;
+          grad_finalize_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, s_>>>(ctx->d_tape, rec_words, ctx->d_mout, ctx->d_dU, max_work, p, l,
+                                                                              ops_cap, dgrad, P.order, P.count);
+          CK(cudaGetLastError());
+          ctx->stats.launches += 1;
+        }
       } else {
         Q.slot_bits = ctx->c_dmin + bin;
         Q.order = ctx->d_order + (size_t)bin * B;
@@ -761,22 +776,16 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   }
   if (!tiny && !capturing) { CK(cudaEventRecord(ctx->ek1, st)); ctx->ek_pending = true; }
   stamp(4);
-  if (want_grad && !small && !fused_reduce) {
+  if (want_grad && !small && !use_c) {
     const size_t nthr = (size_t)B * ops_cap;
     grad_finalize_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ctx->d_tape, rec_words, ctx->d_mout, ctx->d_dU, B, p, l,
-                                                                        ops_cap, dgrad);
+                                                                        ops_cap, dgrad, nullptr, nullptr);
     CK(cudaGetLastError());
     ctx->stats.launches += 1;
   }
   stamp(5);
 
-  if (fused_reduce) {
-    const double scale = (flags & QAS_F_GRAD_SUM) ? 1.0 : 1.0 / (double)B;
-    CK(qas_launch_finalize_reduce(ctx, ctx->d_tape, rec_words, ctx->d_mout, B, p, ops_cap, scale, ddense, st));
-    ctx->stats.launches += 2;
-    stamp(6);
-    stamp(7);
-  } else if (grad_dense) {
+  if (grad_dense) {
     int chunk = 64;            // circuits per CTA of the first stage (1024 CTAs at B = 65536)
     if (const char *ce = getenv("QAS_B200_REDUCE_CHUNK")) chunk = std::max(1, atoi(ce));   // tuning knob
     const int nchunks = (B + chunk - 1) / chunk;

@@ -118,5 +118,3 @@ cudaError_t qas_launch_compile_c(qas_ctx *ctx, const CompileCParams &P, cudaStre
 cudaError_t qas_launch_plan_full(qas_ctx *ctx, uint32_t *tape, size_t rec_stride, const int *count, const int *order, int B,
                                  int ops_cap, int swizzled, cudaStream_t st);
 cudaError_t qas_launch_evalc(qas_ctx *ctx, const EvalCParams &P, int max_work, bool grad, cudaStream_t st);
-cudaError_t qas_launch_finalize_reduce(qas_ctx *ctx, const uint32_t *tape, size_t rec_stride, const double *mout, int B, int p,
-                                       int ops_cap, double scale, double *dense, cudaStream_t st);

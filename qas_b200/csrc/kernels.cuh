@@ -1064,11 +1064,14 @@ __global__ void __launch_bounds__(BLK) eval_small_kernel(const EvalParams P) {
 // dE/dtheta_j = 2 Re sum_ab (dU_j)_ab M_ab for every parametrised op of every circuit: one thread
 // per (circuit, tape op), all of its <= 3 parameter slots.  Kept out of the evaluation kernel so that no team
 // waits on the dU table (L2 latency) between passes.  grad must be zero-filled beforehand.
+// order / count: the circuits the classic kernel evaluated (the full bin of a binned call), or null for all B.
 static __global__ void grad_finalize_kernel(const uint32_t *tape, size_t rec_stride, const double *mout, const GateDTab *dU, int B,
-                                     int p, int l, int ops_cap, double *grad) {
+                                     int p, int l, int ops_cap, double *grad, const int *order, const int *count) {
   const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= (size_t)B * ops_cap) return;
-  const int b = (int)(x / ops_cap), oi = (int)(x % ops_cap);
+  const int qi = (int)(x / ops_cap), oi = (int)(x % ops_cap);
+  if (count && qi >= *count) return;
+  const int b = order ? order[qi] : qi;
   const uint32_t *rec = tape + (size_t)b * rec_stride;
   if (oi >= (int)rec[0] || rec[1]) return;
   const uint32_t *o = rec + QAS_REC_HDR + (size_t)oi * QAS_OP_WORDS;

@@ -106,7 +106,9 @@ struct EvalCParams {
   const int *count;            // ... and how many
   int *work_counter;           // this bin's queue head (zeroed before the launch)
   double *energy;              // [B]
-  double *mout;                // [B][ops_cap][8]
+  const GateDTab *dU;          // [NCONST + p*c] dU/dtheta table (gradient launches)
+  double *grad;                // [B][p][l] compact gradients, zero-filled beforehand (gradient launches)
+  int p, l;
   unsigned long long *phase_clk;   // diagnostic: summed per-team clock64 deltas [prologue, forward, H, adjoint] at +4*.. or null
   size_t rec_stride;
   int n, ops_cap, S, S_real, slot_bits;
@@ -119,6 +121,7 @@ __host__ __device__ inline size_t evalc_team_smem_bytes(int slot_bits, int T, bo
   b += 16 * 4;                                         // nsl + basis (<= QAS_CT_MAX_D words)
   b += (((size_t)S * 4) + 15) & ~(size_t)15;           // slice list
   b += (size_t)ops_cap * 64;                           // staged gate matrices
+  if (grad) b += (size_t)ops_cap * 64;                 // cross matrices M of the circuit's ops
   if (grad && wpt > 1) b += (size_t)2 * 2 * wpt * 64;  // cross-matrix ring (two buffers, <= 2 gates per pass)
   b += (((size_t)wpt * 8) + 15) & ~(size_t)15;
   b += 16;                                             // the team's work-queue slot
@@ -338,6 +341,8 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
   base += (((size_t)P.S * 4) + 15) & ~(size_t)15;
   double2 *Us = reinterpret_cast<double2 *>(base);
   base += (size_t)P.ops_cap * 64;
+  double *Ms = reinterpret_cast<double *>(base);                 // [ops_cap][8] (GRAD)
+  if constexpr (GRAD) base += (size_t)P.ops_cap * 64;
   double *red = nullptr;
   if constexpr (GRAD && WPT > 1) { red = reinterpret_cast<double *>(base); base += (size_t)2 * 2 * WPT * 64; }
   double *ered = reinterpret_cast<double *>(base);
@@ -426,7 +431,7 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
         const int g = (int)QAS_META_GFIRST(o[4]);
         const int dj = (int)QAS_META_DJ(o[4]);
         double *ring = WPT > 1 ? red + (size_t)(it & 1) * 2 * WPT * 8 : nullptr;
-        double *mop = P.mout + ((size_t)b * P.ops_cap + j) * 8;
+        double *mop = Ms + (size_t)j * 8;
         if (qas_meta_kind(o[4]) == QAS_K_U1) {
           if (g == 2) c_adj_group<2, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
           else c_adj_group<1, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
@@ -467,84 +472,30 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
         }
         j += g;
       }
+      // dE/dtheta_j = 2 Re sum_ab (dU_j)_ab M_ab for every parametrised op: one lane per op, all the dU loads of
+      // the circuit in flight together (one L2 round trip per circuit), straight into the compact gradient
+      for (int oi = tid; oi < nops; oi += T) {
+        const uint32_t *o = ops + (size_t)oi * QAS_OP_WORDS;
+        const int npar = min(qas_meta_npar(o[4]), P.l);
+        if (!npar) continue;
+        const double2 *mp = reinterpret_cast<const double2 *>(Ms + (size_t)oi * 8);
+        double2 m[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m[q] = mp[q];
+        double *gout = P.grad + ((size_t)b * P.p + qas_meta_depth(o[4])) * P.l;
+        const GateDTab *dt = P.dU + o[3];
+        for (int jj = 0; jj < npar; ++jj) {
+          double part = 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double2 dq = dt->d[jj][q];
+            part += dq.x * m[q].x - dq.y * m[q].y;
+          }
+          gout[jj] = 2.0 * part;
+        }
+      }
     }
     if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 3, (unsigned long long)(c_ - clk_prev)); atomicAdd(P.phase_clk + 4, 1ull); }
     team_sync<T>(team, tmask);   // state buffers are reused by the next circuit of this team
-  }
-}
-
-// ------------------------------------------------------------------------------ fused finalize + reduce
-// When the caller only wants the batch mean of the dense gradient (search(), qas/mcts/mcts.py:340-347),
-// the per-circuit compact gradients never need to exist: one CTA per chunk of circuits contracts the
-// cross matrices with dU/dtheta and accumulates straight into the dense (depth, key, slot) layout --
-// the table index of an op IS its (depth, key).  Thread (op slot, j) walks the chunk's circuits in order
-// (deterministic); ops of one circuit sit at distinct depths, so there are no collisions inside a
-// circuit, and __syncthreads separates the circuits.  partial[chunk][p*c*l] feeds grad_final_reduce_kernel.
-static __global__ void grad_finalize_reduce_kernel(const uint32_t *tape, size_t rec_stride, const double *mout,
-                                            const GateDTab *dU, int B, int p, int c, int l, int ops_cap,
-                                            int chunk, int depth_tile, double *partial) {
-  extern __shared__ double acc_all[];             // [warps][depth_tile][c][l]
-  const int depth0 = blockIdx.y * depth_tile;
-  const int nd = min(depth_tile, p - depth0);
-  const int nw = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int words = nd * c * l;
-  for (int x = threadIdx.x; x < words * nw; x += blockDim.x) acc_all[x] = 0.0;
-  __syncthreads();
-  double *acc = acc_all + (size_t)wid * words;
-  const int b_lo = blockIdx.x * chunk, b_hi = min(B, b_lo + chunk);
-  // Warp w takes the chunk's circuits b_lo + 4 (w + nw i) + s, s = 0..3: four circuits at a time, eight lanes each
-  // (lane = 8 s + op slot), so that four circuits' record / cross-matrix / dU loads are in flight together; the
-  // contributions are then added one circuit after the other, in circuit order -- the summation order of every
-  // accumulator depends only on (B, chunk), never on scheduling.  Ops of one circuit sit at distinct depths.
-  const int sub = lane >> 3, slot = lane & 7;
-  for (int b0 = b_lo + 4 * wid; b0 < b_hi; b0 += 4 * nw) {
-    const int b = b0 + sub;
-    const bool live = b < b_hi;
-    const uint32_t *rec = tape + (size_t)(live ? b : b_lo) * rec_stride;
-    const int nops = (live && !rec[1]) ? (int)rec[0] : 0;
-    int nmax = nops;
-#pragma unroll
-    for (int off = 8; off < 32; off <<= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, off));
-    for (int o0 = 0; o0 < nmax; o0 += 8) {
-      const int oi = o0 + slot;
-      double g[3] = {0.0, 0.0, 0.0};
-      int npar = 0;
-      double *a = acc;
-      if (oi < nops) {
-        const uint32_t *o = rec + QAS_REC_HDR + (size_t)oi * QAS_OP_WORDS;
-        const uint32_t mt = o[4], tab = o[3];
-        const int depth = qas_meta_depth(mt);
-        npar = min(qas_meta_npar(mt), l);
-        if (depth < depth0 || depth >= depth0 + nd) npar = 0;
-        if (npar) {
-          const double2 *mp = reinterpret_cast<const double2 *>(mout + ((size_t)b * ops_cap + oi) * 8);
-          double2 m[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) m[q] = mp[q];
-          a = acc + ((size_t)(depth - depth0) * c + (int)((tab - QAS_NCONST) % (uint32_t)c)) * l;
-          for (int jj = 0; jj < npar; ++jj) {
-            const double2 *dd = dU[tab].d[jj];
-            double part = 0.0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) part += dd[q].x * m[q].x - dd[q].y * m[q].y;
-            g[jj] = nan_to_num_d(2.0 * part);
-          }
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        if (sub == s)
-          for (int jj = 0; jj < npar; ++jj) a[jj] += g[jj];
-        __syncwarp();
-      }
-    }
-  }
-  __syncthreads();
-  // fixed-order sum of the warps' copies
-  double *out = partial + ((size_t)blockIdx.x * p + depth0) * c * l;
-  for (int x = threadIdx.x; x < words; x += blockDim.x) {
-    double v = 0.0;
-    for (int w = 0; w < nw; ++w) v += acc_all[(size_t)w * words + x];
-    out[x] = v;
   }
 }

@@ -60,25 +60,3 @@ cudaError_t qas_launch_evalc(qas_ctx *ctx, const EvalCParams &P, int max_work, b
 #undef QAS_CCASE
   return cudaErrorInvalidConfiguration;
 }
-
-cudaError_t qas_launch_finalize_reduce(qas_ctx *ctx, const uint32_t *tape, size_t rec_stride, const double *mout, int B, int p,
-                                       int ops_cap, double scale, double *dense, cudaStream_t st) {
-  const int c = ctx->c, l = ctx->l;
-  const size_t npar = (size_t)p * c * l;
-  const int nw = 4, chunk = 64;
-  const int nchunks = (B + chunk - 1) / chunk;
-  int depth_tile = p;
-  while ((size_t)depth_tile * c * l * 8 * nw > 96 * 1024 && depth_tile > 1) depth_tile = (depth_tile + 1) / 2;
-  const size_t sm = (size_t)depth_tile * c * l * 8 * nw;
-  cudaError_t e = ensure(&ctx->d_partial, &ctx->cap_partial, (size_t)nchunks * npar);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(grad_finalize_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  if (e != cudaSuccess) return e;
-  dim3 grid(nchunks, (p + depth_tile - 1) / depth_tile);
-  grad_finalize_reduce_kernel<<<grid, nw * 32, sm, st>>>(tape, rec_stride, mout, ctx->d_dU, B, p, c, l, ops_cap, chunk, depth_tile,
-                                                        ctx->d_partial);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  grad_final_reduce_kernel<<<(unsigned)((npar * 32 + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, npar, scale, dense);
-  return cudaGetLastError();
-}

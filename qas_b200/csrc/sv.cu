@@ -194,118 +194,51 @@ __device__ __forceinline__ void sv_tma_store_5d(const void *tmap, const void *sr
 }
 __device__ __forceinline__ void sv_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Persistent CTAs, one tile at a time.  Tile element j (kb bits) lives at slab index base | spread(j): the low c
-// bits are contiguous (coalesced 16*2^c-byte runs), the others are scattered by offs[].
-// TMA = true: the tile is fetched by cp.async.bulk.tensor from a 5-d tensor map of the slab (one box per
-// combination of the tile bits beyond its first two runs of consecutive positions), completion on an mbarrier,
-// shared-memory layout = the TMA 128-byte swizzle; a pass that ends with the identity frame is written back with
-// cp.async.bulk.tensor as well, a framed pass by the threads (the frame is undone by the store addresses).
-// TMA = false: cp.async staging with the fold-all swizzle (tiles the tensor map cannot describe, test sizes).
-// dynamic shared memory: tile [2^kb] double2 (1024-byte aligned for the TMA swizzle)
-template <int MINB, bool TMA>
-__global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBlockParams P, const __grid_constant__ CUtensorMap tmap) {
-  extern __shared__ __align__(1024) double2 tile[];
-  __shared__ unsigned long long offs[1 << 8];
-  __shared__ unsigned long long s_base;
-  __shared__ __align__(8) unsigned long long s_mbar;
-  const int kb = P.kb, c = P.c;
-  const uint32_t tsize = 1u << kb, nhi = 1u << (kb - c), lowmask = (1u << c) - 1u;
-  for (uint32_t h = threadIdx.x; h < nhi; h += SV_THREADS) {
-    unsigned long long o = 0;
-    for (int q = c; q < kb; ++q) o |= (unsigned long long)((h >> (q - c)) & 1u) << P.bits[q];
-    offs[h] = o;
-  }
-  if constexpr (TMA) {
-    if (threadIdx.x == 0) sv_mbar_init(&s_mbar, 1);
-  }
-  uint32_t phase = 0;
-  const unsigned long long ntiles = 1ull << (P.n_local - kb);
-  for (unsigned long long tid_ = blockIdx.x; tid_ < ntiles; tid_ += gridDim.x) {
-    if (threadIdx.x == 0) {
-      unsigned long long base = 0, rest = tid_;
-      int q = 0;
-      for (int pos = 0; pos < P.n_local; ++pos) {
-        if (q < kb && P.bits[q] == pos) { ++q; continue; }
-        base |= (rest & 1ull) << pos;
-        rest >>= 1;
-      }
-      s_base = base;
-    }
-    __syncthreads();
-    const unsigned long long base = s_base;
-    double2 *g = P.state + base;
-    const int ncombo = 1 << P.nh;
-    const uint32_t box_amps = 1u << (P.a0 + P.l1);
-    if constexpr (TMA) {
-      // one warp issues the tile's boxes; every thread then waits on the mbarrier's phase
-      if (threadIdx.x < 32) {
-        if (threadIdx.x == 0) sv_mbar_expect_tx(&s_mbar, 16u << kb);
-        __syncwarp();
-        for (int ci = threadIdx.x; ci < ncombo; ci += 32) {
-          unsigned long long hi = base;
-          for (int q = 0; q < P.nh; ++q) hi |= (unsigned long long)((ci >> q) & 1) << P.hib[q];
-          const int c2 = (int)((hi >> P.a0) & ((1ull << (P.s1 - P.a0)) - 1ull));
-          const int c4 = (int)(hi >> (P.s1 + P.l1));
-          sv_tma_load_5d(&tmap, &s_mbar, tile + (size_t)ci * box_amps, 0, 0, c2, 0, c4);
+// ---- the gate groups of a pass on one shared-memory tile (all threads of the CTA; ends with a CTA barrier) ----
+template <bool TMA, int NT>
+__device__ __forceinline__ void sv_apply_groups(double2 *tile, const SvBlockParams &P, unsigned long long base) {
+  const int kb = P.kb;
+  const uint32_t tsize = 1u << kb;
+  for (int gr = 0; gr < P.ngroups; ++gr) {
+    const SvGroup &grp = c_sv_groups[gr];
+    const uint32_t s1 = grp.m[0], s2 = grp.m[1], s4 = grp.m[2];
+    const uint32_t w1 = grp.w[0], w2 = grp.w[1], w4 = grp.w[2];           // the swizzle is xor-linear
+    const int simple = grp.simple;
+    const unsigned short *ctab = P.ctab + ((size_t)gr << (kb - 3));
+    for (uint32_t t = threadIdx.x; t < (tsize >> 3); t += NT) {
+      // coset representative from the host-built table (the index arithmetic -- bit swaps, zero
+      // insertion, swizzle -- was a third of the kernel's instructions)
+      const uint32_t Ps = __ldg(ctab + t);
+      uint32_t sm[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sm[q] = Ps ^ ((q & 1) ? w1 : 0u) ^ ((q & 2) ? w2 : 0u) ^ ((q & 4) ? w4 : 0u);
+      double2 a[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = tile[sm[q]];
+      if (simple) {
+        // at most one uncontrolled 2x2 per register slot, in slot order: no descriptor decoding
+        const SvTileGate *gt = c_sv_gates + grp.first;
+        if (simple & 1) {
+          double2 u[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) u[e] = gt->u[e];
+          sv_apply_slot_nc<0>(a, u);
+          ++gt;
         }
-      }
-      sv_mbar_wait(&s_mbar, phase);
-      phase ^= 1u;
-    } else {
-      // HBM -> shared memory with cp.async: every thread has all of its 16-byte copies in flight at once
-      const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
-      const uint32_t sw0 = sv_swz(threadIdx.x) * 16u;
-#pragma unroll 4
-      for (uint32_t k = 0; k < tsize; k += SV_THREADS) {   // swz(tid | k) = swz(tid) ^ swz(k): disjoint bits
-        const uint32_t j = threadIdx.x | k;
-        if (j >= tsize) break;               // tiles smaller than the CTA (test sizes)
-        const double2 *src = g + ((j & lowmask) | offs[j >> c]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_s + (sw0 ^ (sv_swz(k) * 16u))), "l"(src) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
-    }
-    for (int gr = 0; gr < P.ngroups; ++gr) {
-      const SvGroup &grp = c_sv_groups[gr];
-      const uint32_t s1 = grp.m[0], s2 = grp.m[1], s4 = grp.m[2];
-      const uint32_t w1 = grp.w[0], w2 = grp.w[1], w4 = grp.w[2];           // the swizzle is xor-linear
-      const int simple = grp.simple;
-      const unsigned short *ctab = P.ctab + ((size_t)gr << (kb - 3));
-      for (uint32_t t = threadIdx.x; t < (tsize >> 3); t += SV_THREADS) {
-        // coset representative from the host-built table (the index arithmetic -- bit swaps, zero
-        // insertion, swizzle -- was a third of the kernel's instructions)
-        const uint32_t Ps = __ldg(ctab + t);
-        uint32_t sm[8];
+        if (simple & 2) {
+          double2 u[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) sm[q] = Ps ^ ((q & 1) ? w1 : 0u) ^ ((q & 2) ? w2 : 0u) ^ ((q & 4) ? w4 : 0u);
-        double2 a[8];
+          for (int e = 0; e < 4; ++e) u[e] = gt->u[e];
+          sv_apply_slot_nc<1>(a, u);
+          ++gt;
+        }
+        if (simple & 4) {
+          double2 u[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) a[q] = tile[sm[q]];
-        if (simple) {
-          // at most one uncontrolled 2x2 per register slot, in slot order: no descriptor decoding
-          const SvTileGate *gt = c_sv_gates + grp.first;
-          if (simple & 1) {
-            double2 u[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) u[e] = gt->u[e];
-            sv_apply_slot_nc<0>(a, u);
-            ++gt;
-          }
-          if (simple & 2) {
-            double2 u[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) u[e] = gt->u[e];
-            sv_apply_slot_nc<1>(a, u);
-            ++gt;
-          }
-          if (simple & 4) {
-            double2 u[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) u[e] = gt->u[e];
-            sv_apply_slot_nc<2>(a, u);
-          }
-        } else {
+          for (int e = 0; e < 4; ++e) u[e] = gt->u[e];
+          sv_apply_slot_nc<2>(a, u);
+        }
+      } else {
         const uint32_t Pj = sv_sw<TMA>(Ps);   // the swizzle is an involution
         for (int gi = grp.first; gi < grp.first + grp.ngates; ++gi) {
           const SvTileGate *gt = c_sv_gates + gi;
@@ -342,25 +275,122 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
             }
           }
         }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) tile[sm[q]] = a[q];
       }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tile[sm[q]] = a[q];
+    }
+    __syncthreads();
+  }
+}
+// write a tile back with the frame of the pass undone: logical index j sits at tile position A^-1 j
+template <bool TMA, int NT>
+__device__ __forceinline__ void sv_store_framed(const double2 *tile, double2 *g, const SvBlockParams &P, const unsigned long long *offs) {
+  const int c = P.c;
+  const uint32_t tsize = 1u << P.kb, lowmask = (1u << c) - 1u;
+  constexpr int LB = NT == 512 ? 9 : 8;
+  uint32_t pt = 0;
+#pragma unroll
+  for (int q = 0; q < LB; ++q) pt ^= ((threadIdx.x >> q) & 1u) ? (uint32_t)P.ainv[q] : 0u;
+  const uint32_t sw0 = sv_sw<TMA>(pt);
+#pragma unroll 2
+  for (uint32_t k = 0; k < tsize; k += NT) {
+    const uint32_t j = threadIdx.x | k;
+    if (j >= tsize) break;
+    uint32_t pk = 0;
+#pragma unroll
+    for (int q = LB; q < SV_MAX_TILE_BITS; ++q) pk ^= ((k >> q) & 1u) ? (uint32_t)P.ainv[q] : 0u;
+    g[(j & lowmask) | offs[j >> c]] = tile[sw0 ^ sv_sw<TMA>(pk)];
+  }
+}
+__device__ __forceinline__ unsigned long long sv_tile_base(const SvBlockParams &P, unsigned long long tid_) {
+  unsigned long long base = 0, rest = tid_;
+  int q = 0;
+  for (int pos = 0; pos < P.n_local; ++pos) {
+    if (q < P.kb && P.bits[q] == pos) { ++q; continue; }
+    base |= (rest & 1ull) << pos;
+    rest >>= 1;
+  }
+  return base;
+}
+// one warp issues / stores the TMA boxes of a tile
+template <bool STORE>
+__device__ __forceinline__ void sv_tma_tile(const CUtensorMap *tmap, const SvBlockParams &P, unsigned long long base, double2 *tile,
+                                            unsigned long long *mbar) {
+  const int ncombo = 1 << P.nh;
+  const uint32_t box_amps = 1u << (P.a0 + P.l1);
+  for (int ci = threadIdx.x & 31; ci < ncombo; ci += 32) {
+    unsigned long long hi = base;
+    for (int q = 0; q < P.nh; ++q) hi |= (unsigned long long)((ci >> q) & 1) << P.hib[q];
+    const int c2 = (int)((hi >> P.a0) & ((1ull << (P.s1 - P.a0)) - 1ull));
+    const int c4 = (int)(hi >> (P.s1 + P.l1));
+    if constexpr (STORE) sv_tma_store_5d(tmap, tile + (size_t)ci * box_amps, 0, 0, c2, 0, c4);
+    else sv_tma_load_5d(tmap, mbar, tile + (size_t)ci * box_amps, 0, 0, c2, 0, c4);
+  }
+}
+
+// Persistent CTAs, one tile at a time.  Tile element j (kb bits) lives at slab index base | spread(j): the low c
+// bits are contiguous (coalesced 16*2^c-byte runs), the others are scattered by offs[].
+// TMA = true: the tile is fetched by cp.async.bulk.tensor from a 5-d tensor map of the slab (one box per
+// combination of the tile bits beyond its first two runs of consecutive positions), completion on an mbarrier,
+// shared-memory layout = the TMA 128-byte swizzle; a pass that ends with the identity frame is written back with
+// cp.async.bulk.tensor as well, a framed pass by the threads (the frame is undone by the store addresses).
+// TMA = false: cp.async staging with the fold-all swizzle (tiles the tensor map cannot describe, test sizes).
+// dynamic shared memory: tile [2^kb] double2 (1024-byte aligned for the TMA swizzle)
+template <int MINB, bool TMA>
+__global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBlockParams P, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) double2 tile[];
+  __shared__ unsigned long long offs[1 << 8];
+  __shared__ unsigned long long s_base;
+  __shared__ __align__(8) unsigned long long s_mbar;
+  const int kb = P.kb, c = P.c;
+  const uint32_t tsize = 1u << kb, nhi = 1u << (kb - c), lowmask = (1u << c) - 1u;
+  for (uint32_t h = threadIdx.x; h < nhi; h += SV_THREADS) {
+    unsigned long long o = 0;
+    for (int q = c; q < kb; ++q) o |= (unsigned long long)((h >> (q - c)) & 1u) << P.bits[q];
+    offs[h] = o;
+  }
+  if constexpr (TMA) {
+    if (threadIdx.x == 0) sv_mbar_init(&s_mbar, 1);
+  }
+  uint32_t phase = 0;
+  const unsigned long long ntiles = 1ull << (P.n_local - kb);
+  for (unsigned long long tid_ = blockIdx.x; tid_ < ntiles; tid_ += gridDim.x) {
+    if (threadIdx.x == 0) s_base = sv_tile_base(P, tid_);
+    __syncthreads();
+    const unsigned long long base = s_base;
+    double2 *g = P.state + base;
+    if constexpr (TMA) {
+      // one warp issues the tile's boxes; every thread then waits on the mbarrier's phase
+      if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) sv_mbar_expect_tx(&s_mbar, 16u << kb);
+        __syncwarp();
+        sv_tma_tile<false>(&tmap, P, base, tile, &s_mbar);
+      }
+      sv_mbar_wait(&s_mbar, phase);
+      phase ^= 1u;
+    } else {
+      // HBM -> shared memory with cp.async: every thread has all of its 16-byte copies in flight at once
+      const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+      const uint32_t sw0 = sv_swz(threadIdx.x) * 16u;
+#pragma unroll 4
+      for (uint32_t k = 0; k < tsize; k += SV_THREADS) {   // swz(tid | k) = swz(tid) ^ swz(k): disjoint bits
+        const uint32_t j = threadIdx.x | k;
+        if (j >= tsize) break;               // tiles smaller than the CTA (test sizes)
+        const double2 *src = g + ((j & lowmask) | offs[j >> c]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_s + (sw0 ^ (sv_swz(k) * 16u))), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
     }
+    sv_apply_groups<TMA, SV_THREADS>(tile, P, base);
     if (!P.framed) {
       if constexpr (TMA) {
         // shared memory (generic-proxy writes) -> async proxy, then one warp stores the boxes back
         sv_fence_async_smem();
         __syncthreads();
         if (threadIdx.x < 32) {
-          for (int ci = threadIdx.x; ci < ncombo; ci += 32) {
-            unsigned long long hi = base;
-            for (int q = 0; q < P.nh; ++q) hi |= (unsigned long long)((ci >> q) & 1) << P.hib[q];
-            const int c2 = (int)((hi >> P.a0) & ((1ull << (P.s1 - P.a0)) - 1ull));
-            const int c4 = (int)(hi >> (P.s1 + P.l1));
-            sv_tma_store_5d(&tmap, tile + (size_t)ci * box_amps, 0, 0, c2, 0, c4);
-          }
+          sv_tma_tile<true>(&tmap, P, base, tile, nullptr);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the tile may be overwritten again
         }
@@ -373,20 +403,8 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
           g[(j & lowmask) | offs[j >> c]] = tile[sw0 ^ sv_swz(k)];
         }
       }
-    } else {     // undo the frame: logical index j sits at tile position A^-1 j
-      uint32_t pt = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) pt ^= ((threadIdx.x >> q) & 1u) ? (uint32_t)P.ainv[q] : 0u;
-      const uint32_t sw0 = sv_sw<TMA>(pt);
-#pragma unroll 2
-      for (uint32_t k = 0; k < tsize; k += SV_THREADS) {
-        const uint32_t j = threadIdx.x | k;
-        if (j >= tsize) break;
-        uint32_t pk = 0;
-#pragma unroll
-        for (int q = 8; q < SV_MAX_TILE_BITS; ++q) pk ^= ((k >> q) & 1u) ? (uint32_t)P.ainv[q] : 0u;
-        g[(j & lowmask) | offs[j >> c]] = tile[sw0 ^ sv_sw<TMA>(pk)];
-      }
+    } else {
+      sv_store_framed<TMA, SV_THREADS>(tile, g, P, offs);
       if constexpr (TMA) sv_fence_async_smem();     // these reads precede the next tile's async-proxy writes
     }
     __syncthreads();
@@ -394,6 +412,71 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
   if constexpr (TMA) {
     if (threadIdx.x < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA exits
   }
+}
+
+// Software-pipelined TMA variant: ONE CTA of 512 threads per SM owns TWO tile buffers; while the threads apply the
+// gate groups to tile k, the TMA unit is already fetching tile k + 1 into the other buffer (its own mbarrier), so
+// HBM reads overlap the arithmetic inside every SM by construction -- with single-buffered CTAs all tiles cost the
+// same and the CTAs of the whole grid fall into lock-step (everybody loads, then everybody computes), leaving HBM
+// idle during the arithmetic and the FP64 pipe idle during the copies.
+// dynamic shared memory: 2 x tile [2^kb] double2
+#define SV_PIPE_THREADS 512
+__global__ void __launch_bounds__(SV_PIPE_THREADS, 1) sv_pipe_kernel(const SvBlockParams P, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) double2 tiles[];
+  __shared__ unsigned long long offs[1 << 8];
+  __shared__ unsigned long long s_base[2];
+  __shared__ __align__(8) unsigned long long s_mbar[2];
+  const int kb = P.kb, c = P.c;
+  const uint32_t tsize = 1u << kb, nhi = 1u << (kb - c);
+  for (uint32_t h = threadIdx.x; h < nhi; h += SV_PIPE_THREADS) {
+    unsigned long long o = 0;
+    for (int q = c; q < kb; ++q) o |= (unsigned long long)((h >> (q - c)) & 1u) << P.bits[q];
+    offs[h] = o;
+  }
+  const unsigned long long ntiles = 1ull << (P.n_local - kb);
+  if (threadIdx.x == 0) {
+    sv_mbar_init(&s_mbar[0], 1);
+    sv_mbar_init(&s_mbar[1], 1);
+  }
+  __syncthreads();
+  // prologue: fetch this CTA's first tile
+  if (threadIdx.x < 32 && blockIdx.x < ntiles) {
+    unsigned long long b0 = 0;
+    if (threadIdx.x == 0) { b0 = sv_tile_base(P, blockIdx.x); s_base[0] = b0; sv_mbar_expect_tx(&s_mbar[0], 16u << kb); }
+    b0 = __shfl_sync(0xffffffffu, b0, 0);
+    sv_tma_tile<false>(&tmap, P, b0, tiles, &s_mbar[0]);
+  }
+  uint32_t it = 0;
+  for (unsigned long long tid_ = blockIdx.x; tid_ < ntiles; tid_ += gridDim.x, ++it) {
+    const int cur = it & 1, nxt = cur ^ 1;
+    double2 *tile = tiles + (size_t)cur * tsize;
+    // prefetch the next tile into the other buffer (free since the barrier that ended iteration it - 1)
+    const unsigned long long tnext = tid_ + gridDim.x;
+    if (threadIdx.x < 32 && tnext < ntiles) {
+      unsigned long long bn = 0;
+      if (threadIdx.x == 0) { bn = sv_tile_base(P, tnext); s_base[nxt] = bn; sv_mbar_expect_tx(&s_mbar[nxt], 16u << kb); }
+      bn = __shfl_sync(0xffffffffu, bn, 0);
+      sv_tma_tile<false>(&tmap, P, bn, tiles + (size_t)nxt * tsize, &s_mbar[nxt]);
+    }
+    sv_mbar_wait(&s_mbar[cur], (it >> 1) & 1u);
+    const unsigned long long base = s_base[cur];     // written before the barrier that preceded this tile's wait
+    double2 *g = P.state + base;
+    sv_apply_groups<true, SV_PIPE_THREADS>(tile, P, base);
+    if (!P.framed) {
+      sv_fence_async_smem();
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        sv_tma_tile<true>(&tmap, P, base, tile, nullptr);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    } else {
+      sv_store_framed<true, SV_PIPE_THREADS>(tile, g, P, offs);
+      sv_fence_async_smem();
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __global__ void sv_init_kernel(double2 *state, unsigned long long dim, long long index, double2 amp) {
@@ -824,6 +907,12 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
   if (minb == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv_block_kernel<2, true>, SV_THREADS, smem_max);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv_block_kernel<3, true>, SV_THREADS, smem_max);
   const int grid = (int)std::min<unsigned long long>(ntiles, (unsigned long long)std::max(1, occ) * num_sms);
+  // double-buffered TMA pipeline (one 512-thread CTA per SM, two tile buffers): default wherever two tiles fit
+  int use_pipe = 1;
+  if (const char *pe = getenv("QAS_B200_SV_PIPE")) use_pipe = atoi(pe) != 0;      // tuning knob
+  const bool pipe_fits = 2 * smem_max <= 200 * 1024 && kb >= 9;
+  if (use_pipe && pipe_fits) SVCK(cudaFuncSetAttribute(sv_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem_max)));
+  const int grid_pipe = (int)std::min<unsigned long long>(ntiles, (unsigned long long)num_sms);
   for (size_t bi = 0; bi < blocks.size(); ++bi) {
     SvBlockParams P{};
     P.state = (double2 *)state;
@@ -846,7 +935,10 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
       for (int q = 0; q < 16; ++q) P.hib[q] = geom[bi].hib[q];
       if (!sv_make_tensor_map(state, n_local, geom[bi], &tmap)) { g_sv_error = "cuTensorMapEncodeTiled failed for a tile geometry"; return QAS_ERR_CUDA; }
     }
-    if (tma) {
+    if (tma && use_pipe && pipe_fits) {
+      sv_pipe_kernel<<<grid_pipe, SV_PIPE_THREADS, 2 * smem, st>>>(P, tmap);
+      ++tma_passes;
+    } else if (tma) {
       if (minb == 2) sv_block_kernel<2, true><<<grid, SV_THREADS, smem, st>>>(P, tmap);
       else sv_block_kernel<3, true><<<grid, SV_THREADS, smem, st>>>(P, tmap);
       ++tma_passes;

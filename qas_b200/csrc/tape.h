@@ -628,11 +628,13 @@ QAS_HD int qas_compress_packed(uint32_t *pk, uint32_t *gops, int *nops_io, int *
   uint32_t ev[NQ], ec[NQ], bs[NQ];
 QAS_PUNROLL
   for (int p = 0; p < NQ; ++p) ev[p] = ec[p] = bs[p] = 0u;
-  int d = 0;
+  int d = 0, fail = 0;
+  // (no return inside the loops: on the GPU the threads of a warp leave them at different iterations, and an
+  // early exit would keep them from re-converging for the rest of the function)
   for (int j = nops - 1; j >= 0; --j) {            // time order
     uint32_t *q = pk + (size_t)j * QAS_PK_WORDS;
     uint32_t c = 0u;
-    if (qas_meta_kind(q[2]) == QAS_K_U1) {
+    if (qas_meta_kind(q[2]) == QAS_K_U1 && !fail) {
       const uint32_t m = q[0] & 0xffffu;
       uint32_t x = m;
 QAS_PUNROLL
@@ -641,8 +643,9 @@ QAS_PUNROLL
         x ^= hit ? ev[p] : 0u;
         c ^= hit ? ec[p] : 0u;
       }
-      if (x) {                                     // enlarges the span: B_d = m, coordinates e_d
-        if (d >= max_d || d >= n - 1) return d >= n - 1 ? QAS_CT_FULL : QAS_CT_TOO_BIG;
+      if (x && (d >= max_d || d >= n - 1)) {       // would reach the whole register / exceed the largest slot
+        fail = d >= n - 1 ? QAS_CT_FULL : QAS_CT_TOO_BIG;
+      } else if (x) {                              // enlarges the span: B_d = m, coordinates e_d
         const int pv = qas_msb32(x);
         const uint32_t cv = c | (1u << d);
 QAS_PUNROLL
@@ -660,6 +663,7 @@ QAS_PUNROLL
     q[0] = (q[0] & 0xffff0000u) | c;               // m' in place of m
     q[2] = (q[2] & 0x0fffffffu) | ((uint32_t)d << 28);
   }
+  if (fail) return fail;
   // translate, dropping controlled ops whose control is constant on the support
   int w = 0, ndrop = 0;
   for (int j = 0; j < nops; ++j) {

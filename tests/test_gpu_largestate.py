@@ -53,13 +53,15 @@ def test_tma_and_cp_async_tiles_agree_on_hea_22q(monkeypatch):
     n = 22
     gl = hea_gate_list(n, 3, seed=1)
     out = {}
-    for tma in ("1", "0"):
+    for tma, pipe in (("1", "1"), ("1", "0"), ("0", "0")):       # double-buffered TMA pipeline, single-buffered TMA, cp.async
         monkeypatch.setenv("QAS_B200_SV_TMA", tma)
+        monkeypatch.setenv("QAS_B200_SV_PIPE", pipe)
         s = LargeStateSimulator(n).run(gl)
-        out[tma] = (s.expval(zz_chain_terms(n)), s.backend.tma_passes, s.backend.passes, _state(s)[:4096].copy())
-    assert abs(out["1"][0] - out["0"][0]) < 1e-11
-    assert np.max(np.abs(out["1"][3] - out["0"][3])) < 1e-13
-    assert out["1"][1] == out["1"][2] and out["0"][1] == 0
+        out[tma + pipe] = (s.expval(zz_chain_terms(n)), s.backend.tma_passes, s.backend.passes, _state(s)[:4096].copy())
+    for key in ("10", "00"):
+        assert abs(out["11"][0] - out[key][0]) < 1e-11
+        assert np.max(np.abs(out["11"][3] - out[key][3])) < 1e-13
+    assert out["11"][1] == out["11"][2] and out["10"][1] == out["10"][2] and out["00"][1] == 0
 
 
 def test_hea_20q_energy_matches_oracle():
