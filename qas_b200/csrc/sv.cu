@@ -282,25 +282,42 @@ __device__ __forceinline__ void sv_apply_groups(double2 *tile, const SvBlockPara
     __syncthreads();
   }
 }
-// write a tile back with the frame of the pass undone: logical index j sits at tile position A^-1 j
+// Write a tile back with the frame of the pass undone: logical index j sits at tile position A^-1 j.  Thread
+// `tid` stores the elements j = tid | (i << LB): their tile positions are sw(A^-1 tid) ^ sw(A^-1 (i << LB)) and their
+// slab offsets offs(tid) ^ offs(i << LB) (both maps are xor-linear), so the i-dependent halves come from two small
+// per-pass tables (spk / goff, filled once per CTA by sv_fill_store_tables) instead of being recomputed per element.
+template <int NT>
+struct SvStoreTables {
+  static constexpr int LB = NT == 512 ? 9 : 8;
+  uint32_t spk[1 << (SV_MAX_TILE_BITS - 8)];
+  unsigned long long goff[1 << (SV_MAX_TILE_BITS - 8)];
+};
 template <bool TMA, int NT>
-__device__ __forceinline__ void sv_store_framed(const double2 *tile, double2 *g, const SvBlockParams &P, const unsigned long long *offs) {
+__device__ __forceinline__ void sv_fill_store_tables(SvStoreTables<NT> &tb, const SvBlockParams &P, const unsigned long long *offs) {
+  constexpr int LB = SvStoreTables<NT>::LB;
+  const int nhi = P.kb > LB ? 1 << (P.kb - LB) : 1;
+  for (int i = threadIdx.x; i < nhi; i += NT) {
+    uint32_t pk = 0;
+    for (int q = LB; q < P.kb; ++q) pk ^= ((i >> (q - LB)) & 1) ? (uint32_t)P.ainv[q] : 0u;
+    tb.spk[i] = sv_sw<TMA>(pk);
+    tb.goff[i] = LB >= P.c ? offs[(uint32_t)i << (LB - P.c)] : 0ull;
+  }
+}
+template <bool TMA, int NT>
+__device__ __forceinline__ void sv_store_framed(const double2 *tile, double2 *g, const SvBlockParams &P, const unsigned long long *offs,
+                                                const SvStoreTables<NT> &tb) {
+  constexpr int LB = SvStoreTables<NT>::LB;
   const int c = P.c;
   const uint32_t tsize = 1u << P.kb, lowmask = (1u << c) - 1u;
-  constexpr int LB = NT == 512 ? 9 : 8;
+  if (threadIdx.x >= tsize) return;              // tiles smaller than the CTA (test sizes)
   uint32_t pt = 0;
 #pragma unroll
   for (int q = 0; q < LB; ++q) pt ^= ((threadIdx.x >> q) & 1u) ? (uint32_t)P.ainv[q] : 0u;
   const uint32_t sw0 = sv_sw<TMA>(pt);
-#pragma unroll 2
-  for (uint32_t k = 0; k < tsize; k += NT) {
-    const uint32_t j = threadIdx.x | k;
-    if (j >= tsize) break;
-    uint32_t pk = 0;
-#pragma unroll
-    for (int q = LB; q < SV_MAX_TILE_BITS; ++q) pk ^= ((k >> q) & 1u) ? (uint32_t)P.ainv[q] : 0u;
-    g[(j & lowmask) | offs[j >> c]] = tile[sw0 ^ sv_sw<TMA>(pk)];
-  }
+  double2 *g0 = g + ((threadIdx.x & lowmask) | offs[threadIdx.x >> c]);
+  const int nhi = P.kb > LB ? 1 << (P.kb - LB) : 1;
+#pragma unroll 4
+  for (int i = 0; i < nhi; ++i) g0[tb.goff[i]] = tile[sw0 ^ tb.spk[i]];
 }
 __device__ __forceinline__ unsigned long long sv_tile_base(const SvBlockParams &P, unsigned long long tid_) {
   unsigned long long base = 0, rest = tid_;
@@ -342,6 +359,7 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
   __shared__ unsigned long long offs[1 << 8];
   __shared__ unsigned long long s_base;
   __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ SvStoreTables<SV_THREADS> s_tb;
   const int kb = P.kb, c = P.c;
   const uint32_t tsize = 1u << kb, nhi = 1u << (kb - c), lowmask = (1u << c) - 1u;
   for (uint32_t h = threadIdx.x; h < nhi; h += SV_THREADS) {
@@ -352,6 +370,8 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
   if constexpr (TMA) {
     if (threadIdx.x == 0) sv_mbar_init(&s_mbar, 1);
   }
+  __syncthreads();
+  if (P.framed) sv_fill_store_tables<TMA, SV_THREADS>(s_tb, P, offs);
   uint32_t phase = 0;
   const unsigned long long ntiles = 1ull << (P.n_local - kb);
   for (unsigned long long tid_ = blockIdx.x; tid_ < ntiles; tid_ += gridDim.x) {
@@ -404,7 +424,7 @@ __global__ void __launch_bounds__(SV_THREADS, MINB) sv_block_kernel(const SvBloc
         }
       }
     } else {
-      sv_store_framed<TMA, SV_THREADS>(tile, g, P, offs);
+      sv_store_framed<TMA, SV_THREADS>(tile, g, P, offs, s_tb);
       if constexpr (TMA) sv_fence_async_smem();     // these reads precede the next tile's async-proxy writes
     }
     __syncthreads();
@@ -426,6 +446,7 @@ __global__ void __launch_bounds__(SV_PIPE_THREADS, 1) sv_pipe_kernel(const SvBlo
   __shared__ unsigned long long offs[1 << 8];
   __shared__ unsigned long long s_base[2];
   __shared__ __align__(8) unsigned long long s_mbar[2];
+  __shared__ SvStoreTables<SV_PIPE_THREADS> s_tb;
   const int kb = P.kb, c = P.c;
   const uint32_t tsize = 1u << kb, nhi = 1u << (kb - c);
   for (uint32_t h = threadIdx.x; h < nhi; h += SV_PIPE_THREADS) {
@@ -439,6 +460,7 @@ __global__ void __launch_bounds__(SV_PIPE_THREADS, 1) sv_pipe_kernel(const SvBlo
     sv_mbar_init(&s_mbar[1], 1);
   }
   __syncthreads();
+  if (P.framed) sv_fill_store_tables<true, SV_PIPE_THREADS>(s_tb, P, offs);
   // prologue: fetch this CTA's first tile
   if (threadIdx.x < 32 && blockIdx.x < ntiles) {
     unsigned long long b0 = 0;
@@ -471,7 +493,7 @@ __global__ void __launch_bounds__(SV_PIPE_THREADS, 1) sv_pipe_kernel(const SvBlo
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     } else {
-      sv_store_framed<true, SV_PIPE_THREADS>(tile, g, P, offs);
+      sv_store_framed<true, SV_PIPE_THREADS>(tile, g, P, offs, s_tb);
       sv_fence_async_smem();
     }
     __syncthreads();
@@ -907,8 +929,10 @@ extern "C" int qas_sv_apply(void *state, int n_local, const qas_sv_gate *gates, 
   if (minb == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv_block_kernel<2, true>, SV_THREADS, smem_max);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sv_block_kernel<3, true>, SV_THREADS, smem_max);
   const int grid = (int)std::min<unsigned long long>(ntiles, (unsigned long long)std::max(1, occ) * num_sms);
-  // double-buffered TMA pipeline (one 512-thread CTA per SM, two tile buffers): default wherever two tiles fit
-  int use_pipe = 1;
+  // double-buffered TMA pipeline (one 512-thread CTA per SM, two tile buffers).  Opt-in: measured SLOWER than three
+  // single-buffered CTAs per SM (28 qubits: 49.3 vs 39.4 ms per 12 passes) -- the pass is bound by instruction issue
+  // and by the CTA barrier after every gate group, and three independent CTAs hide each other's barriers.
+  int use_pipe = 0;
   if (const char *pe = getenv("QAS_B200_SV_PIPE")) use_pipe = atoi(pe) != 0;      // tuning knob
   const bool pipe_fits = 2 * smem_max <= 200 * 1024 && kb >= 9;
   if (use_pipe && pipe_fits) SVCK(cudaFuncSetAttribute(sv_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem_max)));

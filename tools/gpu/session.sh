@@ -47,6 +47,28 @@ for step in "$@"; do
       envs=$(echo "${b:-}" | tr ',' ' ')
       env $envs timeout 600 python bench.py --workload "$a" --steps 5 --warmup 3 --tune > "$out/$name.json" 2> "$out/$name.err"
       echo "rc=$?" | tee -a "$out/steps.log"; tail -c 1500 "$out/$name.json"; tail -3 "$out/$name.err" ;;
+    mgpu)    # mgpu:<N>:<workload>[:envs]  -- bench.py under torchrun on N GPUs of the box
+      IFS=: read -r _k ng wl envs <<< "$step"
+      envs=$(echo "${envs:-}" | tr ',' ' ')
+      env $envs timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$ng" --master-addr 127.0.0.1 --master-port 29517 \
+        bench.py --gpus "$ng" --workload "$wl" --steps 20 --warmup 5 --tune > "$out/$name.json" 2> "$out/$name.err"
+      echo "rc=$?" | tee -a "$out/steps.log"; python tools/bench_brief.py "$out/$name.json"; tail -c 1200 "$out/$name.json"; tail -5 "$out/$name.err" ;;
+    gputests2)   # the multi-GPU pytest cases (need >= 2 GPUs)
+      timeout 900 python -m pytest tests -x -q -m gpu -k "two_gpu" > "$out/$name.log" 2>&1
+      echo "rc=$?" | tee -a "$out/steps.log"; tail -5 "$out/$name.log" ;;
+    searchepoch)
+      timeout 900 python bench.py --search-epoch --workload "$a" > "$out/$name.json" 2> "$out/$name.err"
+      echo "rc=$?" | tee -a "$out/steps.log"; tail -c 1500 "$out/$name.json"; tail -3 "$out/$name.err" ;;
+    leafstudy)   # leafstudy:<LiH|H2O>:<seeds>
+      timeout 1500 python tools/leaf_parallel_study.py "$a" --seeds "${b:-20}" > "$out/$name.json" 2> "$out/$name.err"
+      echo "rc=$?" | tee -a "$out/steps.log"; python - "$out/$name.json" <<'PY'
+import json,sys
+d=json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
+for k,v in d.items():
+    if isinstance(v,dict): print(k,{a:b for a,b in v.items() if a!="runs"})
+    else: print(k,v)
+PY
+      tail -3 "$out/$name.err" ;;
     sanity)
       timeout 600 python tools/gpu/sanity.py > "$out/$name.log" 2>&1
       echo "rc=$?" | tee -a "$out/steps.log"; tail -3 "$out/$name.log" ;;
