@@ -64,7 +64,9 @@ WORKLOADS = {
 }
 
 
-def make_workload(name, B, seed):
+def make_workload(name, B, seed, param_seed=None):
+    """structure lists from `seed` (each rank its own shard); the parameter super-set from `param_seed` (the same on
+    every rank: data parallelism replicates it, qas/mcts/mcts.py:340-352 averages the gradients of ONE params array)"""
     from qas_b200.qml_models import kagome_heisenberg_model, qchem_model
     from qas_b200.qml_models import qml_models_legacy as L
     from qas_b200.qml_models.qml_gate_ops import QMLPool
@@ -73,7 +75,7 @@ def make_workload(name, B, seed):
     model = next(getattr(m, mname) for m in (L, qchem_model, kagome_heisenberg_model) if hasattr(m, mname))
     pool = QMLPool(n, ["Rot", "PlaceHolder"], ["CNOT"], False, coupling)
     c = len(pool)
-    params = np.random.default_rng(seed).standard_normal((p, c, 3)) * scale
+    params = np.random.default_rng(seed if param_seed is None else param_seed).standard_normal((p, c, 3)) * scale
     ks = sample_structure_lists(pool, p, {"CNOT": cx_lim}, B, seed=seed)
     return model, pool, params, ks
 
@@ -259,7 +261,7 @@ def run_b200(args):
     name = args.workload
     mname, n, p = WORKLOADS[name][:3]
     B = args.batch
-    model, pool, params, ks = make_workload(name, B, args.seed + 1000 * rank)   # each rank its own shard
+    model, pool, params, ks = make_workload(name, B, args.seed + 1000 * rank, param_seed=args.seed)   # each rank its own shard, one parameter super-set
     c = len(pool)
     ev = model.evaluator(pool, 3, local)
     T = len(model.terms())
@@ -548,7 +550,7 @@ def secondary_workload(name, args, dev, local, flush, peak):
 
 
 # ------------------------------------------------------------------------------- large-state mode
-LARGE_WORKLOADS = {"hea_24q": (24, 4), "hea_26q": (26, 4), "hea_28q": (28, 4), "hea_30q": (30, 4)}
+LARGE_WORKLOADS = {"hea_%dq" % q: (q, 4) for q in range(24, 34)}     # 2^n x 16 B must fit the GPUs it is sharded over
 
 
 def run_largestate(args):

@@ -118,8 +118,8 @@ __host__ __device__ inline size_t evalc_team_smem_bytes(int slot_bits, int T, bo
   const int wpt = T >= 32 ? T / 32 : 1;
   size_t b = ((size_t)16 << slot_bits) * (grad ? 2 : 1);
   b += (((size_t)(QAS_REC_HDR + ops_cap * QAS_OP_WORDS) * 4) + 15) & ~(size_t)15;
-  b += 16 * 4;                                         // nsl + basis (<= QAS_CT_MAX_D words)
-  b += (((size_t)S * 4) + 15) & ~(size_t)15;           // slice list
+  b += 32 * 4;                                         // nsl + basis (<= QAS_CT_MAX_D words) | physical offsets of the HA strides
+  b += (size_t)S * 16;                                 // slice records (CSlice)
   b += (size_t)ops_cap * 64;                           // staged gate matrices
   if (grad) b += (size_t)ops_cap * 64;                 // cross matrices M of the circuit's ops
   if (grad && wpt > 1) b += (size_t)2 * 2 * wpt * 64;  // cross-matrix ring (two buffers, <= 2 gates per pass)
@@ -249,60 +249,109 @@ __device__ __forceinline__ void c_adj_group(double2 *psi, double2 *lam, const ui
                                                                         : ring + ((size_t)q * WPT + warp_in_team) * 8, false);
 }
 
+// Per-circuit slice record of the compressed H phase, built once per circuit by one lane per slice:
+//   x = x' (compressed X mask, < 2^12) | CS_FLAT | CS_IMAG | slice index << 16
+//   y, z = the (<= 4) basis masks zeta_q of the slice's Z span pulled back to compressed coordinates:
+//          parity(i(t) & zeta_q) = parity(t & zc_q) with bit k of zc_q = parity(B_k & zeta_q)   (i(t) = xor_k t_k B_k)
+//   w = eight nibbles: the sign index of the stride offsets a * T, a < 8  (the index is linear in t)
+#define CS_FLAT 0x4000u
+#define CS_IMAG 0x8000u
+#define CS_PHA 16          // chead[CS_PHA + a] = physical index of the stride offset a * T
+
+template <int T>
+__device__ __forceinline__ void c_prepare_slices(const EvalCParams &P, const uint32_t *gci, uint4 *sl, uint32_t *chead, int nsl,
+                                                 int d, int tid) {
+  const int n = P.n;
+  for (int s = tid; s < nsl; s += T) {
+    const uint32_t ent = gci[1 + n + s];
+    const uint32_t si = ent >> 16;
+    const uint4 info = __ldg(P.sinfo + si);
+    uint4 r = make_uint4((ent & 0xfffu) | (si << 16) | ((int)si >= P.S_real ? CS_IMAG : 0u), 0u, 0u, 0u);
+    if (info.x <= 4u) {
+      const uint32_t z0 = info.y & 0xffffu, z1 = info.y >> 16, z2 = info.z & 0xffffu, z3 = info.z >> 16;
+      uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
+      for (int k = 0; k < d; ++k) {
+        const uint32_t bk = gci[1 + k];
+        c0 |= (uint32_t)(__popc(bk & z0) & 1) << k;
+        c1 |= (uint32_t)(__popc(bk & z1) & 1) << k;
+        c2 |= (uint32_t)(__popc(bk & z2) & 1) << k;
+        c3 |= (uint32_t)(__popc(bk & z3) & 1) << k;
+      }
+      uint32_t D = 0u;
+#pragma unroll
+      for (int a = 1; a < 8; ++a) {
+        const uint32_t x = (uint32_t)(a * T);
+        D |= (uint32_t)((__popc(x & c0) & 1) | ((__popc(x & c1) & 1) << 1) | ((__popc(x & c2) & 1) << 2) | ((__popc(x & c3) & 1) << 3)) << (4 * a);
+      }
+      r.y = c0 | (c1 << 16);
+      r.z = c2 | (c3 << 16);
+      r.w = D;
+    } else {
+      r.x |= CS_FLAT;
+    }
+    sl[s] = r;
+  }
+  for (int a = tid; a < 8; a += T) {
+    const uint32_t x = (uint32_t)(a * T);
+    uint32_t ph = 0u;
+    for (int k = 0; k < d; ++k) ph ^= ((x >> k) & 1u) ? gci[1 + k] : 0u;
+    chead[CS_PHA + a] = ph;
+  }
+}
+
 // lambda = H psi on the support (compressed coordinates), returns this thread's share of Re <psi|lambda>.
 // A thread takes HA amplitudes at a time (t = t0 + T a) and walks the in-span slices ONCE for all of them.  The
 // sign V_s[i] at the physical index i = xor_k t_k B_k comes
 //   * for slices whose Z masks span <= 4 dimensions (all the excitation slices of a chemistry Hamiltonian: 28 of
-//     35 for LiH) from a 16-entry table indexed by the parities of i with a basis of that span -- two sectors per
-//     warp instead of one scattered 8-byte look-up per lane (the scattered look-ups made this phase L1-request
-//     bound: one sector per lane per slice);
+//     35 for LiH) from a 16-entry table indexed by the parities of t with the pulled-back span basis: the index of
+//     t0 costs four popcounts per (slice, thread), the indices of the HA strided amplitudes are that index xor a
+//     per-slice nibble (CSlice.w) -- the index is linear in t and t0, a * T have disjoint bits;
 //   * for the few slices with many Z masks (the diagonal one, the number-operator dressed single excitations) from
-//     the flat 2^n table.
+//     the flat 2^n table at the physical index (base index xor the per-circuit stride offsets).
 template <int HA, int T, bool GRAD>
 __device__ __forceinline__ double c_hphase(const EvalCParams &P, const double2 *psi, double2 *lam, const uint32_t *chead,
-                                           const uint32_t *list, int nsl, int d, int tid) {
+                                           const uint4 *sl, int nsl, int d, int tid) {
   double e_part = 0.0;
   const uint32_t dim = 1u << d;
   const int n = P.n;
   for (uint32_t t0 = tid; t0 < dim; t0 += T * HA) {
-    uint32_t ph[HA];
+    uint32_t ph0 = 0u;
+    for (int kk = 0; kk < d; ++kk) ph0 ^= ((t0 >> kk) & 1u) ? chead[1 + kk] : 0u;
     double2 acc[HA];
 #pragma unroll
-    for (int a = 0; a < HA; ++a) {
-      const uint32_t t = t0 + (uint32_t)(T * a);
-      uint32_t i = 0u;
-      for (int kk = 0; kk < d; ++kk) i ^= ((t >> kk) & 1u) ? chead[1 + kk] : 0u;
-      ph[a] = i;
-      acc[a] = make_double2(0.0, 0.0);
-    }
+    for (int a = 0; a < HA; ++a) acc[a] = make_double2(0.0, 0.0);
     for (int s = 0; s < nsl; ++s) {
-      const uint32_t ent = list[s];
-      const uint32_t xp = ent & 0xffffu, si = ent >> 16;
-      const bool imag = (int)si >= P.S_real;
-      const uint4 info = __ldg(P.sinfo + si);
+      const uint4 r = sl[s];
+      const uint32_t xp = r.x & 0xfffu, si = r.x >> 16;
       double v[HA];
-      if (info.x <= 4u) {
+      if (!(r.x & CS_FLAT)) {
         const double *lut = P.slut + (size_t)si * 16;
-        const uint32_t z0 = info.y & 0xffffu, z1 = info.y >> 16, z2 = info.z & 0xffffu, z3 = info.z >> 16;
+        const uint32_t idx0 = (__popc(t0 & (r.y & 0xffffu)) & 1) | ((__popc(t0 & (r.y >> 16)) & 1) << 1) |
+                              ((__popc(t0 & (r.z & 0xffffu)) & 1) << 2) | ((__popc(t0 & (r.z >> 16)) & 1) << 3);
 #pragma unroll
-        for (int a = 0; a < HA; ++a) {
-          const uint32_t i = ph[a];
-          uint32_t idx = (__popc(i & z0) & 1) | ((__popc(i & z1) & 1) << 1);
-          if (info.x > 2u) idx |= ((__popc(i & z2) & 1) << 2) | ((__popc(i & z3) & 1) << 3);
-          v[a] = __ldg(lut + idx);
-        }
+        for (int a = 0; a < HA; ++a) v[a] = __ldg(lut + ((idx0 ^ (r.w >> (4 * a))) & 15u));
       } else {
         const double *vrow = P.vflat + ((size_t)si << n);
 #pragma unroll
-        for (int a = 0; a < HA; ++a) v[a] = (t0 + (uint32_t)(T * a) < dim) ? __ldg(vrow + ph[a]) : 0.0;
+        for (int a = 0; a < HA; ++a) v[a] = (t0 + (uint32_t)(T * a) < dim) ? __ldg(vrow + (ph0 ^ chead[CS_PHA + a])) : 0.0;
       }
+      if (!(r.x & CS_IMAG)) {
 #pragma unroll
-      for (int a = 0; a < HA; ++a) {
-        const uint32_t t = t0 + (uint32_t)(T * a);
-        if (t < dim) {
-          const double2 pa = psi[t ^ xp];
-          if (!imag) { acc[a].x = fma(v[a], pa.x, acc[a].x); acc[a].y = fma(v[a], pa.y, acc[a].y); }
-          else { acc[a].x = fma(-v[a], pa.y, acc[a].x); acc[a].y = fma(v[a], pa.x, acc[a].y); }
+        for (int a = 0; a < HA; ++a) {
+          const uint32_t t = t0 + (uint32_t)(T * a);
+          if (t < dim) {
+            const double2 pa = psi[t ^ xp];
+            acc[a].x = fma(v[a], pa.x, acc[a].x); acc[a].y = fma(v[a], pa.y, acc[a].y);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < HA; ++a) {
+          const uint32_t t = t0 + (uint32_t)(T * a);
+          if (t < dim) {
+            const double2 pa = psi[t ^ xp];
+            acc[a].x = fma(-v[a], pa.y, acc[a].x); acc[a].y = fma(v[a], pa.x, acc[a].y);
+          }
         }
       }
     }
@@ -335,10 +384,10 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
   uint32_t *rec = reinterpret_cast<uint32_t *>(base);
   uint32_t *ops = rec + QAS_REC_HDR;
   base += (((size_t)(QAS_REC_HDR + P.ops_cap * QAS_OP_WORDS) * 4) + 15) & ~(size_t)15;
-  uint32_t *chead = reinterpret_cast<uint32_t *>(base);          // nsl, B_0 ..
-  base += 16 * 4;
-  uint32_t *list = reinterpret_cast<uint32_t *>(base);
-  base += (((size_t)P.S * 4) + 15) & ~(size_t)15;
+  uint32_t *chead = reinterpret_cast<uint32_t *>(base);          // nsl, B_0 .. | CS_PHA: stride offsets
+  base += 32 * 4;
+  uint4 *sl = reinterpret_cast<uint4 *>(base);                   // slice records of this circuit
+  base += (size_t)P.S * 16;
   double2 *Us = reinterpret_cast<double2 *>(base);
   base += (size_t)P.ops_cap * 64;
   double *Ms = reinterpret_cast<double *>(base);                 // [ops_cap][8] (GRAD)
@@ -367,7 +416,7 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
       const int used = QAS_REC_HDR + nops * QAS_OP_WORDS;
       for (int w = tid; w < used; w += T) rec[w] = grec[w];
       for (int w = tid; w <= d; w += T) chead[w] = gci[w];
-      for (int w = tid; w < nsl; w += T) list[w] = gci[1 + n + w];
+      c_prepare_slices<T>(P, gci, sl, chead, nsl, d, tid);
       const uint32_t dim = 1u << d;
       for (uint32_t i = tid; i < dim; i += T) psi[i] = make_double2(i == 0u ? 1.0 : 0.0, 0.0);
     }
@@ -402,9 +451,9 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
     double e_part;
     {
       const int per = (1 << d) / T;                 // amplitudes per thread
-      if (per <= 2) e_part = c_hphase<2, T, GRAD>(P, psi, lam, chead, list, nsl, d, tid);
-      else if (per <= 4) e_part = c_hphase<4, T, GRAD>(P, psi, lam, chead, list, nsl, d, tid);
-      else e_part = c_hphase<8, T, GRAD>(P, psi, lam, chead, list, nsl, d, tid);
+      if (per <= 2) e_part = c_hphase<2, T, GRAD>(P, psi, lam, chead, sl, nsl, d, tid);
+      else if (per <= 4) e_part = c_hphase<4, T, GRAD>(P, psi, lam, chead, sl, nsl, d, tid);
+      else e_part = c_hphase<8, T, GRAD>(P, psi, lam, chead, sl, nsl, d, tid);
     }
 #pragma unroll
     for (int off = TW / 2; off > 0; off >>= 1) e_part += shfl_xor_d(e_part, off, tmask);

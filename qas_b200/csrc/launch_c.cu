@@ -47,10 +47,11 @@ int qas_evalc_team_threads(int slot_bits) { return slot_bits <= 8 ? 32 : slot_bi
 cudaError_t qas_launch_evalc(qas_ctx *ctx, const EvalCParams &P, int max_work, bool grad, cudaStream_t st) {
   const int T = qas_evalc_team_threads(P.slot_bits);
   // QAS_B200_C_MINB (tuning knob, one-warp teams): CTAs per SM the register allocation is bounded for -- 4 (128
-  // registers, default), 6 (85) or 8 (64): more circuits in flight against spills in the two-gate adjoint pass
-  static const int minb32 = []() { const char *e = getenv("QAS_B200_C_MINB"); const int v = e ? atoi(e) : 4; return (v == 6 || v == 8) ? v : 4; }();
+  // registers, default), 5 (102), 6 (85) or 8 (64): more circuits in flight against spills in the two-gate adjoint pass
+  static const int minb32 = []() { const char *e = getenv("QAS_B200_C_MINB"); const int v = e ? atoi(e) : 4; return (v == 5 || v == 6 || v == 8) ? v : 4; }();
 #define QAS_CCASE(T_, BLK_, MINB_) \
   return grad ? launch_evalc_t<T_, true, BLK_, MINB_>(ctx, P, max_work, st) : launch_evalc_t<T_, false, BLK_, MINB_>(ctx, P, max_work, st);
+  if (T == 32 && minb32 == 5) { QAS_CCASE(32, 128, 5) }
   if (T == 32 && minb32 == 6) { QAS_CCASE(32, 128, 6) }
   if (T == 32 && minb32 == 8) { QAS_CCASE(32, 128, 8) }
   if (T == 32) { QAS_CCASE(32, 128, 4) }
