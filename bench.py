@@ -345,6 +345,7 @@ def run_b200(args):
     # step i (so the untimed flush never hides it) and must be FINISHED before the end event of step i + 1 (so
     # it is either overlapped with timed kernels or shows up in that step's time); the exchange of the last step
     # has nothing to hide behind and is added in full.
+    serial_exchange = os.environ.get("QAS_BENCH_EXCHANGE", "overlap") == "serial"
     flush.zero_()
     for i in range(args.steps):
         e0[i].record(stream)
@@ -353,7 +354,11 @@ def run_b200(args):
             stream.wait_event(x1[i - 1])
         e1[i].record(stream)
         flush.zero_()
-        if world > 1:
+        if world > 1 and serial_exchange:      # diagnostic: the exchange on the compute stream, nothing overlapped
+            x0[i].record(stream)
+            exchange(i, B * world)
+            x1[i].record(stream)
+        elif world > 1:
             fl[i].record(stream)
             with torch.cuda.stream(side):
                 side.wait_event(fl[i])

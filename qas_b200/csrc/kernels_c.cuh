@@ -260,42 +260,50 @@ __device__ __forceinline__ void c_adj_group(double2 *psi, double2 *lam, const ui
 
 template <int T>
 __device__ __forceinline__ void c_prepare_slices(const EvalCParams &P, const uint32_t *gci, uint4 *sl, uint32_t *chead, int nsl,
-                                                 int d, int tid) {
+                                                 int d, int tid, uint32_t ent0, uint32_t hb) {
   const int n = P.n;
-  for (int s = tid; s < nsl; s += T) {
-    const uint32_t ent = gci[1 + n + s];
-    const uint32_t si = ent >> 16;
+  // (warp-uniform trip count: the basis vectors travel by shuffle from the lanes that loaded them)
+  for (int s0 = 0; s0 < nsl; s0 += T) {
+    const int s = s0 + tid;
+    const bool on = s < nsl;
+    const uint32_t ent = s0 == 0 ? ent0 : (on ? gci[1 + n + s] : 0u);
+    const uint32_t si = on ? ent >> 16 : 0u;
     const uint4 info = __ldg(P.sinfo + si);
     uint4 r = make_uint4((ent & 0xfffu) | (si << 16) | ((int)si >= P.S_real ? CS_IMAG : 0u), 0u, 0u, 0u);
-    if (info.x <= 4u) {
-      const uint32_t z0 = info.y & 0xffffu, z1 = info.y >> 16, z2 = info.z & 0xffffu, z3 = info.z >> 16;
-      uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
-      for (int k = 0; k < d; ++k) {
-        const uint32_t bk = gci[1 + k];
-        c0 |= (uint32_t)(__popc(bk & z0) & 1) << k;
-        c1 |= (uint32_t)(__popc(bk & z1) & 1) << k;
-        c2 |= (uint32_t)(__popc(bk & z2) & 1) << k;
-        c3 |= (uint32_t)(__popc(bk & z3) & 1) << k;
-      }
-      uint32_t D = 0u;
+    const bool small = info.x <= 4u;
+    const uint32_t z0 = info.y & 0xffffu, z1 = info.y >> 16, z2 = info.z & 0xffffu, z3 = info.z >> 16;
+    uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
+    for (int k = 0; k < d; ++k) {
+      const uint32_t bk = __shfl_sync(0xffffffffu, hb, 1 + k);
+      c0 |= (uint32_t)(__popc(bk & z0) & 1) << k;
+      c1 |= (uint32_t)(__popc(bk & z1) & 1) << k;
+      c2 |= (uint32_t)(__popc(bk & z2) & 1) << k;
+      c3 |= (uint32_t)(__popc(bk & z3) & 1) << k;
+    }
+    // nibble a of D = sign index of a * T = xor of e_j over the set bits j of a, e_j = index of the single bit T << j
+    constexpr int LT = (T == 32) ? 5 : (T == 64) ? 6 : (T == 128) ? 7 : 8;
+    uint32_t e[3];
 #pragma unroll
-      for (int a = 1; a < 8; ++a) {
-        const uint32_t x = (uint32_t)(a * T);
-        D |= (uint32_t)((__popc(x & c0) & 1) | ((__popc(x & c1) & 1) << 1) | ((__popc(x & c2) & 1) << 2) | ((__popc(x & c3) & 1) << 3)) << (4 * a);
-      }
+    for (int j = 0; j < 3; ++j)
+      e[j] = ((c0 >> (LT + j)) & 1u) | (((c1 >> (LT + j)) & 1u) << 1) | (((c2 >> (LT + j)) & 1u) << 2) | (((c3 >> (LT + j)) & 1u) << 3);
+    const uint32_t D = ((e[0] * 0x11111111u) & 0xf0f0f0f0u) ^ ((e[1] * 0x11111111u) & 0xff00ff00u) ^ ((e[2] * 0x11111111u) & 0xffff0000u);
+    if (small) {
       r.y = c0 | (c1 << 16);
       r.z = c2 | (c3 << 16);
       r.w = D;
     } else {
       r.x |= CS_FLAT;
     }
-    sl[s] = r;
+    if (on) sl[s] = r;
   }
-  for (int a = tid; a < 8; a += T) {
-    const uint32_t x = (uint32_t)(a * T);
+  {
+    const uint32_t x = (uint32_t)((tid & 7) * T);
     uint32_t ph = 0u;
-    for (int k = 0; k < d; ++k) ph ^= ((x >> k) & 1u) ? gci[1 + k] : 0u;
-    chead[CS_PHA + a] = ph;
+    for (int k = 0; k < d; ++k) {
+      const uint32_t bk = __shfl_sync(0xffffffffu, hb, 1 + k);
+      ph ^= ((x >> k) & 1u) ? bk : 0u;
+    }
+    if (tid < 8) chead[CS_PHA + tid] = ph;
   }
 }
 
@@ -400,23 +408,42 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
   const int count = *P.count;
   const int n = P.n;
 
+  // Work queue with the next circuit's index in flight: lane 0 draws the queue slot of circuit i + 1 while circuit
+  // i is being set up and reads its batch index after the forward sweep, so that neither the L2 atomic nor the
+  // order look-up sits on the serial path of a team (four dependent L2 round trips per circuit before).
+  int qnext = 0, bnext = -1;
+  if (tid == 0) {
+    qnext = atomicAdd(P.work_counter, 1);
+    bnext = qnext < count ? P.order[qnext] : -1;
+  }
   for (;;) {
-    if (tid == 0) *bslot = atomicAdd(P.work_counter, 1);
+    if (tid == 0) *bslot = bnext;
     team_sync<T>(team, tmask);
-    const int qi = *bslot;
-    if (qi >= count) break;
-    const int b = P.order[qi];
+    const int b = *bslot;
+    if (b < 0) break;
+    if (tid == 0) qnext = atomicAdd(P.work_counter, 1);
     long long clk_prev = 0;
     if (P.phase_clk && tid == 0) clk_prev = clock64();
     // ---- 1. fetch the record, zero the support
     const uint32_t *grec = P.tape + (size_t)b * P.rec_stride;
     const uint32_t *gci = grec + QAS_REC_HDR + (size_t)P.ops_cap * QAS_OP_WORDS;
-    const int nops = (int)grec[0], status = (int)grec[1], d = (int)grec[2], ngroups = (int)grec[3], nsl = (int)gci[0];
+    // everything a lane needs from the record is requested before the header is consumed: one L2 round trip
+    // instead of header -> body -> slice list
+    const int recw = QAS_REC_HDR + P.ops_cap * QAS_OP_WORDS;
+    uint32_t early[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int w = tid + j * T; early[j] = w < recw ? grec[w] : 0u; }
+    const uint32_t ent0 = tid < P.S ? gci[1 + n + tid] : 0u;           // this lane's slice entry
+    const uint32_t hb = lane <= QAS_CT_MAX_D ? gci[lane] : 0u;         // nsl, B_0 .. (every warp of the team its own copy)
+    const int nops = (int)grec[0], status = (int)grec[1], d = (int)grec[2], ngroups = (int)grec[3];
+    const int nsl = (int)__shfl_sync(0xffffffffu, hb, 0);
     {
       const int used = QAS_REC_HDR + nops * QAS_OP_WORDS;
-      for (int w = tid; w < used; w += T) rec[w] = grec[w];
-      for (int w = tid; w <= d; w += T) chead[w] = gci[w];
-      c_prepare_slices<T>(P, gci, sl, chead, nsl, d, tid);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const int w = tid + j * T; if (w < used) rec[w] = early[j]; }
+      for (int w = tid + 4 * T; w < used; w += T) rec[w] = grec[w];
+      if (tid <= d) chead[tid] = hb;
+      c_prepare_slices<T>(P, gci, sl, chead, nsl, d, tid, ent0, hb);
       const uint32_t dim = 1u << d;
       for (uint32_t i = tid; i < dim; i += T) psi[i] = make_double2(i == 0u ? 1.0 : 0.0, 0.0);
     }
@@ -446,6 +473,7 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
       }
     }
 
+    if (tid == 0) bnext = qnext < count ? P.order[qnext] : -1;
     if (P.phase_clk && tid == 0) { const long long c_ = clock64(); atomicAdd(P.phase_clk + 1, (unsigned long long)(c_ - clk_prev)); clk_prev = c_; }
     // ---- 3. lambda = H psi on the support, E = Re <psi|lambda>
     double e_part;
