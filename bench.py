@@ -18,6 +18,7 @@ Prints ONE JSON line on rank 0.
 import argparse
 import json
 import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA starts: see qas_b200/__init__.py
 import statistics
 import subprocess
 import sys
@@ -375,7 +376,12 @@ def run_b200(args):
     # the exchange of the last step has nothing left to hide behind: its whole duration is exposed
     tail_ms = comm_ms[-1] if comm_ms else 0.0
     total_ms = torch.tensor([sum(step_ms) + tail_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        mine_ms = torch.tensor([float(total_ms.item()) / args.steps, statistics.mean(eval_ms)], dtype=torch.float64, device=dev)
+        all_ms = torch.empty(2 * world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(all_ms, mine_ms)
+        per_rank = all_ms.view(world, 2).cpu().numpy()
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     launches = ev.stats()["launches"] - launches0        # this library's kernels only
@@ -503,6 +509,7 @@ def run_b200(args):
     }
     if world > 1:
         line["parity_check"] = parity
+        line["per_rank"] = {"ms_per_step": [round(float(x), 4) for x in per_rank[:, 0]], "kernel_ms": [round(float(x), 4) for x in per_rank[:, 1]]}
         line["comm_us_per_step"] = 1e3 * statistics.mean(comm_ms)
         line["comm_exposed_us_per_step"] = 1e3 * tail_ms / args.steps
         line["config"]["exchange"] = ("one all_gather of [rewards | gradient sum] per rank (%d B) + fixed-order reduction kernel, on a "
@@ -844,7 +851,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="lih_10q", choices=sorted(WORKLOADS) + sorted(LARGE_WORKLOADS))
     ap.add_argument("--batch", type=int, default=65536, help="circuits per GPU per step")
-    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=int(os.environ.get("QAS_BENCH_SEED", "0")))
     ap.add_argument("--tune", action="store_true", help="kernel tuning: skip the CPU-baseline leg")
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads block of the default line")
     ap.add_argument("--compact", action="store_true", help="also write the per-circuit compact gradients [B][p][l] in the timed step")

@@ -5,6 +5,11 @@
 
 thread_local std::string g_create_error;
 
+// The support bins of one call run on forked streams; with the driver's default of 8 hardware work queues they
+// alias (with each other, and with NCCL's streams in a multi-GPU process) and serialise.  The driver reads the
+// variable when the CUDA context is created: set it when the library is loaded, unless the host already did.
+__attribute__((constructor)) static void qas_request_work_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 // ---------------------------------------------------------------------------------- info
 extern "C" int qas_abi_version(void) { return QAS_ABI_VERSION; }
 extern "C" const char *qas_build_info(void) {

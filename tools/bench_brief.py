@@ -14,6 +14,6 @@ for path in sys.argv[1:]:
         d.get("config", {}).get("workload"), d["value"] / 1e6, (d.get("e2e") or {}).get("value", 0) / 1e6,
         (d.get("reward_only") or {}).get("value", 0) / 1e6, d["ms_per_step"], r.get("kernel_ms", 0), r.get("frac", 0),
         d.get("gpu_launches"), (d.get("clocks") or {}).get("sm_mhz")))
-    for k in ("parity_check", "other_workloads", "comm_us_per_step"):
+    for k in ("parity_check", "other_workloads", "comm_us_per_step", "per_rank"):
         if k in d:
             print("   ", k, json.dumps(d[k]))
