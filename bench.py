@@ -409,7 +409,9 @@ def run_b200(args):
     reward_value = world * B * args.steps / (float(reward_ms.item()) * 1e-3)
 
     # ---- end to end through the public host API: pinned host buffers in, host results out
-    h_k = torch.from_numpy(ks).pin_memory()
+    # structure lists as one byte per key when the pool allows it (QAS_F_K_U8: a quarter of the upload)
+    k8 = c <= 256
+    h_k = torch.from_numpy(ks.astype(np.uint8) if k8 else ks).pin_memory()
     h_params = torch.from_numpy(params).pin_memory()
     hk_np, hp_np = h_k.numpy(), h_params.numpy()
     for _ in range(2):
@@ -423,7 +425,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(e2e_s.item())
-    h2d = ks.nbytes + params.nbytes
+    h2d = hk_np.nbytes + params.nbytes
     d2h = out["energy"].nbytes + out["grad_dense"].nbytes
     # ... and with plain (pageable) NumPy arrays, which is what the drop-in model classes receive from search()
     pk_np, pp_np = ks.copy(), params.copy()
@@ -497,9 +499,10 @@ def run_b200(args):
                    "circuits_per_gpu_per_step": B, "pauli_terms": T, "xmask_groups": S,
                    "source": "search-scripts-legacy/" + WORKLOADS[name][7], "l2_flush_between_steps": True,
                    "parallelism": "circuits sharded over %d GPU(s); all_gather rewards + all_reduce gradient" % world},
-        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "key_dtype": "u8" if k8 else "i32", "host_buffers": "pinned"},
         "e2e_pageable": {"value": e2e_pageable, "unit": "evals/s",
-                         "note": "same call with pageable NumPy arrays (what search() hands the drop-in classes)"},
+                         "note": "same call with pageable int32 NumPy arrays (what search() hands the drop-in classes)"},
         "reward_only": {"value": reward_value, "unit": "evals/s", "ms_per_step": float(reward_ms.item()) / args.steps,
                         "note": "energy without gradient (getReward), same batch, device-resident inputs"},
         "gpu_launches": int(launches),
@@ -633,6 +636,16 @@ def run_largestate(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = be.bytes / (be.kernel_ms * 1e-3) / 1e9
+    # The gate passes are co-bound by the FP64 pipe: a 2x2 complex unitary on an amplitude pair is 16 DFMA-class
+    # instructions (32 flop with FMA = 2, the convention of the live DFMA peak), CNOTs are folded into the
+    # indexing and cost none.  Both rooflines are reported; the larger of the two peak times bounds a pass.
+    from qas_b200.evaluator import fp64_peak_tflops
+    n_u = sum(1 for g in gl if g[0] not in ("CNOT", "SWAP", "PlaceHolder"))
+    flop_step = 32.0 * n_u * 2.0 ** (sim.n_local - 1)
+    fp64_peak = fp64_peak_tflops(local)
+    fp64_ach = flop_step * steps / (be.kernel_ms * 1e-3) / 1e12
+    hbm_floor_ms = be.bytes / steps / (peak * 1e9) * 1e3
+    fp64_floor_ms = flop_step / (fp64_peak * 1e12) * 1e3
     # CPU baseline: the same algorithm through the NumPy slab backend (tests/sv_numpy_backend.py) on a 22-qubit,
     # one-layer sample, scaled by 2^(n - 22) * L (the work is linear in both)
     cpu_baseline = None
@@ -664,7 +677,14 @@ def run_largestate(args):
                      "kernel": "sv_block_kernel", "kernel_ms": be.kernel_ms / steps, "passes_per_step": be.passes / steps,
                      "tma_passes_per_step": be.tma_passes / steps,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                     "note": "algorithmic bytes = passes * 32 * 2^n_local per GPU (one read + one write of the slab per pass)"},
+                     "note": "algorithmic bytes = passes * 32 * 2^n_local per GPU (one read + one write of the slab per pass)",
+                     "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
+                              "unitary_gates": n_u, "flop_per_step_per_gpu": flop_step,
+                              "peak_source": "measured live: qas_fp64_peak_tflops DFMA micro-benchmark"},
+                     "floor_ms_per_step": {"hbm": hbm_floor_ms, "fp64": fp64_floor_ms,
+                                           "note": "time of one step's gate passes at the HBM peak / at the FP64 peak: the passes "
+                                                   "cannot be faster than the larger of the two, so the HBM fraction is capped at "
+                                                   "hbm / max(hbm, fp64)"}},
         "cpu_baseline": cpu_baseline,
     }
     if world > 1:

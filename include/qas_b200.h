@@ -81,6 +81,9 @@ typedef struct {
                                   /* one-reward-at-a-time rollouts of mcts.py:100-105,181 then cost   */
                                   /* one k upload, the kernels and an 8-byte read-back                */
 
+#define QAS_F_K_U8 0x8u            /* `k` holds one byte per key (uint8_t[B][p]; pools of <= 256 entries): a     */
+                                  /* quarter of the structure-list upload; widened to int32 on the device      */
+
 /* Threading / stream contract: a context is NOT thread-safe and owns one set of scratch buffers (tape records,
  * gate tables, cross matrices, bin queues, reduction partials).  Use it from one thread and one stream at a
  * time: a second call may only be issued on another stream after the first one has completed (device-pointer

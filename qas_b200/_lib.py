@@ -22,6 +22,7 @@ QAS_INIT_PLUS = 2
 QAS_F_DEVICE_PTRS = 0x1
 QAS_F_GRAD_SUM = 0x2
 QAS_F_PARAMS_RESIDENT = 0x4
+QAS_F_K_U8 = 0x8
 
 QAS_OP_WORDS = 5
 

@@ -264,6 +264,9 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   guard(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
   cx->num_sms = prop.multiProcessorCount;
   guard(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  guard(cudaStreamCreateWithFlags(&cx->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  guard(cudaEventCreateWithFlags(&cx->copy_gate, cudaEventDisableTiming), "cudaEventCreate");
+  guard(cudaEventCreateWithFlags(&cx->copy_done, cudaEventDisableTiming), "cudaEventCreate");
   guard(cudaEventCreate(&cx->ev0), "cudaEventCreate");
   guard(cudaEventCreate(&cx->ev1), "cudaEventCreate");
   guard(cudaEventCreate(&cx->ek0), "cudaEventCreate");
@@ -433,6 +436,10 @@ extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   if (ctx->ek1) cudaEventDestroy(ctx->ek1);
   for (int i = 0; i < 8; ++i) if (ctx->sev[i]) cudaEventDestroy(ctx->sev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->copy_gate) cudaEventDestroy(ctx->copy_gate);
+  if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+  cudaFree(ctx->d_k8);
   delete ctx;
   return QAS_OK;
 }
@@ -510,6 +517,17 @@ extern "C" int qas_set_params(qas_ctx *ctx, int p, const double *params) {
   return QAS_OK;
 }
 
+// QAS_F_K_U8: structure lists uploaded as one byte per key, widened on the device
+__global__ void widen_keys_kernel(const uint8_t *src, int32_t *dst, size_t n) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const uchar4 v = *reinterpret_cast<const uchar4 *>(src + i);
+    *reinterpret_cast<int4 *>(dst + i) = make_int4(v.x, v.y, v.z, v.w);
+  } else {
+    for (size_t j = i; j < n; ++j) dst[j] = src[j];
+  }
+}
+
 extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, const double *params,
                               double *energy, double *grad_compact, double *grad_dense,
                               uint32_t flags, void *stream) {
@@ -517,8 +535,10 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   if (B <= 0 || p <= 0 || p > 65535 || !k || (!params && !(flags & QAS_F_PARAMS_RESIDENT)) || !energy)
     return fail(ctx, QAS_ERR_INVALID, "bad arguments to qas_eval_batch");
   const bool dev = flags & QAS_F_DEVICE_PTRS;
+  const bool k8 = (flags & QAS_F_K_U8) != 0;
   const bool want_grad = grad_compact || grad_dense;
   const int c = ctx->c, l = ctx->l;
+  if (k8 && c > 256) return fail(ctx, QAS_ERR_INVALID, "QAS_F_K_U8 needs a pool of at most 256 entries");
   CK(cudaSetDevice(ctx->device));
   // device-pointer calls run on exactly the stream given (NULL = the CUDA default stream, which is
   // what torch.cuda.current_stream() is unless the caller changed it); host-pointer calls default to
@@ -543,14 +563,39 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   { const int rc = ensure_gate_tables(ctx, p, st); if (rc != QAS_OK) return rc; }
   if (!resident) ctx->resident_p = 0;      // the tables are about to be rebuilt from other parameters
 
+  // QAS_F_K_U8 on a small host batch: the host-side compiler and checks below read int32 keys
+  std::vector<int32_t> k_wide;
+  const uint8_t *k_bytes = reinterpret_cast<const uint8_t *>(k);
+  if (k8 && !dev && B <= 16) {
+    k_wide.assign(k_bytes, k_bytes + nk);
+    k = k_wide.data();
+  }
+  const bool k8_dev = k8 && (dev || B > 16);      // keys reach the device as bytes and are widened there
   const int32_t *dk = k;
   const double *dparams = params;
   double *denergy = energy, *dgrad = grad_compact, *ddense = grad_dense;
+  bool k_on_copy_stream = false;
+  if (k8_dev) {
+    CK(ensure(&ctx->d_k, &ctx->cap_k, (nk + 3) & ~(size_t)3));
+    dk = ctx->d_k;
+  }
   if (!dev) {
-    CK(ensure(&ctx->d_k, &ctx->cap_k, nk));
+    CK(ensure(&ctx->d_k, &ctx->cap_k, (nk + 3) & ~(size_t)3));
     CK(ensure(&ctx->d_params, &ctx->cap_params, npar));
     CK(ensure(&ctx->d_energy, &ctx->cap_energy, (size_t)B));
-    if (!(tiny && !want_grad && !small)) CK(cudaMemcpyAsync(ctx->d_k, k, nk * 4, cudaMemcpyHostToDevice, st));
+    if (k8_dev) CK(ensure(&ctx->d_k8, &ctx->cap_k8, (nk + 3) & ~(size_t)3));
+    if (B > 16 && !capturing) {
+      // large batches: the upload of the structure lists runs on the copy stream, so that the memsets and the
+      // gate-table kernel of this call overlap it; the tape compiler waits for it
+      CK(cudaEventRecord(ctx->copy_gate, st));
+      CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_gate, 0));
+      if (k8_dev) CK(cudaMemcpyAsync(ctx->d_k8, k_bytes, nk, cudaMemcpyHostToDevice, ctx->copy_stream));
+      else CK(cudaMemcpyAsync(ctx->d_k, k, nk * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+      k_on_copy_stream = true;
+    } else if (!(tiny && !want_grad && !small)) {
+      CK(cudaMemcpyAsync(ctx->d_k, k, nk * 4, cudaMemcpyHostToDevice, st));
+    }
     // the reference's asserts on k (utils.py:12-15).  Batches compiled on the host are checked now;
     // for the others the device code tolerates any key (status word -> NaN energy), so the check
     // runs on the host while the kernels do (below, before the results are copied back)
@@ -633,6 +678,21 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   if (want_grad) { CK(cudaMemsetAsync(dgrad, 0, ng * 8, st)); ctx->stats.launches += 1; }
   if (!small) CK(cudaMemsetAsync(ctx->d_bins, 0, sizeof(int) * 2 * QAS_MAX_BINS, st));   // bin counts + work-queue heads
   stamp(1);
+  // gate table first (it only needs the parameters), then the structure lists: the upload has had the memsets and
+  // this kernel to hide behind
+  if (!resident) {
+    build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
+    CK(cudaGetLastError());
+    ctx->stats.launches += 1;
+  }
+  stamp(2);
+  if (k_on_copy_stream) CK(cudaStreamWaitEvent(st, ctx->copy_done, 0));
+  if (k8_dev) {
+    const uint8_t *src8 = dev ? k_bytes : ctx->d_k8;
+    widen_keys_kernel<<<(unsigned)((nk / 4 + 256) / 256), 256, 0, st>>>(src8, ctx->d_k, nk);
+    CK(cudaGetLastError());
+    ctx->stats.launches += 1;
+  }
   // Tiny host-pointer batches (the one-reward-at-a-time rollouts of the tree search): the tape
   // compiler and pass planner are host-callable, and one CPU core runs them in a few microseconds,
   // whereas a single GPU thread needs tens -- compile here and upload the records.
@@ -707,14 +767,8 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     ctx->stats.launches += 1;
   }
   CK(cudaGetLastError());
-  stamp(2);
-  if (!resident) {
-    build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
-    CK(cudaGetLastError());
-    ctx->stats.launches += 1;
-  }
-  if (!tiny && !capturing) CK(cudaEventRecord(ctx->ek0, st));
   stamp(3);
+  if (!tiny && !capturing) CK(cudaEventRecord(ctx->ek0, st));
   auto launch_classic = [&](cudaStream_t s_) { return want_grad ? qas_launch_eval_grad(ctx, P, s_) : qas_launch_eval_nograd(ctx, P, s_); };
   if (!use_c) {
     CK(launch_classic(st));
@@ -812,7 +866,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   }
   if (ctx->stage_times) {
     cudaStreamSynchronize(st);
-    const char *names[7] = {"memset", "compile_tapes", "gate_table", "eval", "finalize", "chunk_reduce", "final_reduce"};
+    const char *names[7] = {"memset", "gate_table", "compile_tapes", "eval", "finalize", "chunk_reduce", "final_reduce"};
     fprintf(stderr, "[qas stage times] B=%d:", B);
     for (int i = 0; i < (grad_dense ? 7 : 5); ++i) {
       float ms = 0.f;
@@ -828,7 +882,8 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     if (B > 16) {      // deferred range check of the structure lists; branch-free so that it vectorises
       uint32_t bad = 0;
       const uint32_t cu = (uint32_t)c;
-      for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k[i] >= cu);
+      if (k8) for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k_bytes[i] >= cu);
+      else for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k[i] >= cu);
       if (bad) {
         cudaStreamSynchronize(st);
         return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");

@@ -63,6 +63,9 @@ struct qas_ctx {
   int tab_p = 0;
   int resident_p = 0;              // depth of the parameter super-set left on the device by qas_set_params (0: none)
   int32_t *d_k = nullptr;  size_t cap_k = 0;
+  uint8_t *d_k8 = nullptr;  size_t cap_k8 = 0;     // QAS_F_K_U8 uploads (widened into d_k on the device)
+  cudaStream_t copy_stream = nullptr;            // structure-list upload of host-pointer calls (overlaps memsets + gate table)
+  cudaEvent_t copy_gate = nullptr, copy_done = nullptr;
   double *d_params = nullptr; size_t cap_params = 0;
   double *d_energy = nullptr; size_t cap_energy = 0;
   double *d_grad = nullptr; size_t cap_grad = 0;

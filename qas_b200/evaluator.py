@@ -67,9 +67,12 @@ class BatchEvaluator:
 
     # ------------------------------------------------------------------ host-array entry
     def evaluate(self, ks, params, want_grad=True, dense=True, compact=False, avg=True):
-        """ks: int array [B, p]; params: float64 [p, c, l].
+        """ks: int array [B, p]; params: float64 [p, c, l].  A uint8 array (pools of <= 256 entries) is uploaded
+        as it is -- a quarter of the bytes -- and widened on the device (QAS_F_K_U8).
         Returns dict(energy[B], grad_dense[p,c,l] | None, grad_compact[B,p,l] | None)."""
-        ks = np.ascontiguousarray(np.asarray(ks, dtype=np.int32))
+        ks = np.asarray(ks)
+        k8 = ks.dtype == np.uint8 and self.c <= 256
+        ks = np.ascontiguousarray(ks if k8 else ks.astype(np.int32, copy=False))
         if ks.ndim == 1:
             ks = ks[None, :]
         params = np.ascontiguousarray(np.asarray(params, dtype=np.float64))
@@ -78,7 +81,7 @@ class BatchEvaluator:
         energy = np.empty(B, dtype=np.float64)
         gd = np.empty((p, self.c, self.l), dtype=np.float64) if (want_grad and dense) else None
         gc = np.empty((B, p, self.l), dtype=np.float64) if (want_grad and compact) else None
-        flags = 0 if avg else _lib.QAS_F_GRAD_SUM
+        flags = (0 if avg else _lib.QAS_F_GRAD_SUM) | (_lib.QAS_F_K_U8 if k8 else 0)
         rc = self._lib.qas_eval_batch(
             self._h, B, p, ks.ctypes.data, params.ctypes.data, energy.ctypes.data,
             gc.ctypes.data if gc is not None else None,
@@ -97,7 +100,8 @@ class BatchEvaluator:
         assert ks.is_contiguous() and params.is_contiguous() and energy.is_contiguous()
         assert tuple(params.shape) == (p, self.c, self.l)
         assert energy.numel() == B
-        flags = _lib.QAS_F_DEVICE_PTRS | (0 if avg else _lib.QAS_F_GRAD_SUM)
+        import torch
+        flags = _lib.QAS_F_DEVICE_PTRS | (0 if avg else _lib.QAS_F_GRAD_SUM) | (_lib.QAS_F_K_U8 if ks.dtype == torch.uint8 else 0)
         sp = ctypes.c_void_p(stream.cuda_stream) if stream is not None else None
         rc = self._lib.qas_eval_batch(
             self._h, B, p, ks.data_ptr(), params.data_ptr(), energy.data_ptr(),

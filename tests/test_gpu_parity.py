@@ -639,3 +639,34 @@ def test_property_random_legal_structure_lists_match_oracle(n, p, seed, init_kin
         g = sim.grad_adjoint(n, k, pool.pool, params, terms, init)
         for i, key in enumerate(k):
             assert np.max(np.abs(out["grad_compact"][b, i] - g[i, key])) <= G_TOL
+
+
+@pytest.mark.parametrize("cfg,B", [("lih_10q", 5), ("lih_10q", 301), ("h2o_8q", 77), ("h2_4q_hf", 130)])
+def test_uint8_structure_lists_equal_int32(cfg, B):
+    """QAS_F_K_U8: keys uploaded as bytes and widened on the device give bit-identical results (host batches
+    compiled on the host, large host batches through the copy stream, device-resident batches)."""
+    import torch
+    mname, n, p, mk, lim = helpers.CONFIGS[cfg]
+    model = helpers.get_model(mname)
+    pool = mk()
+    c = len(pool)
+    params = np.random.default_rng(5).standard_normal((p, c, 3))
+    ks = sample_structure_lists(pool, p, lim, B, seed=11)
+    a = model.evaluate_batch(ks, params, pool, want_grad=True, compact=True)
+    b = model.evaluate_batch(ks.astype(np.uint8), params, pool, want_grad=True, compact=True)
+    assert np.array_equal(a["energy"], b["energy"])
+    assert np.array_equal(a["grad_compact"], b["grad_compact"])
+    assert np.array_equal(a["grad_dense"], b["grad_dense"])
+    ev = model.evaluator(pool, 3)
+    dev = torch.device("cuda", ev.device)
+    e8 = torch.empty(B, dtype=torch.float64, device=dev)
+    g8 = torch.empty(p, c, 3, dtype=torch.float64, device=dev)
+    ev.evaluate_device(torch.from_numpy(ks.astype(np.uint8)).to(dev), torch.from_numpy(params).to(dev), e8, None, g8)
+    torch.cuda.synchronize()
+    assert np.array_equal(e8.cpu().numpy(), a["energy"])
+    assert np.array_equal(g8.cpu().numpy(), a["grad_dense"])
+    # a key outside the pool is still refused (utils.py:12-15)
+    bad = ks.astype(np.uint8).copy()
+    bad[0, 0] = c
+    with pytest.raises(AssertionError):
+        model.evaluate_batch(bad, params, pool, want_grad=False)
