@@ -140,33 +140,53 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        """nvidia-smi needs ~0.1-0.3 s before its first row: start it BEFORE the warm-up steps, then call mark()
+        when the timed region begins."""
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+        self.first = 0
+
+    def mark(self):
+        """the timed region starts here: rows sampled before it (warm-up, idle) are not used"""
+        self.first = len(self.rows)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def samples(self):
+        return len(self.rows) - self.first
+
+    def stop(self, keep_busy=None, want=3, budget_s=2.0):
+        """keep_busy: callable that runs one more (untimed) step of the same workload; a timed region shorter than
+        the sampling period is extended with such steps until `want` rows were taken under load."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        extended = 0
+        t0 = time.perf_counter()
+        while keep_busy is not None and self.samples() < want and time.perf_counter() - t0 < budget_s:
+            keep_busy()
+            extended += 1
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[self.first:]
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 7:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if extended:
+            out["untimed_steps_added_for_sampling"] = extended
+        return out
 
 
 # ------------------------------------------------------------------------------- CPU arms
@@ -330,11 +350,20 @@ def run_b200(args):
 
     launches0 = ev.stats()["launches"]
     sampler = ClockSampler(local)
+
+    def busy_step():
+        compute(0)
+        torch.cuda.synchronize()
+
     if rank == 0:
         sampler.start()
+        t_w = time.perf_counter()
+        while not sampler.rows and sampler.proc is not None and time.perf_counter() - t_w < 2.0:
+            busy_step()              # nvidia-smi start-up: the GPU stays under load until its first row
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark()
     e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     x0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -383,8 +412,8 @@ def run_b200(args):
         dist.all_gather_into_tensor(all_ms, mine_ms)
         per_rank = all_ms.view(world, 2).cpu().numpy()
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if rank == 0 else None
     launches = ev.stats()["launches"] - launches0        # this library's kernels only
+    clocks = sampler.stop(keep_busy=busy_step) if rank == 0 else None
     launches += args.steps if world > 1 else 0            # + qas_reduce_rows per exchange
     total_s = float(total_ms.item()) * 1e-3
     value = world * B * args.steps / total_s
@@ -609,11 +638,13 @@ def run_largestate(args):
     torch.cuda.synchronize()
     be = sim.backend
     be.passes, be.tma_passes, be.kernel_ms, be.bytes, sim.swaps = 0, 0, 0.0, 0.0, 0
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)              # nvidia-smi start-up (a step is tens of milliseconds: rows follow by themselves)
+        sampler.mark()
     if world > 1:
         be.swap_ms()
         dist.barrier()
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
