@@ -298,12 +298,29 @@ def run_b200(args):
     # all_gather of the packed rows, then a fixed-order sum of the gathered gradient rows scaled by 1 / (B * world)
     # (qas_reduce_rows: bit-identical on every rank).  Two send / receive buffers alternate so that the exchange of
     # step i runs on a side stream while the kernels of step i + 1 do.
-    packs = [torch.empty(B + npar, dtype=torch.float64, device=dev) for _ in range(2 if world > 1 else 1)]
-    gathered = [torch.empty(world * (B + npar), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    nrow = (B + npar + 1) & ~1
+    packs = [torch.zeros(nrow, dtype=torch.float64, device=dev) for _ in range(2 if world > 1 else 1)]
+    gathered = [torch.empty(world * nrow, dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    # Exchange over NVLink peer memory (csrc/exchange.cu: one push kernel + flag wait + fixed-order reduction) when
+    # torch symmetric memory can map the receive buffers into the peers; otherwise ONE NCCL all-gather + reduction.
+    px, px_why = None, None
+    if world > 1:
+        if os.environ.get("QAS_BENCH_EXCHANGE", "") != "nccl":
+            try:
+                from qas_b200.distributed import PeerExchange
+                px = PeerExchange(nrow, dev)
+            except Exception as exc:                       # noqa: BLE001 -- any failure means "not available here"
+                px_why = "%s: %s" % (type(exc).__name__, str(exc).splitlines()[0][:160])
+        else:
+            px_why = "QAS_BENCH_EXCHANGE=nccl"
+        agree = torch.tensor([1 if px is not None else 0], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if not int(agree.item()):
+            px = None
     d_mean = torch.empty(p, c, 3, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
     stream = torch.cuda.current_stream()
-    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    side = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None   # the exchange kernels take the first free CTA slots
 
     def compute(i, kk=None):
         pk = packs[i % len(packs)]
@@ -311,16 +328,26 @@ def run_b200(args):
         nb = kk.shape[0]
         # per-circuit energies + the batch-mean dense gradient, which is all search() consumes (mcts.py:340-347);
         # --compact also materialises the per-circuit [B][p][l] gradients.  Multi-GPU: gradient SUM per rank.
-        ev.evaluate_device(kk, d_params, pk[:nb], d_gc if (args.compact and nb == B) else None, pk[B:].view(p, c, 3),
+        ev.evaluate_device(kk, d_params, pk[:nb], d_gc if (args.compact and nb == B) else None, pk[B:B + npar].view(p, c, 3),
                            avg=(world == 1), stream=stream)
 
+    last_rows = [None]
+
     def exchange(i, nb_total):
-        """the exchange step on the CURRENT stream: one all-gather + the fixed-order mean of the gradient rows"""
+        """the exchange step on the CURRENT stream: the packed rows to every rank + the fixed-order mean of the
+        gradient parts"""
+        cur = torch.cuda.current_stream()
+        if px is not None:
+            px.push(packs[i % 2], cur)
+            px.wait_reduce(B, npar, 1.0 / nb_total, d_mean, cur)
+            last_rows[0] = px.rows()
+            return
         g = gathered[i % 2]
         dist.all_gather_into_tensor(g, packs[i % 2])
-        rc = lib.qas_reduce_rows(g.data_ptr() + 8 * B, world, B + npar, npar, 1.0 / nb_total, d_mean.data_ptr(),
-                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        rc = lib.qas_reduce_rows(g.data_ptr() + 8 * B, world, nrow, npar, 1.0 / nb_total, d_mean.data_ptr(),
+                                 ctypes.c_void_p(cur.cuda_stream))
         assert rc == 0
+        last_rows[0] = g.view(world, nrow)
 
     def step_sync(i, kk=None, nb_total=None):
         compute(i, kk)
@@ -335,7 +362,7 @@ def run_b200(args):
     # ---- multi-GPU parity self-check (untimed): the sharded batch and the sharded statevector against one GPU
     parity = None
     if world > 1:
-        parity = multi_gpu_parity_check(args, name, model, pool, ev, B, p, c, rank, world, dev, packs, gathered, d_mean,
+        parity = multi_gpu_parity_check(args, name, model, pool, ev, B, p, c, rank, world, dev, packs, last_rows, d_mean,
                                         d_params, step_sync, lib)
         flag = torch.tensor([0 if (rank != 0 or parity["ok"]) else 1], device=dev)
         dist.all_reduce(flag)
@@ -348,7 +375,6 @@ def run_b200(args):
             step_sync(i)
         torch.cuda.synchronize()
 
-    launches0 = ev.stats()["launches"]
     sampler = ClockSampler(local)
 
     def busy_step():
@@ -364,6 +390,7 @@ def run_b200(args):
         dist.barrier()
     torch.cuda.synchronize()
     sampler.mark()
+    launches0 = ev.stats()["launches"]
     e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     x0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -414,7 +441,10 @@ def run_b200(args):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     launches = ev.stats()["launches"] - launches0        # this library's kernels only
     clocks = sampler.stop(keep_busy=busy_step) if rank == 0 else None
-    launches += args.steps if world > 1 else 0            # + qas_reduce_rows per exchange
+    launches += (3 if px is not None else 1) * args.steps if world > 1 else 0   # + push / wait / reduce (or qas_reduce_rows) per exchange
+    if px is not None and px.timed_out():
+        print(json.dumps({"error": "peer exchange: a rank's row did not arrive within 5 s"}), flush=True)
+        sys.exit(4)
     total_s = float(total_ms.item()) * 1e-3
     value = world * B * args.steps / total_s
     d_energy = packs[0][:B]
@@ -527,7 +557,7 @@ def run_b200(args):
         "config": {"workload": name, "model": mname, "n_qubits": n, "depth_p": p, "pool_c": c,
                    "circuits_per_gpu_per_step": B, "pauli_terms": T, "xmask_groups": S,
                    "source": "search-scripts-legacy/" + WORKLOADS[name][7], "l2_flush_between_steps": True,
-                   "parallelism": "circuits sharded over %d GPU(s); all_gather rewards + all_reduce gradient" % world},
+                   "parallelism": "circuits sharded over %d GPU(s); packed [rewards | gradient sum] rows to every rank + fixed-order mean" % world},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "key_dtype": "u8" if k8 else "i32", "host_buffers": "pinned"},
         "e2e_pageable": {"value": e2e_pageable, "unit": "evals/s",
@@ -542,6 +572,9 @@ def run_b200(args):
     if world > 1:
         line["parity_check"] = parity
         line["per_rank"] = {"ms_per_step": [round(float(x), 4) for x in per_rank[:, 0]], "kernel_ms": [round(float(x), 4) for x in per_rank[:, 1]]}
+        line["exchange"] = ("one push kernel per rank over NVLink peer memory + flag wait + fixed-order reduction (csrc/exchange.cu), "
+                            "no collective library on the data path") if px is not None else \
+                           ("NCCL all_gather_into_tensor + qas_reduce_rows (peer path not used: %s)" % px_why)
         line["comm_us_per_step"] = 1e3 * statistics.mean(comm_ms)
         line["comm_exposed_us_per_step"] = 1e3 * tail_ms / args.steps
         line["config"]["exchange"] = ("one all_gather of [rewards | gradient sum] per rank (%d B) + fixed-order reduction kernel, on a "
@@ -819,7 +852,7 @@ def run_search_epoch(args):
     print(json.dumps(line), flush=True)
 
 
-def multi_gpu_parity_check(args, name, model, pool, ev, B, p, c, rank, world, dev, packs, gathered, d_mean, d_params,
+def multi_gpu_parity_check(args, name, model, pool, ev, B, p, c, rank, world, dev, packs, last_rows, d_mean, d_params,
                            step_sync, lib):
     """Untimed self-check of both NCCL paths on the hardware the bench runs on (the GPU tests that cover them
     need >= 2 GPUs and are skipped on a one-GPU test box).
@@ -839,7 +872,7 @@ def multi_gpu_parity_check(args, name, model, pool, ev, B, p, c, rank, world, de
     # ---- (1) rewards of the sharded bench batch
     step_sync(0)
     torch.cuda.synchronize()
-    all_e = gathered[0].view(world, B + npar)[:, :B].cpu().numpy()
+    all_e = last_rows[0][:, :B].cpu().numpy()
     m = max(1, 1024 // world)
     if rank == 0:
         worst = 0.0
@@ -859,7 +892,7 @@ def multi_gpu_parity_check(args, name, model, pool, ev, B, p, c, rank, world, de
     if rank == 0:
         single = ev.evaluate(ks_s, d_params.cpu().numpy(), want_grad=True, dense=True, compact=False)
         rep["grad_max_abs"] = float(np.max(np.abs(single["grad_dense"] - d_mean.cpu().numpy())))
-        e_sh = gathered[0].view(world, B + npar)[:, :Bs // world].cpu().numpy()
+        e_sh = last_rows[0][:, :Bs // world].cpu().numpy()
         e_full = np.empty(Bs)
         for r in range(world):
             e_full[r::world] = e_sh[r]

@@ -258,6 +258,25 @@ int qas_vqls_combine(const void *N, const void *D, void *gN, const void *gD, int
 int qas_reduce_rows(const void *rows, int nrows, uint64_t row_stride, uint64_t total, double scale, void *out,
                     void *stream);
 
+/* The same exchange over NVLink peer memory, without a collective library on the data path (csrc/exchange.cu).
+ * Every rank owns a receive buffer of `world` rows plus `world` 64-bit flags (zero-initialised) that is mapped into
+ * every peer's address space (CUDA IPC / torch symmetric memory; the host passes the mapped pointers).
+ *   qas_peer_push_row: one kernel stores `count` doubles (even; 16-byte aligned) of the local packed row into
+ *     peer_rows[r] for every r < world -- the slot of THIS rank in rank r's receive buffer, r = own rank included --
+ *     and then release-stores `seq` (>= 1, increasing by one per step) into peer_flags[r].
+ *   qas_peer_wait_reduce: waits on the LOCAL flags until every rank's row of step `seq` has landed (status[0], a
+ *     device uint32 the host zero-initialises, becomes 1 if one has not after 5 s -- the call never hangs), then
+ *     out[x] = scale * sum_r rows[r * row_stride + offset + x], x < total, in the fixed order of qas_reduce_rows
+ *     (total = 0: wait only).
+ * Contract: every rank issues push(s), wait_reduce(s), push(s + 1), ... on ONE stream and alternates between two
+ * receive buffers (s & 1); a slot is then never overwritten before its reader is done, without acknowledgements.
+ * Both calls are asynchronous on `stream`.  Replaces all_gather (rewards) + all_reduce (gradient) of the batch mean
+ * of mcts.py:345-347 spread over ranks; bench.py --gpus N and qas_b200.distributed.PeerExchange use it.          */
+int qas_peer_push_row(const void *row, uint64_t count, void *const *peer_rows, void *const *peer_flags, int world,
+                      uint64_t seq, void *stream);
+int qas_peer_wait_reduce(const void *rows, int world, uint64_t row_stride, uint64_t offset, uint64_t total, double scale,
+                         void *out, const void *flags, uint64_t seq, void *status, void *stream);
+
 /* Diagnostic (contexts created with the environment variable QAS_B200_PHASE_CLOCKS=1 only): sums,
  * over all circuits evaluated so far, of the SM clock cycles a team spent in the four phases of the
  * evaluation kernel -- out4 = {prologue, forward sweep, H application + energy, adjoint sweep}.

@@ -75,7 +75,7 @@ EXPORTS = [
     "qas_eval_batch", "qas_compile_tape", "qas_compile_tape_host", "qas_plan_passes_host",
     "qas_plan_hsupport_host", "qas_compile_ctape_host",
     "qas_get_stats", "qas_debug_phase_clocks", "qas_debug_phase_clocks_c", "qas_adam_step", "qas_set_params",
-    "qas_fp64_peak_tflops", "qas_reduce_rows", "qas_batch_mean", "qas_vqls_combine", "qas_tuning_tick", "qas_adam_step_dev",
+    "qas_fp64_peak_tflops", "qas_reduce_rows", "qas_peer_push_row", "qas_peer_wait_reduce", "qas_batch_mean", "qas_vqls_combine", "qas_tuning_tick", "qas_adam_step_dev",
 ]
 # include/qas_b200_sv.h
 SV_EXPORTS = ["qas_sv_init", "qas_sv_apply", "qas_sv_plan", "qas_sv_expval", "qas_sv_norm2", "qas_sv_last_error"]
@@ -131,6 +131,11 @@ def load():
                                   ctypes.c_double, ctypes.c_double, ctypes.c_double, vp]
     lib.qas_reduce_rows.restype = ctypes.c_int
     lib.qas_reduce_rows.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_double, vp, vp]
+    lib.qas_peer_push_row.restype = ctypes.c_int
+    lib.qas_peer_push_row.argtypes = [vp, ctypes.c_uint64, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.c_int, ctypes.c_uint64, vp]
+    lib.qas_peer_wait_reduce.restype = ctypes.c_int
+    lib.qas_peer_wait_reduce.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_double, vp, vp,
+                                         ctypes.c_uint64, vp, vp]
     lib.qas_tuning_tick.restype = ctypes.c_int
     lib.qas_tuning_tick.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp]
     lib.qas_adam_step_dev.restype = ctypes.c_int

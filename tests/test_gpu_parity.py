@@ -491,6 +491,63 @@ def test_two_gpu_sharded_batch_matches_single_gpu():
     assert np.max(np.abs(grad - ref["grad_dense"])) <= 1e-12
 
 
+def _peer_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from qas_b200.distributed import PeerExchange
+    B, npar = 1001, 333                      # odd sizes: the row is padded to an even number of doubles
+    px = PeerExchange(B + npar, dev)
+    stream = torch.cuda.Stream(device=dev)
+    out = torch.empty(npar, dtype=torch.float64, device=dev)
+    worst_rows, worst_mean = 0.0, 0.0
+    for step in range(5):                    # both buffer parities, several times
+        rows_ref = [np.random.default_rng(100 * step + r).standard_normal(px.row) for r in range(world)]
+        mine = torch.from_numpy(rows_ref[rank]).to(dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream):
+            px.push(mine, stream)
+            px.wait_reduce(B, npar, 1.0 / world, out, stream)
+        stream.synchronize()
+        got = px.rows().cpu().numpy()
+        worst_rows = max(worst_rows, max(float(np.max(np.abs(got[r] - rows_ref[r]))) for r in range(world)))
+        mean = sum(rows_ref[r][B:B + npar] for r in range(world)) * (1.0 / world)     # ascending rank order
+        worst_mean = max(worst_mean, float(np.max(np.abs(out.cpu().numpy() - mean))))
+    assert not px.timed_out()
+    if rank == 0:
+        q.put((worst_rows, worst_mean))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_peer_exchange_rows_and_fixed_order_mean():
+    """qas_peer_push_row / qas_peer_wait_reduce (NVLink peer memory, no NCCL on the data path): every rank ends up
+    with every rank's packed row bit for bit and with the fixed-order mean of the gradient parts.  Skipped on a
+    1-GPU box; bench.py --gpus N runs the same path under its parity self-check."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    worst_rows, worst_mean = q.get(timeout=300)
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    assert worst_rows == 0.0
+    assert worst_mean <= 1e-15
+
+
 def test_search_and_tuning_drop_in_on_gpu():
     """The reference's driver calls, through the CUDA-backed model: a short nested-MCTS search on the
     4-qubit H2 model followed by fine-tuning must reach chemical accuracy territory, and the golden
