@@ -165,6 +165,17 @@ int qas_plan_passes_host(int n_qubits, uint32_t *ops, int num_ops, int gmax, int
                          uint32_t init_index, int swizzled, uint32_t *gdesc, int gdesc_words,
                          int *num_groups);
 
+/* Tile-pass planner of the tiled kernel for 13..16-qubit full-register circuits (host run of the code the kernel
+ * executes right before every pass; qas_b200/csrc/tape.h qas_plan_tile_pass).  ops must carry group marks
+ * (qas_plan_passes_host).  Starting at tape index `start` and walking in direction dir (+1 = adjoint sweep, -1 =
+ * forward sweep) it takes as many whole groups as keep span(xor masks) + the clow lowest index bits within tb
+ * dimensions (at most max_ops ops), writes the frame columns col[n_qubits] (pass coordinate x <-> physical index
+ * xor of the columns selected by the bits of x; columns 0..tb-1 span the tile, tb.. number the tiles) and the
+ * pivot table piv[n_qubits] (highest set bit -> column), and returns the number of ops taken in *num_ops.
+ * No reference counterpart (lightning.qubit applies one gate per pass over the dense state).            */
+int qas_plan_tile_pass_host(int n_qubits, const uint32_t *ops, int num_ops_total, int start, int dir, int tb,
+                            int clow, int max_ops, uint32_t *col, int *piv, int *num_ops);
+
 /* Final-support descriptor of the H application (host run of the planner code the tape-compile
  * kernel executes).  W = register subspace of the H blocking: w_rank <= 3 basis vectors in reduced
  * echelon form (highest-bit pivots w_pivots ascending).  hdesc (>= 32 words) receives
@@ -285,6 +296,9 @@ int qas_debug_phase_clocks(qas_ctx *ctx, uint64_t *out4, int reset);
 /* ... and of the compressed kernel, per bin: out[bin * 8 + 0..3] = the four phase sums, out[bin * 8 + 4] = circuits
  * evaluated; bin i holds the circuits whose support dimension is *dmin + i (the first bin also the smaller ones). */
 int qas_debug_phase_clocks_c(qas_ctx *ctx, uint64_t *out, int max_bins, int *dmin, int reset);
+/* ... of the tiled kernel for 13..16-qubit registers (stats.path == 4): out8 = summed cycles of the cluster's first
+ * CTA [prologue, forward sweep, H + energy, adjoint sweep], forward tile passes, adjoint tile passes, circuits, 0 */
+int qas_debug_phase_clocks_t(qas_ctx *ctx, uint64_t *out8, int reset);
 
 /* Measured FP64 roofline denominator: runs a dependent-chain-free DFMA micro-benchmark on
  * `device` and returns the best of `reps` timings in TFLOP/s (2 flop per DFMA).            */

@@ -181,6 +181,10 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   cx->RB = qas_hrb(n_qubits <= 13 ? n_qubits : 20, cx->T);
   cx->PD = qas_hpd(n_qubits <= 13 ? n_qubits : 20, cx->T);
   if (const char *sk = getenv("QAS_B200_SMALL")) cx->small_kernel = atoi(sk) != 0;
+  if (const char *te = getenv("QAS_B200_TILED")) cx->tiled = atoi(te) != 0;
+  if (const char *te = getenv("QAS_B200_TILED_FORCE_N")) cx->tiled_force_n = atoi(te);
+  if (const char *te = getenv("QAS_B200_TILED_TB")) cx->tiled_tb = atoi(te) == 12 ? 12 : 11;
+  if (const char *te = getenv("QAS_B200_TILED_CS")) cx->tiled_cs = atoi(te);
   if (n_qubits <= 5 && cx->small_kernel) { cx->GMAX = 1; cx->RB = n_qubits >= 4 ? 1 : 0; cx->PD = cx->RB >= 1 ? 2 : 1; }
 
   // group the Hamiltonian by X mask: slice key = (xmask, is_imag); term sign from i^{nY}
@@ -452,6 +456,18 @@ extern "C" int qas_debug_phase_clocks(qas_ctx *ctx, uint64_t *out4, int reset) {
   unsigned long long h[8 * (QAS_MAX_BINS + 1)];
   CK(cudaMemcpy(h, ctx->d_phase, sizeof h, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 4; ++i) out4[i] = h[i];
+  if (reset) CK(cudaMemset(ctx->d_phase, 0, sizeof h));
+  return QAS_OK;
+}
+// tiled kernel (kernels_t.cuh): out8 = cycles [prologue, forward, H, adjoint], forward passes, adjoint passes, circuits, 0
+extern "C" int qas_debug_phase_clocks_t(qas_ctx *ctx, uint64_t *out8, int reset) {
+  if (!ctx || !out8) return QAS_ERR_INVALID;
+  if (!ctx->d_phase) return fail(ctx, QAS_ERR_UNSUPPORTED, "create the context with QAS_B200_PHASE_CLOCKS=1");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  unsigned long long h[8];
+  CK(cudaMemcpy(h, ctx->d_phase, sizeof h, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; ++i) out8[i] = h[i];
   if (reset) CK(cudaMemset(ctx->d_phase, 0, sizeof h));
   return QAS_OK;
 }
@@ -925,6 +941,15 @@ extern "C" int qas_plan_passes_host(int n_qubits, uint32_t *ops, int num_ops, in
     return QAS_ERR_INVALID;
   if (gdesc && gdesc_words < num_ops * QAS_GD_STRIDE(n_qubits)) return QAS_ERR_NOMEM;
   *num_groups = qas_plan_groups(ops, num_ops, gmax, n_qubits, init_kind, init_index, gdesc, swizzled);
+  return QAS_OK;
+}
+
+extern "C" int qas_plan_tile_pass_host(int n_qubits, const uint32_t *ops, int num_ops_total, int start, int dir, int tb,
+                                       int clow, int max_ops, uint32_t *col, int *piv, int *num_ops) {
+  if ((num_ops_total > 0 && !ops) || num_ops_total < 0 || n_qubits < 1 || n_qubits > QAS_TP_MAXQ || tb < 1 || tb > n_qubits ||
+      clow < 0 || clow > tb || (dir != 1 && dir != -1) || max_ops < 3 || !col || !piv || !num_ops)
+    return QAS_ERR_INVALID;
+  *num_ops = qas_plan_tile_pass(ops, num_ops_total, start, dir, n_qubits, tb, clow, max_ops, col, piv);
   return QAS_OK;
 }
 

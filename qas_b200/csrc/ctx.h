@@ -41,6 +41,11 @@ struct qas_ctx {
   int PD = 1;                      // H-apply prefetch depth (rows)
   bool small_kernel = true;        // n <= 5: thread-per-circuit kernel (QAS_B200_SMALL=0 disables)
   bool small_now = false;          // ... and chosen for the call in progress
+  // tiled kernel (kernels_t.cuh) for registers that do not fit shared memory: QAS_B200_TILED (0 = keep the round-1
+  // global-memory kernel), QAS_B200_TILED_FORCE_N (registers >= this skip the shared-memory kernels: tests),
+  // QAS_B200_TILED_TB (log2 amplitudes per tile, 11 | 12), QAS_B200_TILED_CS (CTAs per cluster, 0 = by register size)
+  bool tiled = true;
+  int tiled_force_n = 99, tiled_tb = 11, tiled_cs = 0;
   int *d_counter = nullptr;        // work-queue head of the classic team kernels (= d_bins + QAS_MAX_BINS + full bin)
   // support-compressed path (kernels_c.cuh): circuits binned by the dimension d of their support span
   bool compress = false;           // all-zero start, n >= 7, QAS_B200_COMPRESS != 0
@@ -111,6 +116,9 @@ static inline cudaError_t ensure(Tp **ptr, size_t *cap, size_t need_elems) {
 // launch_classic_grad.cu / launch_classic_nograd.cu: the classic evaluation kernels (kernels.cuh)
 cudaError_t qas_launch_eval_grad(qas_ctx *ctx, EvalParams &P, cudaStream_t st);
 cudaError_t qas_launch_eval_nograd(qas_ctx *ctx, EvalParams &P, cudaStream_t st);
+// launch_tiled.cu: tiled kernel for full-register circuits on 11..16 qubits (kernels_t.cuh)
+bool qas_tiled_applies(const qas_ctx *ctx);
+cudaError_t qas_launch_tiled(qas_ctx *ctx, EvalParams &P, bool grad, cudaStream_t st);
 // launch_plan.cu: device-side classic tape compiler / pass planner (kernels_plan.cuh)
 int qas_launch_compile_classic(qas_ctx *ctx, const int32_t *dk, int B, int p, int ops_cap, int swz_plan, size_t rec_words,
                                cudaStream_t st);

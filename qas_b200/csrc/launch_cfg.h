@@ -45,7 +45,8 @@ static inline int qas_classic_path(const qas_ctx *ctx, bool grad, int ops_cap, i
   // and sign tables are shared with the gradient launches).  LiH reward-only 72 -> 84 M evals/s; the
   // gradient kernel is slower that way (1.15 -> 1.44 ms: the dense tail of the batch runs on one warp).
   if (!grad && ctx->n == 10 && ctx->team_shift == 0 && T == 64 && blk == 128) { T = 32; blk = 64; }
-  if (ctx->n <= (grad ? 12 : 13)) {
+  const bool forced_tiled = ctx->tiled && ctx->n >= ctx->tiled_force_n && ctx->n >= 11 && ctx->n <= QAS_TP_MAXQ;
+  if (ctx->n <= (grad ? 12 : 13) && !forced_tiled) {
     const size_t smem = eval_team_smem_bytes(ctx->n, T, grad, ops_cap, true, qas_stage_u(ctx->n)) * (blk / T) +
                         sdesc_bytes(ctx->C_real + ctx->C_imag);
     if (smem <= 227 * 1024) { *T_out = T; *blk_out = blk; return 0; }

@@ -96,6 +96,7 @@ static cudaError_t launch_eval(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
     if constexpr (!GRAD) { if (P.n == 13 && T == 256) return launch_smem<13, 256, false, qas_hrb(13, 256), qas_hpd(13, 256)>(ctx, P, st); }
     return cudaErrorInvalidConfiguration;      // no instantiation for this (n, T, CTA) combination
   }
+  if (qas_tiled_applies(ctx)) return qas_launch_tiled(ctx, P, GRAD, st);
   return launch_gmem<GRAD>(ctx, P, st);
 }
 

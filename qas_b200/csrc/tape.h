@@ -703,3 +703,56 @@ QAS_PUNROLL
   }
   return d;
 }
+
+// ---- tile passes (kernels_t.cuh: full-register circuits on 13..16 qubits) ---------------------------------
+// A tile pass is a run of consecutive tape ops (whole pass groups) whose xor masks, together with the `clow`
+// lowest index bits, span at most TB dimensions.  The pass gets a frame A = [col_0 .. col_{n-1}]:
+//   col_0 .. col_{clow-1}   the unit vectors of the low bits (a tile is made of contiguous 2^clow-amplitude chunks),
+//   col_clow .. col_{TB-1}  the reduced masks of the pass in the order they enlarge the span (low bits cleared),
+//                           completed by unit vectors of unused positions,
+//   col_TB .. col_{n-1}     unit vectors of the positions left over: they enumerate the tiles.
+// Pass coordinate x (n bits: tile coordinate t | tile number tau << TB) <-> physical index A x.  piv[p] = index of
+// the column whose highest set bit is p (every column has a distinct one, so reducing a mask from the top yields
+// its coordinates).  Greedy from tape index `start` in direction dir (+1: adjoint sweep, groups marked by GFIRST;
+// -1: forward sweep, GLAST); returns the number of ops taken.
+#define QAS_TP_MAXQ 16
+QAS_HD int qas_plan_tile_pass(const uint32_t *ops, int nops, int start, int dir, int n, int TB, int clow, int max_ops,
+                              uint32_t *col, int *piv) {
+  const uint32_t lowmask = (1u << clow) - 1u;
+  for (int q = 0; q < n; ++q) piv[q] = -1;
+  for (int q = 0; q < clow; ++q) { col[q] = 1u << q; piv[q] = q; }
+  int d = clow, cnt = 0, j = start;
+  while (j >= 0 && j < nops) {
+    const uint32_t meta = ops[(size_t)j * QAS_OP_WORDS + 4];
+    int g = (int)(dir > 0 ? QAS_META_GFIRST(meta) : QAS_META_GLAST(meta));
+    if (g < 1) g = 1;
+    if (cnt + g > max_ops) break;
+    int added[3], na = 0;
+    bool fits = true;
+    for (int q = 0; q < g && fits; ++q) {
+      const uint32_t *o = ops + (size_t)(j + dir * q) * QAS_OP_WORDS;
+      if (qas_meta_kind(o[4]) != QAS_K_U1) continue;
+      uint32_t x = o[0] & ~lowmask;
+      int pnew = -1;
+      for (int p = n - 1; p >= clow; --p)
+        if ((x >> p) & 1u) {
+          if (piv[p] >= 0) x ^= col[piv[p]];
+          else { pnew = p; break; }
+        }
+      if (pnew >= 0) {
+        if (d >= TB) { fits = false; break; }
+        col[d] = x; piv[pnew] = d; added[na++] = pnew; ++d;
+      }
+    }
+    if (!fits) {
+      for (int a = 0; a < na; ++a) piv[added[a]] = -1;
+      d -= na;
+      break;
+    }
+    cnt += g;
+    j += dir * g;
+  }
+  for (int p = clow; p < n && d < TB; ++p) if (piv[p] < 0) { col[d] = 1u << p; piv[p] = d; ++d; }
+  for (int p = clow; p < n; ++p) if (piv[p] < 0) { col[d] = 1u << p; piv[p] = d; ++d; }
+  return cnt;
+}

@@ -137,7 +137,8 @@ def test_qubit_count_sweep_including_global_memory_path(n, grad, compress, monke
     params = rng.standard_normal((p, c, 3))
     out = ev.evaluate(ks, params, want_grad=grad, compact=grad)
     st = ev.stats()
-    assert st["path"] == (3 if compress == "1" else (0 if n <= (12 if grad else 13) else 1))
+    # 4 = tiled kernel (kernels_t.cuh: thread-block cluster per circuit, tile passes over the slab)
+    assert st["path"] == (3 if compress == "1" else (0 if n <= (12 if grad else 13) else 4))
     e_ref, g_ref = _oracle_batch(n, ks, pool.pool, params, terms, ("zero", 0), grad)
     assert np.max(np.abs(out["energy"] - e_ref)) <= E_TOL
     if grad:
@@ -402,7 +403,7 @@ def test_deep_tapes_fall_back_to_the_global_memory_kernel_with_a_consistent_layo
     ks = sample_structure_lists(pool, p, {"CNOT": p // 2}, B, seed=33)
     ev = BatchEvaluator(n, terms, pool, init=("basis", 0b101010101010))
     out = ev.evaluate(ks, params, want_grad=True, dense=False, compact=True)
-    assert ev.stats()["path"] == 1
+    assert ev.stats()["path"] == 4
     ev.close()
     for b in range(B):
         k = [int(x) for x in ks[b]]
@@ -410,6 +411,53 @@ def test_deep_tapes_fall_back_to_the_global_memory_kernel_with_a_consistent_layo
         g = sim.grad_adjoint(n, k, pool.pool, params, terms, ("basis", 0b101010101010))
         for i, key in enumerate(k):
             assert np.max(np.abs(out["grad_compact"][b, i] - g[i, key])) <= G_TOL
+
+
+@pytest.mark.parametrize("n,tb,cs,init,vocab", [
+    (11, 11, 0, ("zero", 0), "near_cx"), (12, 11, 2, ("basis", 0b100110101101), "full"), (12, 12, 1, ("plus", 0), "full"),
+    (13, 11, 4, ("basis", 0b1000000000001), "near_cx"), (13, 12, 2, ("zero", 0), "full"), (14, 11, 1, ("zero", 0), "near_cx"),
+    (14, 12, 4, ("plus", 0), "near_cx"), (15, 11, 4, ("zero", 0), "near_cx")])
+def test_tiled_kernel_tile_sizes_cluster_sizes_start_states(n, tb, cs, init, vocab, monkeypatch):
+    """eval_tiled_kernel (kernels_t.cuh) forced onto 11..15-qubit registers (QAS_B200_TILED_FORCE_N): both tile sizes,
+    clusters of 1 / 2 / 4 CTAs, all three start states, the full gate vocabulary (controlled gates and parity
+    phases whose masks fall on tile-number bits), energy-only and gradient launches -- against the oracle, and
+    against the round-1 global-memory kernel (QAS_B200_TILED=0) to 1e-12."""
+    monkeypatch.setenv("QAS_B200_COMPRESS", "0")
+    monkeypatch.setenv("QAS_B200_TILED_FORCE_N", "11")
+    monkeypatch.setenv("QAS_B200_TILED_TB", str(tb))
+    monkeypatch.setenv("QAS_B200_TILED_CS", str(cs))
+    rng = np.random.default_rng(1000 + n + tb + cs)
+    pool = helpers.near_cx_pool(n) if vocab == "near_cx" else helpers.full_vocab_pool(n)
+    c = len(pool)
+    terms = [(float(rng.standard_normal()), "".join(rng.choice(list("IXYZ"), size=n, p=[.55, .15, .15, .15])))
+             for _ in range(9)] + [(0.25, "I" * n)]
+    p, B = (40 if vocab == "near_cx" else 18), 5
+    if vocab == "near_cx":
+        ks = sample_structure_lists(pool, p, {"CNOT": p // 2}, B, seed=n)
+    else:
+        ks = rng.integers(0, c, size=(B, p)).astype(np.int32)
+    params = rng.standard_normal((p, c, 3))
+    ev = BatchEvaluator(n, terms, pool, init)
+    out = ev.evaluate(ks, params, want_grad=True, compact=True)
+    assert ev.stats()["path"] == 4
+    out_e = ev.evaluate(ks, params, want_grad=False)
+    assert ev.stats()["path"] == 4
+    ev.close()
+    assert np.max(np.abs(out_e["energy"] - out["energy"])) <= 1e-12
+    for b in range(2):
+        k = [int(x) for x in ks[b]]
+        assert abs(out["energy"][b] - sim.energy(n, k, pool.pool, params, terms, init)) <= E_TOL
+        ga = sim.grad_adjoint(n, k, pool.pool, params, terms, init)
+        dense = helpers.dense_from_compact([k], out["grad_compact"][b:b + 1], c)[0]
+        assert np.max(np.abs(dense - ga)) <= G_TOL
+    monkeypatch.setenv("QAS_B200_TILED", "0")
+    monkeypatch.setenv("QAS_B200_TILED_FORCE_N", "99")
+    ev = BatchEvaluator(n, terms, pool, init)
+    ref = ev.evaluate(ks, params, want_grad=True, compact=True)
+    assert ev.stats()["path"] in (0, 1)
+    ev.close()
+    assert np.max(np.abs(ref["energy"] - out["energy"])) <= 1e-12
+    assert np.max(np.abs(ref["grad_compact"] - out["grad_compact"])) <= 1e-12
 
 
 def test_linearity_in_hamiltonian():
