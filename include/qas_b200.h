@@ -292,6 +292,8 @@ int qas_peer_wait_reduce(const void *rows, int world, uint64_t row_stride, uint6
  * over all circuits evaluated so far, of the SM clock cycles a team spent in the four phases of the
  * evaluation kernel -- out4 = {prologue, forward sweep, H application + energy, adjoint sweep}.
  * Synchronises the device.  Used by tools/phase_clocks.py to see where a circuit's latency goes.   */
+/* parameter slots per gate (the l of the (p, c, l) super-set) the context was created with */
+int qas_ctx_param_slots(const qas_ctx *ctx);
 int qas_debug_phase_clocks(qas_ctx *ctx, uint64_t *out4, int reset);
 /* ... and of the compressed kernel, per bin: out[bin * 8 + 0..3] = the four phase sums, out[bin * 8 + 4] = circuits
  * evaluated; bin i holds the circuits whose support dimension is *dmin + i (the first bin also the smaller ones). */

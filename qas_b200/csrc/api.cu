@@ -448,6 +448,8 @@ extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   return QAS_OK;
 }
 
+extern "C" int qas_ctx_param_slots(const qas_ctx *ctx) { return ctx ? ctx->l : QAS_ERR_INVALID; }
+
 extern "C" int qas_debug_phase_clocks(qas_ctx *ctx, uint64_t *out4, int reset) {
   if (!ctx || !out4) return QAS_ERR_INVALID;
   if (!ctx->d_phase) return fail(ctx, QAS_ERR_UNSUPPORTED, "create the context with QAS_B200_PHASE_CLOCKS=1");
@@ -691,6 +693,9 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   };
   if (!dev && !tiny && !capturing) CK(cudaEventRecord(ctx->ev0, st));
   stamp(0);
+  // (Tried: zero-fill + gate table on a forked stream next to the tape compiler.  Slower -- 0.780 -> 0.798 ms per LiH
+  // step: the 31 MB zero-fill then lands between the compiler and the evaluation kernels and pushes the tape
+  // records out of L2.)
   if (want_grad) { CK(cudaMemsetAsync(dgrad, 0, ng * 8, st)); ctx->stats.launches += 1; }
   if (!small) CK(cudaMemsetAsync(ctx->d_bins, 0, sizeof(int) * 2 * QAS_MAX_BINS, st));   // bin counts + work-queue heads
   stamp(1);
@@ -861,17 +866,25 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   stamp(5);
 
   if (grad_dense) {
-    int chunk = 64;            // circuits per CTA of the first stage (1024 CTAs at B = 65536)
+    int chunk = 64;            // circuits per thread group of the first stage
     if (const char *ce = getenv("QAS_B200_REDUCE_CHUNK")) chunk = std::max(1, atoi(ce));   // tuning knob
-    const int nchunks = (B + chunk - 1) / chunk;
     int depth_tile = p;
     while ((size_t)depth_tile * c * l * 8 > 96 * 1024 && depth_tile > 1) depth_tile = (depth_tile + 1) / 2;
-    const size_t sm = (size_t)depth_tile * c * l * 8;
+    const size_t sm1 = (size_t)depth_tile * c * l * 8;
+    const int gthreads = std::min(256, std::max(64, ((std::min(depth_tile, p) * l + 31) / 32) * 32));
+    // thread groups per CTA, each with its own accumulator copy over its own `chunk` circuits, summed in fixed group
+    // order before the partial is written: a quarter of the partial-sum traffic of one group per CTA (LiH: 18.7 MB
+    // written and re-read per 65536 circuits before)
+    int ngroups_r = 4;
+    if (const char *ge = getenv("QAS_B200_REDUCE_GROUPS")) ngroups_r = std::max(1, std::min(8, atoi(ge)));   // tuning knob
+    while (ngroups_r > 1 && (sm1 * ngroups_r > 96 * 1024 || gthreads * ngroups_r > 512 || (B + chunk * ngroups_r - 1) / (chunk * ngroups_r) < ctx->num_sms))
+      ngroups_r >>= 1;
+    const int nchunks = (B + chunk * ngroups_r - 1) / (chunk * ngroups_r);
+    const size_t sm = sm1 * ngroups_r;
     CK(ensure(&ctx->d_partial, &ctx->cap_partial, (size_t)nchunks * npar));
     CK(cudaFuncSetAttribute(grad_chunk_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid(nchunks, (p + depth_tile - 1) / depth_tile);
-    const int cthreads = std::min(256, std::max(64, ((std::min(depth_tile, p) * l + 31) / 32) * 32));
-    grad_chunk_reduce_kernel<<<grid, cthreads, sm, st>>>(dk, dgrad, B, p, c, l, chunk, depth_tile, ctx->d_partial);
+    grad_chunk_reduce_kernel<<<grid, gthreads * ngroups_r, sm, st>>>(dk, dgrad, B, p, c, l, chunk, depth_tile, ngroups_r, ctx->d_partial);
     CK(cudaGetLastError());
     stamp(6);
     const double scale = (flags & QAS_F_GRAD_SUM) ? 1.0 : 1.0 / (double)B;
@@ -1110,7 +1123,7 @@ extern "C" int qas_batch_mean(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   CK(cudaFuncSetAttribute(grad_chunk_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   dim3 grid(nchunks, (p + depth_tile - 1) / depth_tile);
   const int cthreads = std::min(256, std::max(64, ((std::min(depth_tile, p) * l + 31) / 32) * 32));
-  grad_chunk_reduce_kernel<<<grid, cthreads, sm, st>>>(k, grad_compact, B, p, c, l, chunk, depth_tile, ctx->d_partial);
+  grad_chunk_reduce_kernel<<<grid, cthreads, sm, st>>>(k, grad_compact, B, p, c, l, chunk, depth_tile, 1, ctx->d_partial);
   CK(cudaGetLastError());
   const double scale = (flags & QAS_F_GRAD_SUM) ? 1.0 : 1.0 / (double)B;
   grad_final_reduce_kernel<<<(unsigned)((npar * 32 + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, npar, scale, grad_dense);

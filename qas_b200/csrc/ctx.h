@@ -124,7 +124,7 @@ int qas_launch_compile_classic(qas_ctx *ctx, const int32_t *dk, int B, int p, in
                                cudaStream_t st);
 // launch_c.cu: compressed path (kernels_c.cuh)
 size_t qas_ccompile_smem_bytes(const qas_ctx *ctx, int ops_cap, int p);
-int qas_evalc_team_threads(int slot_bits);
+int qas_evalc_team_threads(int slot_bits, bool grad);
 cudaError_t qas_launch_compile_c(qas_ctx *ctx, const CompileCParams &P, cudaStream_t st);
 cudaError_t qas_launch_plan_full(qas_ctx *ctx, uint32_t *tape, size_t rec_stride, const int *count, const int *order, int B,
                                  int ops_cap, int swizzled, cudaStream_t st);

@@ -1104,28 +1104,31 @@ __device__ __forceinline__ double nan_to_num_d(double x) {
 }
 
 static __global__ void grad_chunk_reduce_kernel(const int32_t *k, const double *grad, int B, int p, int c,
-                                         int l, int chunk, int depth_tile, double *partial) {
-  extern __shared__ double acc[];                 // [depth_tile][c][l]
+                                         int l, int chunk, int depth_tile, int ngroups, double *partial) {
+  extern __shared__ double acc_all[];             // [ngroups][depth_tile][c][l]
   const int ch = blockIdx.x, i0 = blockIdx.y * depth_tile;
   const int nd = min(depth_tile, p - i0);
-  for (int x = threadIdx.x; x < nd * c * l; x += blockDim.x) acc[x] = 0.0;
+  const int gthreads = blockDim.x / ngroups, grp = threadIdx.x / gthreads, gt = threadIdx.x % gthreads;
+  const size_t asz = (size_t)depth_tile * c * l;
+  for (size_t x = threadIdx.x; x < asz * ngroups; x += blockDim.x) acc_all[x] = 0.0;
   __syncthreads();
-  const int b_lo = ch * chunk, b_hi = min(B, b_lo + chunk);
-  for (int x = threadIdx.x; x < nd * l; x += blockDim.x) {
+  double *acc = acc_all + (size_t)grp * asz;
+  const int b_lo = min(B, (ch * ngroups + grp) * chunk), b_hi = min(B, b_lo + chunk);
+  for (int x = gt; x < nd * l; x += gthreads) {
     const int di = x / l, j = x % l;
     double *a = acc + (size_t)di * c * l + j;
-    // four circuits' loads in flight per step; the accumulation order stays b ascending
+    // eight circuits' loads in flight per step; the accumulation order stays b ascending within the group
     int b = b_lo;
-    for (; b + 4 <= b_hi; b += 4) {
-      int key[4];
-      double gval[4];
+    for (; b + 8 <= b_hi; b += 8) {
+      int key[8];
+      double gval[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
         key[q] = k[(size_t)(b + q) * p + i0 + di];
         gval[q] = grad[((size_t)(b + q) * p + i0 + di) * l + j];
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 8; ++q)
         if (key[q] >= 0 && key[q] < c) a[key[q] * l] += nan_to_num_d(gval[q]);
     }
     for (; b < b_hi; ++b) {
@@ -1136,7 +1139,11 @@ static __global__ void grad_chunk_reduce_kernel(const int32_t *k, const double *
   }
   __syncthreads();
   double *out = partial + ((size_t)ch * p + i0) * c * l;
-  for (int x = threadIdx.x; x < nd * c * l; x += blockDim.x) out[x] = acc[x];
+  for (int x = threadIdx.x; x < nd * c * l; x += blockDim.x) {
+    double s = acc_all[x];
+    for (int g = 1; g < ngroups; ++g) s += acc_all[(size_t)g * asz + x];      // fixed group order
+    out[x] = s;
+  }
 }
 
 // one warp per output element: lane q sums chunks q, q+32, ... in order, then a fixed shuffle tree

@@ -260,7 +260,7 @@ __device__ __forceinline__ void c_adj_group(double2 *psi, double2 *lam, const ui
 
 template <int T>
 __device__ __forceinline__ void c_prepare_slices(const EvalCParams &P, const uint32_t *gci, uint4 *sl, uint32_t *chead, int nsl,
-                                                 int d, int tid, uint32_t ent0, uint32_t hb) {
+                                                 int d, int tid, uint32_t ent0, uint32_t hb, uint32_t tmask, int lane0) {
   const int n = P.n;
   // (warp-uniform trip count: the basis vectors travel by shuffle from the lanes that loaded them)
   for (int s0 = 0; s0 < nsl; s0 += T) {
@@ -274,14 +274,14 @@ __device__ __forceinline__ void c_prepare_slices(const EvalCParams &P, const uin
     const uint32_t z0 = info.y & 0xffffu, z1 = info.y >> 16, z2 = info.z & 0xffffu, z3 = info.z >> 16;
     uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
     for (int k = 0; k < d; ++k) {
-      const uint32_t bk = __shfl_sync(0xffffffffu, hb, 1 + k);
+      const uint32_t bk = __shfl_sync(tmask, hb, lane0 + 1 + k);
       c0 |= (uint32_t)(__popc(bk & z0) & 1) << k;
       c1 |= (uint32_t)(__popc(bk & z1) & 1) << k;
       c2 |= (uint32_t)(__popc(bk & z2) & 1) << k;
       c3 |= (uint32_t)(__popc(bk & z3) & 1) << k;
     }
     // nibble a of D = sign index of a * T = xor of e_j over the set bits j of a, e_j = index of the single bit T << j
-    constexpr int LT = (T == 32) ? 5 : (T == 64) ? 6 : (T == 128) ? 7 : 8;
+    constexpr int LT = (T == 8) ? 3 : (T == 16) ? 4 : (T == 32) ? 5 : (T == 64) ? 6 : (T == 128) ? 7 : 8;
     uint32_t e[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j)
@@ -300,7 +300,7 @@ __device__ __forceinline__ void c_prepare_slices(const EvalCParams &P, const uin
     const uint32_t x = (uint32_t)((tid & 7) * T);
     uint32_t ph = 0u;
     for (int k = 0; k < d; ++k) {
-      const uint32_t bk = __shfl_sync(0xffffffffu, hb, 1 + k);
+      const uint32_t bk = __shfl_sync(tmask, hb, lane0 + 1 + k);
       ph ^= ((x >> k) & 1u) ? bk : 0u;
     }
     if (tid < 8) chead[CS_PHA + tid] = ph;
@@ -434,16 +434,19 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) { const int w = tid + j * T; early[j] = w < recw ? grec[w] : 0u; }
     const uint32_t ent0 = tid < P.S ? gci[1 + n + tid] : 0u;           // this lane's slice entry
-    const uint32_t hb = lane <= QAS_CT_MAX_D ? gci[lane] : 0u;         // nsl, B_0 .. (every warp of the team its own copy)
+    // nsl, B_0 .. : every warp of a multi-warp team its own copy; sub-warp teams (T = 16) index by their own lanes
+    constexpr int LW = T >= 32 ? 32 : T;
+    const int tl = lane % LW, lane0 = lane - tl;
+    const uint32_t hb = tl <= QAS_CT_MAX_D ? gci[tl] : 0u;
     const int nops = (int)grec[0], status = (int)grec[1], d = (int)grec[2], ngroups = (int)grec[3];
-    const int nsl = (int)__shfl_sync(0xffffffffu, hb, 0);
+    const int nsl = (int)__shfl_sync(tmask, hb, lane0);
     {
       const int used = QAS_REC_HDR + nops * QAS_OP_WORDS;
 #pragma unroll
       for (int j = 0; j < 4; ++j) { const int w = tid + j * T; if (w < used) rec[w] = early[j]; }
       for (int w = tid + 4 * T; w < used; w += T) rec[w] = grec[w];
       if (tid <= d) chead[tid] = hb;
-      c_prepare_slices<T>(P, gci, sl, chead, nsl, d, tid, ent0, hb);
+      c_prepare_slices<T>(P, gci, sl, chead, nsl, d, tid, ent0, hb, tmask, lane0);
       const uint32_t dim = 1u << d;
       for (uint32_t i = tid; i < dim; i += T) psi[i] = make_double2(i == 0u ? 1.0 : 0.0, 0.0);
     }

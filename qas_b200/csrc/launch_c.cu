@@ -42,15 +42,28 @@ static cudaError_t launch_evalc_t(qas_ctx *ctx, const EvalCParams &P, int max_wo
 }
 
 // threads per team of a compressed bin by its slot size (log2 amplitudes)
-int qas_evalc_team_threads(int slot_bits) { return slot_bits <= 8 ? 32 : slot_bits <= 10 ? 64 : slot_bits == 11 ? 128 : 256; }
+// Sub-warp teams for the small registers (several circuits per warp): the register file -- not the lanes -- bounds the
+// circuits in flight, and a G = 2 pass of a 2^6-amplitude register has 16 cosets, so half a warp's lanes were idle.
+// QAS_B200_C_T16 (tuning knob): registers of <= 2^(5 + value) amplitudes run as 16-lane teams (0 = off; default 1 for
+// energy-only launches, whose forward sweep and H phase are full-width, 2 for gradient launches).
+// QAS_B200_C_T8: registers of <= 2^6 amplitudes of gradient launches as 8-lane teams (default 0).
+int qas_evalc_team_threads(int slot_bits, bool grad) {
+  static const int t16 = []() { const char *e = getenv("QAS_B200_C_T16"); return e ? atoi(e) : -1; }();
+  static const int t8 = []() { const char *e = getenv("QAS_B200_C_T8"); return e ? atoi(e) : 0; }();
+  const int lim16 = t16 >= 0 ? t16 : (grad ? 2 : 1);
+  if (t8 > 0 && grad && slot_bits <= 6) return 8;
+  return (lim16 > 0 && slot_bits <= 5 + lim16) ? 16 : slot_bits <= 8 ? 32 : slot_bits <= 10 ? 64 : slot_bits == 11 ? 128 : 256;
+}
 
 cudaError_t qas_launch_evalc(qas_ctx *ctx, const EvalCParams &P, int max_work, bool grad, cudaStream_t st) {
-  const int T = qas_evalc_team_threads(P.slot_bits);
+  const int T = qas_evalc_team_threads(P.slot_bits, grad);
   // QAS_B200_C_MINB (tuning knob, one-warp teams): CTAs per SM the register allocation is bounded for -- 4 (128
   // registers, default), 5 (102), 6 (85) or 8 (64): more circuits in flight against spills in the two-gate adjoint pass
   static const int minb32 = []() { const char *e = getenv("QAS_B200_C_MINB"); const int v = e ? atoi(e) : 4; return (v == 5 || v == 6 || v == 8) ? v : 4; }();
 #define QAS_CCASE(T_, BLK_, MINB_) \
   return grad ? launch_evalc_t<T_, true, BLK_, MINB_>(ctx, P, max_work, st) : launch_evalc_t<T_, false, BLK_, MINB_>(ctx, P, max_work, st);
+  if (T == 8) { QAS_CCASE(8, 128, 4) }
+  if (T == 16) { QAS_CCASE(16, 128, 4) }
   if (T == 32 && minb32 == 5) { QAS_CCASE(32, 128, 5) }
   if (T == 32 && minb32 == 6) { QAS_CCASE(32, 128, 6) }
   if (T == 32 && minb32 == 8) { QAS_CCASE(32, 128, 8) }

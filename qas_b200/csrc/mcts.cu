@@ -401,9 +401,10 @@ extern "C" int qas_mcts_set_params(qas_mcts *m, const double *params, int p, int
   if (!m) return QAS_ERR_INVALID;
   if (p != m->cfg.max_depth || c != m->c) return m->fail(QAS_ERR_INVALID, "parameter super-set shape does not match (max_depth, pool size)");
   m->cache.clear();
-  (void)l;
   if (m->ctx) {
     if (!params) return m->fail(QAS_ERR_INVALID, "params is null");
+    if (l != qas_ctx_param_slots(m->ctx))      // the evaluator reads params with its own stride
+      return m->fail(QAS_ERR_INVALID, "parameter slots per gate (l) differ from the evaluator context's");
     const int rc = qas_set_params(m->ctx, p, params);
     if (rc != QAS_OK) return m->fail(rc, std::string("evaluator: ") + qas_last_error(m->ctx));
   }
