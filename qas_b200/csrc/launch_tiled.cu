@@ -53,7 +53,9 @@ static cudaError_t launch_tiled_g(qas_ctx *ctx, EvalParams &P, cudaStream_t st) 
   int cs = ctx->tiled_cs;
   if (cs <= 0) {
     const int resident = (tb == 11 ? 2 : 1) * ctx->num_sms;
-    const int work = P.B;      // (a device-side count of the full bin is unknown here: sized for the whole batch)
+    // the full bin of a device-compiled batch (P.count on the device, unknown here) is a small tail of the batch
+    // (LiH 0.8 %, H2O-14q a few dozen circuits): largest clusters, so that it does not outlast the compressed bins
+    const int work = P.count ? 1 : P.B;
     cs = 1;
     while (cs < 8 && work * cs * 2 <= resident) cs <<= 1;
     if (tb == 12 && cs > 4) cs = 4;

@@ -66,9 +66,12 @@ class BatchEvaluator:
         raise QasError("libqas_b200 error %d: %s" % (rc, msg))
 
     # ------------------------------------------------------------------ host-array entry
-    def evaluate(self, ks, params, want_grad=True, dense=True, compact=False, avg=True):
+    def evaluate(self, ks, params, want_grad=True, dense=True, compact=False, avg=True, out=None):
         """ks: int array [B, p]; params: float64 [p, c, l].  A uint8 array (pools of <= 256 entries) is uploaded
         as it is -- a quarter of the bytes -- and widened on the device (QAS_F_K_U8).
+        out: optional dict of preallocated C-contiguous float64 result arrays ("energy" [B], "grad_dense" [p,c,l],
+        "grad_compact" [B,p,l]) -- e.g. page-locked memory, so that the read-back is a true asynchronous DMA instead
+        of the driver's staged copy into fresh pageable pages.
         Returns dict(energy[B], grad_dense[p,c,l] | None, grad_compact[B,p,l] | None)."""
         ks = np.asarray(ks)
         k8 = ks.dtype == np.uint8 and self.c <= 256
@@ -78,9 +81,15 @@ class BatchEvaluator:
         params = np.ascontiguousarray(np.asarray(params, dtype=np.float64))
         B, p = ks.shape
         assert params.shape == (p, self.c, self.l), (params.shape, (p, self.c, self.l))
-        energy = np.empty(B, dtype=np.float64)
-        gd = np.empty((p, self.c, self.l), dtype=np.float64) if (want_grad and dense) else None
-        gc = np.empty((B, p, self.l), dtype=np.float64) if (want_grad and compact) else None
+        def _buf(name, shape):
+            a = out.get(name) if out else None
+            if a is None:
+                return np.empty(shape, dtype=np.float64)
+            assert a.dtype == np.float64 and a.shape == tuple(shape) and a.flags["C_CONTIGUOUS"], name
+            return a
+        energy = _buf("energy", (B,))
+        gd = _buf("grad_dense", (p, self.c, self.l)) if (want_grad and dense) else None
+        gc = _buf("grad_compact", (B, p, self.l)) if (want_grad and compact) else None
         flags = (0 if avg else _lib.QAS_F_GRAD_SUM) | (_lib.QAS_F_K_U8 if k8 else 0)
         rc = self._lib.qas_eval_batch(
             self._h, B, p, ks.ctypes.data, params.ctypes.data, energy.ctypes.data,

@@ -55,12 +55,13 @@ class HamiltonianModel(ModelFromK):
         return ev
 
     @classmethod
-    def evaluate_batch(cls, ks, super_circ_params, op_pool, want_grad=True, avg=True, compact=False):
+    def evaluate_batch(cls, ks, super_circ_params, op_pool, want_grad=True, avg=True, compact=False, out=None):
         """Energies (losses) [B] and the batch-mean (or sum) dense gradient [p, c, l] of a batch
-        of structure lists sharing `super_circ_params` (mcts.py:340-347 in one launch)."""
+        of structure lists sharing `super_circ_params` (mcts.py:340-347 in one launch).
+        out: optional preallocated result arrays (BatchEvaluator.evaluate)."""
         l = np.asarray(super_circ_params).shape[2]
         return cls.evaluator(op_pool, l).evaluate(ks, super_circ_params, want_grad=want_grad,
-                                                  dense=True, compact=compact, avg=avg)
+                                                  dense=True, compact=compact, avg=avg, out=out)
 
     @classmethod
     def evaluate_batch_sharded(cls, ks, super_circ_params, op_pool, want_grad=True, avg=True, group=None):

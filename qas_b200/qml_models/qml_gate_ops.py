@@ -136,6 +136,11 @@ class QMLPool(Pool):
 def pool_table(op_pool):
     """QMLPool / plain dict -> [(gate_id, wire0, wire1)] in key order, for the C ABI."""
     src = getattr(op_pool, "pool", op_pool)
+    # the batched entries look their evaluator up by this table on every call: keep it with the pool object
+    # (pools are built once per experiment and never edited -- qas/qml_models/qml_gate_ops.py:136-185)
+    cached = getattr(op_pool, "_qas_pool_table", None) if isinstance(op_pool, QMLPool) else None
+    if cached is not None and cached[0] == len(src):
+        return cached[1]
     out = []
     for key in range(len(src)):
         entry = src[key] if key in src else src[str(key)]
@@ -146,4 +151,6 @@ def pool_table(op_pool):
             raise ValueError("gate %s is not supported by the evaluator" % name)
         w = list(wires)
         out.append((gid, int(w[0]), int(w[1]) if len(w) > 1 else -1))
+    if isinstance(op_pool, QMLPool):
+        op_pool._qas_pool_table = (len(src), out)
     return out
