@@ -176,6 +176,12 @@ int qas_plan_passes_host(int n_qubits, uint32_t *ops, int num_ops, int gmax, int
 int qas_plan_tile_pass_host(int n_qubits, const uint32_t *ops, int num_ops_total, int start, int dir, int tb,
                             int clow, int max_ops, uint32_t *col, int *piv, int *num_ops);
 
+/* Coset basis of one pass group inside a tile of the tiled kernel (qas_b200/csrc/tape.h qas_tile_group_basis): g <= 2
+ * gates with tile-coordinate xor masks m[g] and parity masks r[g] (tb bits); kb (>= tb words) receives a basis of the
+ * common kernel of the parity masks in lowest-set-bit echelon form, ascending pivots; returns its dimension tb - g in
+ * *dim.  Coset c of the group is represented by the xor of the kb[i] selected by the bits of c.                  */
+int qas_tile_group_basis_host(int g, const uint32_t *m, const uint32_t *r, int tb, uint32_t *kb, int *dim);
+
 /* Final-support descriptor of the H application (host run of the planner code the tape-compile
  * kernel executes).  W = register subspace of the H blocking: w_rank <= 3 basis vectors in reduced
  * echelon form (highest-bit pivots w_pivots ascending).  hdesc (>= 32 words) receives

@@ -966,6 +966,12 @@ extern "C" int qas_plan_tile_pass_host(int n_qubits, const uint32_t *ops, int nu
   return QAS_OK;
 }
 
+extern "C" int qas_tile_group_basis_host(int g, const uint32_t *m, const uint32_t *r, int tb, uint32_t *kb, int *dim) {
+  if (g < 1 || g > 2 || !m || !r || tb < g || tb > QAS_TP_MAXQ || !kb || !dim) return QAS_ERR_INVALID;
+  *dim = qas_tile_group_basis(g, m, r, tb, kb);
+  return QAS_OK;
+}
+
 extern "C" int qas_plan_hsupport_host(int n_qubits, const uint32_t *ops, int num_ops, int init_kind,
                                       uint32_t init_index, int w_rank, const int *w_pivots,
                                       const uint32_t *w_basis, uint32_t *hdesc, int hdesc_words) {

@@ -34,6 +34,7 @@
 #include "kernels.cuh"
 
 #define QAS_T_MAXP 32          // ops per pass (shared-memory staging of their matrices / cross matrices)
+#define QAS_T_KBW 12           // words per coset basis (tile bits - 1 at most)
 
 __host__ __device__ inline size_t evalt_smem_bytes(int tb, int nt, bool grad, int ops_cap, int C) {
   const int nw = nt / 32;
@@ -41,6 +42,7 @@ __host__ __device__ inline size_t evalt_smem_bytes(int tb, int nt, bool grad, in
   b += (((size_t)ops_cap * QAS_OP_WORDS * 4) + 15) & ~(size_t)15;       // the circuit's tape
   b += (size_t)QAS_T_MAXP * 64;                                          // gate matrices of the pass
   b += (size_t)QAS_T_MAXP * 16;                                          // translated ops of the pass
+  b += (size_t)QAS_T_MAXP * QAS_T_KBW * 4;                               // coset bases of the pass's groups
   if (grad) b += (size_t)QAS_T_MAXP * nw * 64 + (size_t)2 * QAS_T_MAXP * 64;   // per-warp cross matrices | CTA sums (two buffers)
   b += 2 * QAS_TP_MAXQ * 4;                                              // frame columns, pivot table
   b += (((size_t)nw * 8) + 15) & ~(size_t)15;                            // energy partials of the warps
@@ -52,45 +54,54 @@ __host__ __device__ inline size_t evalt_smem_bytes(int tb, int nt, bool grad, in
 struct TCtl { int q, cnt, j0, pad; double epart; };
 
 // ---- one forward pass group on a tile: G gates on the 2^G amplitudes of every coset
+// coset representative machinery shared by the two sweeps: the group's basis of K (qas_tile_group_basis, tape.h) is
+// folded into one word per thread (the bits of tid select kb[0 .. LT-1]) and one word per loop iteration
 template <int G, int TB, int NT>
-__device__ __forceinline__ void t_fwd_group(double2 *tile, const uint4 *top, const double2 *Us, uint32_t tau, int tid) {
-  uint32_t m[G], rl[G], xm[1 << G];
-  bool flip[G];
+struct TGeom {
+  static constexpr int LT = (NT == 128) ? 7 : (NT == 256) ? 8 : (NT == 512) ? 9 : 10;
+  static constexpr int NIT = (1 << (TB - G)) / NT;            // cosets per thread (1, 2 or 4)
+  uint32_t m[G], xm[1 << G], base, k8, k9;     // k8, k9: the basis vectors selected by the iteration counter
+  __device__ __forceinline__ void load(const uint4 *top, const uint32_t *kb, uint32_t tau, int tid) {
+    uint32_t off = 0u;
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      m[q] = top[q].x;
+      off ^= (__popc(tau & (top[q].y >> TB)) & 1) ? m[q] : 0u;      // tile-number part of the parity mask: a role flip
+    }
+    xm[0] = 0u;
+#pragma unroll
+    for (int c = 1; c < (1 << G); ++c) xm[c] = xm[c & ~(c >= 2 ? 2 : 1)] ^ m[c >= 2 ? 1 : 0];
+    uint32_t b = off;
+#pragma unroll
+    for (int i = 0; i < LT; ++i) b ^= ((tid >> i) & 1) ? kb[i] : 0u;
+    base = b;
+    k8 = NIT > 1 ? kb[LT] : 0u;
+    k9 = NIT > 2 ? kb[LT + 1] : 0u;
+  }
+  __device__ __forceinline__ uint32_t rep(int it) const { return base ^ ((it & 1) ? k8 : 0u) ^ ((it & 2) ? k9 : 0u); }
+};
+
+// ---- one forward pass group on a tile: G gates on the 2^G amplitudes of every coset
+template <int G, int TB, int NT>
+__device__ __forceinline__ void t_fwd_group(double2 *tile, const uint4 *top, const uint32_t *kb, const double2 *Us, uint32_t tau,
+                                            int tid) {
+  TGeom<G, TB, NT> gg;
+  gg.load(top, kb, tau, tid);
   double2 u[G][4];
 #pragma unroll
-  for (int q = 0; q < G; ++q) {
-    m[q] = top[q].x;
-    rl[q] = top[q].y & ((1u << TB) - 1u);
-    flip[q] = __popc(tau & (top[q].y >> TB)) & 1;
+  for (int q = 0; q < G; ++q)
 #pragma unroll
     for (int e = 0; e < 4; ++e) u[q][e] = Us[4 * q + e];
-  }
   const uint32_t rc = (G == 1) ? top[0].z : 0u;
   const bool cflip = (G == 1) && (__popc(tau & (rc >> TB)) & 1);
   const uint32_t rcl = rc & ((1u << TB) - 1u);
-  const int q0 = 31 - __clz(m[0]);
-  int qlo = q0, qhi = q0;
-  if constexpr (G == 2) {
-    const uint32_t e1 = ((m[1] >> q0) & 1u) ? (m[1] ^ m[0]) : m[1];
-    const int q1 = 31 - __clz(e1);
-    qlo = min(q0, q1);
-    qhi = max(q0, q1);
-  }
-  xm[0] = 0u;
 #pragma unroll
-  for (int c = 1; c < (1 << G); ++c) xm[c] = xm[c & ~(c >= 2 ? 2 : 1)] ^ m[c >= 2 ? 1 : 0];
-  constexpr uint32_t NCOS = 1u << (TB - G);
-#pragma unroll 2
-  for (uint32_t c = tid; c < NCOS; c += NT) {
-    uint32_t t = insert_zero(c, qlo);
-    if constexpr (G == 2) t = insert_zero(t, qhi);
-    uint32_t Pp = t;
-#pragma unroll
-    for (int q = 0; q < G; ++q) Pp ^= (((__popc(t & rl[q]) & 1) != 0) != flip[q]) ? m[q] : 0u;
+  for (int it = 0; it < TGeom<G, TB, NT>::NIT; ++it) {
+    const uint32_t Pp = gg.rep(it);
     if (G == 1 && rc && (((__popc(Pp & rcl) & 1) != 0) == cflip)) continue;     // control parity 0: the gate does not fire
     double2 a[1 << G];
 #pragma unroll
-    for (int s = 0; s < (1 << G); ++s) a[s] = tile[Pp ^ xm[s]];
+    for (int s = 0; s < (1 << G); ++s) a[s] = tile[Pp ^ gg.xm[s]];
 #pragma unroll
     for (int q = G - 1; q >= 0; --q) {       // time order = descending tape index
 #pragma unroll
@@ -98,7 +109,7 @@ __device__ __forceinline__ void t_fwd_group(double2 *tile, const uint4 *top, con
         if (!((s >> q) & 1)) apply_u(a[s], a[s | (1 << q)], u[q]);
     }
 #pragma unroll
-    for (int s = 0; s < (1 << G); ++s) tile[Pp ^ xm[s]] = a[s];
+    for (int s = 0; s < (1 << G); ++s) tile[Pp ^ gg.xm[s]] = a[s];
   }
 }
 
@@ -106,51 +117,30 @@ __device__ __forceinline__ void t_fwd_group(double2 *tile, const uint4 *top, con
 // The cross matrices are reduced over the warp and ADDED to the warp's own slots Mw[op][warp][8] (one writer lane
 // per slot: no atomics, fixed order); the CTA sums the warps after the last tile of the pass.
 template <int G, int TB, int NT>
-__device__ __forceinline__ void t_adj_group(double2 *tile, double2 *ltile, const uint4 *top, const double2 *Us, uint32_t tau,
-                                            int tid, int lane, double *mw /* this warp's [8] of the group's first op */,
+__device__ __forceinline__ void t_adj_group(double2 *tile, double2 *ltile, const uint4 *top, const uint32_t *kb, const double2 *Us,
+                                            uint32_t tau, int tid, int lane, double *mw /* this warp's [8] of the group's first op */,
                                             int mw_op_stride) {
-  uint32_t m[G], rl[G], xm[1 << G];
-  bool flip[G];
+  TGeom<G, TB, NT> gg;
+  gg.load(top, kb, tau, tid);
   int npar[G];
 #pragma unroll
-  for (int q = 0; q < G; ++q) {
-    m[q] = top[q].x;
-    rl[q] = top[q].y & ((1u << TB) - 1u);
-    flip[q] = __popc(tau & (top[q].y >> TB)) & 1;
-    npar[q] = qas_meta_npar(top[q].w);
-  }
+  for (int q = 0; q < G; ++q) npar[q] = qas_meta_npar(top[q].w);
   const uint32_t rc = (G == 1) ? top[0].z : 0u;
   const bool cflip = (G == 1) && (__popc(tau & (rc >> TB)) & 1);
   const uint32_t rcl = rc & ((1u << TB) - 1u);
-  const int q0 = 31 - __clz(m[0]);
-  int qlo = q0, qhi = q0;
-  if constexpr (G == 2) {
-    const uint32_t e1 = ((m[1] >> q0) & 1u) ? (m[1] ^ m[0]) : m[1];
-    const int q1 = 31 - __clz(e1);
-    qlo = min(q0, q1);
-    qhi = max(q0, q1);
-  }
-  xm[0] = 0u;
-#pragma unroll
-  for (int c = 1; c < (1 << G); ++c) xm[c] = xm[c & ~(c >= 2 ? 2 : 1)] ^ m[c >= 2 ? 1 : 0];
   double M[G][8];
 #pragma unroll
   for (int q = 0; q < G; ++q)
 #pragma unroll
     for (int e = 0; e < 8; ++e) M[q][e] = 0.0;
-  constexpr uint32_t NCOS = 1u << (TB - G);
-  for (uint32_t c = tid; c < NCOS; c += NT) {
-    uint32_t t = insert_zero(c, qlo);
-    if constexpr (G == 2) t = insert_zero(t, qhi);
-    uint32_t Pp = t;
-#pragma unroll
-    for (int q = 0; q < G; ++q) Pp ^= (((__popc(t & rl[q]) & 1) != 0) != flip[q]) ? m[q] : 0u;
+  for (int it = 0; it < TGeom<G, TB, NT>::NIT; ++it) {
+    const uint32_t Pp = gg.rep(it);
     if (G == 1 && rc && (((__popc(Pp & rcl) & 1) != 0) == cflip)) continue;
     double2 a[1 << G], l[1 << G];
 #pragma unroll
     for (int s = 0; s < (1 << G); ++s) {
-      a[s] = tile[Pp ^ xm[s]];
-      l[s] = ltile[Pp ^ xm[s]];
+      a[s] = tile[Pp ^ gg.xm[s]];
+      l[s] = ltile[Pp ^ gg.xm[s]];
     }
 #pragma unroll
     for (int q = 0; q < G; ++q) {
@@ -168,8 +158,8 @@ __device__ __forceinline__ void t_adj_group(double2 *tile, double2 *ltile, const
     }
 #pragma unroll
     for (int s = 0; s < (1 << G); ++s) {
-      tile[Pp ^ xm[s]] = a[s];
-      ltile[Pp ^ xm[s]] = l[s];
+      tile[Pp ^ gg.xm[s]] = a[s];
+      ltile[Pp ^ gg.xm[s]] = l[s];
     }
   }
   __syncwarp();
@@ -255,6 +245,8 @@ __global__ void __launch_bounds__(NT, MINB) eval_tiled_kernel(const EvalParams P
   base += (size_t)QAS_T_MAXP * 64;
   uint4 *top = reinterpret_cast<uint4 *>(base);                 // translated ops: m', A^T r, A^T rc, meta
   base += (size_t)QAS_T_MAXP * 16;
+  uint32_t *gkb = reinterpret_cast<uint32_t *>(base);           // coset basis of every group, at its first op
+  base += (size_t)QAS_T_MAXP * QAS_T_KBW * 4;
   double *Mw = nullptr, *Ms = nullptr;
   if constexpr (GRAD) {
     Mw = reinterpret_cast<double *>(base); base += (size_t)QAS_T_MAXP * NW * 64;
@@ -316,6 +308,18 @@ __global__ void __launch_bounds__(NT, MINB) eval_tiled_kernel(const EvalParams P
     for (int w = tid; w < cnt * 4; w += NT) Us[w] = P.U[ops[(size_t)(j0 + (w >> 2)) * QAS_OP_WORDS + 3]].u[w & 3];
   };
 
+  // coset bases of the pass's groups (needs every translated op: call after a barrier), one thread per group
+  auto group_bases = [&](int cnt) {
+    if (tid < cnt) {
+      const int g = (int)QAS_META_GFIRST(top[tid].w);
+      if (g >= 1 && qas_meta_kind(top[tid].w) == QAS_K_U1) {
+        uint32_t mm[2], rr[2];
+        for (int q = 0; q < g && q < 2; ++q) { mm[q] = top[tid + q].x; rr[q] = top[tid + q].y & ((1u << TB) - 1u); }
+        qas_tile_group_basis(g < 2 ? g : 2, mm, rr, TB, gkb + (size_t)tid * QAS_T_KBW);
+      }
+    }
+  };
+
   for (;;) {
     // ---- work queue: rank 0 draws a circuit for the cluster and posts the slot into every CTA's control block
     if (rank == 0 && tid == 0) {
@@ -355,6 +359,8 @@ __global__ void __launch_bounds__(NT, MINB) eval_tiled_kernel(const EvalParams P
         translate(j0, cnt);
         frame_regs();
         __syncthreads();
+        group_bases(cnt);
+        __syncthreads();
         for (uint32_t tau = rank; tau < ntiles; tau += CS) {
           const uint32_t p0 = tile_origin(tau);
           if (first) {
@@ -375,8 +381,8 @@ __global__ void __launch_bounds__(NT, MINB) eval_tiled_kernel(const EvalParams P
             const int g = max(1, (int)QAS_META_GLAST(top[i].w));
             const int f = i - g + 1;
             if (qas_meta_kind(top[f].w) == QAS_K_U1) {
-              if (g == 2) t_fwd_group<2, TB, NT>(tile, top + f, Us + 4 * f, tau, tid);
-              else t_fwd_group<1, TB, NT>(tile, top + f, Us + 4 * f, tau, tid);
+              if (g == 2) t_fwd_group<2, TB, NT>(tile, top + f, gkb + (size_t)f * QAS_T_KBW, Us + 4 * f, tau, tid);
+              else t_fwd_group<1, TB, NT>(tile, top + f, gkb + (size_t)f * QAS_T_KBW, Us + 4 * f, tau, tid);
             } else {
               const double2 d0 = Us[4 * f], d1 = Us[4 * f + 3];
               const uint32_t rl = top[f].y & ((1u << TB) - 1u);
@@ -438,6 +444,8 @@ __global__ void __launch_bounds__(NT, MINB) eval_tiled_kernel(const EvalParams P
         frame_regs();
         for (int w = tid; w < cnt * NW * 8; w += NT) Mw[w] = 0.0;
         __syncthreads();
+        group_bases(cnt);
+        __syncthreads();
         for (uint32_t tau = rank; tau < ntiles; tau += CS) {
           const uint32_t p0 = tile_origin(tau);
           {
@@ -458,8 +466,8 @@ __global__ void __launch_bounds__(NT, MINB) eval_tiled_kernel(const EvalParams P
             const int g = max(1, (int)QAS_META_GFIRST(top[f].w));
             double *mw = Mw + ((size_t)f * NW + warp) * 8;
             if (qas_meta_kind(top[f].w) == QAS_K_U1) {
-              if (g == 2) t_adj_group<2, TB, NT>(tile, ltile, top + f, Us + 4 * f, tau, tid, lane, mw, NW * 8);
-              else t_adj_group<1, TB, NT>(tile, ltile, top + f, Us + 4 * f, tau, tid, lane, mw, NW * 8);
+              if (g == 2) t_adj_group<2, TB, NT>(tile, ltile, top + f, gkb + (size_t)f * QAS_T_KBW, Us + 4 * f, tau, tid, lane, mw, NW * 8);
+              else t_adj_group<1, TB, NT>(tile, ltile, top + f, gkb + (size_t)f * QAS_T_KBW, Us + 4 * f, tau, tid, lane, mw, NW * 8);
             } else {
               const double2 d0 = Us[4 * f], d1 = Us[4 * f + 3];
               const uint32_t rl = top[f].y & ((1u << TB) - 1u);

@@ -756,3 +756,27 @@ QAS_HD int qas_plan_tile_pass(const uint32_t *ops, int nops, int start, int dir,
   for (int p = clow; p < n; ++p) if (piv[p] < 0) { col[d] = 1u << p; piv[p] = d; ++d; }
   return cnt;
 }
+
+// Coset representatives of a pass group inside a tile: K = {x in GF(2)^tb : parity(x & r_q) = 0 for every gate q of the
+// group} meets every coset of span(m_0 .. m_{g-1}) exactly once (parity(m_a & r_b) = delta_ab), and on K the slot index
+// bits of x ^ (c_0 m_0 ^ c_1 m_1) are the gates' logical bits.  kb receives a basis of K in lowest-set-bit echelon form,
+// ascending pivots: coset c of the group is represented by the xor of the kb[i] selected by the bits of c, so the
+// eight lanes of a quarter-warp (c bits 0..2) land on eight different 16-byte bank groups whenever K has vectors with
+// lowest set bits 0, 1 and 2 -- the pivot set of an echelon basis is the smallest possible, i.e. this is the best
+// any enumeration of K can do.  Returns the dimension (tb - g).
+QAS_HD int qas_tile_group_basis(int g, const uint32_t *m, const uint32_t *r, int tb, uint32_t *kb) {
+  uint32_t pv[QAS_TP_MAXQ];
+  for (int p = 0; p < tb; ++p) pv[p] = 0u;
+  for (int i = 0; i < tb; ++i) {
+    uint32_t x = 1u << i;
+    for (int q = 0; q < g; ++q) if ((r[q] >> i) & 1u) x ^= m[q];      // projection of e_i onto K along span(m)
+    while (x) {
+      const int p = qas_lsb32(x);
+      if (pv[p]) x ^= pv[p];
+      else { pv[p] = x; break; }
+    }
+  }
+  int cnt = 0;
+  for (int p = 0; p < tb; ++p) if (pv[p]) kb[cnt++] = pv[p];
+  return cnt;
+}

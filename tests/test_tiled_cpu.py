@@ -95,3 +95,33 @@ def test_tiled_empty_tape():
     ops, idx = compile_tape_host(n, pool, k, 0)
     e, gr, npf, npa = TL.run_tiled(n, ops.reshape(-1, 5), ("zero", 0), idx, pool.pool, len(pool), params, terms, 4, 2)
     assert abs(e - 0.9) < 1e-14 and not gr and npf == 1 and npa == 0
+
+
+def test_group_coset_bases_are_conflict_free_where_possible():
+    """qas_tile_group_basis: the basis lies in the common kernel of the parity masks, has distinct ascending lowest-set-bit
+    pivots, enumerates every coset of span(m) exactly once, and a quarter-warp (eight consecutive cosets) touches eight
+    different 16-byte bank groups whenever the kernel has vectors with lowest set bits 0, 1 and 2."""
+    rng = np.random.default_rng(11)
+    tb = 9
+    degs = []
+    for trial in range(60):
+        g = 1 + trial % 2
+        while True:       # random masks with parity(m_a & r_b) = delta_ab
+            ms = [int(rng.integers(1, 1 << tb)) for _ in range(g)]
+            rs = [int(rng.integers(1, 1 << tb)) for _ in range(g)]
+            if all(TL._parity(ms[a] & rs[b]) == (1 if a == b else 0) for a in range(g) for b in range(g)):
+                break
+        kb = TL.group_basis(g, tb, ms, rs)
+        lsb = [(v & -v).bit_length() - 1 for v in kb]
+        assert lsb == sorted(set(lsb)) and len(kb) == tb - g
+        pp, xm = TL._cosets(g, tb, ms, rs, [bool(trial & 4)] * g)
+        cover = np.zeros(1 << tb, dtype=int)
+        for x in xm:
+            cover[pp ^ x] += 1
+        assert (cover == 1).all()
+        q = (pp.reshape(-1, 8) & 7)
+        deg = max(int((q == b).sum(axis=1).max()) for b in range(8))
+        if lsb[:3] == [0, 1, 2]:
+            assert deg == 1
+        degs.append(deg)
+    assert np.mean(degs) < 1.5

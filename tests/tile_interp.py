@@ -3,8 +3,8 @@
 Restates, on the CPU, what eval_tiled_kernel (qas_b200/csrc/kernels_t.cuh) does with a grouped tape: tile passes
 planned by the C planner (qas_plan_tile_pass_host -- the code the kernel runs before every pass), ops translated to
 pass coordinates (m' = A^-1 m by reduction against the pivot table, r' = A^T r), every pass executed tile by tile
-with the kernel's coset enumeration (insert zeros at the mask pivots, project onto the common kernel of the parity
-masks, tile-number parities as role flips / constant controls), slab written back through the frame, cross
+with the kernel's coset enumeration (an echelon basis of the common kernel of the group's parity masks from the C
+routine qas_tile_group_basis, tile-number parities as role flips / constant controls), slab written back through the frame, cross
 matrices accumulated over the tiles.  It is not part of the product.
 """
 import ctypes
@@ -64,18 +64,33 @@ def _insert_zero(t, b):
 _par = np.vectorize(_parity)
 
 
+def group_basis(g, tb, ms, rls):
+    """the C routine the kernel runs once per group and pass (qas_tile_group_basis)"""
+    from qas_b200 import _lib
+    lib = _lib.load()
+    m = np.array(ms, dtype=np.uint32)
+    r = np.array(rls, dtype=np.uint32)
+    kb = np.zeros(16, dtype=np.uint32)
+    dim = ctypes.c_int(0)
+    rc = lib.qas_tile_group_basis_host(g, m.ctypes.data, r.ctypes.data, tb, kb.ctypes.data, ctypes.byref(dim))
+    assert rc == 0 and dim.value == tb - g
+    return [int(x) for x in kb[:dim.value]]
+
+
 def _cosets(g, tb, ms, rls, flips):
-    """representatives Pp (projected: logical bits of the group's gates are 0) and the slot masks xm"""
-    q0 = ms[0].bit_length() - 1
-    t = _insert_zero(np.arange(1 << (tb - g)), q0) if g == 1 else None
-    if g == 2:
-        e1 = ms[1] ^ ms[0] if (ms[1] >> q0) & 1 else ms[1]
-        q1 = e1.bit_length() - 1
-        t = _insert_zero(_insert_zero(np.arange(1 << (tb - g)), min(q0, q1)), max(q0, q1))
-    pp = t.copy()
+    """representatives Pp (logical bits of the group's gates are 0) in the kernel's enumeration order -- coset c =
+    role-flip offset xor the basis vectors of K selected by the bits of c -- and the slot masks xm"""
+    kb = group_basis(g, tb, ms, rls)
+    for v in kb:
+        assert all(_parity(v & rls[q]) == 0 for q in range(g))
+    off = 0
     for q in range(g):
-        fire = (_par(t & rls[q]) == 1) != flips[q]
-        pp ^= np.where(fire, ms[q], 0)
+        if flips[q]:
+            off ^= ms[q]
+    c = np.arange(1 << (tb - g))
+    pp = np.full(1 << (tb - g), off, dtype=np.int64)
+    for i, v in enumerate(kb):
+        pp ^= np.where((c >> i) & 1, v, 0)
     xm = [0, ms[0]] if g == 1 else [0, ms[0], ms[1], ms[0] ^ ms[1]]
     return pp, xm
 
