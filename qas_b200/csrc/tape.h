@@ -204,15 +204,13 @@ QAS_HD int qas_compile_circuit(const int32_t *k, int p, const qas_pool_entry *po
 // The X_i are put in lowest-set-bit echelon form of their (swizzled) shared-memory slot index and
 // sorted by pivot, so that the three lane bits of a quarter-warp get independent low address bits
 // whenever the subspace allows it (bank conflicts).  Uniform initial state: D is everything.
-// Loops over the pivot tables: unrolled, so that the tables live in registers.  Measured alternative
-// (-DQAS_PLAN_ROLLED: tables in local memory, 4k instead of 63k instructions in the tape-compile kernel):
-// compile time LiH-10q 0.21 -> 0.56 ms per 65536 circuits -- the local-memory round trips cost more than
-// the instruction-fetch stalls of the unrolled code.
-#if defined(QAS_PLAN_ROLLED)
-#define QAS_PUNROLL _Pragma("unroll 1")
-#else
-#define QAS_PUNROLL _Pragma("unroll")
-#endif
+// The pivot tables are PACKED into a few 32-bit registers (QasPackTab: 8-bit entries up to 8 qubits, 16-bit up to 16) and
+// every reduction is a data-dependent loop over the set bits it actually meets -- a handful of iterations -- instead of
+// a fully unrolled sweep over all NQ pivots: a third of the executed instructions for an 8-qubit H2O tape and a code
+// footprint that fits the instruction cache (the unrolled tables made compile_tapes_kernel 63 k SASS instructions with
+// `no_instruction` as its top stall; tables in local memory, the other way to roll the loops, were slower still).  The
+// results are bit-identical to the unrolled formulation (same insertion order, same reductions).
+#define QAS_PUNROLL _Pragma("unroll")     // register-resident tables of the c-tape compiler (qas_compress_packed)
 #define QAS_META_GFIRST(m) (((m) >> 24) & 3u)
 #define QAS_META_GLAST(m) (((m) >> 26) & 3u)
 #define QAS_GD_HDR 2        // P0, dc
@@ -250,42 +248,72 @@ QAS_HD uint32_t qas_swz(uint32_t i) {
   return i ^ (f & 7u);
 }
 
-// Subspaces of GF(2)^n are kept as pivot-indexed tables, tab[p] = the basis vector whose pivot is
-// bit p (0 = none), and every loop over them has a compile-time trip count NQ: on the device the
-// tables then live in registers (one thread plans one circuit).
+// Subspaces of GF(2)^n are kept as pivot-indexed tables, entry p = the basis vector whose pivot is bit p (0 = none),
+// packed EB bits per entry into 32-bit words that stay in registers: a run-time index costs a select chain over the
+// W words and one shift, never a local-memory access (one thread plans one circuit).
 template <int NQ>
-struct QasPivTab {
-  uint32_t v[NQ];
+struct QasPackTab {
+  static constexpr int EB = NQ <= 8 ? 8 : (NQ <= 16 ? 16 : 32);
+  static constexpr int PER = 32 / EB;
+  static constexpr int W = (NQ + PER - 1) / PER;
+  static constexpr uint32_t EM = EB == 32 ? 0xffffffffu : ((1u << (EB & 31)) - 1u);
+  uint32_t w[W];
   QAS_HD void clear() {
-QAS_PUNROLL
-    for (int p = 0; p < NQ; ++p) v[p] = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < W; ++i) w[i] = 0u;
+  }
+  QAS_HD uint32_t get(int p) const {
+    const int wi = p / PER;
+    uint32_t x = w[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 1; i < W; ++i) x = (wi == i) ? w[i] : x;
+    return (x >> ((p % PER) * EB)) & EM;
+  }
+  QAS_HD void toggle(int p, uint32_t v) {          // entry p ^= v  (v = the whole vector for an empty entry)
+    const int wi = p / PER;
+    const uint32_t s = v << ((p % PER) * EB);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < W; ++i) w[i] ^= (wi == i) ? s : 0u;
+  }
+  QAS_HD int rank(int n) const {
+    int r = 0;
+    for (int p = 0; p < n; ++p) r += get(p) ? 1 : 0;
+    return r;
   }
 };
 // highest-set-bit pivots (rank / membership)
 template <int NQ>
-QAS_HD bool qas_tab_add_msb(QasPivTab<NQ> &t, uint32_t x) {
+QAS_HD bool qas_tab_add_msb(QasPackTab<NQ> &t, uint32_t x) {
   bool placed = false;
-QAS_PUNROLL
-  for (int p = NQ - 1; p >= 0; --p) {
-    if (!placed && ((x >> p) & 1u)) {
-      if (t.v[p]) x ^= t.v[p];
-      else { t.v[p] = x; placed = true; }
-    }
+  while (x) {
+    const int p = qas_msb32(x);
+    const uint32_t v = t.get(p);
+    if (!v) { t.toggle(p, x); placed = true; break; }
+    x ^= v;
   }
   return placed;
 }
-// lowest-set-bit pivots: x is reduced against `a` and `b` (either may hold pivot p) and, if something
-// is left, stored in `dst` (which is `a` or `b`).  Reducing at pivot p only changes bits above p.
+// lowest-set-bit pivots: x is reduced against `all` (the union of the tables built so far: their pivots are disjoint)
+// and, if something is left, stored in `dst` and in `all`.  Reducing at pivot p only changes bits above p.
 template <int NQ>
-QAS_HD bool qas_tab_add_lsb(const QasPivTab<NQ> &a, QasPivTab<NQ> &b, bool into_b, QasPivTab<NQ> &a_mut, uint32_t x) {
+QAS_HD bool qas_tab_add_lsb(QasPackTab<NQ> &all, QasPackTab<NQ> &dst, bool dst_is_all, uint32_t x) {
   bool placed = false;
-QAS_PUNROLL
-  for (int p = 0; p < NQ; ++p) {
-    if (!placed && ((x >> p) & 1u)) {
-      const uint32_t v = a.v[p] ? a.v[p] : b.v[p];
-      if (v) x ^= v;
-      else { if (into_b) b.v[p] = x; else a_mut.v[p] = x; placed = true; }
+  while (x) {
+    const int p = qas_lsb32(x);
+    const uint32_t v = all.get(p);
+    if (!v) {
+      all.toggle(p, x);
+      if (!dst_is_all) dst.toggle(p, x);
+      placed = true;
+      break;
     }
+    x ^= v;
   }
   return placed;
 }
@@ -308,8 +336,15 @@ struct QasHInfo {
   uint32_t wv[3];      // basis of W in reduced echelon form (wv[q] has pivot rb[q])
 };
 QAS_HD uint32_t qas_ubar(const QasHInfo &hi, uint32_t x) {
-  for (int q = 0; q < hi.RB; ++q) if ((x >> hi.rb[q]) & 1u) x ^= hi.wv[q];
-  for (int q = hi.RB - 1; q >= 0; --q) x = ((x >> (hi.rb[q] + 1)) << hi.rb[q]) | (x & ((1u << hi.rb[q]) - 1u));
+  // compile-time trip counts: the descriptor is a kernel argument and must not be indexed at run time (local memory)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 3; ++q) if (q < hi.RB && ((x >> hi.rb[q]) & 1u)) x ^= hi.wv[q];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 2; q >= 0; --q) if (q < hi.RB) x = ((x >> (hi.rb[q] + 1)) << hi.rb[q]) | (x & ((1u << hi.rb[q]) - 1u));
   return x;
 }
 
@@ -317,11 +352,12 @@ template <int NQ>
 QAS_HD void qas_plan_supports(const uint32_t *ops, int nops, int ngroups, int n, int init_kind,
                               uint32_t init_index, uint32_t *gd, int swizzled,
                               const QasHInfo *hi = nullptr, uint32_t *hd = nullptr) {
-  QasPivTab<NQ> D;
+  QasPackTab<NQ> D;
   D.clear();
+  int drank = 0;
   if (init_kind == QAS_INIT_PLUS) {
-QAS_PUNROLL
-    for (int p = 0; p < NQ; ++p) if (p < n) D.v[p] = 1u << p;
+    for (int p = 0; p < n; ++p) D.toggle(p, 1u << p);
+    drank = n;
   }
   const uint32_t b0 = (init_kind == QAS_INIT_BASIS) ? init_index : 0u;
   const int stride = QAS_GD_STRIDE(n);
@@ -348,76 +384,73 @@ QAS_PUNROLL
       if (qas_parity32(r2 & x)) y ^= m2;
       return swizzled ? qas_swz(y) : y;
     };
-    QasPivTab<NQ> Sin, Sout;
-    Sin.clear();
-    Sout.clear();
-    int dc = 0, tot = 0, drank = 0;
-QAS_PUNROLL
-    for (int p = 0; p < NQ; ++p) drank += D.v[p] ? 1 : 0;
+    auto proj_unit = [&](int p) {                 // proj(1 << p): the parities are single bits of the r's
+      uint32_t y = 1u << p;
+      if ((r0 >> p) & 1u) y ^= m0;
+      if ((r1 >> p) & 1u) y ^= m1;
+      if ((r2 >> p) & 1u) y ^= m2;
+      return swizzled ? qas_swz(y) : y;
+    };
+    QasPackTab<NQ> Sall, Sin;                     // Sall = Sin + the completion vectors (disjoint pivots)
+    Sall.clear();
+    int dc = 0, tot = 0;
     if (drank == n) {     // the state is dense already: every coset is inside, one echelon pass
-QAS_PUNROLL
-      for (int p = 0; p < NQ; ++p)
-        if (p < n) dc += qas_tab_add_lsb<NQ>(Sin, Sout, false, Sin, proj(1u << p)) ? 1 : 0;
+      for (int p = 0; p < n; ++p) dc += qas_tab_add_lsb<NQ>(Sall, Sall, true, proj_unit(p)) ? 1 : 0;
       tot = dc;
+      d[0] = proj(b0);
+      d[1] = (uint32_t)dc;
+      int cnt = 0;
+      for (int p = 0; p < n; ++p) { const uint32_t v = Sall.get(p); if (v) d[QAS_GD_HDR + cnt++] = v; }
     } else {
-QAS_PUNROLL
-      for (int p = 0; p < NQ; ++p)
-        if (D.v[p]) dc += qas_tab_add_lsb<NQ>(Sin, Sout, false, Sin, proj(D.v[p])) ? 1 : 0;
+      for (int p = 0; p < n; ++p) {
+        const uint32_t v = D.get(p);
+        if (v) dc += qas_tab_add_lsb<NQ>(Sall, Sall, true, proj(v)) ? 1 : 0;
+      }
+      Sin = Sall;
       tot = dc;
-QAS_PUNROLL
-      for (int p = 0; p < NQ; ++p)
-        if (p < n && tot < n - g) tot += qas_tab_add_lsb<NQ>(Sin, Sout, true, Sin, proj(1u << p)) ? 1 : 0;
+      for (int p = 0; p < n && tot < n - g; ++p) tot += qas_tab_add_lsb<NQ>(Sall, Sall, true, proj_unit(p)) ? 1 : 0;
+      d[0] = proj(b0);
+      d[1] = (uint32_t)dc;
+      int cnt = 0;
+      for (int p = 0; p < n; ++p) { const uint32_t v = Sin.get(p); if (v) d[QAS_GD_HDR + cnt++] = v; }
+      for (int p = 0; p < n; ++p) { const uint32_t v = Sall.get(p); if (v && !Sin.get(p)) d[QAS_GD_HDR + cnt++] = v; }
+      drank += qas_tab_add_msb<NQ>(D, m0) ? 1 : 0;
+      if (g > 1) drank += qas_tab_add_msb<NQ>(D, m1) ? 1 : 0;
+      if (g > 2) drank += qas_tab_add_msb<NQ>(D, m2) ? 1 : 0;
     }
-    d[0] = proj(b0);
-    d[1] = (uint32_t)dc;
-    int cnt = 0;
-QAS_PUNROLL
-    for (int p = 0; p < NQ; ++p) if (Sin.v[p]) d[QAS_GD_HDR + cnt++] = Sin.v[p];
-QAS_PUNROLL
-    for (int p = 0; p < NQ; ++p) if (Sout.v[p]) d[QAS_GD_HDR + cnt++] = Sout.v[p];
-    qas_tab_add_msb<NQ>(D, m0);
-    if (g > 1) qas_tab_add_msb<NQ>(D, m1);
-    if (g > 2) qas_tab_add_msb<NQ>(D, m2);
   }
   if (!hd) return;
   const int nu = n - (hi ? hi->RB : 0);
   hd[0] = 0u;
   hd[1] = (uint32_t)nu;                           // dense unless shown otherwise
   if (!hi || !hi->enable || nu > NQ || 2 + 2 * nu > QAS_HD_WORDS) return;
-  int drank = 0;
-QAS_PUNROLL
-  for (int p = 0; p < NQ; ++p) drank += D.v[p] ? 1 : 0;
   if (drank >= n) return;                         // the final state is dense
-  QasPivTab<NQ> E;
+  QasPackTab<NQ> E;
   E.clear();
   int dbar = 0;
-QAS_PUNROLL
-  for (int p = 0; p < NQ; ++p)
-    if (D.v[p]) dbar += qas_tab_add_msb<NQ>(E, qas_ubar(*hi, D.v[p])) ? 1 : 0;
+  for (int p = 0; p < n; ++p) {
+    const uint32_t v = D.get(p);
+    if (v) dbar += qas_tab_add_msb<NQ>(E, qas_ubar(*hi, v)) ? 1 : 0;
+  }
   if (dbar >= nu) return;
   // reduced echelon form: clear every pivot bit from the other basis vectors (ascending pivots, so the
   // vector xor-ed in is already free of lower pivot bits)
-QAS_PUNROLL
-  for (int p = 0; p < NQ; ++p)
-    if (E.v[p]) {
-QAS_PUNROLL
-      for (int p2 = 0; p2 < NQ; ++p2)
-        if (p2 > p && ((E.v[p2] >> p) & 1u)) E.v[p2] ^= E.v[p];
-    }
+  for (int p = 0; p < nu; ++p) {
+    const uint32_t v = E.get(p);
+    if (!v) continue;
+    for (int p2 = p + 1; p2 < nu; ++p2)
+      if ((E.get(p2) >> p) & 1u) E.toggle(p2, v);
+  }
   hd[0] = qas_ubar(*hi, b0);
   hd[1] = (uint32_t)dbar;
   int cnt = 0;
-QAS_PUNROLL
-  for (int p = 0; p < NQ; ++p) if (p < nu && E.v[p]) hd[2 + cnt++] = E.v[p];
-QAS_PUNROLL
-  for (int p = 0; p < NQ; ++p) if (p < nu && !E.v[p]) hd[2 + cnt++] = 1u << p;
+  for (int p = 0; p < nu; ++p) { const uint32_t v = E.get(p); if (v) hd[2 + cnt++] = v; }
+  for (int p = 0; p < nu; ++p) if (!E.get(p)) hd[2 + cnt++] = 1u << p;
   int kc = 0;
-QAS_PUNROLL
-  for (int f = 0; f < NQ; ++f)
-    if (f < nu && !E.v[f]) {
+  for (int f = 0; f < nu; ++f)
+    if (!E.get(f)) {
       uint32_t chk = 1u << f;
-QAS_PUNROLL
-      for (int p = 0; p < NQ; ++p) if (E.v[p] && ((E.v[p] >> f) & 1u)) chk |= 1u << p;
+      for (int p = 0; p < nu; ++p) if ((E.get(p) >> f) & 1u) chk |= 1u << p;
       hd[2 + nu + kc++] = chk;
     }
 }
