@@ -432,6 +432,7 @@ extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
   cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_cdesc_plain); cudaFree(ctx->d_cdesc_u);
   cudaFree(ctx->d_U); cudaFree(ctx->d_dU); cudaFree(ctx->d_k); cudaFree(ctx->d_params);
   cudaFree(ctx->d_energy); cudaFree(ctx->d_grad); cudaFree(ctx->d_partial); cudaFree(ctx->d_dense);
+  if (ctx->h_k8) cudaFreeHost(ctx->h_k8);
   cudaFree(ctx->d_gstate); cudaFree(ctx->d_mout); cudaFree(ctx->d_tape); cudaFree(ctx->d_phase);
   if (ctx->h_tape) cudaFreeHost(ctx->h_tape);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -553,7 +554,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   if (B <= 0 || p <= 0 || p > 65535 || !k || (!params && !(flags & QAS_F_PARAMS_RESIDENT)) || !energy)
     return fail(ctx, QAS_ERR_INVALID, "bad arguments to qas_eval_batch");
   const bool dev = flags & QAS_F_DEVICE_PTRS;
-  const bool k8 = (flags & QAS_F_K_U8) != 0;
+  bool k8 = (flags & QAS_F_K_U8) != 0;
   const bool want_grad = grad_compact || grad_dense;
   const int c = ctx->c, l = ctx->l;
   if (k8 && c > 256) return fail(ctx, QAS_ERR_INVALID, "QAS_F_K_U8 needs a pool of at most 256 entries");
@@ -587,6 +588,38 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   if (k8 && !dev && B <= 16) {
     k_wide.assign(k_bytes, k_bytes + nk);
     k = k_wide.data();
+  }
+  // Pageable int32 structure lists of a large host batch (plain NumPy arrays: what search() hands the drop-in classes):
+  // the driver would stage 4 bytes per key through its own bounce buffers while the calling thread waits.  Narrow them
+  // to one byte per key into a page-locked buffer instead -- the reference's range asserts (utils.py:12-15) in the same
+  // pass -- and upload a quarter of the bytes asynchronously, like a QAS_F_K_U8 call.
+  bool k_checked = false;
+  if (!dev && !k8 && B > 16 && !capturing && c <= 256) {
+    cudaPointerAttributes pa{};
+    bool pageable = false;
+    if (cudaPointerGetAttributes(&pa, k) == cudaSuccess) pageable = pa.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+    if (pageable) {
+      if (ctx->cap_hk8 < nk) {
+        if (ctx->h_k8) cudaFreeHost(ctx->h_k8);
+        ctx->h_k8 = nullptr; ctx->cap_hk8 = 0;
+        CK(cudaHostAlloc((void **)&ctx->h_k8, std::max<size_t>(nk, 4096), cudaHostAllocDefault));
+        ctx->cap_hk8 = std::max<size_t>(nk, 4096);
+      }
+      // the previous call's upload from this buffer has completed: every host-pointer call ends with a stream sync
+      uint8_t *h8 = ctx->h_k8;
+      const uint32_t cu = (uint32_t)c;
+      uint32_t bad = 0;
+      for (size_t i = 0; i < nk; ++i) {
+        const uint32_t v = (uint32_t)k[i];
+        bad |= (uint32_t)(v >= cu);
+        h8[i] = (uint8_t)v;
+      }
+      if (bad) return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
+      k_bytes = h8;
+      k8 = true;
+      k_checked = true;
+    }
   }
   const bool k8_dev = k8 && (dev || B > 16);      // keys reach the device as bytes and are widened there
   const int32_t *dk = k;
@@ -855,6 +888,22 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     }
   }
   if (!tiny && !capturing) { CK(cudaEventRecord(ctx->ek1, st)); ctx->ek_pending = true; }
+  // Host-pointer calls: the energies are final once the evaluation kernels have finished -- read them back on the copy
+  // stream while the finalize / batch-reduction kernels still run (LiH: 0.5 MB = 25 us of PCIe time behind 40 us of kernels)
+  // Only into page-locked caller memory: a device-to-host copy into pageable pages blocks the calling thread until it
+  // has run, and the reduction kernels would not even be enqueued before the evaluation kernels end (measured: 0.86 ->
+  // 1.54 ms per call).
+  bool energy_early = false;
+  if (!dev && !tiny && !capturing && want_grad && ctx->copy_stream) {
+    cudaPointerAttributes pa{};
+    if (cudaPointerGetAttributes(&pa, energy) == cudaSuccess) energy_early = pa.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
+  if (energy_early) {
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ek1, 0));
+    CK(cudaMemcpyAsync(energy, denergy, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+  }
   stamp(4);
   if (want_grad && !small && !use_c) {
     const size_t nthr = (size_t)B * ops_cap;
@@ -908,17 +957,19 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
 
   if (!dev) {
     if (!tiny) CK(cudaEventRecord(ctx->ev1, st));
-    if (B > 16) {      // deferred range check of the structure lists; branch-free so that it vectorises
+    if (B > 16 && !k_checked) {      // deferred range check of the structure lists; branch-free so that it vectorises
       uint32_t bad = 0;
       const uint32_t cu = (uint32_t)c;
       if (k8) for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k_bytes[i] >= cu);
       else for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k[i] >= cu);
       if (bad) {
         cudaStreamSynchronize(st);
+        if (energy_early) cudaStreamSynchronize(ctx->copy_stream);      // nothing may land in caller memory after the return
         return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
       }
     }
-    CK(cudaMemcpyAsync(energy, denergy, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if (energy_early) CK(cudaStreamWaitEvent(st, ctx->copy_done, 0));
+    else CK(cudaMemcpyAsync(energy, denergy, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     if (grad_compact) CK(cudaMemcpyAsync(grad_compact, dgrad, ng * 8, cudaMemcpyDeviceToHost, st));
     if (grad_dense) CK(cudaMemcpyAsync(grad_dense, ddense, npar * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

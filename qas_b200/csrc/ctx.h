@@ -79,6 +79,7 @@ struct qas_ctx {
   double2 *d_gstate = nullptr; size_t cap_gstate = 0;
   uint32_t *d_tape = nullptr; size_t cap_tape = 0;
   uint32_t *h_tape = nullptr; size_t cap_htape = 0;   // pinned staging for host-compiled tapes (tiny batches)
+  uint8_t *h_k8 = nullptr; size_t cap_hk8 = 0;        // pinned staging: pageable int32 structure lists narrowed to one byte per key
   qas_stats stats{};
   mutable std::string err;
 };
