@@ -120,8 +120,8 @@ __host__ __device__ inline size_t evalc_team_smem_bytes(int slot_bits, int T, bo
   b += (((size_t)(QAS_REC_HDR + ops_cap * QAS_OP_WORDS) * 4) + 15) & ~(size_t)15;
   b += 32 * 4;                                         // nsl + basis (<= QAS_CT_MAX_D words) | physical offsets of the HA strides
   b += (size_t)S * 16;                                 // slice records (CSlice)
-  b += (size_t)ops_cap * 64;                           // staged gate matrices
-  if (grad) b += (size_t)ops_cap * 64;                 // cross matrices M of the circuit's ops
+  b += (size_t)ops_cap * 64;                           // staged gate matrices; gradient launches overwrite the slot of an op with its
+                                                       // cross matrix M once the adjoint sweep has passed the op (last use of the gate)
   if (grad && wpt > 1) b += (size_t)2 * 2 * wpt * 64;  // cross-matrix ring (two buffers, <= 2 gates per pass)
   b += (((size_t)wpt * 8) + 15) & ~(size_t)15;
   b += 16;                                             // the team's work-queue slot
@@ -398,8 +398,11 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
   base += (size_t)P.S * 16;
   double2 *Us = reinterpret_cast<double2 *>(base);
   base += (size_t)P.ops_cap * 64;
-  double *Ms = reinterpret_cast<double *>(base);                 // [ops_cap][8] (GRAD)
-  if constexpr (GRAD) base += (size_t)P.ops_cap * 64;
+  // cross matrices [ops_cap][8] (GRAD): in place of the gate matrices.  The adjoint sweep reads U_j for the last time in
+  // the pass of op j and publishes M_j after that pass's sweep (all lanes of the team are past their loads: warp shuffles
+  // of the reduction for one-warp teams, the team barrier before the fixed-order sum for multi-warp teams), so the
+  // 64 bytes of the op's slot are free -- 16 one-warp circuits of a 2^7 register fit an SM instead of 12
+  double *Ms = reinterpret_cast<double *>(Us);
   double *red = nullptr;
   if constexpr (GRAD && WPT > 1) { red = reinterpret_cast<double *>(base); base += (size_t)2 * 2 * WPT * 64; }
   double *ered = reinterpret_cast<double *>(base);
@@ -579,3 +582,4 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
     team_sync<T>(team, tmask);   // state buffers are reused by the next circuit of this team
   }
 }
+
