@@ -286,6 +286,7 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
     if (const char *me = getenv("QAS_B200_COMPRESS_MIN_N")) cmin = std::max(7, atoi(me));
     cx->compress = (!ce || atoi(ce) != 0) && init_kind == QAS_INIT_ZERO && n_qubits >= cmin && n_qubits <= 16;
     if (const char *de = getenv("QAS_B200_COMPRESS_DMIN")) cx->c_dmin = std::max(1, std::min(QAS_CT_MAX_D, atoi(de)));
+    if (const char *ge = getenv("QAS_B200_GATE_IN_COMPILE")) cx->gate_in_compile = atoi(ge) != 0;
     cx->c_maxd = std::min(QAS_CT_MAX_D, n_qubits - 1);
     cx->c_dmin = std::min(cx->c_dmin, cx->c_maxd);
     cx->c_nbins = cx->c_maxd - cx->c_dmin + 1;
@@ -734,7 +735,9 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   stamp(1);
   // gate table first (it only needs the parameters), then the structure lists: the upload has had the memsets and
   // this kernel to hide behind
-  if (!resident) {
+  // device-compiled compressed batches: spare CTAs of the c-tape compile kernel build the table (no launch of its own)
+  const bool gate_table_in_compile = !resident && use_c && !(!small && !dev && B <= 16) && ctx->gate_in_compile;
+  if (!resident && !gate_table_in_compile) {
     build_gate_table_kernel<<<(p * c + 127) / 128, 128, 0, st>>>(ctx->d_pool, c, p, l, dparams, ctx->d_U, ctx->d_dU);
     CK(cudaGetLastError());
     ctx->stats.launches += 1;
@@ -814,6 +817,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     C.k = dk; C.pool = ctx->d_pool; C.sxflat = ctx->d_sxflat; C.tape = ctx->d_tape; C.bin_count = ctx->d_bins;
     C.bin_order = ctx->d_order; C.B = B; C.p = p; C.c = c; C.n = ctx->n; C.ops_cap = ops_cap; C.S = ctx->S_flat;
     C.gmax = ctx->GMAX; C.dmin = ctx->c_dmin; C.max_d = ctx->c_maxd; C.full_bin = ctx->c_nbins; C.rec_stride = rec_words;
+    C.params = dparams; C.U = ctx->d_U; C.dU = ctx->d_dU; C.l = l; C.gate_blocks = gate_table_in_compile ? (p * c + 63) / 64 : 0;
     CK(qas_launch_compile_c(ctx, C, st));
     ctx->stats.launches += 1;
   } else {

@@ -49,6 +49,7 @@ struct qas_ctx {
   int *d_counter = nullptr;        // work-queue head of the classic team kernels (= d_bins + QAS_MAX_BINS + full bin)
   // support-compressed path (kernels_c.cuh): circuits binned by the dimension d of their support span
   bool compress = false;           // all-zero start, n >= 7, QAS_B200_COMPRESS != 0
+  bool gate_in_compile = true;     // gate table built by spare CTAs of the c-tape compile kernel (QAS_B200_GATE_IN_COMPILE=0: own launch)
   int c_dmin = 6, c_maxd = QAS_CT_MAX_D;   // smallest / largest compressed slot (log2 amplitudes)
   int c_nbins = 0;                 // compressed bins: slot c_dmin + i, i < c_nbins; the full bin is index c_nbins
   int *d_bins = nullptr;           // [QAS_MAX_BINS] counts | [QAS_MAX_BINS] work-queue heads

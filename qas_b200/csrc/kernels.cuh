@@ -99,9 +99,10 @@ __device__ __forceinline__ double2 cexpi(double t) {
 __device__ __forceinline__ double2 cscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
 __device__ __forceinline__ double2 cmuli(double2 a) { return make_double2(-a.y, a.x); }   // i*a
 
-static __global__ void build_gate_table_kernel(const qas_pool_entry *pool, int c, int p, int l,
-                                        const double *params, GateTab *U, GateDTab *dU) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// entry idx = depth * c + key of the table; also called by spare CTAs of the c-tape compile kernel (kernels_c.cuh), which
+// saves the separate launch in front of the compiler
+__device__ __forceinline__ void qas_gate_table_entry(const qas_pool_entry *pool, int c, int p, int l, const double *params,
+                                                     GateTab *U, GateDTab *dU, int idx) {
   if (idx >= p * c) return;
   const int key = idx % c;
   const int g = pool[key].gate_id;
@@ -194,6 +195,11 @@ static __global__ void build_gate_table_kernel(const qas_pool_entry *pool, int c
   }
   U[QAS_NCONST + idx] = u;
   dU[QAS_NCONST + idx] = d;
+}
+
+static __global__ void build_gate_table_kernel(const qas_pool_entry *pool, int c, int p, int l,
+                                        const double *params, GateTab *U, GateDTab *dU) {
+  qas_gate_table_entry(pool, c, p, l, params, U, dU, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------ sign tables

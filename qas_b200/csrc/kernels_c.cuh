@@ -30,6 +30,12 @@ struct CompileCParams {
   int *bin_order;              // [QAS_MAX_BINS][B]
   int B, p, c, n, ops_cap, S, gmax, dmin, max_d, full_bin;
   size_t rec_stride;
+  // gate table of this call, built by `gate_blocks` extra CTAs at the end of the grid (0: a separate launch did it):
+  // the table only has to be complete before the evaluation kernels start, i.e. when this kernel ends
+  const double *params;
+  GateTab *U;
+  GateDTab *dU;
+  int l, gate_blocks;
 };
 
 // per-thread shared-memory words of the c-tape compile kernel: col[n] row[n] | packed ops [cap * 3]  (odd stride)
@@ -46,6 +52,10 @@ __host__ __device__ __forceinline__ size_t qas_ccompile_smem_words(int n, int op
 template <int CTHREADS, int NQ>
 __global__ void __launch_bounds__(CTHREADS) compile_ctapes_kernel(const CompileCParams P) {
   extern __shared__ uint32_t csm[];
+  if (blockIdx.x >= gridDim.x - P.gate_blocks) {        // spare CTAs: U and dU/dtheta of every (depth, key)
+    qas_gate_table_entry(P.pool, P.c, P.p, P.l, P.params, P.U, P.dU, (int)(blockIdx.x - (gridDim.x - P.gate_blocks)) * CTHREADS + threadIdx.x);
+    return;
+  }
   const int b = blockIdx.x * CTHREADS + threadIdx.x;
   const bool live = b < P.B;
   const int n = P.n;
@@ -376,8 +386,12 @@ __device__ __forceinline__ double c_hphase(const EvalCParams &P, const double2 *
   return e_part;
 }
 
-template <int T, bool GRAD, int BLK, int MINB>
+// AG = gates per ADJOINT pass (forward passes always follow the tape's groups).  AG = 1 un-applies the two gates of a
+// group in two passes: the adjoint pass of a two-gate group holds 4 + 4 amplitudes and two cross matrices (the kernel's
+// register peak); one gate at a time needs half of that, which buys more circuits in flight for more passes.
+template <int T, bool GRAD, int BLK, int MINB, int AG = 2>
 __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
+  static_assert(AG == 2 || T <= 32, "one-gate adjoint passes are wired for one-warp and sub-warp teams");
   constexpr int WPT = T >= 32 ? T / 32 : 1;
   constexpr int TW = T >= 32 ? 32 : T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -516,8 +530,16 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
         double *ring = WPT > 1 ? red + (size_t)(it & 1) * 2 * WPT * 8 : nullptr;
         double *mop = Ms + (size_t)j * 8;
         if (qas_meta_kind(o[4]) == QAS_K_U1) {
-          if (g == 2) c_adj_group<2, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
-          else c_adj_group<1, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
+          if (g == 2) {
+            if constexpr (AG >= 2) {
+              c_adj_group<2, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
+            } else {       // tape order: op j first (the support is still the one after the group), then op j + 1 on its own support
+              c_adj_group<1, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
+              team_sync<T>(team, tmask);
+              c_adj_group<1, T, TW, WPT>(psi, lam, o + QAS_OP_WORDS, (int)QAS_META_DJ(o[QAS_OP_WORDS + 4]), Us + 4 * (j + 1), tid, lane,
+                                         warp_in_team, tmask, ring, mop + 8);
+            }
+          } else c_adj_group<1, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
         } else {
           const double2 d0 = Us[4 * j], d1 = Us[4 * j + 3];
           const uint32_t r = o[1], sup = 1u << dj;

@@ -12,7 +12,7 @@ static cudaError_t launch_compile_c_t(qas_ctx *ctx, const CompileCParams &P, cud
   const size_t smem = qas_ccompile_smem_words(ctx->n, P.ops_cap, P.p) * 4 * CT + (size_t)P.c * sizeof(qas_pool_entry);
   cudaError_t e = cudaFuncSetAttribute(compile_ctapes_kernel<CT, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  compile_ctapes_kernel<CT, NQ><<<(P.B + CT - 1) / CT, CT, smem, st>>>(P);
+  compile_ctapes_kernel<CT, NQ><<<(P.B + CT - 1) / CT + P.gate_blocks, CT, smem, st>>>(P);
   return cudaGetLastError();
 }
 cudaError_t qas_launch_compile_c(qas_ctx *ctx, const CompileCParams &P, cudaStream_t st) {
@@ -21,12 +21,12 @@ cudaError_t qas_launch_compile_c(qas_ctx *ctx, const CompileCParams &P, cudaStre
   return launch_compile_c_t<16>(ctx, P, st);
 }
 
-template <int T, bool GRAD, int BLK, int MINB>
+template <int T, bool GRAD, int BLK, int MINB, int AG = 2>
 static cudaError_t launch_evalc_t(qas_ctx *ctx, const EvalCParams &P, int max_work, cudaStream_t st) {
   constexpr int TEAMS = BLK / T;
   const size_t smem = evalc_team_smem_bytes(P.slot_bits, T, GRAD, P.ops_cap, P.S) * TEAMS;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-  auto kern = evalc_kernel<T, GRAD, BLK, MINB>;
+  auto kern = evalc_kernel<T, GRAD, BLK, MINB, AG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -62,6 +62,14 @@ cudaError_t qas_launch_evalc(qas_ctx *ctx, const EvalCParams &P, int max_work, b
   static const int minb32 = []() { const char *e = getenv("QAS_B200_C_MINB"); const int v = e ? atoi(e) : 4; return (v == 5 || v == 6 || v == 8) ? v : 4; }();
 #define QAS_CCASE(T_, BLK_, MINB_) \
   return grad ? launch_evalc_t<T_, true, BLK_, MINB_>(ctx, P, max_work, st) : launch_evalc_t<T_, false, BLK_, MINB_>(ctx, P, max_work, st);
+  // QAS_B200_C_AG1 (tuning knob, bit mask, default 3): one-gate adjoint passes, registers bounded for more CTAs per SM, for the
+  // gradient launches of bit 0: the 2^6-amplitude slot (16-lane teams; QAS_B200_C_AG1_MINB = 5 | 6 CTAs per SM),
+  // bit 1: the one-warp teams (5 CTAs per SM).  The 2^7 slot is bound by shared memory at 4 CTAs either way.
+  static const int ag1 = []() { const char *e = getenv("QAS_B200_C_AG1"); return e ? atoi(e) : 3; }();
+  static const int ag1_minb = []() { const char *e = getenv("QAS_B200_C_AG1_MINB"); return e && atoi(e) == 6 ? 6 : 5; }();
+  if ((ag1 & 1) && grad && T == 16 && P.slot_bits <= 6)
+    return ag1_minb == 6 ? launch_evalc_t<16, true, 128, 6, 1>(ctx, P, max_work, st) : launch_evalc_t<16, true, 128, 5, 1>(ctx, P, max_work, st);
+  if ((ag1 & 2) && grad && T == 32 && minb32 == 4) return launch_evalc_t<32, true, 128, 5, 1>(ctx, P, max_work, st);
   if (T == 8) { QAS_CCASE(8, 128, 4) }
   if (T == 16) { QAS_CCASE(16, 128, 4) }
   if (T == 32 && minb32 == 5) { QAS_CCASE(32, 128, 5) }
