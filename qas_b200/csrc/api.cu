@@ -287,6 +287,7 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
     cx->compress = (!ce || atoi(ce) != 0) && init_kind == QAS_INIT_ZERO && n_qubits >= cmin && n_qubits <= 16;
     if (const char *de = getenv("QAS_B200_COMPRESS_DMIN")) cx->c_dmin = std::max(1, std::min(QAS_CT_MAX_D, atoi(de)));
     if (const char *ge = getenv("QAS_B200_GATE_IN_COMPILE")) cx->gate_in_compile = atoi(ge) != 0;
+    if (const char *se = getenv("QAS_B200_SPARSE_REDUCE")) cx->sparse_reduce = atoi(se) != 0;
     cx->c_maxd = std::min(QAS_CT_MAX_D, n_qubits - 1);
     cx->c_dmin = std::min(cx->c_dmin, cx->c_maxd);
     cx->c_nbins = cx->c_maxd - cx->c_dmin + 1;
@@ -333,6 +334,14 @@ extern "C" int qas_ctx_create(qas_ctx **out, int device, int n_qubits, int init_
   guard(cudaMalloc(&d_sbegin, 4 * sbegin.size()), "cudaMalloc sbegin");
   if (rc == QAS_OK) {
     guard(cudaMemcpy(cx->d_pool, pool, sizeof(qas_pool_entry) * c, cudaMemcpyHostToDevice), "copy pool");
+    std::vector<uint8_t> npk((size_t)c);
+    for (int i = 0; i < c; ++i) {
+      const int g = pool[i].gate_id;
+      npk[(size_t)i] = (uint8_t)std::min(qas_gate_nparams(g), l);
+      if (g == QAS_G_CRX || g == QAS_G_CRY || g == QAS_G_CRZ || g == QAS_G_CROT || g == QAS_G_CPHASE) cx->pool_ctrl_param = true;
+    }
+    guard(cudaMalloc(&cx->d_npar_key, (size_t)c), "cudaMalloc npar");
+    guard(cudaMemcpy(cx->d_npar_key, npk.data(), (size_t)c, cudaMemcpyHostToDevice), "copy npar");
     guard(cudaMemcpy(d_sx, sx.data(), 4 * sx.size(), cudaMemcpyHostToDevice), "copy sx");
     guard(cudaMemcpy(cx->d_sdesc, cdesc_swz.data(), 4 * cdesc_swz.size(), cudaMemcpyHostToDevice), "copy cdesc");
     guard(cudaMemcpy(cx->d_cdesc_plain, cdesc_plain.data(), 4 * cdesc_plain.size(), cudaMemcpyHostToDevice), "copy cdesc");
@@ -430,7 +439,7 @@ extern "C" int qas_ctx_destroy(qas_ctx *ctx) {
     if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
     if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
   }
-  cudaFree(ctx->d_pool); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_cdesc_plain); cudaFree(ctx->d_cdesc_u);
+  cudaFree(ctx->d_pool); cudaFree(ctx->d_npar_key); cudaFree(ctx->d_vtab); cudaFree(ctx->d_sdesc); cudaFree(ctx->d_cdesc_plain); cudaFree(ctx->d_cdesc_u);
   cudaFree(ctx->d_U); cudaFree(ctx->d_dU); cudaFree(ctx->d_k); cudaFree(ctx->d_params);
   cudaFree(ctx->d_energy); cudaFree(ctx->d_grad); cudaFree(ctx->d_partial); cudaFree(ctx->d_dense);
   if (ctx->h_k8) cudaFreeHost(ctx->h_k8);
@@ -730,7 +739,13 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   // (Tried: zero-fill + gate table on a forked stream next to the tape compiler.  Slower -- 0.780 -> 0.798 ms per LiH
   // step: the 31 MB zero-fill then lands between the compiler and the evaluation kernels and pushes the tape
   // records out of L2.)
-  if (want_grad) { CK(cudaMemsetAsync(dgrad, 0, ng * 8, st)); ctx->stats.launches += 1; }
+  // Only the dense batch mean is wanted (the compact gradients never leave the device): no zero-fill.  The reduction
+  // then reads exactly the entries the kernels write -- slot j of depth i iff j < #parameters of the gate k[b][i] -- and
+  // skips circuits whose energy is NaN (bad structure list / tape overflow: nothing was written; NaN parameters: the
+  // entries would be zeroed by nan_to_num anyway).  Not with pools whose controlled rotations the c-tape translation
+  // may drop, and not for host-compiled handfuls of circuits.
+  const bool sparse_reduce = want_grad && grad_dense && !grad_compact && B > 16 && !(use_c && ctx->pool_ctrl_param) && ctx->sparse_reduce;
+  if (want_grad && !sparse_reduce) { CK(cudaMemsetAsync(dgrad, 0, ng * 8, st)); ctx->stats.launches += 1; }
   if (!small) CK(cudaMemsetAsync(ctx->d_bins, 0, sizeof(int) * 2 * QAS_MAX_BINS, st));   // bin counts + work-queue heads
   stamp(1);
   // gate table first (it only needs the parameters), then the structure lists: the upload has had the memsets and
@@ -933,11 +948,12 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     while (ngroups_r > 1 && (sm1 * ngroups_r > 96 * 1024 || gthreads * ngroups_r > 512 || (B + chunk * ngroups_r - 1) / (chunk * ngroups_r) < ctx->num_sms))
       ngroups_r >>= 1;
     const int nchunks = (B + chunk * ngroups_r - 1) / (chunk * ngroups_r);
-    const size_t sm = sm1 * ngroups_r;
+    const size_t sm = sm1 * ngroups_r + (((size_t)c + 15) & ~(size_t)15);
     CK(ensure(&ctx->d_partial, &ctx->cap_partial, (size_t)nchunks * npar));
     CK(cudaFuncSetAttribute(grad_chunk_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid(nchunks, (p + depth_tile - 1) / depth_tile);
-    grad_chunk_reduce_kernel<<<grid, gthreads * ngroups_r, sm, st>>>(dk, dgrad, B, p, c, l, chunk, depth_tile, ngroups_r, ctx->d_partial);
+    grad_chunk_reduce_kernel<<<grid, gthreads * ngroups_r, sm, st>>>(dk, dgrad, B, p, c, l, chunk, depth_tile, ngroups_r, ctx->d_partial,
+                                                                     sparse_reduce ? denergy : nullptr, sparse_reduce ? ctx->d_npar_key : nullptr);
     CK(cudaGetLastError());
     stamp(6);
     const double scale = (flags & QAS_F_GRAD_SUM) ? 1.0 : 1.0 / (double)B;
@@ -1179,12 +1195,12 @@ extern "C" int qas_batch_mean(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   const int chunk = 64, nchunks = (B + chunk - 1) / chunk;
   int depth_tile = p;
   while ((size_t)depth_tile * c * l * 8 > 96 * 1024 && depth_tile > 1) depth_tile = (depth_tile + 1) / 2;
-  const size_t sm = (size_t)depth_tile * c * l * 8;
+  const size_t sm = (size_t)depth_tile * c * l * 8 + (((size_t)c + 15) & ~(size_t)15);
   CK(ensure(&ctx->d_partial, &ctx->cap_partial, (size_t)nchunks * npar));
   CK(cudaFuncSetAttribute(grad_chunk_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   dim3 grid(nchunks, (p + depth_tile - 1) / depth_tile);
   const int cthreads = std::min(256, std::max(64, ((std::min(depth_tile, p) * l + 31) / 32) * 32));
-  grad_chunk_reduce_kernel<<<grid, cthreads, sm, st>>>(k, grad_compact, B, p, c, l, chunk, depth_tile, 1, ctx->d_partial);
+  grad_chunk_reduce_kernel<<<grid, cthreads, sm, st>>>(k, grad_compact, B, p, c, l, chunk, depth_tile, 1, ctx->d_partial, nullptr, nullptr);
   CK(cudaGetLastError());
   const double scale = (flags & QAS_F_GRAD_SUM) ? 1.0 : 1.0 / (double)B;
   grad_final_reduce_kernel<<<(unsigned)((npar * 32 + 255) / 256), 256, 0, st>>>(ctx->d_partial, nchunks, npar, npar, scale, grad_dense);

@@ -24,6 +24,8 @@ struct qas_ctx {
   bool ek_pending = false;
   // device buffers owned by the context
   qas_pool_entry *d_pool = nullptr;
+  uint8_t *d_npar_key = nullptr;   // [c] parameters per pool key (sparse batch reduction)
+  bool pool_ctrl_param = false;    // the pool has controlled parametrised gates (the c-tape translation may drop such ops)
   double *d_vtab = nullptr;
   uint32_t *d_sdesc = nullptr;
   int team_shift = 0;              // QAS_B200_TEAM_SHIFT: threads per team = default << shift (tuning)
@@ -49,6 +51,7 @@ struct qas_ctx {
   int *d_counter = nullptr;        // work-queue head of the classic team kernels (= d_bins + QAS_MAX_BINS + full bin)
   // support-compressed path (kernels_c.cuh): circuits binned by the dimension d of their support span
   bool compress = false;           // all-zero start, n >= 7, QAS_B200_COMPRESS != 0
+  bool sparse_reduce = true;       // batch reduction without a zero-filled [B][p][l] (QAS_B200_SPARSE_REDUCE=0: memset + dense read)
   bool gate_in_compile = true;     // gate table built by spare CTAs of the c-tape compile kernel (QAS_B200_GATE_IN_COMPILE=0: own launch)
   int c_dmin = 6, c_maxd = QAS_CT_MAX_D;   // smallest / largest compressed slot (log2 amplitudes)
   int c_nbins = 0;                 // compressed bins: slot c_dmin + i, i < c_nbins; the full bin is index c_nbins

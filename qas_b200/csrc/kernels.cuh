@@ -1109,14 +1109,21 @@ __device__ __forceinline__ double nan_to_num_d(double x) {
   return x;
 }
 
+// Sparse mode (energy and npar_key given): grad was NOT zero-filled; entry (b, i, j) is read iff the kernels wrote it, i.e.
+// j < npar_key[k[b][i]] and the circuit's energy is not NaN (qas_eval_batch, "sparse_reduce").  Half of the keys of a
+// Rot + CNOT pool carry no parameters, so this also halves the gradient bytes the reduction reads.
 static __global__ void grad_chunk_reduce_kernel(const int32_t *k, const double *grad, int B, int p, int c,
-                                         int l, int chunk, int depth_tile, int ngroups, double *partial) {
-  extern __shared__ double acc_all[];             // [ngroups][depth_tile][c][l]
+                                         int l, int chunk, int depth_tile, int ngroups, double *partial,
+                                         const double *energy, const uint8_t *npar_key) {
+  extern __shared__ double acc_all[];             // [ngroups][depth_tile][c][l] | npar per key [c] u8
   const int ch = blockIdx.x, i0 = blockIdx.y * depth_tile;
   const int nd = min(depth_tile, p - i0);
   const int gthreads = blockDim.x / ngroups, grp = threadIdx.x / gthreads, gt = threadIdx.x % gthreads;
   const size_t asz = (size_t)depth_tile * c * l;
+  uint8_t *snp = reinterpret_cast<uint8_t *>(acc_all + asz * ngroups);
+  const bool sparse = energy != nullptr && npar_key != nullptr;
   for (size_t x = threadIdx.x; x < asz * ngroups; x += blockDim.x) acc_all[x] = 0.0;
+  for (int x = threadIdx.x; x < c; x += blockDim.x) snp[x] = sparse ? npar_key[x] : (uint8_t)l;
   __syncthreads();
   double *acc = acc_all + (size_t)grp * asz;
   const int b_lo = min(B, (ch * ngroups + grp) * chunk), b_hi = min(B, b_lo + chunk);
@@ -1128,19 +1135,30 @@ static __global__ void grad_chunk_reduce_kernel(const int32_t *k, const double *
     for (; b + 8 <= b_hi; b += 8) {
       int key[8];
       double gval[8];
+      double en[8];
+      // keys, energies and gradient entries are requested together (one round trip per step): an entry the kernels did
+      // not write is loaded as whatever the buffer holds and dropped below
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         key[q] = k[(size_t)(b + q) * p + i0 + di];
+        en[q] = sparse ? energy[b + q] : 0.0;
         gval[q] = grad[((size_t)(b + q) * p + i0 + di) * l + j];
       }
 #pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const bool on = key[q] >= 0 && key[q] < c && j < (int)snp[key[q]];
+        if (!on || en[q] != en[q]) key[q] = -1;
+      }
+#pragma unroll
       for (int q = 0; q < 8; ++q)
-        if (key[q] >= 0 && key[q] < c) a[key[q] * l] += nan_to_num_d(gval[q]);
+        if (key[q] >= 0) a[key[q] * l] += nan_to_num_d(gval[q]);
     }
     for (; b < b_hi; ++b) {
       const int key = k[(size_t)b * p + i0 + di];
+      if (key < 0 || key >= c || j >= (int)snp[key]) continue;
+      if (sparse) { const double en = energy[b]; if (en != en) continue; }
       const double gval = grad[((size_t)b * p + i0 + di) * l + j];
-      if (key >= 0 && key < c) a[key * l] += nan_to_num_d(gval);
+      a[key * l] += nan_to_num_d(gval);
     }
   }
   __syncthreads();

@@ -391,7 +391,6 @@ __device__ __forceinline__ double c_hphase(const EvalCParams &P, const double2 *
 // register peak); one gate at a time needs half of that, which buys more circuits in flight for more passes.
 template <int T, bool GRAD, int BLK, int MINB, int AG = 2>
 __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
-  static_assert(AG == 2 || T <= 32, "one-gate adjoint passes are wired for one-warp and sub-warp teams");
   constexpr int WPT = T >= 32 ? T / 32 : 1;
   constexpr int TW = T >= 32 ? 32 : T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -534,10 +533,12 @@ __global__ void __launch_bounds__(BLK, MINB) evalc_kernel(const EvalCParams P) {
             if constexpr (AG >= 2) {
               c_adj_group<2, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
             } else {       // tape order: op j first (the support is still the one after the group), then op j + 1 on its own support
+              // (multi-warp teams: the second pass publishes its per-warp partials in the ring slots of gate 1; both gates'
+              // partials are summed in fixed warp order after the group, as for a two-gate pass)
               c_adj_group<1, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
               team_sync<T>(team, tmask);
               c_adj_group<1, T, TW, WPT>(psi, lam, o + QAS_OP_WORDS, (int)QAS_META_DJ(o[QAS_OP_WORDS + 4]), Us + 4 * (j + 1), tid, lane,
-                                         warp_in_team, tmask, ring, mop + 8);
+                                         warp_in_team, tmask, WPT > 1 ? ring + (size_t)WPT * 8 : ring, mop + 8);
             }
           } else c_adj_group<1, T, TW, WPT>(psi, lam, o, dj, Us + 4 * j, tid, lane, warp_in_team, tmask, ring, mop);
         } else {

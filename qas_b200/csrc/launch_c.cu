@@ -64,12 +64,13 @@ cudaError_t qas_launch_evalc(qas_ctx *ctx, const EvalCParams &P, int max_work, b
   return grad ? launch_evalc_t<T_, true, BLK_, MINB_>(ctx, P, max_work, st) : launch_evalc_t<T_, false, BLK_, MINB_>(ctx, P, max_work, st);
   // QAS_B200_C_AG1 (tuning knob, bit mask, default 3): one-gate adjoint passes, registers bounded for more CTAs per SM, for the
   // gradient launches of bit 0: the 2^6-amplitude slot (16-lane teams; QAS_B200_C_AG1_MINB = 5 | 6 CTAs per SM),
-  // bit 1: the one-warp teams (5 CTAs per SM).  The 2^7 slot is bound by shared memory at 4 CTAs either way.
+  // bit 1: the one-warp teams (5 CTAs per SM), bit 2: the two-warp teams (5 CTAs per SM).  The 2^7 slot is bound by shared memory at 4 CTAs either way.
   static const int ag1 = []() { const char *e = getenv("QAS_B200_C_AG1"); return e ? atoi(e) : 3; }();
   static const int ag1_minb = []() { const char *e = getenv("QAS_B200_C_AG1_MINB"); return e && atoi(e) == 6 ? 6 : 5; }();
   if ((ag1 & 1) && grad && T == 16 && P.slot_bits <= 6)
     return ag1_minb == 6 ? launch_evalc_t<16, true, 128, 6, 1>(ctx, P, max_work, st) : launch_evalc_t<16, true, 128, 5, 1>(ctx, P, max_work, st);
   if ((ag1 & 2) && grad && T == 32 && minb32 == 4) return launch_evalc_t<32, true, 128, 5, 1>(ctx, P, max_work, st);
+  if ((ag1 & 4) && grad && T == 64) return launch_evalc_t<64, true, 128, 5, 1>(ctx, P, max_work, st);
   if (T == 8) { QAS_CCASE(8, 128, 4) }
   if (T == 16) { QAS_CCASE(16, 128, 4) }
   if (T == 32 && minb32 == 5) { QAS_CCASE(32, 128, 5) }

@@ -108,6 +108,20 @@ QAS_HD int qas_compile_circuit(const int32_t *k, int p, const qas_pool_entry *po
     const int a = pool[key].wire0, b = pool[key].wire1;
     const uint32_t ptab = (uint32_t)QAS_NCONST + (uint32_t)i * (uint32_t)c + (uint32_t)key;
     const int np = qas_gate_nparams(g);
+    if (g <= QAS_G_CNOT) {
+      // PlaceHolder, every one-qubit gate and CNOT -- the whole vocabulary of the near-neighbour-CNOT pools the search
+      // scripts use -- on ONE predicated path: the threads of a warp compile different circuits, and the three-way
+      // branch per depth step was the main divergence of the compile kernels.  Same emits / frame updates as the
+      // cases below (a one-qubit gate or a PlaceHolder leaves the frame as it is: bb == a, xor with zero).
+      const bool cx = g == QAS_G_CNOT;
+      const int bb = cx ? b : a;
+      const uint32_t ca = col[a], ra = row[a], cb = col[bb], rb = row[bb];
+      if (g != QAS_G_PLACEHOLDER && !cx)
+        qas_emit(s, ca, ra, 0u, g < QAS_G_ROT ? (uint32_t)(g - QAS_G_HADAMARD) : ptab, qas_meta(i, QAS_K_U1, np));
+      col[a] = ca ^ (cx ? cb : 0u);
+      row[bb] = rb ^ (cx ? ra : 0u);
+      continue;
+    }
     switch (g) {
       case QAS_G_PLACEHOLDER: break;
       case QAS_G_HADAMARD: case QAS_G_PAULIX: case QAS_G_PAULIY: case QAS_G_PAULIZ:

@@ -769,7 +769,13 @@ def test_uint8_structure_lists_equal_int32(cfg, B):
     ev.evaluate_device(torch.from_numpy(ks.astype(np.uint8)).to(dev), torch.from_numpy(params).to(dev), e8, None, g8)
     torch.cuda.synchronize()
     assert np.array_equal(e8.cpu().numpy(), a["energy"])
-    assert np.array_equal(g8.cpu().numpy(), a["grad_dense"])
+    if B > 16:
+        assert np.array_equal(g8.cpu().numpy(), a["grad_dense"])
+    else:
+        # a handful of host circuits is compiled on the host and evaluated in ONE launch sized for the largest support
+        # among them; the device-resident call bins them, and the small bins un-apply one gate per adjoint pass
+        # (QAS_B200_C_AG1): another summation order of the cross matrices, not another result
+        assert np.max(np.abs(g8.cpu().numpy() - a["grad_dense"])) <= 1e-13
     # a key outside the pool is still refused (utils.py:12-15)
     bad = ks.astype(np.uint8).copy()
     bad[0, 0] = c
