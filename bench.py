@@ -538,7 +538,10 @@ def run_b200(args):
     except Exception:
         pass
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "eval_kernel<%d>" % n, "kernel_ms": k_ms,
+                "traffic": traffic,
+                "kernel": ("evalc_kernel<T> per support bin (T = 16/32/64 lanes per circuit) + eval_kernel<%d> for the full bin" % n)
+                          if ev.stats().get("path") == 3 else "eval_kernel<%d>" % n,
+                "kernel_ms": k_ms,
                 "kernel_share_of_step": k_ms * args.steps / sum(step_ms),
                 "achieved_dense_adjoint_model": f_exec / (k_ms * 1e-3) / 1e12,
                 "achieved_survey_8d_formula": f_survey / (k_ms * 1e-3) / 1e12,
