@@ -1,5 +1,10 @@
 // api.cu -- host side of libqas_b200.so: context, launch logic and the extern "C" ABI declared
 // in include/qas_b200.h.  No torch types, no exceptions across the boundary.
+#include <chrono>
+#if defined(__SSE2__) || defined(_M_X64)
+#include <emmintrin.h>
+#define QAS_HAVE_SSE2 1
+#endif
 #include "ctx.h"
 #include "launch_cfg.h"
 
@@ -557,6 +562,74 @@ __global__ void widen_keys_kernel(const uint8_t *src, int32_t *dst, size_t n) {
   }
 }
 
+// The reference's asserts on k (utils.py:12-15: 0 <= k < c) for a whole batch.  Measured on the GPU boxes' hosts the
+// plain loop ran at one key per 0.53 ns -- 0.69 ms for the 1.3 M keys of a LiH step, LONGER than the GPU needs for the
+// step, so it, not the device, bounded the end-to-end rate (QAS_B200_HOST_TIMES=1 prints the call's host timeline).
+// 16 keys per instruction: the byte maximum (pmaxub) / or-ed signed compares, then one test.
+static bool keys_out_of_range_u8(const uint8_t *k, size_t nk, uint32_t c) {
+  size_t i = 0;
+  uint32_t mx = 0;
+#if QAS_HAVE_SSE2
+  __m128i m = _mm_setzero_si128();
+  for (; i + 64 <= nk; i += 64) {
+    const __m128i a = _mm_loadu_si128((const __m128i *)(k + i)), b = _mm_loadu_si128((const __m128i *)(k + i + 16));
+    const __m128i e = _mm_loadu_si128((const __m128i *)(k + i + 32)), f = _mm_loadu_si128((const __m128i *)(k + i + 48));
+    m = _mm_max_epu8(m, _mm_max_epu8(_mm_max_epu8(a, b), _mm_max_epu8(e, f)));
+  }
+  uint8_t t[16];
+  _mm_storeu_si128((__m128i *)t, m);
+  for (int j = 0; j < 16; ++j) mx = t[j] > mx ? t[j] : mx;
+#endif
+  for (; i < nk; ++i) mx = k[i] > mx ? k[i] : mx;
+  return mx >= c;
+}
+static bool keys_out_of_range_i32(const int32_t *k, size_t nk, uint32_t c) {
+  size_t i = 0;
+  uint32_t bad = 0;
+#if QAS_HAVE_SSE2
+  if (c <= 0x7fffffffu) {
+    __m128i acc = _mm_setzero_si128();
+    const __m128i lim = _mm_set1_epi32((int)c - 1), zero = _mm_setzero_si128();
+    for (; i + 8 <= nk; i += 8) {
+      const __m128i a = _mm_loadu_si128((const __m128i *)(k + i)), b = _mm_loadu_si128((const __m128i *)(k + i + 4));
+      acc = _mm_or_si128(acc, _mm_or_si128(_mm_or_si128(_mm_cmpgt_epi32(a, lim), _mm_cmpgt_epi32(b, lim)),
+                                           _mm_or_si128(_mm_cmplt_epi32(a, zero), _mm_cmplt_epi32(b, zero))));
+    }
+    bad = _mm_movemask_epi8(acc) ? 1u : 0u;
+  }
+#endif
+  for (; i < nk; ++i) bad |= (uint32_t)((uint32_t)k[i] >= c);
+  return bad != 0;
+}
+
+// int32 keys -> one byte per key (page-locked staging of pageable structure lists), range asserts in the same pass
+static bool narrow_keys_i32_to_u8(const int32_t *k, uint8_t *h8, size_t nk, uint32_t c) {
+  size_t i = 0;
+  uint32_t bad = 0;
+#if QAS_HAVE_SSE2
+  if (c <= 256u) {
+    __m128i acc = _mm_setzero_si128();
+    const __m128i lim = _mm_set1_epi32((int)c - 1), zero = _mm_setzero_si128();
+    for (; i + 16 <= nk; i += 16) {
+      const __m128i a = _mm_loadu_si128((const __m128i *)(k + i)), b = _mm_loadu_si128((const __m128i *)(k + i + 4));
+      const __m128i e = _mm_loadu_si128((const __m128i *)(k + i + 8)), f = _mm_loadu_si128((const __m128i *)(k + i + 12));
+      acc = _mm_or_si128(acc, _mm_or_si128(_mm_or_si128(_mm_cmpgt_epi32(a, lim), _mm_cmpgt_epi32(b, lim)),
+                                           _mm_or_si128(_mm_cmpgt_epi32(e, lim), _mm_cmpgt_epi32(f, lim))));
+      acc = _mm_or_si128(acc, _mm_or_si128(_mm_or_si128(_mm_cmplt_epi32(a, zero), _mm_cmplt_epi32(b, zero)),
+                                           _mm_or_si128(_mm_cmplt_epi32(e, zero), _mm_cmplt_epi32(f, zero))));
+      _mm_storeu_si128((__m128i *)(h8 + i), _mm_packus_epi16(_mm_packs_epi32(a, b), _mm_packs_epi32(e, f)));
+    }
+    bad = _mm_movemask_epi8(acc) ? 1u : 0u;
+  }
+#endif
+  for (; i < nk; ++i) {
+    const uint32_t v = (uint32_t)k[i];
+    bad |= (uint32_t)(v >= c);
+    h8[i] = (uint8_t)v;
+  }
+  return bad != 0;
+}
+
 extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, const double *params,
                               double *energy, double *grad_compact, double *grad_dense,
                               uint32_t flags, void *stream) {
@@ -568,6 +641,9 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   const bool want_grad = grad_compact || grad_dense;
   const int c = ctx->c, l = ctx->l;
   if (k8 && c > 256) return fail(ctx, QAS_ERR_INVALID, "QAS_F_K_U8 needs a pool of at most 256 entries");
+  static const bool host_times = []() { const char *e = getenv("QAS_B200_HOST_TIMES"); return e && atoi(e) != 0; }();
+  const auto ht0 = std::chrono::steady_clock::now();
+  auto hus = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::micro>(t - ht0).count(); };
   CK(cudaSetDevice(ctx->device));
   // device-pointer calls run on exactly the stream given (NULL = the CUDA default stream, which is
   // what torch.cuda.current_stream() is unless the caller changed it); host-pointer calls default to
@@ -618,14 +694,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
       }
       // the previous call's upload from this buffer has completed: every host-pointer call ends with a stream sync
       uint8_t *h8 = ctx->h_k8;
-      const uint32_t cu = (uint32_t)c;
-      uint32_t bad = 0;
-      for (size_t i = 0; i < nk; ++i) {
-        const uint32_t v = (uint32_t)k[i];
-        bad |= (uint32_t)(v >= cu);
-        h8[i] = (uint8_t)v;
-      }
-      if (bad) return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
+      if (narrow_keys_i32_to_u8(k, h8, nk, (uint32_t)c)) return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
       k_bytes = h8;
       k8 = true;
       k_checked = true;
@@ -977,22 +1046,27 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
 
   if (!dev) {
     if (!tiny) CK(cudaEventRecord(ctx->ev1, st));
+    const auto ht1 = std::chrono::steady_clock::now();
     if (B > 16 && !k_checked) {      // deferred range check of the structure lists; branch-free so that it vectorises
-      uint32_t bad = 0;
-      const uint32_t cu = (uint32_t)c;
-      if (k8) for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k_bytes[i] >= cu);
-      else for (size_t i = 0; i < nk; ++i) bad |= (uint32_t)((uint32_t)k[i] >= cu);
+      const bool bad = k8 ? keys_out_of_range_u8(k_bytes, nk, (uint32_t)c) : keys_out_of_range_i32(k, nk, (uint32_t)c);
       if (bad) {
         cudaStreamSynchronize(st);
         if (energy_early) cudaStreamSynchronize(ctx->copy_stream);      // nothing may land in caller memory after the return
         return fail(ctx, QAS_ERR_INVALID, "structure list entry out of range: need 0 <= k < c");
       }
     }
+    const auto ht2 = std::chrono::steady_clock::now();
     if (energy_early) CK(cudaStreamWaitEvent(st, ctx->copy_done, 0));
     else CK(cudaMemcpyAsync(energy, denergy, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     if (grad_compact) CK(cudaMemcpyAsync(grad_compact, dgrad, ng * 8, cudaMemcpyDeviceToHost, st));
     if (grad_dense) CK(cudaMemcpyAsync(grad_dense, ddense, npar * 8, cudaMemcpyDeviceToHost, st));
+    const auto ht3 = std::chrono::steady_clock::now();
     CK(cudaStreamSynchronize(st));
+    if (host_times && !tiny) {      // diagnostic: where the calling thread spends a host-pointer call
+      const auto ht4 = std::chrono::steady_clock::now();
+      fprintf(stderr, "[qas host times] B=%d: enqueued at %.0f us, range check done %.0f, copies enqueued %.0f, synchronised %.0f\n",
+              B, hus(ht1), hus(ht2), hus(ht3), hus(ht4));
+    }
     float ms = 0.f;
     if (!tiny && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.last_kernel_ms = ms;
   }
