@@ -72,7 +72,12 @@ typedef struct {
                                /* copied straight from / to the caller's memory with              */
                                /* cudaMemcpyAsync (truly asynchronous only for pinned memory;     */
                                /* pageable memory works and is staged by the CUDA driver) and    */
-                               /* the call returns synchronously.                                */
+                               /* the call returns synchronously.  Two exceptions: pageable      */
+                               /* int32 structure lists of large batches are narrowed to one     */
+                               /* byte per key into a page-locked buffer of the context (range   */
+                               /* asserts in the same pass) and uploaded from there; energies    */
+                               /* going to page-locked memory are read back on a second stream   */
+                               /* while the batch reduction still runs.                          */
 #define QAS_F_GRAD_SUM 0x2u    /* grad_dense = sum over the batch instead of mean                */
                                /* (search(..., avg_gradients=False), mcts.py:347)                */
 
