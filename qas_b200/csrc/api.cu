@@ -562,6 +562,8 @@ __global__ void widen_keys_kernel(const uint8_t *src, int32_t *dst, size_t n) {
   }
 }
 
+static QasLaunchCache g_chunk_reduce_cache;      // grad_chunk_reduce_kernel is launched from qas_eval_batch and qas_batch_mean
+
 // The reference's asserts on k (utils.py:12-15: 0 <= k < c) for a whole batch.  Measured on the GPU boxes' hosts the
 // plain loop ran at one key per 0.53 ns -- 0.69 ms for the 1.3 M keys of a LiH step, LONGER than the GPU needs for the
 // step, so it, not the device, bounded the end-to-end rate (QAS_B200_HOST_TIMES=1 prints the call's host timeline).
@@ -1019,7 +1021,7 @@ extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, cons
     const int nchunks = (B + chunk * ngroups_r - 1) / (chunk * ngroups_r);
     const size_t sm = sm1 * ngroups_r + (((size_t)c + 15) & ~(size_t)15);
     CK(ensure(&ctx->d_partial, &ctx->cap_partial, (size_t)nchunks * npar));
-    CK(cudaFuncSetAttribute(grad_chunk_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    CK(qas_prepare_launch(g_chunk_reduce_cache, ctx->device, grad_chunk_reduce_kernel, 0, sm, nullptr));
     dim3 grid(nchunks, (p + depth_tile - 1) / depth_tile);
     grad_chunk_reduce_kernel<<<grid, gthreads * ngroups_r, sm, st>>>(dk, dgrad, B, p, c, l, chunk, depth_tile, ngroups_r, ctx->d_partial,
                                                                      sparse_reduce ? denergy : nullptr, sparse_reduce ? ctx->d_npar_key : nullptr);
@@ -1271,7 +1273,7 @@ extern "C" int qas_batch_mean(qas_ctx *ctx, int B, int p, const int32_t *k, cons
   while ((size_t)depth_tile * c * l * 8 > 96 * 1024 && depth_tile > 1) depth_tile = (depth_tile + 1) / 2;
   const size_t sm = (size_t)depth_tile * c * l * 8 + (((size_t)c + 15) & ~(size_t)15);
   CK(ensure(&ctx->d_partial, &ctx->cap_partial, (size_t)nchunks * npar));
-  CK(cudaFuncSetAttribute(grad_chunk_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  CK(qas_prepare_launch(g_chunk_reduce_cache, ctx->device, grad_chunk_reduce_kernel, 0, sm, nullptr));
   dim3 grid(nchunks, (p + depth_tile - 1) / depth_tile);
   const int cthreads = std::min(256, std::max(64, ((std::min(depth_tile, p) * l + 31) / 32) * 32));
   grad_chunk_reduce_kernel<<<grid, cthreads, sm, st>>>(k, grad_compact, B, p, c, l, chunk, depth_tile, 1, ctx->d_partial, nullptr, nullptr);

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -117,6 +118,41 @@ static inline cudaError_t ensure(Tp **ptr, size_t *cap, size_t need_elems) {
   return e;
 }
 
+
+// Launch attributes of ONE kernel instantiation (a function-local static per call site): the dynamic shared-memory cap is
+// only ever raised, and the occupancy of the last (block, shared memory) pair is remembered, so that a call's ~10 launches
+// do not cost ~15 extra driver calls (cudaFuncSetAttribute + cudaOccupancyMaxActiveBlocksPerMultiprocessor, a few
+// microseconds each: most of the host time of a search-sized batch).  Process-wide, hence the mutex.
+#define QAS_MAX_DEVICES 16
+struct QasLaunchCache {
+  std::mutex mu;
+  size_t max_smem[QAS_MAX_DEVICES] = {0};
+  size_t occ_smem[QAS_MAX_DEVICES] = {0};
+  int occ_block[QAS_MAX_DEVICES] = {0}, occ[QAS_MAX_DEVICES] = {0};
+};
+template <class K>
+static inline cudaError_t qas_prepare_launch(QasLaunchCache &c, int device, K kern, int block, size_t smem, int *occ) {
+  const int d = (device >= 0 && device < QAS_MAX_DEVICES) ? device : 0;
+  const bool cacheable = device >= 0 && device < QAS_MAX_DEVICES;
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (!cacheable || smem > c.max_smem[d] || c.max_smem[d] == 0) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, cacheable ? c.max_smem[d] : smem));
+    if (e != cudaSuccess) return e;
+    if (cacheable) c.max_smem[d] = std::max(std::max(smem, c.max_smem[d]), (size_t)1);
+  }
+  if (occ) {
+    if (!cacheable || c.occ_block[d] != block || c.occ_smem[d] != smem || c.occ[d] == 0) {
+      int o = 0;
+      const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, block, smem);
+      if (e != cudaSuccess) return e;
+      if (cacheable) { c.occ_block[d] = block; c.occ_smem[d] = smem; c.occ[d] = o; }
+      *occ = o;
+    } else {
+      *occ = c.occ[d];
+    }
+  }
+  return cudaSuccess;
+}
 
 // launch_classic_grad.cu / launch_classic_nograd.cu: the classic evaluation kernels (kernels.cuh)
 cudaError_t qas_launch_eval_grad(qas_ctx *ctx, EvalParams &P, cudaStream_t st);

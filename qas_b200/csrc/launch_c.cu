@@ -10,7 +10,8 @@ template <int NQ>
 static cudaError_t launch_compile_c_t(qas_ctx *ctx, const CompileCParams &P, cudaStream_t st) {
   constexpr int CT = 64;
   const size_t smem = qas_ccompile_smem_words(ctx->n, P.ops_cap, P.p) * 4 * CT + (size_t)P.c * sizeof(qas_pool_entry);
-  cudaError_t e = cudaFuncSetAttribute(compile_ctapes_kernel<CT, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static QasLaunchCache cache;
+  cudaError_t e = qas_prepare_launch(cache, ctx->device, compile_ctapes_kernel<CT, NQ>, CT, smem, nullptr);
   if (e != cudaSuccess) return e;
   compile_ctapes_kernel<CT, NQ><<<(P.B + CT - 1) / CT + P.gate_blocks, CT, smem, st>>>(P);
   return cudaGetLastError();
@@ -27,10 +28,10 @@ static cudaError_t launch_evalc_t(qas_ctx *ctx, const EvalCParams &P, int max_wo
   const size_t smem = evalc_team_smem_bytes(P.slot_bits, T, GRAD, P.ops_cap, P.S) * TEAMS;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   auto kern = evalc_kernel<T, GRAD, BLK, MINB, AG>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static QasLaunchCache cache;
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLK, smem);
+  cudaError_t e = qas_prepare_launch(cache, ctx->device, kern, BLK, smem, &occ);
+  if (e != cudaSuccess) return e;
   const int grid = std::min((max_work + TEAMS - 1) / TEAMS, std::max(1, occ) * ctx->num_sms);   // persistent CTAs, queue-fed
   ctx->stats.teams_per_cta = TEAMS;
   ctx->stats.threads_per_team = T;

@@ -15,10 +15,10 @@ static cudaError_t launch_smem(qas_ctx *ctx, const EvalParams &P, cudaStream_t s
   constexpr int TEAMS = BLK / T;
   const size_t smem = eval_team_smem_bytes(N, T, GRAD, P.ops_cap, true, qas_stage_u(N)) * TEAMS + sdesc_bytes(P.C_real + P.C_imag);
   auto kern = eval_kernel<N, T, GRAD, (GMAX_ ? GMAX_ : qas_gmax(N, T)), RBH, PD, (MINB_ ? MINB_ : qas_minb(N, T, BLK)), BLK>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static QasLaunchCache cache;
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLK, smem);
+  cudaError_t e = qas_prepare_launch(cache, ctx->device, kern, BLK, smem, &occ);
+  if (e != cudaSuccess) return e;
   const int grid = std::min((P.B + TEAMS - 1) / TEAMS, std::max(1, occ) * ctx->num_sms);   // persistent CTAs, queue-fed
   ctx->stats.teams_per_cta = TEAMS;
   ctx->stats.threads_per_team = T;
@@ -33,10 +33,10 @@ template <bool GRAD>
 [[maybe_unused]] static cudaError_t launch_gmem(qas_ctx *ctx, EvalParams &P, cudaStream_t st) {
   const size_t smem = eval_team_smem_bytes(P.n, 256, GRAD, P.ops_cap, false, true) + sdesc_bytes(P.C_real + P.C_imag);
   auto kern = eval_kernel<0, 256, GRAD, 2, 2, 2, 2>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static QasLaunchCache cache;
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
+  cudaError_t e = qas_prepare_launch(cache, ctx->device, kern, 256, smem, &occ);
+  if (e != cudaSuccess) return e;
   occ = std::max(1, std::min(occ, 4));
   const size_t per_cta = ((size_t)1 << P.n) * (GRAD ? 2 : 1);
   int grid = std::min(P.B, ctx->num_sms * occ);
@@ -58,10 +58,10 @@ static cudaError_t launch_small(qas_ctx *ctx, const EvalParams &P, cudaStream_t 
   constexpr int BLK = N <= 4 ? 128 : 64;
   const size_t smem = eval_small_smem_bytes(N, BLK, GRAD, P.ops_cap, P.c);
   auto kern = eval_small_kernel<N, GRAD, BLK>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static QasLaunchCache cache;
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLK, smem);
+  cudaError_t e = qas_prepare_launch(cache, ctx->device, kern, BLK, smem, &occ);
+  if (e != cudaSuccess) return e;
   ctx->stats.teams_per_cta = BLK;
   ctx->stats.threads_per_team = 1;
   ctx->stats.ctas_per_sm = occ;

@@ -13,11 +13,13 @@ int qas_launch_compile_classic(qas_ctx *ctx, const int32_t *dk, int B, int p, in
   const size_t csm = qas_compile_smem_words(ctx->n, ops_cap, p, ops_smem) * 4 * cthr;
   if (csm > 200 * 1024) return fail(ctx, QAS_ERR_UNSUPPORTED, "structure lists too long for the tape-compile kernel");
   if (ops_smem) {
-    CK(cudaFuncSetAttribute(compile_tapes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+    static QasLaunchCache cache;
+    CK(qas_prepare_launch(cache, ctx->device, compile_tapes_kernel<true>, cthr, csm, nullptr));
     compile_tapes_kernel<true><<<(B + cthr - 1) / cthr, cthr, csm, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, ops_cap, ctx->init_kind,
                                                                        ctx->init_basis, ctx->GMAX, swz_plan, ctx->hinfo, ctx->d_tape, rec_words);
   } else {
-    CK(cudaFuncSetAttribute(compile_tapes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+    static QasLaunchCache cache;
+    CK(qas_prepare_launch(cache, ctx->device, compile_tapes_kernel<false>, cthr, csm, nullptr));
     compile_tapes_kernel<false><<<(B + cthr - 1) / cthr, cthr, csm, st>>>(dk, ctx->d_pool, B, p, c, ctx->n, ops_cap, ctx->init_kind,
                                                                         ctx->init_basis, ctx->GMAX, swz_plan, ctx->hinfo, ctx->d_tape, rec_words);
   }
@@ -29,7 +31,8 @@ cudaError_t qas_launch_plan_full(qas_ctx *ctx, uint32_t *tape, size_t rec_stride
                                  int ops_cap, int swizzled, cudaStream_t st) {
   const int thr = 32;
   const size_t smem = (size_t)thr * ((ops_cap * QAS_OP_WORDS) | 1) * 4;
-  cudaError_t e = cudaFuncSetAttribute(plan_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static QasLaunchCache cache;
+  cudaError_t e = qas_prepare_launch(cache, ctx->device, plan_full_kernel, thr, smem, nullptr);
   if (e != cudaSuccess) return e;
   plan_full_kernel<<<(B + thr - 1) / thr, thr, smem, st>>>(tape, rec_stride, count, order, ctx->n, ops_cap, ctx->init_kind, swizzled, ctx->hinfo);
   return cudaGetLastError();
