@@ -181,6 +181,12 @@ int qas_plan_passes_host(int n_qubits, uint32_t *ops, int num_ops, int gmax, int
 int qas_plan_tile_pass_host(int n_qubits, const uint32_t *ops, int num_ops_total, int start, int dir, int tb,
                             int clow, int max_ops, uint32_t *col, int *piv, int *num_ops);
 
+/* Host-side range asserts on structure lists (the reference's `min(k) >= 0, max(k) < c`, utils.py:12-15), exactly the
+ * vectorised passes qas_eval_batch runs on large host batches: key_bytes = 1 (uint8) or 4 (int32).  *out_of_range = 1
+ * if some key is < 0 or >= c.  With narrowed != NULL (int32 keys, c <= 256) the keys are also written there as one byte
+ * each (the page-locked staging of pageable lists).  No GPU involved.                                                  */
+int qas_check_keys_host(const void *k, uint64_t num_keys, int key_bytes, int c, uint8_t *narrowed, int *out_of_range);
+
 /* Coset basis of one pass group inside a tile of the tiled kernel (qas_b200/csrc/tape.h qas_tile_group_basis): g <= 2
  * gates with tile-coordinate xor masks m[g] and parity masks r[g] (tb bits); kb (>= tb words) receives a basis of the
  * common kernel of the parity masks in lowest-set-bit echelon form, ascending pivots; returns its dimension tb - g in

@@ -73,7 +73,7 @@ _lib = None
 EXPORTS = [
     "qas_abi_version", "qas_build_info", "qas_ctx_create", "qas_ctx_destroy", "qas_last_error",
     "qas_eval_batch", "qas_compile_tape", "qas_compile_tape_host", "qas_plan_passes_host",
-    "qas_plan_hsupport_host", "qas_plan_tile_pass_host", "qas_tile_group_basis_host", "qas_compile_ctape_host",
+    "qas_plan_hsupport_host", "qas_plan_tile_pass_host", "qas_tile_group_basis_host", "qas_compile_ctape_host", "qas_check_keys_host",
     "qas_get_stats", "qas_debug_phase_clocks", "qas_debug_phase_clocks_c", "qas_debug_phase_clocks_t", "qas_ctx_param_slots", "qas_adam_step", "qas_set_params",
     "qas_fp64_peak_tflops", "qas_reduce_rows", "qas_peer_push_row", "qas_peer_wait_reduce", "qas_batch_mean", "qas_vqls_combine", "qas_tuning_tick", "qas_adam_step_dev",
 ]
@@ -119,6 +119,8 @@ def load():
     lib.qas_plan_tile_pass_host.restype = ctypes.c_int
     lib.qas_plan_tile_pass_host.argtypes = [ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_int, vp, vp, ctypes.POINTER(ctypes.c_int)]
+    lib.qas_check_keys_host.restype = ctypes.c_int
+    lib.qas_check_keys_host.argtypes = [vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_int)]
     lib.qas_tile_group_basis_host.restype = ctypes.c_int
     lib.qas_tile_group_basis_host.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_int)]
     lib.qas_plan_hsupport_host.restype = ctypes.c_int

@@ -632,6 +632,16 @@ static bool narrow_keys_i32_to_u8(const int32_t *k, uint8_t *h8, size_t nk, uint
   return bad != 0;
 }
 
+extern "C" int qas_check_keys_host(const void *k, uint64_t num_keys, int key_bytes, int c, uint8_t *narrowed, int *out_of_range) {
+  if (!k || !out_of_range || c <= 0 || (key_bytes != 1 && key_bytes != 4) || (narrowed && (key_bytes != 4 || c > 256))) return QAS_ERR_INVALID;
+  bool bad;
+  if (key_bytes == 1) bad = keys_out_of_range_u8(static_cast<const uint8_t *>(k), (size_t)num_keys, (uint32_t)c);
+  else if (narrowed) bad = narrow_keys_i32_to_u8(static_cast<const int32_t *>(k), narrowed, (size_t)num_keys, (uint32_t)c);
+  else bad = keys_out_of_range_i32(static_cast<const int32_t *>(k), (size_t)num_keys, (uint32_t)c);
+  *out_of_range = bad ? 1 : 0;
+  return QAS_OK;
+}
+
 extern "C" int qas_eval_batch(qas_ctx *ctx, int B, int p, const int32_t *k, const double *params,
                               double *energy, double *grad_compact, double *grad_dense,
                               uint32_t flags, void *stream) {

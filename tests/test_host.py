@@ -440,3 +440,38 @@ def test_property_tape_paths_agree_with_oracle(n, p, seed, vocab):
         for (dd, j), v in gr2.items():
             got[dd, k[dd], j] = v
         assert np.max(np.abs(got - g_ref)) < 1e-9
+
+
+def test_vectorised_key_range_check_matches_the_scalar_rule():
+    """qas_check_keys_host = the passes qas_eval_batch runs on large host batches (16 keys per instruction): the
+    reference's asserts min(k) >= 0, max(k) < c (utils.py:12-15) for byte and int32 keys, and the int32 -> byte
+    narrowing of pageable lists; every length 0..130 (vector bodies and tails), bad keys at random places."""
+    import ctypes
+    from qas_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(2)
+    for trial in range(600):
+        nk = int(rng.integers(0, 131)) if trial % 3 else int(rng.integers(1000, 5000))
+        c = int(rng.integers(1, 257))
+        k = rng.integers(0, c, size=nk).astype(np.int32)
+        kind = trial % 4
+        if nk and kind == 1:
+            k[int(rng.integers(0, nk))] = c + int(rng.integers(0, 3))
+        if nk and kind == 2:
+            k[int(rng.integers(0, nk))] = -1 - int(rng.integers(0, 3))
+        want = bool(np.any((k < 0) | (k >= c)))
+        flag = ctypes.c_int(-1)
+        kk = np.ascontiguousarray(k) if nk else np.zeros(1, dtype=np.int32)
+        assert lib.qas_check_keys_host(kk.ctypes.data, nk, 4, c, None, ctypes.byref(flag)) == 0
+        assert bool(flag.value) == want
+        out = np.full(nk + 1, 0xAA, dtype=np.uint8)
+        assert lib.qas_check_keys_host(kk.ctypes.data, nk, 4, c, out.ctypes.data, ctypes.byref(flag)) == 0
+        assert bool(flag.value) == want and out[nk] == 0xAA
+        if not want:
+            assert np.array_equal(out[:nk], k.astype(np.uint8))
+        k8 = (k & 0xFF).astype(np.uint8)
+        kk8 = np.ascontiguousarray(k8) if nk else np.zeros(1, dtype=np.uint8)
+        assert lib.qas_check_keys_host(kk8.ctypes.data, nk, 1, c, None, ctypes.byref(flag)) == 0
+        assert bool(flag.value) == bool(np.any(k8 >= c))
+    assert lib.qas_check_keys_host(None, 0, 4, 4, None, ctypes.byref(flag)) != 0
+
