@@ -202,6 +202,37 @@ def test_device_pointer_entry_is_equivalent():
     assert np.array_equal(dgd.cpu().numpy(), host["grad_dense"])
 
 
+def test_dense_mean_without_zero_fill_reads_only_written_entries():
+    """Only the dense batch mean requested (the search's gradient step, mcts.py:345-347): the compact gradients are not
+    zero-filled and the reduction reads exactly the entries the kernels write.  Bit-identical to the zero-filled path;
+    a circuit with an out-of-range key (device-pointer calls are not range-checked on the host: NaN energy, nothing
+    written) contributes zeros although the scratch buffer still holds the previous call's values."""
+    import torch
+    from qas_b200.qml_models.qml_models_legacy import LiH
+    pool = helpers.near_cx_pool(10)
+    c, p, B = len(pool), 20, 96
+    params = np.random.default_rng(3).standard_normal((p, c, 3))
+    ks = sample_structure_lists(pool, p, {"CNOT": 10}, B, seed=21)
+    ref = LiH.evaluate_batch(ks, params, pool, compact=True)              # compact requested: zero-filled path
+    ev = LiH.evaluator(pool)
+    dp = torch.from_numpy(params).cuda()
+    de = torch.empty(B, dtype=torch.float64, device="cuda")
+    dgd = torch.empty(p, c, 3, dtype=torch.float64, device="cuda")
+    ev.evaluate_device(torch.from_numpy(ks).cuda(), dp, de, None, dgd)
+    torch.cuda.synchronize()
+    assert np.array_equal(de.cpu().numpy(), ref["energy"])
+    assert np.array_equal(dgd.cpu().numpy(), ref["grad_dense"])
+    bad = ks.copy()
+    bad[5, 3] = c + 2
+    ev.evaluate_device(torch.from_numpy(bad).cuda(), dp, de, None, dgd)
+    torch.cuda.synchronize()
+    e = de.cpu().numpy()
+    assert np.isnan(e[5]) and np.all(np.isfinite(np.delete(e, 5)))
+    dense = helpers.dense_from_compact(ks, ref["grad_compact"], c)
+    dense[5] = 0.0
+    assert np.max(np.abs(dgd.cpu().numpy() - dense.sum(axis=0) / B)) <= 1e-13
+
+
 # --------------------------------------------------------------------------- BASELINE-size properties
 def test_baseline_size_properties_lih():
     """LiH near_cx at the script's depth (p=20) and a saturating batch: properties that do not
