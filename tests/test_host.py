@@ -475,3 +475,17 @@ def test_vectorised_key_range_check_matches_the_scalar_rule():
         assert bool(flag.value) == bool(np.any(k8 >= c))
     assert lib.qas_check_keys_host(None, 0, 4, 4, None, ctypes.byref(flag)) != 0
 
+
+def test_planner_output_is_pinned_word_by_word():
+    """Compiled tapes, group marks, group descriptors and final-support descriptors of 48 seeded circuits equal the
+    committed fixture (tools/make_planner_golden.py): the planner was rewritten on packed pivot tables with bit-identical
+    output, and every kernel-side enumeration depends on these words."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_planner_golden", os.path.join(root, "tools", "make_planner_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = np.load(os.path.join(root, "tests", "golden", "planner_descriptors.npz"))["words"]
+    got = mod.planner_outputs()
+    assert got.shape == want.shape and np.array_equal(got, want)
+
