@@ -100,8 +100,10 @@ def group_cosets(grp, dj):
     return Ps, xm
 
 
-def run_ctape(ct, n, pool, c, params, xmasks, imag, V, want_grad=True, poison=True):
-    """-> (energy, {(depth, j): dE/dtheta}) of a compressed record, following evalc_kernel."""
+def run_ctape(ct, n, pool, c, params, xmasks, imag, V, want_grad=True, poison=True, adjoint_gates=2):
+    """-> (energy, {(depth, j): dE/dtheta}) of a compressed record, following evalc_kernel.
+    adjoint_gates = 1: the adjoint sweep un-applies the gates of a two-gate group in two one-gate passes, tape order, the
+    second on its own support d_j (evalc_kernel<..., AG = 1>); the forward sweep keeps the groups."""
     d, ops = ct["d"], ct["ops"]
     assert d >= 0
     dim = 1 << d
@@ -116,9 +118,9 @@ def run_ctape(ct, n, pool, c, params, xmasks, imag, V, want_grad=True, poison=Tr
     assert len(groups) == ct["ngroups"]
     par = np.vectorize(_parity)
 
-    def apply_group(gi, adjoint, lam=None, grads=None):
+    def apply_group(gi, adjoint, lam=None, grads=None, sub=None):
         nonlocal psi
-        j, g = groups[gi]
+        j, g = groups[gi] if sub is None else sub
         grp = [ops[j + q] for q in range(g)]
         dj = int(grp[0][4]) >> 28                  # support dimension after the group
         sup = 1 << dj
@@ -203,5 +205,10 @@ def run_ctape(ct, n, pool, c, params, xmasks, imag, V, want_grad=True, poison=Tr
     grads = {}
     if want_grad:
         for gi in range(len(groups)):
-            apply_group(gi, True, lam, grads)
+            j, g = groups[gi]
+            if adjoint_gates == 1 and g == 2 and (int(ops[j][4]) >> 16) & 0xF == 0:
+                apply_group(gi, True, lam, grads, sub=(j, 1))
+                apply_group(gi, True, lam, grads, sub=(j + 1, 1))
+            else:
+                apply_group(gi, True, lam, grads)
     return energy, grads

@@ -328,6 +328,11 @@ def _ctape_case(n, pool, p, lim, terms, seeds, k_override=None):
         for (dd, j), v in gr.items():
             got[dd, k[dd], j] = v
         assert np.max(np.abs(got - ga)) < 1e-10
+        # one-gate adjoint passes (evalc_kernel<..., AG = 1>): the gates of a two-gate group un-applied one at a time, the
+        # second inside its own (smaller or equal) support prefix -- same cross matrices
+        e1, gr1 = CT.run_ctape(ct, n, pool.pool, c, params, xs, imag, V, adjoint_gates=1)
+        assert e1 == e and gr1.keys() == gr.keys()
+        assert max([abs(gr1[key] - gr[key]) for key in gr] + [0.0]) < 1e-13
     return stats
 
 
